@@ -1,0 +1,389 @@
+"""ctypes bindings of the product libraries: the C ABI (include/vga_b200.h) and the host layer
+(include/vga_host.h).  Importing this module never touches oracle/ -- there is no CPU compute
+path; every compute call fails loudly without a CUDA device."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIBDIR = os.path.join(HERE, "lib")
+
+
+class VgaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"vga error {code}: {msg}")
+        self.code = code
+
+
+class VgaGrid(C.Structure):
+    _fields_ = [("cols", C.c_int32), ("rows", C.c_int32), ("spacing", C.c_double), ("bl_x", C.c_double),
+                ("bl_y", C.c_double), ("maxdist", C.c_double), ("state", C.c_void_p), ("line_off", C.c_void_p),
+                ("lines", C.c_void_p)]
+
+
+class VgaTiming(C.Structure):
+    _fields_ = [("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double),
+                ("main_kernel_ms", C.c_double), ("launches", C.c_int64), ("main_launches", C.c_int64),
+                ("algo_bytes", C.c_double)]
+
+
+ABI_SYMBOLS = [
+    "vga_last_error", "vga_version", "vga_device_count", "vga_ctx_create", "vga_ctx_destroy", "vga_ctx_set_callbacks",
+    "vga_ctx_set_option", "vga_ctx_timing", "vga_ctx_sync", "vga_graph_build", "vga_grid_upload", "vga_dgrid_free",
+    "vga_graph_build_resident", "vga_graph_from_csr", "vga_graph_free", "vga_graph_num_cells", "vga_graph_num_ghosts",
+    "vga_graph_num_edges", "vga_graph_src_begin", "vga_graph_src_end", "vga_graph_csr", "vga_graph_cell_refs",
+    "vga_graph_node_stats", "vga_global", "vga_global_attributes", "vga_local", "vga_local_attributes",
+    "vga_graph_device_rows", "vga_graph_from_device_rows",
+]
+HOST_SYMBOLS = [
+    "dmxh_last_error", "dmxh_map_create", "dmxh_map_destroy", "dmxh_map_grid", "dmxh_map_block_lines", "dmxh_map_fill",
+    "dmxh_map_filled_count", "dmxh_map_flat", "dmxh_map_make_graph", "dmxh_map_vga_global", "dmxh_map_vga_local",
+    "dmxh_map_columns", "dmxh_map_attr", "dmxh_map_grid_connections", "dmxh_map_graph", "dmxh_release_context",
+]
+
+_abi = None
+_host = None
+vp = C.c_void_p
+i64 = C.c_int64
+
+
+def abi():
+    global _abi
+    if _abi is None:
+        path = os.path.join(LIBDIR, "libvga_b200.so")
+        if not os.path.exists(path):
+            raise ImportError(f"{path} is missing: run `python -m depthmapx_b200.build` (there is no fallback)")
+        L = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        L.vga_last_error.restype = C.c_char_p
+        L.vga_version.restype = C.c_char_p
+        L.vga_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.vga_ctx_destroy.argtypes = [vp]
+        L.vga_ctx_set_option.argtypes = [vp, C.c_char_p, i64]
+        L.vga_ctx_timing.argtypes = [vp, C.POINTER(VgaTiming)]
+        L.vga_ctx_sync.argtypes = [vp]
+        L.vga_graph_build.argtypes = [vp, C.POINTER(VgaGrid), i64, i64, C.POINTER(vp)]
+        L.vga_grid_upload.argtypes = [vp, C.POINTER(VgaGrid), C.POINTER(vp)]
+        L.vga_dgrid_free.argtypes = [vp]
+        L.vga_graph_build_resident.argtypes = [vp, vp, i64, i64, C.POINTER(vp)]
+        L.vga_graph_from_csr.argtypes = [vp, i64, i64, vp, vp, vp, C.POINTER(vp)]
+        L.vga_graph_free.argtypes = [vp]
+        for f in ("vga_graph_num_cells", "vga_graph_num_ghosts", "vga_graph_num_edges", "vga_graph_src_begin",
+                  "vga_graph_src_end"):
+            getattr(L, f).restype = i64
+            getattr(L, f).argtypes = [vp]
+        L.vga_graph_csr.argtypes = [vp] * 5
+        L.vga_graph_cell_refs.argtypes = [vp, vp]
+        L.vga_graph_node_stats.argtypes = [vp] * 7
+        L.vga_global.argtypes = [vp, vp, C.c_int, i64, i64, vp, vp, vp, C.c_int32, C.POINTER(C.c_int32)]
+        L.vga_global_attributes.argtypes = [i64, vp, vp, vp, C.c_int32] + [vp] * 7
+        L.vga_local.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp]
+        L.vga_local_attributes.argtypes = [i64] + [vp] * 7
+        L.vga_graph_device_rows.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
+        L.vga_graph_from_device_rows.argtypes = [vp, i64, i64, vp, vp, i64, C.POINTER(vp)]
+        _abi = L
+    return _abi
+
+
+def host():
+    global _host
+    if _host is None:
+        abi()
+        path = os.path.join(LIBDIR, "libvga_host.so")
+        if not os.path.exists(path):
+            raise ImportError(f"{path} is missing: run `python -m depthmapx_b200.build`")
+        H = C.CDLL(path)
+        H.dmxh_last_error.restype = C.c_char_p
+        H.dmxh_map_create.restype = vp
+        H.dmxh_map_create.argtypes = [vp, C.c_int, C.c_double]
+        H.dmxh_map_destroy.argtypes = [vp]
+        H.dmxh_map_grid.argtypes = [vp] * 6
+        H.dmxh_map_block_lines.argtypes = [vp]
+        H.dmxh_map_fill.argtypes = [vp, C.c_double, C.c_double]
+        H.dmxh_map_filled_count.argtypes = [vp]
+        H.dmxh_map_flat.argtypes = [vp] * 6
+        H.dmxh_map_make_graph.argtypes = [vp, C.c_int, C.c_double]
+        H.dmxh_map_vga_global.argtypes = [vp, C.c_double, C.c_int]
+        H.dmxh_map_vga_local.argtypes = [vp, C.c_int]
+        H.dmxh_map_columns.argtypes = [vp, C.c_char_p, C.c_int]
+        H.dmxh_map_attr.argtypes = [vp, C.c_char_p, vp]
+        H.dmxh_map_grid_connections.argtypes = [vp, vp]
+        H.dmxh_map_graph.restype = vp
+        H.dmxh_map_graph.argtypes = [vp]
+        _host = H
+    return _host
+
+
+def check(rc):
+    if rc != 0:
+        raise VgaError(rc, abi().vga_last_error().decode())
+
+
+def _p(a):
+    return a.ctypes.data if a is not None else None
+
+
+def device_count() -> int:
+    return abi().vga_device_count()
+
+
+class FlatGrid:
+    """The vga_grid arrays (see include/vga_b200.h)."""
+
+    def __init__(self, cols, rows, spacing, bl_x, bl_y, state, line_off, lines, maxdist=-1.0):
+        self.cols, self.rows, self.spacing, self.bl_x, self.bl_y, self.maxdist = cols, rows, spacing, bl_x, bl_y, maxdist
+        self.state = np.ascontiguousarray(state, np.uint16)
+        self.line_off = np.ascontiguousarray(line_off, np.uint32)
+        self.lines = np.ascontiguousarray(lines, np.float64).reshape(-1, 5)
+
+    def c(self) -> VgaGrid:
+        return VgaGrid(self.cols, self.rows, self.spacing, self.bl_x, self.bl_y, self.maxdist, _p(self.state),
+                       _p(self.line_off), _p(self.lines) if self.lines.size else None)
+
+    @property
+    def n_filled(self) -> int:
+        return int(((self.state & 2) != 0).sum())
+
+    def input_bytes(self) -> int:
+        return self.state.nbytes + self.line_off.nbytes + self.lines.nbytes
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self.h = vp()
+        check(abi().vga_ctx_create(device, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            abi().vga_ctx_destroy(self.h)
+            self.h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key: str, value: int):
+        check(abi().vga_ctx_set_option(self.h, key.encode(), int(value)))
+
+    def timing(self) -> dict:
+        t = VgaTiming()
+        check(abi().vga_ctx_timing(self.h, C.byref(t)))
+        return {k: getattr(t, k) for k, _ in VgaTiming._fields_}
+
+    def sync(self):
+        check(abi().vga_ctx_sync(self.h))
+
+    def upload(self, grid: FlatGrid) -> "DeviceGrid":
+        return DeviceGrid(self, grid)
+
+    def build(self, grid, src=(0, -1)) -> "Graph":
+        g = vp()
+        if isinstance(grid, DeviceGrid):
+            check(abi().vga_graph_build_resident(self.h, grid.h, src[0], src[1], C.byref(g)))
+        else:
+            cg = grid.c()
+            check(abi().vga_graph_build(self.h, C.byref(cg), src[0], src[1], C.byref(g)))
+        return Graph(self, g)
+
+    def graph_from_csr(self, n_cells, n_ghosts, rowptr, col, bin=None) -> "Graph":
+        rowptr = np.ascontiguousarray(rowptr, np.uint64)
+        col = np.ascontiguousarray(col, np.uint32)
+        b = np.ascontiguousarray(bin, np.uint8) if bin is not None else None
+        g = vp()
+        check(abi().vga_graph_from_csr(self.h, n_cells, n_ghosts, _p(rowptr), _p(col), _p(b), C.byref(g)))
+        return Graph(self, g)
+
+    def graph_from_device_rows(self, n_cells, n_ghosts, d_rowptr: int, d_adj: int, n_entries: int) -> "Graph":
+        g = vp()
+        check(abi().vga_graph_from_device_rows(self.h, n_cells, n_ghosts, d_rowptr, d_adj, n_entries, C.byref(g)))
+        return Graph(self, g)
+
+
+class DeviceGrid:
+    def __init__(self, ctx: Context, grid: FlatGrid):
+        self.ctx = ctx
+        self.h = vp()
+        cg = grid.c()
+        check(abi().vga_grid_upload(ctx.h, C.byref(cg), C.byref(self.h)))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            abi().vga_dgrid_free(self.h)
+            self.h = None
+
+
+class Graph:
+    def __init__(self, ctx: Context, handle, owned=True):
+        self.ctx, self.h, self.owned = ctx, handle, owned
+        L = abi()
+        self.n = L.vga_graph_num_cells(handle)
+        self.ghosts = L.vga_graph_num_ghosts(handle)
+        self.entries = L.vga_graph_num_edges(handle)
+        self.src_begin = L.vga_graph_src_begin(handle)
+        self.src_end = L.vga_graph_src_end(handle)
+
+    def free(self):
+        if self.h and self.owned:
+            abi().vga_graph_free(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def csr(self):
+        rows = self.src_end - self.src_begin
+        rowptr = np.zeros(rows + 1, np.uint64)
+        col = np.zeros(max(self.entries, 1), np.uint32)
+        b = np.zeros(max(self.entries, 1), np.uint8)
+        acc = np.zeros(max(self.entries, 1), np.uint8)
+        check(abi().vga_graph_csr(self.h, _p(rowptr), _p(col), _p(b), _p(acc)))
+        return rowptr, col[:self.entries], b[:self.entries], acc[:self.entries]
+
+    def cell_refs(self):
+        r = np.zeros(self.n + self.ghosts, np.int32)
+        check(abi().vga_graph_cell_refs(self.h, _p(r)))
+        return r
+
+    def node_stats(self):
+        rows = self.src_end - self.src_begin
+        out = dict(connectivity=np.zeros(rows, np.int32), sum_d=np.zeros(rows), sum_d2=np.zeros(rows),
+                   far=np.zeros((rows, 32), np.float32), bin_count=np.zeros((rows, 32), np.int32),
+                   gridconn=np.zeros(rows, np.uint8))
+        check(abi().vga_graph_node_stats(self.h, _p(out["connectivity"]), _p(out["sum_d"]), _p(out["sum_d2"]),
+                                         _p(out["far"]), _p(out["bin_count"]), _p(out["gridconn"])))
+        return out
+
+    def device_rows(self):
+        rp, adj, ne = vp(), vp(), i64()
+        check(abi().vga_graph_device_rows(self.h, C.byref(rp), C.byref(adj), C.byref(ne)))
+        return rp.value, adj.value, ne.value
+
+    def global_ints(self, radius=-1, src=None, maxl=32):
+        b, e = (0, self.n) if src is None else src
+        k = e - b
+        while True:
+            tn = np.zeros(k, np.int32)
+            td = np.zeros(k, np.int64)
+            dist = np.zeros((k, maxl), np.int32)
+            used = C.c_int32(0)
+            rc = abi().vga_global(self.ctx.h, self.h, radius, b, e, _p(tn), _p(td), _p(dist), maxl, C.byref(used))
+            if rc == -5 and used.value > maxl:
+                maxl = used.value
+                continue
+            check(rc)
+            return tn, td, dist, used.value
+
+    def local_ints(self, src=None):
+        b, e = (0, self.n) if src is None else src
+        k = e - b
+        cl = np.zeros(k, np.int64)
+        kk = np.zeros(k, np.int32)
+        tot = np.zeros(k, np.int32)
+        ctl = np.zeros(k, np.float32)
+        check(abi().vga_local(self.ctx.h, self.h, b, e, _p(cl), _p(kk), _p(tot), _p(ctl)))
+        return cl, kk, tot, ctl
+
+
+GLOBAL_COLS = ["Visual Node Count", "Visual Mean Depth", "Visual Integration [HH]", "Visual Integration [P-value]",
+               "Visual Integration [Tekl]", "Visual Entropy", "Visual Relativised Entropy"]
+LOCAL_COLS = ["Visual Clustering Coefficient", "Visual Control", "Visual Controllability"]
+
+
+def global_attributes(tn, td, dist):
+    n = len(tn)
+    dist = np.ascontiguousarray(dist, np.int32)
+    outs = [np.zeros(n, np.float32) for _ in range(7)]
+    check(abi().vga_global_attributes(n, _p(np.ascontiguousarray(tn, np.int32)), _p(np.ascontiguousarray(td, np.int64)),
+                                      _p(dist), dist.shape[1], *[_p(o) for o in outs]))
+    return dict(zip(GLOBAL_COLS, outs))
+
+
+def local_attributes(cl, kk, tot, ctl):
+    n = len(cl)
+    outs = [np.zeros(n, np.float32) for _ in range(3)]
+    check(abi().vga_local_attributes(n, _p(np.ascontiguousarray(cl, np.int64)), _p(np.ascontiguousarray(kk, np.int32)),
+                                     _p(np.ascontiguousarray(tot, np.int32)), _p(np.ascontiguousarray(ctl, np.float32)),
+                                     *[_p(o) for o in outs]))
+    return dict(zip(LOCAL_COLS, outs))
+
+
+class HostMap:
+    """dmx::PointMap through the flat C view (mirrors PointMap's setGrid/makePoints/sparkGraph2 and the
+    two VGA modules' run())."""
+
+    def __init__(self, walls, spacing=1.0):
+        w = np.ascontiguousarray(walls, np.float64).reshape(-1, 4)
+        self.h = host().dmxh_map_create(_p(w), w.shape[0], spacing)
+        c, r = C.c_int32(), C.c_int32()
+        s, bx, by = C.c_double(), C.c_double(), C.c_double()
+        host().dmxh_map_grid(self.h, C.addressof(c), C.addressof(r), C.addressof(s), C.addressof(bx), C.addressof(by))
+        self.cols, self.rows, self.spacing, self.bl_x, self.bl_y = c.value, r.value, s.value, bx.value, by.value
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            host().dmxh_map_destroy(self.h)
+            self.h = None
+
+    def _ret(self, rc):
+        if rc < 0:
+            raise RuntimeError(host().dmxh_last_error().decode())
+        return bool(rc)
+
+    def block_lines(self):
+        return self._ret(host().dmxh_map_block_lines(self.h))
+
+    def fill(self, x, y):
+        return self._ret(host().dmxh_map_fill(self.h, x, y))
+
+    @property
+    def n(self):
+        return host().dmxh_map_filled_count(self.h)
+
+    def flat(self, maxdist=-1.0) -> FlatGrid:
+        cells, nseg = i64(), i64()
+        host().dmxh_map_flat(self.h, C.addressof(cells), C.addressof(nseg), None, None, None)
+        state = np.zeros(cells.value, np.uint16)
+        off = np.zeros(cells.value + 1, np.uint32)
+        lines = np.zeros((max(nseg.value, 1), 5))
+        host().dmxh_map_flat(self.h, None, None, _p(state), _p(off), _p(lines))
+        return FlatGrid(self.cols, self.rows, self.spacing, self.bl_x, self.bl_y, state, off, lines[:nseg.value], maxdist)
+
+    def make_graph(self, boundary=False, maxdist=-1.0):
+        return self._ret(host().dmxh_map_make_graph(self.h, int(boundary), maxdist))
+
+    def vga_global(self, radius=-1.0, simple=False):
+        return self._ret(host().dmxh_map_vga_global(self.h, radius, int(simple)))
+
+    def vga_local(self, simple=False):
+        return self._ret(host().dmxh_map_vga_local(self.h, int(simple)))
+
+    def columns(self):
+        buf = C.create_string_buffer(8192)
+        host().dmxh_map_columns(self.h, buf, 8192)
+        return [s for s in buf.value.decode().split("\n") if s]
+
+    def attr(self, name):
+        out = np.zeros(self.n, np.float32)
+        if not host().dmxh_map_attr(self.h, name.encode(), _p(out)):
+            raise KeyError(name)
+        return out
+
+    def grid_connections(self):
+        out = np.zeros(self.n, np.uint8)
+        host().dmxh_map_grid_connections(self.h, _p(out))
+        return out
+
+
+def prepare(plan, maxdist=-1.0) -> FlatGrid:
+    """Plan -> flat hot-path inputs via the host layer (setGrid, blockLines, fill)."""
+    m = HostMap(plan.walls, plan.spacing)
+    for s in plan.seeds:
+        m.fill(*s)
+    return m.flat(maxdist)

@@ -1,0 +1,459 @@
+// All-sources BFS of VGA visibility analysis (VGAVisualGlobal::run + extractUnseen,
+// salalib/vgamodules/vgavisualglobal.cpp:66-130, 218-240) as a bit-parallel multi-source BFS.
+//
+// 64 consecutive x-major sources form a batch; a batch carries one 64-bit word per vertex for
+// each of visited / frontier / next.  Many batches (a "chunk") advance level by level together:
+// grid = (vertex tiles, batches), so one launch per level serves the whole chunk and the host
+// synchronises once per level, not once per batch.  Batches whose frontier emptied are skipped.
+//
+// Per level and batch the step is direction-optimising:
+//   push  (top-down)  every vertex with a non-zero frontier word streams its adjacency row with
+//                     coalesced 32-bit loads and ORs its word into `next` of unvisited targets
+//                     (atomicOr on L2-resident words, filtered by a plain read of `visited`);
+//   pull  (bottom-up) every vertex that still misses some source bit streams its in-row
+//                     (transpose adjacency) and ORs the frontier words of its in-neighbours,
+//                     leaving the row as soon as every missing bit is found (warp-wide redux).
+// The choice is made on the device from the frontier's and the unvisited set's edge counts.
+// `update` folds `next` into visited/frontier and counts the new vertices per source with
+// ballot + popc (bit b of lane l's word -> source b), i.e. the reference's distribution[level].
+//
+// The reference's `extents` run short-circuit is a pure optimisation; the result
+// is the plain level structure computed here.  Ghost vertices (unfilled cells inside a diagonal
+// run) are never counted or expanded by the reference (p.filled() test, :104) and are dropped.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <memory>
+
+#include "vga_dev.cuh"
+
+namespace vga {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int TPB = 256;
+
+typedef unsigned long long u64;
+
+struct BfsDev {
+    int64_t n;           // filled vertices
+    const uint64_t *rowptr;
+    const uint32_t *adj;  // packed col<<6|..
+    const uint64_t *t_rowptr;
+    const uint32_t *t_col;
+    u64 *visited, *frontier, *next;  // [chunk][n]
+    const u64 *valid;     // [chunk] valid source bits of each batch
+    int *active;          // [chunk] 1 while the batch's frontier is non-empty
+    int *mode;            // [chunk] 0 push, 1 pull
+    u64 *stats;           // [chunk][4]: frontier edges, unvisited in-edges, new vertices, -
+    int *any;             // [1] any batch still active
+};
+
+__global__ void k_init(BfsDev d, int64_t first_src, int64_t nsrc) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsrc) return;
+    int64_t b = i >> 6;
+    int bit = (int)(i & 63);
+    int64_t v = first_src + i;
+    u64 w = 1ULL << bit;
+    d.visited[b * d.n + v] = w;  // distinct (b, v) per thread: sources of a batch are distinct vertices
+    d.frontier[b * d.n + v] = w;
+}
+
+// top-down step
+__global__ void __launch_bounds__(TPB) k_push(BfsDev d) {
+    const int b = blockIdx.y;
+    if (!d.active[b] || d.mode[b] != 0) return;
+    const int lane = threadIdx.x & 31;
+    const u64 *fr = d.frontier + (int64_t)b * d.n;
+    const u64 *vis = d.visited + (int64_t)b * d.n;
+    u64 *nx = d.next + (int64_t)b * d.n;
+    for (int64_t base = (int64_t)blockIdx.x * TPB; base < d.n; base += (int64_t)gridDim.x * TPB) {
+        int64_t u = base + threadIdx.x;
+        u64 f = (u < d.n) ? fr[u] : 0ULL;
+        unsigned m = __ballot_sync(FULL, f != 0ULL);
+        while (m) {
+            int src_lane = __ffs(m) - 1;
+            m &= m - 1;
+            u64 fw = __shfl_sync(FULL, f, src_lane);
+            int64_t uu = (base + (threadIdx.x & ~31)) + src_lane;
+            uint64_t e0 = d.rowptr[uu], e1 = d.rowptr[uu + 1];
+            for (uint64_t e = e0 + lane; e < e1; e += 32) {
+                uint32_t c = d.adj[e] >> 6;
+                if (c < (uint32_t)d.n) {
+                    u64 add = fw & ~vis[c];
+                    if (add) atomicOr(&nx[c], add);
+                }
+            }
+        }
+    }
+}
+
+// bottom-up step with early exit
+__global__ void __launch_bounds__(TPB) k_pull(BfsDev d) {
+    const int b = blockIdx.y;
+    if (!d.active[b] || d.mode[b] != 1) return;
+    const int lane = threadIdx.x & 31;
+    const u64 *fr = d.frontier + (int64_t)b * d.n;
+    const u64 *vis = d.visited + (int64_t)b * d.n;
+    u64 *nx = d.next + (int64_t)b * d.n;
+    const u64 valid = d.valid[b];
+    for (int64_t base = (int64_t)blockIdx.x * TPB; base < d.n; base += (int64_t)gridDim.x * TPB) {
+        int64_t w = base + threadIdx.x;
+        u64 need = (w < d.n) ? (valid & ~vis[w]) : 0ULL;
+        unsigned m = __ballot_sync(FULL, need != 0ULL);
+        while (m) {
+            int src_lane = __ffs(m) - 1;
+            m &= m - 1;
+            u64 nd = __shfl_sync(FULL, need, src_lane);
+            int64_t ww = (base + (threadIdx.x & ~31)) + src_lane;
+            uint64_t e0 = d.t_rowptr[ww], e1 = d.t_rowptr[ww + 1];
+            u64 acc = 0ULL;
+            for (uint64_t e = e0; e < e1; e += 32) {
+                uint64_t ee = e + lane;
+                u64 g = 0ULL;
+                if (ee < e1) g = fr[d.t_col[ee]];
+                unsigned lo = __reduce_or_sync(FULL, (unsigned)g);
+                unsigned hi = __reduce_or_sync(FULL, (unsigned)(g >> 32));
+                acc |= ((u64)hi << 32) | lo;
+                if ((acc & nd) == nd) break;
+            }
+            if (lane == 0) {
+                u64 nw = acc & nd;
+                if (nw) nx[ww] = nw;
+            }
+        }
+    }
+}
+
+// fold next into visited/frontier, count new vertices per source, gather direction statistics
+__global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[chunk][64] for this level*/, int want_stats) {
+    const int b = blockIdx.y;
+    if (!d.active[b]) return;
+    __shared__ int s_cnt[64];
+    __shared__ u64 s_stat[3];
+    if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x < 3) s_stat[threadIdx.x] = 0ULL;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    u64 *fr = d.frontier + (int64_t)b * d.n;
+    u64 *vis = d.visited + (int64_t)b * d.n;
+    u64 *nx = d.next + (int64_t)b * d.n;
+    const u64 valid = d.valid[b];
+    int c0 = 0, c1 = 0;  // lane l counts source bits l and l+32
+    u64 f_edges = 0, u_edges = 0, n_new = 0;
+    for (int64_t base = (int64_t)blockIdx.x * TPB; base < d.n; base += (int64_t)gridDim.x * TPB) {
+        int64_t v = base + threadIdx.x;
+        u64 nw = 0ULL, vv = valid;
+        if (v < d.n) {
+            vv = vis[v];
+            nw = nx[v] & ~vv;
+            if (nw) {
+                vv |= nw;
+                vis[v] = vv;
+                nx[v] = 0ULL;
+            }
+            fr[v] = nw;
+            if (want_stats) {
+                if (nw) {
+                    f_edges += d.rowptr[v + 1] - d.rowptr[v];
+                    n_new += 1;
+                }
+                if ((valid & ~vv) != 0ULL && d.t_rowptr) u_edges += d.t_rowptr[v + 1] - d.t_rowptr[v];
+            } else if (nw) {
+                n_new += 1;
+            }
+        }
+        unsigned lo_any = __reduce_or_sync(FULL, (unsigned)nw);
+        unsigned hi_any = __reduce_or_sync(FULL, (unsigned)(nw >> 32));
+        while (lo_any) {
+            int bit = __ffs(lo_any) - 1;
+            lo_any &= lo_any - 1;
+            int c = __popc(__ballot_sync(FULL, (nw >> bit) & 1ULL));
+            if (lane == bit) c0 += c;
+        }
+        while (hi_any) {
+            int bit = __ffs(hi_any) - 1;
+            hi_any &= hi_any - 1;
+            int c = __popc(__ballot_sync(FULL, (nw >> (bit + 32)) & 1ULL));
+            if (lane == bit) c1 += c;
+        }
+    }
+    if (c0) atomicAdd(&s_cnt[lane], c0);
+    if (c1) atomicAdd(&s_cnt[lane + 32], c1);
+    // warp-reduce the statistics
+    for (int o = 16; o > 0; o >>= 1) {
+        f_edges += __shfl_down_sync(FULL, f_edges, o);
+        u_edges += __shfl_down_sync(FULL, u_edges, o);
+        n_new += __shfl_down_sync(FULL, n_new, o);
+    }
+    if (lane == 0) {
+        if (f_edges) atomicAdd(&s_stat[0], f_edges);
+        if (u_edges) atomicAdd(&s_stat[1], u_edges);
+        if (n_new) atomicAdd(&s_stat[2], n_new);
+    }
+    __syncthreads();
+    if (threadIdx.x < 64 && s_cnt[threadIdx.x]) atomicAdd(&counts[b * 64 + threadIdx.x], s_cnt[threadIdx.x]);
+    if (threadIdx.x < 3 && s_stat[threadIdx.x]) atomicAdd(&d.stats[b * 4 + threadIdx.x], s_stat[threadIdx.x]);
+}
+
+// per batch: retire empty batches, choose the next step's direction, reset statistics
+__global__ void k_decide(BfsDev d, int chunk, int bfs_mode, int64_t alpha, u64 *work /*[2] push edges, pull edges*/) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= chunk) return;
+    if (!d.active[b]) return;
+    u64 fe = d.stats[b * 4 + 0], ue = d.stats[b * 4 + 1], nn = d.stats[b * 4 + 2];
+    d.stats[b * 4 + 0] = 0;
+    d.stats[b * 4 + 1] = 0;
+    d.stats[b * 4 + 2] = 0;
+    if (nn == 0) {
+        d.active[b] = 0;
+        return;
+    }
+    *d.any = 1;
+    int m = 0;
+    if (bfs_mode == 1)
+        m = 1;
+    else if (bfs_mode == 2)
+        m = (fe * (u64)alpha > ue) ? 1 : 0;
+    d.mode[b] = m;
+    atomicAdd(&work[m], m ? ue : fe);
+}
+
+// ---- transpose (in-edge lists of filled vertices), needed by the pull step --------------------
+__global__ void k_indeg(const uint32_t *adj, uint64_t n_entries, uint32_t n, u64 *indeg) {
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_entries) return;
+    uint32_t c = adj[e] >> 6;
+    if (c < n) atomicAdd(&indeg[c], 1ULL);
+}
+__global__ void k_scatter_t(const uint64_t *rowptr, const uint32_t *adj, int64_t n, u64 *cursor, uint32_t *t_col) {
+    // one warp per source row
+    int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (u >= n) return;
+    for (uint64_t e = rowptr[u] + lane; e < rowptr[u + 1]; e += 32) {
+        uint32_t c = adj[e] >> 6;
+        if (c < (uint32_t)n) {
+            u64 p = atomicAdd(&cursor[c], 1ULL);
+            t_col[p] = (uint32_t)u;
+        }
+    }
+}
+
+inline unsigned blocks_for(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace
+
+int ensure_transpose(vga_ctx *ctx, vga_graph *g) {
+    if (g->has_transpose) return VGA_OK;
+    cudaStream_t st = ctx->stream;
+    const int64_t n = g->n;
+    DevBuf<u64> indeg, cursor;
+    VGA_TRY(indeg.alloc_zero((size_t)n + 1, st));
+    VGA_TRY(g->t_rowptr.alloc((size_t)n + 1));
+    if (g->entries > 0) {
+        k_indeg<<<blocks_for(g->entries, 256), 256, 0, st>>>(g->adj.p, (uint64_t)g->entries, (uint32_t)n, indeg.p);
+        ctx->timing.launches++;
+    }
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, indeg.p, (u64 *)g->t_rowptr.p, (int)(n + 1), st);
+    DevBuf<unsigned char> tmp;
+    VGA_TRY(tmp.alloc(tb + 16));
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb, indeg.p, (u64 *)g->t_rowptr.p, (int)(n + 1), st);
+    ctx->timing.launches++;
+    uint64_t total = 0;
+    VGA_CUDA(cudaMemcpyAsync(&total, g->t_rowptr.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    VGA_CUDA(cudaStreamSynchronize(st));
+    g->t_entries = (int64_t)total;
+    VGA_TRY(g->t_col.alloc((size_t)total + 1));
+    VGA_TRY(cursor.alloc((size_t)n + 1));
+    VGA_CUDA(cudaMemcpyAsync(cursor.p, g->t_rowptr.p, sizeof(u64) * (n + 1), cudaMemcpyDeviceToDevice, st));
+    if (n > 0) {
+        k_scatter_t<<<blocks_for(n * 32, 256), 256, 0, st>>>(g->rowptr.p, g->adj.p, n, cursor.p, g->t_col.p);
+        ctx->timing.launches++;
+    }
+    VGA_CUDA(cudaStreamSynchronize(st));
+    VGA_CUDA(cudaGetLastError());
+    g->has_transpose = true;
+    return VGA_OK;
+}
+
+int run_global(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_t src_end, int32_t *total_nodes,
+               int64_t *total_depth, int32_t *dist, int32_t max_levels, int32_t *levels_used) {
+    cudaStream_t st = ctx->stream;
+    const int64_t n = g->n;
+    if (g->src_begin != 0 || g->src_end != n) {
+        set_error("vga_global: the graph must hold the rows of all cells (gather the shards first)");
+        return VGA_ERR_INVALID;
+    }
+    if (src_end < 0 || src_end > n) src_end = n;
+    if (src_begin < 0) src_begin = 0;
+    const int64_t nsrc = std::max<int64_t>(0, src_end - src_begin);
+    if (levels_used) *levels_used = 0;
+    if (nsrc == 0) return VGA_OK;
+    Timing &tm = ctx->timing;
+    const int bfs_mode = (int)ctx->opt.bfs_mode;
+    StageTimer kt(ctx, 0, &tm.kernel_ms);
+    StageTimer mt(ctx, 2, &tm.main_kernel_ms);
+    StageTimer dt(ctx, 4, &tm.d2h_ms);
+
+    kt.start();
+    if (bfs_mode != 0) VGA_TRY(ensure_transpose(ctx, g));
+    kt.stop();
+
+    const int64_t nbatch = (nsrc + 63) / 64;
+    // chunk size: state of 3 words per (batch, vertex); keep below ~40% of free memory and 48 GB
+    size_t free_b = 0, total_b = 0;
+    VGA_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    int64_t budget = (int64_t)std::min<size_t>((size_t)(free_b * 0.4), (size_t)48 << 30);
+    int64_t chunk = ctx->opt.bfs_chunk > 0 ? ctx->opt.bfs_chunk : std::max<int64_t>(1, budget / (24 * std::max<int64_t>(n, 1)));
+    chunk = std::min<int64_t>(chunk, nbatch);
+    chunk = std::min<int64_t>(chunk, 65535);
+
+    DevBuf<u64> visited, frontier, next, valid, stats, work;
+    DevBuf<int> active, mode, any;
+    DevBuf<int32_t> counts;
+    int lcap = 16;
+    VGA_TRY(visited.alloc((size_t)chunk * n));
+    VGA_TRY(frontier.alloc((size_t)chunk * n));
+    VGA_TRY(next.alloc((size_t)chunk * n));
+    VGA_TRY(valid.alloc((size_t)chunk));
+    VGA_TRY(stats.alloc((size_t)chunk * 4));
+    VGA_TRY(work.alloc_zero(2, st));
+    VGA_TRY(active.alloc((size_t)chunk));
+    VGA_TRY(mode.alloc((size_t)chunk));
+    VGA_TRY(any.alloc(1));
+    VGA_TRY(counts.alloc((size_t)lcap * chunk * 64));
+
+    BfsDev d;
+    d.n = n;
+    d.rowptr = g->rowptr.p;
+    d.adj = g->adj.p;
+    d.t_rowptr = g->has_transpose ? g->t_rowptr.p : nullptr;
+    d.t_col = g->has_transpose ? g->t_col.p : nullptr;
+    d.visited = visited.p;
+    d.frontier = frontier.p;
+    d.next = next.p;
+    d.valid = valid.p;
+    d.active = active.p;
+    d.mode = mode.p;
+    d.stats = stats.p;
+    d.any = any.p;
+
+    const unsigned xblocks = (unsigned)std::min<int64_t>((n + TPB - 1) / TPB, 4096);
+    int deepest = 0;
+    std::vector<int32_t> h_counts;
+    std::vector<u64> h_valid;
+
+    for (int64_t b0 = 0; b0 < nbatch; b0 += chunk) {
+        const int64_t cb = std::min<int64_t>(chunk, nbatch - b0);
+        const int64_t first = src_begin + b0 * 64;
+        const int64_t cs = std::min<int64_t>(cb * 64, src_end - first);
+        if (ctx->cancel && ctx->cancel(ctx->user)) {
+            set_error("cancelled");
+            return VGA_ERR_CANCELLED;
+        }
+        h_valid.assign((size_t)cb, ~0ULL);
+        if (cs & 63) h_valid[(size_t)cb - 1] = (1ULL << (cs & 63)) - 1ULL;
+        kt.start();
+        VGA_CUDA(cudaMemcpyAsync(valid.p, h_valid.data(), sizeof(u64) * cb, cudaMemcpyHostToDevice, st));
+        VGA_CUDA(cudaMemsetAsync(visited.p, 0, sizeof(u64) * (size_t)cb * n, st));
+        VGA_CUDA(cudaMemsetAsync(frontier.p, 0, sizeof(u64) * (size_t)cb * n, st));
+        VGA_CUDA(cudaMemsetAsync(next.p, 0, sizeof(u64) * (size_t)cb * n, st));
+        VGA_CUDA(cudaMemsetAsync(stats.p, 0, sizeof(u64) * (size_t)cb * 4, st));
+        VGA_CUDA(cudaMemsetAsync(mode.p, 0, sizeof(int) * (size_t)cb, st));
+        VGA_CUDA(cudaMemsetAsync(counts.p, 0, sizeof(int32_t) * (size_t)lcap * chunk * 64, st));
+        {
+            std::vector<int> ones((size_t)cb, 1);
+            VGA_CUDA(cudaMemcpyAsync(active.p, ones.data(), sizeof(int) * cb, cudaMemcpyHostToDevice, st));
+            VGA_CUDA(cudaStreamSynchronize(st));
+        }
+        k_init<<<blocks_for(cs, 256), 256, 0, st>>>(d, first, cs);
+        tm.launches++;
+        if (bfs_mode == 1) VGA_CUDA(cudaMemsetAsync(mode.p, 0, sizeof(int) * (size_t)cb, st));  // level 0 always pushes
+        mt.start();
+        int level = 0;  // frontier holds level `level`
+        int nlev = 1;
+        while (radius == -1 || level < radius) {
+            dim3 grid(xblocks, (unsigned)cb);
+            k_push<<<grid, TPB, 0, st>>>(d);
+            tm.launches++;
+            tm.main_launches++;
+            if (bfs_mode != 0 && level > 0) {
+                k_pull<<<grid, TPB, 0, st>>>(d);
+                tm.launches++;
+                tm.main_launches++;
+            }
+            if (level + 1 >= lcap) {
+                // grow the level histogram
+                mt.stop();
+                DevBuf<int32_t> bigger;
+                VGA_TRY(bigger.alloc_zero((size_t)lcap * 2 * chunk * 64, st));
+                VGA_CUDA(cudaMemcpyAsync(bigger.p, counts.p, sizeof(int32_t) * (size_t)lcap * chunk * 64,
+                                         cudaMemcpyDeviceToDevice, st));
+                VGA_CUDA(cudaStreamSynchronize(st));
+                counts = std::move(bigger);
+                lcap *= 2;
+                mt.start();
+            }
+            VGA_CUDA(cudaMemsetAsync(any.p, 0, sizeof(int), st));
+            k_update<<<grid, TPB, 0, st>>>(d, counts.p + (size_t)(level + 1) * chunk * 64, bfs_mode == 2 ? 1 : 0);
+            k_decide<<<blocks_for(cb, 128), 128, 0, st>>>(d, (int)cb, bfs_mode, ctx->opt.pull_alpha, work.p);
+            tm.launches += 2;
+            tm.main_launches += 2;
+            int h_any = 0;
+            VGA_CUDA(cudaMemcpyAsync(&h_any, any.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            VGA_CUDA(cudaStreamSynchronize(st));
+            if (!h_any) break;
+            level++;
+            nlev = level + 1;
+        }
+        mt.stop();
+        kt.stop();
+        VGA_CUDA(cudaGetLastError());
+        deepest = std::max(deepest, nlev);
+
+        // results of this chunk: level histogram -> host
+        dt.start();
+        h_counts.resize((size_t)nlev * chunk * 64);
+        VGA_CUDA(cudaMemcpyAsync(h_counts.data(), counts.p, sizeof(int32_t) * (size_t)nlev * chunk * 64,
+                                 cudaMemcpyDeviceToHost, st));
+        dt.stop();
+        for (int64_t i = 0; i < cs; i++) {
+            int64_t o = (first - src_begin) + i;
+            int64_t b = i >> 6;
+            int bit = (int)(i & 63);
+            int64_t tn = 1, td = 0;
+            if (dist && max_levels > 0) {
+                for (int l = 0; l < max_levels; l++) dist[o * max_levels + l] = 0;
+                dist[o * max_levels] = 1;
+            }
+            for (int l = 1; l < nlev; l++) {
+                int32_t c = h_counts[((size_t)l * chunk + b) * 64 + bit];
+                tn += c;
+                td += (int64_t)l * c;
+                if (dist && l < max_levels) dist[o * max_levels + l] = c;
+            }
+            if (total_nodes) total_nodes[o] = (int32_t)tn;
+            if (total_depth) total_depth[o] = td;
+        }
+        if (ctx->progress) ctx->progress(ctx->user, std::min<int64_t>(nsrc, (b0 + cb) * 64), nsrc);
+    }
+    // deepest counts levels 0..deepest-1 that were *computed*; trailing empty level is not reported
+    if (levels_used) *levels_used = deepest;
+    {
+        u64 hw[2] = {0, 0};
+        VGA_CUDA(cudaMemcpy(hw, work.p, sizeof(hw), cudaMemcpyDeviceToHost));
+        // algorithmic bytes: adjacency entries streamed by expanding vertices (4 B each)
+        tm.algo_bytes = 4.0 * ((double)hw[0] + (double)hw[1]);
+    }
+    if (dist && deepest > max_levels) {
+        set_error("vga_global: level histogram needs " + std::to_string(deepest) + " columns");
+        return VGA_ERR_CAPACITY;
+    }
+    return VGA_OK;
+}
+
+}  // namespace vga

@@ -1,0 +1,1084 @@
+// makegraph: grid visibility-graph construction on sm_100a.
+//
+// Replaces PointMap::sparkGraph2 / sparkPixel2 / sieve2 (salalib/pointdata.cpp:1246-1565) and
+// sparkSieve2 (salalib/sparksieve2.cpp:33-173).  The algorithm is NOT a port of the reference's
+// per-pixel std::list / std::vector / std::set code; it is re-derived for a warp:
+//
+//   * one warp owns one (source cell, octant) task; the 8 octants of a source sit in 8
+//     consecutive warps so their cell reads share L1/L2 lines;
+//   * the angular gap list and the row's wall "blocks" live in shared memory (per-warp slices);
+//     rare tasks that overflow the slices are re-run by a second launch with global scratch;
+//   * a depth row is swept by all 32 lanes at once: the union of the gaps' widened index ranges
+//     is enumerated with a warp scan, every lane tests one candidate cell (centre-gap rule, FILLED,
+//     axis/diagonal de-duplication, FP64 line test against the cell's own wall segments), accepted
+//     cells are emitted in ascending index order with a ballot/popc prefix -- this equals the
+//     reference's (gap, ind) visiting order because gaps are disjoint and sorted;
+//   * blocks are sorted (start asc, end desc) by a warp bitonic network and subtracted from the
+//     gap list by the reference's sequential rule (erase-if <= start+1e-10, split, "stay on this
+//     block"), which is order dependent and therefore executed by one lane;
+//   * all geometry is IEEE FP64 with explicit round-to-nearest mul/add (no FMA contraction), and
+//     x/0 = +-inf is kept as the reference relies on it (sparksieve2.cpp:143-173).
+//
+// Two passes (count, emit) size the edge buffer exactly; rows are then finalised:
+//   node_stats  -- Connectivity, the order-dependent double sums of the two moments, far bin
+//                  distances, per-bin counts, grid connections (pointdata.cpp:1463-1497, 1735-1768)
+//   make_keys + cub segmented sort -- rows sorted by x-major ordinal, packed col<<6|accepted<<5|bin.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <memory>
+
+#include "vga_dev.cuh"
+
+namespace vga {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int WARPS_PER_BLOCK = 8;
+
+struct Zone {
+    double s, e;
+};
+
+struct Ln {
+    double blx, bly, trx, try_;
+    int parity;
+};
+
+struct GridDev {
+    int cols, rows;
+    double spacing, blx, bly, maxdist;
+    const uint8_t *cflag;
+    const uint8_t *cflag_t;
+    const uint32_t *line_off;
+    const double *lines;
+    const int32_t *cellord;
+    const int32_t *cellref;
+    int64_t n;
+};
+
+// ---- FP64 helpers: explicit rn ops so that no fused multiply-add can ever be formed ------------
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dvd(double a, double b) { return __ddiv_rn(a, b); }
+
+__device__ __forceinline__ Ln load_line(const double *p) {
+    Ln l;
+    l.blx = p[0];
+    l.bly = p[1];
+    l.trx = p[2];
+    l.try_ = p[3];
+    l.parity = p[4] != 0.0;
+    return l;
+}
+
+// normal form of the segment a->b (genlib/p2dpoly.cpp:291-336 semantics)
+__device__ __forceinline__ Ln make_line(double ax, double ay, double bx, double by) {
+    Ln l;
+    bool swap = ax > bx;
+    double lx = swap ? bx : ax, ly = swap ? by : ay;  // left end (or a when vertical)
+    double rx = swap ? ax : bx, ry = swap ? ay : by;
+    l.blx = lx;
+    l.trx = rx;
+    if (ax == bx) {
+        l.parity = 1;
+        l.bly = fmin(ay, by);
+        l.try_ = fmax(ay, by);
+    } else if (ly <= ry) {
+        l.parity = 1;
+        l.bly = ly;
+        l.try_ = ry;
+    } else {
+        l.parity = 0;
+        l.bly = ry;
+        l.try_ = ly;
+    }
+    return l;
+}
+
+__device__ __forceinline__ double l_ay(const Ln &l) { return l.parity ? l.bly : l.try_; }
+__device__ __forceinline__ double l_by(const Ln &l) { return l.parity ? l.try_ : l.bly; }
+__device__ __forceinline__ double l_w(const Ln &l) { return fabs(sub(l.trx, l.blx)); }
+__device__ __forceinline__ double l_h(const Ln &l) { return fabs(sub(l.try_, l.bly)); }
+
+__device__ __forceinline__ bool overlap1(double abl, double atr, double bbl, double btr, double tol) {
+    return (abl > bbl) ? (btr >= sub(abl, tol)) : (atr >= sub(bbl, tol));
+}
+
+// intersect_region && intersect_line (genlib/p2dpoly.cpp:247-279, 350-363)
+__device__ __forceinline__ bool line_hits(const Ln &a, const Ln &b, double tol) {
+    if (!(overlap1(a.blx, a.trx, b.blx, b.trx, tol) && overlap1(a.bly, a.try_, b.bly, b.try_, tol))) return false;
+    double aax = a.blx, aay = l_ay(a), abx = a.trx, aby = l_by(a);
+    double bax = b.blx, bay = l_ay(b), bbx = b.trx, bby = l_by(b);
+    double ady = sub(aay, aby), adx = sub(abx, aax);
+    double t1 = add(mul(ady, sub(bax, aax)), mul(adx, sub(bay, aay)));
+    double t2 = add(mul(ady, sub(bbx, aax)), mul(adx, sub(bby, aay)));
+    if (!(mul(t1, t2) <= tol)) return false;
+    double bdy = sub(bay, bby), bdx = sub(bbx, bax);
+    double t3 = add(mul(bdy, sub(aax, bax)), mul(bdx, sub(aay, bay)));
+    double t4 = add(mul(bdy, sub(abx, bax)), mul(bdx, sub(aby, bay)));
+    return mul(t3, t4) <= tol;
+}
+
+// Line::crop semantics (genlib/p2dpoly.cpp:626-667): clip order left, right, bottom, top, each with
+// the current width/height.
+__device__ bool crop_line(Ln &l, double rblx, double rbly, double rtrx, double rtry) {
+    double sign = l.parity ? 1.0 : -1.0;
+    if (!(l.trx >= rblx)) return false;
+    if (l.blx < rblx) {
+        double d = mul(sign, dvd(mul(l_h(l), sub(rblx, l.blx)), l_w(l)));
+        if (l.parity)
+            l.bly = add(l.bly, d);
+        else
+            l.try_ = add(l.try_, d);
+        l.blx = rblx;
+    }
+    if (!(l.blx <= rtrx)) return false;
+    if (l.trx > rtrx) {
+        double d = dvd(mul(mul(sign, l_h(l)), sub(l.trx, rtrx)), l_w(l));
+        if (l.parity)
+            l.try_ = sub(l.try_, d);
+        else
+            l.bly = sub(l.bly, d);
+        l.trx = rtrx;
+    }
+    if (!(l.try_ >= rbly)) return false;
+    if (l.bly < rbly) {
+        double d = dvd(mul(l_w(l), sub(rbly, l.bly)), l_h(l));
+        if (l.parity)
+            l.blx = add(l.blx, d);
+        else
+            l.trx = sub(l.trx, d);
+        l.bly = rbly;
+    }
+    if (!(l.bly <= rtry)) return false;
+    if (l.try_ > rtry) {
+        double d = dvd(mul(l_w(l), sub(l.try_, rtry)), l_h(l));
+        if (l.parity)
+            l.trx = sub(l.trx, d);
+        else
+            l.blx = add(l.blx, d);
+        l.try_ = rtry;
+    }
+    return true;
+}
+
+__device__ __forceinline__ double tanify(double cx, double cy, double px, double py, int q) {
+    switch (q) {
+    case 0: return dvd(sub(py, cy), sub(cx, px));
+    case 1: return dvd(sub(py, cy), sub(px, cx));
+    case 2: return dvd(sub(cy, py), sub(cx, px));
+    case 3: return dvd(sub(cy, py), sub(px, cx));
+    case 4: return dvd(sub(cx, px), sub(cy, py));
+    case 5: return dvd(sub(px, cx), sub(cy, py));
+    case 6: return dvd(sub(cx, px), sub(py, cy));
+    default: return dvd(sub(px, cx), sub(py, cy));
+    }
+}
+
+// angular interval covered by a wall segment, padded by 1e-10 (sparksieve2.cpp:67-82)
+__device__ __forceinline__ Zone make_block(const Ln &l, double cx, double cy, int q) {
+    double a = tanify(cx, cy, l.blx, l_ay(l), q);
+    double b = tanify(cx, cy, l.trx, l_by(l), q);
+    Zone z;
+    if (a < b) {
+        z.s = sub(a, 1e-10);
+        z.e = add(b, 1e-10);
+    } else {
+        z.s = sub(b, 1e-10);
+        z.e = add(a, 1e-10);
+    }
+    return z;
+}
+
+__device__ __forceinline__ bool zone_less(const Zone &a, const Zone &b) {
+    return (a.s == b.s) ? (a.e > b.e) : (a.s < b.s);
+}
+
+// direction bin of a target (salalib/pointdata.h:432-520 semantics)
+__device__ __forceinline__ int which_bin(double gx, double gy) {
+    double ax = fabs(gx), ay = fabs(gy);
+    int bin;
+    double ratio;
+    if (ay > ax) {
+        ratio = dvd(ax, ay);
+        bin = (gy > 0.0) ? ((gx >= 0.0) ? -8 : 8) : ((gx >= 0.0) ? 24 : -24);
+    } else {
+        ratio = dvd(ay, ax);
+        bin = (gx > 0.0) ? ((gy >= 0.0) ? 0 : -32) : ((gy >= 0.0) ? -16 : 16);
+    }
+    if (ratio < 1e-12) {
+    } else if (ratio < 0.2679491924311227)
+        bin += 1;
+    else if (ratio < 0.5773502691896257)
+        bin += 2;
+    else if (ratio < 1.0 - 1e-12)
+        bin += 3;
+    else
+        bin += 4;
+    if (bin < 0) bin = -bin;
+    return bin % 32;
+}
+
+__device__ __forceinline__ int warp_incl_sum(int v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(FULL, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ int warp_incl_max(int v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(FULL, v, d);
+        if (lane >= d) v = max(v, t);
+    }
+    return v;
+}
+
+// Per-warp scratch (shared or global memory)
+struct Scratch {
+    Zone *ga, *gb, *blk;
+    int *rstart, *rprefix;
+    int gcap, bcap;
+};
+
+enum { TASK_OK = 0, TASK_OVERFLOW = 1, TASK_NAN = 2 };
+
+// Sort the row's blocks and subtract them from the gap list.  Returns the new gap count
+// (written to gout) or -1 on capacity overflow.
+__device__ int subtract_blocks(const Zone *gin, int ng, Zone *blk, int nb, Zone *gout, int gcap, int bcap, int lane) {
+    if (nb > 1) {
+        int P = 1;
+        while (P < nb) P <<= 1;  // P <= bcap is guaranteed by the caller (bcap is a power of two)
+        for (int i = nb + lane; i < P; i += 32) {
+            blk[i].s = __longlong_as_double(0x7ff0000000000000LL);   // +inf
+            blk[i].e = __longlong_as_double(0xfff0000000000000LL);   // -inf: sorts after every real block
+        }
+        __syncwarp();
+        for (int k = 2; k <= P; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = lane; i < P; i += 32) {
+                    int p = i ^ j;
+                    if (p > i) {
+                        Zone a = blk[i], b = blk[p];
+                        bool up = ((i & k) == 0);
+                        if (zone_less(b, a) == up) {
+                            blk[i] = b;
+                            blk[p] = a;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    int ngo = 0;
+    if (lane == 0) {
+        // sequential interval subtraction (sparksieve2.cpp:89-132), duplicates of the sorted block
+        // list skipped on the fly (std::unique), output streamed to gout
+        int gi = 0, bi = 0;
+        Zone cur = gin[0];
+        bool over = false;
+        while (bi < nb && gi < ng) {
+            Zone B = blk[bi];
+            if (bi > 0) {
+                Zone Bp = blk[bi - 1];
+                if (Bp.s == B.s && Bp.e == B.e) {
+                    bi++;
+                    continue;
+                }
+            }
+            if (B.e < cur.s) {
+                bi++;
+                continue;
+            }
+            bool create = true;
+            if (B.s <= cur.s) {
+                create = false;
+                if (B.e > cur.s) cur.s = B.e;
+            }
+            if (B.e >= cur.e) {
+                create = false;
+                if (B.s < cur.e) cur.e = B.s;
+            }
+            if (cur.e <= add(cur.s, 1e-10)) {
+                gi++;
+                if (gi < ng) cur = gin[gi];
+                continue;
+            } else if (B.e > cur.e) {
+                if (ngo < gcap) gout[ngo] = cur; else over = true;
+                ngo++;
+                gi++;
+                if (gi < ng) cur = gin[gi];
+                continue;
+            } else if (create) {
+                Zone left;
+                left.s = cur.s;
+                left.e = B.s;
+                if (ngo < gcap) gout[ngo] = left; else over = true;
+                ngo++;
+                cur.s = B.e;
+            }
+            bi++;
+        }
+        if (gi < ng) {
+            if (ngo < gcap) gout[ngo] = cur; else over = true;
+            ngo++;
+            for (int r = gi + 1; r < ng; r++) {
+                if (ngo < gcap) gout[ngo] = gin[r]; else over = true;
+                ngo++;
+            }
+        }
+        if (over) ngo = -1;
+    }
+    ngo = __shfl_sync(FULL, ngo, 0);
+    __syncwarp();
+    return ngo;
+}
+
+struct TaskOut {
+    uint32_t nacc, nfill;
+    int status;
+};
+
+template <bool EMIT>
+__device__ TaskOut sieve_task(const GridDev &g, int cx, int cy, int q, const Scratch &sc, uint8_t *ghostflag,
+                              uint64_t acc_off, uint64_t fill_off, uint32_t *e_ref, uint8_t *e_bin) {
+    const int lane = threadIdx.x & 31;
+    const unsigned ltmask = (1u << lane) - 1u;
+    const double s = g.spacing;
+    const double c0x = add(g.blx, mul(s, (double)cx));
+    const double c0y = add(g.bly, mul(s, (double)cy));
+    const double tol = mul(s, 1e-10);
+    const bool xmajor = q < 4;
+    const int sx = (q & 1) ? 1 : -1;
+    const int sy = (q <= 1 || q >= 6) ? 1 : -1;
+    const int diagbin = (q == 0) ? 12 : (q == 1) ? 4 : (q == 2) ? 20 : 28;
+
+    Zone *G = sc.ga, *Gn = sc.gb;
+    TaskOut out;
+    out.nacc = 0;
+    out.nfill = 0;
+    out.status = TASK_OK;
+    int ng = 1;
+    if (lane == 0) {
+        G[0].s = 0.0;
+        G[0].e = 1.0;
+    }
+    __syncwarp();
+    bool bad_nan = false;
+
+    // ---- depth 0: own-cell wall lines clipped to the octant's quadrant (pointdata.cpp:1399-1449)
+    {
+        int64_t c = (int64_t)cx * g.rows + cy;
+        uint32_t lo = g.line_off[c];
+        int nl = (int)(g.line_off[c + 1] - lo);
+        if (nl > 0) {
+            double fx = (double)cx, fy = (double)cy;
+            double vblx = add(g.blx, mul(s, sub(sub(fx, 0.5), 1e-10)));
+            double vbly = add(g.bly, mul(s, sub(sub(fy, 0.5), 1e-10)));
+            double vtrx = add(g.blx, mul(s, add(add(fx, 0.5), 1e-10)));
+            double vtry = add(g.bly, mul(s, add(add(fy, 0.5), 1e-10)));
+            const double border = tol;
+            switch (q) {
+            case 0: vtrx = c0x; vbly = sub(c0y, border); break;
+            case 6: vtrx = add(c0x, border); vbly = c0y; break;
+            case 1: vblx = c0x; vbly = sub(c0y, border); break;
+            case 7: vblx = sub(c0x, border); vbly = c0y; break;
+            case 2: vtrx = c0x; vtry = add(c0y, border); break;
+            case 4: vtrx = add(c0x, border); vtry = c0y; break;
+            case 3: vblx = c0x; vtry = add(c0y, border); break;
+            default: vblx = sub(c0x, border); vtry = c0y; break;
+            }
+            int nb = 0;
+            for (int base = 0; base < nl; base += 32) {
+                int i = base + lane;
+                bool ok = false;
+                Zone z;
+                z.s = z.e = 0.0;
+                if (i < nl) {
+                    Ln l = load_line(g.lines + 5 * (size_t)(lo + i));
+                    ok = crop_line(l, vblx, vbly, vtrx, vtry);
+                    if (ok) {
+                        z = make_block(l, c0x, c0y, q);
+                        if (z.s != z.s || z.e != z.e) bad_nan = true;
+                    }
+                }
+                unsigned m = __ballot_sync(FULL, ok);
+                if (ok) {
+                    int pos = nb + __popc(m & ltmask);
+                    if (pos < sc.bcap) sc.blk[pos] = z;
+                }
+                nb += __popc(m);
+            }
+            __syncwarp();
+            if (nb > sc.bcap) {
+                out.status = TASK_OVERFLOW;
+                return out;
+            }
+            if (nb > 0) {
+                ng = subtract_blocks(G, ng, sc.blk, nb, Gn, sc.gcap, sc.bcap, lane);
+                if (ng < 0) {
+                    out.status = TASK_OVERFLOW;
+                    return out;
+                }
+                Zone *t = G;
+                G = Gn;
+                Gn = t;
+            }
+        }
+    }
+
+    uint32_t nacc = 0, nfill = 0;
+    int diag_last = 0;
+
+    for (int depth = 1; ng > 0; depth++) {
+        // ---- enumerate the union of the gaps' widened index ranges (pointdata.cpp:1522-1534)
+        const double dd = (double)depth;
+        int T = 0;
+        int run_max = -1;
+        for (int base = 0; base < ng; base += 32) {
+            int i = base + lane;
+            int lo = 0, hi = -1;
+            if (i < ng) {
+                Zone z = G[i];
+                lo = (int)ceil(sub(mul(z.s, sub(dd, 0.5)), 0.5));
+                hi = (int)floor(add(mul(z.e, add(dd, 0.5)), 0.5));
+                hi = min(hi, depth);
+            }
+            bool nonempty = (i < ng) && (lo <= hi);
+            int hv = nonempty ? hi : -1;
+            int imax = warp_incl_max(hv, lane);
+            int emax = __shfl_up_sync(FULL, imax, 1);
+            if (lane == 0) emax = -1;
+            emax = max(emax, run_max);
+            int st = max(lo, emax + 1);
+            int len = nonempty ? max(0, hi - st + 1) : 0;
+            int isum = warp_incl_sum(len, lane);
+            if (i < ng) {
+                sc.rstart[i] = st;
+                sc.rprefix[i] = T + isum - len;
+            }
+            T += __shfl_sync(FULL, isum, 31);
+            run_max = max(run_max, __shfl_sync(FULL, imax, 31));
+        }
+        if (lane == 0) sc.rprefix[ng] = T;
+        __syncwarp();
+
+        bool anyin = false;
+        int nbrow = 0;
+        for (int t0 = 0; t0 < T; t0 += 32) {
+            int t = t0 + lane;
+            bool act = t < T;
+            int ind = 0, gi = 0;
+            if (act) {
+                int lo = 0, hi = ng;  // last gi with rprefix[gi] <= t
+                while (hi - lo > 1) {
+                    int mid = (lo + hi) >> 1;
+                    if (sc.rprefix[mid] <= t) lo = mid; else hi = mid;
+                }
+                gi = lo;
+                ind = sc.rstart[gi] + (t - sc.rprefix[gi]);
+            }
+            int ox = xmajor ? depth : ind;
+            int oy = xmajor ? ind : depth;
+            int hx = cx + sx * ox, hy = cy + sy * oy;
+            bool ing = act && hx >= 0 && hx < g.cols && hy >= 0 && hy < g.rows;
+            anyin |= (__ballot_sync(FULL, ing) != 0);
+            uint8_t fl = 0;
+            int64_t c = (int64_t)hx * g.rows + hy;
+            if (ing) fl = xmajor ? g.cflag[c] : g.cflag_t[(int64_t)hy * g.cols + hx];
+            const bool haslines = (fl & 2) != 0;
+            uint32_t llo = 0;
+            int nl = 0;
+            if (haslines) {
+                llo = g.line_off[c];
+                nl = (int)(g.line_off[c + 1] - llo);
+            }
+            bool cand = false;
+            if (ing && (fl & 1)) {
+                // don't repeat axes / diagonals (pointdata.cpp:1551)
+                if ((ind != 0 || q == 0 || q == 1 || q == 5 || q == 6) && (ind != depth || q < 4)) {
+                    double di = (double)ind;
+                    for (int k = gi; k < ng; k++) {
+                        Zone z = G[k];
+                        if (di < mul(z.s, dd)) break;
+                        if (di <= mul(z.e, dd)) {
+                            cand = true;
+                            break;
+                        }
+                    }
+                }
+            }
+            double px = 0.0, py = 0.0;
+            if (cand) {
+                px = add(g.blx, mul(s, (double)hx));
+                py = add(g.bly, mul(s, (double)hy));
+                if (nl > 0 || g.maxdist != -1.0) {
+                    Ln l = make_line(c0x, c0y, px, py);
+                    if (g.maxdist != -1.0) {
+                        double w = sub(l.trx, l.blx), h = sub(l.try_, l.bly);
+                        double len = __dsqrt_rn(add(mul(w, w), mul(h, h)));
+                        if (len > g.maxdist) cand = false;
+                    }
+                    for (int j = 0; cand && j < nl; j++) {
+                        Ln wl = load_line(g.lines + 5 * (size_t)(llo + j));
+                        if (line_hits(l, wl, tol)) cand = false;
+                    }
+                }
+            }
+            unsigned am = __ballot_sync(FULL, cand);
+            // diagonal bins are stored by the reference as ONE run first..last (ngraph.cpp:243-259):
+            // cells between two accepted diagonal cells that were not accepted themselves still
+            // belong to the iterated adjacency ("fill-ins")
+            unsigned dm = __ballot_sync(FULL, cand && xmajor && ind == depth);
+            if (dm) {
+                if (diag_last > 0) {
+                    int gap = depth - 1 - diag_last;
+                    for (int d = diag_last + 1 + lane; d < depth; d += 32) {
+                        int fx = cx + sx * d, fy = cy + sy * d;
+                        int64_t fc = (int64_t)fx * g.rows + fy;
+                        if (EMIT) {
+                            uint64_t p = fill_off + nfill + (uint32_t)(d - diag_last - 1);
+                            e_ref[p] = ((uint32_t)fx << 16) | ((uint32_t)fy & 0xffffu);
+                            e_bin[p] = (uint8_t)(diagbin | 0x80);
+                        } else if (!(g.cflag[fc] & 1)) {
+                            ghostflag[fc] = 1;
+                        }
+                    }
+                    nfill += (uint32_t)gap;
+                }
+                diag_last = depth;
+            }
+            if (EMIT && cand) {
+                uint64_t p = acc_off + nacc + (uint32_t)__popc(am & ltmask);
+                e_ref[p] = ((uint32_t)hx << 16) | ((uint32_t)hy & 0xffffu);
+                e_bin[p] = (uint8_t)which_bin(sub(px, c0x), sub(py, c0y));
+            }
+            nacc += (uint32_t)__popc(am);
+
+            // every visited in-grid cell contributes its wall segments as blocks (pointdata.cpp:1558)
+            int isum = warp_incl_sum(nl, lane);
+            int tot = __shfl_sync(FULL, isum, 31);
+            if (tot > 0) {
+                int off = nbrow + isum - nl;
+                for (int j = 0; j < nl; j++) {
+                    Ln wl = load_line(g.lines + 5 * (size_t)(llo + j));
+                    Zone z = make_block(wl, c0x, c0y, q);
+                    if (z.s != z.s || z.e != z.e) bad_nan = true;
+                    if (off + j < sc.bcap) sc.blk[off + j] = z;
+                }
+                nbrow += tot;
+            }
+        }
+        __syncwarp();
+        if (nbrow > sc.bcap) {
+            out.status = TASK_OVERFLOW;
+            return out;
+        }
+        if (nbrow > 0) {
+            ng = subtract_blocks(G, ng, sc.blk, nbrow, Gn, sc.gcap, sc.bcap, lane);
+            if (ng < 0) {
+                out.status = TASK_OVERFLOW;
+                return out;
+            }
+            Zone *t = G;
+            G = Gn;
+            Gn = t;
+        }
+        if (!anyin) break;
+    }
+    if (__any_sync(FULL, bad_nan)) out.status = TASK_NAN;
+    out.nacc = nacc;
+    out.nfill = nfill;
+    return out;
+}
+
+struct SieveArgs {
+    GridDev g;
+    int64_t src_begin;      // first source ordinal of this launch's numbering
+    int64_t ntasks;         // tasks in this launch
+    const int64_t *tasklist;  // explicit global task ids (big mode) or nullptr = task range
+    int64_t task_begin;     // first global task id when tasklist == nullptr
+    int gcap, bcap;
+    Zone *gscratch;         // nullptr = shared memory
+    uint8_t *bigflag;       // [ntasks_total] 1 = task needs the big-capacity launch
+    // count outputs
+    uint32_t *cnt;          // [nsrc*8]
+    uint32_t *fillcnt;      // [nsrc*4]
+    uint8_t *ghostflag;     // [cells]
+    int64_t *overflow_list;
+    unsigned long long *n_overflow;
+    int *error_flag;
+    // emit inputs/outputs (offsets relative to the chunk's temp buffers)
+    const uint64_t *row_off;  // [nsrc+1] global row offsets
+    uint64_t chunk_base;      // subtracted from row_off
+    uint32_t *e_ref;
+    uint8_t *e_bin;
+};
+
+template <bool EMIT> __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_sieve(SieveArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    Scratch sc;
+    sc.gcap = a.gcap;
+    sc.bcap = a.bcap;
+    const size_t per_warp = (size_t)(2 * a.gcap + a.bcap) * sizeof(Zone) + (size_t)(2 * a.gcap + 2) * sizeof(int);
+    const bool big = a.gscratch != nullptr;
+    int64_t wglobal = (int64_t)blockIdx.x * WARPS_PER_BLOCK + wib;
+    int64_t wstride = (int64_t)gridDim.x * WARPS_PER_BLOCK;
+    {
+        unsigned char *base = big ? ((unsigned char *)a.gscratch + (size_t)wglobal * ((per_warp + 15) / 16 * 16))
+                                  : (smem + (size_t)wib * ((per_warp + 15) / 16 * 16));
+        sc.ga = (Zone *)base;
+        sc.gb = sc.ga + a.gcap;
+        sc.blk = sc.gb + a.gcap;
+        sc.rstart = (int *)(sc.blk + a.bcap);
+        sc.rprefix = sc.rstart + a.gcap;
+    }
+    for (int64_t w = wglobal; w < a.ntasks; w += wstride) {
+        int64_t task = a.tasklist ? a.tasklist[w] : (a.task_begin + w);
+        if (!big && a.bigflag[task]) continue;  // handled by the big-capacity launch
+        int64_t src_local = task >> 3;          // relative to src_begin
+        int q = (int)(task & 7);
+        int32_t ref = a.g.cellref[a.src_begin + src_local];
+        int cx = ref >> 16, cy = ref & 0xffff;
+        uint64_t acc_off = 0, fill_off = 0;
+        if (EMIT) {
+            uint64_t ro = a.row_off[src_local] - a.chunk_base;
+            uint32_t before = 0, all = 0;
+            for (int k = 0; k < 8; k++) {
+                uint32_t cv = a.cnt[src_local * 8 + k];
+                if (k < q) before += cv;
+                all += cv;
+            }
+            acc_off = ro + before;
+            uint32_t fb = 0;
+            for (int k = 0; k < 4 && k < q; k++) fb += a.fillcnt[src_local * 4 + k];
+            fill_off = ro + all + fb;
+        }
+        TaskOut o = sieve_task<EMIT>(a.g, cx, cy, q, sc, a.ghostflag, acc_off, fill_off, a.e_ref, a.e_bin);
+        if (lane == 0) {
+            if (o.status == TASK_OVERFLOW) {
+                if (!big) {
+                    a.bigflag[task] = 1;
+                    unsigned long long p = atomicAdd(a.n_overflow, 1ULL);
+                    a.overflow_list[p] = task;
+                } else {
+                    atomicExch(a.error_flag, VGA_ERR_CAPACITY);
+                }
+            } else if (o.status == TASK_NAN) {
+                atomicExch(a.error_flag, VGA_ERR_UNSUPPORTED);
+            } else if (!EMIT) {
+                a.cnt[src_local * 8 + q] = o.nacc;
+                if (q < 4) a.fillcnt[src_local * 4 + q] = o.nfill;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// per-source row sizes -> totals (accepted + fill-ins)
+__global__ void k_row_totals(const uint32_t *cnt, const uint32_t *fillcnt, int64_t nsrc, uint64_t *tot) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsrc) return;
+    uint64_t t = 0;
+    for (int k = 0; k < 8; k++) t += cnt[i * 8 + k];
+    for (int k = 0; k < 4; k++) t += fillcnt[i * 4 + k];
+    tot[i] = t;
+}
+
+// Connectivity, moments (double running sums in reference order), far distances, bin counts,
+// grid connections: one thread per source walking its unsorted row (pointdata.cpp:1463-1497,
+// 1735-1768).
+__global__ void k_node_stats(GridDev g, int64_t src_begin, int64_t chunk_first, int64_t nsrc_chunk,
+                             const uint64_t *row_off, uint64_t chunk_base, const uint32_t *cnt,
+                             const uint32_t *e_ref, const uint8_t *e_bin, int32_t *connectivity, double *sum_d,
+                             double *sum_d2, float *far_dist, int32_t *bin_count, uint8_t *gridconn) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsrc_chunk) return;
+    int64_t sl = chunk_first + i;  // source index relative to src_begin
+    int32_t ref = g.cellref[src_begin + sl];
+    int cx = ref >> 16, cy = ref & 0xffff;
+    float far[32];
+    int32_t bc[32];
+#pragma unroll
+    for (int b = 0; b < 32; b++) {
+        far[b] = 0.0f;
+        bc[b] = 0;
+    }
+    uint64_t beg = row_off[sl] - chunk_base, end = row_off[sl + 1] - chunk_base;
+    uint32_t nacc = 0;
+    for (int k = 0; k < 8; k++) nacc += cnt[sl * 8 + k];
+    double td = 0.0, td2 = 0.0;
+    uint8_t gc = 0;
+    for (uint64_t e = beg; e < end; e++) {
+        uint32_t r = e_ref[e];
+        int b = e_bin[e] & 31;
+        int dx = (int)(r >> 16) - cx, dy = (int)(r & 0xffff) - cy;
+        if (e - beg < nacc) {
+            double fx = (double)dx, fy = (double)dy;
+            double d = mul(__dsqrt_rn(add(mul(fx, fx), mul(fy, fy))), g.spacing);
+            if (d > (double)far[b]) far[b] = (float)d;
+            td = add(td, d);
+            td2 = add(td2, mul(d, d));
+            bc[b]++;
+        }
+        if (dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1) {
+            // neighbour i of the 8-neighbourhood (E, NE, N, NW, W, SW, S, SE) is looked up in bin 4i
+            const int idx_of[9] = {5, 6, 7, 4, -1, 0, 3, 2, 1};  // [(dy+1)*3 + (dx+1)]
+            int idx = idx_of[(dy + 1) * 3 + (dx + 1)];
+            if (idx >= 0 && b == idx * 4) gc |= (uint8_t)(1 << idx);
+        }
+    }
+    connectivity[sl] = (int32_t)nacc;
+    sum_d[sl] = td;
+    sum_d2[sl] = td2;
+    for (int b = 0; b < 32; b++) {
+        far_dist[sl * 32 + b] = far[b];
+        bin_count[sl * 32 + b] = bc[b];
+    }
+    gridconn[sl] = gc;
+}
+
+// sort keys: col<<6 | accepted<<5 | bin   (col = ordinal of a filled cell, or N + ghost rank)
+__global__ void k_make_keys(GridDev g, const uint32_t *e_ref, const uint8_t *e_bin, uint64_t n_entries,
+                            const int32_t *ghost_rank, uint32_t *keys) {
+    uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_entries) return;
+    uint32_t r = e_ref[e];
+    uint8_t b = e_bin[e];
+    int64_t c = (int64_t)(r >> 16) * g.rows + (r & 0xffff);
+    int32_t ord = g.cellord[c];
+    uint32_t col = (ord >= 0) ? (uint32_t)ord : (uint32_t)(g.n + ghost_rank[c]);
+    keys[e] = (col << 6) | ((b & 0x80) ? 0u : 32u) | (uint32_t)(b & 31);
+}
+
+__global__ void k_ghost_mark_to_int(const uint8_t *flag, int64_t cells, int32_t *out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cells) out[i] = flag[i] ? 1 : 0;
+}
+
+__global__ void k_rebase(const uint64_t *in, int64_t n, uint64_t base, uint64_t *out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] - base;
+}
+
+inline unsigned blocks_for(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+size_t per_warp_bytes(int gcap, int bcap) {
+    size_t b = (size_t)(2 * gcap + bcap) * sizeof(Zone) + (size_t)(2 * gcap + 2) * sizeof(int);
+    return (b + 15) / 16 * 16;
+}
+
+int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+}  // namespace
+
+int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t src_end, vga_graph **out) {
+    cudaStream_t st = ctx->stream;
+    const int64_t N = dg->n;
+    if (src_end < 0 || src_end > N) src_end = N;
+    if (src_begin < 0) src_begin = 0;
+    if (src_begin > src_end) src_begin = src_end;
+    const int64_t nsrc = src_end - src_begin;
+    if (N >= ((int64_t)1 << 26) - 65536) {
+        set_error("vga_graph_build: more than 2^26 cells is not supported");
+        return VGA_ERR_UNSUPPORTED;
+    }
+
+    GridDev g;
+    g.cols = dg->cols;
+    g.rows = dg->rows;
+    g.spacing = dg->spacing;
+    g.blx = dg->bl_x;
+    g.bly = dg->bl_y;
+    g.maxdist = dg->maxdist;
+    g.cflag = dg->cflag.p;
+    g.cflag_t = dg->cflag_t.p;
+    g.line_off = dg->line_off.p;
+    g.lines = dg->lines.p;
+    g.cellord = dg->cellord.p;
+    g.cellref = dg->cellref.p;
+    g.n = N;
+
+    std::unique_ptr<vga_graph> gr(new vga_graph());
+    gr->ctx = ctx;
+    gr->n = N;
+    gr->src_begin = src_begin;
+    gr->src_end = src_end;
+    gr->has_bins = true;
+    gr->has_stats = true;
+    gr->h_refs = dg->h_cellref;
+
+    Timing &tm = ctx->timing;
+    StageTimer kt(ctx, 0, &tm.kernel_ms);
+    StageTimer mt(ctx, 2, &tm.main_kernel_ms);
+
+    const int64_t ntasks = nsrc * 8;
+    DevBuf<uint32_t> cnt, fillcnt;
+    DevBuf<uint8_t> ghostflag, bigflag;
+    DevBuf<int64_t> overflow_list;
+    DevBuf<unsigned long long> n_overflow;
+    DevBuf<int> error_flag;
+    DevBuf<uint64_t> row_tot, row_off;
+    VGA_TRY(cnt.alloc_zero((size_t)nsrc * 8 + 8, st));
+    VGA_TRY(fillcnt.alloc_zero((size_t)nsrc * 4 + 4, st));
+    VGA_TRY(ghostflag.alloc_zero((size_t)dg->cells + 1, st));
+    VGA_TRY(bigflag.alloc_zero((size_t)ntasks + 1, st));
+    VGA_TRY(overflow_list.alloc((size_t)ntasks + 1));
+    VGA_TRY(n_overflow.alloc_zero(1, st));
+    VGA_TRY(error_flag.alloc_zero(1, st));
+    VGA_TRY(row_tot.alloc((size_t)nsrc + 1));
+    VGA_TRY(row_off.alloc((size_t)nsrc + 1));
+    VGA_TRY(gr->rowptr.alloc((size_t)nsrc + 1));
+    VGA_TRY(gr->connectivity.alloc((size_t)nsrc + 1));
+    VGA_TRY(gr->sum_d.alloc((size_t)nsrc + 1));
+    VGA_TRY(gr->sum_d2.alloc((size_t)nsrc + 1));
+    VGA_TRY(gr->far_dist.alloc((size_t)nsrc * 32 + 32));
+    VGA_TRY(gr->bin_count.alloc((size_t)nsrc * 32 + 32));
+    VGA_TRY(gr->gridconn.alloc((size_t)nsrc + 1));
+
+    const int gcap = (int)ctx->opt.sieve_gcap;
+    const int bcap = next_pow2((int)ctx->opt.sieve_bcap);
+    const int big_gcap = (int)ctx->opt.sieve_big_gcap;
+    const int big_bcap = next_pow2((int)ctx->opt.sieve_big_bcap);
+    const size_t smem_bytes = per_warp_bytes(gcap, bcap) * WARPS_PER_BLOCK;
+    if (smem_bytes > ctx->smem_optin) {
+        set_error("vga_graph_build: sieve shared-memory slices exceed the device limit");
+        return VGA_ERR_INVALID;
+    }
+    VGA_CUDA(cudaFuncSetAttribute(k_sieve<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    VGA_CUDA(cudaFuncSetAttribute(k_sieve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+
+    SieveArgs a;
+    a.g = g;
+    a.src_begin = src_begin;
+    a.ntasks = ntasks;
+    a.tasklist = nullptr;
+    a.task_begin = 0;
+    a.gcap = gcap;
+    a.bcap = bcap;
+    a.gscratch = nullptr;
+    a.bigflag = bigflag.p;
+    a.cnt = cnt.p;
+    a.fillcnt = fillcnt.p;
+    a.ghostflag = ghostflag.p;
+    a.overflow_list = overflow_list.p;
+    a.n_overflow = n_overflow.p;
+    a.error_flag = error_flag.p;
+    a.row_off = nullptr;
+    a.chunk_base = 0;
+    a.e_ref = nullptr;
+    a.e_bin = nullptr;
+
+    // big-capacity scratch (allocated on demand)
+    DevBuf<unsigned char> big_scratch;
+    const int big_warps = ctx->sm_count * WARPS_PER_BLOCK;
+    unsigned long long h_over = 0;
+    int h_err = 0;
+
+    kt.start();
+    mt.start();
+    // ---- pass 1: count
+    if (ntasks > 0) {
+        k_sieve<false><<<blocks_for(ntasks, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, smem_bytes, st>>>(a);
+        tm.launches++;
+        tm.main_launches++;
+        VGA_CUDA(cudaGetLastError());
+    }
+    VGA_CUDA(cudaMemcpyAsync(&h_over, n_overflow.p, sizeof(h_over), cudaMemcpyDeviceToHost, st));
+    VGA_CUDA(cudaStreamSynchronize(st));
+    if (h_over > 0) {
+        VGA_TRY(big_scratch.alloc(per_warp_bytes(big_gcap, big_bcap) * (size_t)big_warps));
+        SieveArgs b = a;
+        b.ntasks = (int64_t)h_over;
+        b.tasklist = overflow_list.p;
+        b.gcap = big_gcap;
+        b.bcap = big_bcap;
+        b.gscratch = (Zone *)big_scratch.p;
+        k_sieve<false><<<ctx->sm_count, WARPS_PER_BLOCK * 32, 0, st>>>(b);
+        tm.launches++;
+        tm.main_launches++;
+        VGA_CUDA(cudaGetLastError());
+    }
+    mt.stop();
+    VGA_CUDA(cudaMemcpyAsync(&h_err, error_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    VGA_CUDA(cudaStreamSynchronize(st));
+    if (h_err != 0) {
+        set_error(h_err == VGA_ERR_CAPACITY ? "vga_graph_build: gap/block capacity exceeded even in big mode"
+                                            : "vga_graph_build: NaN angular block (a wall passes exactly through a cell "
+                                              "centre); the reference's result is unspecified for this input");
+        return h_err;
+    }
+
+    // ---- ghosts: unfilled cells covered by a diagonal first..last run
+    DevBuf<int32_t> ghost_rank;
+    VGA_TRY(ghost_rank.alloc((size_t)dg->cells + 1));
+    {
+        DevBuf<int32_t> gi;
+        VGA_TRY(gi.alloc((size_t)dg->cells + 1));
+        k_ghost_mark_to_int<<<blocks_for(dg->cells, 256), 256, 0, st>>>(ghostflag.p, dg->cells, gi.p);
+        tm.launches++;
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, gi.p, ghost_rank.p, (int)dg->cells, st);
+        DevBuf<unsigned char> tmp;
+        VGA_TRY(tmp.alloc(tb + 16));
+        cub::DeviceScan::ExclusiveSum(tmp.p, tb, gi.p, ghost_rank.p, (int)dg->cells, st);
+        tm.launches++;
+        int32_t last_rank = 0, last_flag = 0;
+        if (dg->cells > 0) {
+            VGA_CUDA(cudaMemcpyAsync(&last_rank, ghost_rank.p + dg->cells - 1, 4, cudaMemcpyDeviceToHost, st));
+            VGA_CUDA(cudaMemcpyAsync(&last_flag, gi.p + dg->cells - 1, 4, cudaMemcpyDeviceToHost, st));
+        }
+        VGA_CUDA(cudaStreamSynchronize(st));
+        gr->ghosts = (int64_t)last_rank + last_flag;
+        if (gr->ghosts > 0) {
+            std::vector<uint8_t> hf((size_t)dg->cells);
+            VGA_CUDA(cudaMemcpy(hf.data(), ghostflag.p, (size_t)dg->cells, cudaMemcpyDeviceToHost));
+            for (int64_t c = 0; c < dg->cells; c++)
+                if (hf[c]) gr->h_refs.push_back((int32_t)(((uint32_t)(c / dg->rows) << 16) | (uint32_t)(c % dg->rows)));
+        }
+    }
+
+    // ---- row offsets
+    if (nsrc > 0) {
+        k_row_totals<<<blocks_for(nsrc, 256), 256, 0, st>>>(cnt.p, fillcnt.p, nsrc, row_tot.p);
+        tm.launches++;
+    }
+    VGA_CUDA(cudaMemsetAsync(row_tot.p + nsrc, 0, sizeof(uint64_t), st));
+    {
+        size_t tb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tb, row_tot.p, row_off.p, (int)(nsrc + 1), st);
+        DevBuf<unsigned char> tmp;
+        VGA_TRY(tmp.alloc(tb + 16));
+        cub::DeviceScan::ExclusiveSum(tmp.p, tb, row_tot.p, row_off.p, (int)(nsrc + 1), st);
+        tm.launches++;
+        VGA_CUDA(cudaStreamSynchronize(st));
+    }
+    std::vector<uint64_t> h_off((size_t)nsrc + 1);
+    VGA_CUDA(cudaMemcpy(h_off.data(), row_off.p, sizeof(uint64_t) * (nsrc + 1), cudaMemcpyDeviceToHost));
+    const uint64_t total = h_off[nsrc];
+    gr->entries = (int64_t)total;
+    VGA_TRY(gr->adj.alloc((size_t)total + 1));
+    VGA_CUDA(cudaMemcpyAsync(gr->rowptr.p, row_off.p, sizeof(uint64_t) * (nsrc + 1), cudaMemcpyDeviceToDevice, st));
+
+    // ---- pass 2 in chunks of sources: emit, node stats, keys, segmented sort into the final rows
+    const uint64_t chunk_cap = (uint64_t)std::max<int64_t>(ctx->opt.build_chunk_entries, 1 << 20);
+    uint64_t max_chunk = 0;
+    {
+        int64_t i = 0;
+        while (i < nsrc) {
+            int64_t j = i + 1;
+            while (j < nsrc && h_off[j + 1] - h_off[i] <= chunk_cap) j++;
+            max_chunk = std::max<uint64_t>(max_chunk, h_off[j] - h_off[i]);
+            i = j;
+        }
+    }
+    if (max_chunk >= ((uint64_t)1 << 31)) {
+        set_error("vga_graph_build: a single row chunk exceeds 2^31 entries");
+        return VGA_ERR_CAPACITY;
+    }
+    DevBuf<uint32_t> e_ref, keys;
+    DevBuf<uint8_t> e_bin;
+    DevBuf<uint64_t> seg_off;
+    DevBuf<unsigned char> sort_tmp;
+    VGA_TRY(e_ref.alloc((size_t)max_chunk + 1));
+    VGA_TRY(e_bin.alloc((size_t)max_chunk + 1));
+    VGA_TRY(keys.alloc((size_t)max_chunk + 1));
+    VGA_TRY(seg_off.alloc((size_t)nsrc + 1));
+
+    int64_t i = 0;
+    while (i < nsrc) {
+        int64_t j = i + 1;
+        while (j < nsrc && h_off[j + 1] - h_off[i] <= chunk_cap) j++;
+        const int64_t ns = j - i;
+        const uint64_t base = h_off[i], cnt_e = h_off[j] - h_off[i];
+        if (ctx->cancel && ctx->cancel(ctx->user)) {
+            set_error("cancelled");
+            return VGA_ERR_CANCELLED;
+        }
+        SieveArgs e = a;
+        e.src_begin = src_begin + i;
+        e.ntasks = ns * 8;
+        e.task_begin = 0;
+        e.bigflag = bigflag.p + i * 8;
+        e.cnt = cnt.p + i * 8;
+        e.fillcnt = fillcnt.p + i * 4;
+        e.row_off = row_off.p + i;
+        e.chunk_base = base;
+        e.e_ref = e_ref.p;
+        e.e_bin = e_bin.p;
+        mt.start();
+        k_sieve<true><<<blocks_for(ns * 8, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, smem_bytes, st>>>(e);
+        tm.launches++;
+        tm.main_launches++;
+        VGA_CUDA(cudaGetLastError());
+        if (h_over > 0) {
+            // big tasks of this chunk: the overflow list holds global task ids; filter on host
+            // (rare path) -- re-run them with global scratch
+            std::vector<int64_t> all((size_t)h_over);
+            VGA_CUDA(cudaMemcpyAsync(all.data(), overflow_list.p, sizeof(int64_t) * h_over, cudaMemcpyDeviceToHost, st));
+            VGA_CUDA(cudaStreamSynchronize(st));
+            std::vector<int64_t> mine;
+            for (int64_t t : all)
+                if (t >= i * 8 && t < j * 8) mine.push_back(t - i * 8);
+            if (!mine.empty()) {
+                DevBuf<int64_t> dl;
+                VGA_TRY(dl.alloc(mine.size()));
+                VGA_CUDA(cudaMemcpyAsync(dl.p, mine.data(), sizeof(int64_t) * mine.size(), cudaMemcpyHostToDevice, st));
+                SieveArgs b = e;
+                b.ntasks = (int64_t)mine.size();
+                b.tasklist = dl.p;
+                b.gcap = big_gcap;
+                b.bcap = big_bcap;
+                b.gscratch = (Zone *)big_scratch.p;
+                k_sieve<true><<<ctx->sm_count, WARPS_PER_BLOCK * 32, 0, st>>>(b);
+                tm.launches++;
+                tm.main_launches++;
+                VGA_CUDA(cudaGetLastError());
+                VGA_CUDA(cudaStreamSynchronize(st));
+            }
+        }
+        mt.stop();
+        k_node_stats<<<blocks_for(ns, 128), 128, 0, st>>>(g, src_begin, i, ns, row_off.p, base, cnt.p, e_ref.p, e_bin.p,
+                                                         gr->connectivity.p, gr->sum_d.p, gr->sum_d2.p,
+                                                         gr->far_dist.p, gr->bin_count.p, gr->gridconn.p);
+        tm.launches++;
+        VGA_CUDA(cudaGetLastError());
+        if (cnt_e > 0) {
+            k_make_keys<<<blocks_for((int64_t)cnt_e, 256), 256, 0, st>>>(g, e_ref.p, e_bin.p, cnt_e, ghost_rank.p, keys.p);
+            tm.launches++;
+            k_rebase<<<blocks_for(ns + 1, 256), 256, 0, st>>>(row_off.p + i, ns + 1, base, seg_off.p);
+            tm.launches++;
+            size_t tb = 0;
+            cub::DeviceSegmentedSort::SortKeys(nullptr, tb, keys.p, gr->adj.p + base, (int)cnt_e, (int)ns, seg_off.p,
+                                               seg_off.p + 1, st);
+            if (tb + 16 > sort_tmp.n) VGA_TRY(sort_tmp.alloc(tb + 16));
+            VGA_CUDA(cub::DeviceSegmentedSort::SortKeys(sort_tmp.p, tb, keys.p, gr->adj.p + base, (int)cnt_e, (int)ns,
+                                                        seg_off.p, seg_off.p + 1, st));
+            tm.launches += 3;
+        }
+        VGA_CUDA(cudaGetLastError());
+        if (ctx->progress) ctx->progress(ctx->user, j, nsrc);
+        i = j;
+    }
+    kt.stop();
+    VGA_CUDA(cudaStreamSynchronize(st));
+    VGA_CUDA(cudaGetLastError());
+    // algorithmic bytes of construction: 8 B per accepted edge + 40 B per wall segment
+    tm.algo_bytes = 8.0 * (double)total + 40.0 * (double)dg->nseg;
+    *out = gr.release();
+    return VGA_OK;
+}
+
+}  // namespace vga

@@ -1,0 +1,175 @@
+// Internal declarations shared by the CUDA translation units of libvga_b200.so.
+// Public surface: include/vga_b200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/vga_b200.h"
+
+namespace vga {
+
+void set_error(const std::string &msg);
+
+#define VGA_CUDA(call)                                                                            \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            vga::set_error(std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + \
+                           ":" + std::to_string(__LINE__) + ")");                                 \
+            return VGA_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+#define VGA_TRY(call)               \
+    do {                            \
+        int rc__ = (call);          \
+        if (rc__ != VGA_OK) return rc__; \
+    } while (0)
+
+// RAII device buffer (cudaMalloc / cudaFree); zero-size allocations are represented by nullptr.
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept {
+        if (this != &o) {
+            release();
+            p = o.p;
+            n = o.n;
+            o.p = nullptr;
+            o.n = 0;
+        }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    int alloc(size_t count) {
+        release();
+        if (count == 0) return VGA_OK;
+        VGA_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+        n = count;
+        return VGA_OK;
+    }
+    int alloc_zero(size_t count, cudaStream_t s) {
+        VGA_TRY(alloc(count));
+        if (count) VGA_CUDA(cudaMemsetAsync(p, 0, count * sizeof(T), s));
+        return VGA_OK;
+    }
+};
+
+struct Timing {
+    double h2d_ms = 0, kernel_ms = 0, d2h_ms = 0, main_kernel_ms = 0, algo_bytes = 0;
+    int64_t launches = 0, main_launches = 0;
+};
+
+// Tunables (vga_ctx_set_option / environment)
+struct Options {
+    int64_t bfs_mode = 2;        // 0 push only, 1 pull only, 2 direction-optimising hybrid
+    int64_t bfs_chunk = 0;       // batches (of 64 sources) in flight; 0 = auto from free memory
+    int64_t sieve_gcap = 48;     // shared-memory gap capacity per warp
+    int64_t sieve_bcap = 192;    // shared-memory block capacity per warp
+    int64_t sieve_big_gcap = 4096;
+    int64_t sieve_big_bcap = 32768;
+    int64_t build_chunk_entries = (int64_t)1 << 30;
+    int64_t pull_alpha = 4;      // switch to pull when frontier edges*alpha > unvisited edges (per batch)
+};
+
+}  // namespace vga
+
+struct vga_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    vga::Options opt;
+    vga::Timing timing;
+    vga_progress_fn progress = nullptr;
+    vga_cancel_fn cancel = nullptr;
+    void *user = nullptr;
+};
+
+struct vga_dgrid {
+    vga_ctx *ctx = nullptr;
+    int32_t cols = 0, rows = 0;
+    double spacing = 0, bl_x = 0, bl_y = 0, maxdist = -1.0;
+    int64_t cells = 0, n = 0, nseg = 0;
+    vga::DevBuf<uint8_t> cflag;    // [cells] x-major: bit0 FILLED, bit1 has lines
+    vga::DevBuf<uint8_t> cflag_t;  // [cells] y-major copy (index y*cols+x) for the y-major octants
+    vga::DevBuf<uint32_t> line_off;
+    vga::DevBuf<double> lines;
+    vga::DevBuf<int32_t> cellord;  // [cells] ordinal or -1
+    vga::DevBuf<int32_t> cellref;  // [n] packed PixelRef per ordinal
+    std::vector<int32_t> h_cellref;
+};
+
+struct vga_graph {
+    vga_ctx *ctx = nullptr;
+    int64_t n = 0;        // filled cells
+    int64_t ghosts = 0;   // ghost vertices
+    int64_t src_begin = 0, src_end = 0;
+    int64_t entries = 0;  // adjacency entries of rows [src_begin, src_end)
+    // rows sorted by column; packed entry = col<<6 | accepted<<5 | bin
+    vga::DevBuf<uint64_t> rowptr;  // [rows+1], local (starts at 0)
+    vga::DevBuf<uint32_t> adj;     // [entries]
+    bool has_bins = false;
+    // node stats (only for built graphs)
+    bool has_stats = false;
+    vga::DevBuf<int32_t> connectivity;
+    vga::DevBuf<double> sum_d, sum_d2;
+    vga::DevBuf<float> far_dist;    // [rows*32]
+    vga::DevBuf<int32_t> bin_count; // [rows*32]
+    vga::DevBuf<uint8_t> gridconn;
+    std::vector<int32_t> h_refs;    // N + G packed PixelRefs (host)
+    // derived analysis structures, built lazily
+    vga::DevBuf<uint64_t> t_rowptr; // transpose (in-edges), [n+1]
+    vga::DevBuf<uint32_t> t_col;    // [entries to filled targets]
+    bool has_transpose = false;
+    int64_t t_entries = 0;
+};
+
+namespace vga {
+// makegraph.cu
+int build_graph(vga_ctx *ctx, const vga_dgrid *g, int64_t src_begin, int64_t src_end, vga_graph **out);
+// bfs.cu
+int ensure_transpose(vga_ctx *ctx, vga_graph *g);
+int run_global(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_t src_end, int32_t *total_nodes,
+               int64_t *total_depth, int32_t *dist, int32_t max_levels, int32_t *levels_used);
+// local.cu
+int run_local(vga_ctx *ctx, vga_graph *g, int64_t src_begin, int64_t src_end, int64_t *cluster, int32_t *k,
+              int32_t *total, float *control);
+
+// helpers for timing: record an event pair around a region on ctx->stream
+struct StageTimer {
+    vga_ctx *ctx;
+    cudaEvent_t a, b;
+    double *acc;
+    bool on = false;
+    StageTimer(vga_ctx *c, int slot, double *accum) : ctx(c), a(c->ev[slot]), b(c->ev[slot + 1]), acc(accum) {}
+    void start() {
+        cudaEventRecord(a, ctx->stream);
+        on = true;
+    }
+    // stop() synchronises the stream
+    void stop() {
+        if (!on) return;
+        cudaEventRecord(b, ctx->stream);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        *acc += ms;
+        on = false;
+    }
+};
+}  // namespace vga

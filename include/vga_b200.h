@@ -1,0 +1,175 @@
+/* vga_b200.h -- C ABI of libvga_b200.so: the B200 (sm_100a) implementation of depthmapX's
+ * visibility-graph hot path.  Plain C: pointers and sizes only, no C++/torch types.
+ *
+ * What each entry point replaces in the reference (/root/reference, depthmapX 0.8.0):
+ *
+ *   vga_graph_build*      PointMap::sparkGraph2 -> sparkPixel2 -> sieve2 -> sparkSieve2
+ *                         salalib/pointdata.cpp:1246-1565, salalib/sparksieve2.cpp:33-173,
+ *                         whichbin salalib/pointdata.h:432-520, Node::make/Bin::make
+ *                         salalib/ngraph.cpp:27-58,234-304 (adjacency content + iteration set),
+ *                         addGridConnections salalib/pointdata.cpp:1735-1768
+ *   vga_graph_from_csr    the adjacency a loaded .graph holds in Point::m_node
+ *                         (Node::first/next iteration, salalib/ngraph.cpp:158-191,392-416)
+ *   vga_global            VGAVisualGlobal::run BFS part + extractUnseen
+ *                         salalib/vgamodules/vgavisualglobal.cpp:66-130, 218-240
+ *   vga_global_attributes the formula stage of VGAVisualGlobal::run :131-193 (host, glibc libm)
+ *   vga_local             VGAVisualLocal::run salalib/vgamodules/vgavisuallocal.cpp:41-81
+ *   vga_local_attributes  the formula stage :84-96
+ *
+ * Conventions: every function returns 0 on success and a negative vga_status otherwise;
+ * vga_last_error() gives the message of the last failure on the calling thread.  There is NO CPU
+ * fallback: without a CUDA device every compute entry point fails with VGA_ERR_NO_DEVICE.
+ * Unsupported inputs (merged pixels, CONTEXTFILLED cells, NaN blocks, N >= 2^27) are errors.
+ * One process drives one GPU (vga_ctx_create(device)); multi-GPU runs shard sources across
+ * processes (src_begin/src_end arguments) and exchange shards outside this library.
+ *
+ * Vertex numbering: "ordinal" = index of a FILLED cell in x-major order (for x: for y:), the
+ * iteration order of every hot loop of the reference and of its attribute table
+ * (AttributeKey = int(PixelRef), salalib/pixelref.h:81-82).  "Ghost" vertices (ordinals
+ * N..N+G-1) are unfilled cells covered by a diagonal bin's first..last run
+ * (Bin::make, salalib/ngraph.cpp:243-259); they have no row of their own, are never BFS
+ * sources or counted, but are members of neighbourhoods in the local measures.
+ */
+#ifndef VGA_B200_H
+#define VGA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    VGA_OK = 0,
+    VGA_ERR_INVALID = -1,     /* bad argument */
+    VGA_ERR_NO_DEVICE = -2,   /* no CUDA device / driver: there is no CPU path */
+    VGA_ERR_CUDA = -3,        /* CUDA runtime error, see vga_last_error() */
+    VGA_ERR_UNSUPPORTED = -4, /* input outside the supported subset (see header comment) */
+    VGA_ERR_CAPACITY = -5,    /* a fixed-capacity device structure overflowed */
+    VGA_ERR_CANCELLED = -6    /* the cancel callback returned non-zero */
+} vga_status;
+
+typedef struct vga_ctx vga_ctx;
+typedef struct vga_graph vga_graph;
+
+/* Flat image of what PointMap holds when sparkGraph2 starts (after blockLines + makePoints):
+ * Point::m_state and Point::m_lines for every cell (salalib/point.h:32-64). */
+typedef struct {
+    int32_t cols, rows;       /* PointMap::m_cols, m_rows */
+    double spacing;           /* m_spacing */
+    double bl_x, bl_y;        /* m_bottom_left = centre of cell (0,0) */
+    double maxdist;           /* sparkGraph2's maxdist, -1.0 = unlimited */
+    const uint16_t *state;    /* [cols*rows] index x*rows+y; FILLED = 0x0002 */
+    const uint32_t *line_off; /* [cols*rows+1] offsets into lines */
+    const double *lines;      /* 5 doubles per cropped segment: bl.x, bl.y, tr.x, tr.y, parity */
+} vga_grid;
+
+/* Progress / cancel callbacks (Communicator::CommPostMessage / IsCancelled, genlib/comm.h).
+ * progress(user, done, total); cancel(user) != 0 aborts with VGA_ERR_CANCELLED. */
+typedef void (*vga_progress_fn)(void *user, int64_t done, int64_t total);
+typedef int (*vga_cancel_fn)(void *user);
+
+/* Stage timings of the most recent call on a context, CUDA-event measured (milliseconds). */
+typedef struct {
+    double h2d_ms;     /* host->device copies of inputs */
+    double kernel_ms;  /* all kernels of the call */
+    double d2h_ms;     /* device->host copies of results */
+    double main_kernel_ms;   /* the dominant kernel(s) only: BFS level kernels / sieve passes / local */
+    int64_t launches;  /* kernels launched by the call */
+    int64_t main_launches;
+    double algo_bytes; /* algorithmic bytes of the dominant kernel(s), DESIGN.md formula */
+} vga_timing;
+
+const char *vga_last_error(void);
+const char *vga_version(void);
+/* number of visible CUDA devices; 0 when there is no driver/device (never an error) */
+int vga_device_count(void);
+
+int vga_ctx_create(int device, vga_ctx **out);
+void vga_ctx_destroy(vga_ctx *ctx);
+int vga_ctx_set_callbacks(vga_ctx *ctx, vga_progress_fn progress, vga_cancel_fn cancel, void *user);
+/* tuning knobs, also readable from the environment (VGA_BFS_MODE, VGA_BFS_CHUNK, ...);
+ * unknown keys are VGA_ERR_INVALID */
+int vga_ctx_set_option(vga_ctx *ctx, const char *key, int64_t value);
+int vga_ctx_timing(const vga_ctx *ctx, vga_timing *out);
+/* cudaDeviceSynchronize + error check */
+int vga_ctx_sync(vga_ctx *ctx);
+
+/* ---- construction (makegraph) ------------------------------------------------------------- */
+
+/* Build the visibility graph rows of the sources with ordinals [src_begin, src_end)
+ * (src_end < 0 = all).  The graph always knows all N cells. */
+int vga_graph_build(vga_ctx *ctx, const vga_grid *grid, int64_t src_begin, int64_t src_end, vga_graph **out);
+
+/* Two-step variant for measurements with inputs resident in HBM: upload once, build many times. */
+typedef struct vga_dgrid vga_dgrid;
+int vga_grid_upload(vga_ctx *ctx, const vga_grid *grid, vga_dgrid **out);
+void vga_dgrid_free(vga_dgrid *g);
+int vga_graph_build_resident(vga_ctx *ctx, const vga_dgrid *grid, int64_t src_begin, int64_t src_end,
+                             vga_graph **out);
+
+/* Adopt an adjacency that already exists (e.g. flattened from the Nodes of a loaded .graph, or the
+ * concatenation of per-rank shards).  n_cells filled cells, n_ghosts ghost vertices, rows sorted or
+ * not; col values < n_cells + n_ghosts.  bin may be NULL. */
+int vga_graph_from_csr(vga_ctx *ctx, int64_t n_cells, int64_t n_ghosts, const uint64_t *rowptr,
+                       const uint32_t *col, const uint8_t *bin, vga_graph **out);
+
+void vga_graph_free(vga_graph *g);
+
+int64_t vga_graph_num_cells(const vga_graph *g);  /* N */
+int64_t vga_graph_num_ghosts(const vga_graph *g); /* G */
+int64_t vga_graph_num_edges(const vga_graph *g);  /* iterated adjacency entries held */
+int64_t vga_graph_src_begin(const vga_graph *g);
+int64_t vga_graph_src_end(const vga_graph *g);
+
+/* Rows src_begin..src_end, each sorted by column ordinal (= PixelRef x-major order, ghosts last).
+ * rowptr has (src_end-src_begin+1) entries starting at 0.  accepted[e] = 1 for cells the sieve
+ * accepted (they count towards Connectivity and the moments), 0 for diagonal first..last run
+ * fill-ins.  Any output pointer may be NULL. */
+int vga_graph_csr(const vga_graph *g, uint64_t *rowptr, uint32_t *col, uint8_t *bin, uint8_t *accepted);
+/* Packed PixelRef ((x<<16)+(y&0xffff)) of every vertex: N cells then G ghosts. */
+int vga_graph_cell_refs(const vga_graph *g, int32_t *ref);
+/* Per source row: what sparkPixel2 stores besides the pixel lists.  connectivity = neighbourhood_size,
+ * sum_d / sum_d2 = total_dist / total_dist_sqr (double running sums in reference order),
+ * far_bin_dists [rows*32] floats, bin_count [rows*32] (accepted pixels per bin),
+ * grid_connections [rows] bytes.  Any pointer may be NULL. */
+int vga_graph_node_stats(const vga_graph *g, int32_t *connectivity, double *sum_d, double *sum_d2,
+                         float *far_bin_dists, int32_t *bin_count, uint8_t *grid_connections);
+
+/* ---- analysis ----------------------------------------------------------------------------- */
+
+/* All-sources BFS for sources [src_begin, src_end) over the (complete) graph.  radius -1 = n.
+ * Outputs (host): total_nodes[k], total_depth[k], dist[k*max_levels] level histogram (level 0 =
+ * the source itself), *levels_used = 1 + deepest non-empty level over these sources.  If the
+ * histogram needs more than max_levels columns the call fails with VGA_ERR_CAPACITY and sets
+ * *levels_used to the required value. */
+int vga_global(vga_ctx *ctx, const vga_graph *g, int radius, int64_t src_begin, int64_t src_end,
+               int32_t *total_nodes, int64_t *total_depth, int32_t *dist, int32_t max_levels,
+               int32_t *levels_used);
+
+/* Formula stage (host, FP64 -> float exactly as AttributeRow::setValue stores them); -1 sentinels
+ * as in the reference.  Any output may be NULL. */
+int vga_global_attributes(int64_t n, const int32_t *total_nodes, const int64_t *total_depth, const int32_t *dist,
+                          int32_t max_levels, float *node_count, float *mean_depth, float *integ_hh,
+                          float *integ_pv, float *integ_tk, float *entropy, float *rel_entropy);
+
+/* Local measures for cells [src_begin, src_end): cluster = sum_u |iter(N(u)) n N(v)|, k = |N(v)|,
+ * total = |U_u iter(N(u))|, control = float32 running sum of 1/retro_size(u) in PixelRef order. */
+int vga_local(vga_ctx *ctx, const vga_graph *g, int64_t src_begin, int64_t src_end, int64_t *cluster,
+              int32_t *k, int32_t *total, float *control);
+int vga_local_attributes(int64_t n, const int64_t *cluster, const int32_t *k, const int32_t *total,
+                         const float *control, float *clustering, float *control_out, float *controllability);
+
+/* ---- device-resident access for multi-GPU plumbing (pointers are CUDA device pointers) ------ */
+
+/* Device pointers of the sorted shard rows (valid until vga_graph_free): rowptr (u64, local,
+ * rows+1), packed adjacency entries (u32: col<<5 | bin), number of entries. */
+int vga_graph_device_rows(const vga_graph *g, const uint64_t **d_rowptr, const uint32_t **d_adj, int64_t *n_entries);
+/* Adopt device-resident packed rows for all N cells (e.g. after an NCCL all-gather of shards). */
+int vga_graph_from_device_rows(vga_ctx *ctx, int64_t n_cells, int64_t n_ghosts, const uint64_t *d_rowptr,
+                               const uint32_t *d_adj, int64_t n_entries, vga_graph **out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VGA_B200_H */
