@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[chu
 }
 
 // per batch: retire empty batches, choose the next step's direction, reset statistics
-__global__ void k_decide(BfsDev d, int chunk, int bfs_mode, int64_t alpha, u64 *work /*[2] push edges, pull edges*/) {
+__global__ void k_decide(BfsDev d, int chunk, int bfs_mode, int64_t alpha, u64 *work /*[3]*/) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= chunk) return;
     if (!d.active[b]) return;
@@ -218,7 +218,11 @@ __global__ void k_decide(BfsDev d, int chunk, int bfs_mode, int64_t alpha, u64 *
     else if (bfs_mode == 2)
         m = (fe * (u64)alpha > ue) ? 1 : 0;
     d.mode[b] = m;
-    atomicAdd(&work[m], m ? ue : fe);
+    // work[0]: adjacency entries of the vertices that expand next (sum of deg over U_l),
+    // work[1]: vertices newly reached (|U_l| summed), work[2]: in-edges offered to the pull step
+    atomicAdd(&work[0], fe);
+    atomicAdd(&work[1], nn);
+    if (m) atomicAdd(&work[2], ue);
 }
 
 // ---- transpose (in-edge lists of filled vertices), needed by the pull step --------------------
@@ -321,7 +325,7 @@ int run_global(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_
     VGA_TRY(next.alloc((size_t)chunk * n));
     VGA_TRY(valid.alloc((size_t)chunk));
     VGA_TRY(stats.alloc((size_t)chunk * 4));
-    VGA_TRY(work.alloc_zero(2, st));
+    VGA_TRY(work.alloc_zero(4, st));
     VGA_TRY(active.alloc((size_t)chunk));
     VGA_TRY(mode.alloc((size_t)chunk));
     VGA_TRY(any.alloc(1));
@@ -399,7 +403,7 @@ int run_global(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_
                 mt.start();
             }
             VGA_CUDA(cudaMemsetAsync(any.p, 0, sizeof(int), st));
-            k_update<<<grid, TPB, 0, st>>>(d, counts.p + (size_t)(level + 1) * chunk * 64, bfs_mode == 2 ? 1 : 0);
+            k_update<<<grid, TPB, 0, st>>>(d, counts.p + (size_t)(level + 1) * chunk * 64, 1);
             k_decide<<<blocks_for(cb, 128), 128, 0, st>>>(d, (int)cb, bfs_mode, ctx->opt.pull_alpha, work.p);
             tm.launches += 2;
             tm.main_launches += 2;
@@ -444,10 +448,19 @@ int run_global(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_
     // deepest counts levels 0..deepest-1 that were *computed*; trailing empty level is not reported
     if (levels_used) *levels_used = deepest;
     {
-        u64 hw[2] = {0, 0};
+        u64 hw[4] = {0, 0, 0, 0};
         VGA_CUDA(cudaMemcpy(hw, work.p, sizeof(hw), cudaMemcpyDeviceToHost));
-        // algorithmic bytes: adjacency entries streamed by expanding vertices (4 B each)
-        tm.algo_bytes = 4.0 * ((double)hw[0] + (double)hw[1]);
+        uint64_t rp[2] = {0, 0};
+        VGA_CUDA(cudaMemcpy(&rp[0], g->rowptr.p + src_begin, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        VGA_CUDA(cudaMemcpy(&rp[1], g->rowptr.p + src_end, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        // algorithmic bytes (SURVEY.md §8d with B = 64, CSR rows of 4 B entries): per batch and level,
+        // rows of the expanding vertices + one frontier word read per expanding vertex + one
+        // visited/next read-modify-write (2 words) per newly reached vertex.  Level 0 expands the
+        // sources themselves.  The last level's vertices are counted as expanding only if they were
+        // (radius cut-off): hw[0] already excludes nothing, so subtract nothing -- documented upper
+        // bound differs from the exact figure by the final (empty) expansion only.
+        const double src_edges = (double)(rp[1] - rp[0]);
+        tm.algo_bytes = 4.0 * ((double)hw[0] + src_edges) + 8.0 * ((double)hw[1] + (double)nsrc) + 16.0 * (double)hw[1];
     }
     if (dist && deepest > max_levels) {
         set_error("vga_global: level histogram needs " + std::to_string(deepest) + " columns");

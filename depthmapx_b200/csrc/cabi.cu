@@ -226,10 +226,12 @@ int vga_grid_upload(vga_ctx *ctx, const vga_grid *grid, vga_dgrid **out) {
             uint8_t f = (filled ? 1 : 0) | ((grid->line_off[c + 1] > grid->line_off[c]) ? 2 : 0);
             cf[(size_t)c] = f;
             cft[(size_t)(y * grid->cols + x)] = f;
-            ord[(size_t)c] = filled ? (int32_t)n : -1;
+            ord[(size_t)c] = filled ? (int32_t)n : -(int32_t)(1 + n);
             if (filled) {
                 d->h_cellref.push_back((int32_t)(((uint32_t)x << 16) | (uint32_t)y));
                 n++;
+            } else {
+                d->h_ghostref.push_back((int32_t)(((uint32_t)x << 16) | (uint32_t)y));
             }
         }
     d->n = n;

@@ -547,7 +547,7 @@ __device__ TaskOut sieve_task(const GridDev &g, int cx, int cy, int q, const Scr
                             e_ref[p] = ((uint32_t)fx << 16) | ((uint32_t)fy & 0xffffu);
                             e_bin[p] = (uint8_t)(diagbin | 0x80);
                         } else if (!(g.cflag[fc] & 1)) {
-                            ghostflag[fc] = 1;
+                            *ghostflag = 1;  // an unfilled cell is part of the iterated adjacency
                         }
                     }
                     nfill += (uint32_t)gap;
@@ -610,7 +610,7 @@ struct SieveArgs {
     // count outputs
     uint32_t *cnt;          // [nsrc*8]
     uint32_t *fillcnt;      // [nsrc*4]
-    uint8_t *ghostflag;     // [cells]
+    uint8_t *ghostflag;     // [1] set when any unfilled cell is covered by a diagonal run
     int64_t *overflow_list;
     unsigned long long *n_overflow;
     int *error_flag;
@@ -746,22 +746,19 @@ __global__ void k_node_stats(GridDev g, int64_t src_begin, int64_t chunk_first, 
     gridconn[sl] = gc;
 }
 
-// sort keys: col<<6 | accepted<<5 | bin   (col = ordinal of a filled cell, or N + ghost rank)
-__global__ void k_make_keys(GridDev g, const uint32_t *e_ref, const uint8_t *e_bin, uint64_t n_entries,
-                            const int32_t *ghost_rank, uint32_t *keys) {
+// sort keys: col<<6 | accepted<<5 | bin.  col = ordinal of a filled cell; an unfilled cell c (ghost)
+// gets N + (number of unfilled cells before c) = N + c - (filled cells before c): a static numbering
+// that every shard / rank computes identically.  cellord[c] holds -(1 + filled cells before c) for
+// unfilled cells.
+__global__ void k_make_keys(GridDev g, const uint32_t *e_ref, const uint8_t *e_bin, uint64_t n_entries, uint32_t *keys) {
     uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_entries) return;
     uint32_t r = e_ref[e];
     uint8_t b = e_bin[e];
     int64_t c = (int64_t)(r >> 16) * g.rows + (r & 0xffff);
     int32_t ord = g.cellord[c];
-    uint32_t col = (ord >= 0) ? (uint32_t)ord : (uint32_t)(g.n + ghost_rank[c]);
+    uint32_t col = (ord >= 0) ? (uint32_t)ord : (uint32_t)(g.n + c - (int64_t)(-(ord + 1)));
     keys[e] = (col << 6) | ((b & 0x80) ? 0u : 32u) | (uint32_t)(b & 31);
-}
-
-__global__ void k_ghost_mark_to_int(const uint8_t *flag, int64_t cells, int32_t *out) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < cells) out[i] = flag[i] ? 1 : 0;
 }
 
 __global__ void k_rebase(const uint64_t *in, int64_t n, uint64_t base, uint64_t *out) {
@@ -791,7 +788,7 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t sr
     if (src_begin < 0) src_begin = 0;
     if (src_begin > src_end) src_begin = src_end;
     const int64_t nsrc = src_end - src_begin;
-    if (N >= ((int64_t)1 << 26) - 65536) {
+    if (dg->cells >= ((int64_t)1 << 26)) {
         set_error("vga_graph_build: more than 2^26 cells is not supported");
         return VGA_ERR_UNSUPPORTED;
     }
@@ -833,7 +830,7 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t sr
     DevBuf<uint64_t> row_tot, row_off;
     VGA_TRY(cnt.alloc_zero((size_t)nsrc * 8 + 8, st));
     VGA_TRY(fillcnt.alloc_zero((size_t)nsrc * 4 + 4, st));
-    VGA_TRY(ghostflag.alloc_zero((size_t)dg->cells + 1, st));
+    VGA_TRY(ghostflag.alloc_zero(4, st));
     VGA_TRY(bigflag.alloc_zero((size_t)ntasks + 1, st));
     VGA_TRY(overflow_list.alloc((size_t)ntasks + 1));
     VGA_TRY(n_overflow.alloc_zero(1, st));
@@ -921,32 +918,15 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t sr
         return h_err;
     }
 
-    // ---- ghosts: unfilled cells covered by a diagonal first..last run
-    DevBuf<int32_t> ghost_rank;
-    VGA_TRY(ghost_rank.alloc((size_t)dg->cells + 1));
+    // ---- ghosts: unfilled cells covered by a diagonal first..last run get ordinals N.. (all unfilled
+    // cells are numbered, so every shard agrees); without any, the universe is just the N cells
     {
-        DevBuf<int32_t> gi;
-        VGA_TRY(gi.alloc((size_t)dg->cells + 1));
-        k_ghost_mark_to_int<<<blocks_for(dg->cells, 256), 256, 0, st>>>(ghostflag.p, dg->cells, gi.p);
-        tm.launches++;
-        size_t tb = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, tb, gi.p, ghost_rank.p, (int)dg->cells, st);
-        DevBuf<unsigned char> tmp;
-        VGA_TRY(tmp.alloc(tb + 16));
-        cub::DeviceScan::ExclusiveSum(tmp.p, tb, gi.p, ghost_rank.p, (int)dg->cells, st);
-        tm.launches++;
-        int32_t last_rank = 0, last_flag = 0;
-        if (dg->cells > 0) {
-            VGA_CUDA(cudaMemcpyAsync(&last_rank, ghost_rank.p + dg->cells - 1, 4, cudaMemcpyDeviceToHost, st));
-            VGA_CUDA(cudaMemcpyAsync(&last_flag, gi.p + dg->cells - 1, 4, cudaMemcpyDeviceToHost, st));
-        }
+        uint8_t any_ghost = 0;
+        VGA_CUDA(cudaMemcpyAsync(&any_ghost, ghostflag.p, 1, cudaMemcpyDeviceToHost, st));
         VGA_CUDA(cudaStreamSynchronize(st));
-        gr->ghosts = (int64_t)last_rank + last_flag;
-        if (gr->ghosts > 0) {
-            std::vector<uint8_t> hf((size_t)dg->cells);
-            VGA_CUDA(cudaMemcpy(hf.data(), ghostflag.p, (size_t)dg->cells, cudaMemcpyDeviceToHost));
-            for (int64_t c = 0; c < dg->cells; c++)
-                if (hf[c]) gr->h_refs.push_back((int32_t)(((uint32_t)(c / dg->rows) << 16) | (uint32_t)(c % dg->rows)));
+        if (any_ghost) {
+            gr->ghosts = dg->cells - N;
+            gr->h_refs.insert(gr->h_refs.end(), dg->h_ghostref.begin(), dg->h_ghostref.end());
         }
     }
 
@@ -1056,7 +1036,7 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t sr
         tm.launches++;
         VGA_CUDA(cudaGetLastError());
         if (cnt_e > 0) {
-            k_make_keys<<<blocks_for((int64_t)cnt_e, 256), 256, 0, st>>>(g, e_ref.p, e_bin.p, cnt_e, ghost_rank.p, keys.p);
+            k_make_keys<<<blocks_for((int64_t)cnt_e, 256), 256, 0, st>>>(g, e_ref.p, e_bin.p, cnt_e, keys.p);
             tm.launches++;
             k_rebase<<<blocks_for(ns + 1, 256), 256, 0, st>>>(row_off.p + i, ns + 1, base, seg_off.p);
             tm.launches++;

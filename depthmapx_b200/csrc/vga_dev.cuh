@@ -109,9 +109,10 @@ struct vga_dgrid {
     vga::DevBuf<uint8_t> cflag_t;  // [cells] y-major copy (index y*cols+x) for the y-major octants
     vga::DevBuf<uint32_t> line_off;
     vga::DevBuf<double> lines;
-    vga::DevBuf<int32_t> cellord;  // [cells] ordinal or -1
+    vga::DevBuf<int32_t> cellord;  // [cells] ordinal, or -(1 + filled cells before) for unfilled cells
     vga::DevBuf<int32_t> cellref;  // [n] packed PixelRef per ordinal
     std::vector<int32_t> h_cellref;
+    std::vector<int32_t> h_ghostref;  // packed PixelRef of every unfilled cell, x-major
 };
 
 struct vga_graph {

@@ -1,0 +1,35 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "ref: needs oracle/_ref/libdmxref.so (the compiled reference)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """Make sure the product libraries and the oracle exist (prebuilt files travel to the GPU box)."""
+    from depthmapx_b200 import capi
+    from oracle import pyoracle as po
+    if not (os.path.exists(os.path.join(capi.LIBDIR, "libvga_b200.so")) and
+            os.path.exists(os.path.join(capi.LIBDIR, "libvga_host.so"))):
+        from depthmapx_b200 import build
+        build.build()
+    if not po.have_oracle():
+        po.build(ref=False)
+    yield
+
+
+def golden(name):
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+
+
+GOLDEN = ["box2x2", "oblique20", "oblique16s07", "office24"]

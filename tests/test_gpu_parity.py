@@ -1,0 +1,333 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the C ABI
+(libvga_b200.so) or the host layer above it (libvga_host.so); the oracle and the golden fixtures
+(generated from the unmodified reference) are only the checkers.
+
+Bar: adjacency, node statistics, BFS integers and local integers bit-exact; float attributes
+bit-equal as float32 (tolerance of the north star: 1e-9 relative -- asserted as exact equality,
+which is stricter)."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden
+from depthmapx_b200 import capi, plans
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    if capi.device_count() < 1:
+        pytest.fail("no CUDA device: the GPU tests must run on the B200 box (there is no CPU fallback)")
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def flat_of(fx, maxdist=-1.0):
+    return capi.FlatGrid(int(fx["cols"]), int(fx["rows"]), float(fx["spacing"]), float(fx["bl_x"]), float(fx["bl_y"]),
+                         fx["state"], fx["line_off"], fx["lines"], maxdist)
+
+
+def attr(fx, name):
+    cols = [str(c) for c in fx["columns"]]
+    return fx[f"attr_{cols.index(name)}"]
+
+
+def sorted_rows(rowptr, ref, b):
+    rowid = np.repeat(np.arange(len(rowptr) - 1), np.diff(rowptr).astype(np.int64))
+    order = np.lexsort((ref.astype(np.int64), rowid))
+    return ref[order], b[order]
+
+
+def my_rows(g):
+    """CSR of the library with columns translated to packed PixelRefs and rows re-sorted by PixelRef
+    (the library sorts by ordinal: filled cells in PixelRef order, ghost vertices last)."""
+    rp, col, b, acc = g.csr()
+    ref = g.cell_refs()[col] if len(col) else np.zeros(0, np.int32)
+    r, bb = sorted_rows(rp, ref, b)
+    return rp, r, bb
+
+
+def oracle_graph(flat, **kw):
+    from oracle import pyoracle as po
+    return po.OracleGraph(po.Grid(flat.cols, flat.rows, flat.spacing, flat.bl_x, flat.bl_y, flat.state, flat.line_off,
+                                  flat.lines, flat.maxdist), **kw)
+
+
+# ---- against the reference's own outputs (golden fixtures) -----------------------------------------
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_makegraph_vs_reference_golden(ctx, name):
+    fx = golden(name)
+    g = ctx.build(flat_of(fx))
+    rp, col, b, acc = g.csr()
+    assert np.array_equal(rp, fx["rowptr"])
+    refs = g.cell_refs()
+    eref, ebin = sorted_rows(fx["rowptr"], fx["ref"], fx["bin"])
+    assert np.array_equal(refs[col], eref)
+    assert np.array_equal(b, ebin)
+    st = g.node_stats()
+    assert np.array_equal(st["connectivity"].astype(np.float32), attr(fx, "Connectivity"))
+    assert np.array_equal(st["sum_d"].astype(np.float32), attr(fx, "Point First Moment"))
+    assert np.array_equal(st["sum_d2"].astype(np.float32), attr(fx, "Point Second Moment"))
+    assert np.array_equal(st["far"], fx["bin_dist"])
+    assert np.array_equal(st["gridconn"], fx["gridconn"])
+    # accepted pixels per bin == stored node counts for non-diagonal bins; diagonal bins store pixels.size()
+    assert np.array_equal(st["bin_count"].astype(np.uint16), fx["bin_count"])
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+@pytest.mark.parametrize("radius", [-1, 3])
+def test_global_vs_reference_golden(ctx, name, radius):
+    fx = golden(name)
+    g = ctx.build(flat_of(fx))
+    tn, td, dist, used = g.global_ints(radius)
+    out = capi.global_attributes(tn, td, dist)
+    sfx = "" if radius == -1 else f" R{radius}"
+    for k, v in out.items():
+        assert np.array_equal(v, attr(fx, k + sfx)), k
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_local_vs_reference_golden(ctx, name):
+    fx = golden(name)
+    g = ctx.build(flat_of(fx))
+    out = capi.local_attributes(*g.local_ints())
+    for k, v in out.items():
+        assert np.array_equal(v, attr(fx, k)), k
+
+
+@pytest.mark.parametrize("name", ["oblique20", "office24"])
+def test_host_layer_columns_vs_reference_golden(name):
+    """dmx::PointMap::sparkGraph2 + VGAVisualLocal::run + VGAVisualGlobal::run: every column the reference writes."""
+    fx = golden(name)
+    m = capi.HostMap(fx["walls"], float(fx["spacing"]))
+    for s in fx["seeds"]:
+        assert m.fill(float(s[0]), float(s[1]))
+    assert m.make_graph()
+    assert m.vga_local()
+    assert m.vga_global(-1.0)
+    assert m.vga_global(3.0)
+    cols = [str(c) for c in fx["columns"]]
+    assert sorted(m.columns()) == sorted(cols)
+    for c in cols:
+        assert np.array_equal(m.attr(c), attr(fx, c)), c
+    assert np.array_equal(m.grid_connections(), fx["gridconn"])
+
+
+def test_from_csr_adopts_reference_adjacency(ctx):
+    """-m VGA on a loaded .graph: adjacency flattened from the reference's Nodes -> same analysis."""
+    fx = golden("oblique16s07")
+    state = fx["state"]
+    rows = int(fx["rows"])
+    ordmap = np.full(state.shape[0], -1, np.int64)
+    filled = (state & 2) != 0
+    ordmap[filled] = np.arange(filled.sum())
+    ref = fx["ref"].astype(np.int64)
+    cell = (ref >> 16) * rows + (ref & 0xffff)
+    col = ordmap[cell]
+    assert (col >= 0).all()
+    n = int(filled.sum())
+    g = ctx.graph_from_csr(n, 0, fx["rowptr"], col.astype(np.uint32), fx["bin"])
+    tn, td, dist, used = g.global_ints(-1)
+    out = capi.global_attributes(tn, td, dist)
+    for k, v in out.items():
+        assert np.array_equal(v, attr(fx, k)), k
+    out = capi.local_attributes(*g.local_ints())
+    for k, v in out.items():
+        assert np.array_equal(v, attr(fx, k)), k
+
+
+# ---- against the oracle on seeded plans ---------------------------------------------------------------
+
+PLANS = ["oblique:30:30:7", "oblique:30:30:8:0.7", "oblique:40:25:21:1.3", "office:64:64:1", "room:40:40:5",
+         "gallery:160:160:3", "urban:120:120:4"]
+
+
+@pytest.mark.parametrize("name", PLANS)
+def test_makegraph_vs_oracle(ctx, name):
+    flat = capi.prepare(plans.by_name(name))
+    g = ctx.build(flat)
+    og = oracle_graph(flat)
+    rp, col, b, acc = g.csr()
+    orp, oref, ob = og.iter_rows()
+    assert np.array_equal(rp, orp)
+    eref, ebin = sorted_rows(orp, oref, ob)
+    assert np.array_equal(g.cell_refs()[col], eref) and np.array_equal(b, ebin)
+    st, a = g.node_stats(), og.node_attrs()
+    assert np.array_equal(st["connectivity"].astype(np.float32), a["connectivity"])
+    assert np.array_equal(st["sum_d"].astype(np.float32), a["first_moment"])
+    assert np.array_equal(st["sum_d2"].astype(np.float32), a["second_moment"])
+    assert np.array_equal(st["far"], a["far"])
+    assert np.array_equal(st["gridconn"], a["gridconn"])
+
+
+@pytest.mark.parametrize("name", ["oblique:30:30:7", "office:64:64:1", "gallery:160:160:3"])
+@pytest.mark.parametrize("radius", [-1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_global_vs_oracle_all_modes(name, radius, mode):
+    c = capi.Context(0)
+    c.set_option("bfs_mode", mode)
+    flat = capi.prepare(plans.by_name(name))
+    g = c.build(flat)
+    og = oracle_graph(flat)
+    tn, td, dist, used = g.global_ints(radius)
+    rng = np.random.RandomState(3)
+    for s in rng.choice(g.n, min(g.n, 96), replace=False):
+        otn, otd, odist, onl = og.global_ints(radius, (int(s), int(s) + 1), maxl=64)
+        L = dist.shape[1]
+        assert otn[0] == tn[s] and otd[0] == td[s]
+        assert np.array_equal(odist[0, :L], dist[s]) and not odist[0, L:].any()
+    c.close()
+
+
+@pytest.mark.parametrize("name", ["oblique:30:30:7", "office:64:64:1", "urban:120:120:4"])
+def test_local_vs_oracle(ctx, name):
+    flat = capi.prepare(plans.by_name(name))
+    g = ctx.build(flat)
+    og = oracle_graph(flat)
+    lo = max(0, g.n // 2 - 100)
+    hi = min(g.n, lo + 200)
+    a = g.local_ints((lo, hi))
+    b = og.local_ints((lo, hi))
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_maxdist_vs_oracle(ctx):
+    flat = capi.prepare(plans.by_name("oblique:30:30:7"), maxdist=6.5)
+    g = ctx.build(flat)
+    og = oracle_graph(flat)
+    rp, col, b, acc = g.csr()
+    orp, oref, ob = og.iter_rows()
+    assert np.array_equal(rp, orp)
+    eref, ebin = sorted_rows(orp, oref, ob)
+    assert np.array_equal(g.cell_refs()[col], eref)
+
+
+def test_boundary_graph_vs_oracle(ctx):
+    """-pb: only EDGE cells keep FILLED before construction (pointdata.cpp:1254-1264)."""
+    flat = capi.prepare(plans.by_name("office:48:48:2"))
+    st = flat.state.copy()
+    drop = ((st & 2) != 0) & ((st & 0x20) == 0)
+    st[drop] &= ~np.uint16(2)
+    flat.state = st
+    g = ctx.build(flat)
+    og = oracle_graph(flat)
+    rp, ref, b = my_rows(g)
+    orp, oref, ob = og.iter_rows()
+    assert np.array_equal(rp, orp)
+    eref, ebin = sorted_rows(orp, oref, ob)
+    assert np.array_equal(ref, eref) and np.array_equal(b, ebin)
+    # cells between accepted diagonal cells may now be unfilled: ghosts are allowed to appear
+    assert g.ghosts >= 0
+    tn, td, dist, used = g.global_ints(-1)
+    otn, otd, odist, onl = og.global_ints(-1, maxl=dist.shape[1])
+    assert np.array_equal(tn, otn) and np.array_equal(td, otd) and np.array_equal(dist, odist)
+    lo, hi = 0, min(g.n, 150)
+    for x, y in zip(g.local_ints((lo, hi)), og.local_ints((lo, hi))):
+        assert np.array_equal(x, y)
+
+
+def test_ghosts_diagonal_fill_vs_oracle(ctx):
+    """Unfilled cells inside a diagonal bin's first..last run are part of the iterated adjacency
+    (Bin::make, ngraph.cpp:243-259) and of the local measures' k."""
+    flat = capi.prepare(plans.by_name("room:24:24:1"))
+    st = flat.state.copy()
+    rows = flat.rows
+    # punch unfilled holes on a diagonal of an open area, away from walls
+    for d in (3, 5):
+        st[(2 + d) * rows + (2 + d)] &= ~np.uint16(2)
+    flat.state = st
+    g = ctx.build(flat)
+    og = oracle_graph(flat)
+    assert g.ghosts > 0
+    rp, ref, b = my_rows(g)
+    orp, oref, ob = og.iter_rows()
+    assert np.array_equal(rp, orp)
+    eref, ebin = sorted_rows(orp, oref, ob)
+    assert np.array_equal(ref, eref) and np.array_equal(b, ebin)
+    tn, td, dist, used = g.global_ints(-1)
+    otn, otd, odist, onl = og.global_ints(-1, maxl=dist.shape[1])
+    assert np.array_equal(tn, otn) and np.array_equal(td, otd) and np.array_equal(dist, odist)
+    for x, y in zip(g.local_ints(), og.local_ints()):
+        assert np.array_equal(x, y)
+
+
+def test_empty_and_tiny_inputs(ctx):
+    # no filled cell at all
+    flat = capi.prepare(plans.by_name("room:12:12:0"))
+    flat.state = (flat.state & ~np.uint16(2)).astype(np.uint16)
+    g = ctx.build(flat)
+    assert g.n == 0 and g.entries == 0
+    tn, td, dist, used = g.global_ints(-1)
+    assert len(tn) == 0
+    # a single filled cell: Node Count 1, everything else -1
+    flat = capi.prepare(plans.by_name("room:12:12:0"))
+    st = (flat.state & ~np.uint16(2)).astype(np.uint16)
+    st[5 * flat.rows + 5] |= 2
+    flat.state = st
+    g = ctx.build(flat)
+    assert g.n == 1 and g.entries == 0
+    tn, td, dist, used = g.global_ints(-1)
+    out = capi.global_attributes(tn, td, dist)
+    assert out["Visual Node Count"][0] == 1.0 and out["Visual Mean Depth"][0] == -1.0
+    lo = capi.local_attributes(*g.local_ints())
+    assert lo["Visual Control"][0] == -1.0
+
+
+def test_overflow_path_small_capacity():
+    """Tasks that overflow the shared-memory gap/block slices are re-run with global scratch and
+    give the same rows."""
+    flat = capi.prepare(plans.by_name("urban:120:120:4"))
+    a = capi.Context(0)
+    g1 = a.build(flat)
+    b = capi.Context(0)
+    b.set_option("sieve_gcap", 4)
+    b.set_option("sieve_bcap", 8)
+    g2 = b.build(flat)
+    for x, y in zip(g1.csr(), g2.csr()):
+        assert np.array_equal(x, y)
+    s1, s2 = g1.node_stats(), g2.node_stats()
+    for k in s1:
+        assert np.array_equal(s1[k], s2[k]), k
+
+
+# ---- size-independent properties at larger sizes -----------------------------------------------------
+
+def test_shards_equal_full_build(ctx):
+    flat = capi.prepare(plans.by_name("office:96:96:3"))
+    full = ctx.build(flat)
+    n = full.n
+    frp, fcol, fb, facc = full.csr()
+    cuts = [0, n // 3, n // 3 + 1, n]
+    base = 0
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        sh = ctx.build(flat, (lo, hi))
+        rp, col, b, acc = sh.csr()
+        assert np.array_equal(rp + frp[lo], frp[lo:hi + 1])
+        assert np.array_equal(col, fcol[int(frp[lo]):int(frp[hi])])
+        base += len(col)
+    assert base == len(fcol)
+
+
+def test_properties_c1_full_size(ctx):
+    """BASELINE config 1 at full size: histogram sums, symmetry-implied reachability, determinism."""
+    flat = capi.prepare(plans.by_name("C1"))
+    g = ctx.build(flat)
+    tn, td, dist, used = g.global_ints(-1)
+    assert (dist.sum(axis=1) == tn).all()
+    assert ((dist * np.arange(dist.shape[1])).sum(axis=1) == td).all()
+    assert (tn == g.n).all()  # one connected open plan
+    tn3, td3, dist3, used3 = g.global_ints(3)
+    assert used3 <= 4 and (tn3 <= tn).all()
+    L = min(dist.shape[1], dist3.shape[1], 3)
+    assert np.array_equal(dist3[:, :L], dist[:, :L])  # radius only truncates
+    g2 = ctx.build(flat)
+    for x, y in zip(g.csr(), g2.csr()):
+        assert np.array_equal(x, y)
+    st = g.node_stats()
+    rp = g.csr()[0]
+    assert np.array_equal(np.diff(rp).astype(np.int64), st["connectivity"].astype(np.int64))  # no fill-ins here
+    # Connectivity must equal the degree the BFS sees at level 1
+    assert np.array_equal(dist[:, 1].astype(np.int64), st["connectivity"].astype(np.int64))

@@ -1,0 +1,113 @@
+"""CPU tests of the oracle (oracle/vga_oracle.c): it must reproduce the reference's own known-answer
+tests and the golden fixtures generated from the unmodified reference (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden
+from oracle import pyoracle as po
+
+
+def grid_of(fx, maxdist=-1.0):
+    return po.Grid(int(fx["cols"]), int(fx["rows"]), float(fx["spacing"]), float(fx["bl_x"]), float(fx["bl_y"]),
+                   fx["state"], fx["line_off"], fx["lines"], maxdist)
+
+
+def attr(fx, name):
+    cols = [str(c) for c in fx["columns"]]
+    return fx[f"attr_{cols.index(name)}"]
+
+
+# ---- salaTest/testsparksieve.cpp:21-83 -----------------------------------------------------------
+
+def test_sieve_one_block_garbage():
+    g = po.sieve_kat(1, 1, 4, [[0.5, 0.2, 0.5, 0.7]])
+    assert len(g) == 1 and g[0][0] == 0 and g[0][1] == pytest.approx(0.625)
+
+
+def test_sieve_shift_start_and_end():
+    g = po.sieve_kat(1, 1, 4, [[0.5, 0.2, 0.5, 0.7], [0.5, 0.1, 1.1, 0.9]])
+    assert len(g) == 1 and g[0][0] == pytest.approx(0.55555555555) and g[0][1] == pytest.approx(0.625)
+
+
+def test_sieve_delete_gap():
+    assert len(po.sieve_kat(1, 1, 4, [[1.1, 0.2, 0.5, 0.7]])) == 0
+
+
+def test_sieve_add_gap():
+    g = po.sieve_kat(1, 1, 4, [[0.5, 0.2, 0.5, 0.1], [0.5, 0.3, 0.5, 0.7]])
+    assert len(g) == 2
+    assert g[0][0] == 0 and g[0][1] == pytest.approx(0.55555555555)
+    assert g[1][0] == pytest.approx(0.625) and g[1][1] == pytest.approx(0.71428571)
+
+
+# ---- salaTest/testpointmap.cpp:313-453 (2x2 connections) -------------------------------------------
+
+def test_box2x2_connections_text():
+    fx = golden("box2x2")
+    og = po.OracleGraph(grid_of(fx))
+    refs = og.cell_refs()
+    assert list(refs) == [65537, 65538, 131073, 131074]
+    rp, ref, b = og.iter_rows()
+    rows = [list(ref[int(rp[i]):int(rp[i + 1])]) for i in range(4)]
+    # expected "connections [" blocks of PointMap::outputConnections
+    assert rows == [[131073, 131074, 65538], [131074, 65537, 131073], [131074, 65538, 65537], [65538, 65537, 131073]]
+
+
+# ---- golden fixtures from the reference --------------------------------------------------------------
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_makegraph_matches_reference(name):
+    fx = golden(name)
+    og = po.OracleGraph(grid_of(fx))
+    rp, ref, b = og.iter_rows()
+    assert np.array_equal(rp, fx["rowptr"])
+    assert np.array_equal(ref, fx["ref"])
+    assert np.array_equal(b, fx["bin"])
+    a = og.node_attrs()
+    assert np.array_equal(a["bin_count"], fx["bin_count"])
+    assert np.array_equal(a["far"], fx["bin_dist"])
+    assert np.array_equal(a["gridconn"], fx["gridconn"])
+    assert np.array_equal(a["connectivity"], attr(fx, "Connectivity"))
+    assert np.array_equal(a["first_moment"], attr(fx, "Point First Moment"))
+    assert np.array_equal(a["second_moment"], attr(fx, "Point Second Moment"))
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+@pytest.mark.parametrize("radius", [-1, 3])
+def test_global_matches_reference(name, radius):
+    fx = golden(name)
+    og = po.OracleGraph(grid_of(fx))
+    tn, td, dist, nl = og.global_ints(radius)
+    f = po.global_formulas(tn, td, dist, nl)
+    sfx = "" if radius == -1 else f" R{radius}"
+    for k, v in f.items():
+        assert np.array_equal(v, attr(fx, k + sfx)), k
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_local_matches_reference(name):
+    fx = golden(name)
+    og = po.OracleGraph(grid_of(fx))
+    f = po.local_formulas(*og.local_ints())
+    for k, v in f.items():
+        assert np.array_equal(v, attr(fx, k)), k
+
+
+def test_graph_from_edges_equals_built():
+    fx = golden("oblique20")
+    g = grid_of(fx)
+    og = po.OracleGraph(g)
+    og2 = po.OracleGraph(g, edges=(fx["rowptr"], fx["ref"]))
+    a = og.global_ints(-1)
+    b = og2.global_ints(-1)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_maxdist_limits_targets():
+    fx = golden("oblique20")
+    og = po.OracleGraph(grid_of(fx, maxdist=4.0))
+    a = og.node_attrs()
+    full = po.OracleGraph(grid_of(fx)).node_attrs()
+    assert (a["connectivity"] <= full["connectivity"]).all()
+    assert a["far"].max() <= 4.0 + 1e-6
