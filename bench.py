@@ -326,6 +326,10 @@ def main():
                    "sieve_kernels_ms": sieve_main_ms, "bfs_level_kernels_ms": bfs_main_ms},
         "e2e": {"value": n / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(flat.input_bytes()), "d2h_bytes_per_step": int(st_e2e[0]["d2h_bytes"]),
+                "makegraph_ms": float(np.mean([s["build_ms"] for s in st_e2e])),
+                "global_bfs_ms": float(np.mean([s["bfs_ms"] for s in st_e2e])),
+                "h2d_ms": float(np.mean([s["build_timing"]["h2d_ms"] for s in st_e2e])),
+                "d2h_ms": float(np.mean([s["bfs_timing"]["d2h_ms"] for s in st_e2e])),
                 "note": "vga_graph_build(host vga_grid) + vga_global(host outputs); pageable host buffers"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "BFS level kernels k_push/k_pull/k_update/k_decide",

@@ -34,7 +34,7 @@ ABI_SYMBOLS = [
     "vga_last_error", "vga_version", "vga_device_count", "vga_ctx_create", "vga_ctx_destroy", "vga_ctx_set_callbacks",
     "vga_ctx_set_option", "vga_ctx_timing", "vga_ctx_sync", "vga_graph_build", "vga_grid_upload", "vga_dgrid_free",
     "vga_graph_build_resident", "vga_graph_from_csr", "vga_graph_free", "vga_graph_num_cells", "vga_graph_num_ghosts",
-    "vga_graph_num_edges", "vga_graph_src_begin", "vga_graph_src_end", "vga_graph_csr", "vga_graph_cell_refs",
+    "vga_graph_num_edges", "vga_graph_src_begin", "vga_graph_src_end", "vga_graph_csr", "vga_graph_cell_refs", "vga_graph_set_cell_refs",
     "vga_graph_node_stats", "vga_global", "vga_global_attributes", "vga_local", "vga_local_attributes",
     "vga_graph_device_rows", "vga_graph_from_device_rows",
 ]
@@ -76,6 +76,7 @@ def abi():
             getattr(L, f).argtypes = [vp]
         L.vga_graph_csr.argtypes = [vp] * 5
         L.vga_graph_cell_refs.argtypes = [vp, vp]
+        L.vga_graph_set_cell_refs.argtypes = [vp, vp, i64]
         L.vga_graph_node_stats.argtypes = [vp] * 7
         L.vga_global.argtypes = [vp, vp, C.c_int, i64, i64, vp, vp, vp, C.c_int32, C.POINTER(C.c_int32)]
         L.vga_global_attributes.argtypes = [i64, vp, vp, vp, C.c_int32] + [vp] * 7
@@ -152,11 +153,15 @@ class FlatGrid:
 
 class Context:
     def __init__(self, device: int = 0):
+        import weakref
         self.h = vp()
+        self._children = weakref.WeakSet()  # graphs / device grids that must die before the context
         check(abi().vga_ctx_create(device, C.byref(self.h)))
 
     def close(self):
         if self.h:
+            for ch in list(self._children):
+                ch.free()
             abi().vga_ctx_destroy(self.h)
             self.h = vp()
 
@@ -209,16 +214,24 @@ class DeviceGrid:
         self.h = vp()
         cg = grid.c()
         check(abi().vga_grid_upload(ctx.h, C.byref(cg), C.byref(self.h)))
+        ctx._children.add(self)
 
-    def __del__(self):
+    def free(self):
         if getattr(self, "h", None):
             abi().vga_dgrid_free(self.h)
             self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 class Graph:
     def __init__(self, ctx: Context, handle, owned=True):
         self.ctx, self.h, self.owned = ctx, handle, owned
+        ctx._children.add(self)
         L = abi()
         self.n = L.vga_graph_num_cells(handle)
         self.ghosts = L.vga_graph_num_ghosts(handle)
@@ -250,6 +263,10 @@ class Graph:
         r = np.zeros(self.n + self.ghosts, np.int32)
         check(abi().vga_graph_cell_refs(self.h, _p(r)))
         return r
+
+    def set_cell_refs(self, refs):
+        r = np.ascontiguousarray(refs, np.int32)
+        check(abi().vga_graph_set_cell_refs(self.h, _p(r), len(r)))
 
     def node_stats(self):
         rows = self.src_end - self.src_begin

@@ -1,19 +1,24 @@
 // All-sources BFS of VGA visibility analysis (VGAVisualGlobal::run + extractUnseen,
 // salalib/vgamodules/vgavisualglobal.cpp:66-130, 218-240) as a bit-parallel multi-source BFS.
 //
-// 64 consecutive x-major sources form a batch; a batch carries one 64-bit word per vertex for
-// each of visited / frontier / next.  Many batches (a "chunk") advance level by level together:
-// grid = (vertex tiles, batches), so one launch per level serves the whole chunk and the host
-// synchronises once per level, not once per batch.  Batches whose frontier emptied are skipped.
+// 64 sources form a batch; a batch carries one 64-bit word per vertex for each of
+// visited / frontier / next.  Batches are formed from spatially compact groups of sources (8x8 cell
+// tiles in Morton order) because cells that are close see almost the same set: their BFS levels
+// coincide for most vertices, so a vertex joins the batch's frontier about once instead of once per
+// distinct level.  Many batches (a "chunk") advance level by level together: grid = (vertex tiles,
+// batches), one launch per level serves the whole chunk and the host reads one flag per level.
 //
 // Per level and batch the step is direction-optimising:
 //   push  (top-down)  every vertex with a non-zero frontier word streams its adjacency row with
 //                     coalesced 32-bit loads and ORs its word into `next` of unvisited targets
 //                     (atomicOr on L2-resident words, filtered by a plain read of `visited`);
 //   pull  (bottom-up) every vertex that still misses some source bit streams its in-row
-//                     (transpose adjacency) and ORs the frontier words of its in-neighbours,
-//                     leaving the row as soon as every missing bit is found (warp-wide redux).
-// The choice is made on the device from the frontier's and the unvisited set's edge counts.
+//                     (transpose adjacency) and ORs the frontier words of its in-neighbours with a
+//                     warp-wide redux, leaving the row as soon as every missing bit is found.
+// A pull step wastes a full row scan on every vertex that cannot be reached yet.  A cheap coarse pass
+// removes most of that: for each group of `bfs_group` consecutive batches one single-bit BFS from ALL
+// the group's sources gives lo[w] = min over the group's sources of level(w), a lower bound for every
+// batch of the group; the pull step skips w while lo[w] > level + 1.
 // `update` folds `next` into visited/frontier and counts the new vertices per source with
 // ballot + popc (bit b of lane l's word -> source b), i.e. the reference's distribution[level].
 //
@@ -24,6 +29,7 @@
 
 #include <algorithm>
 #include <memory>
+#include <numeric>
 
 #include "vga_dev.cuh"
 
@@ -37,28 +43,42 @@ constexpr int TPB = 256;
 typedef unsigned long long u64;
 
 struct BfsDev {
-    int64_t n;           // filled vertices
+    int64_t n;  // filled vertices
     const uint64_t *rowptr;
     const uint32_t *adj;  // packed col<<6|..
     const uint64_t *t_rowptr;
     const uint32_t *t_col;
-    u64 *visited, *frontier, *next;  // [chunk][n]
-    const u64 *valid;     // [chunk] valid source bits of each batch
-    int *active;          // [chunk] 1 while the batch's frontier is non-empty
-    int *mode;            // [chunk] 0 push, 1 pull
-    u64 *stats;           // [chunk][4]: frontier edges, unvisited in-edges, new vertices, -
-    int *any;             // [1] any batch still active
+    u64 *visited, *frontier, *next;  // [batches][n]
+    const u64 *valid;                // [batches] valid source bits of each batch
+    int *active;                     // [batches] 1 while the batch's frontier is non-empty
+    int *mode;                       // [batches] 0 push, 1 pull
+    u64 *stats;                      // [batches][4]: frontier edges, candidate in-edges, new vertices, -
+    int *any;                        // [1] any batch still active
+    const uint8_t *lvl_in;           // [groups][n] coarse lower-bound level, or nullptr
+    uint8_t *lvl_out;                // [batches][n] written by the coarse pass, or nullptr
+    int group;                       // batches per coarse group
 };
 
-__global__ void k_init(BfsDev d, int64_t first_src, int64_t nsrc) {
+__global__ void k_init(BfsDev d, const int32_t *src, int64_t nsrc) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nsrc) return;
     int64_t b = i >> 6;
     int bit = (int)(i & 63);
-    int64_t v = first_src + i;
+    int64_t v = src[i];
     u64 w = 1ULL << bit;
-    d.visited[b * d.n + v] = w;  // distinct (b, v) per thread: sources of a batch are distinct vertices
+    d.visited[b * d.n + v] = w;  // sources of a batch are distinct vertices: one writer per word
     d.frontier[b * d.n + v] = w;
+}
+
+// coarse pass: all sources of a group of batches share bit 0 of the group's word
+__global__ void k_init_coarse(BfsDev d, const int32_t *src, int64_t nsrc, int per_group) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsrc) return;
+    int64_t gb = i / per_group;
+    int64_t v = src[i];
+    d.visited[gb * d.n + v] = 1ULL;
+    d.frontier[gb * d.n + v] = 1ULL;
+    d.lvl_out[gb * d.n + v] = 0;
 }
 
 // top-down step
@@ -90,18 +110,23 @@ __global__ void __launch_bounds__(TPB) k_push(BfsDev d) {
     }
 }
 
-// bottom-up step with early exit
-__global__ void __launch_bounds__(TPB) k_pull(BfsDev d) {
+// bottom-up step with early exit; `level` = level of the current frontier
+__global__ void __launch_bounds__(TPB) k_pull(BfsDev d, int level) {
     const int b = blockIdx.y;
     if (!d.active[b] || d.mode[b] != 1) return;
     const int lane = threadIdx.x & 31;
     const u64 *fr = d.frontier + (int64_t)b * d.n;
     const u64 *vis = d.visited + (int64_t)b * d.n;
     u64 *nx = d.next + (int64_t)b * d.n;
+    const uint8_t *lvl = d.lvl_in ? d.lvl_in + (int64_t)(b / d.group) * d.n : nullptr;
     const u64 valid = d.valid[b];
     for (int64_t base = (int64_t)blockIdx.x * TPB; base < d.n; base += (int64_t)gridDim.x * TPB) {
         int64_t w = base + threadIdx.x;
-        u64 need = (w < d.n) ? (valid & ~vis[w]) : 0ULL;
+        u64 need = 0ULL;
+        if (w < d.n) {
+            need = valid & ~vis[w];
+            if (need && lvl && (int)lvl[w] > level + 1) need = 0ULL;  // cannot be reached yet
+        }
         unsigned m = __ballot_sync(FULL, need != 0ULL);
         while (m) {
             int src_lane = __ffs(m) - 1;
@@ -127,8 +152,9 @@ __global__ void __launch_bounds__(TPB) k_pull(BfsDev d) {
     }
 }
 
-// fold next into visited/frontier, count new vertices per source, gather direction statistics
-__global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[chunk][64] for this level*/, int want_stats) {
+// fold next into visited/frontier, count new vertices per source, gather direction statistics;
+// `level_next` = level of the vertices being added
+__global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[batches][64] of level_next*/, int level_next) {
     const int b = blockIdx.y;
     if (!d.active[b]) return;
     __shared__ int s_cnt[64];
@@ -140,30 +166,29 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[chu
     u64 *fr = d.frontier + (int64_t)b * d.n;
     u64 *vis = d.visited + (int64_t)b * d.n;
     u64 *nx = d.next + (int64_t)b * d.n;
+    const uint8_t *lvl = d.lvl_in ? d.lvl_in + (int64_t)(b / d.group) * d.n : nullptr;
+    uint8_t *lout = d.lvl_out ? d.lvl_out + (int64_t)b * d.n : nullptr;
     const u64 valid = d.valid[b];
     int c0 = 0, c1 = 0;  // lane l counts source bits l and l+32
     u64 f_edges = 0, u_edges = 0, n_new = 0;
     for (int64_t base = (int64_t)blockIdx.x * TPB; base < d.n; base += (int64_t)gridDim.x * TPB) {
         int64_t v = base + threadIdx.x;
-        u64 nw = 0ULL, vv = valid;
+        u64 nw = 0ULL;
         if (v < d.n) {
-            vv = vis[v];
+            u64 vv = vis[v];
             nw = nx[v] & ~vv;
             if (nw) {
                 vv |= nw;
                 vis[v] = vv;
                 nx[v] = 0ULL;
+                f_edges += d.rowptr[v + 1] - d.rowptr[v];
+                n_new += 1;
+                if (lout) lout[v] = (uint8_t)min(level_next, 254);
             }
             fr[v] = nw;
-            if (want_stats) {
-                if (nw) {
-                    f_edges += d.rowptr[v + 1] - d.rowptr[v];
-                    n_new += 1;
-                }
-                if ((valid & ~vv) != 0ULL && d.t_rowptr) u_edges += d.t_rowptr[v + 1] - d.t_rowptr[v];
-            } else if (nw) {
-                n_new += 1;
-            }
+            // in-edges the next pull step would have to consider
+            if (d.t_rowptr && (valid & ~vv) != 0ULL && (!lvl || (int)lvl[v] <= level_next + 1))
+                u_edges += d.t_rowptr[v + 1] - d.t_rowptr[v];
         }
         unsigned lo_any = __reduce_or_sync(FULL, (unsigned)nw);
         unsigned hi_any = __reduce_or_sync(FULL, (unsigned)(nw >> 32));
@@ -182,7 +207,6 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[chu
     }
     if (c0) atomicAdd(&s_cnt[lane], c0);
     if (c1) atomicAdd(&s_cnt[lane + 32], c1);
-    // warp-reduce the statistics
     for (int o = 16; o > 0; o >>= 1) {
         f_edges += __shfl_down_sync(FULL, f_edges, o);
         u_edges += __shfl_down_sync(FULL, u_edges, o);
@@ -194,14 +218,14 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[chu
         if (n_new) atomicAdd(&s_stat[2], n_new);
     }
     __syncthreads();
-    if (threadIdx.x < 64 && s_cnt[threadIdx.x]) atomicAdd(&counts[b * 64 + threadIdx.x], s_cnt[threadIdx.x]);
+    if (counts && threadIdx.x < 64 && s_cnt[threadIdx.x]) atomicAdd(&counts[b * 64 + threadIdx.x], s_cnt[threadIdx.x]);
     if (threadIdx.x < 3 && s_stat[threadIdx.x]) atomicAdd(&d.stats[b * 4 + threadIdx.x], s_stat[threadIdx.x]);
 }
 
 // per batch: retire empty batches, choose the next step's direction, reset statistics
-__global__ void k_decide(BfsDev d, int chunk, int bfs_mode, int64_t alpha, u64 *work /*[3]*/) {
+__global__ void k_decide(BfsDev d, int nb, int bfs_mode, int64_t alpha, u64 *work /*[4]*/) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= chunk) return;
+    if (b >= nb) return;
     if (!d.active[b]) return;
     u64 fe = d.stats[b * 4 + 0], ue = d.stats[b * 4 + 1], nn = d.stats[b * 4 + 2];
     d.stats[b * 4 + 0] = 0;
@@ -218,11 +242,13 @@ __global__ void k_decide(BfsDev d, int chunk, int bfs_mode, int64_t alpha, u64 *
     else if (bfs_mode == 2)
         m = (fe * (u64)alpha > ue) ? 1 : 0;
     d.mode[b] = m;
-    // work[0]: adjacency entries of the vertices that expand next (sum of deg over U_l),
-    // work[1]: vertices newly reached (|U_l| summed), work[2]: in-edges offered to the pull step
-    atomicAdd(&work[0], fe);
-    atomicAdd(&work[1], nn);
-    if (m) atomicAdd(&work[2], ue);
+    if (work) {
+        // work[0]: adjacency entries of the vertices that expand next (sum of deg over U_l),
+        // work[1]: vertices newly reached (|U_l| summed), work[2]: in-edges offered to the pull step
+        atomicAdd(&work[0], fe);
+        atomicAdd(&work[1], nn);
+        if (m) atomicAdd(&work[2], ue);
+    }
 }
 
 // ---- transpose (in-edge lists of filled vertices), needed by the pull step --------------------
@@ -233,8 +259,7 @@ __global__ void k_indeg(const uint32_t *adj, uint64_t n_entries, uint32_t n, u64
     if (c < n) atomicAdd(&indeg[c], 1ULL);
 }
 __global__ void k_scatter_t(const uint64_t *rowptr, const uint32_t *adj, int64_t n, u64 *cursor, uint32_t *t_col) {
-    // one warp per source row
-    int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per source row
     int lane = threadIdx.x & 31;
     if (u >= n) return;
     for (uint64_t e = rowptr[u] + lane; e < rowptr[u + 1]; e += 32) {
@@ -247,6 +272,62 @@ __global__ void k_scatter_t(const uint64_t *rowptr, const uint32_t *adj, int64_t
 }
 
 inline unsigned blocks_for(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+inline uint32_t morton2(uint32_t x, uint32_t y) {
+    auto spread = [](uint32_t v) {
+        v &= 0xffff;
+        v = (v | (v << 8)) & 0x00ff00ff;
+        v = (v | (v << 4)) & 0x0f0f0f0f;
+        v = (v | (v << 2)) & 0x33333333;
+        v = (v | (v << 1)) & 0x55555555;
+        return v;
+    };
+    return spread(x) | (spread(y) << 1);
+}
+
+// Level loop over a set of batches.  Returns the number of levels with data (>= 1) via nlev.
+int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, DevBuf<int32_t> *counts, int *lcap,
+               int64_t counts_stride, u64 *work, StageTimer &mt, int *nlev_out) {
+    cudaStream_t st = ctx->stream;
+    Timing &tm = ctx->timing;
+    const unsigned xblocks = (unsigned)std::min<int64_t>((d.n + TPB - 1) / TPB, 4096);
+    int level = 0, nlev = 1;
+    while (radius == -1 || level < radius) {
+        dim3 grid(xblocks, (unsigned)nb);
+        k_push<<<grid, TPB, 0, st>>>(d);
+        tm.launches++;
+        tm.main_launches++;
+        if (bfs_mode != 0 && level > 0) {
+            k_pull<<<grid, TPB, 0, st>>>(d, level);
+            tm.launches++;
+            tm.main_launches++;
+        }
+        if (counts && level + 1 >= *lcap) {
+            mt.stop();
+            DevBuf<int32_t> bigger;
+            VGA_TRY(bigger.alloc_zero((size_t)(*lcap) * 2 * counts_stride, st));
+            VGA_CUDA(cudaMemcpyAsync(bigger.p, counts->p, sizeof(int32_t) * (size_t)(*lcap) * counts_stride,
+                                     cudaMemcpyDeviceToDevice, st));
+            VGA_CUDA(cudaStreamSynchronize(st));
+            *counts = std::move(bigger);
+            *lcap *= 2;
+            mt.start();
+        }
+        VGA_CUDA(cudaMemsetAsync(d.any, 0, sizeof(int), st));
+        k_update<<<grid, TPB, 0, st>>>(d, counts ? counts->p + (size_t)(level + 1) * counts_stride : nullptr, level + 1);
+        k_decide<<<blocks_for(nb, 128), 128, 0, st>>>(d, (int)nb, bfs_mode, ctx->opt.pull_alpha, work);
+        tm.launches += 2;
+        tm.main_launches += 2;
+        int h_any = 0;
+        VGA_CUDA(cudaMemcpyAsync(&h_any, d.any, sizeof(int), cudaMemcpyDeviceToHost, st));
+        VGA_CUDA(cudaStreamSynchronize(st));
+        if (!h_any) break;
+        level++;
+        nlev = level + 1;
+    }
+    *nlev_out = nlev;
+    return VGA_OK;
+}
 
 }  // namespace
 
@@ -307,18 +388,42 @@ int run_global(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_
     if (bfs_mode != 0) VGA_TRY(ensure_transpose(ctx, g));
     kt.stop();
 
+    // ---- source order: 8x8 cell tiles in Morton order (needs cell coordinates), else ordinal order
+    std::vector<int32_t> order((size_t)nsrc);
+    std::iota(order.begin(), order.end(), (int32_t)src_begin);
+    const bool spatial = ctx->opt.bfs_order != 0 && (int64_t)g->h_refs.size() >= n;
+    if (spatial) {
+        std::vector<uint64_t> key((size_t)nsrc);
+        for (int64_t i = 0; i < nsrc; i++) {
+            uint32_t r = (uint32_t)g->h_refs[(size_t)(src_begin + i)];
+            uint32_t x = r >> 16, y = r & 0xffff;
+            key[(size_t)i] = ((uint64_t)morton2(x >> 3, y >> 3) << 38) | ((uint64_t)(x & 7) << 35) | ((uint64_t)(y & 7) << 32) |
+                             (uint64_t)(uint32_t)i;
+        }
+        std::sort(key.begin(), key.end());
+        for (int64_t i = 0; i < nsrc; i++) order[(size_t)i] = (int32_t)(src_begin + (int64_t)(key[(size_t)i] & 0xffffffffu));
+    }
+    DevBuf<int32_t> d_order;
+    VGA_TRY(d_order.alloc((size_t)nsrc));
+    VGA_CUDA(cudaMemcpyAsync(d_order.p, order.data(), sizeof(int32_t) * nsrc, cudaMemcpyHostToDevice, st));
+
     const int64_t nbatch = (nsrc + 63) / 64;
-    // chunk size: state of 3 words per (batch, vertex); keep below ~40% of free memory and 48 GB
+    const int group = (int)std::max<int64_t>(1, ctx->opt.bfs_group);
+    const bool coarse = bfs_mode != 0 && ctx->opt.bfs_coarse != 0;
+    // chunk size: 3 words per (batch, vertex) + the coarse pass; below ~40% of free memory and 48 GB
     size_t free_b = 0, total_b = 0;
     VGA_CUDA(cudaMemGetInfo(&free_b, &total_b));
     int64_t budget = (int64_t)std::min<size_t>((size_t)(free_b * 0.4), (size_t)48 << 30);
-    int64_t chunk = ctx->opt.bfs_chunk > 0 ? ctx->opt.bfs_chunk : std::max<int64_t>(1, budget / (24 * std::max<int64_t>(n, 1)));
+    int64_t chunk = ctx->opt.bfs_chunk > 0 ? ctx->opt.bfs_chunk : std::max<int64_t>(1, budget / (26 * std::max<int64_t>(n, 1)));
     chunk = std::min<int64_t>(chunk, nbatch);
     chunk = std::min<int64_t>(chunk, 65535);
+    if (chunk > group) chunk -= chunk % group;  // whole groups per chunk
+    const int64_t max_groups = (chunk + group - 1) / group;
 
-    DevBuf<u64> visited, frontier, next, valid, stats, work;
-    DevBuf<int> active, mode, any;
+    DevBuf<u64> visited, frontier, next, valid, stats, work, c_visited, c_frontier, c_next, c_valid, c_stats;
+    DevBuf<int> active, mode, any, c_active, c_mode;
     DevBuf<int32_t> counts;
+    DevBuf<uint8_t> lvl;
     int lcap = 16;
     VGA_TRY(visited.alloc((size_t)chunk * n));
     VGA_TRY(frontier.alloc((size_t)chunk * n));
@@ -330,6 +435,16 @@ int run_global(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_
     VGA_TRY(mode.alloc((size_t)chunk));
     VGA_TRY(any.alloc(1));
     VGA_TRY(counts.alloc((size_t)lcap * chunk * 64));
+    if (coarse) {
+        VGA_TRY(c_visited.alloc((size_t)max_groups * n));
+        VGA_TRY(c_frontier.alloc((size_t)max_groups * n));
+        VGA_TRY(c_next.alloc((size_t)max_groups * n));
+        VGA_TRY(c_valid.alloc((size_t)max_groups));
+        VGA_TRY(c_stats.alloc((size_t)max_groups * 4));
+        VGA_TRY(c_active.alloc((size_t)max_groups));
+        VGA_TRY(c_mode.alloc((size_t)max_groups));
+        VGA_TRY(lvl.alloc((size_t)max_groups * n));
+    }
 
     BfsDev d;
     d.n = n;
@@ -345,75 +460,74 @@ int run_global(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_
     d.mode = mode.p;
     d.stats = stats.p;
     d.any = any.p;
+    d.lvl_in = coarse ? lvl.p : nullptr;
+    d.lvl_out = nullptr;
+    d.group = group;
 
-    const unsigned xblocks = (unsigned)std::min<int64_t>((n + TPB - 1) / TPB, 4096);
     int deepest = 0;
     std::vector<int32_t> h_counts;
     std::vector<u64> h_valid;
+    std::vector<int> ones;
 
     for (int64_t b0 = 0; b0 < nbatch; b0 += chunk) {
         const int64_t cb = std::min<int64_t>(chunk, nbatch - b0);
-        const int64_t first = src_begin + b0 * 64;
-        const int64_t cs = std::min<int64_t>(cb * 64, src_end - first);
+        const int64_t first = b0 * 64;  // index into the ordered source list
+        const int64_t cs = std::min<int64_t>(cb * 64, nsrc - first);
         if (ctx->cancel && ctx->cancel(ctx->user)) {
             set_error("cancelled");
             return VGA_ERR_CANCELLED;
         }
+        kt.start();
+        // ---- coarse pass: one single-bit BFS per group of batches (push only)
+        if (coarse) {
+            const int64_t ng = (cb + group - 1) / group;
+            BfsDev c = d;
+            c.visited = c_visited.p;
+            c.frontier = c_frontier.p;
+            c.next = c_next.p;
+            c.valid = c_valid.p;
+            c.active = c_active.p;
+            c.mode = c_mode.p;
+            c.stats = c_stats.p;
+            c.lvl_in = nullptr;
+            c.lvl_out = lvl.p;
+            c.group = 1;
+            h_valid.assign((size_t)ng, 1ULL);
+            ones.assign((size_t)ng, 1);
+            VGA_CUDA(cudaMemcpyAsync(c_valid.p, h_valid.data(), sizeof(u64) * ng, cudaMemcpyHostToDevice, st));
+            VGA_CUDA(cudaMemcpyAsync(c_active.p, ones.data(), sizeof(int) * ng, cudaMemcpyHostToDevice, st));
+            VGA_CUDA(cudaMemsetAsync(c_visited.p, 0, sizeof(u64) * (size_t)ng * n, st));
+            VGA_CUDA(cudaMemsetAsync(c_frontier.p, 0, sizeof(u64) * (size_t)ng * n, st));
+            VGA_CUDA(cudaMemsetAsync(c_next.p, 0, sizeof(u64) * (size_t)ng * n, st));
+            VGA_CUDA(cudaMemsetAsync(c_stats.p, 0, sizeof(u64) * (size_t)ng * 4, st));
+            VGA_CUDA(cudaMemsetAsync(c_mode.p, 0, sizeof(int) * (size_t)ng, st));
+            VGA_CUDA(cudaMemsetAsync(lvl.p, 0xff, (size_t)ng * n, st));
+            VGA_CUDA(cudaStreamSynchronize(st));  // host staging vectors are reused below
+            k_init_coarse<<<blocks_for(cs, 256), 256, 0, st>>>(c, d_order.p + first, cs, 64 * group);
+            tm.launches++;
+            mt.start();
+            int cl = 0;
+            VGA_TRY(run_levels(ctx, c, ng, radius, 0, nullptr, nullptr, 0, nullptr, mt, &cl));
+            mt.stop();
+        }
+        // ---- exact pass
         h_valid.assign((size_t)cb, ~0ULL);
         if (cs & 63) h_valid[(size_t)cb - 1] = (1ULL << (cs & 63)) - 1ULL;
-        kt.start();
+        ones.assign((size_t)cb, 1);
         VGA_CUDA(cudaMemcpyAsync(valid.p, h_valid.data(), sizeof(u64) * cb, cudaMemcpyHostToDevice, st));
+        VGA_CUDA(cudaMemcpyAsync(active.p, ones.data(), sizeof(int) * cb, cudaMemcpyHostToDevice, st));
         VGA_CUDA(cudaMemsetAsync(visited.p, 0, sizeof(u64) * (size_t)cb * n, st));
         VGA_CUDA(cudaMemsetAsync(frontier.p, 0, sizeof(u64) * (size_t)cb * n, st));
         VGA_CUDA(cudaMemsetAsync(next.p, 0, sizeof(u64) * (size_t)cb * n, st));
         VGA_CUDA(cudaMemsetAsync(stats.p, 0, sizeof(u64) * (size_t)cb * 4, st));
-        VGA_CUDA(cudaMemsetAsync(mode.p, 0, sizeof(int) * (size_t)cb, st));
+        VGA_CUDA(cudaMemsetAsync(mode.p, 0, sizeof(int) * (size_t)cb, st));  // level 0 always pushes
         VGA_CUDA(cudaMemsetAsync(counts.p, 0, sizeof(int32_t) * (size_t)lcap * chunk * 64, st));
-        {
-            std::vector<int> ones((size_t)cb, 1);
-            VGA_CUDA(cudaMemcpyAsync(active.p, ones.data(), sizeof(int) * cb, cudaMemcpyHostToDevice, st));
-            VGA_CUDA(cudaStreamSynchronize(st));
-        }
-        k_init<<<blocks_for(cs, 256), 256, 0, st>>>(d, first, cs);
+        VGA_CUDA(cudaStreamSynchronize(st));
+        k_init<<<blocks_for(cs, 256), 256, 0, st>>>(d, d_order.p + first, cs);
         tm.launches++;
-        if (bfs_mode == 1) VGA_CUDA(cudaMemsetAsync(mode.p, 0, sizeof(int) * (size_t)cb, st));  // level 0 always pushes
         mt.start();
-        int level = 0;  // frontier holds level `level`
         int nlev = 1;
-        while (radius == -1 || level < radius) {
-            dim3 grid(xblocks, (unsigned)cb);
-            k_push<<<grid, TPB, 0, st>>>(d);
-            tm.launches++;
-            tm.main_launches++;
-            if (bfs_mode != 0 && level > 0) {
-                k_pull<<<grid, TPB, 0, st>>>(d);
-                tm.launches++;
-                tm.main_launches++;
-            }
-            if (level + 1 >= lcap) {
-                // grow the level histogram
-                mt.stop();
-                DevBuf<int32_t> bigger;
-                VGA_TRY(bigger.alloc_zero((size_t)lcap * 2 * chunk * 64, st));
-                VGA_CUDA(cudaMemcpyAsync(bigger.p, counts.p, sizeof(int32_t) * (size_t)lcap * chunk * 64,
-                                         cudaMemcpyDeviceToDevice, st));
-                VGA_CUDA(cudaStreamSynchronize(st));
-                counts = std::move(bigger);
-                lcap *= 2;
-                mt.start();
-            }
-            VGA_CUDA(cudaMemsetAsync(any.p, 0, sizeof(int), st));
-            k_update<<<grid, TPB, 0, st>>>(d, counts.p + (size_t)(level + 1) * chunk * 64, 1);
-            k_decide<<<blocks_for(cb, 128), 128, 0, st>>>(d, (int)cb, bfs_mode, ctx->opt.pull_alpha, work.p);
-            tm.launches += 2;
-            tm.main_launches += 2;
-            int h_any = 0;
-            VGA_CUDA(cudaMemcpyAsync(&h_any, any.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-            VGA_CUDA(cudaStreamSynchronize(st));
-            if (!h_any) break;
-            level++;
-            nlev = level + 1;
-        }
+        VGA_TRY(run_levels(ctx, d, cb, radius, bfs_mode, &counts, &lcap, chunk * 64, work.p, mt, &nlev));
         mt.stop();
         kt.stop();
         VGA_CUDA(cudaGetLastError());
@@ -426,9 +540,9 @@ int run_global(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_
                                  cudaMemcpyDeviceToHost, st));
         dt.stop();
         for (int64_t i = 0; i < cs; i++) {
-            int64_t o = (first - src_begin) + i;
-            int64_t b = i >> 6;
-            int bit = (int)(i & 63);
+            const int64_t o = (int64_t)order[(size_t)(first + i)] - src_begin;
+            const int64_t b = i >> 6;
+            const int bit = (int)(i & 63);
             int64_t tn = 1, td = 0;
             if (dist && max_levels > 0) {
                 for (int l = 0; l < max_levels; l++) dist[o * max_levels + l] = 0;
@@ -445,7 +559,6 @@ int run_global(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_
         }
         if (ctx->progress) ctx->progress(ctx->user, std::min<int64_t>(nsrc, (b0 + cb) * 64), nsrc);
     }
-    // deepest counts levels 0..deepest-1 that were *computed*; trailing empty level is not reported
     if (levels_used) *levels_used = deepest;
     {
         u64 hw[4] = {0, 0, 0, 0};
@@ -453,12 +566,9 @@ int run_global(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_
         uint64_t rp[2] = {0, 0};
         VGA_CUDA(cudaMemcpy(&rp[0], g->rowptr.p + src_begin, sizeof(uint64_t), cudaMemcpyDeviceToHost));
         VGA_CUDA(cudaMemcpy(&rp[1], g->rowptr.p + src_end, sizeof(uint64_t), cudaMemcpyDeviceToHost));
-        // algorithmic bytes (SURVEY.md §8d with B = 64, CSR rows of 4 B entries): per batch and level,
+        // algorithmic bytes (SURVEY.md §8d with B = 64, CSR rows of 4-byte entries), per batch and level:
         // rows of the expanding vertices + one frontier word read per expanding vertex + one
-        // visited/next read-modify-write (2 words) per newly reached vertex.  Level 0 expands the
-        // sources themselves.  The last level's vertices are counted as expanding only if they were
-        // (radius cut-off): hw[0] already excludes nothing, so subtract nothing -- documented upper
-        // bound differs from the exact figure by the final (empty) expansion only.
+        // visited/next read-modify-write (2 words) per newly reached vertex; level 0 expands the sources.
         const double src_edges = (double)(rp[1] - rp[0]);
         tm.algo_bytes = 4.0 * ((double)hw[0] + src_edges) + 8.0 * ((double)hw[1] + (double)nsrc) + 16.0 * (double)hw[1];
     }

@@ -14,6 +14,7 @@
 namespace vga {
 
 static thread_local std::string g_last_error;
+thread_local cudaStream_t g_alloc_stream = nullptr;
 
 void set_error(const std::string &msg) { g_last_error = msg; }
 
@@ -32,6 +33,9 @@ static int set_option(Options &o, const std::string &key, int64_t value) {
     else if (key == "sieve_big_bcap") o.sieve_big_bcap = value;
     else if (key == "build_chunk_entries") o.build_chunk_entries = value;
     else if (key == "pull_alpha") o.pull_alpha = value;
+    else if (key == "bfs_order") o.bfs_order = value;
+    else if (key == "bfs_group") o.bfs_group = value;
+    else if (key == "bfs_coarse") o.bfs_coarse = value;
     else return VGA_ERR_INVALID;
     return VGA_OK;
 }
@@ -131,6 +135,13 @@ int vga_ctx_create(int device, vga_ctx **out) {
     VGA_CUDA(cudaGetDeviceProperties(&p, device));
     c->sm_count = p.multiProcessorCount;
     c->smem_optin = p.sharedMemPerBlockOptin;
+    {
+        // keep freed blocks in the stream-ordered pool (see g_alloc_stream)
+        cudaMemPool_t pool;
+        VGA_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = UINT64_MAX;
+        VGA_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     Options &o = c->opt;
     o.bfs_mode = env_i64("VGA_BFS_MODE", o.bfs_mode);
     o.bfs_chunk = env_i64("VGA_BFS_CHUNK", o.bfs_chunk);
@@ -144,6 +155,12 @@ int vga_ctx_create(int device, vga_ctx **out) {
 void vga_ctx_destroy(vga_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    }
+    if (g_alloc_stream == ctx->stream) g_alloc_stream = nullptr;
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -194,6 +211,7 @@ int vga_grid_upload(vga_ctx *ctx, const vga_grid *grid, vga_dgrid **out) {
         return VGA_ERR_INVALID;
     }
     VGA_CUDA(cudaSetDevice(ctx->device));
+    g_alloc_stream = ctx->stream;
     ctx->timing = Timing();
     const int64_t cells = (int64_t)grid->cols * grid->rows;
     std::unique_ptr<vga_dgrid> d(new vga_dgrid());
@@ -257,12 +275,19 @@ int vga_grid_upload(vga_ctx *ctx, const vga_grid *grid, vga_dgrid **out) {
     return VGA_OK;
 }
 
-void vga_dgrid_free(vga_dgrid *g) { delete g; }
+void vga_dgrid_free(vga_dgrid *g) {
+    if (g && g->ctx) {
+        cudaSetDevice(g->ctx->device);
+        g_alloc_stream = g->ctx->stream;
+    }
+    delete g;
+}
 
 int vga_graph_build_resident(vga_ctx *ctx, const vga_dgrid *grid, int64_t src_begin, int64_t src_end, vga_graph **out) {
     if (!ctx || !grid || !out) return VGA_ERR_INVALID;
     *out = nullptr;
     VGA_CUDA(cudaSetDevice(ctx->device));
+    g_alloc_stream = ctx->stream;
     double h2d = ctx->timing.h2d_ms;
     ctx->timing = Timing();
     ctx->timing.h2d_ms = h2d;
@@ -288,6 +313,7 @@ int vga_graph_from_csr(vga_ctx *ctx, int64_t n_cells, int64_t n_ghosts, const ui
         return VGA_ERR_UNSUPPORTED;
     }
     VGA_CUDA(cudaSetDevice(ctx->device));
+    g_alloc_stream = ctx->stream;
     ctx->timing = Timing();
     cudaStream_t st = ctx->stream;
     const int64_t entries = (int64_t)rowptr[n_cells];
@@ -338,6 +364,7 @@ int vga_graph_from_device_rows(vga_ctx *ctx, int64_t n_cells, int64_t n_ghosts, 
     if (!ctx || !out || !d_rowptr || n_cells < 0 || n_entries < 0) return VGA_ERR_INVALID;
     *out = nullptr;
     VGA_CUDA(cudaSetDevice(ctx->device));
+    g_alloc_stream = ctx->stream;
     ctx->timing = Timing();
     cudaStream_t st = ctx->stream;
     std::unique_ptr<vga_graph> g(new vga_graph());
@@ -360,7 +387,10 @@ int vga_graph_from_device_rows(vga_ctx *ctx, int64_t n_cells, int64_t n_ghosts, 
 
 void vga_graph_free(vga_graph *g) {
     if (!g) return;
-    if (g->ctx) cudaSetDevice(g->ctx->device);
+    if (g->ctx) {
+        cudaSetDevice(g->ctx->device);
+        g_alloc_stream = g->ctx->stream;
+    }
     delete g;
 }
 
@@ -373,6 +403,7 @@ int64_t vga_graph_src_end(const vga_graph *g) { return g ? g->src_end : -1; }
 int vga_graph_csr(const vga_graph *g, uint64_t *rowptr, uint32_t *col, uint8_t *bin, uint8_t *accepted) {
     if (!g) return VGA_ERR_INVALID;
     VGA_CUDA(cudaSetDevice(g->ctx->device));
+    g_alloc_stream = g->ctx->stream;
     const int64_t rows = g->src_end - g->src_begin;
     if (rowptr) VGA_CUDA(cudaMemcpy(rowptr, g->rowptr.p, sizeof(uint64_t) * (rows + 1), cudaMemcpyDeviceToHost));
     if ((col || bin || accepted) && g->entries > 0) {
@@ -398,6 +429,15 @@ int vga_graph_cell_refs(const vga_graph *g, int32_t *ref) {
     return VGA_OK;
 }
 
+int vga_graph_set_cell_refs(vga_graph *g, const int32_t *ref, int64_t count) {
+    if (!g || !ref || count != g->n + g->ghosts) {
+        set_error("vga_graph_set_cell_refs: count must be cells + ghosts");
+        return VGA_ERR_INVALID;
+    }
+    g->h_refs.assign(ref, ref + count);
+    return VGA_OK;
+}
+
 int vga_graph_node_stats(const vga_graph *g, int32_t *connectivity, double *sum_d, double *sum_d2, float *far_bin_dists,
                          int32_t *bin_count, uint8_t *grid_connections) {
     if (!g) return VGA_ERR_INVALID;
@@ -406,6 +446,7 @@ int vga_graph_node_stats(const vga_graph *g, int32_t *connectivity, double *sum_
         return VGA_ERR_INVALID;
     }
     VGA_CUDA(cudaSetDevice(g->ctx->device));
+    g_alloc_stream = g->ctx->stream;
     const int64_t rows = g->src_end - g->src_begin;
     if (rows == 0) return VGA_OK;
     if (connectivity) VGA_CUDA(cudaMemcpy(connectivity, g->connectivity.p, sizeof(int32_t) * rows, cudaMemcpyDeviceToHost));
@@ -435,6 +476,7 @@ int vga_global(vga_ctx *ctx, const vga_graph *g, int radius, int64_t src_begin, 
         return VGA_ERR_INVALID;
     }
     VGA_CUDA(cudaSetDevice(ctx->device));
+    g_alloc_stream = ctx->stream;
     ctx->timing = Timing();
     return run_global(ctx, const_cast<vga_graph *>(g), radius, src_begin, src_end, total_nodes, total_depth, dist, max_levels,
                       levels_used);
@@ -486,6 +528,7 @@ int vga_local(vga_ctx *ctx, const vga_graph *g, int64_t src_begin, int64_t src_e
               int32_t *total, float *control) {
     if (!ctx || !g) return VGA_ERR_INVALID;
     VGA_CUDA(cudaSetDevice(ctx->device));
+    g_alloc_stream = ctx->stream;
     ctx->timing = Timing();
     return run_local(ctx, const_cast<vga_graph *>(g), src_begin, src_end, cluster, k, total, control);
 }

@@ -30,7 +30,13 @@ void set_error(const std::string &msg);
         if (rc__ != VGA_OK) return rc__; \
     } while (0)
 
-// RAII device buffer (cudaMalloc / cudaFree); zero-size allocations are represented by nullptr.
+// Stream all allocations of the calling thread are ordered on (set by every C-ABI entry point to
+// its context's stream).  Device memory comes from CUDA's stream-ordered pool with an unlimited
+// release threshold, so the GB-sized BFS state / edge buffers are recycled between calls instead of
+// being mapped and unmapped every time (cudaMalloc/cudaFree of GBs costs 100s of ms).
+extern thread_local cudaStream_t g_alloc_stream;
+
+// RAII device buffer (cudaMallocAsync / cudaFreeAsync); zero-size allocations are nullptr.
 template <typename T> struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
@@ -50,14 +56,14 @@ template <typename T> struct DevBuf {
     }
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, g_alloc_stream);
         p = nullptr;
         n = 0;
     }
     int alloc(size_t count) {
         release();
         if (count == 0) return VGA_OK;
-        VGA_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+        VGA_CUDA(cudaMallocAsync((void **)&p, count * sizeof(T), g_alloc_stream));
         n = count;
         return VGA_OK;
     }
@@ -82,7 +88,10 @@ struct Options {
     int64_t sieve_big_gcap = 4096;
     int64_t sieve_big_bcap = 32768;
     int64_t build_chunk_entries = (int64_t)1 << 30;
-    int64_t pull_alpha = 4;      // switch to pull when frontier edges*alpha > unvisited edges (per batch)
+    int64_t pull_alpha = 4;      // switch to pull when frontier edges*alpha > candidate in-edges (per batch)
+    int64_t bfs_order = 1;       // 1: batches from 8x8 cell tiles in Morton order, 0: x-major ordinals
+    int64_t bfs_group = 16;      // batches per coarse lower-bound group
+    int64_t bfs_coarse = 0;      // 1: coarse single-bit pass prunes the pull step (measured: not a win on office plans)
 };
 
 }  // namespace vga

@@ -129,6 +129,9 @@ int64_t vga_graph_src_end(const vga_graph *g);
 int vga_graph_csr(const vga_graph *g, uint64_t *rowptr, uint32_t *col, uint8_t *bin, uint8_t *accepted);
 /* Packed PixelRef ((x<<16)+(y&0xffff)) of every vertex: N cells then G ghosts. */
 int vga_graph_cell_refs(const vga_graph *g, int32_t *ref);
+/* Attach packed PixelRefs (N cells, then G ghosts) to an adopted graph so that the analyses can form
+ * spatially coherent source batches.  Optional: results never depend on it, only speed does. */
+int vga_graph_set_cell_refs(vga_graph *g, const int32_t *ref, int64_t count);
 /* Per source row: what sparkPixel2 stores besides the pixel lists.  connectivity = neighbourhood_size,
  * sum_d / sum_d2 = total_dist / total_dist_sqr (double running sums in reference order),
  * far_bin_dists [rows*32] floats, bin_count [rows*32] (accepted pixels per bin),
