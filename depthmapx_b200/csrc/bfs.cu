@@ -92,14 +92,29 @@ __global__ void __launch_bounds__(TPB) k_push(BfsDev d) {
     for (int64_t base = (int64_t)blockIdx.x * TPB; base < d.n; base += (int64_t)gridDim.x * TPB) {
         int64_t u = base + threadIdx.x;
         u64 f = (u < d.n) ? fr[u] : 0ULL;
+        // every lane fetches its own row bounds up front (coalesced); they are broadcast below
+        uint64_t my0 = 0, my1 = 0;
+        if (f != 0ULL) {
+            my0 = d.rowptr[u];
+            my1 = d.rowptr[u + 1];
+        }
         unsigned m = __ballot_sync(FULL, f != 0ULL);
         while (m) {
             int src_lane = __ffs(m) - 1;
             m &= m - 1;
             u64 fw = __shfl_sync(FULL, f, src_lane);
-            int64_t uu = (base + (threadIdx.x & ~31)) + src_lane;
-            uint64_t e0 = d.rowptr[uu], e1 = d.rowptr[uu + 1];
-            for (uint64_t e = e0 + lane; e < e1; e += 32) {
+            uint64_t e0 = __shfl_sync(FULL, my0, src_lane), e1 = __shfl_sync(FULL, my1, src_lane);
+            uint64_t e = e0 + lane;
+            // two independent entries per lane per trip: more loads in flight
+            for (; e + 32 < e1; e += 64) {
+                uint32_t c0 = d.adj[e] >> 6, c1 = d.adj[e + 32] >> 6;
+                u64 v0 = (c0 < (uint32_t)d.n) ? vis[c0] : ~0ULL;
+                u64 v1 = (c1 < (uint32_t)d.n) ? vis[c1] : ~0ULL;
+                u64 a0 = fw & ~v0, a1 = fw & ~v1;
+                if (a0) atomicOr(&nx[c0], a0);
+                if (a1) atomicOr(&nx[c1], a1);
+            }
+            if (e < e1) {
                 uint32_t c = d.adj[e] >> 6;
                 if (c < (uint32_t)d.n) {
                     u64 add = fw & ~vis[c];
@@ -127,27 +142,46 @@ __global__ void __launch_bounds__(TPB) k_pull(BfsDev d, int level) {
             need = valid & ~vis[w];
             if (need && lvl && (int)lvl[w] > level + 1) need = 0ULL;  // cannot be reached yet
         }
-        unsigned m = __ballot_sync(FULL, need != 0ULL);
-        while (m) {
-            int src_lane = __ffs(m) - 1;
-            m &= m - 1;
-            u64 nd = __shfl_sync(FULL, need, src_lane);
-            int64_t ww = (base + (threadIdx.x & ~31)) + src_lane;
-            uint64_t e0 = d.t_rowptr[ww], e1 = d.t_rowptr[ww + 1];
-            u64 acc = 0ULL;
-            for (uint64_t e = e0; e < e1; e += 32) {
-                uint64_t ee = e + lane;
-                u64 g = 0ULL;
-                if (ee < e1) g = fr[d.t_col[ee]];
-                unsigned lo = __reduce_or_sync(FULL, (unsigned)g);
-                unsigned hi = __reduce_or_sync(FULL, (unsigned)(g >> 32));
-                acc |= ((u64)hi << 32) | lo;
-                if ((acc & nd) == nd) break;
+        uint64_t my0 = 0, my1 = 0;
+        if (need != 0ULL) {
+            my0 = d.t_rowptr[w];
+            my1 = d.t_rowptr[w + 1];
+        }
+        // Candidates of this warp are served by 4 groups of 8 lanes, each group scanning a different
+        // vertex's in-row: 4 rows in flight per warp hide the dependent index->word latency, and a
+        // row is left after 8 (not 32) in-neighbours when they already cover the missing bits.
+        const unsigned m = __ballot_sync(FULL, need != 0ULL);
+        const int ncand = __popc(m);
+        const int grp = lane >> 3, gl = lane & 7;
+        const unsigned gmask = 0xffu << (grp * 8);
+        for (int r = 0; r * 4 < ncand; r++) {
+            const int k = r * 4 + grp;
+            const bool has = k < ncand;
+            const int src_lane = has ? (int)__fns(m, 0, k + 1) : 0;
+            const u64 nd = __shfl_sync(FULL, need, src_lane);
+            const uint64_t e0 = __shfl_sync(FULL, my0, src_lane), e1 = __shfl_sync(FULL, my1, src_lane);
+            if (has) {
+                u64 acc = 0ULL;
+                for (uint64_t e = e0; e < e1; e += 16) {
+                    const uint64_t ea = e + gl, eb = e + 8 + gl;
+                    u64 g0 = 0ULL, g1 = 0ULL;
+                    uint32_t ca = 0, cb = 0;
+                    if (ea < e1) ca = d.t_col[ea];
+                    if (eb < e1) cb = d.t_col[eb];
+                    if (ea < e1) g0 = fr[ca];
+                    if (eb < e1) g1 = fr[cb];
+                    g0 |= g1;
+                    unsigned lo = __reduce_or_sync(gmask, (unsigned)g0);
+                    unsigned hi = __reduce_or_sync(gmask, (unsigned)(g0 >> 32));
+                    acc |= ((u64)hi << 32) | lo;
+                    if ((acc & nd) == nd) break;
+                }
+                if (gl == 0) {
+                    u64 nw = acc & nd;
+                    if (nw) nx[(base + (threadIdx.x & ~31)) + src_lane] = nw;
+                }
             }
-            if (lane == 0) {
-                u64 nw = acc & nd;
-                if (nw) nx[ww] = nw;
-            }
+            __syncwarp();
         }
     }
 }
@@ -402,6 +436,58 @@ int run_global(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_
         }
         std::sort(key.begin(), key.end());
         for (int64_t i = 0; i < nsrc; i++) order[(size_t)i] = (int32_t)(src_begin + (int64_t)(key[(size_t)i] & 0xffffffffu));
+        if (ctx->opt.bfs_order >= 2 && g->has_stats && g->src_begin == 0 && g->src_end == n) {
+            // Wall-respecting clusters: a raw 8x8 tile often straddles a wall, which puts cells of two
+            // rooms (very different level structure) into one batch.  Grow each batch as a flood of up
+            // to 64 cells over the direct-neighbour links (grid connection bits, i.e. the 8 neighbours
+            // that are actually visible), seeded in Morton order.
+            std::vector<uint8_t> gc((size_t)n);
+            VGA_CUDA(cudaMemcpy(gc.data(), g->gridconn.p, (size_t)n, cudaMemcpyDeviceToHost));
+            int maxx = 0, maxy = 0;
+            for (int64_t v = 0; v < n; v++) {
+                uint32_t r = (uint32_t)g->h_refs[(size_t)v];
+                maxx = std::max(maxx, (int)(r >> 16));
+                maxy = std::max(maxy, (int)(r & 0xffff));
+            }
+            const int64_t cols = maxx + 1, rows = maxy + 1;
+            std::vector<int32_t> ord_of((size_t)(cols * rows), -1);
+            for (int64_t v = 0; v < n; v++) {
+                uint32_t r = (uint32_t)g->h_refs[(size_t)v];
+                ord_of[(size_t)((int64_t)(r >> 16) * rows + (r & 0xffff))] = (int32_t)v;
+            }
+            static const int dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
+            static const int dy[8] = {0, 1, 1, 1, 0, -1, -1, -1};
+            std::vector<uint8_t> taken((size_t)n, 0);
+            std::vector<int32_t> clustered, queue;
+            clustered.reserve((size_t)nsrc);
+            for (int64_t i = 0; i < nsrc; i++) {
+                const int32_t seed = order[(size_t)i];
+                if (taken[(size_t)seed]) continue;
+                queue.clear();
+                queue.push_back(seed);
+                taken[(size_t)seed] = 1;
+                size_t head = 0;
+                int count = 0;
+                while (head < queue.size() && count < 64) {
+                    const int32_t v = queue[head++];
+                    clustered.push_back(v);
+                    count++;
+                    const uint32_t r = (uint32_t)g->h_refs[(size_t)v];
+                    const int x = (int)(r >> 16), y = (int)(r & 0xffff);
+                    for (int k = 0; k < 8; k++) {
+                        if (!(gc[(size_t)v] & (1 << k))) continue;
+                        const int nx = x + dx[k], ny = y + dy[k];
+                        if (nx < 0 || nx >= cols || ny < 0 || ny >= rows) continue;
+                        const int32_t w = ord_of[(size_t)((int64_t)nx * rows + ny)];
+                        if (w < (int32_t)src_begin || w >= (int32_t)src_end || taken[(size_t)w]) continue;
+                        taken[(size_t)w] = 1;
+                        queue.push_back(w);
+                    }
+                }
+                for (; head < queue.size(); head++) taken[(size_t)queue[head]] = 0;  // not placed: free again
+            }
+            if ((int64_t)clustered.size() == nsrc) order.swap(clustered);
+        }
     }
     DevBuf<int32_t> d_order;
     VGA_TRY(d_order.alloc((size_t)nsrc));

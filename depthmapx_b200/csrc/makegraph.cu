@@ -683,6 +683,265 @@ template <bool EMIT> __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_s
     }
 }
 
+// ---- thread-per-task variant ------------------------------------------------------------------
+// One THREAD per (source, octant).  ncu on the warp kernel (profiles/r1_*) showed ~230 warp
+// instructions per depth row at 45 % lane use and a long tail (8 warps of a CTA wait for the slowest
+// octant): on plans with short rows (rooms, corridors) a row holds only a handful of cells, so the
+// warp-wide scans cost more than the cells.  Here every thread walks its own octant sequentially
+// (the same per-gap, per-index order as sieve2), 32 consecutive threads take the same octant of 32
+// consecutive cells (octant-major numbering) so that warps stay convergent, the gap list lives in
+// shared memory (TG entries per thread, interleaved), the row's blocks in local memory.  Tasks that
+// exceed TG gaps / TB blocks are flagged and re-run by the warp kernel with global scratch.
+constexpr int TT = 128;  // threads per CTA
+constexpr int TG = 8;    // gaps per thread (shared memory)
+constexpr int TB = 24;   // blocks per row per thread (local memory)
+
+template <bool EMIT> __global__ void __launch_bounds__(TT) k_sieve_thread(SieveArgs a, int64_t nsrc) {
+    __shared__ Zone s_gaps[TG * TT];
+    const int tid = threadIdx.x;
+    const int64_t t = (int64_t)blockIdx.x * TT + tid;
+    if (t >= a.ntasks) return;
+    const int q = (int)(t / nsrc);
+    const int64_t src_local = t % nsrc;
+    const int64_t task = src_local * 8 + q;
+    if (a.bigflag[task]) return;
+    const GridDev &g = a.g;
+    const int32_t ref = g.cellref[a.src_begin + src_local];
+    const int cx = ref >> 16, cy = ref & 0xffff;
+    uint64_t acc_off = 0, fill_off = 0;
+    if (EMIT) {
+        uint64_t ro = a.row_off[src_local] - a.chunk_base;
+        uint32_t before = 0, all = 0;
+        for (int k = 0; k < 8; k++) {
+            uint32_t cv = a.cnt[src_local * 8 + k];
+            if (k < q) before += cv;
+            all += cv;
+        }
+        acc_off = ro + before;
+        uint32_t fb = 0;
+        for (int k = 0; k < 4 && k < q; k++) fb += a.fillcnt[src_local * 4 + k];
+        fill_off = ro + all + fb;
+    }
+#define GAP(i) s_gaps[(i) * TT + tid]
+    const double s = g.spacing;
+    const double c0x = add(g.blx, mul(s, (double)cx));
+    const double c0y = add(g.bly, mul(s, (double)cy));
+    const double tol = mul(s, 1e-10);
+    const bool xmajor = q < 4;
+    const int sx = (q & 1) ? 1 : -1;
+    const int sy = (q <= 1 || q >= 6) ? 1 : -1;
+    const int diagbin = (q == 0) ? 12 : (q == 1) ? 4 : (q == 2) ? 20 : 28;
+    Zone blk[TB];
+    int ng = 1, nb = 0;
+    {
+        Zone z0;
+        z0.s = 0.0;
+        z0.e = 1.0;
+        GAP(0) = z0;
+    }
+    bool overflow = false, bad_nan = false;
+
+    // sort the row's blocks (insertion sort, start asc / end desc) and subtract them from the gap
+    // list in place, exactly the sequential rule of sparksieve2.cpp:89-132
+    auto subtract = [&]() {
+        for (int i = 1; i < nb; i++) {
+            Zone x = blk[i];
+            int j = i - 1;
+            while (j >= 0 && zone_less(x, blk[j])) {
+                blk[j + 1] = blk[j];
+                j--;
+            }
+            blk[j + 1] = x;
+        }
+        int gi = 0, bi = 0;
+        while (bi < nb && gi < ng) {
+            Zone B = blk[bi];
+            if (bi > 0 && blk[bi - 1].s == B.s && blk[bi - 1].e == B.e) {
+                bi++;
+                continue;
+            }
+            Zone G = GAP(gi);
+            if (B.e < G.s) {
+                bi++;
+                continue;
+            }
+            bool create = true;
+            if (B.s <= G.s) {
+                create = false;
+                if (B.e > G.s) G.s = B.e;
+            }
+            if (B.e >= G.e) {
+                create = false;
+                if (B.s < G.e) G.e = B.s;
+            }
+            if (G.e <= add(G.s, 1e-10)) {
+                for (int r = gi; r + 1 < ng; r++) GAP(r) = GAP(r + 1);
+                ng--;
+                continue;
+            } else if (B.e > G.e) {
+                GAP(gi) = G;
+                gi++;
+                continue;
+            } else if (create) {
+                if (ng == TG) {
+                    overflow = true;
+                    return;
+                }
+                for (int r = ng; r > gi + 1; r--) GAP(r) = GAP(r - 1);
+                ng++;
+                Zone left;
+                left.s = G.s;
+                left.e = B.s;
+                GAP(gi) = left;
+                G.s = B.e;
+                GAP(gi + 1) = G;
+                gi++;
+            } else {
+                GAP(gi) = G;
+            }
+            bi++;
+        }
+        nb = 0;
+    };
+    auto push_blocks = [&](uint32_t llo, int nl) {
+        for (int j = 0; j < nl; j++) {
+            if (nb == TB) {
+                overflow = true;
+                return;
+            }
+            Ln wl = load_line(g.lines + 5 * (size_t)(llo + j));
+            Zone z = make_block(wl, c0x, c0y, q);
+            if (z.s != z.s || z.e != z.e) bad_nan = true;
+            blk[nb++] = z;
+        }
+    };
+
+    // ---- depth 0: own-cell lines clipped to the octant's quadrant
+    {
+        int64_t c = (int64_t)cx * g.rows + cy;
+        uint32_t lo = g.line_off[c];
+        int nl = (int)(g.line_off[c + 1] - lo);
+        if (nl > 0) {
+            double fx = (double)cx, fy = (double)cy;
+            double vblx = add(g.blx, mul(s, sub(sub(fx, 0.5), 1e-10)));
+            double vbly = add(g.bly, mul(s, sub(sub(fy, 0.5), 1e-10)));
+            double vtrx = add(g.blx, mul(s, add(add(fx, 0.5), 1e-10)));
+            double vtry = add(g.bly, mul(s, add(add(fy, 0.5), 1e-10)));
+            switch (q) {
+            case 0: vtrx = c0x; vbly = sub(c0y, tol); break;
+            case 6: vtrx = add(c0x, tol); vbly = c0y; break;
+            case 1: vblx = c0x; vbly = sub(c0y, tol); break;
+            case 7: vblx = sub(c0x, tol); vbly = c0y; break;
+            case 2: vtrx = c0x; vtry = add(c0y, tol); break;
+            case 4: vtrx = add(c0x, tol); vtry = c0y; break;
+            case 3: vblx = c0x; vtry = add(c0y, tol); break;
+            default: vblx = sub(c0x, tol); vtry = c0y; break;
+            }
+            for (int i = 0; i < nl && !overflow; i++) {
+                Ln l = load_line(g.lines + 5 * (size_t)(lo + i));
+                if (crop_line(l, vblx, vbly, vtrx, vtry)) {
+                    if (nb == TB) {
+                        overflow = true;
+                        break;
+                    }
+                    Zone z = make_block(l, c0x, c0y, q);
+                    if (z.s != z.s || z.e != z.e) bad_nan = true;
+                    blk[nb++] = z;
+                }
+            }
+            if (!overflow && nb > 0) subtract();
+        }
+    }
+
+    uint32_t nacc = 0, nfill = 0;
+    int diag_last = 0;
+    for (int depth = 1; ng > 0 && !overflow; depth++) {
+        const double dd = (double)depth;
+        bool hasgaps = false;
+        int firstind = 0;
+        for (int gi = 0; gi < ng && !overflow; gi++) {
+            const Zone z = GAP(gi);
+            const int lo = (int)ceil(sub(mul(z.s, sub(dd, 0.5)), 0.5));
+            int hi = (int)floor(add(mul(z.e, add(dd, 0.5)), 0.5));
+            if (hi > depth) hi = depth;
+            const double lo_c = mul(z.s, dd), hi_c = mul(z.e, dd);
+            for (int ind = max(lo, firstind); ind <= hi; ind++) {
+                firstind = ind;
+                const int ox = xmajor ? depth : ind, oy = xmajor ? ind : depth;
+                const int hx = cx + sx * ox, hy = cy + sy * oy;
+                if (hx < 0 || hx >= g.cols || hy < 0 || hy >= g.rows) continue;
+                hasgaps = true;
+                const int64_t c = (int64_t)hx * g.rows + hy;
+                const uint8_t fl = g.cflag[c];
+                uint32_t llo = 0;
+                int nl = 0;
+                if (fl & 2) {
+                    llo = g.line_off[c];
+                    nl = (int)(g.line_off[c + 1] - llo);
+                }
+                const double di = (double)ind;
+                if ((fl & 1) && di >= lo_c && di <= hi_c &&
+                    (ind != 0 || q == 0 || q == 1 || q == 5 || q == 6) && (ind != depth || q < 4)) {
+                    const double px = add(g.blx, mul(s, (double)hx));
+                    const double py = add(g.bly, mul(s, (double)hy));
+                    bool ok = true;
+                    if (nl > 0 || g.maxdist != -1.0) {
+                        Ln l = make_line(c0x, c0y, px, py);
+                        if (g.maxdist != -1.0) {
+                            double w = sub(l.trx, l.blx), h = sub(l.try_, l.bly);
+                            if (__dsqrt_rn(add(mul(w, w), mul(h, h))) > g.maxdist) ok = false;
+                        }
+                        for (int j = 0; ok && j < nl; j++) {
+                            Ln wl = load_line(g.lines + 5 * (size_t)(llo + j));
+                            if (line_hits(l, wl, tol)) ok = false;
+                        }
+                    }
+                    if (ok) {
+                        if (xmajor && ind == depth) {
+                            // diagonal bin: cells skipped between two accepted diagonal cells are fill-ins
+                            if (diag_last > 0) {
+                                for (int d = diag_last + 1; d < depth; d++) {
+                                    const int fx = cx + sx * d, fy = cy + sy * d;
+                                    if (EMIT) {
+                                        uint64_t p = fill_off + nfill + (uint32_t)(d - diag_last - 1);
+                                        a.e_ref[p] = ((uint32_t)fx << 16) | ((uint32_t)fy & 0xffffu);
+                                        a.e_bin[p] = (uint8_t)(diagbin | 0x80);
+                                    } else if (!(g.cflag[(int64_t)fx * g.rows + fy] & 1)) {
+                                        *a.ghostflag = 1;
+                                    }
+                                }
+                                nfill += (uint32_t)(depth - 1 - diag_last);
+                            }
+                            diag_last = depth;
+                        }
+                        if (EMIT) {
+                            uint64_t p = acc_off + nacc;
+                            a.e_ref[p] = ((uint32_t)hx << 16) | ((uint32_t)hy & 0xffffu);
+                            a.e_bin[p] = (uint8_t)which_bin(sub(px, c0x), sub(py, c0y));
+                        }
+                        nacc++;
+                    }
+                }
+                if (nl > 0) push_blocks(llo, nl);
+            }
+        }
+        if (overflow) break;
+        if (nb > 0) subtract();
+        if (!hasgaps) break;
+    }
+#undef GAP
+    if (overflow) {
+        a.bigflag[task] = 1;
+        unsigned long long p = atomicAdd(a.n_overflow, 1ULL);
+        a.overflow_list[p] = task;
+    } else if (bad_nan) {
+        atomicExch(a.error_flag, VGA_ERR_UNSUPPORTED);
+    } else if (!EMIT) {
+        a.cnt[src_local * 8 + q] = nacc;
+        if (q < 4) a.fillcnt[src_local * 4 + q] = nfill;
+    }
+}
+
 // per-source row sizes -> totals (accepted + fill-ins)
 __global__ void k_row_totals(const uint32_t *cnt, const uint32_t *fillcnt, int64_t nsrc, uint64_t *tot) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -888,7 +1147,10 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t sr
     mt.start();
     // ---- pass 1: count
     if (ntasks > 0) {
-        k_sieve<false><<<blocks_for(ntasks, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, smem_bytes, st>>>(a);
+        if (ctx->opt.sieve_mode == 1)
+            k_sieve_thread<false><<<blocks_for(ntasks, TT), TT, 0, st>>>(a, nsrc);
+        else
+            k_sieve<false><<<blocks_for(ntasks, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, smem_bytes, st>>>(a);
         tm.launches++;
         tm.main_launches++;
         VGA_CUDA(cudaGetLastError());
@@ -999,7 +1261,10 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t sr
         e.e_ref = e_ref.p;
         e.e_bin = e_bin.p;
         mt.start();
-        k_sieve<true><<<blocks_for(ns * 8, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, smem_bytes, st>>>(e);
+        if (ctx->opt.sieve_mode == 1)
+            k_sieve_thread<true><<<blocks_for(ns * 8, TT), TT, 0, st>>>(e, ns);
+        else
+            k_sieve<true><<<blocks_for(ns * 8, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, smem_bytes, st>>>(e);
         tm.launches++;
         tm.main_launches++;
         VGA_CUDA(cudaGetLastError());

@@ -83,13 +83,14 @@ struct Timing {
 struct Options {
     int64_t bfs_mode = 2;        // 0 push only, 1 pull only, 2 direction-optimising hybrid
     int64_t bfs_chunk = 0;       // batches (of 64 sources) in flight; 0 = auto from free memory
+    int64_t sieve_mode = 1;      // 1: thread-per-(source,octant) kernel + warp kernel for overflow, 0: warp kernel
     int64_t sieve_gcap = 48;     // shared-memory gap capacity per warp
     int64_t sieve_bcap = 192;    // shared-memory block capacity per warp
     int64_t sieve_big_gcap = 4096;
     int64_t sieve_big_bcap = 32768;
     int64_t build_chunk_entries = (int64_t)1 << 30;
     int64_t pull_alpha = 4;      // switch to pull when frontier edges*alpha > candidate in-edges (per batch)
-    int64_t bfs_order = 1;       // 1: batches from 8x8 cell tiles in Morton order, 0: x-major ordinals
+    int64_t bfs_order = 2;       // 0: x-major ordinals, 1: 8x8 tiles in Morton order, 2: + wall-respecting floods
     int64_t bfs_group = 16;      // batches per coarse lower-bound group
     int64_t bfs_coarse = 0;      // 1: coarse single-bit pass prunes the pull step (measured: not a win on office plans)
 };

@@ -283,6 +283,7 @@ def test_overflow_path_small_capacity():
     a = capi.Context(0)
     g1 = a.build(flat)
     b = capi.Context(0)
+    b.set_option("sieve_mode", 0)
     b.set_option("sieve_gcap", 4)
     b.set_option("sieve_bcap", 8)
     g2 = b.build(flat)
@@ -291,6 +292,29 @@ def test_overflow_path_small_capacity():
     s1, s2 = g1.node_stats(), g2.node_stats()
     for k in s1:
         assert np.array_equal(s1[k], s2[k]), k
+
+
+@pytest.mark.parametrize("name", ["oblique:30:30:7", "oblique:40:25:21:1.3", "office:64:64:1", "urban:120:120:4"])
+def test_sieve_kernels_agree_and_match_oracle(name):
+    """The thread-per-octant kernel (default, falls back to the warp kernel on overflow) and the
+    warp-per-octant kernel must produce identical rows and statistics, equal to the oracle's."""
+    flat = capi.prepare(plans.by_name(name))
+    og = oracle_graph(flat)
+    orp, oref, ob = og.iter_rows()
+    eref, ebin = sorted_rows(orp, oref, ob)
+    a = og.node_attrs()
+    for mode in (0, 1):
+        c = capi.Context(0)
+        c.set_option("sieve_mode", mode)
+        g = c.build(flat)
+        rp, ref, b = my_rows(g)
+        assert np.array_equal(rp, orp)
+        assert np.array_equal(ref, eref) and np.array_equal(b, ebin)
+        st = g.node_stats()
+        assert np.array_equal(st["sum_d"].astype(np.float32), a["first_moment"])
+        assert np.array_equal(st["sum_d2"].astype(np.float32), a["second_moment"])
+        assert np.array_equal(st["far"], a["far"])
+        c.close()
 
 
 # ---- size-independent properties at larger sizes -----------------------------------------------------
