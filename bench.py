@@ -233,6 +233,7 @@ def main():
             rp_full, adj_full, base = multi.allgather_rows(rp_local, adj_local, dist, world)
             torch.cuda.synchronize(dev)
             full = ctx.graph_from_device_rows(n, g.ghosts, rp_full.data_ptr(), adj_full.data_ptr(), base)
+            full.set_cell_refs(g.cell_refs())  # coordinates -> spatially coherent BFS batches
             stats["gather_bytes"] = int(base) * 4
         t2 = time.perf_counter()
         tn, td, hist, used = full.global_ints(args.radius, (lo, hi))
@@ -269,6 +270,11 @@ def main():
             step(grid_obj, st)
             barrier()
             dt = (time.perf_counter() - t0) * 1e3
+            if os.environ.get("VGA_BENCH_DEBUG"):
+                print(f"[rank {rank}] it={it} total={dt:.1f} build={st['build_ms']:.1f} gather={st['gather_ms']:.1f} "
+                      f"bfs={st['bfs_ms']:.1f} (kernels {st['bfs_timing']['kernel_ms']:.1f}, level kernels "
+                      f"{st['bfs_timing']['main_kernel_ms']:.1f}) tail={st['total_ms'] - st['build_ms'] - st['gather_ms'] - st['bfs_ms']:.1f}",
+                      file=sys.stderr, flush=True)
             if it >= warmup:
                 per.append(dt)
                 acc.append(st)

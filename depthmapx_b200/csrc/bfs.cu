@@ -70,15 +70,19 @@ __global__ void k_init(BfsDev d, const int32_t *src, int64_t nsrc) {
     d.frontier[b * d.n + v] = w;
 }
 
-// coarse pass: all sources of a group of batches share bit 0 of the group's word
+// coarse pass: the sources of group j (a run of `per_group` consecutive sources) all carry bit j%64 of
+// coarse batch j/64, so one bit-parallel BFS yields 64 group lower bounds at once.  A vertex is a
+// source of exactly one group: one writer per word.
 __global__ void k_init_coarse(BfsDev d, const int32_t *src, int64_t nsrc, int per_group) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nsrc) return;
-    int64_t gb = i / per_group;
+    int64_t grp = i / per_group;
+    int64_t cb = grp >> 6;
+    u64 w = 1ULL << (grp & 63);
     int64_t v = src[i];
-    d.visited[gb * d.n + v] = 1ULL;
-    d.frontier[gb * d.n + v] = 1ULL;
-    d.lvl_out[gb * d.n + v] = 0;
+    d.visited[cb * d.n + v] = w;
+    d.frontier[cb * d.n + v] = w;
+    d.lvl_out[grp * d.n + v] = 0;
 }
 
 // top-down step
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[bat
     u64 *vis = d.visited + (int64_t)b * d.n;
     u64 *nx = d.next + (int64_t)b * d.n;
     const uint8_t *lvl = d.lvl_in ? d.lvl_in + (int64_t)(b / d.group) * d.n : nullptr;
-    uint8_t *lout = d.lvl_out ? d.lvl_out + (int64_t)b * d.n : nullptr;
+    uint8_t *lout = d.lvl_out ? d.lvl_out + (int64_t)b * 64 * d.n : nullptr;
     const u64 valid = d.valid[b];
     int c0 = 0, c1 = 0;  // lane l counts source bits l and l+32
     u64 f_edges = 0, u_edges = 0, n_new = 0;
@@ -217,7 +221,15 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[bat
                 nx[v] = 0ULL;
                 f_edges += d.rowptr[v + 1] - d.rowptr[v];
                 n_new += 1;
-                if (lout) lout[v] = (uint8_t)min(level_next, 254);
+                if (lout) {
+                    // coarse pass: bit j of batch b is group b*64+j
+                    u64 bits = nw;
+                    while (bits) {
+                        int j = __ffsll((long long)bits) - 1;
+                        bits &= bits - 1;
+                        lout[(int64_t)j * d.n + v] = (uint8_t)min(level_next, 254);
+                    }
+                }
             }
             fr[v] = nw;
             // in-edges the next pull step would have to consider
@@ -257,7 +269,7 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[bat
 }
 
 // per batch: retire empty batches, choose the next step's direction, reset statistics
-__global__ void k_decide(BfsDev d, int nb, int bfs_mode, int64_t alpha, u64 *work /*[4]*/) {
+__global__ void k_decide(BfsDev d, int nb, int bfs_mode, int64_t alpha, int64_t beta, u64 *work /*[4]*/) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
     if (!d.active[b]) return;
@@ -274,7 +286,7 @@ __global__ void k_decide(BfsDev d, int nb, int bfs_mode, int64_t alpha, u64 *wor
     if (bfs_mode == 1)
         m = 1;
     else if (bfs_mode == 2)
-        m = (fe * (u64)alpha > ue) ? 1 : 0;
+        m = (fe * (u64)alpha > ue * (u64)beta) ? 1 : 0;
     d.mode[b] = m;
     if (work) {
         // work[0]: adjacency entries of the vertices that expand next (sum of deg over U_l),
@@ -303,6 +315,34 @@ __global__ void k_scatter_t(const uint64_t *rowptr, const uint32_t *adj, int64_t
             t_col[p] = (uint32_t)u;
         }
     }
+}
+
+// bit k of gc[v] = the k-th of the 8 grid neighbours (E, NE, N, NW, W, SW, S, SE) is in v's row;
+// rows are sorted by column, so each lookup is a binary search.  Used to grow source batches that
+// do not cross walls.
+__global__ void k_neighbour_bits(int64_t n, const uint64_t *rowptr, const uint32_t *adj, const int32_t *refs,
+                                 const int32_t *ord_of, int cols, int rows, uint8_t *gc) {
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const int dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
+    const int dy[8] = {0, 1, 1, 1, 0, -1, -1, -1};
+    uint32_t r = (uint32_t)refs[v];
+    int x = (int)(r >> 16), y = (int)(r & 0xffff);
+    uint64_t e0 = rowptr[v], e1 = rowptr[v + 1];
+    uint8_t out = 0;
+    for (int k = 0; k < 8; k++) {
+        int nx = x + dx[k], ny = y + dy[k];
+        if (nx < 0 || nx >= cols || ny < 0 || ny >= rows) continue;
+        int32_t w = ord_of[(int64_t)nx * rows + ny];
+        if (w < 0) continue;
+        uint64_t lo = e0, hi = e1;  // first entry with col >= w
+        while (lo < hi) {
+            uint64_t mid = (lo + hi) >> 1;
+            if ((adj[mid] >> 6) < (uint32_t)w) lo = mid + 1; else hi = mid;
+        }
+        if (lo < e1 && (adj[lo] >> 6) == (uint32_t)w) out |= (uint8_t)(1 << k);
+    }
+    gc[v] = out;
 }
 
 inline unsigned blocks_for(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
@@ -349,7 +389,7 @@ int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, De
         }
         VGA_CUDA(cudaMemsetAsync(d.any, 0, sizeof(int), st));
         k_update<<<grid, TPB, 0, st>>>(d, counts ? counts->p + (size_t)(level + 1) * counts_stride : nullptr, level + 1);
-        k_decide<<<blocks_for(nb, 128), 128, 0, st>>>(d, (int)nb, bfs_mode, ctx->opt.pull_alpha, work);
+        k_decide<<<blocks_for(nb, 128), 128, 0, st>>>(d, (int)nb, bfs_mode, ctx->opt.pull_alpha, ctx->opt.pull_beta, work);
         tm.launches += 2;
         tm.main_launches += 2;
         int h_any = 0;
@@ -436,13 +476,11 @@ int run_global(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_
         }
         std::sort(key.begin(), key.end());
         for (int64_t i = 0; i < nsrc; i++) order[(size_t)i] = (int32_t)(src_begin + (int64_t)(key[(size_t)i] & 0xffffffffu));
-        if (ctx->opt.bfs_order >= 2 && g->has_stats && g->src_begin == 0 && g->src_end == n) {
+        if (ctx->opt.bfs_order >= 2) {
             // Wall-respecting clusters: a raw 8x8 tile often straddles a wall, which puts cells of two
             // rooms (very different level structure) into one batch.  Grow each batch as a flood of up
-            // to 64 cells over the direct-neighbour links (grid connection bits, i.e. the 8 neighbours
-            // that are actually visible), seeded in Morton order.
-            std::vector<uint8_t> gc((size_t)n);
-            VGA_CUDA(cudaMemcpy(gc.data(), g->gridconn.p, (size_t)n, cudaMemcpyDeviceToHost));
+            // to 64 cells over the direct-neighbour links (the 8 grid neighbours that are in the cell's
+            // row, i.e. actually visible), seeded in Morton order.
             int maxx = 0, maxy = 0;
             for (int64_t v = 0; v < n; v++) {
                 uint32_t r = (uint32_t)g->h_refs[(size_t)v];
@@ -454,6 +492,21 @@ int run_global(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_
             for (int64_t v = 0; v < n; v++) {
                 uint32_t r = (uint32_t)g->h_refs[(size_t)v];
                 ord_of[(size_t)((int64_t)(r >> 16) * rows + (r & 0xffff))] = (int32_t)v;
+            }
+            std::vector<uint8_t> gc((size_t)n);
+            {
+                DevBuf<int32_t> d_refs, d_ord;
+                DevBuf<uint8_t> d_gc;
+                VGA_TRY(d_refs.alloc((size_t)n));
+                VGA_TRY(d_ord.alloc((size_t)(cols * rows)));
+                VGA_TRY(d_gc.alloc((size_t)n));
+                VGA_CUDA(cudaMemcpyAsync(d_refs.p, g->h_refs.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+                VGA_CUDA(cudaMemcpyAsync(d_ord.p, ord_of.data(), sizeof(int32_t) * cols * rows, cudaMemcpyHostToDevice, st));
+                k_neighbour_bits<<<blocks_for(n, 256), 256, 0, st>>>(n, g->rowptr.p, g->adj.p, d_refs.p, d_ord.p, (int)cols,
+                                                                    (int)rows, d_gc.p);
+                tm.launches++;
+                VGA_CUDA(cudaMemcpyAsync(gc.data(), d_gc.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+                VGA_CUDA(cudaStreamSynchronize(st));
             }
             static const int dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
             static const int dy[8] = {0, 1, 1, 1, 0, -1, -1, -1};
@@ -521,15 +574,16 @@ int run_global(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_
     VGA_TRY(mode.alloc((size_t)chunk));
     VGA_TRY(any.alloc(1));
     VGA_TRY(counts.alloc((size_t)lcap * chunk * 64));
+    const int64_t max_cbatch = (max_groups + 63) / 64;  // coarse batches: 64 groups per word
     if (coarse) {
-        VGA_TRY(c_visited.alloc((size_t)max_groups * n));
-        VGA_TRY(c_frontier.alloc((size_t)max_groups * n));
-        VGA_TRY(c_next.alloc((size_t)max_groups * n));
-        VGA_TRY(c_valid.alloc((size_t)max_groups));
-        VGA_TRY(c_stats.alloc((size_t)max_groups * 4));
-        VGA_TRY(c_active.alloc((size_t)max_groups));
-        VGA_TRY(c_mode.alloc((size_t)max_groups));
-        VGA_TRY(lvl.alloc((size_t)max_groups * n));
+        VGA_TRY(c_visited.alloc((size_t)max_cbatch * n));
+        VGA_TRY(c_frontier.alloc((size_t)max_cbatch * n));
+        VGA_TRY(c_next.alloc((size_t)max_cbatch * n));
+        VGA_TRY(c_valid.alloc((size_t)max_cbatch));
+        VGA_TRY(c_stats.alloc((size_t)max_cbatch * 4));
+        VGA_TRY(c_active.alloc((size_t)max_cbatch));
+        VGA_TRY(c_mode.alloc((size_t)max_cbatch));
+        VGA_TRY(lvl.alloc((size_t)max_cbatch * 64 * n));
     }
 
     BfsDev d;
@@ -564,9 +618,10 @@ int run_global(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_
             return VGA_ERR_CANCELLED;
         }
         kt.start();
-        // ---- coarse pass: one single-bit BFS per group of batches (push only)
+        // ---- coarse pass: group lower bounds, 64 groups per bit-parallel batch (push only)
         if (coarse) {
-            const int64_t ng = (cb + group - 1) / group;
+            const int64_t ngroups = (cb + group - 1) / group;
+            const int64_t ng = (ngroups + 63) / 64;
             BfsDev c = d;
             c.visited = c_visited.p;
             c.frontier = c_frontier.p;
@@ -578,7 +633,8 @@ int run_global(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_
             c.lvl_in = nullptr;
             c.lvl_out = lvl.p;
             c.group = 1;
-            h_valid.assign((size_t)ng, 1ULL);
+            h_valid.assign((size_t)ng, ~0ULL);
+            if (ngroups & 63) h_valid[(size_t)ng - 1] = (1ULL << (ngroups & 63)) - 1ULL;
             ones.assign((size_t)ng, 1);
             VGA_CUDA(cudaMemcpyAsync(c_valid.p, h_valid.data(), sizeof(u64) * ng, cudaMemcpyHostToDevice, st));
             VGA_CUDA(cudaMemcpyAsync(c_active.p, ones.data(), sizeof(int) * ng, cudaMemcpyHostToDevice, st));
@@ -587,7 +643,7 @@ int run_global(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_
             VGA_CUDA(cudaMemsetAsync(c_next.p, 0, sizeof(u64) * (size_t)ng * n, st));
             VGA_CUDA(cudaMemsetAsync(c_stats.p, 0, sizeof(u64) * (size_t)ng * 4, st));
             VGA_CUDA(cudaMemsetAsync(c_mode.p, 0, sizeof(int) * (size_t)ng, st));
-            VGA_CUDA(cudaMemsetAsync(lvl.p, 0xff, (size_t)ng * n, st));
+            VGA_CUDA(cudaMemsetAsync(lvl.p, 0xff, (size_t)ng * 64 * n, st));
             VGA_CUDA(cudaStreamSynchronize(st));  // host staging vectors are reused below
             k_init_coarse<<<blocks_for(cs, 256), 256, 0, st>>>(c, d_order.p + first, cs, 64 * group);
             tm.launches++;

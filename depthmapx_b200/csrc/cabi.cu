@@ -34,6 +34,7 @@ static int set_option(Options &o, const std::string &key, int64_t value) {
     else if (key == "sieve_big_bcap") o.sieve_big_bcap = value;
     else if (key == "build_chunk_entries") o.build_chunk_entries = value;
     else if (key == "pull_alpha") o.pull_alpha = value;
+    else if (key == "pull_beta") o.pull_beta = value;
     else if (key == "bfs_order") o.bfs_order = value;
     else if (key == "bfs_group") o.bfs_group = value;
     else if (key == "bfs_coarse") o.bfs_coarse = value;

@@ -1180,17 +1180,11 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t sr
         return h_err;
     }
 
-    // ---- ghosts: unfilled cells covered by a diagonal first..last run get ordinals N.. (all unfilled
-    // cells are numbered, so every shard agrees); without any, the universe is just the N cells
-    {
-        uint8_t any_ghost = 0;
-        VGA_CUDA(cudaMemcpyAsync(&any_ghost, ghostflag.p, 1, cudaMemcpyDeviceToHost, st));
-        VGA_CUDA(cudaStreamSynchronize(st));
-        if (any_ghost) {
-            gr->ghosts = dg->cells - N;
-            gr->h_refs.insert(gr->h_refs.end(), dg->h_ghostref.begin(), dg->h_ghostref.end());
-        }
-    }
+    // ---- ghosts: unfilled cells covered by a diagonal first..last run get ordinals N..; ALL unfilled
+    // cells are numbered (statically, in x-major order) so that every shard and every rank agrees on
+    // the vertex universe without communication, whether or not a fill-in actually occurred
+    gr->ghosts = dg->cells - N;
+    gr->h_refs.insert(gr->h_refs.end(), dg->h_ghostref.begin(), dg->h_ghostref.end());
 
     // ---- row offsets
     if (nsrc > 0) {

@@ -89,10 +89,11 @@ struct Options {
     int64_t sieve_big_gcap = 4096;
     int64_t sieve_big_bcap = 32768;
     int64_t build_chunk_entries = (int64_t)1 << 30;
-    int64_t pull_alpha = 4;      // switch to pull when frontier edges*alpha > candidate in-edges (per batch)
+    int64_t pull_alpha = 1;      // pull when frontier edges * alpha > candidate in-edges * beta (per batch)
+    int64_t pull_beta = 1;
     int64_t bfs_order = 2;       // 0: x-major ordinals, 1: 8x8 tiles in Morton order, 2: + wall-respecting floods
     int64_t bfs_group = 16;      // batches per coarse lower-bound group
-    int64_t bfs_coarse = 0;      // 1: coarse single-bit pass prunes the pull step (measured: not a win on office plans)
+    int64_t bfs_coarse = 1;      // 1: coarse pass (64 group lower bounds per bit-parallel batch) prunes the pull step
 };
 
 }  // namespace vga

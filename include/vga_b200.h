@@ -26,9 +26,11 @@
  * Vertex numbering: "ordinal" = index of a FILLED cell in x-major order (for x: for y:), the
  * iteration order of every hot loop of the reference and of its attribute table
  * (AttributeKey = int(PixelRef), salalib/pixelref.h:81-82).  "Ghost" vertices (ordinals
- * N..N+G-1) are unfilled cells covered by a diagonal bin's first..last run
- * (Bin::make, salalib/ngraph.cpp:243-259); they have no row of their own, are never BFS
- * sources or counted, but are members of neighbourhoods in the local measures.
+ * N..N+G-1) are the unfilled cells, numbered in x-major order: an unfilled cell can be covered by
+ * a diagonal bin's first..last run (Bin::make, salalib/ngraph.cpp:243-259) and is then a member
+ * of neighbourhoods in the local measures, although it has no row of its own and is never a BFS
+ * source or counted.  Graphs made by vga_graph_build number ALL unfilled cells (G = cells - N) so
+ * that shards built on different GPUs agree without communication.
  */
 #ifndef VGA_B200_H
 #define VGA_B200_H
