@@ -1,24 +1,27 @@
 // All-sources BFS of VGA visibility analysis (VGAVisualGlobal::run + extractUnseen,
 // salalib/vgamodules/vgavisualglobal.cpp:66-130, 218-240) as a bit-parallel multi-source BFS.
 //
-// 64 sources form a batch; a batch carries one 64-bit word per vertex for each of
-// visited / frontier / next.  Batches are formed from spatially compact groups of sources (8x8 cell
-// tiles in Morton order) because cells that are close see almost the same set: their BFS levels
-// coincide for most vertices, so a vertex joins the batch's frontier about once instead of once per
-// distinct level.  Many batches (a "chunk") advance level by level together: grid = (vertex tiles,
-// batches), one launch per level serves the whole chunk and the host reads one flag per level.
+// B = 64*W sources form a batch (W = 1, 2 or 4 machine words); a batch carries W consecutive 64-bit
+// words per vertex for each of visited / frontier / next, so one adjacency entry serves B sources and
+// the per-vertex state of a batch is one 8/16/32-byte vector (a full 32-byte sector for W = 4).
+// Batches are formed from spatially compact groups of sources (floods of 64 cells over the direct
+// neighbour links, seeded along 8x8 tiles in Morton order) because cells that are close and not
+// separated by a wall see almost the same set: their BFS levels coincide for most vertices, so a
+// vertex joins the batch's frontier about once instead of once per distinct level.
+// Many batches (a "chunk") advance level by level together: grid = (vertex tiles, batches), one
+// launch per level serves the whole chunk and the host reads one flag per level.
 //
 // Per level and batch the step is direction-optimising:
-//   push  (top-down)  every vertex with a non-zero frontier word streams its adjacency row with
-//                     coalesced 32-bit loads and ORs its word into `next` of unvisited targets
-//                     (atomicOr on L2-resident words, filtered by a plain read of `visited`);
+//   push  (top-down)  every vertex with a non-zero frontier vector streams its adjacency row with
+//                     coalesced 32-bit loads and ORs its words into `next` of unvisited targets
+//                     (atomicOr on L2-resident words, filtered by a vector read of `visited`);
 //   pull  (bottom-up) every vertex that still misses some source bit streams its in-row
-//                     (transpose adjacency) and ORs the frontier words of its in-neighbours with a
-//                     warp-wide redux, leaving the row as soon as every missing bit is found.
+//                     (transpose adjacency) and ORs the frontier vectors of its in-neighbours
+//                     (8-lane groups, redux.or), leaving the row as soon as every missing bit is found.
 // A pull step wastes a full row scan on every vertex that cannot be reached yet.  A cheap coarse pass
-// removes most of that: for each group of `bfs_group` consecutive batches one single-bit BFS from ALL
-// the group's sources gives lo[w] = min over the group's sources of level(w), a lower bound for every
-// batch of the group; the pull step skips w while lo[w] > level + 1.
+// removes most of that: one extra bit-parallel BFS in which bit j stands for ALL sources of group j
+// (bfs_group*64 consecutive sources) gives lo[j][w] = min over the group of level(w), a lower bound
+// for every batch of the group; the pull step skips w while lo[w] > level + 1.
 // `update` folds `next` into visited/frontier and counts the new vertices per source with
 // ballot + popc (bit b of lane l's word -> source b), i.e. the reference's distribution[level].
 //
@@ -48,31 +51,58 @@ struct BfsDev {
     const uint32_t *adj;  // packed col<<6|..
     const uint64_t *t_rowptr;
     const uint32_t *t_col;
-    u64 *visited, *frontier, *next;  // [batches][n]
-    const u64 *valid;                // [batches] valid source bits of each batch
+    u64 *visited, *frontier, *next;  // [batches][n][W]
+    const u64 *valid;                // [batches*W] valid source bits of each word
     int *active;                     // [batches] 1 while the batch's frontier is non-empty
     int *mode;                       // [batches] 0 push, 1 pull
     u64 *stats;                      // [batches][4]: frontier edges, candidate in-edges, new vertices, -
     int *any;                        // [1] any batch still active
     const uint8_t *lvl_in;           // [groups][n] coarse lower-bound level, or nullptr
-    uint8_t *lvl_out;                // [batches][n] written by the coarse pass, or nullptr
+    uint8_t *lvl_out;                // [coarse batches*64][n] written by the coarse pass, or nullptr
     int group;                       // batches per coarse group
 };
 
-__global__ void k_init(BfsDev d, const int32_t *src, int64_t nsrc) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nsrc) return;
-    int64_t b = i >> 6;
-    int bit = (int)(i & 63);
-    int64_t v = src[i];
-    u64 w = 1ULL << bit;
-    d.visited[b * d.n + v] = w;  // sources of a batch are distinct vertices: one writer per word
-    d.frontier[b * d.n + v] = w;
+template <int W> __device__ __forceinline__ void ldw(const u64 *p, u64 (&o)[W]) {
+    if constexpr (W == 1) {
+        o[0] = p[0];
+    } else {
+#pragma unroll
+        for (int j = 0; j < W; j += 2) {
+            ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(p + j);
+            o[j] = t.x;
+            o[j + 1] = t.y;
+        }
+    }
+}
+template <int W> __device__ __forceinline__ void stw(u64 *p, const u64 (&o)[W]) {
+    if constexpr (W == 1) {
+        p[0] = o[0];
+    } else {
+#pragma unroll
+        for (int j = 0; j < W; j += 2) {
+            ulonglong2 t;
+            t.x = o[j];
+            t.y = o[j + 1];
+            *reinterpret_cast<ulonglong2 *>(p + j) = t;
+        }
+    }
 }
 
-// coarse pass: the sources of group j (a run of `per_group` consecutive sources) all carry bit j%64 of
-// coarse batch j/64, so one bit-parallel BFS yields 64 group lower bounds at once.  A vertex is a
-// source of exactly one group: one writer per word.
+// source i of the ordered list -> bit (i & 63) of word (i >> 6); word wi lives in batch wi / W, slot wi % W
+template <int W> __global__ void k_init(BfsDev d, const int32_t *src, int64_t nsrc) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsrc) return;
+    int64_t wi = i >> 6;
+    int64_t b = wi / W;
+    int j = (int)(wi % W);
+    int64_t v = src[i];
+    u64 w = 1ULL << (i & 63);
+    d.visited[(b * d.n + v) * W + j] = w;  // a vertex is a source in exactly one word: one writer
+    d.frontier[(b * d.n + v) * W + j] = w;
+}
+
+// coarse pass (W = 1): the sources of group j (`per_group` consecutive sources) all carry bit j%64 of
+// coarse batch j/64, so one bit-parallel BFS yields 64 group lower bounds at once.
 __global__ void k_init_coarse(BfsDev d, const int32_t *src, int64_t nsrc, int per_group) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nsrc) return;
@@ -86,43 +116,46 @@ __global__ void k_init_coarse(BfsDev d, const int32_t *src, int64_t nsrc, int pe
 }
 
 // top-down step
-__global__ void __launch_bounds__(TPB) k_push(BfsDev d) {
+template <int W> __global__ void __launch_bounds__(TPB) k_push(BfsDev d) {
     const int b = blockIdx.y;
     if (!d.active[b] || d.mode[b] != 0) return;
     const int lane = threadIdx.x & 31;
-    const u64 *fr = d.frontier + (int64_t)b * d.n;
-    const u64 *vis = d.visited + (int64_t)b * d.n;
-    u64 *nx = d.next + (int64_t)b * d.n;
+    const u64 *fr = d.frontier + (int64_t)b * d.n * W;
+    const u64 *vis = d.visited + (int64_t)b * d.n * W;
+    u64 *nx = d.next + (int64_t)b * d.n * W;
     for (int64_t base = (int64_t)blockIdx.x * TPB; base < d.n; base += (int64_t)gridDim.x * TPB) {
         int64_t u = base + threadIdx.x;
-        u64 f = (u < d.n) ? fr[u] : 0ULL;
+        u64 f[W];
+#pragma unroll
+        for (int j = 0; j < W; j++) f[j] = 0ULL;
+        if (u < d.n) ldw<W>(fr + u * W, f);
+        u64 anyf = 0ULL;
+#pragma unroll
+        for (int j = 0; j < W; j++) anyf |= f[j];
         // every lane fetches its own row bounds up front (coalesced); they are broadcast below
         uint64_t my0 = 0, my1 = 0;
-        if (f != 0ULL) {
+        if (anyf != 0ULL) {
             my0 = d.rowptr[u];
             my1 = d.rowptr[u + 1];
         }
-        unsigned m = __ballot_sync(FULL, f != 0ULL);
+        unsigned m = __ballot_sync(FULL, anyf != 0ULL);
         while (m) {
             int src_lane = __ffs(m) - 1;
             m &= m - 1;
-            u64 fw = __shfl_sync(FULL, f, src_lane);
+            u64 fw[W];
+#pragma unroll
+            for (int j = 0; j < W; j++) fw[j] = __shfl_sync(FULL, f[j], src_lane);
             uint64_t e0 = __shfl_sync(FULL, my0, src_lane), e1 = __shfl_sync(FULL, my1, src_lane);
-            uint64_t e = e0 + lane;
-            // two independent entries per lane per trip: more loads in flight
-            for (; e + 32 < e1; e += 64) {
-                uint32_t c0 = d.adj[e] >> 6, c1 = d.adj[e + 32] >> 6;
-                u64 v0 = (c0 < (uint32_t)d.n) ? vis[c0] : ~0ULL;
-                u64 v1 = (c1 < (uint32_t)d.n) ? vis[c1] : ~0ULL;
-                u64 a0 = fw & ~v0, a1 = fw & ~v1;
-                if (a0) atomicOr(&nx[c0], a0);
-                if (a1) atomicOr(&nx[c1], a1);
-            }
-            if (e < e1) {
+            for (uint64_t e = e0 + lane; e < e1; e += 32) {
                 uint32_t c = d.adj[e] >> 6;
                 if (c < (uint32_t)d.n) {
-                    u64 add = fw & ~vis[c];
-                    if (add) atomicOr(&nx[c], add);
+                    u64 vv[W];
+                    ldw<W>(vis + (int64_t)c * W, vv);
+#pragma unroll
+                    for (int j = 0; j < W; j++) {
+                        u64 add = fw[j] & ~vv[j];
+                        if (add) atomicOr(&nx[(int64_t)c * W + j], add);
+                    }
                 }
             }
         }
@@ -130,31 +163,41 @@ __global__ void __launch_bounds__(TPB) k_push(BfsDev d) {
 }
 
 // bottom-up step with early exit; `level` = level of the current frontier
-__global__ void __launch_bounds__(TPB) k_pull(BfsDev d, int level) {
+template <int W> __global__ void __launch_bounds__(TPB) k_pull(BfsDev d, int level) {
     const int b = blockIdx.y;
     if (!d.active[b] || d.mode[b] != 1) return;
     const int lane = threadIdx.x & 31;
-    const u64 *fr = d.frontier + (int64_t)b * d.n;
-    const u64 *vis = d.visited + (int64_t)b * d.n;
-    u64 *nx = d.next + (int64_t)b * d.n;
+    const u64 *fr = d.frontier + (int64_t)b * d.n * W;
+    const u64 *vis = d.visited + (int64_t)b * d.n * W;
+    u64 *nx = d.next + (int64_t)b * d.n * W;
     const uint8_t *lvl = d.lvl_in ? d.lvl_in + (int64_t)(b / d.group) * d.n : nullptr;
-    const u64 valid = d.valid[b];
+    u64 valid[W];
+#pragma unroll
+    for (int j = 0; j < W; j++) valid[j] = d.valid[(int64_t)b * W + j];
     for (int64_t base = (int64_t)blockIdx.x * TPB; base < d.n; base += (int64_t)gridDim.x * TPB) {
         int64_t w = base + threadIdx.x;
-        u64 need = 0ULL;
-        if (w < d.n) {
-            need = valid & ~vis[w];
-            if (need && lvl && (int)lvl[w] > level + 1) need = 0ULL;  // cannot be reached yet
+        u64 need[W];
+#pragma unroll
+        for (int j = 0; j < W; j++) need[j] = 0ULL;
+        u64 anyneed = 0ULL;
+        if (w < d.n && !(lvl && (int)lvl[w] > level + 1)) {  // lvl > level+1: cannot be reached yet
+            u64 vv[W];
+            ldw<W>(vis + w * W, vv);
+#pragma unroll
+            for (int j = 0; j < W; j++) {
+                need[j] = valid[j] & ~vv[j];
+                anyneed |= need[j];
+            }
         }
         uint64_t my0 = 0, my1 = 0;
-        if (need != 0ULL) {
+        if (anyneed != 0ULL) {
             my0 = d.t_rowptr[w];
             my1 = d.t_rowptr[w + 1];
         }
         // Candidates of this warp are served by 4 groups of 8 lanes, each group scanning a different
         // vertex's in-row: 4 rows in flight per warp hide the dependent index->word latency, and a
-        // row is left after 8 (not 32) in-neighbours when they already cover the missing bits.
-        const unsigned m = __ballot_sync(FULL, need != 0ULL);
+        // row is left as soon as the in-neighbours seen so far cover the missing bits.
+        const unsigned m = __ballot_sync(FULL, anyneed != 0ULL);
         const int ncand = __popc(m);
         const int grp = lane >> 3, gl = lane & 7;
         const unsigned gmask = 0xffu << (grp * 8);
@@ -162,27 +205,42 @@ __global__ void __launch_bounds__(TPB) k_pull(BfsDev d, int level) {
             const int k = r * 4 + grp;
             const bool has = k < ncand;
             const int src_lane = has ? (int)__fns(m, 0, k + 1) : 0;
-            const u64 nd = __shfl_sync(FULL, need, src_lane);
+            u64 nd[W];
+#pragma unroll
+            for (int j = 0; j < W; j++) nd[j] = __shfl_sync(FULL, need[j], src_lane);
             const uint64_t e0 = __shfl_sync(FULL, my0, src_lane), e1 = __shfl_sync(FULL, my1, src_lane);
             if (has) {
-                u64 acc = 0ULL;
+                u64 acc[W];
+#pragma unroll
+                for (int j = 0; j < W; j++) acc[j] = 0ULL;
                 for (uint64_t e = e0; e < e1; e += 16) {
                     const uint64_t ea = e + gl, eb = e + 8 + gl;
-                    u64 g0 = 0ULL, g1 = 0ULL;
+                    u64 g0[W], g1[W];
+#pragma unroll
+                    for (int j = 0; j < W; j++) g0[j] = g1[j] = 0ULL;
                     uint32_t ca = 0, cb = 0;
                     if (ea < e1) ca = d.t_col[ea];
                     if (eb < e1) cb = d.t_col[eb];
-                    if (ea < e1) g0 = fr[ca];
-                    if (eb < e1) g1 = fr[cb];
-                    g0 |= g1;
-                    unsigned lo = __reduce_or_sync(gmask, (unsigned)g0);
-                    unsigned hi = __reduce_or_sync(gmask, (unsigned)(g0 >> 32));
-                    acc |= ((u64)hi << 32) | lo;
-                    if ((acc & nd) == nd) break;
+                    if (ea < e1) ldw<W>(fr + (int64_t)ca * W, g0);
+                    if (eb < e1) ldw<W>(fr + (int64_t)cb * W, g1);
+                    bool done = true;
+#pragma unroll
+                    for (int j = 0; j < W; j++) {
+                        u64 gj = g0[j] | g1[j];
+                        unsigned lo = __reduce_or_sync(gmask, (unsigned)gj);
+                        unsigned hi = __reduce_or_sync(gmask, (unsigned)(gj >> 32));
+                        acc[j] |= ((u64)hi << 32) | lo;
+                        done = done && ((acc[j] & nd[j]) == nd[j]);
+                    }
+                    if (done) break;
                 }
                 if (gl == 0) {
-                    u64 nw = acc & nd;
-                    if (nw) nx[(base + (threadIdx.x & ~31)) + src_lane] = nw;
+                    const int64_t ww = (base + (threadIdx.x & ~31)) + src_lane;
+#pragma unroll
+                    for (int j = 0; j < W; j++) {
+                        u64 nw = acc[j] & nd[j];
+                        if (nw) nx[ww * W + j] = nw;
+                    }
                 }
             }
             __syncwarp();
@@ -192,38 +250,56 @@ __global__ void __launch_bounds__(TPB) k_pull(BfsDev d, int level) {
 
 // fold next into visited/frontier, count new vertices per source, gather direction statistics;
 // `level_next` = level of the vertices being added
-__global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[batches][64] of level_next*/, int level_next) {
+template <int W>
+__global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[batches*W][64] of level_next*/, int level_next) {
     const int b = blockIdx.y;
     if (!d.active[b]) return;
-    __shared__ int s_cnt[64];
+    __shared__ int s_cnt[W * 64];
     __shared__ u64 s_stat[3];
-    if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < W * 64; i += TPB) s_cnt[i] = 0;
     if (threadIdx.x < 3) s_stat[threadIdx.x] = 0ULL;
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    u64 *fr = d.frontier + (int64_t)b * d.n;
-    u64 *vis = d.visited + (int64_t)b * d.n;
-    u64 *nx = d.next + (int64_t)b * d.n;
+    u64 *fr = d.frontier + (int64_t)b * d.n * W;
+    u64 *vis = d.visited + (int64_t)b * d.n * W;
+    u64 *nx = d.next + (int64_t)b * d.n * W;
     const uint8_t *lvl = d.lvl_in ? d.lvl_in + (int64_t)(b / d.group) * d.n : nullptr;
     uint8_t *lout = d.lvl_out ? d.lvl_out + (int64_t)b * 64 * d.n : nullptr;
-    const u64 valid = d.valid[b];
-    int c0 = 0, c1 = 0;  // lane l counts source bits l and l+32
+    u64 valid[W];
+#pragma unroll
+    for (int j = 0; j < W; j++) valid[j] = d.valid[(int64_t)b * W + j];
+    int cnt[W][2];  // lane l counts source bits l and l+32 of each word
+#pragma unroll
+    for (int j = 0; j < W; j++) cnt[j][0] = cnt[j][1] = 0;
     u64 f_edges = 0, u_edges = 0, n_new = 0;
     for (int64_t base = (int64_t)blockIdx.x * TPB; base < d.n; base += (int64_t)gridDim.x * TPB) {
         int64_t v = base + threadIdx.x;
-        u64 nw = 0ULL;
+        u64 nw[W];
+#pragma unroll
+        for (int j = 0; j < W; j++) nw[j] = 0ULL;
         if (v < d.n) {
-            u64 vv = vis[v];
-            nw = nx[v] & ~vv;
-            if (nw) {
-                vv |= nw;
-                vis[v] = vv;
-                nx[v] = 0ULL;
+            u64 vv[W], xx[W];
+            ldw<W>(vis + v * W, vv);
+            ldw<W>(nx + v * W, xx);
+            u64 anynew = 0ULL, anyneed = 0ULL;
+#pragma unroll
+            for (int j = 0; j < W; j++) {
+                nw[j] = xx[j] & ~vv[j];
+                vv[j] |= nw[j];
+                anynew |= nw[j];
+                anyneed |= valid[j] & ~vv[j];
+            }
+            if (anynew) {
+                stw<W>(vis + v * W, vv);
+                u64 zero[W];
+#pragma unroll
+                for (int j = 0; j < W; j++) zero[j] = 0ULL;
+                stw<W>(nx + v * W, zero);
                 f_edges += d.rowptr[v + 1] - d.rowptr[v];
                 n_new += 1;
                 if (lout) {
-                    // coarse pass: bit j of batch b is group b*64+j
-                    u64 bits = nw;
+                    // coarse pass (W == 1): bit j of coarse batch b is group b*64+j
+                    u64 bits = nw[0];
                     while (bits) {
                         int j = __ffsll((long long)bits) - 1;
                         bits &= bits - 1;
@@ -231,28 +307,34 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[bat
                     }
                 }
             }
-            fr[v] = nw;
+            stw<W>(fr + v * W, nw);
             // in-edges the next pull step would have to consider
-            if (d.t_rowptr && (valid & ~vv) != 0ULL && (!lvl || (int)lvl[v] <= level_next + 1))
+            if (d.t_rowptr && anyneed != 0ULL && (!lvl || (int)lvl[v] <= level_next + 1))
                 u_edges += d.t_rowptr[v + 1] - d.t_rowptr[v];
         }
-        unsigned lo_any = __reduce_or_sync(FULL, (unsigned)nw);
-        unsigned hi_any = __reduce_or_sync(FULL, (unsigned)(nw >> 32));
-        while (lo_any) {
-            int bit = __ffs(lo_any) - 1;
-            lo_any &= lo_any - 1;
-            int c = __popc(__ballot_sync(FULL, (nw >> bit) & 1ULL));
-            if (lane == bit) c0 += c;
-        }
-        while (hi_any) {
-            int bit = __ffs(hi_any) - 1;
-            hi_any &= hi_any - 1;
-            int c = __popc(__ballot_sync(FULL, (nw >> (bit + 32)) & 1ULL));
-            if (lane == bit) c1 += c;
+#pragma unroll
+        for (int j = 0; j < W; j++) {
+            unsigned lo_any = __reduce_or_sync(FULL, (unsigned)nw[j]);
+            unsigned hi_any = __reduce_or_sync(FULL, (unsigned)(nw[j] >> 32));
+            while (lo_any) {
+                int bit = __ffs(lo_any) - 1;
+                lo_any &= lo_any - 1;
+                int c = __popc(__ballot_sync(FULL, (nw[j] >> bit) & 1ULL));
+                if (lane == bit) cnt[j][0] += c;
+            }
+            while (hi_any) {
+                int bit = __ffs(hi_any) - 1;
+                hi_any &= hi_any - 1;
+                int c = __popc(__ballot_sync(FULL, (nw[j] >> (bit + 32)) & 1ULL));
+                if (lane == bit) cnt[j][1] += c;
+            }
         }
     }
-    if (c0) atomicAdd(&s_cnt[lane], c0);
-    if (c1) atomicAdd(&s_cnt[lane + 32], c1);
+#pragma unroll
+    for (int j = 0; j < W; j++) {
+        if (cnt[j][0]) atomicAdd(&s_cnt[j * 64 + lane], cnt[j][0]);
+        if (cnt[j][1]) atomicAdd(&s_cnt[j * 64 + lane + 32], cnt[j][1]);
+    }
     for (int o = 16; o > 0; o >>= 1) {
         f_edges += __shfl_down_sync(FULL, f_edges, o);
         u_edges += __shfl_down_sync(FULL, u_edges, o);
@@ -264,7 +346,9 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[bat
         if (n_new) atomicAdd(&s_stat[2], n_new);
     }
     __syncthreads();
-    if (counts && threadIdx.x < 64 && s_cnt[threadIdx.x]) atomicAdd(&counts[b * 64 + threadIdx.x], s_cnt[threadIdx.x]);
+    if (counts)
+        for (int i = threadIdx.x; i < W * 64; i += TPB)
+            if (s_cnt[i]) atomicAdd(&counts[(int64_t)b * W * 64 + i], s_cnt[i]);
     if (threadIdx.x < 3 && s_stat[threadIdx.x]) atomicAdd(&d.stats[b * 4 + threadIdx.x], s_stat[threadIdx.x]);
 }
 
@@ -359,7 +443,8 @@ inline uint32_t morton2(uint32_t x, uint32_t y) {
     return spread(x) | (spread(y) << 1);
 }
 
-// Level loop over a set of batches.  Returns the number of levels with data (>= 1) via nlev.
+// Level loop over a set of batches of W words.  nlev = number of levels with data (>= 1).
+template <int W>
 int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, DevBuf<int32_t> *counts, int *lcap,
                int64_t counts_stride, u64 *work, StageTimer &mt, int *nlev_out) {
     cudaStream_t st = ctx->stream;
@@ -368,11 +453,11 @@ int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, De
     int level = 0, nlev = 1;
     while (radius == -1 || level < radius) {
         dim3 grid(xblocks, (unsigned)nb);
-        k_push<<<grid, TPB, 0, st>>>(d);
+        k_push<W><<<grid, TPB, 0, st>>>(d);
         tm.launches++;
         tm.main_launches++;
         if (bfs_mode != 0 && level > 0) {
-            k_pull<<<grid, TPB, 0, st>>>(d, level);
+            k_pull<W><<<grid, TPB, 0, st>>>(d, level);
             tm.launches++;
             tm.main_launches++;
         }
@@ -388,7 +473,7 @@ int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, De
             mt.start();
         }
         VGA_CUDA(cudaMemsetAsync(d.any, 0, sizeof(int), st));
-        k_update<<<grid, TPB, 0, st>>>(d, counts ? counts->p + (size_t)(level + 1) * counts_stride : nullptr, level + 1);
+        k_update<W><<<grid, TPB, 0, st>>>(d, counts ? counts->p + (size_t)(level + 1) * counts_stride : nullptr, level + 1);
         k_decide<<<blocks_for(nb, 128), 128, 0, st>>>(d, (int)nb, bfs_mode, ctx->opt.pull_alpha, ctx->opt.pull_beta, work);
         tm.launches += 2;
         tm.main_launches += 2;
@@ -403,7 +488,300 @@ int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, De
     return VGA_OK;
 }
 
+// Source order for batching (see header comment).  order[i] = ordinal of the i-th source.
+int source_order(vga_ctx *ctx, vga_graph *g, int64_t src_begin, int64_t src_end, std::vector<int32_t> &order) {
+    cudaStream_t st = ctx->stream;
+    const int64_t n = g->n, nsrc = src_end - src_begin;
+    order.resize((size_t)nsrc);
+    std::iota(order.begin(), order.end(), (int32_t)src_begin);
+    if (ctx->opt.bfs_order == 0 || (int64_t)g->h_refs.size() < n) return VGA_OK;
+    std::vector<uint64_t> key((size_t)nsrc);
+    for (int64_t i = 0; i < nsrc; i++) {
+        uint32_t r = (uint32_t)g->h_refs[(size_t)(src_begin + i)];
+        uint32_t x = r >> 16, y = r & 0xffff;
+        key[(size_t)i] = ((uint64_t)morton2(x >> 3, y >> 3) << 38) | ((uint64_t)(x & 7) << 35) | ((uint64_t)(y & 7) << 32) |
+                         (uint64_t)(uint32_t)i;
+    }
+    std::sort(key.begin(), key.end());
+    for (int64_t i = 0; i < nsrc; i++) order[(size_t)i] = (int32_t)(src_begin + (int64_t)(key[(size_t)i] & 0xffffffffu));
+    if (ctx->opt.bfs_order < 2) return VGA_OK;
+    // Wall-respecting clusters: a raw 8x8 tile often straddles a wall, which puts cells of two rooms
+    // (very different level structure) into one batch.  Grow each cluster as a flood of up to 64 cells
+    // over the direct-neighbour links (the 8 grid neighbours that are in the cell's row, i.e. actually
+    // visible), seeded in Morton order.
+    int maxx = 0, maxy = 0;
+    for (int64_t v = 0; v < n; v++) {
+        uint32_t r = (uint32_t)g->h_refs[(size_t)v];
+        maxx = std::max(maxx, (int)(r >> 16));
+        maxy = std::max(maxy, (int)(r & 0xffff));
+    }
+    const int64_t cols = maxx + 1, rows = maxy + 1;
+    std::vector<int32_t> ord_of((size_t)(cols * rows), -1);
+    for (int64_t v = 0; v < n; v++) {
+        uint32_t r = (uint32_t)g->h_refs[(size_t)v];
+        ord_of[(size_t)((int64_t)(r >> 16) * rows + (r & 0xffff))] = (int32_t)v;
+    }
+    std::vector<uint8_t> gc((size_t)n);
+    {
+        DevBuf<int32_t> d_refs, d_ord;
+        DevBuf<uint8_t> d_gc;
+        VGA_TRY(d_refs.alloc((size_t)n));
+        VGA_TRY(d_ord.alloc((size_t)(cols * rows)));
+        VGA_TRY(d_gc.alloc((size_t)n));
+        VGA_CUDA(cudaMemcpyAsync(d_refs.p, g->h_refs.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+        VGA_CUDA(cudaMemcpyAsync(d_ord.p, ord_of.data(), sizeof(int32_t) * cols * rows, cudaMemcpyHostToDevice, st));
+        k_neighbour_bits<<<blocks_for(n, 256), 256, 0, st>>>(n, g->rowptr.p, g->adj.p, d_refs.p, d_ord.p, (int)cols, (int)rows,
+                                                            d_gc.p);
+        ctx->timing.launches++;
+        VGA_CUDA(cudaMemcpyAsync(gc.data(), d_gc.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+        VGA_CUDA(cudaStreamSynchronize(st));
+    }
+    static const int dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
+    static const int dy[8] = {0, 1, 1, 1, 0, -1, -1, -1};
+    std::vector<uint8_t> taken((size_t)n, 0);
+    std::vector<int32_t> clustered, queue;
+    clustered.reserve((size_t)nsrc);
+    for (int64_t i = 0; i < nsrc; i++) {
+        const int32_t seed = order[(size_t)i];
+        if (taken[(size_t)seed]) continue;
+        queue.clear();
+        queue.push_back(seed);
+        taken[(size_t)seed] = 1;
+        size_t head = 0;
+        int count = 0;
+        while (head < queue.size() && count < 64) {
+            const int32_t v = queue[head++];
+            clustered.push_back(v);
+            count++;
+            const uint32_t r = (uint32_t)g->h_refs[(size_t)v];
+            const int x = (int)(r >> 16), y = (int)(r & 0xffff);
+            for (int k = 0; k < 8; k++) {
+                if (!(gc[(size_t)v] & (1 << k))) continue;
+                const int nx = x + dx[k], ny = y + dy[k];
+                if (nx < 0 || nx >= cols || ny < 0 || ny >= rows) continue;
+                const int32_t w = ord_of[(size_t)((int64_t)nx * rows + ny)];
+                if (w < (int32_t)src_begin || w >= (int32_t)src_end || taken[(size_t)w]) continue;
+                taken[(size_t)w] = 1;
+                queue.push_back(w);
+            }
+        }
+        for (; head < queue.size(); head++) taken[(size_t)queue[head]] = 0;  // not placed: free again
+    }
+    if ((int64_t)clustered.size() == nsrc) order.swap(clustered);
+    return VGA_OK;
+}
+
+template <int W>
+int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_t src_end, int32_t *total_nodes,
+                 int64_t *total_depth, int32_t *dist, int32_t max_levels, int32_t *levels_used) {
+    cudaStream_t st = ctx->stream;
+    const int64_t n = g->n;
+    const int64_t nsrc = src_end - src_begin;
+    Timing &tm = ctx->timing;
+    const int bfs_mode = (int)ctx->opt.bfs_mode;
+    StageTimer kt(ctx, 0, &tm.kernel_ms);
+    StageTimer mt(ctx, 2, &tm.main_kernel_ms);
+    StageTimer dt(ctx, 4, &tm.d2h_ms);
+
+    kt.start();
+    if (bfs_mode != 0) VGA_TRY(ensure_transpose(ctx, g));
+    kt.stop();
+
+    std::vector<int32_t> order;
+    VGA_TRY(source_order(ctx, g, src_begin, src_end, order));
+    DevBuf<int32_t> d_order;
+    VGA_TRY(d_order.alloc((size_t)nsrc));
+    VGA_CUDA(cudaMemcpyAsync(d_order.p, order.data(), sizeof(int32_t) * nsrc, cudaMemcpyHostToDevice, st));
+
+    const int64_t nwords = (nsrc + 63) / 64;      // 64-source words
+    const int64_t nbatch = (nwords + W - 1) / W;  // batches of W words
+    // coarse groups: `group` batches each (bfs_group is given in 64-source words)
+    const int group = (int)std::max<int64_t>(1, ctx->opt.bfs_group / W);
+    const bool coarse = bfs_mode != 0 && ctx->opt.bfs_coarse != 0;
+    // chunk size: 3*W words per (batch, vertex) + the coarse pass; below ~40% of free memory and 48 GB
+    size_t free_b = 0, total_b = 0;
+    VGA_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    int64_t budget = (int64_t)std::min<size_t>((size_t)(free_b * 0.4), (size_t)48 << 30);
+    int64_t chunk = ctx->opt.bfs_chunk > 0 ? std::max<int64_t>(1, ctx->opt.bfs_chunk / W)
+                                           : std::max<int64_t>(1, budget / (26 * W * std::max<int64_t>(n, 1)));
+    chunk = std::min<int64_t>(chunk, nbatch);
+    chunk = std::min<int64_t>(chunk, 65535);
+    if (chunk > group) chunk -= chunk % group;  // whole groups per chunk
+    const int64_t max_groups = (chunk + group - 1) / group;
+    const int64_t max_cbatch = (max_groups + 63) / 64;  // coarse batches: 64 groups per word
+
+    DevBuf<u64> visited, frontier, next, valid, stats, work, c_visited, c_frontier, c_next, c_valid, c_stats;
+    DevBuf<int> active, mode, any, c_active, c_mode;
+    DevBuf<int32_t> counts;
+    DevBuf<uint8_t> lvl;
+    int lcap = 16;
+    VGA_TRY(visited.alloc((size_t)chunk * n * W));
+    VGA_TRY(frontier.alloc((size_t)chunk * n * W));
+    VGA_TRY(next.alloc((size_t)chunk * n * W));
+    VGA_TRY(valid.alloc((size_t)chunk * W));
+    VGA_TRY(stats.alloc((size_t)chunk * 4));
+    VGA_TRY(work.alloc_zero(4, st));
+    VGA_TRY(active.alloc((size_t)chunk));
+    VGA_TRY(mode.alloc((size_t)chunk));
+    VGA_TRY(any.alloc(1));
+    VGA_TRY(counts.alloc((size_t)lcap * chunk * W * 64));
+    if (coarse) {
+        VGA_TRY(c_visited.alloc((size_t)max_cbatch * n));
+        VGA_TRY(c_frontier.alloc((size_t)max_cbatch * n));
+        VGA_TRY(c_next.alloc((size_t)max_cbatch * n));
+        VGA_TRY(c_valid.alloc((size_t)max_cbatch));
+        VGA_TRY(c_stats.alloc((size_t)max_cbatch * 4));
+        VGA_TRY(c_active.alloc((size_t)max_cbatch));
+        VGA_TRY(c_mode.alloc((size_t)max_cbatch));
+        VGA_TRY(lvl.alloc((size_t)max_cbatch * 64 * n));
+    }
+
+    BfsDev d;
+    d.n = n;
+    d.rowptr = g->rowptr.p;
+    d.adj = g->adj.p;
+    d.t_rowptr = g->has_transpose ? g->t_rowptr.p : nullptr;
+    d.t_col = g->has_transpose ? g->t_col.p : nullptr;
+    d.visited = visited.p;
+    d.frontier = frontier.p;
+    d.next = next.p;
+    d.valid = valid.p;
+    d.active = active.p;
+    d.mode = mode.p;
+    d.stats = stats.p;
+    d.any = any.p;
+    d.lvl_in = coarse ? lvl.p : nullptr;
+    d.lvl_out = nullptr;
+    d.group = group;
+
+    int deepest = 0;
+    std::vector<int32_t> h_counts;
+    std::vector<u64> h_valid;
+    std::vector<int> ones;
+    const int64_t cstride = chunk * W * 64;  // counts per level
+
+    for (int64_t b0 = 0; b0 < nbatch; b0 += chunk) {
+        const int64_t cb = std::min<int64_t>(chunk, nbatch - b0);
+        const int64_t first = b0 * W * 64;  // index into the ordered source list
+        const int64_t cs = std::min<int64_t>(cb * W * 64, nsrc - first);
+        if (ctx->cancel && ctx->cancel(ctx->user)) {
+            set_error("cancelled");
+            return VGA_ERR_CANCELLED;
+        }
+        kt.start();
+        // ---- coarse pass: group lower bounds, 64 groups per bit-parallel batch (W = 1, push only)
+        if (coarse) {
+            const int64_t ngroups = (cb + group - 1) / group;
+            const int64_t ng = (ngroups + 63) / 64;
+            BfsDev c = d;
+            c.visited = c_visited.p;
+            c.frontier = c_frontier.p;
+            c.next = c_next.p;
+            c.valid = c_valid.p;
+            c.active = c_active.p;
+            c.mode = c_mode.p;
+            c.stats = c_stats.p;
+            c.lvl_in = nullptr;
+            c.lvl_out = lvl.p;
+            c.group = 1;
+            h_valid.assign((size_t)ng, ~0ULL);
+            if (ngroups & 63) h_valid[(size_t)ng - 1] = (1ULL << (ngroups & 63)) - 1ULL;
+            ones.assign((size_t)ng, 1);
+            VGA_CUDA(cudaMemcpyAsync(c_valid.p, h_valid.data(), sizeof(u64) * ng, cudaMemcpyHostToDevice, st));
+            VGA_CUDA(cudaMemcpyAsync(c_active.p, ones.data(), sizeof(int) * ng, cudaMemcpyHostToDevice, st));
+            VGA_CUDA(cudaMemsetAsync(c_visited.p, 0, sizeof(u64) * (size_t)ng * n, st));
+            VGA_CUDA(cudaMemsetAsync(c_frontier.p, 0, sizeof(u64) * (size_t)ng * n, st));
+            VGA_CUDA(cudaMemsetAsync(c_next.p, 0, sizeof(u64) * (size_t)ng * n, st));
+            VGA_CUDA(cudaMemsetAsync(c_stats.p, 0, sizeof(u64) * (size_t)ng * 4, st));
+            VGA_CUDA(cudaMemsetAsync(c_mode.p, 0, sizeof(int) * (size_t)ng, st));
+            VGA_CUDA(cudaMemsetAsync(lvl.p, 0xff, (size_t)ng * 64 * n, st));
+            VGA_CUDA(cudaStreamSynchronize(st));  // host staging vectors are reused below
+            k_init_coarse<<<blocks_for(cs, 256), 256, 0, st>>>(c, d_order.p + first, cs, 64 * W * group);
+            tm.launches++;
+            mt.start();
+            int cl = 0;
+            VGA_TRY(run_levels<1>(ctx, c, ng, radius, 0, nullptr, nullptr, 0, nullptr, mt, &cl));
+            mt.stop();
+        }
+        // ---- exact pass
+        {
+            const int64_t words_here = (cs + 63) / 64;
+            h_valid.assign((size_t)(cb * W), 0ULL);
+            for (int64_t wi = 0; wi < words_here; wi++) h_valid[(size_t)wi] = ~0ULL;
+            if (cs & 63) h_valid[(size_t)words_here - 1] = (1ULL << (cs & 63)) - 1ULL;
+        }
+        ones.assign((size_t)cb, 1);
+        VGA_CUDA(cudaMemcpyAsync(valid.p, h_valid.data(), sizeof(u64) * cb * W, cudaMemcpyHostToDevice, st));
+        VGA_CUDA(cudaMemcpyAsync(active.p, ones.data(), sizeof(int) * cb, cudaMemcpyHostToDevice, st));
+        VGA_CUDA(cudaMemsetAsync(visited.p, 0, sizeof(u64) * (size_t)cb * n * W, st));
+        VGA_CUDA(cudaMemsetAsync(frontier.p, 0, sizeof(u64) * (size_t)cb * n * W, st));
+        VGA_CUDA(cudaMemsetAsync(next.p, 0, sizeof(u64) * (size_t)cb * n * W, st));
+        VGA_CUDA(cudaMemsetAsync(stats.p, 0, sizeof(u64) * (size_t)cb * 4, st));
+        VGA_CUDA(cudaMemsetAsync(mode.p, 0, sizeof(int) * (size_t)cb, st));  // level 0 always pushes
+        VGA_CUDA(cudaMemsetAsync(counts.p, 0, sizeof(int32_t) * (size_t)lcap * cstride, st));
+        VGA_CUDA(cudaStreamSynchronize(st));
+        k_init<W><<<blocks_for(cs, 256), 256, 0, st>>>(d, d_order.p + first, cs);
+        tm.launches++;
+        mt.start();
+        int nlev = 1;
+        VGA_TRY(run_levels<W>(ctx, d, cb, radius, bfs_mode, &counts, &lcap, cstride, work.p, mt, &nlev));
+        mt.stop();
+        kt.stop();
+        VGA_CUDA(cudaGetLastError());
+        deepest = std::max(deepest, nlev);
+
+        // results of this chunk: level histogram -> host
+        dt.start();
+        h_counts.resize((size_t)nlev * cstride);
+        VGA_CUDA(cudaMemcpyAsync(h_counts.data(), counts.p, sizeof(int32_t) * (size_t)nlev * cstride, cudaMemcpyDeviceToHost, st));
+        dt.stop();
+        for (int64_t i = 0; i < cs; i++) {
+            const int64_t o = (int64_t)order[(size_t)(first + i)] - src_begin;
+            const int64_t wi = i >> 6;  // word index within the chunk = b*W + j
+            const int bit = (int)(i & 63);
+            int64_t tn = 1, td = 0;
+            if (dist && max_levels > 0) {
+                for (int l = 0; l < max_levels; l++) dist[o * max_levels + l] = 0;
+                dist[o * max_levels] = 1;
+            }
+            for (int l = 1; l < nlev; l++) {
+                int32_t c = h_counts[(size_t)l * cstride + (size_t)wi * 64 + bit];
+                tn += c;
+                td += (int64_t)l * c;
+                if (dist && l < max_levels) dist[o * max_levels + l] = c;
+            }
+            if (total_nodes) total_nodes[o] = (int32_t)tn;
+            if (total_depth) total_depth[o] = td;
+        }
+        if (ctx->progress) ctx->progress(ctx->user, std::min<int64_t>(nsrc, (b0 + cb) * W * 64), nsrc);
+    }
+    if (levels_used) *levels_used = deepest;
+    {
+        u64 hw[4] = {0, 0, 0, 0};
+        VGA_CUDA(cudaMemcpy(hw, work.p, sizeof(hw), cudaMemcpyDeviceToHost));
+        uint64_t rp[2] = {0, 0};
+        VGA_CUDA(cudaMemcpy(&rp[0], g->rowptr.p + src_begin, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        VGA_CUDA(cudaMemcpy(&rp[1], g->rowptr.p + src_end, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        // algorithmic bytes (SURVEY.md §8d with B = 64*W sources per batch, CSR rows of 4-byte entries), per
+        // batch and level: rows of the expanding vertices + one frontier vector (B/8 bytes) read per
+        // expanding vertex + one visited/next read-modify-write (2 vectors) per newly reached vertex;
+        // level 0 expands the sources.
+        const double src_edges = (double)(rp[1] - rp[0]);
+        const double vec = 8.0 * W;
+        tm.algo_bytes = 4.0 * ((double)hw[0] + src_edges) + vec * ((double)hw[1] + (double)nsrc) + 2.0 * vec * (double)hw[1];
+    }
+    if (dist && deepest > max_levels) {
+        set_error("vga_global: level histogram needs " + std::to_string(deepest) + " columns");
+        return VGA_ERR_CAPACITY;
+    }
+    return VGA_OK;
+}
+
 }  // namespace
+
+int batch_source_order(vga_ctx *ctx, vga_graph *g, int64_t src_begin, int64_t src_end, std::vector<int32_t> &order) {
+    return source_order(ctx, g, src_begin, src_end, order);
+}
 
 int ensure_transpose(vga_ctx *ctx, vga_graph *g) {
     if (g->has_transpose) return VGA_OK;
@@ -441,7 +819,6 @@ int ensure_transpose(vga_ctx *ctx, vga_graph *g) {
 
 int run_global(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_t src_end, int32_t *total_nodes,
                int64_t *total_depth, int32_t *dist, int32_t max_levels, int32_t *levels_used) {
-    cudaStream_t st = ctx->stream;
     const int64_t n = g->n;
     if (g->src_begin != 0 || g->src_end != n) {
         set_error("vga_global: the graph must hold the rows of all cells (gather the shards first)");
@@ -449,276 +826,27 @@ int run_global(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_
     }
     if (src_end < 0 || src_end > n) src_end = n;
     if (src_begin < 0) src_begin = 0;
-    const int64_t nsrc = std::max<int64_t>(0, src_end - src_begin);
     if (levels_used) *levels_used = 0;
-    if (nsrc == 0) return VGA_OK;
-    Timing &tm = ctx->timing;
-    const int bfs_mode = (int)ctx->opt.bfs_mode;
-    StageTimer kt(ctx, 0, &tm.kernel_ms);
-    StageTimer mt(ctx, 2, &tm.main_kernel_ms);
-    StageTimer dt(ctx, 4, &tm.d2h_ms);
-
-    kt.start();
-    if (bfs_mode != 0) VGA_TRY(ensure_transpose(ctx, g));
-    kt.stop();
-
-    // ---- source order: 8x8 cell tiles in Morton order (needs cell coordinates), else ordinal order
-    std::vector<int32_t> order((size_t)nsrc);
-    std::iota(order.begin(), order.end(), (int32_t)src_begin);
-    const bool spatial = ctx->opt.bfs_order != 0 && (int64_t)g->h_refs.size() >= n;
-    if (spatial) {
-        std::vector<uint64_t> key((size_t)nsrc);
-        for (int64_t i = 0; i < nsrc; i++) {
-            uint32_t r = (uint32_t)g->h_refs[(size_t)(src_begin + i)];
-            uint32_t x = r >> 16, y = r & 0xffff;
-            key[(size_t)i] = ((uint64_t)morton2(x >> 3, y >> 3) << 38) | ((uint64_t)(x & 7) << 35) | ((uint64_t)(y & 7) << 32) |
-                             (uint64_t)(uint32_t)i;
-        }
-        std::sort(key.begin(), key.end());
-        for (int64_t i = 0; i < nsrc; i++) order[(size_t)i] = (int32_t)(src_begin + (int64_t)(key[(size_t)i] & 0xffffffffu));
-        if (ctx->opt.bfs_order >= 2) {
-            // Wall-respecting clusters: a raw 8x8 tile often straddles a wall, which puts cells of two
-            // rooms (very different level structure) into one batch.  Grow each batch as a flood of up
-            // to 64 cells over the direct-neighbour links (the 8 grid neighbours that are in the cell's
-            // row, i.e. actually visible), seeded in Morton order.
-            int maxx = 0, maxy = 0;
-            for (int64_t v = 0; v < n; v++) {
-                uint32_t r = (uint32_t)g->h_refs[(size_t)v];
-                maxx = std::max(maxx, (int)(r >> 16));
-                maxy = std::max(maxy, (int)(r & 0xffff));
-            }
-            const int64_t cols = maxx + 1, rows = maxy + 1;
-            std::vector<int32_t> ord_of((size_t)(cols * rows), -1);
-            for (int64_t v = 0; v < n; v++) {
-                uint32_t r = (uint32_t)g->h_refs[(size_t)v];
-                ord_of[(size_t)((int64_t)(r >> 16) * rows + (r & 0xffff))] = (int32_t)v;
-            }
-            std::vector<uint8_t> gc((size_t)n);
-            {
-                DevBuf<int32_t> d_refs, d_ord;
-                DevBuf<uint8_t> d_gc;
-                VGA_TRY(d_refs.alloc((size_t)n));
-                VGA_TRY(d_ord.alloc((size_t)(cols * rows)));
-                VGA_TRY(d_gc.alloc((size_t)n));
-                VGA_CUDA(cudaMemcpyAsync(d_refs.p, g->h_refs.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
-                VGA_CUDA(cudaMemcpyAsync(d_ord.p, ord_of.data(), sizeof(int32_t) * cols * rows, cudaMemcpyHostToDevice, st));
-                k_neighbour_bits<<<blocks_for(n, 256), 256, 0, st>>>(n, g->rowptr.p, g->adj.p, d_refs.p, d_ord.p, (int)cols,
-                                                                    (int)rows, d_gc.p);
-                tm.launches++;
-                VGA_CUDA(cudaMemcpyAsync(gc.data(), d_gc.p, (size_t)n, cudaMemcpyDeviceToHost, st));
-                VGA_CUDA(cudaStreamSynchronize(st));
-            }
-            static const int dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
-            static const int dy[8] = {0, 1, 1, 1, 0, -1, -1, -1};
-            std::vector<uint8_t> taken((size_t)n, 0);
-            std::vector<int32_t> clustered, queue;
-            clustered.reserve((size_t)nsrc);
-            for (int64_t i = 0; i < nsrc; i++) {
-                const int32_t seed = order[(size_t)i];
-                if (taken[(size_t)seed]) continue;
-                queue.clear();
-                queue.push_back(seed);
-                taken[(size_t)seed] = 1;
-                size_t head = 0;
-                int count = 0;
-                while (head < queue.size() && count < 64) {
-                    const int32_t v = queue[head++];
-                    clustered.push_back(v);
-                    count++;
-                    const uint32_t r = (uint32_t)g->h_refs[(size_t)v];
-                    const int x = (int)(r >> 16), y = (int)(r & 0xffff);
-                    for (int k = 0; k < 8; k++) {
-                        if (!(gc[(size_t)v] & (1 << k))) continue;
-                        const int nx = x + dx[k], ny = y + dy[k];
-                        if (nx < 0 || nx >= cols || ny < 0 || ny >= rows) continue;
-                        const int32_t w = ord_of[(size_t)((int64_t)nx * rows + ny)];
-                        if (w < (int32_t)src_begin || w >= (int32_t)src_end || taken[(size_t)w]) continue;
-                        taken[(size_t)w] = 1;
-                        queue.push_back(w);
-                    }
-                }
-                for (; head < queue.size(); head++) taken[(size_t)queue[head]] = 0;  // not placed: free again
-            }
-            if ((int64_t)clustered.size() == nsrc) order.swap(clustered);
-        }
+    if (src_end <= src_begin) return VGA_OK;
+    int words = (int)ctx->opt.bfs_words;
+    if (words <= 0) {
+        // auto (measured, profiles/): while the adjacency is L2 resident one word per batch is as fast as
+        // any; once rows stream from HBM two words halve that traffic; very long rows (large open halls)
+        // amortise best over four
+        const double avg_deg = n > 0 ? (double)g->entries / (double)n : 0.0;
+        if ((double)g->entries * 4.0 <= 256e6)
+            words = 1;
+        else if (avg_deg >= 8192.0)
+            words = 4;
+        else
+            words = 2;
     }
-    DevBuf<int32_t> d_order;
-    VGA_TRY(d_order.alloc((size_t)nsrc));
-    VGA_CUDA(cudaMemcpyAsync(d_order.p, order.data(), sizeof(int32_t) * nsrc, cudaMemcpyHostToDevice, st));
-
-    const int64_t nbatch = (nsrc + 63) / 64;
-    const int group = (int)std::max<int64_t>(1, ctx->opt.bfs_group);
-    const bool coarse = bfs_mode != 0 && ctx->opt.bfs_coarse != 0;
-    // chunk size: 3 words per (batch, vertex) + the coarse pass; below ~40% of free memory and 48 GB
-    size_t free_b = 0, total_b = 0;
-    VGA_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    int64_t budget = (int64_t)std::min<size_t>((size_t)(free_b * 0.4), (size_t)48 << 30);
-    int64_t chunk = ctx->opt.bfs_chunk > 0 ? ctx->opt.bfs_chunk : std::max<int64_t>(1, budget / (26 * std::max<int64_t>(n, 1)));
-    chunk = std::min<int64_t>(chunk, nbatch);
-    chunk = std::min<int64_t>(chunk, 65535);
-    if (chunk > group) chunk -= chunk % group;  // whole groups per chunk
-    const int64_t max_groups = (chunk + group - 1) / group;
-
-    DevBuf<u64> visited, frontier, next, valid, stats, work, c_visited, c_frontier, c_next, c_valid, c_stats;
-    DevBuf<int> active, mode, any, c_active, c_mode;
-    DevBuf<int32_t> counts;
-    DevBuf<uint8_t> lvl;
-    int lcap = 16;
-    VGA_TRY(visited.alloc((size_t)chunk * n));
-    VGA_TRY(frontier.alloc((size_t)chunk * n));
-    VGA_TRY(next.alloc((size_t)chunk * n));
-    VGA_TRY(valid.alloc((size_t)chunk));
-    VGA_TRY(stats.alloc((size_t)chunk * 4));
-    VGA_TRY(work.alloc_zero(4, st));
-    VGA_TRY(active.alloc((size_t)chunk));
-    VGA_TRY(mode.alloc((size_t)chunk));
-    VGA_TRY(any.alloc(1));
-    VGA_TRY(counts.alloc((size_t)lcap * chunk * 64));
-    const int64_t max_cbatch = (max_groups + 63) / 64;  // coarse batches: 64 groups per word
-    if (coarse) {
-        VGA_TRY(c_visited.alloc((size_t)max_cbatch * n));
-        VGA_TRY(c_frontier.alloc((size_t)max_cbatch * n));
-        VGA_TRY(c_next.alloc((size_t)max_cbatch * n));
-        VGA_TRY(c_valid.alloc((size_t)max_cbatch));
-        VGA_TRY(c_stats.alloc((size_t)max_cbatch * 4));
-        VGA_TRY(c_active.alloc((size_t)max_cbatch));
-        VGA_TRY(c_mode.alloc((size_t)max_cbatch));
-        VGA_TRY(lvl.alloc((size_t)max_cbatch * 64 * n));
+    if ((src_end - src_begin) <= 64) words = 1;
+    switch (words) {
+    case 4: return run_global_w<4>(ctx, g, radius, src_begin, src_end, total_nodes, total_depth, dist, max_levels, levels_used);
+    case 2: return run_global_w<2>(ctx, g, radius, src_begin, src_end, total_nodes, total_depth, dist, max_levels, levels_used);
+    default: return run_global_w<1>(ctx, g, radius, src_begin, src_end, total_nodes, total_depth, dist, max_levels, levels_used);
     }
-
-    BfsDev d;
-    d.n = n;
-    d.rowptr = g->rowptr.p;
-    d.adj = g->adj.p;
-    d.t_rowptr = g->has_transpose ? g->t_rowptr.p : nullptr;
-    d.t_col = g->has_transpose ? g->t_col.p : nullptr;
-    d.visited = visited.p;
-    d.frontier = frontier.p;
-    d.next = next.p;
-    d.valid = valid.p;
-    d.active = active.p;
-    d.mode = mode.p;
-    d.stats = stats.p;
-    d.any = any.p;
-    d.lvl_in = coarse ? lvl.p : nullptr;
-    d.lvl_out = nullptr;
-    d.group = group;
-
-    int deepest = 0;
-    std::vector<int32_t> h_counts;
-    std::vector<u64> h_valid;
-    std::vector<int> ones;
-
-    for (int64_t b0 = 0; b0 < nbatch; b0 += chunk) {
-        const int64_t cb = std::min<int64_t>(chunk, nbatch - b0);
-        const int64_t first = b0 * 64;  // index into the ordered source list
-        const int64_t cs = std::min<int64_t>(cb * 64, nsrc - first);
-        if (ctx->cancel && ctx->cancel(ctx->user)) {
-            set_error("cancelled");
-            return VGA_ERR_CANCELLED;
-        }
-        kt.start();
-        // ---- coarse pass: group lower bounds, 64 groups per bit-parallel batch (push only)
-        if (coarse) {
-            const int64_t ngroups = (cb + group - 1) / group;
-            const int64_t ng = (ngroups + 63) / 64;
-            BfsDev c = d;
-            c.visited = c_visited.p;
-            c.frontier = c_frontier.p;
-            c.next = c_next.p;
-            c.valid = c_valid.p;
-            c.active = c_active.p;
-            c.mode = c_mode.p;
-            c.stats = c_stats.p;
-            c.lvl_in = nullptr;
-            c.lvl_out = lvl.p;
-            c.group = 1;
-            h_valid.assign((size_t)ng, ~0ULL);
-            if (ngroups & 63) h_valid[(size_t)ng - 1] = (1ULL << (ngroups & 63)) - 1ULL;
-            ones.assign((size_t)ng, 1);
-            VGA_CUDA(cudaMemcpyAsync(c_valid.p, h_valid.data(), sizeof(u64) * ng, cudaMemcpyHostToDevice, st));
-            VGA_CUDA(cudaMemcpyAsync(c_active.p, ones.data(), sizeof(int) * ng, cudaMemcpyHostToDevice, st));
-            VGA_CUDA(cudaMemsetAsync(c_visited.p, 0, sizeof(u64) * (size_t)ng * n, st));
-            VGA_CUDA(cudaMemsetAsync(c_frontier.p, 0, sizeof(u64) * (size_t)ng * n, st));
-            VGA_CUDA(cudaMemsetAsync(c_next.p, 0, sizeof(u64) * (size_t)ng * n, st));
-            VGA_CUDA(cudaMemsetAsync(c_stats.p, 0, sizeof(u64) * (size_t)ng * 4, st));
-            VGA_CUDA(cudaMemsetAsync(c_mode.p, 0, sizeof(int) * (size_t)ng, st));
-            VGA_CUDA(cudaMemsetAsync(lvl.p, 0xff, (size_t)ng * 64 * n, st));
-            VGA_CUDA(cudaStreamSynchronize(st));  // host staging vectors are reused below
-            k_init_coarse<<<blocks_for(cs, 256), 256, 0, st>>>(c, d_order.p + first, cs, 64 * group);
-            tm.launches++;
-            mt.start();
-            int cl = 0;
-            VGA_TRY(run_levels(ctx, c, ng, radius, 0, nullptr, nullptr, 0, nullptr, mt, &cl));
-            mt.stop();
-        }
-        // ---- exact pass
-        h_valid.assign((size_t)cb, ~0ULL);
-        if (cs & 63) h_valid[(size_t)cb - 1] = (1ULL << (cs & 63)) - 1ULL;
-        ones.assign((size_t)cb, 1);
-        VGA_CUDA(cudaMemcpyAsync(valid.p, h_valid.data(), sizeof(u64) * cb, cudaMemcpyHostToDevice, st));
-        VGA_CUDA(cudaMemcpyAsync(active.p, ones.data(), sizeof(int) * cb, cudaMemcpyHostToDevice, st));
-        VGA_CUDA(cudaMemsetAsync(visited.p, 0, sizeof(u64) * (size_t)cb * n, st));
-        VGA_CUDA(cudaMemsetAsync(frontier.p, 0, sizeof(u64) * (size_t)cb * n, st));
-        VGA_CUDA(cudaMemsetAsync(next.p, 0, sizeof(u64) * (size_t)cb * n, st));
-        VGA_CUDA(cudaMemsetAsync(stats.p, 0, sizeof(u64) * (size_t)cb * 4, st));
-        VGA_CUDA(cudaMemsetAsync(mode.p, 0, sizeof(int) * (size_t)cb, st));  // level 0 always pushes
-        VGA_CUDA(cudaMemsetAsync(counts.p, 0, sizeof(int32_t) * (size_t)lcap * chunk * 64, st));
-        VGA_CUDA(cudaStreamSynchronize(st));
-        k_init<<<blocks_for(cs, 256), 256, 0, st>>>(d, d_order.p + first, cs);
-        tm.launches++;
-        mt.start();
-        int nlev = 1;
-        VGA_TRY(run_levels(ctx, d, cb, radius, bfs_mode, &counts, &lcap, chunk * 64, work.p, mt, &nlev));
-        mt.stop();
-        kt.stop();
-        VGA_CUDA(cudaGetLastError());
-        deepest = std::max(deepest, nlev);
-
-        // results of this chunk: level histogram -> host
-        dt.start();
-        h_counts.resize((size_t)nlev * chunk * 64);
-        VGA_CUDA(cudaMemcpyAsync(h_counts.data(), counts.p, sizeof(int32_t) * (size_t)nlev * chunk * 64,
-                                 cudaMemcpyDeviceToHost, st));
-        dt.stop();
-        for (int64_t i = 0; i < cs; i++) {
-            const int64_t o = (int64_t)order[(size_t)(first + i)] - src_begin;
-            const int64_t b = i >> 6;
-            const int bit = (int)(i & 63);
-            int64_t tn = 1, td = 0;
-            if (dist && max_levels > 0) {
-                for (int l = 0; l < max_levels; l++) dist[o * max_levels + l] = 0;
-                dist[o * max_levels] = 1;
-            }
-            for (int l = 1; l < nlev; l++) {
-                int32_t c = h_counts[((size_t)l * chunk + b) * 64 + bit];
-                tn += c;
-                td += (int64_t)l * c;
-                if (dist && l < max_levels) dist[o * max_levels + l] = c;
-            }
-            if (total_nodes) total_nodes[o] = (int32_t)tn;
-            if (total_depth) total_depth[o] = td;
-        }
-        if (ctx->progress) ctx->progress(ctx->user, std::min<int64_t>(nsrc, (b0 + cb) * 64), nsrc);
-    }
-    if (levels_used) *levels_used = deepest;
-    {
-        u64 hw[4] = {0, 0, 0, 0};
-        VGA_CUDA(cudaMemcpy(hw, work.p, sizeof(hw), cudaMemcpyDeviceToHost));
-        uint64_t rp[2] = {0, 0};
-        VGA_CUDA(cudaMemcpy(&rp[0], g->rowptr.p + src_begin, sizeof(uint64_t), cudaMemcpyDeviceToHost));
-        VGA_CUDA(cudaMemcpy(&rp[1], g->rowptr.p + src_end, sizeof(uint64_t), cudaMemcpyDeviceToHost));
-        // algorithmic bytes (SURVEY.md §8d with B = 64, CSR rows of 4-byte entries), per batch and level:
-        // rows of the expanding vertices + one frontier word read per expanding vertex + one
-        // visited/next read-modify-write (2 words) per newly reached vertex; level 0 expands the sources.
-        const double src_edges = (double)(rp[1] - rp[0]);
-        tm.algo_bytes = 4.0 * ((double)hw[0] + src_edges) + 8.0 * ((double)hw[1] + (double)nsrc) + 16.0 * (double)hw[1];
-    }
-    if (dist && deepest > max_levels) {
-        set_error("vga_global: level histogram needs " + std::to_string(deepest) + " columns");
-        return VGA_ERR_CAPACITY;
-    }
-    return VGA_OK;
 }
 
 }  // namespace vga

@@ -27,6 +27,8 @@ static int64_t env_i64(const char *name, int64_t dflt) {
 static int set_option(Options &o, const std::string &key, int64_t value) {
     if (key == "bfs_mode") o.bfs_mode = value;
     else if (key == "bfs_chunk") o.bfs_chunk = value;
+    else if (key == "bfs_words") o.bfs_words = value;
+    else if (key == "local_mode") o.local_mode = value;
     else if (key == "sieve_mode") o.sieve_mode = value;
     else if (key == "sieve_gcap") o.sieve_gcap = value;
     else if (key == "sieve_bcap") o.sieve_bcap = value;

@@ -82,7 +82,9 @@ struct Timing {
 // Tunables (vga_ctx_set_option / environment)
 struct Options {
     int64_t bfs_mode = 2;        // 0 push only, 1 pull only, 2 direction-optimising hybrid
-    int64_t bfs_chunk = 0;       // batches (of 64 sources) in flight; 0 = auto from free memory
+    int64_t bfs_words = 0;       // 64-bit words per vertex and batch (a batch = 64*words sources): 1, 2, 4; 0 = auto
+    int64_t local_mode = 2;      // 0: one CTA per cell with bitmaps, 1: bit-parallel batches of 64 cells, 2: auto
+    int64_t bfs_chunk = 0;       // 64-source words in flight; 0 = auto from free memory
     int64_t sieve_mode = 1;      // 1: thread-per-(source,octant) kernel + warp kernel for overflow, 0: warp kernel
     int64_t sieve_gcap = 48;     // shared-memory gap capacity per warp
     int64_t sieve_bcap = 192;    // shared-memory block capacity per warp
@@ -156,6 +158,8 @@ namespace vga {
 int build_graph(vga_ctx *ctx, const vga_dgrid *g, int64_t src_begin, int64_t src_end, vga_graph **out);
 // bfs.cu
 int ensure_transpose(vga_ctx *ctx, vga_graph *g);
+// spatially coherent order of the sources [src_begin, src_end) for 64-source batches
+int batch_source_order(vga_ctx *ctx, vga_graph *g, int64_t src_begin, int64_t src_end, std::vector<int32_t> &order);
 int run_global(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_t src_end, int32_t *total_nodes,
                int64_t *total_depth, int32_t *dist, int32_t max_levels, int32_t *levels_used);
 // local.cu

@@ -162,15 +162,28 @@ def test_makegraph_vs_oracle(ctx, name):
     assert np.array_equal(st["gridconn"], a["gridconn"])
 
 
-@pytest.mark.parametrize("name", ["oblique:30:30:7", "office:64:64:1", "gallery:160:160:3"])
+_ORACLE_CACHE = {}
+
+
+def cached_oracle(name):
+    if name not in _ORACLE_CACHE:
+        flat = capi.prepare(plans.by_name(name))
+        _ORACLE_CACHE[name] = (flat, oracle_graph(flat))
+    return _ORACLE_CACHE[name]
+
+
+@pytest.mark.parametrize("name", ["oblique:30:30:7", "office:64:64:1"])
 @pytest.mark.parametrize("radius", [-1, 2])
-@pytest.mark.parametrize("mode", [0, 1, 2])
-def test_global_vs_oracle_all_modes(name, radius, mode):
+@pytest.mark.parametrize("mode,words,coarse,order", [(0, 1, 0, 0), (1, 1, 1, 1), (2, 1, 1, 2), (0, 4, 0, 2), (1, 2, 1, 2),
+                                                     (2, 4, 1, 2), (2, 0, 1, 2)])
+def test_global_vs_oracle_all_modes(name, radius, mode, words, coarse, order):
     c = capi.Context(0)
     c.set_option("bfs_mode", mode)
-    flat = capi.prepare(plans.by_name(name))
+    c.set_option("bfs_words", words)
+    c.set_option("bfs_coarse", coarse)
+    c.set_option("bfs_order", order)
+    flat, og = cached_oracle(name)
     g = c.build(flat)
-    og = oracle_graph(flat)
     tn, td, dist, used = g.global_ints(radius)
     rng = np.random.RandomState(3)
     for s in rng.choice(g.n, min(g.n, 96), replace=False):
@@ -182,16 +195,23 @@ def test_global_vs_oracle_all_modes(name, radius, mode):
 
 
 @pytest.mark.parametrize("name", ["oblique:30:30:7", "office:64:64:1", "urban:120:120:4"])
-def test_local_vs_oracle(ctx, name):
-    flat = capi.prepare(plans.by_name(name))
-    g = ctx.build(flat)
-    og = oracle_graph(flat)
+@pytest.mark.parametrize("local_mode", [0, 1])
+def test_local_vs_oracle(name, local_mode):
+    """Both local kernels (bit-parallel batched = default, CTA-per-cell bitmaps) against the oracle."""
+    flat, og = cached_oracle(name)
+    c = capi.Context(0)
+    c.set_option("local_mode", local_mode)
+    g = c.build(flat)
     lo = max(0, g.n // 2 - 100)
     hi = min(g.n, lo + 200)
     a = g.local_ints((lo, hi))
     b = og.local_ints((lo, hi))
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+    if g.n <= 5000:  # whole map through the batched path (several batches, partial last batch)
+        for x, y in zip(g.local_ints(), og.local_ints()):
+            assert np.array_equal(x, y)
+    c.close()
 
 
 def test_maxdist_vs_oracle(ctx):

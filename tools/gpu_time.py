@@ -20,7 +20,9 @@ for rep in range(2):
 if "global" in what:
     for rad in (-1, 3):
         for rep in range(2):
-            t0 = time.time(); tn, td, dist, used = g.global_ints(rad); dt = time.time() - t0
+            lim = int(os.environ.get("VGA_TIME_SRC", "0"))
+            src = None if lim <= 0 else (g.n // 2 - lim // 2, g.n // 2 - lim // 2 + lim)
+            t0 = time.time(); tn, td, dist, used = g.global_ints(rad, src); dt = time.time() - t0
             print(f"global r={rad} rep{rep}: wall {dt*1e3:.1f} ms levels={used} meandepth={(td/np.maximum(tn-1,1)).mean():.3f} {ctx.timing()}", flush=True)
 if "local" in what:
     t0 = time.time(); cl, kk, tot, ctl = g.local_ints(); dt = time.time() - t0
