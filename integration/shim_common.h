@@ -1,0 +1,101 @@
+// Shared helpers of the shim translation units that put libvga_b200.so behind the reference's
+// own entry points.  These files are compiled INSIDE the reference tree's
+// include path (they are members of reference classes); they hold no reference code.
+#pragma once
+
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "genlib/exceptions.h"
+#include "salalib/pointdata.h"
+#include "vga_b200.h"
+
+namespace vga_shim {
+
+inline vga_ctx *gpu() {  // one process drives one GPU
+    static vga_ctx *c = nullptr;
+    if (!c) {
+        int dev = 0;
+        if (const char *e = std::getenv("VGA_DEVICE")) dev = std::atoi(e);
+        if (vga_ctx_create(dev, &c) != VGA_OK)
+            throw depthmapX::RuntimeException(std::string("GPU path: ") + vga_last_error());  // no CPU fallback
+    }
+    return c;
+}
+
+struct CommState {
+    Communicator *comm;
+    time_t atime;
+};
+inline void progress_cb(void *u, int64_t done, int64_t) {
+    CommState *s = static_cast<CommState *>(u);
+    if (s->comm) s->comm->CommPostMessage(Communicator::CURRENT_RECORD, (int)done);
+}
+inline int cancel_cb(void *u) {
+    CommState *s = static_cast<CommState *>(u);
+    return (s->comm && qtimer(s->atime, 500) && s->comm->IsCancelled()) ? 1 : 0;
+}
+
+// x-major list of filled cells and the cell -> ordinal map (unfilled cells: N + rank among unfilled)
+struct Ordinals {
+    std::vector<PixelRef> cells;   // filled, x-major
+    std::vector<int32_t> ord;      // [cols*rows]
+    int64_t n = 0, ghosts = 0;
+};
+inline Ordinals make_ordinals(PointMap &map) {
+    Ordinals o;
+    const size_t cols = map.getCols(), rows = map.getRows();
+    o.ord.assign(cols * rows, -1);
+    int64_t unfilled = 0;
+    for (size_t i = 0; i < cols; i++)
+        for (size_t j = 0; j < rows; j++) {
+            PixelRef p((short)i, (short)j);
+            if (map.getPoint(p).filled()) {
+                o.ord[i * rows + j] = (int32_t)o.cells.size();
+                o.cells.push_back(p);
+            } else {
+                o.ord[i * rows + j] = -(int32_t)(1 + unfilled++);
+            }
+        }
+    o.n = (int64_t)o.cells.size();
+    o.ghosts = unfilled;
+    return o;
+}
+
+// adjacency of a made graph, flattened from the Nodes (Node::first/next iteration order)
+inline vga_graph *graph_from_nodes(PointMap &map, const Ordinals &o) {
+    std::vector<uint64_t> rowptr((size_t)o.n + 1, 0);
+    std::vector<uint32_t> col;
+    const size_t rows = map.getRows();
+    for (int64_t v = 0; v < o.n; v++) {
+        Point &pt = map.getPoint(o.cells[(size_t)v]);
+        if (!pt.getMergePixel().empty() || pt.contextfilled())
+            throw depthmapX::RuntimeException("GPU path: merged / context-filled cells are not supported");
+        if (pt.hasNode()) {
+            Node &node = pt.getNode();
+            node.first();
+            while (!node.is_tail()) {
+                PixelRef w = node.cursor();
+                int32_t id = o.ord[(size_t)w.x * rows + (size_t)w.y];
+                col.push_back(id >= 0 ? (uint32_t)id : (uint32_t)(o.n + (-(id + 1))));
+                node.next();
+            }
+        }
+        rowptr[(size_t)v + 1] = col.size();
+    }
+    vga_graph *g = nullptr;
+    if (vga_graph_from_csr(gpu(), o.n, o.ghosts, rowptr.data(), col.data(), nullptr, &g) != VGA_OK)
+        throw depthmapX::RuntimeException(std::string("GPU path: ") + vga_last_error());
+    std::vector<int32_t> refs;
+    refs.reserve((size_t)(o.n + o.ghosts));
+    for (const PixelRef &p : o.cells) refs.push_back((int)p);
+    const size_t cols = map.getCols();
+    for (size_t i = 0; i < cols; i++)
+        for (size_t j = 0; j < rows; j++)
+            if (o.ord[i * rows + j] < 0) refs.push_back((int)PixelRef((short)i, (short)j));
+    vga_graph_set_cell_refs(g, refs.data(), (int64_t)refs.size());
+    return g;
+}
+
+}  // namespace vga_shim

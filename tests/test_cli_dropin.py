@@ -1,0 +1,56 @@
+"""Drop-in check on the GPU box: the REAL depthmapXcli with libvga_b200.so behind PointMap::sparkGraph2,
+VGAVisualGlobal::run and VGAVisualLocal::run (oracle/_ref/depthmapXcli_gpu, built by integration/Makefile from
+the unmodified reference sources + the shim translation units in integration/) must write byte-identical
+.graph files to the unmodified reference CLI (oracle/_ref/depthmapXcli_ref) for
+    -m VISPREP -pg .. -pp .. -pm      and      -m VGA -vm visibility -vg -vl -vr {n,3}
+-- the reference's own regression method (RegressionTest/depthmaprunner.py:19-79: byte-diff of the outputs)."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+from depthmapx_b200 import capi, plans
+
+pytestmark = pytest.mark.gpu
+
+REF = os.path.join(ROOT, "oracle", "_ref", "depthmapXcli_ref")
+GPU = os.path.join(ROOT, "oracle", "_ref", "depthmapXcli_gpu")
+
+
+def run(binary, args, cwd):
+    r = subprocess.run([binary] + args, cwd=cwd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, f"{os.path.basename(binary)} {' '.join(args)}\n{r.stdout}\n{r.stderr}"
+    return r.stdout
+
+
+def same(a, b):
+    return open(a, "rb").read() == open(b, "rb").read()
+
+
+@pytest.mark.parametrize("name,grid,seed", [("oblique:20:20:11", "1", "1,1"), ("office:24:24:2", "1", "1,1"),
+                                            ("oblique:16:16:5:0.7", "0.7", "0.7,0.7")])
+def test_cli_outputs_byte_identical(tmp_path, name, grid, seed):
+    if not (os.path.exists(REF) and os.path.exists(GPU)):
+        pytest.skip("integration binaries not built (make -C integration)")
+    if capi.device_count() < 1:
+        pytest.fail("needs a CUDA device")
+    plan = plans.by_name(name)
+    d = str(tmp_path)
+    open(os.path.join(d, "walls.csv"), "w").write(plan.csv())
+    run(REF, ["-m", "IMPORT", "-f", "walls.csv", "-o", "plan.graph", "-it", "drawing"], d)
+    for tag, binary in (("ref", REF), ("gpu", GPU)):
+        run(binary, ["-m", "VISPREP", "-f", "plan.graph", "-o", f"prep_{tag}.graph", "-pg", grid, "-pp", seed, "-pm"], d)
+    assert same(os.path.join(d, "prep_ref.graph"), os.path.join(d, "prep_gpu.graph")), "makegraph .graph differs"
+    for radius in ("n", "3"):
+        for tag, binary in (("ref", REF), ("gpu", GPU)):
+            run(binary, ["-m", "VGA", "-f", "prep_ref.graph", "-o", f"vga_{radius}_{tag}.graph", "-vm", "visibility",
+                         "-vg", "-vl", "-vr", radius], d)
+        assert same(os.path.join(d, f"vga_{radius}_ref.graph"), os.path.join(d, f"vga_{radius}_gpu.graph")), \
+            f"VGA -vr {radius} .graph differs"
+    # boundary graph (-pb) and restricted visibility (-pr) variants of VISPREP
+    for extra, tag2 in ((["-pb"], "pb"), (["-pr", "7.5"], "pr")):
+        for tag, binary in (("ref", REF), ("gpu", GPU)):
+            run(binary, ["-m", "VISPREP", "-f", "plan.graph", "-o", f"prep_{tag2}_{tag}.graph", "-pg", grid, "-pp", seed,
+                         "-pm"] + extra, d)
+        assert same(os.path.join(d, f"prep_{tag2}_ref.graph"), os.path.join(d, f"prep_{tag2}_gpu.graph")), tag2
