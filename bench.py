@@ -200,6 +200,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- libvga_b200 has no CPU path")
     dist = None
     if world > 1:
+        # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION/INFO: keep stdout to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+            os.environ["NCCL_DEBUG_FILE"] = os.environ.get("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

@@ -32,6 +32,9 @@
 
 #include <algorithm>
 #include <memory>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <numeric>
 
 #include "vga_dev.cuh"
@@ -583,12 +586,17 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int6
     StageTimer mt(ctx, 2, &tm.main_kernel_ms);
     StageTimer dt(ctx, 4, &tm.d2h_ms);
 
+    const bool dbg = std::getenv("VGA_DEBUG_TIMING") != nullptr;
+    auto wall = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double w0 = wall();
     kt.start();
     if (bfs_mode != 0) VGA_TRY(ensure_transpose(ctx, g));
     kt.stop();
+    const double w1 = wall();
 
     std::vector<int32_t> order;
     VGA_TRY(source_order(ctx, g, src_begin, src_end, order));
+    const double w2 = wall();
     DevBuf<int32_t> d_order;
     VGA_TRY(d_order.alloc((size_t)nsrc));
     VGA_CUDA(cudaMemcpyAsync(d_order.p, order.data(), sizeof(int32_t) * nsrc, cudaMemcpyHostToDevice, st));
@@ -756,6 +764,9 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int6
         if (ctx->progress) ctx->progress(ctx->user, std::min<int64_t>(nsrc, (b0 + cb) * W * 64), nsrc);
     }
     if (levels_used) *levels_used = deepest;
+    if (dbg)
+        fprintf(stderr, "[vga_global] transpose %.2f ms, source order %.2f ms, alloc+levels+results %.2f ms (level kernels %.2f)\n",
+                w1 - w0, w2 - w1, wall() - w2, tm.main_kernel_ms);
     {
         u64 hw[4] = {0, 0, 0, 0};
         VGA_CUDA(cudaMemcpy(hw, work.p, sizeof(hw), cudaMemcpyDeviceToHost));
