@@ -141,7 +141,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", help="C1..C5 or kind:W:H:seed (default C2, BASELINE.json configs[1])")
     ap.add_argument("--radius", type=int, default=-1)
-    ap.add_argument("--local", action="store_true", help="also run VGA local in the step (not part of the headline metric)")
+    ap.add_argument("--vga-local", dest="local", action="store_true", help="also run VGA local in the step (not part of the headline metric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (big workloads run by hand)")
     ap.add_argument("--cpu-bfs-sources", type=int, default=48)
@@ -200,9 +200,11 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- libvga_b200 has no CPU path")
     dist = None
     if world > 1:
-        # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION/INFO: keep stdout to the one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
-            os.environ["NCCL_DEBUG_FILE"] = os.environ.get("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL prints a version banner on stdout: point fd 1 at stderr while the job runs and give it back
+        # for the one JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -259,9 +261,17 @@ def main():
             pack[:, 2:2 + min(L, hist.shape[1])] = hist[:, :L]
             mine = torch.from_numpy(pack).to(dev)
             cnts = [e - s for s, e in multi.partition(n, world)]
-            multi.gather_results(mine, cnts, dist, rank, world)
+            res = multi.gather_results(mine, cnts, dist, rank, world)
             torch.cuda.synchronize(dev)
+            if rank == 0:
+                r = res.cpu().numpy()
+                stats["checksum"] = {"sum_nodes": int(r[:, 0].sum()), "sum_depth": int(r[:, 1].sum()),
+                                     "sum_hist_weighted": int((r[:, 2:] * (np.arange(L) + 1)[None, :]).sum())}
             full.free()
+        else:
+            Lh = hist.shape[1]
+            stats["checksum"] = {"sum_nodes": int(tn.astype(np.int64).sum()), "sum_depth": int(td.sum()),
+                                 "sum_hist_weighted": int((hist.astype(np.int64) * (np.arange(Lh) + 1)[None, :]).sum())}
         g.free()
         t4 = time.perf_counter()
         stats.update(build_ms=(t1 - t0) * 1e3, gather_ms=(t2 - t1) * 1e3, bfs_ms=(t3 - t2) * 1e3, total_ms=(t4 - t0) * 1e3,
@@ -328,6 +338,9 @@ def main():
     launches = reduce_sum(float(np.sum([s["build_timing"]["launches"] + s["bfs_timing"]["launches"] for s in st_res])))
     main_launches = float(np.mean([s["bfs_timing"]["main_launches"] for s in st_res]))
     edges = reduce_sum(float(st_res[0]["edges"]))
+    # every collective must happen BEFORE the non-zero ranks leave (a lone all_reduce on rank 0 would
+    # block until the NCCL watchdog aborts the process)
+    local_ms = reduce_max(float(np.mean([s["local_ms"] for s in st_res]))) if args.local else None
     peak, peak_src = load_peaks()
     achieved = bfs_algo / (bfs_main_ms * 1e-3) / 1e9 / world  # per GPU
     if rank != 0:
@@ -345,7 +358,7 @@ def main():
                    "makegraph_edges_per_s": edges / (build_ms * 1e-3), "global_bfs_ms": bfs_ms,
                    "global_bfs_cells_per_s": n / (bfs_ms * 1e-3), "allgather_ms": gather_ms,
                    "sieve_kernels_ms": sieve_main_ms, "bfs_level_kernels_ms": bfs_main_ms,
-                   "local_ms": reduce_max(float(np.mean([s["local_ms"] for s in st_res]))) if args.local else None},
+                   "local_ms": local_ms},
         "e2e": {"value": n / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int(flat.input_bytes()), "d2h_bytes_per_step": int(st_e2e[0]["d2h_bytes"]),
                 "makegraph_ms": float(np.mean([s["build_ms"] for s in st_e2e])),
@@ -360,6 +373,9 @@ def main():
                      "algorithmic_bytes_per_step": bfs_algo, "kernel_ms_per_step": bfs_main_ms,
                      "launches_per_step": main_launches},
         "clocks": clocks,
+        # size-independent result check: equal for every N on the same workload (sums over all sources of
+        # Node Count, total depth and the level histogram weighted by level+1)
+        "result_checksum": st_res[-1].get("checksum"),
     }
     if world == 1 and not args.no_cpu_baseline:
         try:
@@ -374,8 +390,12 @@ def main():
                                     "makegraph_cells_per_s": 1.0 / ref["mk_s_per_cell"],
                                     "global_bfs_cells_per_s": 1.0 / ref["bfs_s_per_cell"],
                                     "host_cores_available": os.cpu_count()}
-    print(json.dumps(line))
     if dist is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        os.dup2(2, 1)
         dist.destroy_process_group()
     return 0
 
