@@ -241,7 +241,8 @@ def main():
             full = ctx.graph_from_device_rows(n, g.ghosts, rp_full.data_ptr(), adj_full.data_ptr(), base)
             full.set_cell_refs(g.cell_refs())  # coordinates -> spatially coherent BFS batches
             del rp_full, adj_full, rp_local, adj_local
-            torch.cuda.empty_cache()  # the library holds its own copy now
+            if base * 4 > (4 << 30):
+                torch.cuda.empty_cache()  # the library holds its own copy now; give multi-GB staging buffers back
             stats["gather_bytes"] = int(base) * 4
         t2 = time.perf_counter()
         tn, td, hist, used = full.global_ints(args.radius, (lo, hi))
