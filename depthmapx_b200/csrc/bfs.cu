@@ -618,14 +618,18 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int6
     const int64_t max_groups = (chunk + group - 1) / group;
     const int64_t max_cbatch = (max_groups + 63) / 64;  // coarse batches: 64 groups per word
 
-    DevBuf<u64> visited, frontier, next, valid, stats, work, c_visited, c_frontier, c_next, c_valid, c_stats;
+    DevBuf<u64> valid, stats, work, c_visited, c_frontier, c_next, c_valid, c_stats;
     DevBuf<int> active, mode, any, c_active, c_mode;
     DevBuf<int32_t> counts;
     DevBuf<uint8_t> lvl;
     int lcap = 16;
-    VGA_TRY(visited.alloc((size_t)chunk * n * W));
-    VGA_TRY(frontier.alloc((size_t)chunk * n * W));
-    VGA_TRY(next.alloc((size_t)chunk * n * W));
+    // the three big state arrays live in the context's workspace and are reused by later calls
+    struct {
+        u64 *p;
+    } visited, frontier, next;
+    VGA_TRY(ctx->ws.get("bfs_visited", sizeof(u64) * (size_t)chunk * n * W, (void **)&visited.p));
+    VGA_TRY(ctx->ws.get("bfs_frontier", sizeof(u64) * (size_t)chunk * n * W, (void **)&frontier.p));
+    VGA_TRY(ctx->ws.get("bfs_next", sizeof(u64) * (size_t)chunk * n * W, (void **)&next.p));
     VGA_TRY(valid.alloc((size_t)chunk * W));
     VGA_TRY(stats.alloc((size_t)chunk * 4));
     VGA_TRY(work.alloc_zero(4, st));

@@ -160,6 +160,9 @@ void vga_ctx_destroy(vga_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    g_alloc_stream = ctx->stream;
+    ctx->ws.clear();
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     {
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);

@@ -74,6 +74,26 @@ template <typename T> struct DevBuf {
     }
 };
 
+// Grow-only named device buffers kept by a context across calls (the GB-sized BFS state): even the
+// stream-ordered pool occasionally has to map fresh memory when block sizes differ between calls,
+// which showed up as 30-40 ms of jitter per vga_global call.
+struct Workspace {
+    std::vector<std::pair<std::string, DevBuf<unsigned char>>> bufs;
+    int get(const char *name, size_t bytes, void **out) {
+        for (auto &b : bufs)
+            if (b.first == name) {
+                if (b.second.n < bytes) VGA_TRY(b.second.alloc(bytes));
+                *out = b.second.p;
+                return VGA_OK;
+            }
+        bufs.emplace_back(std::string(name), DevBuf<unsigned char>());
+        VGA_TRY(bufs.back().second.alloc(bytes));
+        *out = bufs.back().second.p;
+        return VGA_OK;
+    }
+    void clear() { bufs.clear(); }
+};
+
 struct Timing {
     double h2d_ms = 0, kernel_ms = 0, d2h_ms = 0, main_kernel_ms = 0, algo_bytes = 0;
     int64_t launches = 0, main_launches = 0;
@@ -108,6 +128,7 @@ struct vga_ctx {
     size_t smem_optin = 0;
     vga::Options opt;
     vga::Timing timing;
+    vga::Workspace ws;
     vga_progress_fn progress = nullptr;
     vga_cancel_fn cancel = nullptr;
     void *user = nullptr;
