@@ -19,7 +19,8 @@
  * Conventions: every function returns 0 on success and a negative vga_status otherwise;
  * vga_last_error() gives the message of the last failure on the calling thread.  There is NO CPU
  * fallback: without a CUDA device every compute entry point fails with VGA_ERR_NO_DEVICE.
- * Unsupported inputs (merged pixels, CONTEXTFILLED cells, NaN blocks, N >= 2^27) are errors.
+ * Unsupported inputs (merged pixels, CONTEXTFILLED cells, NaN blocks, grids of 2^26 cells or more)
+ * are errors.
  * One process drives one GPU (vga_ctx_create(device)); multi-GPU runs shard sources across
  * processes (src_begin/src_end arguments) and exchange shards outside this library.
  *
@@ -94,7 +95,7 @@ int vga_ctx_set_callbacks(vga_ctx *ctx, vga_progress_fn progress, vga_cancel_fn 
  * unknown keys are VGA_ERR_INVALID */
 int vga_ctx_set_option(vga_ctx *ctx, const char *key, int64_t value);
 int vga_ctx_timing(const vga_ctx *ctx, vga_timing *out);
-/* cudaDeviceSynchronize + error check */
+/* wait for the context's stream + error check */
 int vga_ctx_sync(vga_ctx *ctx);
 
 /* ---- construction (makegraph) ------------------------------------------------------------- */
