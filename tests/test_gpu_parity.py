@@ -375,3 +375,42 @@ def test_properties_c1_full_size(ctx):
     assert np.array_equal(np.diff(rp).astype(np.int64), st["connectivity"].astype(np.int64))  # no fill-ins here
     # Connectivity must equal the degree the BFS sees at level 1
     assert np.array_equal(dist[:, 1].astype(np.int64), st["connectivity"].astype(np.int64))
+
+
+def test_properties_c2_full_size(ctx):
+    """BASELINE config 2 (the bench workload) at full size: histogram identities, full reachability, and
+    equality of two entirely different BFS schedules (default: coherent clusters + coarse-pruned hybrid
+    vs. plain x-major push-only single-word batches).  Both local kernels must agree on a slice (config 3)."""
+    flat = capi.prepare(plans.by_name("C2"))
+    g = ctx.build(flat)
+    tn, td, dist, used = g.global_ints(-1)
+    assert (dist.sum(axis=1) == tn).all()
+    assert ((dist * np.arange(dist.shape[1])).sum(axis=1) == td).all()
+    assert (tn == g.n).all()
+    c2 = capi.Context(0)
+    for k, v in (("bfs_mode", 0), ("bfs_words", 1), ("bfs_order", 0), ("bfs_coarse", 0), ("local_mode", 1)):
+        c2.set_option(k, v)
+    g2 = c2.build(flat)
+    tn2, td2, dist2, used2 = g2.global_ints(-1)
+    assert used2 == used
+    assert np.array_equal(tn, tn2) and np.array_equal(td, td2) and np.array_equal(dist, dist2)
+    a = g.local_ints((1000, 1256))    # default: per-cell bitmaps at this degree
+    b = g2.local_ints((1000, 1256))   # bit-parallel batches
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    c2.close()
+
+
+def test_properties_c4_radius_truncates(ctx):
+    """BASELINE config 4 (512x512 gallery, 3.9e9 edges): radius 3 vs radius n on a slice of sources --
+    a radius only truncates the level histogram; the four-word batches are exercised at scale."""
+    flat = capi.prepare(plans.by_name("C4"))
+    g = ctx.build(flat)
+    src = (g.n // 2, g.n // 2 + 2048)
+    tn, td, dist, used = g.global_ints(-1, src)
+    tn3, td3, dist3, used3 = g.global_ints(3, src)
+    assert used3 <= 4
+    assert (tn == g.n).all() and (tn3 <= tn).all()
+    assert np.array_equal(dist3[:, :3], dist[:, :3])
+    assert (dist.sum(axis=1) == tn).all() and (dist3.sum(axis=1) == tn3).all()
+    g.free()
