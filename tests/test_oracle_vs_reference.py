@@ -1,0 +1,53 @@
+"""CPU: the oracle (oracle/vga_oracle.c) and the host pre-steps (depthmapx_b200/host) against the UNMODIFIED
+reference compiled into oracle/_ref/libdmxref.so, on seeded random plans (oblique walls, spacings 0.5..2.0).
+This is what "parity pinned" rests on besides the committed golden fixtures.  Skipped when the reference
+library has not been built (make -C oracle ref needs /root/reference)."""
+import random
+
+import numpy as np
+import pytest
+
+from depthmapx_b200 import capi, plans
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.skipif(not po.have_ref(), reason="oracle/_ref/libdmxref.so not built")
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_plan_bit_equal_to_reference(seed):
+    rng = random.Random(1000 + seed)
+    w, h = rng.randrange(8, 22), rng.randrange(8, 22)
+    sp = rng.choice([1.0, 0.7, 1.3, 0.5, 2.0])
+    p = plans.oblique(w, h, seed, n_axis=rng.randrange(2, 8), n_oblique=rng.randrange(0, 5), spacing=sp)
+    rm = po.RefMap(p.walls, p.spacing)
+    if not rm.fill(*p.seeds[0]):
+        pytest.skip("seed cell not fillable in this plan")
+    g = rm.grid()
+    # host pre-steps (setGrid, blockLines, makePoints) == reference
+    hm = capi.HostMap(p.walls, p.spacing)
+    assert hm.fill(*p.seeds[0])
+    f = hm.flat()
+    assert np.array_equal(g.state, f.state) and np.array_equal(g.line_off, f.line_off) and np.array_equal(g.lines, f.lines)
+    # oracle makegraph == reference sparkGraph2
+    og = po.OracleGraph(g)
+    rm.makegraph()
+    rp, ref, b = rm.edges()
+    orp, oref, ob = og.iter_rows()
+    assert np.array_equal(rp, orp) and np.array_equal(ref, oref) and np.array_equal(b, ob)
+    a = og.node_attrs()
+    cnt, dist, gc = rm.bins()
+    assert np.array_equal(cnt, a["bin_count"]) and np.array_equal(dist, a["far"]) and np.array_equal(gc, a["gridconn"])
+    assert np.array_equal(rm.attr("Connectivity"), a["connectivity"])
+    assert np.array_equal(rm.attr("Point First Moment"), a["first_moment"])
+    assert np.array_equal(rm.attr("Point Second Moment"), a["second_moment"])
+    # oracle global / local == reference VGAVisualGlobal / VGAVisualLocal (all columns, float32 bit-equal)
+    radius = rng.choice([-1, 2, 3])
+    rm.vga_global(float(radius))
+    tn, td, d, nl = og.global_ints(radius)
+    sfx = "" if radius == -1 else f" R{radius}"
+    for k, v in po.global_formulas(tn, td, d, nl).items():
+        assert np.array_equal(rm.attr(k + sfx), v), k
+    if rm.n <= 300:  # the reference's local analysis is O(k^3)
+        rm.vga_local()
+        for k, v in po.local_formulas(*og.local_ints()).items():
+            assert np.array_equal(rm.attr(k), v), k
