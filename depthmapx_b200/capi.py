@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "vga_ctx_set_option", "vga_ctx_timing", "vga_ctx_sync", "vga_graph_build", "vga_grid_upload", "vga_dgrid_free",
     "vga_graph_build_resident", "vga_graph_from_csr", "vga_graph_free", "vga_graph_num_cells", "vga_graph_num_ghosts",
     "vga_graph_num_edges", "vga_graph_src_begin", "vga_graph_src_end", "vga_graph_csr", "vga_graph_cell_refs", "vga_graph_set_cell_refs",
-    "vga_graph_node_stats", "vga_global", "vga_global_attributes", "vga_local", "vga_local_attributes",
+    "vga_graph_node_stats", "vga_global", "vga_global_attributes", "vga_local", "vga_local_attributes", "vga_step_depth",
     "vga_graph_device_rows", "vga_graph_from_device_rows",
 ]
 HOST_SYMBOLS = [
@@ -81,6 +81,7 @@ def abi():
         L.vga_global.argtypes = [vp, vp, C.c_int, i64, i64, vp, vp, vp, C.c_int32, C.POINTER(C.c_int32)]
         L.vga_global_attributes.argtypes = [i64, vp, vp, vp, C.c_int32] + [vp] * 7
         L.vga_local.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp]
+        L.vga_step_depth.argtypes = [vp, vp, vp, i64, vp]
         L.vga_local_attributes.argtypes = [i64] + [vp] * 7
         L.vga_graph_device_rows.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
         L.vga_graph_from_device_rows.argtypes = [vp, i64, i64, vp, vp, i64, C.POINTER(vp)]
@@ -296,6 +297,13 @@ class Graph:
                 continue
             check(rc)
             return tn, td, dist, used.value
+
+    def step_depth(self, sources):
+        """Visual step depth from a set of cells (x-major ordinals): int32 [N], -1 = not reached."""
+        src = np.ascontiguousarray(sources, np.int64)
+        d = np.zeros(self.n, np.int32)
+        check(abi().vga_step_depth(self.ctx.h, self.h, _p(src), len(src), _p(d)))
+        return d
 
     def local_ints(self, src=None):
         b, e = (0, self.n) if src is None else src

@@ -540,6 +540,14 @@ int vga_local(vga_ctx *ctx, const vga_graph *g, int64_t src_begin, int64_t src_e
     return run_local(ctx, const_cast<vga_graph *>(g), src_begin, src_end, cluster, k, total, control);
 }
 
+int vga_step_depth(vga_ctx *ctx, const vga_graph *g, const int64_t *sources, int64_t n_sources, int32_t *depth) {
+    if (!ctx || !g || !depth || n_sources < 0 || (n_sources > 0 && !sources)) return VGA_ERR_INVALID;
+    VGA_CUDA(cudaSetDevice(ctx->device));
+    g_alloc_stream = ctx->stream;
+    ctx->timing = Timing();
+    return run_step_depth(ctx, const_cast<vga_graph *>(g), sources, n_sources, depth);
+}
+
 int vga_local_attributes(int64_t n, const int64_t *cluster, const int32_t *k, const int32_t *total, const float *control,
                          float *clustering, float *control_out, float *controllability) {
     if (n < 0 || !cluster || !k || !total || !control) return VGA_ERR_INVALID;

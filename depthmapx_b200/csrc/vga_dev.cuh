@@ -183,6 +183,8 @@ int ensure_transpose(vga_ctx *ctx, vga_graph *g);
 int batch_source_order(vga_ctx *ctx, vga_graph *g, int64_t src_begin, int64_t src_end, std::vector<int32_t> &order);
 int run_global(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_t src_end, int32_t *total_nodes,
                int64_t *total_depth, int32_t *dist, int32_t max_levels, int32_t *levels_used);
+// stepdepth.cu
+int run_step_depth(vga_ctx *ctx, vga_graph *g, const int64_t *sources, int64_t nsrc, int32_t *depth_out);
 // local.cu
 int run_local(vga_ctx *ctx, vga_graph *g, int64_t src_begin, int64_t src_end, int64_t *cluster, int32_t *k,
               int32_t *total, float *control);

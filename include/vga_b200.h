@@ -166,6 +166,12 @@ int vga_local(vga_ctx *ctx, const vga_graph *g, int64_t src_begin, int64_t src_e
 int vga_local_attributes(int64_t n, const int64_t *cluster, const int32_t *k, const int32_t *total,
                          const float *control, float *clustering, float *control_out, float *controllability);
 
+/* Visual step depth (VGAVisualGlobalDepth::run,
+ * salalib/vgamodules/vgavisualglobaldepth.cpp:23-75): BFS from the SET of cells `sources` (x-major
+ * ordinals, the map's selection); depth[v] for all N cells = level at which v is first reached, -1 if
+ * never.  No merge links / context fill. */
+int vga_step_depth(vga_ctx *ctx, const vga_graph *g, const int64_t *sources, int64_t n_sources, int32_t *depth);
+
 /* ---- device-resident access for multi-GPU plumbing (pointers are CUDA device pointers) ------ */
 
 /* Device pointers of the sorted shard rows (valid until vga_graph_free): rowptr (u64, local,

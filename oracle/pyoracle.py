@@ -106,6 +106,8 @@ def olib():
         L.vgao_local.restype = C.c_int
         L.vgao_local.argtypes = [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 4
         L.vgao_local_formulas.argtypes = [C.c_int64] + [C.c_void_p] * 7
+        L.vgao_step_depth.restype = C.c_int
+        L.vgao_step_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.vgao_sieve_kat.restype = C.c_int
         L.vgao_sieve_kat.argtypes = [C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         _olib = L
@@ -183,6 +185,12 @@ class OracleGraph:
             raise RuntimeError("oracle BFS: maxl too small")
         return tn, td, dist, nl
 
+    def step_depth(self, sources):
+        src = np.ascontiguousarray(sources, np.int32)
+        d = np.zeros(self.n, np.int32)
+        olib().vgao_step_depth(self.h, _p(src), len(src), _p(d))
+        return d
+
     def local_ints(self, src=None):
         b, e = (0, self.n) if src is None else src
         k = e - b
@@ -252,6 +260,8 @@ def rlib():
         L.dmxref_vga_global.argtypes = [C.c_void_p, C.c_double, C.c_int]
         L.dmxref_vga_local.restype = C.c_double
         L.dmxref_vga_local.argtypes = [C.c_void_p, C.c_int]
+        L.dmxref_step_depth.restype = C.c_double
+        L.dmxref_step_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.dmxref_sample_makegraph.restype = C.c_double
         L.dmxref_sample_makegraph.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p]
         L.dmxref_sample_global.restype = C.c_double
@@ -336,6 +346,13 @@ class RefMap:
 
     def vga_local(self, simple=False):
         return rlib().dmxref_vga_local(self.h, int(simple))
+
+    def step_depth(self, sources):
+        src = np.ascontiguousarray(sources, np.int32)
+        t = rlib().dmxref_step_depth(self.h, _p(src), len(src))
+        if t < 0:
+            raise RuntimeError("reference VGAVisualGlobalDepth failed")
+        return self.attr("Visual Step Depth")
 
     def sample_makegraph(self, src, maxdist=-1.0):
         src = np.ascontiguousarray(src, np.int32)

@@ -60,6 +60,7 @@
 #include "salalib/ngraph.h"
 #include "salalib/vgamodules/vgavisualglobal.h"
 #include "salalib/vgamodules/vgavisuallocal.h"
+#include "salalib/vgamodules/vgavisualglobaldepth.h"
 #undef protected
 #undef private
 
@@ -259,6 +260,26 @@ double dmxref_vga_local(void *h, int simple) {
     double t0 = now_s();
     bool ok = VGAVisualLocal(false).run(nullptr, m, simple != 0);
     double t1 = now_s();
+    return ok ? (t1 - t0) : -1.0;
+}
+
+// Visual step depth from a selection of cells (x-major ordinals of filled cells): drives the reference's
+// VGAVisualGlobalDepth::run (salalib/vgamodules/vgavisualglobaldepth.cpp:23-75) through the map's
+// selection set, as the CLI's -m STEPDEPTH does.  Result: column "Visual Step Depth" via dmxref_attr.
+double dmxref_step_depth(void *h, const int32_t *src, int k) {
+    PointMap &m = *static_cast<Ref *>(h)->map;
+    size_t rows = m.getRows(), cols = m.getCols();
+    std::vector<PixelRef> ord;
+    for (size_t x = 0; x < cols; x++)
+        for (size_t y = 0; y < rows; y++)
+            if (m.getPoint(PixelRef((short)x, (short)y)).filled()) ord.push_back(PixelRef((short)x, (short)y));
+    m.getSelSet().clear();
+    for (int i = 0; i < k; i++) m.getSelSet().insert((int)ord[src[i]]);
+    double t0 = now_s();
+    VGAVisualGlobalDepth d;
+    bool ok = d.run(nullptr, m, false);
+    double t1 = now_s();
+    m.getSelSet().clear();
     return ok ? (t1 - t0) : -1.0;
 }
 

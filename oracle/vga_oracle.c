@@ -862,3 +862,44 @@ void vgao_local_formulas(int64_t n, const int64_t *cluster, const int32_t *k, co
         }
     }
 }
+
+/* ---------------------------------------------------------------- step depth (vgavisualglobaldepth.cpp:23-75)
+ * BFS from a set of cells; depth[v] = level at which the filled cell v is first popped, -1 if never
+ * (the column is reset to -1 by insertOrResetColumn).  No merges / context fill. */
+int vgao_step_depth(const vgao_graph *gr, const int32_t *src, int64_t nsrc, int32_t *depth) {
+    int64_t cells = (int64_t)gr->cols * gr->rows;
+    uint8_t *seen = (uint8_t *)calloc(cells, 1);
+    int32_t *cur = (int32_t *)malloc(sizeof(int32_t) * (cells + nsrc + 1));
+    int32_t *nxt = (int32_t *)malloc(sizeof(int32_t) * (cells + nsrc + 1));
+    for (int64_t v = 0; v < gr->n; v++) depth[v] = -1;
+    int64_t ncur = 0;
+    for (int64_t i = 0; i < nsrc; i++) cur[ncur++] = gr->cellref[src[i]];
+    int level = 0;
+    while (ncur > 0) {
+        int64_t nnxt = 0;
+        for (int64_t i = 0; i < ncur; i++) {
+            int64_t c = cell_of_ref(gr, cur[i]);
+            if (!(gr->state[c] & ST_FILLED)) continue;
+            int64_t u = gr->ord[c];
+            if (depth[u] != -1) continue; /* m_misc == ~0: already finalised */
+            depth[u] = level;
+            seen[c] = 1;
+            for (uint64_t e = gr->it_ptr[u]; e < gr->it_ptr[u + 1]; e++) {
+                int64_t wc = cell_of_ref(gr, gr->it.ref[e]);
+                if (!seen[wc]) {
+                    seen[wc] = 1;
+                    nxt[nnxt++] = gr->it.ref[e];
+                }
+            }
+        }
+        int32_t *t = cur;
+        cur = nxt;
+        nxt = t;
+        ncur = nnxt;
+        level++;
+    }
+    free(seen);
+    free(cur);
+    free(nxt);
+    return 0;
+}

@@ -72,6 +72,10 @@ int vgao_local(const vgao_graph *gr, int64_t src_begin, int64_t src_end, int64_t
 void vgao_local_formulas(int64_t n, const int64_t *cluster, const int32_t *k, const int32_t *total,
                          const float *control, float *clustering, float *control_out, float *controllability);
 
+/* visual step depth from a set of source cells (x-major ordinals): depth[N], -1 = not reached
+ * (salalib/vgamodules/vgavisualglobaldepth.cpp:23-75) */
+int vgao_step_depth(const vgao_graph *gr, const int32_t *src, int64_t nsrc, int32_t *depth);
+
 /* known-answer access to the sieve for salaTest/testsparksieve.cpp:21-83:
  * centre (cx,cy), octant q, nlines segments as 4 doubles (x1,y1,x2,y2); after block+collectgarbage
  * returns the number of gaps and writes up to cap (start,end) pairs. */

@@ -111,3 +111,17 @@ def test_maxdist_limits_targets():
     full = po.OracleGraph(grid_of(fx)).node_attrs()
     assert (a["connectivity"] <= full["connectivity"]).all()
     assert a["far"].max() <= 4.0 + 1e-6
+
+
+def test_step_depth_matches_reference():
+    """oracle step depth == the reference's "Visual Step Depth" column (golden)."""
+    sd = golden("stepdepth")
+    keys = sorted(k for k in sd.files if k.endswith("__src"))
+    assert keys
+    cache = {}
+    for k in keys:
+        name, i, _ = k.split("__")
+        if name not in cache:
+            cache[name] = po.OracleGraph(grid_of(golden(name)))
+        d = cache[name].step_depth(sd[k])
+        assert np.array_equal(d.astype(np.float32), sd[f"{name}__{i}__depth"]), k
