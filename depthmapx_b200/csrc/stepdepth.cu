@@ -5,10 +5,7 @@
 // with the whole warp and stamps unreached targets with level+1 (all writers of a word write the same
 // value, so no atomics are needed).  Ghost columns (unfilled cells) are skipped as the reference skips
 // them (p.filled() test, :45).
-//
-// STATUS: added after the round-1 GPU budget was spent -- the oracle and its pinning against the
-// reference are verified on CPU (tests/test_oracle.py), the GPU test (tests/test_zz_stepdepth_gpu.py)
-// is marked xfail(strict=False) until it has run on a B200.
+// Parity: tests/test_zz_stepdepth_gpu.py (reference golden column, oracle, vga_global histogram).
 #include <algorithm>
 
 #include "vga_dev.cuh"

@@ -1,13 +1,12 @@
-"""GPU: visual step depth (vga_step_depth) against the reference's golden column and the
-oracle.  The kernel was added after the round-1 GPU budget had been spent, so this file runs LAST and is
-xfail(strict=False) until it has been seen green on a B200 -- it cannot mask or break the parity suite."""
+"""GPU: visual step depth (vga_step_depth) against the reference's golden column
+(VGAVisualGlobalDepth::run) and the oracle, plus consistency with the all-sources BFS histogram."""
 import numpy as np
 import pytest
 
 from conftest import golden
 from depthmapx_b200 import capi, plans
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first GPU run pending (round-1 budget spent)")]
+pytestmark = pytest.mark.gpu
 
 
 def test_step_depth_vs_reference_golden():
