@@ -103,7 +103,8 @@ struct Timing {
 struct Options {
     int64_t bfs_mode = 2;        // 0 push only, 1 pull only, 2 direction-optimising hybrid
     int64_t bfs_words = 0;       // 64-bit words per vertex and batch (a batch = 64*words sources): 1, 2, 4; 0 = auto
-    int64_t local_mode = 2;      // 0: one CTA per cell with bitmaps, 1: bit-parallel batches of 64 cells, 2: auto
+    int64_t local_mode = 2;      // 0: one CTA per cell with bitmaps, 1: bit-parallel batches of 64 cells, 2: auto,
+                                 // 3: batches with bit-sliced counters (EXPERIMENTAL, opt-in, not yet run on a GPU)
     int64_t bfs_chunk = 0;       // 64-source words in flight; 0 = auto from free memory
     int64_t sieve_mode = 1;      // 1: thread-per-(source,octant) kernel + warp kernel for overflow, 0: warp kernel
     int64_t sieve_gcap = 48;     // shared-memory gap capacity per warp
