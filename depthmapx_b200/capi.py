@@ -42,6 +42,11 @@ HOST_SYMBOLS = [
     "dmxh_last_error", "dmxh_map_create", "dmxh_map_destroy", "dmxh_map_grid", "dmxh_map_block_lines", "dmxh_map_fill",
     "dmxh_map_filled_count", "dmxh_map_flat", "dmxh_map_make_graph", "dmxh_map_vga_global", "dmxh_map_vga_local",
     "dmxh_map_columns", "dmxh_map_attr", "dmxh_map_grid_connections", "dmxh_map_graph", "dmxh_release_context",
+    "dmxh_map_state", "dmxh_map_step_depth", "dmxh_map_select", "dmxh_map_selection", "dmxh_map_flat_rows", "dmxh_map_bins",
+    "dmxh_map_encode_nodes", "dmxh_map_begin_graph", "dmxh_map_finish_graph", "dmxh_map_write_global", "dmxh_map_write_local",
+    "dmxh_map_write_step_depth", "dmxh_graph_open", "dmxh_graph_close", "dmxh_graph_save", "dmxh_graph_num_maps",
+    "dmxh_graph_displayed_map", "dmxh_graph_map", "dmxh_graph_walls", "dmxh_graph_new_map", "dmxh_graph_make_graph",
+    "dmxh_graph_made",
 ]
 
 _abi = None
@@ -114,6 +119,33 @@ def host():
         H.dmxh_map_grid_connections.argtypes = [vp, vp]
         H.dmxh_map_graph.restype = vp
         H.dmxh_map_graph.argtypes = [vp]
+        H.dmxh_map_state.argtypes = [vp, vp]
+        H.dmxh_map_step_depth.argtypes = [vp, vp, C.c_int]
+        H.dmxh_map_select.argtypes = [vp, vp, C.c_int]
+        H.dmxh_map_selection.restype = i64
+        H.dmxh_map_selection.argtypes = [vp, vp]
+        H.dmxh_map_flat_rows.argtypes = [vp] * 6
+        H.dmxh_map_bins.argtypes = [vp] * 3
+        H.dmxh_map_encode_nodes.argtypes = [vp] * 6
+        H.dmxh_map_begin_graph.argtypes = [vp, C.c_int]
+        H.dmxh_map_finish_graph.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+        H.dmxh_map_write_global.argtypes = [vp, C.c_double, C.c_int, vp, vp, vp, C.c_int32]
+        H.dmxh_map_write_local.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+        H.dmxh_map_write_step_depth.argtypes = [vp, vp]
+        H.dmxh_graph_open.restype = vp
+        H.dmxh_graph_open.argtypes = [C.c_char_p]
+        H.dmxh_graph_close.argtypes = [vp]
+        H.dmxh_graph_save.argtypes = [vp, C.c_char_p]
+        H.dmxh_graph_num_maps.argtypes = [vp]
+        H.dmxh_graph_displayed_map.argtypes = [vp]
+        H.dmxh_graph_map.restype = vp
+        H.dmxh_graph_map.argtypes = [vp, C.c_int]
+        H.dmxh_graph_walls.restype = i64
+        H.dmxh_graph_walls.argtypes = [vp, vp]
+        H.dmxh_graph_new_map.restype = vp
+        H.dmxh_graph_new_map.argtypes = [vp, C.c_double]
+        H.dmxh_graph_make_graph.argtypes = [vp, C.c_int, C.c_double]
+        H.dmxh_graph_made.argtypes = [vp]
         _host = H
     return _host
 
@@ -343,18 +375,26 @@ class HostMap:
     """dmx::PointMap through the flat C view (mirrors PointMap's setGrid/makePoints/sparkGraph2 and the
     two VGA modules' run())."""
 
-    def __init__(self, walls, spacing=1.0):
-        w = np.ascontiguousarray(walls, np.float64).reshape(-1, 4)
-        self.h = host().dmxh_map_create(_p(w), w.shape[0], spacing)
+    def __init__(self, walls=None, spacing=1.0, handle=None, owner=None):
+        """walls + spacing: a new map (PointMap(region, drawing) + setGrid); handle: a map owned by a GraphFile."""
+        self._owner = owner  # keeps the GraphFile alive
+        if handle is not None:
+            self.h = handle
+        else:
+            w = np.ascontiguousarray(walls, np.float64).reshape(-1, 4)
+            self.h = host().dmxh_map_create(_p(w), w.shape[0], spacing)
+        self._refresh()
+
+    def _refresh(self):
         c, r = C.c_int32(), C.c_int32()
         s, bx, by = C.c_double(), C.c_double(), C.c_double()
         host().dmxh_map_grid(self.h, C.addressof(c), C.addressof(r), C.addressof(s), C.addressof(bx), C.addressof(by))
         self.cols, self.rows, self.spacing, self.bl_x, self.bl_y = c.value, r.value, s.value, bx.value, by.value
 
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and self._owner is None:
             host().dmxh_map_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def _ret(self, rc):
         if rc < 0:
@@ -404,6 +444,131 @@ class HostMap:
         out = np.zeros(self.n, np.uint8)
         host().dmxh_map_grid_connections(self.h, _p(out))
         return out
+
+    def state(self):
+        out = np.zeros(self.cols * self.rows, np.uint16)
+        host().dmxh_map_state(self.h, _p(out))
+        return out
+
+    def select(self, points):
+        pts = np.ascontiguousarray(points, np.float64).reshape(-1, 2)
+        return self._ret(host().dmxh_map_select(self.h, _p(pts), pts.shape[0]))
+
+    def selection(self):
+        n = host().dmxh_map_selection(self.h, None)
+        out = np.zeros(n, np.int32)
+        host().dmxh_map_selection(self.h, _p(out))
+        return out
+
+    def step_depth(self, points):
+        """VGAVisualGlobalDepth::run from the cells containing `points` (GPU)."""
+        pts = np.ascontiguousarray(points, np.float64).reshape(-1, 2)
+        return self._ret(host().dmxh_map_step_depth(self.h, _p(pts), pts.shape[0]))
+
+    def flat_rows(self):
+        """(rowptr, ref, bin): the run-length adjacency in Node::first/next order."""
+        n, e = i64(), i64()
+        self._ret(host().dmxh_map_flat_rows(self.h, C.addressof(n), C.addressof(e), None, None, None))
+        rowptr = np.zeros(n.value + 1, np.uint64)
+        ref = np.zeros(max(e.value, 1), np.int32)
+        b = np.zeros(max(e.value, 1), np.uint8)
+        self._ret(host().dmxh_map_flat_rows(self.h, None, None, _p(rowptr), _p(ref), _p(b)))
+        return rowptr, ref[:e.value], b[:e.value]
+
+    def bins(self):
+        cnt = np.zeros((self.n, 32), np.uint16)
+        dist = np.zeros((self.n, 32), np.float32)
+        self._ret(host().dmxh_map_bins(self.h, _p(cnt), _p(dist)))
+        return cnt, dist
+
+    def encode_nodes(self, rowptr, ref, b, accepted=None, far=None):
+        rowptr = np.ascontiguousarray(rowptr, np.uint64)
+        ref = np.ascontiguousarray(ref, np.int32)
+        b = np.ascontiguousarray(b, np.uint8)
+        acc = None if accepted is None else np.ascontiguousarray(accepted, np.uint8)
+        f = None if far is None else np.ascontiguousarray(far, np.float32)
+        return self._ret(host().dmxh_map_encode_nodes(self.h, _p(rowptr), _p(ref), _p(b), None if acc is None else _p(acc),
+                                                      None if f is None else _p(f)))
+
+    def begin_graph(self, boundary=False):
+        return self._ret(host().dmxh_map_begin_graph(self.h, int(boundary)))
+
+    def finish_graph(self, boundary, connectivity, sum_d, sum_d2, gridconn):
+        a = np.ascontiguousarray(connectivity, np.int32)
+        b = np.ascontiguousarray(sum_d, np.float64)
+        c = np.ascontiguousarray(sum_d2, np.float64)
+        d = np.ascontiguousarray(gridconn, np.uint8)
+        return self._ret(host().dmxh_map_finish_graph(self.h, int(boundary), _p(a), _p(b), _p(c), _p(d)))
+
+    def write_global(self, radius, simple, total_nodes, total_depth, dist):
+        tn = np.ascontiguousarray(total_nodes, np.int32)
+        td = np.ascontiguousarray(total_depth, np.int64)
+        d = np.ascontiguousarray(dist, np.int32)
+        return self._ret(host().dmxh_map_write_global(self.h, radius, int(simple), _p(tn), _p(td), _p(d), d.shape[1]))
+
+    def write_local(self, simple, cluster, k, total, control):
+        a = np.ascontiguousarray(cluster, np.int64)
+        b = np.ascontiguousarray(k, np.int32)
+        c = np.ascontiguousarray(total, np.int32)
+        d = np.ascontiguousarray(control, np.float32)
+        return self._ret(host().dmxh_map_write_local(self.h, int(simple), _p(a), _p(b), _p(c), _p(d)))
+
+    def write_step_depth(self, depth):
+        d = np.ascontiguousarray(depth, np.int32)
+        return self._ret(host().dmxh_map_write_step_depth(self.h, _p(d)))
+
+
+class GraphFile:
+    """dmx::GraphFile: a .graph container whose PointMap section is decoded / encoded by the host layer
+    (MetaGraph::readFromStream / write, salalib/mgraph.cpp:2492-2763)."""
+
+    def __init__(self, path):
+        self.h = host().dmxh_graph_open(os.fsencode(path))
+        if not self.h:
+            raise RuntimeError(host().dmxh_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            host().dmxh_graph_close(self.h)
+            self.h = None
+
+    @property
+    def num_maps(self):
+        return host().dmxh_graph_num_maps(self.h)
+
+    @property
+    def displayed_map(self):
+        return host().dmxh_graph_displayed_map(self.h)
+
+    def map(self, i=None) -> HostMap:
+        if i is None:
+            i = self.displayed_map
+        return HostMap(handle=host().dmxh_graph_map(self.h, i), owner=self)
+
+    def walls(self):
+        n = host().dmxh_graph_walls(self.h, None)
+        out = np.zeros((max(n, 1), 4))
+        host().dmxh_graph_walls(self.h, _p(out))
+        return out[:n]
+
+    def new_map(self, spacing) -> HostMap:
+        h = host().dmxh_graph_new_map(self.h, spacing)
+        if not h:
+            raise RuntimeError(host().dmxh_last_error().decode())
+        return HostMap(handle=h, owner=self)
+
+    def make_graph(self, boundary=False, maxdist=-1.0):
+        rc = host().dmxh_graph_make_graph(self.h, int(boundary), maxdist)
+        if rc < 0:
+            raise RuntimeError(host().dmxh_last_error().decode())
+        return bool(rc)
+
+    def graph_made(self):
+        host().dmxh_graph_made(self.h)
+
+    def save(self, path):
+        if host().dmxh_graph_save(self.h, os.fsencode(path)) < 0:
+            raise RuntimeError(host().dmxh_last_error().decode())
 
 
 def prepare(plan, maxdist=-1.0) -> FlatGrid:

@@ -4,6 +4,7 @@
 #include <cstring>
 #include <string>
 
+#include "graphfile.h"
 #include "pointmap.h"
 
 static thread_local std::string g_err;
@@ -119,6 +120,177 @@ int dmxh_map_grid_connections(void *map, uint8_t *out) {
         }
     return 1;
 }
+
+int dmxh_map_step_depth(void *map, const double *points, int npoints) {
+    return guarded([&] {
+        dmx::PointMap *m = static_cast<dmx::PointMap *>(map);
+        for (int i = 0; i < npoints; i++) {
+            dmx::Point2f p(points[2 * i], points[2 * i + 1]);
+            m->setCurSel(dmx::Region(p, p), true);
+        }
+        return dmx::VGAVisualGlobalDepth().run(nullptr, *m, false);
+    });
+}
+
+int dmxh_map_select(void *map, const double *points, int npoints) {
+    return guarded([&] {
+        dmx::PointMap *m = static_cast<dmx::PointMap *>(map);
+        for (int i = 0; i < npoints; i++) {
+            dmx::Point2f p(points[2 * i], points[2 * i + 1]);
+            m->setCurSel(dmx::Region(p, p), true);
+        }
+        return true;
+    });
+}
+
+int64_t dmxh_map_selection(void *map, int32_t *refs) {
+    const auto &sel = static_cast<dmx::PointMap *>(map)->getSelSet();
+    if (refs)
+        for (size_t i = 0; i < sel.size(); i++) refs[i] = int(sel[i]);
+    return (int64_t)sel.size();
+}
+
+int dmxh_map_flat_rows(void *map, int64_t *n, int64_t *entries, uint64_t *rowptr, int32_t *ref, uint8_t *bin) {
+    return guarded([&] {
+        dmx::PointMap::FlatRows rows;
+        static_cast<dmx::PointMap *>(map)->flattenNodes(rows);
+        if (n) *n = (int64_t)rows.rowptr.size() - 1;
+        if (entries) *entries = (int64_t)rows.ref.size();
+        if (rowptr) std::memcpy(rowptr, rows.rowptr.data(), rows.rowptr.size() * sizeof(uint64_t));
+        if (ref && !rows.ref.empty()) std::memcpy(ref, rows.ref.data(), rows.ref.size() * sizeof(int32_t));
+        if (bin && !rows.bin.empty()) std::memcpy(bin, rows.bin.data(), rows.bin.size());
+        return true;
+    });
+}
+
+int dmxh_map_bins(void *map, uint16_t *bin_count, float *bin_dist) {
+    return guarded([&] {
+        dmx::PointMap *m = static_cast<dmx::PointMap *>(map);
+        const dmx::NodeStore &ns = m->nodes();
+        size_t v = 0;
+        for (size_t c = 0; c < m->getCols() * m->getRows(); c++) {
+            if (!m->getPoint(dmx::PixelRef((int)(c / m->getRows()), (int)(c % m->getRows()))).filled()) continue;
+            const int32_t node = ns.node_of_cell.empty() ? -1 : ns.node_of_cell[c];
+            for (int i = 0; i < 32; i++) {
+                bin_count[v * 32 + (size_t)i] = node >= 0 ? ns.bins[(size_t)node * 32 + (size_t)i].count : 0;
+                bin_dist[v * 32 + (size_t)i] = node >= 0 ? ns.bins[(size_t)node * 32 + (size_t)i].distance : 0.0f;
+            }
+            v++;
+        }
+        return true;
+    });
+}
+
+int dmxh_map_encode_nodes(void *map, const uint64_t *rowptr, const int32_t *ref, const uint8_t *bin,
+                          const uint8_t *accepted, const float *far_bin_dists) {
+    return guarded([&] {
+        static_cast<dmx::PointMap *>(map)->encodeNodes(rowptr, ref, bin, accepted, far_bin_dists);
+        return true;
+    });
+}
+
+int dmxh_map_finish_graph(void *map, int boundarygraph, const int32_t *connectivity, const double *sum_d,
+                          const double *sum_d2, const uint8_t *grid_connections) {
+    return guarded([&] {
+        static_cast<dmx::PointMap *>(map)->finishSparkGraph(boundarygraph != 0, connectivity, sum_d, sum_d2, grid_connections);
+        return true;
+    });
+}
+
+int dmxh_map_begin_graph(void *map, int boundarygraph) {
+    return guarded([&] {
+        static_cast<dmx::PointMap *>(map)->beginSparkGraph(boundarygraph != 0);
+        return true;
+    });
+}
+
+int dmxh_map_write_global(void *map, double radius, int simple_version, const int32_t *total_nodes,
+                          const int64_t *total_depth, const int32_t *dist, int32_t max_levels) {
+    return guarded([&] {
+        dmx::VGAVisualGlobal::writeAttributes(*static_cast<dmx::PointMap *>(map), radius, simple_version != 0, total_nodes,
+                                              total_depth, dist, max_levels);
+        return true;
+    });
+}
+
+int dmxh_map_write_local(void *map, int simple_version, const int64_t *cluster, const int32_t *k, const int32_t *total,
+                         const float *control) {
+    return guarded([&] {
+        dmx::VGAVisualLocal::writeAttributes(*static_cast<dmx::PointMap *>(map), simple_version != 0, cluster, k, total, control);
+        return true;
+    });
+}
+
+int dmxh_map_write_step_depth(void *map, const int32_t *depth) {
+    return guarded([&] {
+        dmx::VGAVisualGlobalDepth::writeAttributes(*static_cast<dmx::PointMap *>(map), depth);
+        return true;
+    });
+}
+
+int dmxh_map_state(void *map, uint16_t *state) {
+    dmx::PointMap *m = static_cast<dmx::PointMap *>(map);
+    const size_t rows = m->getRows();
+    for (size_t c = 0; c < m->getCols() * rows; c++)
+        state[c] = (uint16_t)m->getPoint(dmx::PixelRef((int)(c / rows), (int)(c % rows))).state;
+    return 1;
+}
+
+void *dmxh_graph_open(const char *path) {
+    dmx::GraphFile *f = new dmx::GraphFile();
+    int rc = f->read(path);
+    if (rc != dmx::GraphFile::OK) {
+        g_err = "GraphFile::read: code " + std::to_string(rc) + " " + f->lastError();
+        delete f;
+        return nullptr;
+    }
+    return f;
+}
+
+void dmxh_graph_close(void *file) { delete static_cast<dmx::GraphFile *>(file); }
+
+int dmxh_graph_save(void *file, const char *path) {
+    return guarded([&] {
+        dmx::GraphFile *f = static_cast<dmx::GraphFile *>(file);
+        int rc = f->write(path);
+        if (rc != dmx::GraphFile::OK) throw dmx::RuntimeException("GraphFile::write: " + f->lastError());
+        return true;
+    });
+}
+
+int dmxh_graph_num_maps(void *file) { return (int)static_cast<dmx::GraphFile *>(file)->getNumPointMaps(); }
+int dmxh_graph_displayed_map(void *file) { return static_cast<dmx::GraphFile *>(file)->getDisplayedPointMapRef(); }
+void *dmxh_graph_map(void *file, int i) { return &static_cast<dmx::GraphFile *>(file)->getPointMap((size_t)i); }
+
+int64_t dmxh_graph_walls(void *file, double *out) {
+    const auto &w = static_cast<dmx::GraphFile *>(file)->getVisibleDrawingLines();
+    if (out)
+        for (size_t i = 0; i < w.size(); i++) {
+            out[4 * i] = w[i].start().x;
+            out[4 * i + 1] = w[i].start().y;
+            out[4 * i + 2] = w[i].end().x;
+            out[4 * i + 3] = w[i].end().y;
+        }
+    return (int64_t)w.size();
+}
+
+void *dmxh_graph_new_map(void *file, double spacing) {
+    dmx::GraphFile *f = static_cast<dmx::GraphFile *>(file);
+    void *out = nullptr;
+    guarded([&] {
+        f->addNewPointMap();
+        f->setGrid(spacing);
+        out = &f->getDisplayedPointMap();
+        return true;
+    });
+    return out;
+}
+
+int dmxh_graph_make_graph(void *file, int boundarygraph, double maxdist) {
+    return guarded([&] { return static_cast<dmx::GraphFile *>(file)->makeGraph(nullptr, boundarygraph != 0, maxdist); });
+}
+
+void dmxh_graph_made(void *file) { static_cast<dmx::GraphFile *>(file)->graphMade(); }
 
 void *dmxh_map_graph(void *map) { return static_cast<dmx::PointMap *>(map)->graph(); }
 

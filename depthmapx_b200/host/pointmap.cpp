@@ -32,32 +32,85 @@ void release_shared_context() {
 
 // ------------------------------------------------------------------------------------ attributes
 
+AttributeTable::AttributeTable() {
+    // LayerManagerImpl of a new table: one layer "Everything", visible (layermanagerimpl.cpp:22-27), written by
+    // LayerManagerImpl::write (:106-149) as available-layers mask, visible mask, count, key 1, name.  The
+    // available-layers word is what the reference's `0xffffffff << (32 + 0xfffffffe)` evaluates to in its build
+    // (an unsigned 32-bit shift by 30: 0xC0000000); tests/test_graphfile.py checks these bytes against files the
+    // reference wrote.
+    const int64_t available = 0xC0000000LL, visible = 1, key = 1;
+    const int32_t count = 1;
+    const char name[] = "Everything";
+    const uint32_t len = sizeof(name) - 1;
+    m_layers.append((const char *)&available, 8).append((const char *)&visible, 8).append((const char *)&count, 4);
+    m_layers.append((const char *)&key, 8).append((const char *)&len, 4).append(name, len);
+}
+
 int AttributeTable::insertOrResetColumn(const std::string &name) {
     int idx = getColumnIndex(name);
     if (idx < 0) {
-        m_names.push_back(name);
+        Column c;
+        c.name = name;
+        m_columns.push_back(c);
         m_cols.emplace_back(m_keys.size(), -1.0f);
-        return (int)m_names.size() - 1;
+        return (int)m_columns.size() - 1;
     }
-    std::fill(m_cols[idx].begin(), m_cols[idx].end(), -1.0f);
+    // reset: fresh statistics, unlocked, then setValue(-1) on every row (total -1, min -1, max -1)
+    Column &c = m_columns[idx];
+    c.min = c.max = c.total = -1.0;
+    c.locked = false;
+    for (size_t r = 0; r < m_keys.size(); r++) setValue(r, idx, -1.0f);
+    return idx;
+}
+
+int AttributeTable::insertOrResetLockedColumn(const std::string &name) {
+    int idx = insertOrResetColumn(name);
+    m_columns[idx].locked = true;
     return idx;
 }
 
 int AttributeTable::getColumnIndex(const std::string &name) const {
-    for (size_t i = 0; i < m_names.size(); i++)
-        if (m_names[i] == name) return (int)i;
+    for (size_t i = 0; i < m_columns.size(); i++)
+        if (m_columns[i].name == name) return (int)i;
     return -1;
+}
+
+// position of the column in name order (the order columns are serialised in); -1 / -2 pass through
+int AttributeTable::getColumnSortedIndex(int idx) const {
+    if (idx == -1 || idx == -2) return idx;
+    if (idx < 0 || idx >= (int)m_columns.size()) return -1;
+    int pos = 0;
+    for (size_t i = 0; i < m_columns.size(); i++)
+        if (m_columns[i].name < m_columns[idx].name) pos++;
+    return pos;
+}
+
+void AttributeTable::setValue(size_t row, int col, float v) {
+    float old = m_cols[col][row];
+    m_cols[col][row] = v;
+    if (old < 0.0f) old = 0.0f;
+    Column &c = m_columns[col];
+    if (c.total < 0) {
+        c.total = v;
+    } else {
+        c.total += v;
+        c.total -= old;
+    }
+    if (v > c.max) c.max = v;
+    if (c.min < 0 || v < c.min) c.min = v;
 }
 
 void AttributeTable::setRows(const std::vector<int> &keys) {
     m_keys = keys;
+    m_layer_keys.assign(keys.size(), 1);
     for (auto &c : m_cols) c.assign(m_keys.size(), -1.0f);
 }
 
 void AttributeTable::clear() {
-    m_names.clear();
+    m_columns.clear();
     m_cols.clear();
     m_keys.clear();
+    m_layer_keys.clear();
 }
 
 // ------------------------------------------------------------------------------------ PointMap
@@ -95,7 +148,13 @@ bool PointMap::setGrid(double spacing, const Point2f &offset) {
                       Point2f(m_bottom_left.x + double(m_cols - 1) * m_spacing + m_spacing / 2.0,
                               m_bottom_left.y + double(m_rows - 1) * m_spacing + m_spacing / 2.0));
     m_points.assign(m_cols * m_rows, Point());
+    for (size_t j = 0; j < m_cols; j++)
+        for (size_t k = 0; k < m_rows; k++) m_points[j * m_rows + k].location = depixelate(PixelRef((int)j, (int)k));
     m_filled_point_count = 0;
+    m_nodes.clear();
+    m_nodes_valid = false;
+    m_selection_set.clear();
+    m_has_selection = false;
     m_initialised = true;
     m_blockedlines = false;
     m_processed = false;
@@ -315,6 +374,8 @@ bool PointMap::unmake() {
     m_boundarygraph = false;
     m_displayed_attribute = -2;
     adoptGraph(nullptr);
+    m_nodes.clear();
+    m_nodes_valid = false;
     return true;
 }
 
@@ -339,8 +400,16 @@ int cancel_cb(void *u) {
 }
 }  // namespace
 
-// pointdata.cpp:1246-1341.  Host: boundary un-fill, columns, rows, flags.  GPU: everything per source.
-bool PointMap::sparkGraph2(Communicator *comm, bool boundarygraph, double maxdist) {
+std::vector<int> PointMap::filledKeys() const {
+    std::vector<int> keys;
+    for (size_t i = 0; i < m_cols; i++)
+        for (size_t j = 0; j < m_rows; j++)
+            if (m_points[i * m_rows + j].filled()) keys.push_back(int(PixelRef((int)i, (int)j)));
+    return keys;
+}
+
+// pointdata.cpp:1250-1264
+void PointMap::beginSparkGraph(bool boundarygraph) {
     if (!m_blockedlines) blockLines();
     if (boundarygraph) {
         for (Point &pt : m_points)
@@ -349,15 +418,39 @@ bool PointMap::sparkGraph2(Communicator *comm, bool boundarygraph, double maxdis
                 m_filled_point_count--;
             }
     }
-    const int connectivity_col = m_attributes.insertOrResetColumn("Connectivity");
+}
+
+// pointdata.cpp:1268-1341 without the per-source work: columns (Connectivity is a locked column), one row per
+// filled cell in x-major order with its three setValue calls, tagState's selection reset, unblockLines(false),
+// grid connections, flags, displayed attribute
+void PointMap::finishSparkGraph(bool boundarygraph, const int32_t *connectivity, const double *sum_d,
+                                const double *sum_d2, const uint8_t *grid_connections) {
+    const int connectivity_col = m_attributes.insertOrResetLockedColumn("Connectivity");
     const int m1_col = m_attributes.insertOrResetColumn("Point First Moment");
     const int m2_col = m_attributes.insertOrResetColumn("Point Second Moment");
+    m_selection_set.clear();  // tagState (pointdata.cpp:1198-1199); Point::SELECTED bits stay as they are
+    m_has_selection = false;
+    const std::vector<int> keys = filledKeys();
+    m_attributes.setRows(keys);
+    for (size_t v = 0; v < keys.size(); v++) {
+        m_attributes.setValue(v, connectivity_col, float(connectivity[v]));
+        m_attributes.setValue(v, m1_col, float(sum_d[v]));
+        m_attributes.setValue(v, m2_col, float(sum_d2[v]));
+        getPoint(PixelRef(keys[v])).grid_connections = grid_connections[v];
+    }
+    unblockLines(false);
+    m_processed = true;
+    if (boundarygraph) m_boundarygraph = true;
+    m_displayed_attribute = -2;
+    setDisplayedAttribute(connectivity_col);
+    m_nodes.clear();
+    m_nodes_valid = false;
+}
 
-    std::vector<int> keys;
-    for (size_t i = 0; i < m_cols; i++)
-        for (size_t j = 0; j < m_rows; j++)
-            if (m_points[i * m_rows + j].filled()) keys.push_back(int(PixelRef((int)i, (int)j)));
-    const int64_t n = (int64_t)keys.size();
+// pointdata.cpp:1246-1341.  Host: boundary un-fill, columns, rows, flags.  GPU: everything per source.
+bool PointMap::sparkGraph2(Communicator *comm, bool boundarygraph, double maxdist) {
+    beginSparkGraph(boundarygraph);
+    const int64_t n = (int64_t)filledKeys().size();
     if (comm) comm->CommPostMessage(Communicator::NUM_RECORDS, (int)n);
 
     Flat flat;
@@ -388,41 +481,63 @@ bool PointMap::sparkGraph2(Communicator *comm, bool boundarygraph, double maxdis
     if (rc != VGA_OK) throw RuntimeException(std::string("sparkGraph2: ") + vga_last_error());
     adoptGraph(g);
 
-    m_attributes.setRows(keys);
     std::vector<int32_t> conn((size_t)n);
     std::vector<double> sd((size_t)n), sd2((size_t)n);
     std::vector<uint8_t> gc((size_t)n);
     rc = vga_graph_node_stats(g, conn.data(), sd.data(), sd2.data(), nullptr, nullptr, gc.data());
     if (rc != VGA_OK) throw RuntimeException(std::string("sparkGraph2: ") + vga_last_error());
-    for (int64_t v = 0; v < n; v++) {
-        m_attributes.setValue((size_t)v, connectivity_col, float(conn[(size_t)v]));
-        m_attributes.setValue((size_t)v, m1_col, float(sd[(size_t)v]));
-        m_attributes.setValue((size_t)v, m2_col, float(sd2[(size_t)v]));
-        getPoint(PixelRef(keys[(size_t)v])).grid_connections = gc[(size_t)v];
-    }
-    unblockLines(false);
-    m_processed = true;
-    if (boundarygraph) m_boundarygraph = true;
-    m_displayed_attribute = -2;
-    setDisplayedAttribute(connectivity_col);
+    finishSparkGraph(boundarygraph, conn.data(), sd.data(), sd2.data(), gc.data());
+    return true;
+}
+
+// ------------------------------------------------------------------------------------ selection
+
+// pointdata.cpp:939-987
+bool PointMap::setCurSel(const Region &r, bool add) {
+    if (!m_has_selection)
+        add = false;
+    else if (!add)
+        clearSel();
+    const PixelRef bl = pixelate(r.bl, true), tr = pixelate(r.tr, true);
+    for (int i = bl.x; i <= tr.x; i++)
+        for (int j = bl.y; j <= tr.y; j++) {
+            Point &pnt = getPoint(PixelRef(i, j));
+            if ((pnt.state & Point::FILLED) && (~pnt.state & Point::SELECTED)) {
+                pnt.state |= Point::SELECTED;
+                const PixelRef ref(i, j);
+                auto pos = std::lower_bound(m_selection_set.begin(), m_selection_set.end(), ref,
+                                            [](const PixelRef &a, const PixelRef &b) { return int(a) < int(b); });
+                if (pos == m_selection_set.end() || int(*pos) != int(ref)) m_selection_set.insert(pos, ref);
+                m_has_selection = true;
+            }
+        }
+    return true;
+}
+
+// pointdata.cpp:923-937
+bool PointMap::clearSel() {
+    if (!m_has_selection) return false;
+    for (const PixelRef &p : m_selection_set) getPoint(p).state &= ~Point::SELECTED;
+    m_selection_set.clear();
+    m_has_selection = false;
     return true;
 }
 
 // ------------------------------------------------------------------------------------ analyses
 
-static void check_supported(const PointMap &map, bool gates_only, const char *who) {
+static void check_supported(PointMap &map, bool gates_only, const char *who) {
     if (gates_only) throw RuntimeException(std::string(who) + ": gates_only is not supported by the GPU path");
+    map.ensureGraph();
     if (!map.graph()) throw RuntimeException(std::string(who) + ": the map has no visibility graph (run sparkGraph2 first)");
 }
 
-// vgavisualglobal.cpp:23-216
-bool VGAVisualGlobal::run(Communicator *comm, PointMap &map, bool simple_version) {
-    check_supported(map, m_gates_only, "VGAVisualGlobal");
+// vgavisualglobal.cpp:33-63 (columns), 131-193 (formulas, which value is written when), 214 (display)
+void VGAVisualGlobal::writeAttributes(PointMap &map, double radius, bool simple_version, const int32_t *nodes,
+                                      const int64_t *depth, const int32_t *dist, int32_t maxl) {
     AttributeTable &attributes = map.getAttributeTable();
     const int64_t n = (int64_t)attributes.getNumRows();
-    if (comm) comm->CommPostMessage(Communicator::NUM_RECORDS, map.getFilledPointCount());
     std::string radius_text;
-    if (m_radius != -1) radius_text = std::string(" R") + std::to_string(int(m_radius));
+    if (radius != -1) radius_text = std::string(" R") + std::to_string(int(radius));
     int entropy_col = -1, rel_entropy_col = -1, integ_dv_col = -1, integ_pv_col = -1, integ_tk_col = -1, depth_col = -1,
         count_col = -1;
     if (!simple_version) entropy_col = attributes.insertOrResetColumn("Visual Entropy" + radius_text);
@@ -434,7 +549,37 @@ bool VGAVisualGlobal::run(Communicator *comm, PointMap &map, bool simple_version
         count_col = attributes.insertOrResetColumn("Visual Node Count" + radius_text);
         rel_entropy_col = attributes.insertOrResetColumn("Visual Relativised Entropy" + radius_text);
     }
+    std::vector<float> nc((size_t)n), md((size_t)n), hh((size_t)n), pv((size_t)n), tk((size_t)n), en((size_t)n), re((size_t)n);
+    vga_global_attributes(n, nodes, depth, dist, maxl, nc.data(), md.data(), hh.data(), pv.data(), tk.data(), en.data(),
+                          re.data());
+    // same setValue calls in the same order as the reference, so the column statistics (double running totals)
+    // come out identical
+    for (int64_t v = 0; v < n; v++) {
+        const size_t r = (size_t)v;
+        if (!simple_version) attributes.setValue(r, count_col, nc[r]);
+        if (nodes[r] > 1) {
+            if (!simple_version) attributes.setValue(r, depth_col, md[r]);
+            attributes.setValue(r, integ_dv_col, hh[r]);
+            if (!simple_version) {
+                attributes.setValue(r, integ_pv_col, pv[r]);
+                attributes.setValue(r, integ_tk_col, tk[r]);
+                attributes.setValue(r, entropy_col, en[r]);
+                attributes.setValue(r, rel_entropy_col, re[r]);
+            }
+        } else if (!simple_version) {
+            attributes.setValue(r, depth_col, -1.0f);
+            attributes.setValue(r, entropy_col, -1.0f);
+            attributes.setValue(r, rel_entropy_col, -1.0f);
+        }
+    }
+    map.setDisplayedAttribute(integ_dv_col);
+}
 
+// vgavisualglobal.cpp:23-216
+bool VGAVisualGlobal::run(Communicator *comm, PointMap &map, bool simple_version) {
+    check_supported(map, m_gates_only, "VGAVisualGlobal");
+    const int64_t n = (int64_t)map.getAttributeTable().getNumRows();
+    if (comm) comm->CommPostMessage(Communicator::NUM_RECORDS, map.getFilledPointCount());
     vga_ctx *ctx = map.context();
     CbState cb{comm, std::chrono::steady_clock::now(), false};
     vga_ctx_set_callbacks(ctx, progress_cb, cancel_cb, &cb);
@@ -455,35 +600,34 @@ bool VGAVisualGlobal::run(Communicator *comm, PointMap &map, bool simple_version
     vga_ctx_set_callbacks(ctx, nullptr, nullptr, nullptr);
     if (rc == VGA_ERR_CANCELLED) throw Communicator::CancelledException();
     if (rc != VGA_OK) throw RuntimeException(std::string("VGAVisualGlobal: ") + vga_last_error());
-
-    std::vector<float> nc((size_t)n), md((size_t)n), hh((size_t)n), pv((size_t)n), tk((size_t)n), en((size_t)n), re((size_t)n);
-    vga_global_attributes(n, nodes.data(), depth.data(), dist.data(), maxl, nc.data(), md.data(), hh.data(), pv.data(),
-                          tk.data(), en.data(), re.data());
-    attributes.column(integ_dv_col) = hh;
-    if (!simple_version) {
-        attributes.column(count_col) = nc;
-        attributes.column(depth_col) = md;
-        attributes.column(integ_pv_col) = pv;
-        attributes.column(integ_tk_col) = tk;
-        attributes.column(entropy_col) = en;
-        attributes.column(rel_entropy_col) = re;
-    }
-    map.setDisplayedAttribute(integ_dv_col);
+    writeAttributes(map, m_radius, simple_version, nodes.data(), depth.data(), dist.data(), maxl);
     return true;
+}
+
+// vgavisuallocal.cpp:31-35, 84-96, 112
+void VGAVisualLocal::writeAttributes(PointMap &map, bool simple_version, const int64_t *cluster, const int32_t *k,
+                                     const int32_t *total, const float *control) {
+    if (simple_version) return;
+    AttributeTable &attributes = map.getAttributeTable();
+    const int64_t n = (int64_t)attributes.getNumRows();
+    const int cluster_col = attributes.insertOrResetColumn("Visual Clustering Coefficient");
+    const int control_col = attributes.insertOrResetColumn("Visual Control");
+    const int controllability_col = attributes.insertOrResetColumn("Visual Controllability");
+    std::vector<float> a((size_t)n), b((size_t)n), c((size_t)n);
+    vga_local_attributes(n, cluster, k, total, control, a.data(), b.data(), c.data());
+    for (int64_t v = 0; v < n; v++) {
+        attributes.setValue((size_t)v, cluster_col, a[(size_t)v]);
+        attributes.setValue((size_t)v, control_col, b[(size_t)v]);
+        attributes.setValue((size_t)v, controllability_col, c[(size_t)v]);
+    }
+    map.setDisplayedAttribute(cluster_col);
 }
 
 // vgavisuallocal.cpp:23-117
 bool VGAVisualLocal::run(Communicator *comm, PointMap &map, bool simple_version) {
     check_supported(map, m_gates_only, "VGAVisualLocal");
-    AttributeTable &attributes = map.getAttributeTable();
-    const int64_t n = (int64_t)attributes.getNumRows();
+    const int64_t n = (int64_t)map.getAttributeTable().getNumRows();
     if (comm) comm->CommPostMessage(Communicator::NUM_RECORDS, map.getFilledPointCount());
-    int cluster_col = -1, control_col = -1, controllability_col = -1;
-    if (!simple_version) {
-        cluster_col = attributes.insertOrResetColumn("Visual Clustering Coefficient");
-        control_col = attributes.insertOrResetColumn("Visual Control");
-        controllability_col = attributes.insertOrResetColumn("Visual Controllability");
-    }
     vga_ctx *ctx = map.context();
     std::vector<int64_t> cluster((size_t)n);
     std::vector<int32_t> k((size_t)n), total((size_t)n);
@@ -491,12 +635,37 @@ bool VGAVisualLocal::run(Communicator *comm, PointMap &map, bool simple_version)
     int rc = vga_local(ctx, map.graph(), 0, n, cluster.data(), k.data(), total.data(), control.data());
     if (rc == VGA_ERR_CANCELLED) throw Communicator::CancelledException();
     if (rc != VGA_OK) throw RuntimeException(std::string("VGAVisualLocal: ") + vga_last_error());
-    if (!simple_version) {
-        vga_local_attributes(n, cluster.data(), k.data(), total.data(), control.data(),
-                             attributes.column(cluster_col).data(), attributes.column(control_col).data(),
-                             attributes.column(controllability_col).data());
-        map.setDisplayedAttribute(cluster_col);
+    writeAttributes(map, simple_version, cluster.data(), k.data(), total.data(), control.data());
+    return true;
+}
+
+// vgavisualglobaldepth.cpp:27-28, 51-52, 71-73: every reached filled cell gets float(level); others keep -1
+void VGAVisualGlobalDepth::writeAttributes(PointMap &map, const int32_t *depth) {
+    AttributeTable &attributes = map.getAttributeTable();
+    const int col = attributes.insertOrResetColumn("Visual Step Depth");
+    const size_t n = attributes.getNumRows();
+    // the reference writes level by level; the statistics are sums of small integers (exact in double in any
+    // order), minimum and maximum
+    for (size_t v = 0; v < n; v++)
+        if (depth[v] >= 0) attributes.setValue(v, col, float(depth[v]));
+    map.setDisplayedAttribute(-2);
+    map.setDisplayedAttribute(col);
+}
+
+// vgavisualglobaldepth.cpp:23-75: BFS from the selection set
+bool VGAVisualGlobalDepth::run(Communicator *, PointMap &map, bool) {
+    check_supported(map, false, "VGAVisualGlobalDepth");
+    const std::vector<int> &keys = map.getAttributeTable().keys();
+    const int64_t n = (int64_t)keys.size();
+    std::vector<int64_t> sources;
+    for (const PixelRef &sel : map.getSelSet()) {
+        auto pos = std::lower_bound(keys.begin(), keys.end(), int(sel));
+        if (pos != keys.end() && *pos == int(sel)) sources.push_back((int64_t)(pos - keys.begin()));
     }
+    std::vector<int32_t> depth((size_t)n, -1);
+    int rc = vga_step_depth(map.context(), map.graph(), sources.data(), (int64_t)sources.size(), depth.data());
+    if (rc != VGA_OK) throw RuntimeException(std::string("VGAVisualGlobalDepth: ") + vga_last_error());
+    writeAttributes(map, depth.data());
     return true;
 }
 

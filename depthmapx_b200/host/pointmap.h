@@ -17,6 +17,7 @@
 #pragma once
 
 #include <cstdint>
+#include <iosfwd>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -50,41 +51,116 @@ struct PixelRef {
 };
 
 struct Point {
-    enum { EMPTY = 0x0001, FILLED = 0x0002, BLOCKED = 0x0004, CONTEXTFILLED = 0x0008, EDGE = 0x0020, MERGED = 0x0040 };
+    enum { EMPTY = 0x0001, FILLED = 0x0002, BLOCKED = 0x0004, CONTEXTFILLED = 0x0008, SELECTED = 0x0010, EDGE = 0x0020, MERGED = 0x0040 };
     int state = EMPTY;
     int misc = 0;
+    int block = 0;            // Point::m_block: unused by the reference but serialised (point.cpp:28-31)
     unsigned char grid_connections = 0;
+    PixelRef merge;           // Point::m_merge, (-1,-1) = not merged
+    Point2f location;         // Point::m_location = centre of the cell (pointdata.cpp:159)
     std::vector<Line> lines;  // wall segments touching the cell, clipped to it
     bool filled() const { return (state & FILLED) != 0; }
     bool blocked() const { return (state & BLOCKED) != 0; }
     bool edge() const { return (state & EDGE) != 0; }
+    bool contextfilled() const { return (state & CONTEXTFILLED) != 0; }
+    bool merged() const { return !(merge.x == -1 && merge.y == -1); }
     void set(int s, int undo) {
         state = s | (state & BLOCKED);
         misc = undo;
     }
 };
 
-// Column store; a row exists for every cell that had a Node made (x-major order).
+// Display parameters stored with every column and with the table (salalib/displayparams.h:3-11).
+struct DisplayParams {
+    float blue = 0.0f, red = 1.0f;
+    int colorscale = 0;
+};
+
+// Column store; a row exists for every cell that had a Node made (x-major order = AttributeKey order).
+// Keeps what the reference serialises per column (salalib/attributetable.cpp:91-124): running statistics
+// (min / max / total, updated by every setValue exactly as AttributeColumnImpl::updateStats :65-84 does),
+// hidden / locked flags, display parameters and formula; per row the layer key.
 class AttributeTable {
   public:
-    int insertOrResetColumn(const std::string &name);
-    int getColumnIndex(const std::string &name) const;  // -1 if absent
+    struct Column {
+        std::string name;
+        double min = -1.0, max = -1.0, total = -1.0;
+        bool hidden = false, locked = false;
+        DisplayParams display;
+        std::string formula;
+    };
+    AttributeTable();
+    int insertOrResetColumn(const std::string &name);        // attributetable.cpp:303-319
+    int insertOrResetLockedColumn(const std::string &name);  // :321-326
+    int getColumnIndex(const std::string &name) const;       // -1 if absent
     bool hasColumn(const std::string &name) const { return getColumnIndex(name) >= 0; }
-    size_t getNumColumns() const { return m_names.size(); }
-    const std::string &getColumnName(size_t i) const { return m_names[i]; }
+    size_t getNumColumns() const { return m_columns.size(); }
+    const std::string &getColumnName(size_t i) const { return m_columns[i].name; }
+    const Column &getColumn(size_t i) const { return m_columns[i]; }
+    int getColumnSortedIndex(int idx) const;                 // :479-485
     size_t getNumRows() const { return m_keys.size(); }
-    void setRows(const std::vector<int> &keys);
+    void setRows(const std::vector<int> &keys);  // addRow for every key (ascending), values -1, layer key 1
     void clear();
     const std::vector<int> &keys() const { return m_keys; }
-    std::vector<float> &column(int idx) { return m_cols[idx]; }
     const std::vector<float> &column(int idx) const { return m_cols[idx]; }
-    void setValue(size_t row, int col, float v) { m_cols[col][row] = v; }
+    void setValue(size_t row, int col, float v);  // AttributeRowImpl::setValue :153-166 (updates the statistics)
     float getValue(size_t row, int col) const { return m_cols[col][row]; }
+    // AttributeTable::read / write (attributetable.cpp:397-457) incl. the layer manager block
+    // (layermanagerimpl.cpp:90-149, kept as opaque bytes)
+    bool read(class ByteReader &in);
+    void write(std::ostream &out) const;
 
   private:
-    std::vector<std::string> m_names;
+    std::vector<Column> m_columns;
     std::vector<std::vector<float>> m_cols;
     std::vector<int> m_keys;
+    std::vector<int64_t> m_layer_keys;
+    DisplayParams m_display;
+    std::string m_layers;  // serialised LayerManagerImpl
+};
+
+// Bounds-checked cursor over a file image (all .graph integers are little-endian, structs are raw x86-64 images).
+class ByteReader {
+  public:
+    ByteReader(const char *data, size_t size) : m_data(data), m_size(size) {}
+    size_t pos() const { return m_pos; }
+    size_t size() const { return m_size; }
+    bool eof() const { return m_pos >= m_size; }
+    const char *at(size_t p) const { return m_data + p; }
+    void raw(void *dst, size_t n);
+    void skip(size_t n);
+    template <typename T> T get() {
+        T v;
+        raw(&v, sizeof(T));
+        return v;
+    }
+    std::string str();  // dXstring::readString: u32 length + bytes
+
+  private:
+    const char *m_data;
+    size_t m_size, m_pos = 0;
+};
+
+// Run-length encoded adjacency of every cell that has a Node (salalib/ngraph.h:31-149): 32 bins per node, each a
+// direction class, the stored node count, the far distance, the occlusion distance and its runs (PixelVec
+// start..end).  Filled by PointMap::read, or from the device rows after sparkGraph2 when the map is written.
+struct NodeStore {
+    struct Run {
+        PixelRef start, end;
+    };
+    struct Bin {
+        signed char dir = 0;  // PixelRef::NODIR / HORIZONTAL 1 / VERTICAL 2 / POSDIAGONAL 4 / NEGDIAGONAL 8
+        uint16_t count = 0;
+        float distance = 0.0f, occ_distance = 0.0f;
+        uint32_t first_run = 0, nruns = 0;
+    };
+    std::vector<int32_t> node_of_cell;  // [cells] node index or -1
+    std::vector<Bin> bins;              // [nodes*32]
+    std::vector<Run> runs;
+    std::vector<uint32_t> occl_off;     // [nodes*32+1] into occl (Node::m_occlusion_bins)
+    std::vector<PixelRef> occl;
+    size_t numNodes() const { return bins.size() / 32; }
+    void clear();
 };
 
 class PointMap {
@@ -131,7 +207,46 @@ class PointMap {
         std::vector<double> lines;
     };
     void flatten(Flat &out) const;
-    // adjacency handle on the device (valid after sparkGraph2 / adoptGraph)
+    // The PointMap section of a .graph file: the bytes PointMap::read / write handle
+    // (salalib/pointdata.cpp:1073-1188; Point::read / write salalib/point.cpp:25-73; Node / Bin / PixelVec
+    // run-length codec salalib/ngraph.cpp:195-220, 420-583; attribute table salalib/attributetable.cpp:91-124,
+    // 397-457).  read() restores grid geometry, cell states, grid connections, merge links, every attribute
+    // column and the run-length adjacency, so `-m VGA` on a loaded map needs no reference object; write()
+    // emits exactly the bytes the reference would write for the same map.
+    bool read(ByteReader &in);
+    void write(std::ostream &out);
+    // Run-length adjacency (the reference's Nodes).  After sparkGraph2 it is produced on demand from the device
+    // rows (the GPU graph is the master copy); after read() it is what the file held.
+    const NodeStore &nodes();
+    // Flat adjacency of the node store in Node::first/next order: rowptr [N+1] over filled cells in x-major
+    // order, packed PixelRef and bin id of every iterated pixel.
+    struct FlatRows {
+        std::vector<uint64_t> rowptr;
+        std::vector<int32_t> ref;
+        std::vector<uint8_t> bin;
+    };
+    void flattenNodes(FlatRows &out);
+    // Rebuild the node store from flat rows (any order inside a row; `accepted` = 0 marks the fill-in pixels of
+    // a diagonal first..last run, NULL = all accepted): the encoder used after a GPU build, Node::make /
+    // Bin::make (ngraph.cpp:27-58, 234-304).  far_bin_dists [N*32].
+    void encodeNodes(const uint64_t *rowptr, const int32_t *ref, const uint8_t *bin, const uint8_t *accepted,
+                     const float *far_bin_dists);
+    // make sure graph() is valid: uploads the loaded adjacency when there is one (needs the GPU)
+    void ensureGraph();
+    // x-major packed PixelRefs of the filled cells (= attribute row keys once the graph is made)
+    std::vector<int> filledKeys() const;
+    // Second half of sparkGraph2 (pointdata.cpp:1268-1341 minus the per-source work): attribute rows, the three
+    // columns, grid connections and flags from per-source results that libvga_b200 produced -- on this GPU
+    // (sparkGraph2 calls it) or on other ranks of a multi-GPU build (gathered by the caller).
+    void finishSparkGraph(bool boundarygraph, const int32_t *connectivity, const double *sum_d, const double *sum_d2,
+                          const uint8_t *grid_connections);
+    // first half: blockLines + boundary un-fill (pointdata.cpp:1250-1264)
+    void beginSparkGraph(bool boundarygraph);
+    // selection (pointdata.cpp:939-987, 905-937): filled cells inside r get Point::SELECTED and join the set
+    bool setCurSel(const Region &r, bool add = false);
+    bool clearSel();
+    const std::vector<PixelRef> &getSelSet() const { return m_selection_set; }  // x-major (std::set<PixelRef> order)
+    // adjacency handle on the device (valid after sparkGraph2 / adoptGraph / ensureGraph)
     vga_graph *graph() const { return m_graph; }
     vga_ctx *context();
     // attach an adjacency produced elsewhere (e.g. flattened from a loaded .graph)
@@ -158,6 +273,10 @@ class PointMap {
     int m_displayed_attribute = -2;
     AttributeTable m_attributes;
     vga_graph *m_graph = nullptr;
+    std::vector<PixelRef> m_selection_set;
+    bool m_has_selection = false;
+    NodeStore m_nodes;
+    bool m_nodes_valid = false;  // m_nodes describes the current graph
 };
 
 class IVGA {
@@ -175,6 +294,11 @@ class VGAVisualGlobal : public IVGA {
     std::string getAnalysisName() const override { return "Global Visibility Analysis"; }
     bool run(Communicator *comm, PointMap &map, bool simple_version) override;
     VGAVisualGlobal(double radius, bool gates_only) : m_radius(radius), m_gates_only(gates_only) {}
+    // column set-up + formula stage + row writes (vgavisualglobal.cpp:33-63, 131-193, 214) from the BFS integers
+    // of all N cells in x-major order -- computed by vga_global on this GPU (run() calls it) or gathered from the
+    // ranks of a multi-GPU run
+    static void writeAttributes(PointMap &map, double radius, bool simple_version, const int32_t *total_nodes,
+                                const int64_t *total_depth, const int32_t *dist, int32_t max_levels);
 };
 
 class VGAVisualLocal : public IVGA {
@@ -184,6 +308,18 @@ class VGAVisualLocal : public IVGA {
     std::string getAnalysisName() const override { return "Local Visibility Analysis"; }
     bool run(Communicator *comm, PointMap &map, bool simple_version) override;
     explicit VGAVisualLocal(bool gates_only) : m_gates_only(gates_only) {}
+    // vgavisuallocal.cpp:31-35, 84-96, 112 from the integers of vga_local
+    static void writeAttributes(PointMap &map, bool simple_version, const int64_t *cluster, const int32_t *k,
+                                const int32_t *total, const float *control);
+};
+
+// Visual step depth from the map's selection (salalib/vgamodules/vgavisualglobaldepth.cpp:23-75)
+class VGAVisualGlobalDepth : public IVGA {
+  public:
+    std::string getAnalysisName() const override { return "Global Visibility Depth"; }
+    bool run(Communicator *comm, PointMap &map, bool simple_version) override;
+    // column "Visual Step Depth" from the per-cell depths of vga_step_depth (-1 = not reached: value stays -1)
+    static void writeAttributes(PointMap &map, const int32_t *depth);
 };
 
 // process-wide GPU context (one process drives one GPU; device from VGA_DEVICE or LOCAL_RANK)

@@ -32,6 +32,46 @@ int dmxh_map_columns(void *map, char *buf, int buflen); /* '\n' separated, retur
 int dmxh_map_attr(void *map, const char *name, float *out /* one per filled cell, x-major */);
 int dmxh_map_grid_connections(void *map, uint8_t *out /* one per filled cell */);
 void *dmxh_map_graph(void *map); /* vga_graph* of include/vga_b200.h, owned by the map */
+int dmxh_map_state(void *map, uint16_t *state /* cols*rows, x-major */);
+
+/* Visual step depth (VGAVisualGlobalDepth::run, salalib/vgamodules/vgavisualglobaldepth.cpp:23-75) from the cells
+ * containing the given points (x,y pairs; PointMap::setCurSel(QtRegion(p,p), true), pointdata.cpp:939)  [GPU] */
+int dmxh_map_step_depth(void *map, const double *points, int npoints);
+int dmxh_map_select(void *map, const double *points, int npoints);
+int64_t dmxh_map_selection(void *map, int32_t *refs /* packed PixelRefs, NULL = count only */);
+
+/* Run-length adjacency (the reference's Nodes, salalib/ngraph.h:31-149) as flat rows in Node::first/next order:
+ * call with NULL arrays for the sizes.  For a map built on the GPU the rows come from the device. */
+int dmxh_map_flat_rows(void *map, int64_t *n, int64_t *entries, uint64_t *rowptr, int32_t *ref, uint8_t *bin);
+int dmxh_map_bins(void *map, uint16_t *bin_count /* N*32 */, float *bin_dist /* N*32 */);
+/* Node::make / Bin::make encoder (ngraph.cpp:27-58, 234-304) from flat rows; `accepted` may be NULL */
+int dmxh_map_encode_nodes(void *map, const uint64_t *rowptr, const int32_t *ref, const uint8_t *bin,
+                          const uint8_t *accepted, const float *far_bin_dists);
+
+/* Attribute stages on their own, fed with the integers libvga_b200 produced (on this GPU or gathered from the
+ * ranks of a multi-GPU run): sparkGraph2's host halves (pointdata.cpp:1250-1264, 1268-1341) and the column +
+ * formula stages of the three analyses. */
+int dmxh_map_begin_graph(void *map, int boundarygraph);
+int dmxh_map_finish_graph(void *map, int boundarygraph, const int32_t *connectivity, const double *sum_d,
+                          const double *sum_d2, const uint8_t *grid_connections);
+int dmxh_map_write_global(void *map, double radius, int simple_version, const int32_t *total_nodes,
+                          const int64_t *total_depth, const int32_t *dist, int32_t max_levels);
+int dmxh_map_write_local(void *map, int simple_version, const int64_t *cluster, const int32_t *k, const int32_t *total,
+                         const float *control);
+int dmxh_map_write_step_depth(void *map, const int32_t *depth);
+
+/* .graph container (MetaGraph::readFromStream / write, salalib/mgraph.cpp:2492-2763): the
+ * PointMap section is decoded / encoded here, the other sections are carried through verbatim. */
+void *dmxh_graph_open(const char *path); /* NULL on failure, see dmxh_last_error() */
+void dmxh_graph_close(void *file);
+int dmxh_graph_save(void *file, const char *path);
+int dmxh_graph_num_maps(void *file);
+int dmxh_graph_displayed_map(void *file);
+void *dmxh_graph_map(void *file, int i); /* owned by the file; usable with every dmxh_map_* call */
+int64_t dmxh_graph_walls(void *file, double *out /* 4 per segment, NULL = count only */);
+void *dmxh_graph_new_map(void *file, double spacing); /* MetaGraph::addNewPointMap + setGrid */
+int dmxh_graph_make_graph(void *file, int boundarygraph, double maxdist); /* MetaGraph::makeGraph  [GPU] */
+void dmxh_graph_made(void *file); /* state / view-class update of MetaGraph::makeGraph after dmxh_map_finish_graph */
 void dmxh_release_context(void);
 
 #ifdef __cplusplus

@@ -266,16 +266,31 @@ def rlib():
         L.dmxref_sample_makegraph.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p]
         L.dmxref_sample_global.restype = C.c_double
         L.dmxref_sample_global.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.dmxref_graph_open.restype = C.c_void_p
+        L.dmxref_graph_open.argtypes = [C.c_char_p]
+        L.dmxref_graph_save.argtypes = [C.c_void_p, C.c_char_p]
+        L.dmxref_graph_rewrite.argtypes = [C.c_char_p, C.c_char_p]
         _rlib = L
     return _rlib
+
+
+def ref_graph_rewrite(src, dst) -> bool:
+    """MetaGraph::readFromFile + MetaGraph::write by the reference, nothing in between."""
+    return bool(rlib().dmxref_graph_rewrite(os.fsencode(src), os.fsencode(dst)))
 
 
 class RefMap:
     """The reference's PointMap driven through oracle/ref_harness.cpp."""
 
-    def __init__(self, walls, spacing=1.0):
-        w = np.ascontiguousarray(walls, np.float64).reshape(-1, 4)
-        self.h = rlib().dmxref_create(_p(w), w.shape[0], spacing)
+    def __init__(self, walls=None, spacing=1.0, graph_file=None):
+        """walls + spacing: a new map; graph_file: the displayed point map of a .graph read by MetaGraph."""
+        if graph_file is not None:
+            self.h = rlib().dmxref_graph_open(os.fsencode(graph_file))
+            if not self.h:
+                raise RuntimeError(f"the reference could not read {graph_file}")
+        else:
+            w = np.ascontiguousarray(walls, np.float64).reshape(-1, 4)
+            self.h = rlib().dmxref_create(_p(w), w.shape[0], spacing)
         c, r = C.c_int(), C.c_int()
         s, bx, by = C.c_double(), C.c_double(), C.c_double()
         rlib().dmxref_grid(self.h, C.byref(c), C.byref(r), C.byref(s), C.byref(bx), C.byref(by))
@@ -288,6 +303,9 @@ class RefMap:
 
     def fill(self, x, y):
         return bool(rlib().dmxref_fill(self.h, x, y))
+
+    def save(self, path):
+        return bool(rlib().dmxref_graph_save(self.h, os.fsencode(path)))
 
     def block_lines(self):
         rlib().dmxref_block_lines(self.h)

@@ -76,7 +76,9 @@ namespace {
 struct Ref {
     std::vector<SpacePixelFile> drawing;
     QtRegion region;
-    std::unique_ptr<PointMap> map;
+    std::unique_ptr<PointMap> owned;
+    std::unique_ptr<MetaGraph> mgraph;  // set when the map came from a .graph file
+    PointMap *map = nullptr;
     std::string err;
 };
 
@@ -100,12 +102,42 @@ void *dmxref_create(const double *walls, int nwalls, double spacing) {
     }
     r->drawing.back().m_region = sm.getRegion();
     r->region = r->drawing.back().m_region;
-    r->map.reset(new PointMap(r->region, r->drawing, "map"));
+    r->owned.reset(new PointMap(r->region, r->drawing, "map"));
+    r->map = r->owned.get();
     r->map->setGrid(spacing, Point2f(0, 0));
     return r;
 }
 
 void dmxref_destroy(void *h) { delete static_cast<Ref *>(h); }
+
+// ---- .graph files through the reference's own MetaGraph (SURVEY.md §8 row f2 checks) --------------------
+
+// MetaGraph::readFromFile; the handle then works with every dmxref_* accessor on the displayed point map.
+void *dmxref_graph_open(const char *path) {
+    Ref *r = new Ref();
+    r->mgraph.reset(new MetaGraph());
+    if (r->mgraph->readFromFile(path) != MetaGraph::OK || r->mgraph->getPointMaps().empty()) {
+        delete r;
+        return nullptr;
+    }
+    r->map = &r->mgraph->getDisplayedPointMap();
+    return r;
+}
+
+// MetaGraph::write(filename, METAGRAPH_VERSION, false) of a handle from dmxref_graph_open
+int dmxref_graph_save(void *h, const char *path) {
+    Ref *r = static_cast<Ref *>(h);
+    if (!r->mgraph) return 0;
+    return r->mgraph->write(path, METAGRAPH_VERSION, false) == MetaGraph::OK ? 1 : 0;
+}
+
+// read + write with nothing in between (also for files without point maps): what the reference itself makes of
+// a file it loads, e.g. the SELECTED flags it drops and the displayed-attribute index it re-maps
+int dmxref_graph_rewrite(const char *in, const char *out) {
+    MetaGraph mg;
+    if (mg.readFromFile(in) != MetaGraph::OK) return 0;
+    return mg.write(out, METAGRAPH_VERSION, false) == MetaGraph::OK ? 1 : 0;
+}
 
 void dmxref_grid(void *h, int *cols, int *rows, double *spacing, double *blx, double *bly) {
     PointMap &m = *static_cast<Ref *>(h)->map;

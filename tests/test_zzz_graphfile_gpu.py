@@ -1,0 +1,97 @@
+"""GPU: the .graph pipelines of tests/test_graphfile.py with libvga_b200 doing the work (SURVEY §8 rows f1 + f2): the host
+layer reads the reference CLI's files, builds / uploads the graph on the B200, runs the analyses and writes .graph files
+that must be byte-identical to what the unmodified reference CLI wrote (tests/golden/graphfiles.npz).
+
+The codec and the attribute stages are pinned on CPU (tests/test_graphfile.py); what is new on the GPU side is
+PointMap::nodes() (Node encoding from the device rows), PointMap::ensureGraph() (upload of a loaded adjacency with bins)
+and the host-level VGAVisualGlobalDepth.  These have not run on a B200 yet (round 1 ran out of GPU minutes), so the
+module is xfail(strict=False) and sorted last: it cannot mask or break the parity suite, and the first GPU run of the
+next round validates it."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from depthmapx_b200 import capi
+
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="first GPU run pending (host-layer .graph pipeline)")]
+
+CASES = ["oblique12", "oblique10s07", "office16"]
+
+
+@pytest.fixture(scope="module")
+def files(tmp_path_factory):
+    d = tmp_path_factory.mktemp("graphs")
+    fx = golden("graphfiles")
+    for k in fx.files:
+        if not k.endswith("__args"):
+            open(os.path.join(d, k + ".graph"), "wb").write(fx[k].tobytes())
+    return str(d), {c: [str(x) for x in fx[c + "__args"]] for c in CASES}
+
+
+def data(path):
+    return open(path, "rb").read()
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("boundary", [False, True])
+def test_visprep_from_drawing(files, tmp_path, case, boundary):
+    """-m VISPREP -pg -pp -pm [-pb]: plan.graph -> grid, fill, makegraph on the GPU -> .graph"""
+    d, args = files
+    _spec, grid, seed, _sdp = args[case]
+    g = capi.GraphFile(os.path.join(d, f"{case}__plan.graph"))
+    m = g.new_map(float(grid))
+    assert m.fill(*[float(x) for x in seed.split(",")])
+    assert g.make_graph(boundary)
+    out = str(tmp_path / "o.graph")
+    g.save(out)
+    assert data(out) == data(os.path.join(d, f"{case}__prep_pb.graph" if boundary else f"{case}__prep.graph"))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_vga_on_loaded_graph(files, tmp_path, case):
+    """-m VGA -vm visibility -vg -vl -vr n, then -vg -vr 3 on the result, each from a file loaded by the host layer"""
+    d, _ = files
+    out = str(tmp_path / "o.graph")
+    g = capi.GraphFile(os.path.join(d, f"{case}__prep.graph"))
+    m = g.map()
+    assert m.vga_local() and m.vga_global(-1.0)
+    g.save(out)
+    assert data(out) == data(os.path.join(d, f"{case}__vga.graph"))
+    g = capi.GraphFile(os.path.join(d, f"{case}__vga.graph"))
+    assert g.map().vga_global(3.0)
+    g.save(out)
+    assert data(out) == data(os.path.join(d, f"{case}__vga3.graph"))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_step_depth_on_loaded_graph(files, tmp_path, case):
+    """-m STEPDEPTH -sdp x,y -sdt visual"""
+    d, args = files
+    sdp = [float(x) for x in args[case][3].split(",")]
+    g = capi.GraphFile(os.path.join(d, f"{case}__prep.graph"))
+    assert g.map().step_depth([sdp])
+    out = str(tmp_path / "o.graph")
+    g.save(out)
+    assert data(out) == data(os.path.join(d, f"{case}__sd.graph"))
+
+
+def test_loaded_and_built_graphs_agree(files):
+    """The adjacency uploaded from a file and the one built on the GPU from the same plan give the same integers."""
+    d, args = files
+    _spec, grid, seed, _sdp = args["office16"]
+    g1 = capi.GraphFile(os.path.join(d, "office16__plan.graph"))
+    m1 = g1.new_map(float(grid))
+    m1.fill(*[float(x) for x in seed.split(",")])
+    g1.make_graph(False)
+    g2 = capi.GraphFile(os.path.join(d, "office16__prep.graph"))
+    m2 = g2.map()
+    for a, b in zip(m1.flat_rows(), m2.flat_rows()):
+        assert np.array_equal(a, b)
+    for m in (m1, m2):
+        m.vga_local()
+        m.vga_global(-1.0)
+    assert m1.columns() == m2.columns()
+    for c in m1.columns():
+        assert np.array_equal(m1.attr(c), m2.attr(c)), c
