@@ -5,7 +5,7 @@
 // with the whole warp and stamps unreached targets with level+1 (all writers of a word write the same
 // value, so no atomics are needed).  Ghost columns (unfilled cells) are skipped as the reference skips
 // them (p.filled() test, :45).
-// Parity: tests/test_zz_stepdepth_gpu.py (reference golden column, oracle, vga_global histogram).
+// Parity: tests/test_stepdepth_gpu.py (reference golden column, oracle, vga_global histogram).
 #include <algorithm>
 
 #include "vga_dev.cuh"

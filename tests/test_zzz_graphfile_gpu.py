@@ -95,3 +95,20 @@ def test_loaded_and_built_graphs_agree(files):
     assert m1.columns() == m2.columns()
     for c in m1.columns():
         assert np.array_equal(m1.attr(c), m2.attr(c)), c
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_cli_stepdepth_shim(files, tmp_path, case):
+    """The real depthmapXcli with integration/vga_depth_gpu.cpp behind VGAVisualGlobalDepth::run:
+    -m STEPDEPTH -sdt visual must write the reference's bytes."""
+    import subprocess
+    from conftest import ROOT
+    gpu_cli = os.path.join(ROOT, "oracle", "_ref", "depthmapXcli_gpu")
+    if not os.path.exists(gpu_cli):
+        pytest.skip("integration binaries not built (make -C integration)")
+    d, args = files
+    out = str(tmp_path / "sd.graph")
+    r = subprocess.run([gpu_cli, "-m", "STEPDEPTH", "-f", os.path.join(d, f"{case}__prep.graph"), "-o", out, "-sdp", args[case][3],
+                        "-sdt", "visual"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert data(out) == data(os.path.join(d, f"{case}__sd.graph"))
