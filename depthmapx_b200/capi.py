@@ -46,8 +46,11 @@ HOST_SYMBOLS = [
     "dmxh_map_encode_nodes", "dmxh_map_begin_graph", "dmxh_map_finish_graph", "dmxh_map_write_global", "dmxh_map_write_local",
     "dmxh_map_write_step_depth", "dmxh_graph_open", "dmxh_graph_close", "dmxh_graph_save", "dmxh_graph_num_maps",
     "dmxh_graph_displayed_map", "dmxh_graph_map", "dmxh_graph_walls", "dmxh_graph_new_map", "dmxh_graph_make_graph",
-    "dmxh_graph_made",
+    "dmxh_graph_made", "dmxh_map_merge", "dmxh_map_contracted_rows", "dmxh_map_radius_correction",
 ]
+
+LEVEL_PREPARE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32))
+LEVEL_RUN_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int32))
 
 _abi = None
 _host = None
@@ -146,6 +149,9 @@ def host():
         H.dmxh_graph_new_map.argtypes = [vp, C.c_double]
         H.dmxh_graph_make_graph.argtypes = [vp, C.c_int, C.c_double]
         H.dmxh_graph_made.argtypes = [vp]
+        H.dmxh_map_merge.argtypes = [vp] + [C.c_double] * 4
+        H.dmxh_map_contracted_rows.argtypes = [vp] * 6
+        H.dmxh_map_radius_correction.argtypes = [vp, C.c_int, LEVEL_PREPARE_FN, LEVEL_RUN_FN, vp, vp, vp, vp, C.c_int32]
         _host = H
     return _host
 
@@ -489,6 +495,41 @@ class HostMap:
         f = None if far is None else np.ascontiguousarray(far, np.float32)
         return self._ret(host().dmxh_map_encode_nodes(self.h, _p(rowptr), _p(ref), _p(b), None if acc is None else _p(acc),
                                                       None if f is None else _p(f)))
+
+    def merge(self, ax, ay, bx, by):
+        """-m LINK -lnk ax,ay,bx,by"""
+        return self._ret(host().dmxh_map_merge(self.h, ax, ay, bx, by))
+
+    def contracted_rows(self):
+        """(rowptr, col, primary): the adjacency the BFS analyses run on when cells are merged."""
+        n, e = i64(), i64()
+        self._ret(host().dmxh_map_contracted_rows(self.h, C.addressof(n), C.addressof(e), None, None, None))
+        rowptr = np.zeros(n.value + 1, np.uint64)
+        col = np.zeros(max(e.value, 1), np.uint32)
+        primary = np.zeros(n.value, np.int32)
+        self._ret(host().dmxh_map_contracted_rows(self.h, None, None, _p(rowptr), _p(col), _p(primary)))
+        return rowptr, col[:e.value], primary
+
+    def radius_correction(self, radius, level_to, total_nodes, total_depth, dist):
+        """dmx::PointMap::radiusCorrection with a caller-supplied BFS: level_to(t_rowptr, t_col, seeds) -> int32 [n]
+        (level of every vertex in a BFS from `seeds` over the given CSR, -1 = unreached).  Arrays are updated in place."""
+        st = {}
+
+        def prep(_u, n, rp, col):
+            st["rp"] = np.ctypeslib.as_array(rp, (n + 1,)).copy()
+            st["col"] = np.ctypeslib.as_array(col, (max(int(st["rp"][-1]), 1),)).copy()[:int(st["rp"][-1])]
+            st["n"] = n
+
+        def run(_u, seeds, ns, level):
+            s = np.ctypeslib.as_array(seeds, (ns,)).copy() if ns else np.zeros(0, np.int64)
+            out = np.ctypeslib.as_array(level, (st["n"],))
+            out[:] = np.asarray(level_to(st["rp"], st["col"], s), np.int32)
+
+        a, b = LEVEL_PREPARE_FN(prep), LEVEL_RUN_FN(run)
+        assert total_nodes.dtype == np.int32 and total_depth.dtype == np.int64 and dist.dtype == np.int32
+        assert total_nodes.flags.c_contiguous and total_depth.flags.c_contiguous and dist.flags.c_contiguous
+        return self._ret(host().dmxh_map_radius_correction(self.h, int(radius), a, b, None, _p(total_nodes), _p(total_depth),
+                                                           _p(dist), dist.shape[1]))
 
     def begin_graph(self, boundary=False):
         return self._ret(host().dmxh_map_begin_graph(self.h, int(boundary)))

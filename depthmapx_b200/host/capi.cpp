@@ -228,6 +228,59 @@ int dmxh_map_write_step_depth(void *map, const int32_t *depth) {
     });
 }
 
+int dmxh_map_merge(void *map, double ax, double ay, double bx, double by) {
+    return guarded([&] {
+        dmx::PointMap *m = static_cast<dmx::PointMap *>(map);
+        // linkutils::pixelateMergeLines + mergePixelPairs (salalib/linkutils.cpp:20-98)
+        const dmx::PixelRef a = m->pixelate(dmx::Point2f(ax, ay), false), b = m->pixelate(dmx::Point2f(bx, by), false);
+        if (!m->includes(a) || !m->getPoint(a).filled() || !m->includes(b) || !m->getPoint(b).filled())
+            throw dmx::RuntimeException("Line ends not both on painted analysis space");
+        if (m->isPixelMerged(a) || m->isPixelMerged(b))
+            throw dmx::RuntimeException("Link pixel found that is already linked on the map");
+        return m->mergePixels(a, b);
+    });
+}
+
+int dmxh_map_contracted_rows(void *map, int64_t *n, int64_t *entries, uint64_t *rowptr, uint32_t *col, int32_t *primary) {
+    return guarded([&] {
+        dmx::PointMap::Contracted c;
+        static_cast<dmx::PointMap *>(map)->contractedRows(c);
+        if (n) *n = c.n;
+        if (entries) *entries = (int64_t)c.col.size();
+        if (rowptr) std::memcpy(rowptr, c.rowptr.data(), c.rowptr.size() * sizeof(uint64_t));
+        if (col && !c.col.empty()) std::memcpy(col, c.col.data(), c.col.size() * sizeof(uint32_t));
+        if (primary && !c.primary.empty()) std::memcpy(primary, c.primary.data(), c.primary.size() * sizeof(int32_t));
+        return true;
+    });
+}
+
+namespace {
+struct CallbackLevelTo : dmx::PointMap::LevelTo {
+    dmxh_level_prepare_fn prep;
+    dmxh_level_run_fn go;
+    void *user;
+    int64_t n = 0;
+    CallbackLevelTo(dmxh_level_prepare_fn p, dmxh_level_run_fn r, void *u) : prep(p), go(r), user(u) {}
+    void prepare(int64_t cells, const std::vector<uint64_t> &t_rowptr, const std::vector<uint32_t> &t_col) override {
+        n = cells;
+        prep(user, cells, t_rowptr.data(), t_col.data());
+    }
+    void run(const std::vector<int64_t> &seeds, std::vector<int32_t> &level) override {
+        level.assign((size_t)n, -1);
+        go(user, seeds.data(), (int64_t)seeds.size(), level.data());
+    }
+};
+}  // namespace
+
+int dmxh_map_radius_correction(void *map, int radius, dmxh_level_prepare_fn prepare, dmxh_level_run_fn run, void *user,
+                               int32_t *total_nodes, int64_t *total_depth, int32_t *dist, int32_t max_levels) {
+    return guarded([&] {
+        CallbackLevelTo cb(prepare, run, user);
+        static_cast<dmx::PointMap *>(map)->radiusCorrection(radius, cb, total_nodes, total_depth, dist, max_levels);
+        return true;
+    });
+}
+
 int dmxh_map_state(void *map, uint16_t *state) {
     dmx::PointMap *m = static_cast<dmx::PointMap *>(map);
     const size_t rows = m->getRows();

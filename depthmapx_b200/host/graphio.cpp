@@ -457,23 +457,30 @@ const NodeStore &PointMap::nodes() {
     return m_nodes;
 }
 
-// upload the adjacency of a loaded map (vga_graph_from_csr): filled cells get their x-major ordinal, unfilled
-// cells N + their x-major rank among the unfilled (the numbering vga_graph_build uses)
+// filled cells get their x-major ordinal, unfilled cells N + their x-major rank among the unfilled (the numbering
+// vga_graph_build uses)
+void PointMap::ordinals(std::vector<int32_t> &ord, int64_t &n, int64_t &ghosts) const {
+    const size_t cells = m_cols * m_rows;
+    ord.resize(cells);
+    n = 0;
+    ghosts = 0;
+    for (size_t c = 0; c < cells; c++)
+        if (m_points[c].filled()) ord[c] = (int32_t)n++;
+    for (size_t c = 0; c < cells; c++)
+        if (!m_points[c].filled()) ord[c] = (int32_t)(n + ghosts++);
+}
+
+// upload the adjacency of a loaded map (vga_graph_from_csr)
 void PointMap::ensureGraph() {
     if (m_graph || !m_nodes_valid || m_nodes.numNodes() == 0) return;
     const size_t cells = m_cols * m_rows;
-    std::vector<int32_t> ord(cells);
-    std::vector<int32_t> refs;
-    int64_t n = 0, ghosts = 0;
+    std::vector<int32_t> ord;
+    int64_t n, ghosts;
+    ordinals(ord, n, ghosts);
     for (size_t c = 0; c < cells; c++)
-        if (m_points[c].filled()) {
-            if (m_points[c].merged() || m_points[c].contextfilled())
-                throw RuntimeException("GPU path: merged / context-filled cells are not supported");
-            ord[c] = (int32_t)n++;
-        }
-    for (size_t c = 0; c < cells; c++)
-        if (!m_points[c].filled()) ord[c] = (int32_t)(n + ghosts++);
-    refs.resize((size_t)(n + ghosts));
+        if (m_points[c].filled() && m_points[c].contextfilled())
+            throw RuntimeException("GPU path: context-filled cells are not supported");
+    std::vector<int32_t> refs((size_t)(n + ghosts));
     for (size_t c = 0; c < cells; c++) refs[(size_t)ord[c]] = int(PixelRef((int)(c / m_rows), (int)(c % m_rows)));
     FlatRows rows;
     flattenNodes(rows);
@@ -488,6 +495,198 @@ void PointMap::ensureGraph() {
         throw RuntimeException(std::string("GPU path: ") + vga_last_error());
     vga_graph_set_cell_refs(g, refs.data(), (int64_t)refs.size());
     m_graph = g;  // m_nodes stays valid: it describes this graph
+}
+
+// ------------------------------------------------------------------------------------ merge links
+
+bool PointMap::hasMerges() const {
+    for (const Point &pt : m_points)
+        if (pt.filled() && pt.merged()) return true;
+    return false;
+}
+
+void PointMap::dropMergedGraph() {
+    if (m_merged_graph) vga_graph_free(m_merged_graph);
+    m_merged_graph = nullptr;
+    m_merged_primary.clear();
+}
+
+// pointdata.cpp:1643-1651
+bool PointMap::unmergePixel(PixelRef a) {
+    const PixelRef c = getPoint(a).merge;
+    if (includes(c)) {
+        getPoint(c).merge = PixelRef();
+        getPoint(c).state &= ~Point::MERGED;
+    }
+    getPoint(a).merge = PixelRef();
+    getPoint(a).state &= ~Point::MERGED;
+    dropMergedGraph();
+    return true;
+}
+
+// pointdata.cpp:1653-1685
+bool PointMap::mergePixels(PixelRef a, PixelRef b) {
+    if (int(a) == int(b) && getPoint(a).merged()) unmergePixel(a);
+    if (int(a) != int(b) && int(getPoint(a).merge) != int(b)) {
+        for (const PixelRef &x : {a, b})
+            if (getPoint(x).merged()) {
+                const PixelRef c = getPoint(x).merge;
+                getPoint(c).merge = PixelRef();
+                getPoint(c).state &= ~Point::MERGED;
+            }
+        getPoint(a).merge = b;
+        getPoint(a).state |= Point::MERGED;
+        getPoint(b).merge = a;
+        getPoint(b).state |= Point::MERGED;
+    }
+    dropMergedGraph();
+    return true;
+}
+
+void PointMap::contractedRows(Contracted &out) {
+    std::vector<int32_t> ord;
+    ordinals(ord, out.n, out.ghosts);
+    const int64_t n = out.n;
+    // the original rows as ordinals
+    std::vector<uint64_t> rowptr;
+    std::vector<uint32_t> col;
+    if (m_nodes_valid) {
+        FlatRows rows;
+        flattenNodes(rows);
+        rowptr.swap(rows.rowptr);
+        col.resize(rows.ref.size());
+        for (size_t e = 0; e < col.size(); e++) {
+            const PixelRef p(rows.ref[e]);
+            if (!includes(p)) throw RuntimeException("graph file: a node run leaves the grid");
+            col[e] = (uint32_t)ord[(size_t)p.x * m_rows + (size_t)p.y];
+        }
+    } else if (m_graph) {
+        rowptr.resize((size_t)n + 1);
+        col.resize((size_t)vga_graph_num_edges(m_graph));
+        if (vga_graph_csr(m_graph, rowptr.data(), col.data(), nullptr, nullptr) != VGA_OK)
+            throw RuntimeException(std::string("contractedRows: ") + vga_last_error());
+    } else {
+        throw RuntimeException("contractedRows: the map has no visibility graph");
+    }
+    // pairing: symmetric and exclusive, both cells filled
+    out.primary.resize((size_t)n);
+    std::vector<int32_t> partner((size_t)n, -1);
+    for (size_t c = 0; c < m_cols * m_rows; c++) {
+        const Point &pt = m_points[c];
+        if (!pt.filled()) continue;
+        const int32_t v = ord[c];
+        out.primary[(size_t)v] = v;
+        if (!pt.merged()) continue;
+        const PixelRef m = pt.merge;
+        if (!includes(m) || !getPoint(m).filled() || int(getPoint(m).merge) != int(PixelRef((int)(c / m_rows), (int)(c % m_rows))))
+            throw RuntimeException("GPU path: merge links must pair filled cells symmetrically");
+        partner[(size_t)v] = ord[(size_t)m.x * m_rows + (size_t)m.y];
+    }
+    for (int64_t v = 0; v < n; v++)
+        if (partner[(size_t)v] >= 0) out.primary[(size_t)v] = std::min<int32_t>((int32_t)v, partner[(size_t)v]);
+    // for every merged cell: the contracted vertices with an edge to the cell itself (radiusCorrection)
+    out.merged_cells.clear();
+    std::vector<int32_t> slot((size_t)n, -1);
+    for (int64_t v = 0; v < n; v++)
+        if (partner[(size_t)v] > v) {
+            slot[(size_t)v] = (int32_t)out.merged_cells.size();
+            out.merged_cells.push_back((int32_t)v);
+            slot[(size_t)partner[(size_t)v]] = (int32_t)out.merged_cells.size();
+            out.merged_cells.push_back(partner[(size_t)v]);
+        }
+    std::vector<std::vector<int32_t>> ins(out.merged_cells.size());
+    for (int64_t u = 0; u < n; u++)
+        for (uint64_t e = rowptr[(size_t)u]; e < rowptr[(size_t)u + 1]; e++)
+            if (col[e] < (uint32_t)n && slot[col[e]] >= 0) ins[(size_t)slot[col[e]]].push_back(out.primary[(size_t)u]);
+    out.in_ptr.assign(1, 0);
+    out.in_list.clear();
+    for (auto &l : ins) {
+        std::sort(l.begin(), l.end());
+        l.erase(std::unique(l.begin(), l.end()), l.end());
+        out.in_list.insert(out.in_list.end(), l.begin(), l.end());
+        out.in_ptr.push_back(out.in_list.size());
+    }
+    // contracted rows: redirect every column to its primary, union the pair's rows into the primary, sort + unique
+    out.rowptr.assign(1, 0);
+    out.col.clear();
+    out.col.reserve(col.size());
+    std::vector<uint32_t> row;
+    for (int64_t v = 0; v < n; v++) {
+        row.clear();
+        if (out.primary[(size_t)v] == v) {
+            const int64_t members[2] = {v, partner[(size_t)v]};
+            for (int64_t u : members) {
+                if (u < 0) continue;
+                for (uint64_t e = rowptr[(size_t)u]; e < rowptr[(size_t)u + 1]; e++) {
+                    const uint32_t c = col[e];
+                    row.push_back(c < (uint32_t)n ? (uint32_t)out.primary[c] : c);
+                }
+            }
+            std::sort(row.begin(), row.end());
+            row.erase(std::unique(row.begin(), row.end()), row.end());
+        }
+        out.col.insert(out.col.end(), row.begin(), row.end());
+        out.rowptr.push_back(out.col.size());
+    }
+}
+
+void PointMap::radiusCorrection(int radius, LevelTo &level_to, int32_t *total_nodes, int64_t *total_depth, int32_t *dist,
+                                int32_t max_levels) {
+    if (radius < 1 || radius >= max_levels) return;
+    Contracted c;
+    contractedRows(c);
+    const int64_t n = c.n;
+    // transpose of the contracted adjacency (cells only: ghosts are never expanded)
+    std::vector<uint64_t> t_rowptr((size_t)n + 1, 0);
+    for (uint32_t x : c.col)
+        if (x < (uint32_t)n) t_rowptr[(size_t)x + 1]++;
+    for (int64_t v = 0; v < n; v++) t_rowptr[(size_t)v + 1] += t_rowptr[(size_t)v];
+    std::vector<uint32_t> t_col(t_rowptr[(size_t)n]);
+    std::vector<uint64_t> fill(t_rowptr.begin(), t_rowptr.end() - 1);
+    for (int64_t u = 0; u < n; u++)
+        for (uint64_t e = c.rowptr[(size_t)u]; e < c.rowptr[(size_t)u + 1]; e++)
+            if (c.col[e] < (uint32_t)n) t_col[fill[c.col[e]]++] = (uint32_t)u;
+    level_to.prepare(n, t_rowptr, t_col);
+    std::vector<int32_t> la, lb;
+    for (size_t k = 0; k + 1 < c.merged_cells.size(); k += 2) {
+        std::vector<int64_t> sa(c.in_list.begin() + (ptrdiff_t)c.in_ptr[k], c.in_list.begin() + (ptrdiff_t)c.in_ptr[k + 1]);
+        std::vector<int64_t> sb(c.in_list.begin() + (ptrdiff_t)c.in_ptr[k + 1], c.in_list.begin() + (ptrdiff_t)c.in_ptr[k + 2]);
+        if (sa.empty() || sb.empty()) continue;
+        level_to.run(sa, la);
+        level_to.run(sb, lb);
+        // a source other than the pair itself reaches the cell at level R iff its nearest in-neighbour of that very
+        // cell is at level R-1
+        for (int64_t s = 0; s < n; s++)
+            if (s != c.merged_cells[k] && la[(size_t)s] == radius - 1 && lb[(size_t)s] == radius - 1) {
+                total_nodes[(size_t)s] += 1;
+                total_depth[(size_t)s] += radius;
+                dist[(size_t)s * (size_t)max_levels + (size_t)radius] += 1;
+            }
+    }
+}
+
+vga_graph *PointMap::analysisGraph(std::vector<int32_t> *primary) {
+    ensureGraph();
+    if (!hasMerges()) {
+        if (primary) primary->clear();
+        return m_graph;
+    }
+    if (!m_merged_graph) {
+        Contracted c;
+        contractedRows(c);
+        std::vector<int32_t> ord, refs((size_t)(c.n + c.ghosts));
+        int64_t n, ghosts;
+        ordinals(ord, n, ghosts);
+        for (size_t i = 0; i < ord.size(); i++) refs[(size_t)ord[i]] = int(PixelRef((int)(i / m_rows), (int)(i % m_rows)));
+        vga_graph *g = nullptr;
+        if (vga_graph_from_csr(context(), c.n, c.ghosts, c.rowptr.data(), c.col.data(), nullptr, &g) != VGA_OK)
+            throw RuntimeException(std::string("GPU path: ") + vga_last_error());
+        vga_graph_set_cell_refs(g, refs.data(), (int64_t)refs.size());
+        m_merged_graph = g;
+        m_merged_primary = c.primary;
+    }
+    if (primary) *primary = m_merged_primary;
+    return m_merged_graph;
 }
 
 // ------------------------------------------------------------------------------------ GraphFile

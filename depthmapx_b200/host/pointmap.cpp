@@ -120,6 +120,7 @@ PointMap::PointMap(const Region &parentRegion, const std::vector<Line> &walls, c
 
 PointMap::~PointMap() {
     if (m_graph) vga_graph_free(m_graph);
+    if (m_merged_graph) vga_graph_free(m_merged_graph);
 }
 
 vga_ctx *PointMap::context() { return shared_context(); }
@@ -127,6 +128,7 @@ vga_ctx *PointMap::context() { return shared_context(); }
 void PointMap::adoptGraph(vga_graph *g) {
     if (m_graph) vga_graph_free(m_graph);
     m_graph = g;
+    dropMergedGraph();
 }
 
 // Grid centres sit on multiples of the spacing ("origin at 0"): pointdata.cpp:122-171
@@ -361,9 +363,10 @@ void PointMap::flatten(Flat &out) const {
     out.line_off[cells] = n;
 }
 
-bool PointMap::unmake() {
+bool PointMap::unmake(bool removeLinks) {
     for (Point &pt : m_points)
         if (pt.filled()) {
+            if (removeLinks) pt.merge = PixelRef();
             pt.grid_connections = 0;
             pt.lines.clear();
             pt.state &= ~Point::BLOCKED;
@@ -525,10 +528,15 @@ bool PointMap::clearSel() {
 
 // ------------------------------------------------------------------------------------ analyses
 
-static void check_supported(PointMap &map, bool gates_only, const char *who) {
-    if (gates_only) throw RuntimeException(std::string(who) + ": gates_only is not supported by the GPU path");
+static void check_supported(PointMap &map, const char *who) {
     map.ensureGraph();
     if (!map.graph()) throw RuntimeException(std::string(who) + ": the map has no visibility graph (run sparkGraph2 first)");
+}
+
+// results of a merged pair's secondary cell = results of its primary (PointMap::contractedRows)
+template <typename T> static void copy_from_primary(const std::vector<int32_t> &primary, T *values, size_t width = 1) {
+    for (size_t v = 0; v < primary.size(); v++)
+        if ((size_t)primary[v] != v) std::copy(values + (size_t)primary[v] * width, values + ((size_t)primary[v] + 1) * width, values + v * width);
 }
 
 // vgavisualglobal.cpp:33-63 (columns), 131-193 (formulas, which value is written when), 214 (display)
@@ -548,6 +556,10 @@ void VGAVisualGlobal::writeAttributes(PointMap &map, double radius, bool simple_
         depth_col = attributes.insertOrResetColumn("Visual Mean Depth" + radius_text);
         count_col = attributes.insertOrResetColumn("Visual Node Count" + radius_text);
         rel_entropy_col = attributes.insertOrResetColumn("Visual Relativised Entropy" + radius_text);
+    }
+    if (!nodes) {  // gates_only: no cell is analysed, the columns stay at -1
+        map.setDisplayedAttribute(integ_dv_col);
+        return;
     }
     std::vector<float> nc((size_t)n), md((size_t)n), hh((size_t)n), pv((size_t)n), tk((size_t)n), en((size_t)n), re((size_t)n);
     vga_global_attributes(n, nodes, depth, dist, maxl, nc.data(), md.data(), hh.data(), pv.data(), tk.data(), en.data(),
@@ -575,11 +587,41 @@ void VGAVisualGlobal::writeAttributes(PointMap &map, double radius, bool simple_
     map.setDisplayedAttribute(integ_dv_col);
 }
 
+namespace {
+// level of every source TO a vertex set = vga_step_depth from the set over the transposed adjacency
+struct GpuLevelTo : PointMap::LevelTo {
+    vga_ctx *ctx;
+    vga_graph *graph = nullptr;
+    int64_t n = 0;
+    explicit GpuLevelTo(vga_ctx *c) : ctx(c) {}
+    ~GpuLevelTo() override {
+        if (graph) vga_graph_free(graph);
+    }
+    void prepare(int64_t cells, const std::vector<uint64_t> &t_rowptr, const std::vector<uint32_t> &t_col) override {
+        n = cells;
+        if (vga_graph_from_csr(ctx, n, 0, t_rowptr.data(), t_col.data(), nullptr, &graph) != VGA_OK)
+            throw RuntimeException(std::string("GPU path: ") + vga_last_error());
+    }
+    void run(const std::vector<int64_t> &seeds, std::vector<int32_t> &level) override {
+        level.assign((size_t)n, -1);
+        if (vga_step_depth(ctx, graph, seeds.data(), (int64_t)seeds.size(), level.data()) != VGA_OK)
+            throw RuntimeException(std::string("GPU path: ") + vga_last_error());
+    }
+};
+}  // namespace
+
 // vgavisualglobal.cpp:23-216
 bool VGAVisualGlobal::run(Communicator *comm, PointMap &map, bool simple_version) {
-    check_supported(map, m_gates_only, "VGAVisualGlobal");
+    check_supported(map, "VGAVisualGlobal");
     const int64_t n = (int64_t)map.getAttributeTable().getNumRows();
     if (comm) comm->CommPostMessage(Communicator::NUM_RECORDS, map.getFilledPointCount());
+    if (m_gates_only) {
+        // the reference skips every cell when gates_only is set (vgavisualglobal.cpp:75-78): columns only
+        writeAttributes(map, m_radius, simple_version, nullptr, nullptr, nullptr, 0);
+        return true;
+    }
+    std::vector<int32_t> primary;
+    vga_graph *graph = map.analysisGraph(&primary);
     vga_ctx *ctx = map.context();
     CbState cb{comm, std::chrono::steady_clock::now(), false};
     vga_ctx_set_callbacks(ctx, progress_cb, cancel_cb, &cb);
@@ -590,7 +632,7 @@ bool VGAVisualGlobal::run(Communicator *comm, PointMap &map, bool simple_version
     int rc;
     while (true) {
         dist.assign((size_t)n * maxl, 0);
-        rc = vga_global(ctx, map.graph(), (int)m_radius, 0, n, nodes.data(), depth.data(), dist.data(), maxl, &used);
+        rc = vga_global(ctx, graph, (int)m_radius, 0, n, nodes.data(), depth.data(), dist.data(), maxl, &used);
         if (rc == VGA_ERR_CAPACITY && used > maxl) {
             maxl = used;
             continue;
@@ -600,6 +642,15 @@ bool VGAVisualGlobal::run(Communicator *comm, PointMap &map, bool simple_version
     vga_ctx_set_callbacks(ctx, nullptr, nullptr, nullptr);
     if (rc == VGA_ERR_CANCELLED) throw Communicator::CancelledException();
     if (rc != VGA_OK) throw RuntimeException(std::string("VGAVisualGlobal: ") + vga_last_error());
+    if (!primary.empty()) {
+        if ((int)m_radius != -1) {
+            GpuLevelTo level_to(ctx);
+            map.radiusCorrection((int)m_radius, level_to, nodes.data(), depth.data(), dist.data(), maxl);
+        }
+        copy_from_primary(primary, nodes.data());
+        copy_from_primary(primary, depth.data());
+        copy_from_primary(primary, dist.data(), (size_t)maxl);
+    }
     writeAttributes(map, m_radius, simple_version, nodes.data(), depth.data(), dist.data(), maxl);
     return true;
 }
@@ -613,6 +664,10 @@ void VGAVisualLocal::writeAttributes(PointMap &map, bool simple_version, const i
     const int cluster_col = attributes.insertOrResetColumn("Visual Clustering Coefficient");
     const int control_col = attributes.insertOrResetColumn("Visual Control");
     const int controllability_col = attributes.insertOrResetColumn("Visual Controllability");
+    if (!cluster) {  // gates_only (vgavisuallocal.cpp:43-46)
+        map.setDisplayedAttribute(cluster_col);
+        return;
+    }
     std::vector<float> a((size_t)n), b((size_t)n), c((size_t)n);
     vga_local_attributes(n, cluster, k, total, control, a.data(), b.data(), c.data());
     for (int64_t v = 0; v < n; v++) {
@@ -625,9 +680,13 @@ void VGAVisualLocal::writeAttributes(PointMap &map, bool simple_version, const i
 
 // vgavisuallocal.cpp:23-117
 bool VGAVisualLocal::run(Communicator *comm, PointMap &map, bool simple_version) {
-    check_supported(map, m_gates_only, "VGAVisualLocal");
+    check_supported(map, "VGAVisualLocal");
     const int64_t n = (int64_t)map.getAttributeTable().getNumRows();
     if (comm) comm->CommPostMessage(Communicator::NUM_RECORDS, map.getFilledPointCount());
+    if (m_gates_only) {
+        writeAttributes(map, simple_version, nullptr, nullptr, nullptr, nullptr);
+        return true;
+    }
     vga_ctx *ctx = map.context();
     std::vector<int64_t> cluster((size_t)n);
     std::vector<int32_t> k((size_t)n), total((size_t)n);
@@ -654,17 +713,22 @@ void VGAVisualGlobalDepth::writeAttributes(PointMap &map, const int32_t *depth) 
 
 // vgavisualglobaldepth.cpp:23-75: BFS from the selection set
 bool VGAVisualGlobalDepth::run(Communicator *, PointMap &map, bool) {
-    check_supported(map, false, "VGAVisualGlobalDepth");
+    check_supported(map, "VGAVisualGlobalDepth");
     const std::vector<int> &keys = map.getAttributeTable().keys();
     const int64_t n = (int64_t)keys.size();
+    std::vector<int32_t> primary;
+    vga_graph *graph = map.analysisGraph(&primary);
     std::vector<int64_t> sources;
     for (const PixelRef &sel : map.getSelSet()) {
         auto pos = std::lower_bound(keys.begin(), keys.end(), int(sel));
-        if (pos != keys.end() && *pos == int(sel)) sources.push_back((int64_t)(pos - keys.begin()));
+        if (pos == keys.end() || *pos != int(sel)) continue;
+        const int64_t v = (int64_t)(pos - keys.begin());
+        sources.push_back(primary.empty() ? v : (int64_t)primary[(size_t)v]);
     }
     std::vector<int32_t> depth((size_t)n, -1);
-    int rc = vga_step_depth(map.context(), map.graph(), sources.data(), (int64_t)sources.size(), depth.data());
+    int rc = vga_step_depth(map.context(), graph, sources.data(), (int64_t)sources.size(), depth.data());
     if (rc != VGA_OK) throw RuntimeException(std::string("VGAVisualGlobalDepth: ") + vga_last_error());
+    copy_from_primary(primary, depth.data());
     writeAttributes(map, depth.data());
     return true;
 }

@@ -48,6 +48,22 @@ int dmxh_map_bins(void *map, uint16_t *bin_count /* N*32 */, float *bin_dist /* 
 int dmxh_map_encode_nodes(void *map, const uint64_t *rowptr, const int32_t *ref, const uint8_t *bin,
                           const uint8_t *accepted, const float *far_bin_dists);
 
+/* Merge links (`-m LINK -lnk x1,y1,x2,y2`: linkutils::pixelateMergeLines + mergePixelPairs, salalib/linkutils.cpp:20-98,
+ * PointMap::mergePixels pointdata.cpp:1653-1685).  The BFS analyses then run on the contracted adjacency (a merged pair
+ * is one vertex); dmxh_map_contracted_rows returns it: rowptr [N+1], col, primary [N] = the ordinal whose
+ * results each cell takes (NULL arrays = sizes only). */
+int dmxh_map_merge(void *map, double ax, double ay, double bx, double by);
+int dmxh_map_contracted_rows(void *map, int64_t *n, int64_t *entries, uint64_t *rowptr, uint32_t *col, int32_t *primary);
+
+/* Radius-limited global analysis of a merged map: adds the second count of every pair whose two cells are both first
+ * reached AT the radius (see dmx::PointMap::radiusCorrection) to the integers of the contracted BFS.  The BFS "level of
+ * every source to a vertex set" over the transposed contracted adjacency is supplied by the caller: the analysis classes
+ * use vga_step_depth on the GPU; the CPU tests plug in the checker. */
+typedef void (*dmxh_level_prepare_fn)(void *user, int64_t n, const uint64_t *t_rowptr, const uint32_t *t_col);
+typedef void (*dmxh_level_run_fn)(void *user, const int64_t *seeds, int64_t nseeds, int32_t *level /* [n], preset -1 */);
+int dmxh_map_radius_correction(void *map, int radius, dmxh_level_prepare_fn prepare, dmxh_level_run_fn run, void *user,
+                               int32_t *total_nodes, int64_t *total_depth, int32_t *dist, int32_t max_levels);
+
 /* Attribute stages on their own, fed with the integers libvga_b200 produced (on this GPU or gathered from the
  * ranks of a multi-GPU run): sparkGraph2's host halves (pointdata.cpp:1250-1264, 1268-1341) and the column +
  * formula stages of the three analyses. */

@@ -266,6 +266,7 @@ def rlib():
         L.dmxref_sample_makegraph.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p]
         L.dmxref_sample_global.restype = C.c_double
         L.dmxref_sample_global.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.dmxref_merge.argtypes = [C.c_void_p] + [C.c_double] * 4
         L.dmxref_graph_open.restype = C.c_void_p
         L.dmxref_graph_open.argtypes = [C.c_char_p]
         L.dmxref_graph_save.argtypes = [C.c_void_p, C.c_char_p]
@@ -306,6 +307,9 @@ class RefMap:
 
     def save(self, path):
         return bool(rlib().dmxref_graph_save(self.h, os.fsencode(path)))
+
+    def merge(self, ax, ay, bx, by):
+        return bool(rlib().dmxref_merge(self.h, ax, ay, bx, by))
 
     def block_lines(self):
         rlib().dmxref_block_lines(self.h)

@@ -148,6 +148,15 @@ void dmxref_grid(void *h, int *cols, int *rows, double *spacing, double *blx, do
     *bly = m.m_bottom_left.y;
 }
 
+// PointMap::mergePixels on the cells containing the two points (what -m LINK -lnk does, salalib/linkutils.cpp:20-98)
+int dmxref_merge(void *h, double ax, double ay, double bx, double by) {
+    PointMap &m = *static_cast<Ref *>(h)->map;
+    PixelRef a = m.pixelate(Point2f(ax, ay), false), b = m.pixelate(Point2f(bx, by), false);
+    if (!m.includes(a) || !m.includes(b) || !m.getPoint(a).filled() || !m.getPoint(b).filled()) return 0;
+    if (m.isPixelMerged(a) || m.isPixelMerged(b)) return 0;
+    return m.mergePixels(a, b) ? 1 : 0;
+}
+
 int dmxref_fill(void *h, double x, double y) {
     PointMap &m = *static_cast<Ref *>(h)->map;
     return m.makePoints(Point2f(x, y), 0) ? 1 : 0;

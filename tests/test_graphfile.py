@@ -15,7 +15,51 @@ from depthmapx_b200 import capi
 from oracle import pyoracle as po
 
 CASES = ["oblique12", "oblique10s07", "office16"]
-KINDS = ["plan", "fill", "prep", "prep_pb", "vga", "vga3", "sd"]
+KINDS = ["plan", "fill", "prep", "prep_pb", "vga", "vga3", "sd", "prep_l", "vga_l", "vga_l2", "sd_l"]
+
+
+def bfs_ints(rp, col, n, radius=-1, maxl=64):
+    """Plain level BFS from every vertex of a small CSR (checker for the contracted adjacency): Node Count, total depth
+    and level histogram with the reference's radius rule (cells at the radius are counted, not expanded)."""
+    tn = np.zeros(n, np.int32)
+    td = np.zeros(n, np.int64)
+    dist = np.zeros((n, maxl), np.int32)
+    for s in range(n):
+        lev = np.full(n, -1, np.int64)
+        lev[s] = 0
+        fr, level = [s], 0
+        while fr:
+            dist[s, level] = len(fr)
+            tn[s] += len(fr)
+            td[s] += level * len(fr)
+            nx = []
+            if radius == -1 or level < radius:
+                for u in fr:
+                    for c in col[rp[u]:rp[u + 1]]:
+                        if c < n and lev[c] < 0:
+                            lev[c] = level + 1
+                            nx.append(int(c))
+            fr, level = nx, level + 1
+    return tn, td, dist
+
+
+def level_from(rp, col, seeds):
+    """Level of every vertex in a BFS from the set `seeds` (-1 = unreached)."""
+    n = len(rp) - 1
+    lev = np.full(n, -1, np.int32)
+    fr = [int(s) for s in seeds]
+    for s in fr:
+        lev[s] = 0
+    level = 0
+    while fr:
+        nx = []
+        for u in fr:
+            for c in col[rp[u]:rp[u + 1]]:
+                if c < n and lev[c] < 0:
+                    lev[c] = level + 1
+                    nx.append(int(c))
+        fr, level = nx, level + 1
+    return lev
 
 
 @pytest.fixture(scope="module")
@@ -94,7 +138,7 @@ def test_node_encoder_reproduces_the_reference_runs(files, tmp_path, case):
     # the file: take the flags from the oracle built from the same plan (the stored map has no wall lists any more)
     _, args = files
     from depthmapx_b200 import plans
-    spec, grid, seed, _sdp = args[case]
+    spec, grid, seed, _sdp = args[case][:4]
     plan = plans.by_name(spec)
     hm = capi.HostMap(plan.walls, float(grid))
     assert hm.fill(*[float(x) for x in seed.split(",")])
@@ -118,7 +162,7 @@ def test_pipeline_from_the_drawing_writes_the_reference_bytes(files, tmp_path, c
     """plan.graph -> new map, grid, fill -> makegraph halves + node encoder -> local + global (n, then 3) -> step depth:
     every saved file byte-identical to what the reference CLI wrote for the same commands."""
     d, args = files
-    spec, grid, seed, sdp = args[case]
+    spec, grid, seed, sdp = args[case][:4]
     g = capi.GraphFile(os.path.join(d, f"{case}__plan.graph"))
     assert g.num_maps == 0 and len(g.walls()) > 0
     m = g.new_map(float(grid))
@@ -158,6 +202,70 @@ def test_pipeline_from_the_drawing_writes_the_reference_bytes(files, tmp_path, c
     m2.write_step_depth(og.step_depth(src))
     g2.save(out)
     assert data(out) == data(os.path.join(d, f"{case}__sd.graph"))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_merge_links_write_the_reference_bytes(files, tmp_path, case):
+    """-m LINK, then VGA global (radius n and 2) + local and STEPDEPTH on the linked map.  The BFS analyses
+    run on the contracted adjacency (a merged pair is one vertex), radius-limited runs add the at-the-radius correction;
+    every file byte-identical to the reference CLI's."""
+    d, args = files
+    out = str(tmp_path / "o.graph")
+    links = [[float(x) for x in l.split(",")] for l in args[case][4:]]
+    g = capi.GraphFile(os.path.join(d, f"{case}__prep.graph"))
+    m = g.map()
+    for l in links:
+        assert m.merge(*l)
+    with pytest.raises(RuntimeError):
+        m.merge(*links[0])  # already linked
+    g.save(out)
+    assert data(out) == data(os.path.join(d, f"{case}__prep_l.graph"))
+    n = m.n
+    rp, col, primary = m.contracted_rows()
+    assert int((primary != np.arange(n)).sum()) == len(links)
+    rp, col = rp.astype(np.int64), col.astype(np.int64)
+    # local is computed on the original adjacency (merges are ignored there): integers from the oracle of the same plan
+    from depthmapx_b200 import plans
+    spec, grid, seed = args[case][:3]
+    hm = capi.HostMap(plans.by_name(spec).walls, float(grid))
+    assert hm.fill(*[float(x) for x in seed.split(",")])
+    hm.begin_graph(False)
+    og = oracle_of(hm)
+    m.write_local(False, *og.local_ints())
+    tn, td, dist = bfs_ints(rp, col, n)
+    assert set(np.unique(tn[primary])) == {n - len(links)}  # every pair counts once
+    m.write_global(-1.0, False, tn[primary], td[primary], dist[primary])
+    g.save(out)
+    assert data(out) == data(os.path.join(d, f"{case}__vga_l.graph"))
+    # radius 2 on the linked map
+    g = capi.GraphFile(os.path.join(d, f"{case}__prep_l.graph"))
+    m = g.map()
+    tn, td, dist = bfs_ints(rp, col, n, 2)
+    m.radius_correction(2, level_from, tn, td, dist)
+    m.write_global(2.0, False, tn[primary], td[primary], dist[primary])
+    g.save(out)
+    assert data(out) == data(os.path.join(d, f"{case}__vga_l2.graph"))
+    # step depth on the linked map
+    g = capi.GraphFile(os.path.join(d, f"{case}__prep_l.graph"))
+    m = g.map()
+    m.select([[float(x) for x in args[case][3].split(",")]])
+    src = [int(primary[int(np.searchsorted(og.cell_refs(), s))]) for s in m.selection()]
+    m.write_step_depth(level_from(rp, col, src)[primary])
+    g.save(out)
+    assert data(out) == data(os.path.join(d, f"{case}__sd_l.graph"))
+
+
+def test_gates_only_writes_columns_only(files):
+    """gates_only makes the reference skip every cell (vgavisualglobal.cpp:75-78, vgavisuallocal.cpp:43-46)."""
+    d, _ = files
+    m = capi.GraphFile(os.path.join(d, "oblique12__prep.graph")).map()
+    from depthmapx_b200.capi import host
+    import ctypes as C
+    assert host().dmxh_map_write_global(m.h, -1.0, 0, None, None, None, 0) == 1
+    assert host().dmxh_map_write_local(m.h, 0, None, None, None, None) == 1
+    assert len(m.columns()) == 13
+    for c in m.columns()[3:]:
+        assert (m.attr(c) == -1).all()
 
 
 def test_simple_version_and_radius_columns(files):
@@ -214,8 +322,50 @@ def test_rewrite_equals_the_references_rewrite(files, tmp_path, case, kind):
 
 
 @pytest.mark.ref
+@pytest.mark.parametrize("case,seed", [("office16", 1), ("oblique12", 2), ("oblique10s07", 3)])
+def test_random_merge_links_against_the_reference(files, case, seed):
+    """Random link pairs and radii: the reference's VGAVisualGlobal::run on its own merged map against the contracted
+    adjacency + at-the-radius correction of the host layer."""
+    if not po.have_ref():
+        pytest.skip("compiled reference not present")
+    d, _ = files
+    src = os.path.join(d, f"{case}__prep.graph")
+    rng = np.random.default_rng(seed)
+    corrected = 0
+    for trial in range(16):
+        m = capi.GraphFile(src).map()
+        r = po.RefMap(graph_file=src)
+        n = m.n
+        st = m.state().reshape(m.cols, m.rows)
+        filled = np.argwhere((st & 2) != 0)
+        npairs, done = int(rng.integers(1, 5)), 0
+        while done < npairs:
+            a, b = filled[rng.integers(len(filled))], filled[rng.integers(len(filled))]
+            if (a == b).all():
+                continue
+            pa = (m.bl_x + a[0] * m.spacing, m.bl_y + a[1] * m.spacing)
+            pb = (m.bl_x + b[0] * m.spacing, m.bl_y + b[1] * m.spacing)
+            if r.merge(*pa, *pb):
+                assert m.merge(*pa, *pb)
+                done += 1
+        radius = int(rng.choice([-1, 1, 1, 2, 3]))
+        r.vga_global(float(radius))
+        rp, col, primary = m.contracted_rows()
+        tn, td, dist = bfs_ints(rp.astype(np.int64), col.astype(np.int64), n, radius)
+        if radius != -1:
+            before = tn.copy()
+            m.radius_correction(radius, level_from, tn, td, dist)
+            corrected += int((tn != before).sum())
+        m.write_global(float(radius), False, tn[primary], td[primary], dist[primary])
+        assert m.columns() == r.columns()
+        for c in m.columns():
+            assert np.array_equal(m.attr(c), r.attr(c)), (trial, radius, c)
+    assert corrected > 0 or case != "office16"  # the correction is exercised
+
+
+@pytest.mark.ref
 @pytest.mark.parametrize("case", CASES)
-@pytest.mark.parametrize("kind", ["prep", "prep_pb", "vga3", "sd"])
+@pytest.mark.parametrize("kind", ["prep", "prep_pb", "vga3", "sd", "vga_l2"])
 def test_loaded_map_equals_the_references_view(files, case, kind):
     if not po.have_ref():
         pytest.skip("compiled reference not present")

@@ -39,7 +39,7 @@ def data(path):
 def test_visprep_from_drawing(files, tmp_path, case, boundary):
     """-m VISPREP -pg -pp -pm [-pb]: plan.graph -> grid, fill, makegraph on the GPU -> .graph"""
     d, args = files
-    _spec, grid, seed, _sdp = args[case]
+    _spec, grid, seed, _sdp = args[case][:4]
     g = capi.GraphFile(os.path.join(d, f"{case}__plan.graph"))
     m = g.new_map(float(grid))
     assert m.fill(*[float(x) for x in seed.split(",")])
@@ -77,10 +77,30 @@ def test_step_depth_on_loaded_graph(files, tmp_path, case):
     assert data(out) == data(os.path.join(d, f"{case}__sd.graph"))
 
 
+@pytest.mark.parametrize("case", CASES)
+def test_merge_links_on_the_gpu(files, tmp_path, case):
+    """VGA global (radius n and 2) + local and step depth on a map with merge links."""
+    d, args = files
+    out = str(tmp_path / "o.graph")
+    g = capi.GraphFile(os.path.join(d, f"{case}__prep_l.graph"))
+    m = g.map()
+    assert m.vga_local() and m.vga_global(-1.0)
+    g.save(out)
+    assert data(out) == data(os.path.join(d, f"{case}__vga_l.graph"))
+    g = capi.GraphFile(os.path.join(d, f"{case}__prep_l.graph"))
+    assert g.map().vga_global(2.0)
+    g.save(out)
+    assert data(out) == data(os.path.join(d, f"{case}__vga_l2.graph"))
+    g = capi.GraphFile(os.path.join(d, f"{case}__prep_l.graph"))
+    assert g.map().step_depth([[float(x) for x in args[case][3].split(",")]])
+    g.save(out)
+    assert data(out) == data(os.path.join(d, f"{case}__sd_l.graph"))
+
+
 def test_loaded_and_built_graphs_agree(files):
     """The adjacency uploaded from a file and the one built on the GPU from the same plan give the same integers."""
     d, args = files
-    _spec, grid, seed, _sdp = args["office16"]
+    _spec, grid, seed, _sdp = args["office16"][:4]
     g1 = capi.GraphFile(os.path.join(d, "office16__plan.graph"))
     m1 = g1.new_map(float(grid))
     m1.fill(*[float(x) for x in seed.split(",")])
