@@ -37,6 +37,7 @@
 #include <cstdlib>
 #include <numeric>
 
+#include "pyramid.cuh"
 #include "vga_dev.cuh"
 
 namespace vga {
@@ -45,6 +46,7 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int TPB = 256;
+constexpr int PYR_LEVELS_DEV = 28;  // pyramid levels passed to the kernels (n < 2^26 vertices, cabi.cu limit)
 
 typedef unsigned long long u64;
 
@@ -63,6 +65,15 @@ struct BfsDev {
     const uint8_t *lvl_in;           // [groups][n] coarse lower-bound level, or nullptr
     uint8_t *lvl_out;                // [coarse batches*64][n] written by the coarse pass, or nullptr
     int group;                       // batches per coarse group
+    // pyramid pull (bfs_pull = 1), nullptr / 0 otherwise
+    u64 *pyr;                        // [batches][pyr_total][W]: OR-pyramid levels >= 1 of the frontier
+    int64_t pyr_total;               // nodes per batch
+    const uint64_t *t_runptr;        // [n+1]
+    const uint2 *t_runs;             // (first ordinal, length) runs of the sorted in-rows
+    const uint64_t *t_costptr;       // [n+1] prefix sums of the pyramid loads of a full in-row scan
+    int pyr_levels;
+    int64_t pyr_off[PYR_LEVELS_DEV];
+    int64_t pyr_cnt[PYR_LEVELS_DEV];
 };
 
 template <int W> __device__ __forceinline__ void ldw(const u64 *p, u64 (&o)[W]) {
@@ -251,6 +262,114 @@ template <int W> __global__ void __launch_bounds__(TPB) k_pull(BfsDev d, int lev
     }
 }
 
+// ---- pyramid pull (bfs_pull = 1, see pyramid.cuh) -----------------------------------------------------------
+
+// Three pyramid levels per launch for every batch whose next step is a pull: level k (the frontier for k = 0) ->
+// levels k+1 .. k+3.  One work item per aligned group of 8 level-k nodes.
+template <int W> __global__ void __launch_bounds__(TPB) k_pyr_build(BfsDev d, int k) {
+    const int b = blockIdx.y;
+    if (!d.active[b] || d.mode[b] != 1) return;
+    u64 *pyr = d.pyr + (int64_t)b * d.pyr_total * W;
+    const u64 *src = k == 0 ? d.frontier + (int64_t)b * d.n * W : pyr + d.pyr_off[k] * W;
+    u64 *d1 = k + 1 < d.pyr_levels ? pyr + d.pyr_off[k + 1] * W : nullptr;
+    u64 *d2 = k + 2 < d.pyr_levels ? pyr + d.pyr_off[k + 2] * W : nullptr;
+    u64 *d3 = k + 3 < d.pyr_levels ? pyr + d.pyr_off[k + 3] * W : nullptr;
+    const int64_t c0 = d.pyr_cnt[k];
+    const int64_t c1 = d1 ? d.pyr_cnt[k + 1] : 0, c2 = d2 ? d.pyr_cnt[k + 2] : 0, c3 = d3 ? d.pyr_cnt[k + 3] : 0;
+    const int64_t groups = (c0 + 7) / 8;
+    for (int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x; t < groups; t += (int64_t)gridDim.x * TPB)
+        pyr_build_group<W>(src, c0, d1, c1, d2, c2, d3, c3, t);
+}
+
+// bottom-up step over run-length in-rows: candidates as in k_pull (4 groups of 8 lanes per warp, one vertex per
+// group); every lane of a group takes one run of the in-row per round and answers it with a range-OR query over the
+// pyramid (at most 2 nodes per level), the group ORs its 8 answers and leaves the row once the missing bits are found.
+template <int W> __global__ void __launch_bounds__(TPB) k_pull_pyr(BfsDev d, int level) {
+    const int b = blockIdx.y;
+    if (!d.active[b] || d.mode[b] != 1) return;
+    const int lane = threadIdx.x & 31;
+    const u64 *fr = d.frontier + (int64_t)b * d.n * W;
+    const u64 *vis = d.visited + (int64_t)b * d.n * W;
+    const u64 *pyr = d.pyr + (int64_t)b * d.pyr_total * W;
+    u64 *nx = d.next + (int64_t)b * d.n * W;
+    const uint8_t *lvl = d.lvl_in ? d.lvl_in + (int64_t)(b / d.group) * d.n : nullptr;
+    u64 valid[W];
+#pragma unroll
+    for (int j = 0; j < W; j++) valid[j] = d.valid[(int64_t)b * W + j];
+    for (int64_t base = (int64_t)blockIdx.x * TPB; base < d.n; base += (int64_t)gridDim.x * TPB) {
+        int64_t w = base + threadIdx.x;
+        u64 need[W];
+#pragma unroll
+        for (int j = 0; j < W; j++) need[j] = 0ULL;
+        u64 anyneed = 0ULL;
+        if (w < d.n && !(lvl && (int)lvl[w] > level + 1)) {
+            u64 vv[W];
+            ldw<W>(vis + w * W, vv);
+#pragma unroll
+            for (int j = 0; j < W; j++) {
+                need[j] = valid[j] & ~vv[j];
+                anyneed |= need[j];
+            }
+        }
+        uint64_t my0 = 0, my1 = 0;
+        if (anyneed != 0ULL) {
+            my0 = d.t_runptr[w];
+            my1 = d.t_runptr[w + 1];
+        }
+        const unsigned m = __ballot_sync(FULL, anyneed != 0ULL);
+        const int ncand = __popc(m);
+        const int grp = lane >> 3, gl = lane & 7;
+        const unsigned gmask = 0xffu << (grp * 8);
+        for (int r = 0; r * 4 < ncand; r++) {
+            const int k = r * 4 + grp;
+            const bool has = k < ncand;
+            const int src_lane = has ? (int)__fns(m, 0, k + 1) : 0;
+            u64 nd[W];
+#pragma unroll
+            for (int j = 0; j < W; j++) nd[j] = __shfl_sync(FULL, need[j], src_lane);
+            const uint64_t e0 = __shfl_sync(FULL, my0, src_lane), e1 = __shfl_sync(FULL, my1, src_lane);
+            if (has) {
+                u64 acc[W];
+#pragma unroll
+                for (int j = 0; j < W; j++) acc[j] = 0ULL;
+                for (uint64_t e = e0; e < e1; e += 8) {
+                    u64 g[W];
+#pragma unroll
+                    for (int j = 0; j < W; j++) g[j] = 0ULL;
+                    if (e + gl < e1) {
+                        const uint2 run = d.t_runs[e + gl];
+                        pyr_decompose(run.x, run.y, [&](int kk, uint32_t i) {
+                            const u64 *p = kk == 0 ? fr + (int64_t)i * W : pyr + (d.pyr_off[kk] + (int64_t)i) * W;
+                            u64 t[W];
+                            ldw<W>(p, t);
+#pragma unroll
+                            for (int j = 0; j < W; j++) g[j] |= t[j];
+                        });
+                    }
+                    bool done = true;
+#pragma unroll
+                    for (int j = 0; j < W; j++) {
+                        unsigned lo = __reduce_or_sync(gmask, (unsigned)g[j]);
+                        unsigned hi = __reduce_or_sync(gmask, (unsigned)(g[j] >> 32));
+                        acc[j] |= ((u64)hi << 32) | lo;
+                        done = done && ((acc[j] & nd[j]) == nd[j]);
+                    }
+                    if (done) break;
+                }
+                if (gl == 0) {
+                    const int64_t ww = (base + (threadIdx.x & ~31)) + src_lane;
+#pragma unroll
+                    for (int j = 0; j < W; j++) {
+                        u64 nw = acc[j] & nd[j];
+                        if (nw) nx[ww * W + j] = nw;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // fold next into visited/frontier, count new vertices per source, gather direction statistics;
 // `level_next` = level of the vertices being added
 template <int W>
@@ -311,9 +430,9 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[bat
                 }
             }
             stw<W>(fr + v * W, nw);
-            // in-edges the next pull step would have to consider
-            if (d.t_rowptr && anyneed != 0ULL && (!lvl || (int)lvl[v] <= level_next + 1))
-                u_edges += d.t_rowptr[v + 1] - d.t_rowptr[v];
+            // in-edges (or, for the pyramid pull, pyramid loads) the next pull step would have to consider
+            const uint64_t *cost = d.t_costptr ? d.t_costptr : d.t_rowptr;
+            if (cost && anyneed != 0ULL && (!lvl || (int)lvl[v] <= level_next + 1)) u_edges += cost[v + 1] - cost[v];
         }
 #pragma unroll
         for (int j = 0; j < W; j++) {
@@ -432,6 +551,53 @@ __global__ void k_neighbour_bits(int64_t n, const uint64_t *rowptr, const uint32
     gc[v] = out;
 }
 
+// ---- run-length in-rows (bfs_pull = 1): one warp per vertex over its SORTED in-row ---------------------------
+// a run starts at entry e iff it is the first of the row or its ordinal does not continue the previous one
+__global__ void k_count_runs(const uint64_t *t_rowptr, const uint32_t *t_col, int64_t n, u64 *count) {
+    const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (v >= n) return;
+    const uint64_t e0 = t_rowptr[v], e1 = t_rowptr[v + 1];
+    unsigned c = 0;
+    for (uint64_t e = e0 + lane; e < e1; e += 32) c += (e == e0 || t_col[e] != t_col[e - 1] + 1u) ? 1u : 0u;
+    c = __reduce_add_sync(FULL, c);
+    if (lane == 0) count[v] = c;
+}
+// first_off[r] = offset (within its row) of the entry that starts run r
+__global__ void k_mark_runs(const uint64_t *t_rowptr, const uint32_t *t_col, int64_t n, const uint64_t *runptr, uint32_t *first_off) {
+    const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (v >= n) return;
+    const uint64_t e0 = t_rowptr[v], e1 = t_rowptr[v + 1];
+    uint64_t out = runptr[v];
+    for (uint64_t eb = e0; eb < e1; eb += 32) {
+        const uint64_t e = eb + lane;
+        const bool start = e < e1 && (e == e0 || t_col[e] != t_col[e - 1] + 1u);
+        const unsigned mask = __ballot_sync(FULL, start);
+        if (start) first_off[out + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)(e - e0);
+        out += __popc(mask);
+    }
+}
+// runs[r] = (first ordinal, length); cost[v] = pyramid loads of a full scan of the in-row of v
+__global__ void k_emit_runs(const uint64_t *t_rowptr, const uint32_t *t_col, int64_t n, const uint64_t *runptr,
+                            const uint32_t *first_off, uint2 *runs, u64 *cost) {
+    const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (v >= n) return;
+    const uint64_t e0 = t_rowptr[v], e1 = t_rowptr[v + 1];
+    const uint64_t r0 = runptr[v], r1 = runptr[v + 1];
+    unsigned c = 0;
+    for (uint64_t r = r0 + lane; r < r1; r += 32) {
+        const uint32_t off = first_off[r];
+        const uint32_t nxt = r + 1 < r1 ? first_off[r + 1] : (uint32_t)(e1 - e0);
+        const uint2 run = make_uint2(t_col[e0 + off], nxt - off);
+        runs[r] = run;
+        c += (unsigned)pyr_cost(run.x, run.y);
+    }
+    c = __reduce_add_sync(FULL, c);
+    if (lane == 0) cost[v] = c;
+}
+
 inline unsigned blocks_for(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 inline uint32_t morton2(uint32_t x, uint32_t y) {
@@ -460,7 +626,18 @@ int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, De
         tm.launches++;
         tm.main_launches++;
         if (bfs_mode != 0 && level > 0) {
-            k_pull<W><<<grid, TPB, 0, st>>>(d, level);
+            if (d.pyr) {
+                for (int k = 0; k + 1 < d.pyr_levels; k += 3) {
+                    const int64_t groups = (d.pyr_cnt[k] + 7) / 8;
+                    dim3 pgrid((unsigned)std::min<int64_t>((groups + TPB - 1) / TPB, 4096), (unsigned)nb);
+                    k_pyr_build<W><<<pgrid, TPB, 0, st>>>(d, k);
+                    tm.launches++;
+                    tm.main_launches++;
+                }
+                k_pull_pyr<W><<<grid, TPB, 0, st>>>(d, level);
+            } else {
+                k_pull<W><<<grid, TPB, 0, st>>>(d, level);
+            }
             tm.launches++;
             tm.main_launches++;
         }
@@ -591,6 +768,9 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int6
     const double w0 = wall();
     kt.start();
     if (bfs_mode != 0) VGA_TRY(ensure_transpose(ctx, g));
+    PyrLayout pl = pyr_layout(n);
+    const bool pyr_pull = bfs_mode != 0 && ctx->opt.bfs_pull == 1 && pl.levels <= PYR_LEVELS_DEV && n > 1;
+    if (pyr_pull) VGA_TRY(ensure_runs(ctx, g));
     kt.stop();
     const double w1 = wall();
 
@@ -611,7 +791,7 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int6
     VGA_CUDA(cudaMemGetInfo(&free_b, &total_b));
     int64_t budget = (int64_t)std::min<size_t>((size_t)(free_b * 0.4), (size_t)48 << 30);
     int64_t chunk = ctx->opt.bfs_chunk > 0 ? std::max<int64_t>(1, ctx->opt.bfs_chunk / W)
-                                           : std::max<int64_t>(1, budget / (26 * W * std::max<int64_t>(n, 1)));
+                                           : std::max<int64_t>(1, budget / ((pyr_pull ? 35 : 26) * W * std::max<int64_t>(n, 1)));
     chunk = std::min<int64_t>(chunk, nbatch);
     chunk = std::min<int64_t>(chunk, 65535);
     if (chunk > group) chunk -= chunk % group;  // whole groups per chunk
@@ -630,6 +810,8 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int6
     VGA_TRY(ctx->ws.get("bfs_visited", sizeof(u64) * (size_t)chunk * n * W, (void **)&visited.p));
     VGA_TRY(ctx->ws.get("bfs_frontier", sizeof(u64) * (size_t)chunk * n * W, (void **)&frontier.p));
     VGA_TRY(ctx->ws.get("bfs_next", sizeof(u64) * (size_t)chunk * n * W, (void **)&next.p));
+    u64 *pyr_p = nullptr;
+    if (pyr_pull) VGA_TRY(ctx->ws.get("bfs_pyr", sizeof(u64) * (size_t)chunk * (size_t)pl.total * W, (void **)&pyr_p));
     VGA_TRY(valid.alloc((size_t)chunk * W));
     VGA_TRY(stats.alloc((size_t)chunk * 4));
     VGA_TRY(work.alloc_zero(4, st));
@@ -665,6 +847,16 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int6
     d.lvl_in = coarse ? lvl.p : nullptr;
     d.lvl_out = nullptr;
     d.group = group;
+    d.pyr = pyr_p;
+    d.pyr_total = pl.total;
+    d.t_runptr = pyr_pull ? g->t_runptr.p : nullptr;
+    d.t_runs = pyr_pull ? g->t_runs.p : nullptr;
+    d.t_costptr = pyr_pull ? g->t_costptr.p : nullptr;
+    d.pyr_levels = pl.levels;
+    for (int k = 0; k < PYR_LEVELS_DEV; k++) {
+        d.pyr_off[k] = pl.off[k];
+        d.pyr_cnt[k] = pl.cnt[k];
+    }
 
     int deepest = 0;
     std::vector<int32_t> h_counts;
@@ -696,6 +888,8 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int6
             c.lvl_in = nullptr;
             c.lvl_out = lvl.p;
             c.group = 1;
+            c.pyr = nullptr;
+            c.t_costptr = nullptr;
             h_valid.assign((size_t)ng, ~0ULL);
             if (ngroups & 63) h_valid[(size_t)ng - 1] = (1ULL << (ngroups & 63)) - 1ULL;
             ones.assign((size_t)ng, 1);
@@ -829,6 +1023,54 @@ int ensure_transpose(vga_ctx *ctx, vga_graph *g) {
     VGA_CUDA(cudaStreamSynchronize(st));
     VGA_CUDA(cudaGetLastError());
     g->has_transpose = true;
+    return VGA_OK;
+}
+
+// Run-length form of the in-rows for the pyramid pull: sort every in-row, then one run per maximal stretch of
+// consecutive ordinals.  Built once per graph.
+int ensure_runs(vga_ctx *ctx, vga_graph *g) {
+    if (g->has_runs) return VGA_OK;
+    VGA_TRY(ensure_transpose(ctx, g));
+    cudaStream_t st = ctx->stream;
+    const int64_t n = g->n;
+    if (g->t_entries > 0) {
+        DevBuf<uint32_t> sorted;
+        VGA_TRY(sorted.alloc((size_t)g->t_entries + 1));
+        VGA_TRY(sort_segments_u32(ctx, g->t_col.p, sorted.p, g->t_entries, n, g->t_rowptr.p));
+        g->t_col = std::move(sorted);
+    }
+    DevBuf<u64> count, cost;
+    DevBuf<unsigned char> tmp;
+    VGA_TRY(count.alloc_zero((size_t)n + 1, st));
+    VGA_TRY(cost.alloc_zero((size_t)n + 1, st));
+    VGA_TRY(g->t_runptr.alloc((size_t)n + 1));
+    VGA_TRY(g->t_costptr.alloc((size_t)n + 1));
+    if (n > 0) {
+        k_count_runs<<<blocks_for(n * 32, 256), 256, 0, st>>>(g->t_rowptr.p, g->t_col.p, n, count.p);
+        ctx->timing.launches++;
+    }
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, count.p, (u64 *)g->t_runptr.p, (int)(n + 1), st);
+    VGA_TRY(tmp.alloc(tb + 16));
+    VGA_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, count.p, (u64 *)g->t_runptr.p, (int)(n + 1), st));
+    uint64_t total = 0;
+    VGA_CUDA(cudaMemcpyAsync(&total, g->t_runptr.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    VGA_CUDA(cudaStreamSynchronize(st));
+    g->t_nruns = (int64_t)total;
+    DevBuf<uint32_t> first_off;
+    VGA_TRY(first_off.alloc((size_t)total + 1));
+    VGA_TRY(g->t_runs.alloc((size_t)total + 1));
+    if (n > 0) {
+        k_mark_runs<<<blocks_for(n * 32, 256), 256, 0, st>>>(g->t_rowptr.p, g->t_col.p, n, g->t_runptr.p, first_off.p);
+        k_emit_runs<<<blocks_for(n * 32, 256), 256, 0, st>>>(g->t_rowptr.p, g->t_col.p, n, g->t_runptr.p, first_off.p, g->t_runs.p,
+                                                             cost.p);
+        ctx->timing.launches += 2;
+    }
+    VGA_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cost.p, (u64 *)g->t_costptr.p, (int)(n + 1), st));
+    ctx->timing.launches += 2;
+    VGA_CUDA(cudaStreamSynchronize(st));
+    VGA_CUDA(cudaGetLastError());
+    g->has_runs = true;
     return VGA_OK;
 }
 

@@ -40,6 +40,7 @@ static int set_option(Options &o, const std::string &key, int64_t value) {
     else if (key == "bfs_order") o.bfs_order = value;
     else if (key == "bfs_group") o.bfs_group = value;
     else if (key == "bfs_coarse") o.bfs_coarse = value;
+    else if (key == "bfs_pull") o.bfs_pull = value;
     else return VGA_ERR_INVALID;
     return VGA_OK;
 }
@@ -100,6 +101,10 @@ inline double p_value(double k) { return 2.0 * (k - log2_paf(k) - 1.0) / ((k - 1
 inline double tekl_integ(double nodes, double depth) { return std::log(0.5 * (nodes - 2.0)) / std::log(depth - nodes + 1.0); }
 
 }  // namespace
+
+int sort_segments_u32(vga_ctx *ctx, uint32_t *keys_in, uint32_t *keys_out, int64_t entries, int64_t rows, const uint64_t *rowptr) {
+    return sort_rows(ctx, keys_in, keys_out, entries, rows, rowptr);
+}
 }  // namespace vga
 
 using namespace vga;
@@ -152,6 +157,7 @@ int vga_ctx_create(int device, vga_ctx **out) {
     o.sieve_gcap = env_i64("VGA_SIEVE_GCAP", o.sieve_gcap);
     o.sieve_bcap = env_i64("VGA_SIEVE_BCAP", o.sieve_bcap);
     o.pull_alpha = env_i64("VGA_PULL_ALPHA", o.pull_alpha);
+    o.bfs_pull = env_i64("VGA_BFS_PULL", o.bfs_pull);
     *out = c.release();
     return VGA_OK;
 }

@@ -117,6 +117,9 @@ struct Options {
     int64_t bfs_order = 2;       // 0: x-major ordinals, 1: 8x8 tiles in Morton order, 2: + wall-respecting floods
     int64_t bfs_group = 16;      // batches per coarse lower-bound group
     int64_t bfs_coarse = 1;      // 1: coarse pass (64 group lower bounds per bit-parallel batch) prunes the pull step
+    int64_t bfs_pull = 0;        // bottom-up step: 0 scans in-row entries (k_pull); 1 = range-OR queries over an
+                                 // OR-pyramid of the frontier with run-length in-rows (k_pull_pyr; EXPERIMENTAL, opt-in,
+                                 // index logic unit-tested on CPU, kernels not yet run on a GPU)
 };
 
 }  // namespace vga
@@ -173,6 +176,14 @@ struct vga_graph {
     vga::DevBuf<uint32_t> t_col;    // [entries to filled targets]
     bool has_transpose = false;
     int64_t t_entries = 0;
+    // run-length in-rows for the pyramid pull (bfs_pull = 1), built lazily: the sorted in-row of v is the union of
+    // the runs t_runs[t_runptr[v] .. t_runptr[v+1]) = (first ordinal, length); t_costptr = prefix sums of the
+    // pyramid loads a full scan of each in-row costs
+    vga::DevBuf<uint64_t> t_runptr;  // [n+1]
+    vga::DevBuf<uint2> t_runs;
+    vga::DevBuf<uint64_t> t_costptr; // [n+1]
+    bool has_runs = false;
+    int64_t t_nruns = 0;
 };
 
 namespace vga {
@@ -180,6 +191,9 @@ namespace vga {
 int build_graph(vga_ctx *ctx, const vga_dgrid *g, int64_t src_begin, int64_t src_end, vga_graph **out);
 // bfs.cu
 int ensure_transpose(vga_ctx *ctx, vga_graph *g);
+int ensure_runs(vga_ctx *ctx, vga_graph *g);
+// cabi.cu: per-segment ascending sort of 32-bit keys (cub::DeviceSegmentedSort in slices of < 2^31 entries)
+int sort_segments_u32(vga_ctx *ctx, uint32_t *keys_in, uint32_t *keys_out, int64_t entries, int64_t rows, const uint64_t *rowptr);
 // spatially coherent order of the sources [src_begin, src_end) for 64-source batches
 int batch_source_order(vga_ctx *ctx, vga_graph *g, int64_t src_begin, int64_t src_end, std::vector<int32_t> &order);
 int run_global(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_t src_end, int32_t *total_nodes,

@@ -22,3 +22,43 @@ def test_local_bit_sliced_counters_vs_oracle(name):
     for x, y in zip(g.local_ints((0, hi)), og.local_ints((0, hi))):
         assert np.array_equal(x, y)
     c.close()
+
+
+@pytest.mark.parametrize("name", ["oblique:30:30:7", "office:64:64:1", "urban:120:120:4"])
+@pytest.mark.parametrize("radius", [-1, 2])
+@pytest.mark.parametrize("mode,words,coarse", [(1, 1, 0), (1, 2, 1), (2, 1, 1), (2, 4, 1), (2, 0, 1)])
+def test_pyramid_pull_vs_oracle(name, radius, mode, words, coarse):
+    """bfs_pull = 1: bottom-up step as range-OR queries over an OR-pyramid of the frontier with run-length in-rows
+    (k_pyr_build / k_pull_pyr, csrc/pyramid.cuh; index logic pinned on CPU by tests/test_pyramid_logic.py)."""
+    from oracle import pyoracle as po
+    flat = capi.prepare(plans.by_name(name))
+    og = po.OracleGraph(po.Grid(flat.cols, flat.rows, flat.spacing, flat.bl_x, flat.bl_y, flat.state, flat.line_off, flat.lines))
+    c = capi.Context(0)
+    for k, v in (("bfs_pull", 1), ("bfs_mode", mode), ("bfs_words", words), ("bfs_coarse", coarse)):
+        c.set_option(k, v)
+    g = c.build(flat)
+    tn, td, dist, used = g.global_ints(radius)
+    rng = np.random.RandomState(3)
+    for s in rng.choice(g.n, min(g.n, 96), replace=False):
+        otn, otd, odist, onl = og.global_ints(radius, (int(s), int(s) + 1), maxl=64)
+        L = dist.shape[1]
+        assert otn[0] == tn[s] and otd[0] == td[s]
+        assert np.array_equal(odist[0, :L], dist[s]) and not odist[0, L:].any()
+    c.close()
+
+
+def test_pyramid_pull_equals_default_on_c2():
+    """Full-size C2: the pyramid pull must give exactly the integers of the default schedule."""
+    flat = capi.prepare(plans.by_name("C2"))
+    a = capi.Context(0)
+    ga = a.build(flat)
+    ref = ga.global_ints(-1)
+    a.close()
+    b = capi.Context(0)
+    b.set_option("bfs_pull", 1)
+    gb = b.build(flat)
+    got = gb.global_ints(-1)
+    b.close()
+    assert ref[3] == got[3]
+    for x, y in zip(ref[:3], got[:3]):
+        assert np.array_equal(x, y)

@@ -1,0 +1,32 @@
+#!/bin/bash
+# First GPU call of the next round (run under gpurun from the repo root):
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/r2_first_call.sh'
+# 1. the whole GPU suite with the outcome of every guarded (xfail) test listed: the host-layer .graph pipelines, merge
+#    links, CLI step-depth shim, bit-sliced local counters and the pyramid pull were written after round 1's GPU budget was
+#    spent -- XPASS = validated, drop the guard; xfail = look at gpurun_out/r2_pytest.log;
+# 2. A/B timings of the opt-in BFS / local variants against the defaults on C2, a C4 slice and a C5 slice.
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q -rxX -p no:cacheprovider > gpurun_out/r2_pytest.log 2>&1
+tail -40 gpurun_out/r2_pytest.log
+{
+  echo "== C2 default";        python tools/gpu_time.py C2 global
+  echo "== C2 bfs_pull=1";     python tools/gpu_time.py C2 global bfs_pull=1
+  echo "== C2 bfs_pull=1 pull_alpha=4"; python tools/gpu_time.py C2 global bfs_pull=1 pull_alpha=4
+  echo "== C2 bfs_pull=1 pull_beta=4";  python tools/gpu_time.py C2 global bfs_pull=1 pull_beta=4
+  echo "== C2 bfs_pull=1 bfs_words=2";  python tools/gpu_time.py C2 global bfs_pull=1 bfs_words=2
+  echo "== C4 slice default";  VGA_TIME_SRC=16384 python tools/gpu_time.py C4 global
+  echo "== C4 slice bfs_pull=1"; VGA_TIME_SRC=16384 python tools/gpu_time.py C4 global bfs_pull=1
+  echo "== C5 slice default";  VGA_TIME_SRC=32768 python tools/gpu_time.py C5 global
+  echo "== C5 slice bfs_pull=1"; VGA_TIME_SRC=32768 python tools/gpu_time.py C5 global bfs_pull=1
+  echo "== C5 slice bfs_pull=1 words=4"; VGA_TIME_SRC=32768 python tools/gpu_time.py C5 global bfs_pull=1 bfs_words=4
+  echo "== C4 local slice default vs local_mode=3"
+  python - <<'PY'
+import time, numpy as np
+from depthmapx_b200 import capi, plans
+flat = capi.prepare(plans.by_name("C4"))
+for mode in (2, 3):
+    c = capi.Context(0); c.set_option("local_mode", mode); g = c.build(flat)
+    t0 = time.time(); r = g.local_ints((100000, 104096)); print("local_mode", mode, "4096 cells", round(time.time() - t0, 3), "s", int(r[0].sum())); c.close()
+PY
+} > gpurun_out/r2_ab.log 2>&1
+tail -60 gpurun_out/r2_ab.log
