@@ -129,8 +129,10 @@ __global__ void k_init_coarse(BfsDev d, const int32_t *src, int64_t nsrc, int pe
     d.lvl_out[grp * d.n + v] = 0;
 }
 
-// top-down step
-template <int W> __global__ void __launch_bounds__(TPB) k_push(BfsDev d) {
+// top-down step.  U = adjacency entries per lane and round: with U > 1 a lane issues U index loads, then U `visited`
+// gathers, then the atomics, so U dependent load chains are in flight per lane instead of one (the kernel is bound by
+// the latency of that chain, profiles/README.md).  U = 1 is the validated default; U = 4 is opt-in (bfs_push_unroll).
+template <int W, int U> __global__ void __launch_bounds__(TPB) k_push(BfsDev d) {
     const int b = blockIdx.y;
     if (!d.active[b] || d.mode[b] != 0) return;
     const int lane = threadIdx.x & 31;
@@ -160,15 +162,41 @@ template <int W> __global__ void __launch_bounds__(TPB) k_push(BfsDev d) {
 #pragma unroll
             for (int j = 0; j < W; j++) fw[j] = __shfl_sync(FULL, f[j], src_lane);
             uint64_t e0 = __shfl_sync(FULL, my0, src_lane), e1 = __shfl_sync(FULL, my1, src_lane);
-            for (uint64_t e = e0 + lane; e < e1; e += 32) {
-                uint32_t c = d.adj[e] >> 6;
-                if (c < (uint32_t)d.n) {
-                    u64 vv[W];
-                    ldw<W>(vis + (int64_t)c * W, vv);
+            if constexpr (U == 1) {
+                for (uint64_t e = e0 + lane; e < e1; e += 32) {
+                    uint32_t c = d.adj[e] >> 6;
+                    if (c < (uint32_t)d.n) {
+                        u64 vv[W];
+                        ldw<W>(vis + (int64_t)c * W, vv);
 #pragma unroll
-                    for (int j = 0; j < W; j++) {
-                        u64 add = fw[j] & ~vv[j];
-                        if (add) atomicOr(&nx[(int64_t)c * W + j], add);
+                        for (int j = 0; j < W; j++) {
+                            u64 add = fw[j] & ~vv[j];
+                            if (add) atomicOr(&nx[(int64_t)c * W + j], add);
+                        }
+                    }
+                }
+            } else {
+                for (uint64_t e = e0 + lane; e < e1; e += 32 * U) {
+                    uint32_t c[U];
+                    u64 vv[U][W];
+#pragma unroll
+                    for (int i = 0; i < U; i++) {
+                        const uint64_t ee = e + 32 * (uint64_t)i;
+                        c[i] = ee < e1 ? d.adj[ee] >> 6 : 0xffffffffu;  // ghosts and the tail fail the c < n test
+                    }
+#pragma unroll
+                    for (int i = 0; i < U; i++) {
+#pragma unroll
+                        for (int j = 0; j < W; j++) vv[i][j] = ~0ULL;
+                        if (c[i] < (uint32_t)d.n) ldw<W>(vis + (int64_t)c[i] * W, vv[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < U; i++) {
+#pragma unroll
+                        for (int j = 0; j < W; j++) {
+                            u64 add = fw[j] & ~vv[i][j];
+                            if (add) atomicOr(&nx[(int64_t)c[i] * W + j], add);
+                        }
                     }
                 }
             }
@@ -622,7 +650,10 @@ int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, De
     int level = 0, nlev = 1;
     while (radius == -1 || level < radius) {
         dim3 grid(xblocks, (unsigned)nb);
-        k_push<W><<<grid, TPB, 0, st>>>(d);
+        if (ctx->opt.bfs_push_unroll == 4)
+            k_push<W, 4><<<grid, TPB, 0, st>>>(d);
+        else
+            k_push<W, 1><<<grid, TPB, 0, st>>>(d);
         tm.launches++;
         tm.main_launches++;
         if (bfs_mode != 0 && level > 0) {

@@ -117,6 +117,8 @@ struct Options {
     int64_t bfs_order = 2;       // 0: x-major ordinals, 1: 8x8 tiles in Morton order, 2: + wall-respecting floods
     int64_t bfs_group = 16;      // batches per coarse lower-bound group
     int64_t bfs_coarse = 1;      // 1: coarse pass (64 group lower bounds per bit-parallel batch) prunes the pull step
+    int64_t bfs_push_unroll = 1; // adjacency entries per lane and round in the top-down step: 1 (default) or 4 (EXPERIMENTAL,
+                                 // opt-in, not yet run on a GPU: more loads in flight per lane)
     int64_t bfs_pull = 0;        // bottom-up step: 0 scans in-row entries (k_pull); 1 = range-OR queries over an
                                  // OR-pyramid of the frontier with run-length in-rows (k_pull_pyr; EXPERIMENTAL, opt-in,
                                  // index logic unit-tested on CPU, kernels not yet run on a GPU)

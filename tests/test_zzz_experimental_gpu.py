@@ -47,6 +47,23 @@ def test_pyramid_pull_vs_oracle(name, radius, mode, words, coarse):
     c.close()
 
 
+@pytest.mark.parametrize("name", ["oblique:30:30:7", "office:64:64:1"])
+@pytest.mark.parametrize("mode,words", [(0, 1), (0, 2), (2, 4), (2, 0)])
+def test_unrolled_push_vs_oracle(name, mode, words):
+    """bfs_push_unroll = 4: four adjacency entries per lane and round in the top-down step."""
+    from oracle import pyoracle as po
+    flat = capi.prepare(plans.by_name(name))
+    og = po.OracleGraph(po.Grid(flat.cols, flat.rows, flat.spacing, flat.bl_x, flat.bl_y, flat.state, flat.line_off, flat.lines))
+    c = capi.Context(0)
+    for k, v in (("bfs_push_unroll", 4), ("bfs_mode", mode), ("bfs_words", words)):
+        c.set_option(k, v)
+    g = c.build(flat)
+    tn, td, dist, used = g.global_ints(-1)
+    otn, otd, odist, onl = og.global_ints(-1, maxl=dist.shape[1])
+    assert np.array_equal(tn, otn) and np.array_equal(td, otd) and np.array_equal(dist, odist)
+    c.close()
+
+
 def test_pyramid_pull_equals_default_on_c2():
     """Full-size C2: the pyramid pull must give exactly the integers of the default schedule."""
     flat = capi.prepare(plans.by_name("C2"))
