@@ -8,6 +8,14 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# TEST INFRASTRUCTURE: tests/test_emulated_kernels.py re-runs GPU test modules in a subprocess against the CPU emulation
+# of libvga_b200 (tests/emu/): the ctypes loader of that subprocess is pointed at the emulation's scratch directory here.
+# The product itself has no such switch.
+if os.environ.get("VGA_EMU_LIBDIR"):
+    from depthmapx_b200 import capi as _capi
+    _capi.LIBDIR = os.environ["VGA_EMU_LIBDIR"]
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "ref: needs oracle/_ref/libdmxref.so (the compiled reference)")
