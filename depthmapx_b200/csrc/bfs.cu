@@ -60,8 +60,8 @@ struct BfsDev {
     const u64 *valid;                // [batches*W] valid source bits of each word
     int *active;                     // [batches] 1 while the batch's frontier is non-empty
     int *mode;                       // [batches] 0 push, 1 pull
-    u64 *stats;                      // [batches][4]: frontier edges, candidate in-edges, new vertices, -
-    int *any;                        // [1] any batch still active
+    u64 *stats;                      // [batches][NSTAT]: frontier edges, pull cost, new vertices, open vertices, run cost
+    int *any;                        // [1] bit 0: some batch still active, bit 1: the level just folded added vertices
     const uint8_t *lvl_in;           // [groups][n] coarse lower-bound level, or nullptr
     uint8_t *lvl_out;                // [coarse batches*64][n] written by the coarse pass, or nullptr
     int group;                       // batches per coarse group
@@ -71,10 +71,18 @@ struct BfsDev {
     const uint64_t *t_runptr;        // [n+1]
     const uint2 *t_runs;             // (first ordinal, length) runs of the sorted in-rows
     const uint64_t *t_costptr;       // [n+1] prefix sums of the pyramid loads of a full in-row scan
+    // pyramid push (bfs_push = 1), nullptr otherwise
+    u64 *npyr;                       // [batches][pyr_total][W]: range-OR update nodes of `next` (levels >= 1), all zero
+                                     // between levels
+    const uint64_t *f_runptr;        // [n+1] runs of the (sorted) out-rows, ghost columns excluded
+    const uint2 *f_runs;
+    const uint64_t *f_costptr;       // [n+1] prefix sums of the pyramid nodes an out-row touches
+    int push_force;                  // bfs_push = 2: every top-down step after level 0 uses the pyramid (tests)
     int pyr_levels;
     int64_t pyr_off[PYR_LEVELS_DEV];
     int64_t pyr_cnt[PYR_LEVELS_DEV];
 };
+constexpr int NSTAT = 8;  // per-batch statistics: frontier edges, pull cost, new vertices, open vertices, frontier run cost
 
 template <int W> __device__ __forceinline__ void ldw(const u64 *p, u64 (&o)[W]) {
     if constexpr (W == 1) {
@@ -290,6 +298,74 @@ template <int W> __global__ void __launch_bounds__(TPB) k_pull(BfsDev d, int lev
     }
 }
 
+// ---- pyramid push (bfs_push = 1, see pyramid.cuh) -----------------------------------------------------------
+
+// top-down step over run-length out-rows: every frontier vertex ORs its words into the pyramid nodes that tile each run
+// of its row (at most 2 per level); single vertices (level-0 nodes) go straight to `next`, filtered by `visited`.
+// A plain read skips the atomic when the node already holds the bits.
+template <int W> __global__ void __launch_bounds__(TPB) k_push_pyr(BfsDev d) {
+    const int b = blockIdx.y;
+    if (!d.active[b] || d.mode[b] != 2) return;
+    const int lane = threadIdx.x & 31;
+    const u64 *fr = d.frontier + (int64_t)b * d.n * W;
+    const u64 *vis = d.visited + (int64_t)b * d.n * W;
+    u64 *nx = d.next + (int64_t)b * d.n * W;
+    u64 *np = d.npyr + (int64_t)b * d.pyr_total * W;
+    for (int64_t base = (int64_t)blockIdx.x * TPB; base < d.n; base += (int64_t)gridDim.x * TPB) {
+        int64_t u = base + threadIdx.x;
+        u64 f[W];
+#pragma unroll
+        for (int j = 0; j < W; j++) f[j] = 0ULL;
+        if (u < d.n) ldw<W>(fr + u * W, f);
+        u64 anyf = 0ULL;
+#pragma unroll
+        for (int j = 0; j < W; j++) anyf |= f[j];
+        uint64_t my0 = 0, my1 = 0;
+        if (anyf != 0ULL) {
+            my0 = d.f_runptr[u];
+            my1 = d.f_runptr[u + 1];
+        }
+        unsigned m = __ballot_sync(FULL, anyf != 0ULL);
+        while (m) {
+            int src_lane = __ffs(m) - 1;
+            m &= m - 1;
+            u64 fw[W];
+#pragma unroll
+            for (int j = 0; j < W; j++) fw[j] = __shfl_sync(FULL, f[j], src_lane);
+            uint64_t r0 = __shfl_sync(FULL, my0, src_lane), r1 = __shfl_sync(FULL, my1, src_lane);
+            for (uint64_t r = r0 + lane; r < r1; r += 32) {
+                const uint2 run = d.f_runs[r];
+                pyr_decompose(run.x, run.y, [&](int kk, uint32_t i) {
+                    u64 *p = kk == 0 ? nx + (int64_t)i * W : np + (d.pyr_off[kk] + (int64_t)i) * W;
+                    u64 cur[W];
+                    ldw<W>(kk == 0 ? vis + (int64_t)i * W : p, cur);  // leaf: reached sources; node: bits already there
+#pragma unroll
+                    for (int j = 0; j < W; j++) {
+                        u64 add = fw[j] & ~cur[j];
+                        if (add) atomicOr(&p[j], add);
+                    }
+                });
+            }
+        }
+    }
+}
+
+// down pass of the pyramid push, three levels per launch, top chunk first: level k+3 .. k+1 -> level k (`next` for k = 0)
+template <int W> __global__ void __launch_bounds__(TPB) k_pyr_down(BfsDev d, int k) {
+    const int b = blockIdx.y;
+    if (!d.active[b] || d.mode[b] != 2) return;
+    u64 *np = d.npyr + (int64_t)b * d.pyr_total * W;
+    u64 *dst = k == 0 ? d.next + (int64_t)b * d.n * W : np + d.pyr_off[k] * W;
+    u64 *s1 = k + 1 < d.pyr_levels ? np + d.pyr_off[k + 1] * W : nullptr;
+    u64 *s2 = k + 2 < d.pyr_levels ? np + d.pyr_off[k + 2] * W : nullptr;
+    u64 *s3 = k + 3 < d.pyr_levels ? np + d.pyr_off[k + 3] * W : nullptr;
+    const int64_t c0 = d.pyr_cnt[k];
+    const int64_t c1 = s1 ? d.pyr_cnt[k + 1] : 0, c2 = s2 ? d.pyr_cnt[k + 2] : 0, c3 = s3 ? d.pyr_cnt[k + 3] : 0;
+    const int64_t groups = (c0 + 7) / 8;
+    for (int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x; t < groups; t += (int64_t)gridDim.x * TPB)
+        pyr_down_group<W>(dst, c0, s1, c1, s2, c2, s3, c3, t);
+}
+
 // ---- pyramid pull (bfs_pull = 1, see pyramid.cuh) -----------------------------------------------------------
 
 // Three pyramid levels per launch for every batch whose next step is a pull: level k (the frontier for k = 0) ->
@@ -405,9 +481,9 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[bat
     const int b = blockIdx.y;
     if (!d.active[b]) return;
     __shared__ int s_cnt[W * 64];
-    __shared__ u64 s_stat[3];
+    __shared__ u64 s_stat[5];
     for (int i = threadIdx.x; i < W * 64; i += TPB) s_cnt[i] = 0;
-    if (threadIdx.x < 3) s_stat[threadIdx.x] = 0ULL;
+    if (threadIdx.x < 5) s_stat[threadIdx.x] = 0ULL;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     u64 *fr = d.frontier + (int64_t)b * d.n * W;
@@ -421,7 +497,7 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[bat
     int cnt[W][2];  // lane l counts source bits l and l+32 of each word
 #pragma unroll
     for (int j = 0; j < W; j++) cnt[j][0] = cnt[j][1] = 0;
-    u64 f_edges = 0, u_edges = 0, n_new = 0;
+    u64 f_edges = 0, u_edges = 0, n_new = 0, n_open = 0, f_runs = 0;
     for (int64_t base = (int64_t)blockIdx.x * TPB; base < d.n; base += (int64_t)gridDim.x * TPB) {
         int64_t v = base + threadIdx.x;
         u64 nw[W];
@@ -446,6 +522,7 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[bat
                 for (int j = 0; j < W; j++) zero[j] = 0ULL;
                 stw<W>(nx + v * W, zero);
                 f_edges += d.rowptr[v + 1] - d.rowptr[v];
+                if (d.f_costptr) f_runs += d.f_costptr[v + 1] - d.f_costptr[v];
                 n_new += 1;
                 if (lout) {
                     // coarse pass (W == 1): bit j of coarse batch b is group b*64+j
@@ -457,7 +534,20 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[bat
                     }
                 }
             }
+            else if (d.npyr) {
+                // the pyramid push does not filter by `visited`: drop words that only repeat reached sources
+                u64 anyx = 0ULL;
+#pragma unroll
+                for (int j = 0; j < W; j++) anyx |= xx[j];
+                if (anyx) {
+                    u64 zero[W];
+#pragma unroll
+                    for (int j = 0; j < W; j++) zero[j] = 0ULL;
+                    stw<W>(nx + v * W, zero);
+                }
+            }
             stw<W>(fr + v * W, nw);
+            if (anyneed != 0ULL) n_open += 1;  // still unreached by some source of the batch
             // in-edges (or, for the pyramid pull, pyramid loads) the next pull step would have to consider
             const uint64_t *cost = d.t_costptr ? d.t_costptr : d.t_rowptr;
             if (cost && anyneed != 0ULL && (!lvl || (int)lvl[v] <= level_next + 1)) u_edges += cost[v + 1] - cost[v];
@@ -489,17 +579,21 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[bat
         f_edges += __shfl_down_sync(FULL, f_edges, o);
         u_edges += __shfl_down_sync(FULL, u_edges, o);
         n_new += __shfl_down_sync(FULL, n_new, o);
+        n_open += __shfl_down_sync(FULL, n_open, o);
+        f_runs += __shfl_down_sync(FULL, f_runs, o);
     }
     if (lane == 0) {
         if (f_edges) atomicAdd(&s_stat[0], f_edges);
         if (u_edges) atomicAdd(&s_stat[1], u_edges);
         if (n_new) atomicAdd(&s_stat[2], n_new);
+        if (n_open) atomicAdd(&s_stat[3], n_open);
+        if (f_runs) atomicAdd(&s_stat[4], f_runs);
     }
     __syncthreads();
     if (counts)
         for (int i = threadIdx.x; i < W * 64; i += TPB)
             if (s_cnt[i]) atomicAdd(&counts[(int64_t)b * W * 64 + i], s_cnt[i]);
-    if (threadIdx.x < 3 && s_stat[threadIdx.x]) atomicAdd(&d.stats[b * 4 + threadIdx.x], s_stat[threadIdx.x]);
+    if (threadIdx.x < 5 && s_stat[threadIdx.x]) atomicAdd(&d.stats[b * NSTAT + threadIdx.x], s_stat[threadIdx.x]);
 }
 
 // per batch: retire empty batches, choose the next step's direction, reset statistics
@@ -507,27 +601,34 @@ __global__ void k_decide(BfsDev d, int nb, int bfs_mode, int64_t alpha, int64_t 
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
     if (!d.active[b]) return;
-    u64 fe = d.stats[b * 4 + 0], ue = d.stats[b * 4 + 1], nn = d.stats[b * 4 + 2];
-    d.stats[b * 4 + 0] = 0;
-    d.stats[b * 4 + 1] = 0;
-    d.stats[b * 4 + 2] = 0;
-    if (nn == 0) {
+    u64 fe = d.stats[b * NSTAT + 0], ue = d.stats[b * NSTAT + 1], nn = d.stats[b * NSTAT + 2], open = d.stats[b * NSTAT + 3];
+    const u64 frc = d.stats[b * NSTAT + 4];
+    for (int i = 0; i < 5; i++) d.stats[b * NSTAT + i] = 0;
+    // Retire the batch when nothing new was reached -- or when every vertex has been reached by every source of the
+    // batch: expanding the last frontier could not find anything (on connected plans that last, useless expansion of
+    // the largest frontier was 10-20 % of the top-down work).
+    if (nn != 0) atomicOr(d.any, 2);  // bit 1: this level added vertices (the histogram has one more level)
+    if (nn == 0 || open == 0) {
         d.active[b] = 0;
         return;
     }
-    *d.any = 1;
+    atomicOr(d.any, 1);  // bit 0: some batch goes on
+    // step of the next level: 0 = push over adjacency entries, 1 = pull, 2 = push as range-OR updates over the runs of the
+    // out-rows (its cost: the pyramid nodes the frontier rows touch plus the down pass over ~2n nodes)
     int m = 0;
     if (bfs_mode == 1)
         m = 1;
     else if (bfs_mode == 2)
         m = (fe * (u64)alpha > ue * (u64)beta) ? 1 : 0;
+    if (m == 0 && d.npyr && (d.push_force || frc + 2 * (u64)d.n < fe)) m = 2;
+    if (m == 1 && d.npyr && bfs_mode == 2 && (frc + 2 * (u64)d.n) * (u64)alpha < ue * (u64)beta) m = 2;
     d.mode[b] = m;
     if (work) {
         // work[0]: adjacency entries of the vertices that expand next (sum of deg over U_l),
         // work[1]: vertices newly reached (|U_l| summed), work[2]: in-edges offered to the pull step
         atomicAdd(&work[0], fe);
         atomicAdd(&work[1], nn);
-        if (m) atomicAdd(&work[2], ue);
+        if (m == 1) atomicAdd(&work[2], ue);
     }
 }
 
@@ -579,46 +680,59 @@ __global__ void k_neighbour_bits(int64_t n, const uint64_t *rowptr, const uint32
     gc[v] = out;
 }
 
-// ---- run-length in-rows (bfs_pull = 1): one warp per vertex over its SORTED in-row ---------------------------
-// a run starts at entry e iff it is the first of the row or its ordinal does not continue the previous one
-__global__ void k_count_runs(const uint64_t *t_rowptr, const uint32_t *t_col, int64_t n, u64 *count) {
+// ---- run-length rows (bfs_pull / bfs_push = 1): one warp per vertex over a SORTED row --------------------------------
+// entry e of row v holds ordinal arr[e] >> shift; ordinals >= limit (ghost columns, which sort last) are not part of
+// any run.  A run starts at a valid entry that is the first of the row or does not continue the previous ordinal.
+__global__ void k_count_runs(const uint64_t *rowptr, const uint32_t *arr, int shift, uint32_t limit, int64_t n, u64 *count,
+                             uint32_t *nvalid) {
     const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (v >= n) return;
-    const uint64_t e0 = t_rowptr[v], e1 = t_rowptr[v + 1];
-    unsigned c = 0;
-    for (uint64_t e = e0 + lane; e < e1; e += 32) c += (e == e0 || t_col[e] != t_col[e - 1] + 1u) ? 1u : 0u;
+    const uint64_t e0 = rowptr[v], e1 = rowptr[v + 1];
+    unsigned c = 0, nv = 0;
+    for (uint64_t e = e0 + lane; e < e1; e += 32) {
+        const uint32_t x = arr[e] >> shift;
+        if (x >= limit) continue;
+        nv++;
+        c += (e == e0 || x != (arr[e - 1] >> shift) + 1u) ? 1u : 0u;
+    }
     c = __reduce_add_sync(FULL, c);
-    if (lane == 0) count[v] = c;
+    nv = __reduce_add_sync(FULL, nv);
+    if (lane == 0) {
+        count[v] = c;
+        nvalid[v] = nv;
+    }
 }
 // first_off[r] = offset (within its row) of the entry that starts run r
-__global__ void k_mark_runs(const uint64_t *t_rowptr, const uint32_t *t_col, int64_t n, const uint64_t *runptr, uint32_t *first_off) {
+__global__ void k_mark_runs(const uint64_t *rowptr, const uint32_t *arr, int shift, const uint32_t *nvalid, int64_t n,
+                            const uint64_t *runptr, uint32_t *first_off) {
     const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (v >= n) return;
-    const uint64_t e0 = t_rowptr[v], e1 = t_rowptr[v + 1];
+    const uint64_t e0 = rowptr[v], e1 = e0 + nvalid[v];
     uint64_t out = runptr[v];
     for (uint64_t eb = e0; eb < e1; eb += 32) {
         const uint64_t e = eb + lane;
-        const bool start = e < e1 && (e == e0 || t_col[e] != t_col[e - 1] + 1u);
+        const bool start = e < e1 && (e == e0 || (arr[e] >> shift) != (arr[e - 1] >> shift) + 1u);
         const unsigned mask = __ballot_sync(FULL, start);
         if (start) first_off[out + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)(e - e0);
         out += __popc(mask);
     }
 }
-// runs[r] = (first ordinal, length); cost[v] = pyramid loads of a full scan of the in-row of v
-__global__ void k_emit_runs(const uint64_t *t_rowptr, const uint32_t *t_col, int64_t n, const uint64_t *runptr,
-                            const uint32_t *first_off, uint2 *runs, u64 *cost) {
+// runs[r] = (first ordinal, length); cost[v] = pyramid nodes a full pass over the row of v touches
+__global__ void k_emit_runs(const uint64_t *rowptr, const uint32_t *arr, int shift, const uint32_t *nvalid, int64_t n,
+                            const uint64_t *runptr, const uint32_t *first_off, uint2 *runs, u64 *cost) {
     const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (v >= n) return;
-    const uint64_t e0 = t_rowptr[v], e1 = t_rowptr[v + 1];
+    const uint64_t e0 = rowptr[v];
+    const uint32_t nv = nvalid[v];
     const uint64_t r0 = runptr[v], r1 = runptr[v + 1];
     unsigned c = 0;
     for (uint64_t r = r0 + lane; r < r1; r += 32) {
         const uint32_t off = first_off[r];
-        const uint32_t nxt = r + 1 < r1 ? first_off[r + 1] : (uint32_t)(e1 - e0);
-        const uint2 run = make_uint2(t_col[e0 + off], nxt - off);
+        const uint32_t nxt = r + 1 < r1 ? first_off[r + 1] : nv;
+        const uint2 run = make_uint2(arr[e0 + off] >> shift, nxt - off);
         runs[r] = run;
         c += (unsigned)pyr_cost(run.x, run.y);
     }
@@ -656,6 +770,20 @@ int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, De
             k_push<W, 1><<<grid, TPB, 0, st>>>(d);
         tm.launches++;
         tm.main_launches++;
+        if (d.npyr && level > 0) {
+            k_push_pyr<W><<<grid, TPB, 0, st>>>(d);
+            tm.launches++;
+            tm.main_launches++;
+            int kmax = 0;
+            while (kmax + 4 < d.pyr_levels) kmax += 3;
+            for (int k = kmax; k >= 0; k -= 3) {
+                const int64_t groups = (d.pyr_cnt[k] + 7) / 8;
+                dim3 pgrid((unsigned)std::min<int64_t>((groups + TPB - 1) / TPB, 4096), (unsigned)nb);
+                k_pyr_down<W><<<pgrid, TPB, 0, st>>>(d, k);
+                tm.launches++;
+                tm.main_launches++;
+            }
+        }
         if (bfs_mode != 0 && level > 0) {
             if (d.pyr) {
                 for (int k = 0; k + 1 < d.pyr_levels; k += 3) {
@@ -691,9 +819,9 @@ int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, De
         int h_any = 0;
         VGA_CUDA(cudaMemcpyAsync(&h_any, d.any, sizeof(int), cudaMemcpyDeviceToHost, st));
         VGA_CUDA(cudaStreamSynchronize(st));
-        if (!h_any) break;
+        if (h_any & 2) nlev = level + 2;
+        if (!(h_any & 1)) break;
         level++;
-        nlev = level + 1;
     }
     *nlev_out = nlev;
     return VGA_OK;
@@ -802,6 +930,8 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int6
     PyrLayout pl = pyr_layout(n);
     const bool pyr_pull = bfs_mode != 0 && ctx->opt.bfs_pull == 1 && pl.levels <= PYR_LEVELS_DEV && n > 1;
     if (pyr_pull) VGA_TRY(ensure_runs(ctx, g));
+    const bool pyr_push = ctx->opt.bfs_push >= 1 && pl.levels <= PYR_LEVELS_DEV && n > 1;
+    if (pyr_push) VGA_TRY(ensure_fwd_runs(ctx, g));
     kt.stop();
     const double w1 = wall();
 
@@ -822,7 +952,7 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int6
     VGA_CUDA(cudaMemGetInfo(&free_b, &total_b));
     int64_t budget = (int64_t)std::min<size_t>((size_t)(free_b * 0.4), (size_t)48 << 30);
     int64_t chunk = ctx->opt.bfs_chunk > 0 ? std::max<int64_t>(1, ctx->opt.bfs_chunk / W)
-                                           : std::max<int64_t>(1, budget / ((pyr_pull ? 35 : 26) * W * std::max<int64_t>(n, 1)));
+                                           : std::max<int64_t>(1, budget / ((26 + (pyr_pull ? 9 : 0) + (pyr_push ? 9 : 0)) * W * std::max<int64_t>(n, 1)));
     chunk = std::min<int64_t>(chunk, nbatch);
     chunk = std::min<int64_t>(chunk, 65535);
     if (chunk > group) chunk -= chunk % group;  // whole groups per chunk
@@ -843,8 +973,14 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int6
     VGA_TRY(ctx->ws.get("bfs_next", sizeof(u64) * (size_t)chunk * n * W, (void **)&next.p));
     u64 *pyr_p = nullptr;
     if (pyr_pull) VGA_TRY(ctx->ws.get("bfs_pyr", sizeof(u64) * (size_t)chunk * (size_t)pl.total * W, (void **)&pyr_p));
+    u64 *npyr_p = nullptr;
+    if (pyr_push) {
+        VGA_TRY(ctx->ws.get("bfs_npyr", sizeof(u64) * (size_t)chunk * (size_t)pl.total * W, (void **)&npyr_p));
+        // all zero between levels: the down pass clears what the push wrote
+        VGA_CUDA(cudaMemsetAsync(npyr_p, 0, sizeof(u64) * (size_t)chunk * (size_t)pl.total * W, st));
+    }
     VGA_TRY(valid.alloc((size_t)chunk * W));
-    VGA_TRY(stats.alloc((size_t)chunk * 4));
+    VGA_TRY(stats.alloc((size_t)chunk * NSTAT));
     VGA_TRY(work.alloc_zero(4, st));
     VGA_TRY(active.alloc((size_t)chunk));
     VGA_TRY(mode.alloc((size_t)chunk));
@@ -855,7 +991,7 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int6
         VGA_TRY(c_frontier.alloc((size_t)max_cbatch * n));
         VGA_TRY(c_next.alloc((size_t)max_cbatch * n));
         VGA_TRY(c_valid.alloc((size_t)max_cbatch));
-        VGA_TRY(c_stats.alloc((size_t)max_cbatch * 4));
+        VGA_TRY(c_stats.alloc((size_t)max_cbatch * NSTAT));
         VGA_TRY(c_active.alloc((size_t)max_cbatch));
         VGA_TRY(c_mode.alloc((size_t)max_cbatch));
         VGA_TRY(lvl.alloc((size_t)max_cbatch * 64 * n));
@@ -883,6 +1019,11 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int6
     d.t_runptr = pyr_pull ? g->t_runptr.p : nullptr;
     d.t_runs = pyr_pull ? g->t_runs.p : nullptr;
     d.t_costptr = pyr_pull ? g->t_costptr.p : nullptr;
+    d.npyr = npyr_p;
+    d.push_force = ctx->opt.bfs_push == 2 ? 1 : 0;
+    d.f_runptr = pyr_push ? g->f_runptr.p : nullptr;
+    d.f_runs = pyr_push ? g->f_runs.p : nullptr;
+    d.f_costptr = pyr_push ? g->f_costptr.p : nullptr;
     d.pyr_levels = pl.levels;
     for (int k = 0; k < PYR_LEVELS_DEV; k++) {
         d.pyr_off[k] = pl.off[k];
@@ -921,6 +1062,8 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int6
             c.group = 1;
             c.pyr = nullptr;
             c.t_costptr = nullptr;
+            c.npyr = nullptr;
+            c.f_costptr = nullptr;
             h_valid.assign((size_t)ng, ~0ULL);
             if (ngroups & 63) h_valid[(size_t)ng - 1] = (1ULL << (ngroups & 63)) - 1ULL;
             ones.assign((size_t)ng, 1);
@@ -929,7 +1072,7 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int6
             VGA_CUDA(cudaMemsetAsync(c_visited.p, 0, sizeof(u64) * (size_t)ng * n, st));
             VGA_CUDA(cudaMemsetAsync(c_frontier.p, 0, sizeof(u64) * (size_t)ng * n, st));
             VGA_CUDA(cudaMemsetAsync(c_next.p, 0, sizeof(u64) * (size_t)ng * n, st));
-            VGA_CUDA(cudaMemsetAsync(c_stats.p, 0, sizeof(u64) * (size_t)ng * 4, st));
+            VGA_CUDA(cudaMemsetAsync(c_stats.p, 0, sizeof(u64) * (size_t)ng * NSTAT, st));
             VGA_CUDA(cudaMemsetAsync(c_mode.p, 0, sizeof(int) * (size_t)ng, st));
             VGA_CUDA(cudaMemsetAsync(lvl.p, 0xff, (size_t)ng * 64 * n, st));
             VGA_CUDA(cudaStreamSynchronize(st));  // host staging vectors are reused below
@@ -953,7 +1096,7 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int6
         VGA_CUDA(cudaMemsetAsync(visited.p, 0, sizeof(u64) * (size_t)cb * n * W, st));
         VGA_CUDA(cudaMemsetAsync(frontier.p, 0, sizeof(u64) * (size_t)cb * n * W, st));
         VGA_CUDA(cudaMemsetAsync(next.p, 0, sizeof(u64) * (size_t)cb * n * W, st));
-        VGA_CUDA(cudaMemsetAsync(stats.p, 0, sizeof(u64) * (size_t)cb * 4, st));
+        VGA_CUDA(cudaMemsetAsync(stats.p, 0, sizeof(u64) * (size_t)cb * NSTAT, st));
         VGA_CUDA(cudaMemsetAsync(mode.p, 0, sizeof(int) * (size_t)cb, st));  // level 0 always pushes
         VGA_CUDA(cudaMemsetAsync(counts.p, 0, sizeof(int32_t) * (size_t)lcap * cstride, st));
         VGA_CUDA(cudaStreamSynchronize(st));
@@ -1057,51 +1200,64 @@ int ensure_transpose(vga_ctx *ctx, vga_graph *g) {
     return VGA_OK;
 }
 
-// Run-length form of the in-rows for the pyramid pull: sort every in-row, then one run per maximal stretch of
-// consecutive ordinals.  Built once per graph.
-int ensure_runs(vga_ctx *ctx, vga_graph *g) {
-    if (g->has_runs) return VGA_OK;
-    VGA_TRY(ensure_transpose(ctx, g));
+// Run-length form of sorted rows: one run per maximal stretch of consecutive ordinals (ghost columns excluded).
+static int build_runs(vga_ctx *ctx, int64_t n, const uint64_t *rowptr, const uint32_t *arr, int shift, DevBuf<uint64_t> &runptr,
+                      DevBuf<uint2> &runs, DevBuf<uint64_t> &costptr, int64_t *nruns) {
     cudaStream_t st = ctx->stream;
-    const int64_t n = g->n;
-    if (g->t_entries > 0) {
-        DevBuf<uint32_t> sorted;
-        VGA_TRY(sorted.alloc((size_t)g->t_entries + 1));
-        VGA_TRY(sort_segments_u32(ctx, g->t_col.p, sorted.p, g->t_entries, n, g->t_rowptr.p));
-        g->t_col = std::move(sorted);
-    }
     DevBuf<u64> count, cost;
+    DevBuf<uint32_t> nvalid, first_off;
     DevBuf<unsigned char> tmp;
     VGA_TRY(count.alloc_zero((size_t)n + 1, st));
     VGA_TRY(cost.alloc_zero((size_t)n + 1, st));
-    VGA_TRY(g->t_runptr.alloc((size_t)n + 1));
-    VGA_TRY(g->t_costptr.alloc((size_t)n + 1));
+    VGA_TRY(nvalid.alloc_zero((size_t)n + 1, st));
+    VGA_TRY(runptr.alloc((size_t)n + 1));
+    VGA_TRY(costptr.alloc((size_t)n + 1));
     if (n > 0) {
-        k_count_runs<<<blocks_for(n * 32, 256), 256, 0, st>>>(g->t_rowptr.p, g->t_col.p, n, count.p);
+        k_count_runs<<<blocks_for(n * 32, 256), 256, 0, st>>>(rowptr, arr, shift, (uint32_t)n, n, count.p, nvalid.p);
         ctx->timing.launches++;
     }
     size_t tb = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tb, count.p, (u64 *)g->t_runptr.p, (int)(n + 1), st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, count.p, (u64 *)runptr.p, (int)(n + 1), st);
     VGA_TRY(tmp.alloc(tb + 16));
-    VGA_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, count.p, (u64 *)g->t_runptr.p, (int)(n + 1), st));
+    VGA_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, count.p, (u64 *)runptr.p, (int)(n + 1), st));
     uint64_t total = 0;
-    VGA_CUDA(cudaMemcpyAsync(&total, g->t_runptr.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    VGA_CUDA(cudaMemcpyAsync(&total, runptr.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     VGA_CUDA(cudaStreamSynchronize(st));
-    g->t_nruns = (int64_t)total;
-    DevBuf<uint32_t> first_off;
+    *nruns = (int64_t)total;
     VGA_TRY(first_off.alloc((size_t)total + 1));
-    VGA_TRY(g->t_runs.alloc((size_t)total + 1));
+    VGA_TRY(runs.alloc((size_t)total + 1));
     if (n > 0) {
-        k_mark_runs<<<blocks_for(n * 32, 256), 256, 0, st>>>(g->t_rowptr.p, g->t_col.p, n, g->t_runptr.p, first_off.p);
-        k_emit_runs<<<blocks_for(n * 32, 256), 256, 0, st>>>(g->t_rowptr.p, g->t_col.p, n, g->t_runptr.p, first_off.p, g->t_runs.p,
-                                                             cost.p);
+        k_mark_runs<<<blocks_for(n * 32, 256), 256, 0, st>>>(rowptr, arr, shift, nvalid.p, n, runptr.p, first_off.p);
+        k_emit_runs<<<blocks_for(n * 32, 256), 256, 0, st>>>(rowptr, arr, shift, nvalid.p, n, runptr.p, first_off.p, runs.p, cost.p);
         ctx->timing.launches += 2;
     }
-    VGA_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cost.p, (u64 *)g->t_costptr.p, (int)(n + 1), st));
+    VGA_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cost.p, (u64 *)costptr.p, (int)(n + 1), st));
     ctx->timing.launches += 2;
     VGA_CUDA(cudaStreamSynchronize(st));
     VGA_CUDA(cudaGetLastError());
+    return VGA_OK;
+}
+
+// in-rows for the pyramid pull: sort every in-row first.  Built once per graph.
+int ensure_runs(vga_ctx *ctx, vga_graph *g) {
+    if (g->has_runs) return VGA_OK;
+    VGA_TRY(ensure_transpose(ctx, g));
+    if (g->t_entries > 0) {
+        DevBuf<uint32_t> sorted;
+        VGA_TRY(sorted.alloc((size_t)g->t_entries + 1));
+        VGA_TRY(sort_segments_u32(ctx, g->t_col.p, sorted.p, g->t_entries, g->n, g->t_rowptr.p));
+        g->t_col = std::move(sorted);
+    }
+    VGA_TRY(build_runs(ctx, g->n, g->t_rowptr.p, g->t_col.p, 0, g->t_runptr, g->t_runs, g->t_costptr, &g->t_nruns));
     g->has_runs = true;
+    return VGA_OK;
+}
+
+// out-rows for the pyramid push (rows are kept sorted by column; packed entries col << 6 | ...)
+int ensure_fwd_runs(vga_ctx *ctx, vga_graph *g) {
+    if (g->has_fwd_runs) return VGA_OK;
+    VGA_TRY(build_runs(ctx, g->n, g->rowptr.p, g->adj.p, 6, g->f_runptr, g->f_runs, g->f_costptr, &g->f_nruns));
+    g->has_fwd_runs = true;
     return VGA_OK;
 }
 

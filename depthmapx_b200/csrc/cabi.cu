@@ -41,6 +41,7 @@ static int set_option(Options &o, const std::string &key, int64_t value) {
     else if (key == "bfs_group") o.bfs_group = value;
     else if (key == "bfs_coarse") o.bfs_coarse = value;
     else if (key == "bfs_pull") o.bfs_pull = value;
+    else if (key == "bfs_push") o.bfs_push = value;
     else if (key == "bfs_push_unroll") o.bfs_push_unroll = value;
     else return VGA_ERR_INVALID;
     return VGA_OK;
@@ -159,6 +160,7 @@ int vga_ctx_create(int device, vga_ctx **out) {
     o.sieve_bcap = env_i64("VGA_SIEVE_BCAP", o.sieve_bcap);
     o.pull_alpha = env_i64("VGA_PULL_ALPHA", o.pull_alpha);
     o.bfs_pull = env_i64("VGA_BFS_PULL", o.bfs_pull);
+    o.bfs_push = env_i64("VGA_BFS_PUSH", o.bfs_push);
     *out = c.release();
     return VGA_OK;
 }

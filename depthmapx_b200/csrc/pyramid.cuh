@@ -115,6 +115,56 @@ VGA_HD void pyr_build_group(const unsigned long long *src, int64_t cnt0, unsigne
     }
 }
 
+// The reverse direction, for range-OR UPDATES (top-down step with run-length rows): words are ORed into the nodes of
+// pyr_decompose(a, len), and a down pass then pushes every node's word to the leaves it covers.  Work item t takes the
+// word of node t of level k+3 (already complete: the pass runs from the top), ORs in the nodes of levels k+2 and k+1
+// below it and adds the result to the 8 nodes [8t, 8t+8) of level k (dst); the nodes it read are cleared for the next
+// round.  Same grouping as pyr_build_group; a count of 0 = that level does not exist.
+template <int W>
+VGA_HD void pyr_down_group(unsigned long long *dst, int64_t cnt0, unsigned long long *s1, int64_t cnt1, unsigned long long *s2,
+                           int64_t cnt2, unsigned long long *s3, int64_t cnt3, int64_t t) {
+    unsigned long long a3[W], a2[2][W], a1[4][W];
+#pragma unroll
+    for (int j = 0; j < W; j++) {
+        a3[j] = 0ULL;
+        if (t < cnt3) {
+            a3[j] = s3[t * W + j];
+            if (a3[j]) s3[t * W + j] = 0ULL;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < W; j++) {
+            a2[i][j] = a3[j];
+            if (2 * t + i < cnt2) {
+                const unsigned long long v = s2[(2 * t + i) * W + j];
+                if (v) s2[(2 * t + i) * W + j] = 0ULL;
+                a2[i][j] |= v;
+            }
+        }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < W; j++) {
+            a1[i][j] = a2[i >> 1][j];
+            if (4 * t + i < cnt1) {
+                const unsigned long long v = s1[(4 * t + i) * W + j];
+                if (v) s1[(4 * t + i) * W + j] = 0ULL;
+                a1[i][j] |= v;
+            }
+        }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int64_t idx = 8 * t + i;
+        if (idx < cnt0) {
+#pragma unroll
+            for (int j = 0; j < W; j++)
+                if (a1[i >> 1][j]) dst[idx * W + j] |= a1[i >> 1][j];
+        }
+    }
+}
+
 // number of pyramid loads a query of [a, a+len) costs (the pull step's work estimate)
 VGA_HD int pyr_cost(uint32_t a, uint32_t len) {
     return pyr_decompose(a, len, [](int, uint32_t) {});

@@ -119,6 +119,9 @@ struct Options {
     int64_t bfs_coarse = 1;      // 1: coarse pass (64 group lower bounds per bit-parallel batch) prunes the pull step
     int64_t bfs_push_unroll = 1; // adjacency entries per lane and round in the top-down step: 1 (default) or 4 (EXPERIMENTAL,
                                  // opt-in, not yet run on a GPU: more loads in flight per lane)
+    int64_t bfs_push = 0;        // top-down step: 0 = adjacency entries (k_push); 1 = additionally range-OR updates over the
+                                 // runs of the out-rows through a pyramid of `next` (k_push_pyr + k_pyr_down) whenever the
+                                 // per-batch cost model prefers them (EXPERIMENTAL, opt-in; validated under SIMT emulation)
     int64_t bfs_pull = 0;        // bottom-up step: 0 scans in-row entries (k_pull); 1 = range-OR queries over an
                                  // OR-pyramid of the frontier with run-length in-rows (k_pull_pyr; EXPERIMENTAL, opt-in,
                                  // index logic unit-tested on CPU, kernels not yet run on a GPU)
@@ -186,6 +189,12 @@ struct vga_graph {
     vga::DevBuf<uint64_t> t_costptr; // [n+1]
     bool has_runs = false;
     int64_t t_nruns = 0;
+    // run-length out-rows for the pyramid push (bfs_push = 1), ghost columns excluded
+    vga::DevBuf<uint64_t> f_runptr;
+    vga::DevBuf<uint2> f_runs;
+    vga::DevBuf<uint64_t> f_costptr;
+    bool has_fwd_runs = false;
+    int64_t f_nruns = 0;
 };
 
 namespace vga {
@@ -194,6 +203,7 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *g, int64_t src_begin, int64_t src
 // bfs.cu
 int ensure_transpose(vga_ctx *ctx, vga_graph *g);
 int ensure_runs(vga_ctx *ctx, vga_graph *g);
+int ensure_fwd_runs(vga_ctx *ctx, vga_graph *g);
 // cabi.cu: per-segment ascending sort of 32-bit keys (cub::DeviceSegmentedSort in slices of < 2^31 entries)
 int sort_segments_u32(vga_ctx *ctx, uint32_t *keys_in, uint32_t *keys_out, int64_t entries, int64_t rows, const uint64_t *rowptr);
 // spatially coherent order of the sources [src_begin, src_end) for 64-source batches

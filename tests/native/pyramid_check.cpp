@@ -33,7 +33,40 @@ template <int W> int query(const u64 *fr, const std::vector<u64> &pyr, const Pyr
 }
 }  // namespace
 
+namespace {
+// range-OR updates through the pyramid + down pass (top chunk first), as the top-down step with run-length rows does it
+template <int W> int updates(int64_t n, const uint32_t *a, const uint32_t *len, const u64 *word, int64_t nu, u64 *leaves) {
+    PyrLayout L = vga::pyr_layout(n);
+    std::vector<u64> pyr((size_t)(L.total * W + 1), 0ULL);
+    for (int64_t q = 0; q < nu; q++)
+        vga::pyr_decompose(a[q], len[q], [&](int k, uint32_t i) {
+            u64 *p = k == 0 ? leaves + (int64_t)i * W : pyr.data() + (L.off[k] + (int64_t)i) * W;
+            for (int j = 0; j < W; j++) p[j] |= word[q * W + j];
+        });
+    int kmax = 0;
+    while (kmax + 3 + 1 < L.levels) kmax += 3;  // largest multiple of 3 with a level above it
+    for (int k = kmax; k >= 0; k -= 3) {
+        if (k + 1 >= L.levels) continue;
+        u64 *dst = k == 0 ? leaves : pyr.data() + L.off[k] * W;
+        auto lvl = [&](int kk) { return kk < L.levels ? pyr.data() + L.off[kk] * W : (u64 *)nullptr; };
+        auto cnt = [&](int kk) { return kk < L.levels ? L.cnt[kk] : (int64_t)0; };
+        const int64_t groups = (L.cnt[k] + 7) / 8;
+        for (int64_t t = 0; t < groups; t++)
+            vga::pyr_down_group<W>(dst, L.cnt[k], lvl(k + 1), cnt(k + 1), lvl(k + 2), cnt(k + 2), lvl(k + 3), cnt(k + 3), t);
+    }
+    for (int64_t i = 0; i < L.total * W; i++)
+        if (pyr[(size_t)i]) return -1;  // every node must have been cleared by the down pass
+    return 0;
+}
+}  // namespace
+
 extern "C" {
+
+// leaves[n*w] |= word[q] over [a[q], a[q]+len[q]) for every update q, done through pyramid nodes + the down pass
+int pyrchk_updates(int w, int64_t n, const uint32_t *a, const uint32_t *len, const u64 *word, int64_t nu, u64 *leaves) {
+    return w == 1 ? updates<1>(n, a, len, word, nu, leaves) : w == 2 ? updates<2>(n, a, len, word, nu, leaves)
+                                                                     : updates<4>(n, a, len, word, nu, leaves);
+}
 
 int pyrchk_layout(int64_t n, int64_t *cnt, int64_t *off, int64_t *total) {
     PyrLayout L = vga::pyr_layout(n);

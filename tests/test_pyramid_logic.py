@@ -19,6 +19,7 @@ def lib(tmp_path_factory):
                            os.path.join(ROOT, "tests", "native", "pyramid_check.cpp")])
     L = C.CDLL(so)
     L.pyrchk_layout.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pyrchk_updates.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     L.pyrchk_queries.argtypes = [C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     return L
 
@@ -57,3 +58,21 @@ def test_range_or_equals_brute_force(lib, w):
             want = np.bitwise_or.reduce(fr[a[q]:a[q] + ln[q]], axis=0)
             assert np.array_equal(out[q], want), (n, int(a[q]), int(ln[q]))
             assert loads[q] <= 2 * max(1, int(np.ceil(np.log2(ln[q] + 1)))) + 2
+
+
+@pytest.mark.parametrize("w", [1, 2, 4])
+def test_range_or_updates_equal_brute_force(lib, w):
+    """Top-down direction: words ORed into the nodes of a range, then the down pass (pyr_down_group, top chunk first)."""
+    rng = np.random.default_rng(10 + w)
+    for n in [1, 2, 3, 5, 8, 9, 64, 65, 100, 511, 512, 513, 1000, 4099]:
+        nu = 1 if n < 4 else 200
+        a = rng.integers(0, n, nu).astype(np.uint32)
+        ln = np.minimum(rng.integers(1, max(2, n), nu), n - a).astype(np.uint32)
+        word = rng.integers(1, 2 ** 63, (nu, w), dtype=np.uint64) & rng.integers(1, 2 ** 63, (nu, w), dtype=np.uint64)
+        pre = np.where(rng.random((n, w)) < 0.1, rng.integers(1, 2 ** 63, (n, w), dtype=np.uint64), np.uint64(0)).astype(np.uint64)
+        leaves = pre.copy()
+        assert lib.pyrchk_updates(w, n, a.ctypes.data, ln.ctypes.data, word.ctypes.data, nu, leaves.ctypes.data) == 0
+        want = pre.copy()
+        for q in range(nu):
+            want[a[q]:a[q] + ln[q]] |= word[q]
+        assert np.array_equal(leaves, want), n

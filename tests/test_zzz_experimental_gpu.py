@@ -65,6 +65,45 @@ def test_unrolled_push_vs_oracle(name, mode, words):
     c.close()
 
 
+@pytest.mark.parametrize("name", ["oblique:30:30:7", "office:64:64:1", "urban:120:120:4"])
+@pytest.mark.parametrize("radius", [-1, 2])
+@pytest.mark.parametrize("push,pull,mode,words", [(2, 0, 0, 1), (2, 0, 2, 2), (2, 1, 2, 4), (1, 1, 2, 0), (1, 0, 2, 1)])
+def test_pyramid_push_vs_oracle(name, radius, push, pull, mode, words):
+    """bfs_push: top-down step as range-OR updates over the runs of the out-rows through a pyramid of `next`
+    (k_push_pyr + k_pyr_down); 2 forces it for every top-down step after level 0, 1 lets the cost model choose."""
+    from oracle import pyoracle as po
+    flat = capi.prepare(plans.by_name(name))
+    og = po.OracleGraph(po.Grid(flat.cols, flat.rows, flat.spacing, flat.bl_x, flat.bl_y, flat.state, flat.line_off, flat.lines))
+    c = capi.Context(0)
+    for k, v in (("bfs_push", push), ("bfs_pull", pull), ("bfs_mode", mode), ("bfs_words", words)):
+        c.set_option(k, v)
+    g = c.build(flat)
+    tn, td, dist, used = g.global_ints(radius)
+    rng = np.random.RandomState(5)
+    for s in rng.choice(g.n, min(g.n, 96), replace=False):
+        otn, otd, odist, onl = og.global_ints(radius, (int(s), int(s) + 1), maxl=64)
+        L = dist.shape[1]
+        assert otn[0] == tn[s] and otd[0] == td[s]
+        assert np.array_equal(odist[0, :L], dist[s]) and not odist[0, L:].any()
+    c.close()
+
+
+def test_pyramid_paths_equal_default_on_c2():
+    """Full-size C2: pyramid push + pull together must give exactly the integers of the default schedule."""
+    flat = capi.prepare(plans.by_name("C2"))
+    a = capi.Context(0)
+    ref = a.build(flat).global_ints(-1)
+    a.close()
+    b = capi.Context(0)
+    b.set_option("bfs_pull", 1)
+    b.set_option("bfs_push", 1)
+    got = b.build(flat).global_ints(-1)
+    b.close()
+    assert ref[3] == got[3]
+    for x, y in zip(ref[:3], got[:3]):
+        assert np.array_equal(x, y)
+
+
 def test_pyramid_pull_equals_default_on_c2():
     """Full-size C2: the pyramid pull must give exactly the integers of the default schedule."""
     flat = capi.prepare(plans.by_name("C2"))
