@@ -14,7 +14,9 @@
 // NOT detected; memory is the host heap ("device" pointers are host pointers).
 #pragma once
 
+#if !defined(__x86_64__)
 #include <ucontext.h>
+#endif
 
 #include <algorithm>
 #include <chrono>
@@ -144,8 +146,39 @@ namespace simt {
 
 enum Op { OP_NONE, OP_BALLOT, OP_ANY, OP_SHFL, OP_SHFL_DOWN, OP_SHFL_UP, OP_RED_OR, OP_RED_ADD, OP_SYNCWARP, OP_SYNCTHREADS };
 
+// Fiber switch.  x86-64: a hand-written switch of the callee-saved registers and the stack pointer (glibc's swapcontext
+// makes a signal-mask system call per switch, which dominated the run time); elsewhere: ucontext.
+#if defined(__x86_64__)
+typedef void *Context;  // saved stack pointer
+extern "C" void simt_switch(Context *save, Context load);
+asm(R"(
+.text
+.weak simt_switch
+.type simt_switch,@function
+simt_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size simt_switch,.-simt_switch
+)");
+#else
+typedef ucontext_t Context;
+#endif
+
 struct Lane {
-    ucontext_t ctx;
+    Context ctx;
     bool done = false, waiting = false;
     Op op = OP_NONE;
     unsigned mask = 0;
@@ -155,7 +188,7 @@ struct Lane {
 };
 
 struct Runtime {
-    ucontext_t sched;
+    Context sched;
     std::vector<Lane> lanes;
     std::vector<char> stacks;
     Lane *cur = nullptr;
@@ -170,10 +203,48 @@ constexpr size_t STACK = 256 * 1024;
 
 inline void *dyn_smem() { return R.dyn.data(); }
 
+inline void to_scheduler(Lane *me) {
+#if defined(__x86_64__)
+    simt_switch(&me->ctx, R.sched);
+#else
+    swapcontext(&me->ctx, &R.sched);
+#endif
+}
+inline void to_lane(Lane *l) {
+    R.cur = l;
+#if defined(__x86_64__)
+    simt_switch(&R.sched, l->ctx);
+#else
+    swapcontext(&R.sched, &l->ctx);
+#endif
+}
+
 inline void trampoline() {
     (*R.body)();
     R.cur->done = true;
     R.cur->waiting = false;
+#if defined(__x86_64__)
+    to_scheduler(R.cur);  // a finished fiber is never resumed
+    abort();
+#endif
+}
+
+inline void make_lane_context(Lane &l, char *stack, size_t size) {
+#if defined(__x86_64__)
+    // initial frame: six callee-saved registers, the entry point for `ret`, and a null return address for the entry
+    uintptr_t top = ((uintptr_t)stack + size) & ~(uintptr_t)15;
+    void **sp = (void **)top;
+    *--sp = nullptr;
+    *--sp = (void *)trampoline;
+    for (int i = 0; i < 6; i++) *--sp = nullptr;
+    l.ctx = (Context)sp;
+#else
+    getcontext(&l.ctx);
+    l.ctx.uc_stack.ss_sp = stack;
+    l.ctx.uc_stack.ss_size = size;
+    l.ctx.uc_link = &R.sched;
+    makecontext(&l.ctx, (void (*)())trampoline, 0);
+#endif
 }
 
 inline void resolve_warp(Lane *w, int count, bool &progress) {
@@ -246,11 +317,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem, const std::function<void(
                     l.waiting = false;
                     l.op = OP_NONE;
                     l.tid = uint3{(unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y)};
-                    getcontext(&l.ctx);
-                    l.ctx.uc_stack.ss_sp = R.stacks.data() + (size_t)t * STACK;
-                    l.ctx.uc_stack.ss_size = STACK;
-                    l.ctx.uc_link = &R.sched;
-                    makecontext(&l.ctx, (void (*)())trampoline, 0);
+                    make_lane_context(l, R.stacks.data() + (size_t)t * STACK, STACK);
                 }
                 for (;;) {
                     bool progress = false, alldone = true;
@@ -259,8 +326,7 @@ inline void launch(dim3 grid, dim3 block, size_t smem, const std::function<void(
                         if (l.done) continue;
                         alldone = false;
                         if (l.waiting) continue;
-                        R.cur = &l;
-                        swapcontext(&R.sched, &l.ctx);
+                        to_lane(&l);
                         progress = true;
                     }
                     if (alldone) break;
@@ -299,7 +365,7 @@ inline uint64_t collective(Op op, unsigned mask, uint64_t val, int arg) {
     me->val = val;
     me->arg = arg;
     me->waiting = true;
-    swapcontext(&me->ctx, &R.sched);
+    to_scheduler(me);
     return me->result;
 }
 
