@@ -145,6 +145,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (big workloads run by hand)")
     ap.add_argument("--cpu-bfs-sources", type=int, default=48)
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
+                    help="vga_ctx_set_option for our arm (e.g. --opt bfs_pull=1): A/B runs of opt-in kernels; recorded in config")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -213,6 +215,11 @@ def main():
 
     flat = capi.prepare(plan)  # host pre-steps (setGrid, blockLines, fill): not part of the hot path
     ctx = capi.Context(local_rank)
+    for kv in args.opt:
+        key, value = kv.split("=")
+        ctx.set_option(key, int(value))
+    if args.opt:
+        workload_desc["options"] = dict(kv.split("=") for kv in args.opt)
     dgrid = ctx.upload(flat)
     n = flat.n_filled
     lo, hi = multi.partition(n, world)[rank]
