@@ -46,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> None:
     if force or _newer(so, objs):
         subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", so] + objs)
     hsrc = [os.path.join(HOST, "pointmap.cpp"), os.path.join(HOST, "graphio.cpp"), os.path.join(HOST, "capi.cpp")]
-    hdeps = hsrc + [os.path.join(HOST, "pointmap.h"), os.path.join(HOST, "graphfile.h"), os.path.join(HOST, "geometry.h"),
+    hdeps = hsrc + [os.path.join(HOST, "pointmap.h"), os.path.join(HOST, "graphfile.h"), os.path.join(HOST, "merge_contract.h"), os.path.join(HOST, "geometry.h"),
                     os.path.join(HERE, "..", "include", "vga_host.h"), so]
     hso = os.path.join(LIB, "libvga_host.so")
     if force or _newer(hso, hdeps):

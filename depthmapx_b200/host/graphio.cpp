@@ -10,6 +10,7 @@
 #include <sstream>
 
 #include "graphfile.h"
+#include "merge_contract.h"
 #include "pointmap.h"
 
 namespace dmx {
@@ -569,65 +570,18 @@ void PointMap::contractedRows(Contracted &out) {
         throw RuntimeException("contractedRows: the map has no visibility graph");
     }
     // pairing: symmetric and exclusive, both cells filled
-    out.primary.resize((size_t)n);
     std::vector<int32_t> partner((size_t)n, -1);
     for (size_t c = 0; c < m_cols * m_rows; c++) {
         const Point &pt = m_points[c];
         if (!pt.filled()) continue;
         const int32_t v = ord[c];
-        out.primary[(size_t)v] = v;
         if (!pt.merged()) continue;
         const PixelRef m = pt.merge;
         if (!includes(m) || !getPoint(m).filled() || int(getPoint(m).merge) != int(PixelRef((int)(c / m_rows), (int)(c % m_rows))))
             throw RuntimeException("GPU path: merge links must pair filled cells symmetrically");
         partner[(size_t)v] = ord[(size_t)m.x * m_rows + (size_t)m.y];
     }
-    for (int64_t v = 0; v < n; v++)
-        if (partner[(size_t)v] >= 0) out.primary[(size_t)v] = std::min<int32_t>((int32_t)v, partner[(size_t)v]);
-    // for every merged cell: the contracted vertices with an edge to the cell itself (radiusCorrection)
-    out.merged_cells.clear();
-    std::vector<int32_t> slot((size_t)n, -1);
-    for (int64_t v = 0; v < n; v++)
-        if (partner[(size_t)v] > v) {
-            slot[(size_t)v] = (int32_t)out.merged_cells.size();
-            out.merged_cells.push_back((int32_t)v);
-            slot[(size_t)partner[(size_t)v]] = (int32_t)out.merged_cells.size();
-            out.merged_cells.push_back(partner[(size_t)v]);
-        }
-    std::vector<std::vector<int32_t>> ins(out.merged_cells.size());
-    for (int64_t u = 0; u < n; u++)
-        for (uint64_t e = rowptr[(size_t)u]; e < rowptr[(size_t)u + 1]; e++)
-            if (col[e] < (uint32_t)n && slot[col[e]] >= 0) ins[(size_t)slot[col[e]]].push_back(out.primary[(size_t)u]);
-    out.in_ptr.assign(1, 0);
-    out.in_list.clear();
-    for (auto &l : ins) {
-        std::sort(l.begin(), l.end());
-        l.erase(std::unique(l.begin(), l.end()), l.end());
-        out.in_list.insert(out.in_list.end(), l.begin(), l.end());
-        out.in_ptr.push_back(out.in_list.size());
-    }
-    // contracted rows: redirect every column to its primary, union the pair's rows into the primary, sort + unique
-    out.rowptr.assign(1, 0);
-    out.col.clear();
-    out.col.reserve(col.size());
-    std::vector<uint32_t> row;
-    for (int64_t v = 0; v < n; v++) {
-        row.clear();
-        if (out.primary[(size_t)v] == v) {
-            const int64_t members[2] = {v, partner[(size_t)v]};
-            for (int64_t u : members) {
-                if (u < 0) continue;
-                for (uint64_t e = rowptr[(size_t)u]; e < rowptr[(size_t)u + 1]; e++) {
-                    const uint32_t c = col[e];
-                    row.push_back(c < (uint32_t)n ? (uint32_t)out.primary[c] : c);
-                }
-            }
-            std::sort(row.begin(), row.end());
-            row.erase(std::unique(row.begin(), row.end()), row.end());
-        }
-        out.col.insert(out.col.end(), row.begin(), row.end());
-        out.rowptr.push_back(out.col.size());
-    }
+    contract_rows(n, rowptr.data(), col.data(), partner.data(), out);
 }
 
 void PointMap::radiusCorrection(int radius, LevelTo &level_to, int32_t *total_nodes, int64_t *total_depth, int32_t *dist,
@@ -635,34 +589,7 @@ void PointMap::radiusCorrection(int radius, LevelTo &level_to, int32_t *total_no
     if (radius < 1 || radius >= max_levels) return;
     Contracted c;
     contractedRows(c);
-    const int64_t n = c.n;
-    // transpose of the contracted adjacency (cells only: ghosts are never expanded)
-    std::vector<uint64_t> t_rowptr((size_t)n + 1, 0);
-    for (uint32_t x : c.col)
-        if (x < (uint32_t)n) t_rowptr[(size_t)x + 1]++;
-    for (int64_t v = 0; v < n; v++) t_rowptr[(size_t)v + 1] += t_rowptr[(size_t)v];
-    std::vector<uint32_t> t_col(t_rowptr[(size_t)n]);
-    std::vector<uint64_t> fill(t_rowptr.begin(), t_rowptr.end() - 1);
-    for (int64_t u = 0; u < n; u++)
-        for (uint64_t e = c.rowptr[(size_t)u]; e < c.rowptr[(size_t)u + 1]; e++)
-            if (c.col[e] < (uint32_t)n) t_col[fill[c.col[e]]++] = (uint32_t)u;
-    level_to.prepare(n, t_rowptr, t_col);
-    std::vector<int32_t> la, lb;
-    for (size_t k = 0; k + 1 < c.merged_cells.size(); k += 2) {
-        std::vector<int64_t> sa(c.in_list.begin() + (ptrdiff_t)c.in_ptr[k], c.in_list.begin() + (ptrdiff_t)c.in_ptr[k + 1]);
-        std::vector<int64_t> sb(c.in_list.begin() + (ptrdiff_t)c.in_ptr[k + 1], c.in_list.begin() + (ptrdiff_t)c.in_ptr[k + 2]);
-        if (sa.empty() || sb.empty()) continue;
-        level_to.run(sa, la);
-        level_to.run(sb, lb);
-        // a source other than the pair itself reaches the cell at level R iff its nearest in-neighbour of that very
-        // cell is at level R-1
-        for (int64_t s = 0; s < n; s++)
-            if (s != c.merged_cells[k] && la[(size_t)s] == radius - 1 && lb[(size_t)s] == radius - 1) {
-                total_nodes[(size_t)s] += 1;
-                total_depth[(size_t)s] += radius;
-                dist[(size_t)s * (size_t)max_levels + (size_t)radius] += 1;
-            }
-    }
+    radius_correction(c, radius, level_to, total_nodes, total_depth, dist, max_levels);
 }
 
 vga_graph *PointMap::analysisGraph(std::vector<int32_t> *primary) {

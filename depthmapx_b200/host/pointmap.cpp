@@ -533,12 +533,6 @@ static void check_supported(PointMap &map, const char *who) {
     if (!map.graph()) throw RuntimeException(std::string(who) + ": the map has no visibility graph (run sparkGraph2 first)");
 }
 
-// results of a merged pair's secondary cell = results of its primary (PointMap::contractedRows)
-template <typename T> static void copy_from_primary(const std::vector<int32_t> &primary, T *values, size_t width = 1) {
-    for (size_t v = 0; v < primary.size(); v++)
-        if ((size_t)primary[v] != v) std::copy(values + (size_t)primary[v] * width, values + ((size_t)primary[v] + 1) * width, values + v * width);
-}
-
 // vgavisualglobal.cpp:33-63 (columns), 131-193 (formulas, which value is written when), 214 (display)
 void VGAVisualGlobal::writeAttributes(PointMap &map, double radius, bool simple_version, const int32_t *nodes,
                                       const int64_t *depth, const int32_t *dist, int32_t maxl) {

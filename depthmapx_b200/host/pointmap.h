@@ -25,6 +25,7 @@
 
 #include "../../include/vga_b200.h"
 #include "geometry.h"
+#include "merge_contract.h"
 
 namespace dmx {
 
@@ -238,37 +239,14 @@ class PointMap {
     bool unmergePixel(PixelRef a);
     bool isPixelMerged(const PixelRef &a) const { return getPoint(a).merged(); }
     bool hasMerges() const;
-    // The adjacency the BFS analyses (global, step depth) run on when cells are merged.  In the reference a cell
-    // that is expanded also expands its merge partner and finalises it without counting it
-    // (vgavisualglobal.cpp:108-121, vgavisualglobaldepth.cpp:54-63), i.e. a merged pair behaves as ONE vertex that is
-    // reached at the smaller of the two levels and counted once.  Here the pair is contracted into
-    // its smaller-ordinal cell: that row becomes the union of both rows, every edge into either cell points at it,
-    // and the other cell keeps an empty row (never reached); `primary[v]` is the ordinal whose results cell v takes.
-    // With a radius limit there is one difference: cells AT the radius are counted but not expanded, so a pair whose
-    // two cells are BOTH reached at exactly that level (each through an edge of its own) counts twice in the
-    // reference.  `merged_cells` / `in_ptr` / `in_list` keep, for every merged cell, the contracted vertices with an
-    // edge to that very cell, from which VGAVisualGlobal::run derives this correction exactly (radiusCorrection).
-    struct Contracted {
-        int64_t n = 0, ghosts = 0;
-        std::vector<uint64_t> rowptr;
-        std::vector<uint32_t> col;
-        std::vector<int32_t> primary;
-        std::vector<int32_t> merged_cells;  // ordinals of all merged cells, pairs adjacent: (primary, secondary)*
-        std::vector<uint64_t> in_ptr;       // [merged_cells.size()+1]
-        std::vector<int32_t> in_list;       // contracted vertices whose (union) row holds the cell itself
-    };
+    // The adjacency the BFS analyses (global, step depth) run on when cells are merged: every merged pair contracted
+    // into its smaller-ordinal cell, see merge_contract.h.
+    typedef dmx::Contracted Contracted;
+    typedef dmx::LevelTo LevelTo;
     void contractedRows(Contracted &out);
     // graph() when nothing is merged, otherwise the contracted adjacency on the device (built on demand)
     vga_graph *analysisGraph(std::vector<int32_t> *primary = nullptr);
-    // For radius R: adds to the integers of the contracted BFS (all N sources) the second count of every pair whose
-    // cells are both first reached at level R: total_nodes += 1, total_depth += R, dist[R] += 1.  `level_to` returns,
-    // for a set of contracted vertices, the BFS level of every source TO that set (a BFS from the set over the
-    // transposed contracted adjacency; -1 = unreachable): vga_step_depth on the GPU, any BFS in the CPU tests.
-    struct LevelTo {
-        virtual ~LevelTo() {}
-        virtual void prepare(int64_t n, const std::vector<uint64_t> &t_rowptr, const std::vector<uint32_t> &t_col) = 0;
-        virtual void run(const std::vector<int64_t> &seeds, std::vector<int32_t> &level) = 0;
-    };
+    // radius-limited global analysis of a merged map: the at-the-radius second counts (merge_contract.h)
     void radiusCorrection(int radius, LevelTo &level_to, int32_t *total_nodes, int64_t *total_depth, int32_t *dist,
                           int32_t max_levels);
     // x-major packed PixelRefs of the filled cells (= attribute row keys once the graph is made)

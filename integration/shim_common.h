@@ -10,6 +10,7 @@
 #include "genlib/exceptions.h"
 #include "salalib/pointdata.h"
 #include "vga_b200.h"
+#include "merge_contract.h"  // depthmapx_b200/host: contraction of merged pairs, shared with the stand-alone host layer
 
 namespace vga_shim {
 
@@ -63,15 +64,100 @@ inline Ordinals make_ordinals(PointMap &map) {
     return o;
 }
 
-// adjacency of a made graph, flattened from the Nodes (Node::first/next iteration order)
+inline void set_refs(vga_graph *g, PointMap &map, const Ordinals &o) {
+    std::vector<int32_t> refs;
+    refs.reserve((size_t)(o.n + o.ghosts));
+    for (const PixelRef &p : o.cells) refs.push_back((int)p);
+    const size_t cols = map.getCols(), rows = map.getRows();
+    for (size_t i = 0; i < cols; i++)
+        for (size_t j = 0; j < rows; j++)
+            if (o.ord[i * rows + j] < 0) refs.push_back((int)PixelRef((short)i, (short)j));
+    vga_graph_set_cell_refs(g, refs.data(), (int64_t)refs.size());
+}
+
+// adjacency of a made graph, flattened from the Nodes (Node::first/next iteration order), as ordinal CSR
+inline void rows_from_nodes(PointMap &map, const Ordinals &o, std::vector<uint64_t> &rowptr, std::vector<uint32_t> &col) {
+    rowptr.assign((size_t)o.n + 1, 0);
+    col.clear();
+    const size_t rows = map.getRows();
+    for (int64_t v = 0; v < o.n; v++) {
+        Point &pt = map.getPoint(o.cells[(size_t)v]);
+        if (pt.contextfilled()) throw depthmapX::RuntimeException("GPU path: context-filled cells are not supported");
+        if (pt.hasNode()) {
+            Node &node = pt.getNode();
+            node.first();
+            while (!node.is_tail()) {
+                PixelRef w = node.cursor();
+                int32_t id = o.ord[(size_t)w.x * rows + (size_t)w.y];
+                col.push_back(id >= 0 ? (uint32_t)id : (uint32_t)(o.n + (-(id + 1))));
+                node.next();
+            }
+        }
+        rowptr[(size_t)v + 1] = col.size();
+    }
+}
+
+// The adjacency the BFS analyses run on: merged pairs contracted (merge_contract.h).  primary is empty when nothing is
+// merged; c is filled only then.
+inline vga_graph *analysis_graph(PointMap &map, const Ordinals &o, dmx::Contracted &c, std::vector<int32_t> &primary) {
+    std::vector<uint64_t> rowptr;
+    std::vector<uint32_t> col;
+    rows_from_nodes(map, o, rowptr, col);
+    const size_t rows = map.getRows();
+    std::vector<int32_t> partner((size_t)o.n, -1);
+    bool any = false;
+    for (int64_t v = 0; v < o.n; v++) {
+        Point &pt = map.getPoint(o.cells[(size_t)v]);
+        PixelRef m = pt.getMergePixel();
+        if (m.empty()) continue;
+        if (!map.includes(m) || !map.getPoint(m).filled() || map.getPoint(m).getMergePixel() != o.cells[(size_t)v])
+            throw depthmapX::RuntimeException("GPU path: merge links must pair filled cells symmetrically");
+        partner[(size_t)v] = o.ord[(size_t)m.x * rows + (size_t)m.y];
+        any = true;
+    }
+    primary.clear();
+    vga_graph *g = nullptr;
+    int rc;
+    if (any) {
+        dmx::contract_rows(o.n, rowptr.data(), col.data(), partner.data(), c);
+        c.ghosts = o.ghosts;
+        primary = c.primary;
+        rc = vga_graph_from_csr(gpu(), o.n, o.ghosts, c.rowptr.data(), c.col.data(), nullptr, &g);
+    } else {
+        rc = vga_graph_from_csr(gpu(), o.n, o.ghosts, rowptr.data(), col.data(), nullptr, &g);
+    }
+    if (rc != VGA_OK) throw depthmapX::RuntimeException(std::string("GPU path: ") + vga_last_error());
+    set_refs(g, map, o);
+    return g;
+}
+
+// level of every source to a vertex set = vga_step_depth from the set over the transposed adjacency
+struct GpuLevelTo : dmx::LevelTo {
+    vga_graph *graph = nullptr;
+    int64_t n = 0;
+    ~GpuLevelTo() override {
+        if (graph) vga_graph_free(graph);
+    }
+    void prepare(int64_t cells, const std::vector<uint64_t> &t_rowptr, const std::vector<uint32_t> &t_col) override {
+        n = cells;
+        if (vga_graph_from_csr(gpu(), n, 0, t_rowptr.data(), t_col.data(), nullptr, &graph) != VGA_OK)
+            throw depthmapX::RuntimeException(std::string("GPU path: ") + vga_last_error());
+    }
+    void run(const std::vector<int64_t> &seeds, std::vector<int32_t> &level) override {
+        level.assign((size_t)n, -1);
+        if (vga_step_depth(gpu(), graph, seeds.data(), (int64_t)seeds.size(), level.data()) != VGA_OK)
+            throw depthmapX::RuntimeException(std::string("GPU path: ") + vga_last_error());
+    }
+};
+
+// adjacency of a made graph as it is (local measures ignore merge links)
 inline vga_graph *graph_from_nodes(PointMap &map, const Ordinals &o) {
     std::vector<uint64_t> rowptr((size_t)o.n + 1, 0);
     std::vector<uint32_t> col;
     const size_t rows = map.getRows();
     for (int64_t v = 0; v < o.n; v++) {
         Point &pt = map.getPoint(o.cells[(size_t)v]);
-        if (!pt.getMergePixel().empty() || pt.contextfilled())
-            throw depthmapX::RuntimeException("GPU path: merged / context-filled cells are not supported");
+        if (pt.contextfilled()) throw depthmapX::RuntimeException("GPU path: context-filled cells are not supported");
         if (pt.hasNode()) {
             Node &node = pt.getNode();
             node.first();
@@ -87,14 +173,7 @@ inline vga_graph *graph_from_nodes(PointMap &map, const Ordinals &o) {
     vga_graph *g = nullptr;
     if (vga_graph_from_csr(gpu(), o.n, o.ghosts, rowptr.data(), col.data(), nullptr, &g) != VGA_OK)
         throw depthmapX::RuntimeException(std::string("GPU path: ") + vga_last_error());
-    std::vector<int32_t> refs;
-    refs.reserve((size_t)(o.n + o.ghosts));
-    for (const PixelRef &p : o.cells) refs.push_back((int)p);
-    const size_t cols = map.getCols();
-    for (size_t i = 0; i < cols; i++)
-        for (size_t j = 0; j < rows; j++)
-            if (o.ord[i * rows + j] < 0) refs.push_back((int)PixelRef((short)i, (short)j));
-    vga_graph_set_cell_refs(g, refs.data(), (int64_t)refs.size());
+    set_refs(g, map, o);
     return g;
 }
 

@@ -13,19 +13,22 @@ bool VGAVisualGlobalDepth::run(Communicator *, PointMap &map, bool) {
     AttributeTable &attributes = map.getAttributeTable();
     int col = attributes.insertOrResetColumn("Visual Step Depth");
     Ordinals o = make_ordinals(map);
-    vga_graph *gr = graph_from_nodes(map, o);
+    dmx::Contracted contracted;
+    std::vector<int32_t> primary;  // merge links: a pair is one vertex (vgavisualglobaldepth.cpp:54-63)
+    vga_graph *gr = analysis_graph(map, o, contracted, primary);
     const size_t rows = map.getRows();
     std::vector<int64_t> sources;
     for (auto &sel : map.getSelSet()) {
         PixelRef p = sel;
         if (!map.includes(p)) continue;
         int32_t id = o.ord[(size_t)p.x * rows + (size_t)p.y];
-        if (id >= 0) sources.push_back(id);
+        if (id >= 0) sources.push_back(primary.empty() ? id : primary[(size_t)id]);
     }
     std::vector<int32_t> depth((size_t)o.n, -1);
     int rc = vga_step_depth(gpu(), gr, sources.data(), (int64_t)sources.size(), depth.data());
     vga_graph_free(gr);
     if (rc != VGA_OK) throw depthmapX::RuntimeException(std::string("GPU step depth: ") + vga_last_error());
+    dmx::copy_from_primary(primary, depth.data());
     for (int64_t v = 0; v < o.n; v++)
         if (depth[(size_t)v] >= 0) attributes.getRow(AttributeKey(o.cells[(size_t)v])).setValue(col, float(depth[(size_t)v]));
     map.setDisplayedAttribute(-2);

@@ -11,7 +11,6 @@
 
 bool VGAVisualGlobal::run(Communicator *comm, PointMap &map, bool simple_version) {
     using namespace vga_shim;
-    if (m_gates_only) throw depthmapX::RuntimeException("GPU path: gates_only is not supported");
     CommState cs{comm, 0};
     if (comm) {
         qtimer(cs.atime, 0);
@@ -32,8 +31,14 @@ bool VGAVisualGlobal::run(Communicator *comm, PointMap &map, bool simple_version
         rel_entropy_col = attributes.insertOrResetColumn("Visual Relativised Entropy" + radius_text);
     }
 
+    if (m_gates_only) {  // the reference skips every cell (vgavisualglobal.cpp:75-78): columns only
+        map.setDisplayedAttribute(integ_dv_col);
+        return true;
+    }
     Ordinals o = make_ordinals(map);
-    vga_graph *gr = graph_from_nodes(map, o);
+    dmx::Contracted contracted;
+    std::vector<int32_t> primary;  // merge links: results of a pair's secondary cell are its primary's
+    vga_graph *gr = analysis_graph(map, o, contracted, primary);
     const int64_t N = o.n;
     std::vector<int32_t> nodes((size_t)N);
     std::vector<int64_t> depth((size_t)N);
@@ -54,6 +59,15 @@ bool VGAVisualGlobal::run(Communicator *comm, PointMap &map, bool simple_version
     vga_graph_free(gr);
     if (rc == VGA_ERR_CANCELLED) throw Communicator::CancelledException();
     if (rc != VGA_OK) throw depthmapX::RuntimeException(std::string("GPU VGA global: ") + vga_last_error());
+    if (!primary.empty()) {
+        if ((int)m_radius != -1) {
+            GpuLevelTo level_to;
+            dmx::radius_correction(contracted, (int)m_radius, level_to, nodes.data(), depth.data(), dist.data(), maxl);
+        }
+        dmx::copy_from_primary(primary, nodes.data());
+        dmx::copy_from_primary(primary, depth.data());
+        dmx::copy_from_primary(primary, dist.data(), (size_t)maxl);
+    }
 
     std::vector<float> nc((size_t)N), md((size_t)N), hh((size_t)N), pv((size_t)N), tk((size_t)N), en((size_t)N), re((size_t)N);
     vga_global_attributes(N, nodes.data(), depth.data(), dist.data(), maxl, nc.data(), md.data(), hh.data(), pv.data(),
@@ -85,13 +99,16 @@ bool VGAVisualGlobal::run(Communicator *comm, PointMap &map, bool simple_version
 
 bool VGAVisualLocal::run(Communicator *comm, PointMap &map, bool simple_version) {
     using namespace vga_shim;
-    if (m_gates_only) throw depthmapX::RuntimeException("GPU path: gates_only is not supported");
     if (comm) comm->CommPostMessage(Communicator::NUM_RECORDS, map.getFilledPointCount());
     int cluster_col = -1, control_col = -1, controllability_col = -1;
     if (!simple_version) {
         cluster_col = map.getAttributeTable().insertOrResetColumn("Visual Clustering Coefficient");
         control_col = map.getAttributeTable().insertOrResetColumn("Visual Control");
         controllability_col = map.getAttributeTable().insertOrResetColumn("Visual Controllability");
+    }
+    if (m_gates_only) {  // vgavisuallocal.cpp:43-46
+        if (!simple_version) map.setDisplayedAttribute(cluster_col);
+        return true;
     }
     Ordinals o = make_ordinals(map);
     vga_graph *gr = graph_from_nodes(map, o);

@@ -132,3 +132,23 @@ def test_cli_stepdepth_shim(files, tmp_path, case):
                         "-sdt", "visual"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert data(out) == data(os.path.join(d, f"{case}__sd.graph"))
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_cli_shims_on_linked_graph(files, tmp_path, case):
+    """The real depthmapXcli with the GPU shims on a map with merge links (-m LINK): VGA global radius n + local, global
+    radius 2 (at-the-radius correction) and visual step depth must write the reference's bytes."""
+    import subprocess
+    from conftest import ROOT
+    gpu_cli = os.path.join(ROOT, "oracle", "_ref", "depthmapXcli_gpu")
+    if not os.path.exists(gpu_cli):
+        pytest.skip("integration binaries not built (make -C integration)")
+    d, args = files
+    src = os.path.join(d, f"{case}__prep_l.graph")
+    out = str(tmp_path / "o.graph")
+    for extra, want in ((["-m", "VGA", "-vm", "visibility", "-vg", "-vl", "-vr", "n"], "vga_l"),
+                        (["-m", "VGA", "-vm", "visibility", "-vg", "-vr", "2"], "vga_l2"),
+                        (["-m", "STEPDEPTH", "-sdp", args[case][3], "-sdt", "visual"], "sd_l")):
+        r = subprocess.run([gpu_cli, "-f", src, "-o", out] + extra, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert data(out) == data(os.path.join(d, f"{case}__{want}.graph")), want
