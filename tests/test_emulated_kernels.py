@@ -114,7 +114,7 @@ def test_graphfile_pipelines_merges_and_cli_shim(emu_dir):
 
 def test_experimental_kernels(emu_dir):
     """local_mode = 3 (bit-sliced counters), bfs_pull = 1 (pyramid pull), bfs_push_unroll = 4 on the small plans."""
-    run_gpu_tests_emulated(emu_dir, ["tests/test_zzz_experimental_gpu.py", "-k", "oblique"])
+    run_gpu_tests_emulated(emu_dir, ["tests/test_zzzz_experimental_gpu.py", "-k", "oblique"])
 
 
 def test_real_cli_with_gpu_shims(emu_dir):
