@@ -414,3 +414,19 @@ def test_properties_c4_radius_truncates(ctx):
     assert np.array_equal(dist3[:, :3], dist[:, :3])
     assert (dist.sum(axis=1) == tn).all() and (dist3.sum(axis=1) == tn3).all()
     g.free()
+
+
+@pytest.mark.parametrize("words,chunk", [(1, 2), (2, 4), (0, 3)])
+def test_global_in_several_chunks(words, chunk):
+    """The batches of one call processed in several chunks (as at C5 scale, where the BFS state of all batches does not
+    fit at once): per-chunk state, statistics and the early retirement of finished batches must not leak across chunks."""
+    flat, og = cached_oracle("oblique:30:30:7")
+    c = capi.Context(0)
+    c.set_option("bfs_words", words)
+    c.set_option("bfs_chunk", chunk)
+    g = c.build(flat)
+    for radius in (-1, 2):
+        tn, td, dist, used = g.global_ints(radius)
+        otn, otd, odist, onl = og.global_ints(radius, maxl=dist.shape[1])
+        assert np.array_equal(tn, otn) and np.array_equal(td, otd) and np.array_equal(dist, odist)
+    c.close()
