@@ -110,6 +110,25 @@ template <int W> __device__ __forceinline__ void stw(u64 *p, const u64 (&o)[W]) 
     }
 }
 
+// 32 x 32 bit-matrix transpose across a warp: lane l passes row l and receives column l (bit i = bit l of lane i's
+// row), five butterfly stages of one shuffle each.  popc of the result = how many lanes had bit l set.
+__device__ __forceinline__ unsigned warp_transpose32(unsigned x, int lane) {
+    const unsigned masks[5] = {0x0000ffffu, 0x00ff00ffu, 0x0f0f0f0fu, 0x33333333u, 0x55555555u};
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        const int j = 16 >> s;
+        const unsigned m = masks[s];
+        const unsigned y = __shfl_xor_sync(FULL, x, j);
+        if (lane & j) {
+            x ^= ((y >> j) ^ x) & m;
+        } else {
+            x ^= (((x >> j) ^ y) & m) << j;
+        }
+    }
+    return x;
+}
+constexpr int DENSE_COLUMNS = 8;  // from this many non-empty bit columns on, transpose + popc beats one ballot per column
+
 // source i of the ordered list -> bit (i & 63) of word (i >> 6); word wi lives in batch wi / W, slot wi % W
 template <int W> __global__ void k_init(BfsDev d, const int32_t *src, int64_t nsrc) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -554,19 +573,31 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[bat
         }
 #pragma unroll
         for (int j = 0; j < W; j++) {
-            unsigned lo_any = __reduce_or_sync(FULL, (unsigned)nw[j]);
-            unsigned hi_any = __reduce_or_sync(FULL, (unsigned)(nw[j] >> 32));
-            while (lo_any) {
-                int bit = __ffs(lo_any) - 1;
-                lo_any &= lo_any - 1;
-                int c = __popc(__ballot_sync(FULL, (nw[j] >> bit) & 1ULL));
-                if (lane == bit) cnt[j][0] += c;
+            // new vertices per source: column sums of the warp's 32 x 64 bit matrix.  Few non-empty columns (late
+            // levels): one ballot per column; many (a coherent batch reaching a vertex with most of its sources at
+            // once): transpose the two 32 x 32 halves and popc.
+            const unsigned lo = (unsigned)nw[j], hi = (unsigned)(nw[j] >> 32);
+            unsigned lo_any = __reduce_or_sync(FULL, lo);
+            unsigned hi_any = __reduce_or_sync(FULL, hi);
+            if (__popc(lo_any) >= DENSE_COLUMNS) {
+                cnt[j][0] += __popc(warp_transpose32(lo, lane));
+            } else {
+                while (lo_any) {
+                    int bit = __ffs(lo_any) - 1;
+                    lo_any &= lo_any - 1;
+                    int c = __popc(__ballot_sync(FULL, (lo >> bit) & 1u));
+                    if (lane == bit) cnt[j][0] += c;
+                }
             }
-            while (hi_any) {
-                int bit = __ffs(hi_any) - 1;
-                hi_any &= hi_any - 1;
-                int c = __popc(__ballot_sync(FULL, (nw[j] >> (bit + 32)) & 1ULL));
-                if (lane == bit) cnt[j][1] += c;
+            if (__popc(hi_any) >= DENSE_COLUMNS) {
+                cnt[j][1] += __popc(warp_transpose32(hi, lane));
+            } else {
+                while (hi_any) {
+                    int bit = __ffs(hi_any) - 1;
+                    hi_any &= hi_any - 1;
+                    int c = __popc(__ballot_sync(FULL, (hi >> bit) & 1u));
+                    if (lane == bit) cnt[j][1] += c;
+                }
             }
         }
     }

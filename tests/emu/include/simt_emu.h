@@ -144,7 +144,7 @@ template <typename F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribu
 // ---------------------------------------------------------------------------------------------- SIMT core
 namespace simt {
 
-enum Op { OP_NONE, OP_BALLOT, OP_ANY, OP_SHFL, OP_SHFL_DOWN, OP_SHFL_UP, OP_RED_OR, OP_RED_ADD, OP_SYNCWARP, OP_SYNCTHREADS };
+enum Op { OP_NONE, OP_BALLOT, OP_ANY, OP_SHFL, OP_SHFL_DOWN, OP_SHFL_UP, OP_SHFL_XOR, OP_RED_OR, OP_RED_ADD, OP_SYNCWARP, OP_SYNCTHREADS };
 
 // Fiber switch.  x86-64: a hand-written switch of the callee-saved registers and the stack pointer (glibc's swapcontext
 // makes a signal-mask system call per switch, which dominated the run time); elsewhere: ucontext.
@@ -281,6 +281,7 @@ inline void resolve_warp(Lane *w, int count, bool &progress) {
             case OP_SHFL: { int s = w[l].arg & 31; res[l] = in(s) ? w[s].val : w[l].val; break; }
             case OP_SHFL_DOWN: { int s = l + w[l].arg; res[l] = (s < 32 && in(s)) ? w[s].val : w[l].val; break; }
             case OP_SHFL_UP: { int s = l - w[l].arg; res[l] = (s >= 0 && in(s)) ? w[s].val : w[l].val; break; }
+            case OP_SHFL_XOR: { int s = (l ^ w[l].arg) & 31; res[l] = in(s) ? w[s].val : w[l].val; break; }
             default: res[l] = 0;
             }
         }
@@ -400,6 +401,9 @@ template <typename T> inline T __shfl_down_sync(unsigned mask, T v, unsigned del
 }
 template <typename T> inline T __shfl_up_sync(unsigned mask, T v, unsigned delta, int = 32) {
     return simt::from_bits<T>(simt::collective(simt::OP_SHFL_UP, mask, simt::to_bits(v), (int)delta));
+}
+template <typename T> inline T __shfl_xor_sync(unsigned mask, T v, int lanemask, int = 32) {
+    return simt::from_bits<T>(simt::collective(simt::OP_SHFL_XOR, mask, simt::to_bits(v), lanemask));
 }
 inline unsigned __reduce_or_sync(unsigned mask, unsigned v) { return (unsigned)simt::collective(simt::OP_RED_OR, mask, v, 0); }
 inline unsigned __reduce_add_sync(unsigned mask, unsigned v) { return (unsigned)simt::collective(simt::OP_RED_ADD, mask, v, 0); }
