@@ -192,13 +192,17 @@ template <int W, int U> __global__ void __launch_bounds__(TPB) k_push(BfsDev d) 
             if constexpr (U == 1) {
                 for (uint64_t e = e0 + lane; e < e1; e += 32) {
                     uint32_t c = d.adj[e] >> 6;
+                    VGA_COUNT(push_entries, 1);
                     if (c < (uint32_t)d.n) {
                         u64 vv[W];
                         ldw<W>(vis + (int64_t)c * W, vv);
 #pragma unroll
                         for (int j = 0; j < W; j++) {
                             u64 add = fw[j] & ~vv[j];
-                            if (add) atomicOr(&nx[(int64_t)c * W + j], add);
+                            if (add) {
+                                atomicOr(&nx[(int64_t)c * W + j], add);
+                                VGA_COUNT(push_atomics, 1);
+                            }
                         }
                     }
                 }
@@ -290,6 +294,7 @@ template <int W> __global__ void __launch_bounds__(TPB) k_pull(BfsDev d, int lev
                     uint32_t ca = 0, cb = 0;
                     if (ea < e1) ca = d.t_col[ea];
                     if (eb < e1) cb = d.t_col[eb];
+                    VGA_COUNT(pull_entries, (ea < e1) + (eb < e1));
                     if (ea < e1) ldw<W>(fr + (int64_t)ca * W, g0);
                     if (eb < e1) ldw<W>(fr + (int64_t)cb * W, g1);
                     bool done = true;
@@ -354,14 +359,19 @@ template <int W> __global__ void __launch_bounds__(TPB) k_push_pyr(BfsDev d) {
             uint64_t r0 = __shfl_sync(FULL, my0, src_lane), r1 = __shfl_sync(FULL, my1, src_lane);
             for (uint64_t r = r0 + lane; r < r1; r += 32) {
                 const uint2 run = d.f_runs[r];
+                VGA_COUNT(ppush_runs, 1);
                 pyr_decompose(run.x, run.y, [&](int kk, uint32_t i) {
                     u64 *p = kk == 0 ? nx + (int64_t)i * W : np + (d.pyr_off[kk] + (int64_t)i) * W;
                     u64 cur[W];
+                    VGA_COUNT(ppush_nodes, 1);
                     ldw<W>(kk == 0 ? vis + (int64_t)i * W : p, cur);  // leaf: reached sources; node: bits already there
 #pragma unroll
                     for (int j = 0; j < W; j++) {
                         u64 add = fw[j] & ~cur[j];
-                        if (add) atomicOr(&p[j], add);
+                        if (add) {
+                            atomicOr(&p[j], add);
+                            VGA_COUNT(ppush_atomics, 1);
+                        }
                     }
                 });
             }
@@ -381,8 +391,10 @@ template <int W> __global__ void __launch_bounds__(TPB) k_pyr_down(BfsDev d, int
     const int64_t c0 = d.pyr_cnt[k];
     const int64_t c1 = s1 ? d.pyr_cnt[k + 1] : 0, c2 = s2 ? d.pyr_cnt[k + 2] : 0, c3 = s3 ? d.pyr_cnt[k + 3] : 0;
     const int64_t groups = (c0 + 7) / 8;
-    for (int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x; t < groups; t += (int64_t)gridDim.x * TPB)
+    for (int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x; t < groups; t += (int64_t)gridDim.x * TPB) {
+        VGA_COUNT(pyr_down_groups, 1);
         pyr_down_group<W>(dst, c0, s1, c1, s2, c2, s3, c3, t);
+    }
 }
 
 // ---- pyramid pull (bfs_pull = 1, see pyramid.cuh) -----------------------------------------------------------
@@ -400,8 +412,10 @@ template <int W> __global__ void __launch_bounds__(TPB) k_pyr_build(BfsDev d, in
     const int64_t c0 = d.pyr_cnt[k];
     const int64_t c1 = d1 ? d.pyr_cnt[k + 1] : 0, c2 = d2 ? d.pyr_cnt[k + 2] : 0, c3 = d3 ? d.pyr_cnt[k + 3] : 0;
     const int64_t groups = (c0 + 7) / 8;
-    for (int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x; t < groups; t += (int64_t)gridDim.x * TPB)
+    for (int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x; t < groups; t += (int64_t)gridDim.x * TPB) {
+        VGA_COUNT(pyr_build_groups, 1);
         pyr_build_group<W>(src, c0, d1, c1, d2, c2, d3, c3, t);
+    }
 }
 
 // bottom-up step over run-length in-rows: candidates as in k_pull (4 groups of 8 lanes per warp, one vertex per
@@ -461,7 +475,9 @@ template <int W> __global__ void __launch_bounds__(TPB) k_pull_pyr(BfsDev d, int
                     for (int j = 0; j < W; j++) g[j] = 0ULL;
                     if (e + gl < e1) {
                         const uint2 run = d.t_runs[e + gl];
+                        VGA_COUNT(ppull_runs, 1);
                         pyr_decompose(run.x, run.y, [&](int kk, uint32_t i) {
+                            VGA_COUNT(ppull_nodes, 1);
                             const u64 *p = kk == 0 ? fr + (int64_t)i * W : pyr + (d.pyr_off[kk] + (int64_t)i) * W;
                             u64 t[W];
                             ldw<W>(p, t);
@@ -523,6 +539,7 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[bat
 #pragma unroll
         for (int j = 0; j < W; j++) nw[j] = 0ULL;
         if (v < d.n) {
+            VGA_COUNT(update_words, 1);
             u64 vv[W], xx[W];
             ldw<W>(vis + v * W, vv);
             ldw<W>(nx + v * W, xx);

@@ -10,6 +10,13 @@
 
 #include "../../include/vga_b200.h"
 
+// Work counters of the CPU emulation used by the tests (tests/emu/): nothing in the CUDA build.
+#ifdef VGA_SIMT_EMULATION
+#define VGA_COUNT(name, n) (simt::counters()[#name] += (long long)(n))
+#else
+#define VGA_COUNT(name, n) ((void)0)
+#endif
+
 namespace vga {
 
 void set_error(const std::string &msg);

@@ -26,6 +26,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
+#include <string>
 #include <vector>
 
 #define __global__
@@ -383,6 +385,23 @@ template <typename T> inline T from_bits(uint64_t b) {
 }
 
 }  // namespace simt
+
+// Work counters: VGA_COUNT(name, n) in kernel code (a no-op in the CUDA build, csrc/vga_dev.cuh) adds n to a named counter
+// here, so that an emulated run reports how many adjacency entries / pyramid nodes / atomics a schedule really touches.
+namespace simt {
+inline std::map<std::string, long long> &counters() {
+    static std::map<std::string, long long> c;
+    return c;
+}
+}  // namespace simt
+extern "C" __attribute__((used, weak)) const char *simt_counters_dump(int reset) {
+    static std::string out;
+    out = "{";
+    for (auto &kv : simt::counters()) out += (out.size() > 1 ? ", \"" : "\"") + kv.first + "\": " + std::to_string(kv.second);
+    out += "}";
+    if (reset) simt::counters().clear();
+    return out.c_str();
+}
 
 #define threadIdx (simt::R.cur->tid)
 #define blockIdx (simt::R.bidx)
