@@ -35,6 +35,7 @@ static int set_option(Options &o, const std::string &key, int64_t value) {
     else if (key == "sieve_big_gcap") o.sieve_big_gcap = value;
     else if (key == "sieve_big_bcap") o.sieve_big_bcap = value;
     else if (key == "build_chunk_entries") o.build_chunk_entries = value;
+    else if (key == "build_sort") o.build_sort = value;
     else if (key == "pull_alpha") o.pull_alpha = value;
     else if (key == "pull_beta") o.pull_beta = value;
     else if (key == "bfs_order") o.bfs_order = value;

@@ -1020,6 +1020,62 @@ __global__ void k_make_keys(GridDev g, const uint32_t *e_ref, const uint8_t *e_b
     keys[e] = (col << 6) | ((b & 0x80) ? 0u : 32u) | (uint32_t)(b & 31);
 }
 
+// Opt-in replacement of the segmented radix sort (build_sort = 1): a row is a SET of vertex numbers below `total`, so
+// its sorted order follows from a bitmap of the row -- rank(col) = number of set bits below col.  One CTA per row: set
+// the bits in shared memory, popc-sum groups of 32 words, scan the group sums, then every entry looks its rank up
+// (group prefix + at most 31 word popcs + one masked popc) and is written to its final place.  O(total/32 + deg) per
+// row instead of four radix passes over small segments.  Needs unique columns per row (the sieve's de-duplication rule
+// guarantees it).  Shared memory: total/32 words + total/1024 group prefixes.
+constexpr int RS_TPB = 256;
+__global__ void __launch_bounds__(RS_TPB) k_rank_sort(const uint32_t *keys, const uint64_t *seg_off, int64_t nrows, uint32_t total,
+                                                      uint32_t *out) {
+    extern __shared__ __align__(16) uint32_t rs_smem[];
+    const uint32_t nw = (total + 31u) >> 5, ng = (nw + 31u) >> 5;
+    uint32_t *bm = rs_smem, *gpre = rs_smem + nw;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = RS_TPB / 32;
+    for (int64_t row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const uint64_t e0 = seg_off[row], e1 = seg_off[row + 1];
+        for (uint32_t w = threadIdx.x; w < nw; w += RS_TPB) bm[w] = 0u;
+        __syncthreads();
+        for (uint64_t e = e0 + threadIdx.x; e < e1; e += RS_TPB) {
+            const uint32_t col = keys[e] >> 6;
+            atomicOr(&bm[col >> 5], 1u << (col & 31u));
+        }
+        __syncthreads();
+        for (uint32_t g = warp; g < ng; g += nwarps) {  // popcount of every group of 32 words
+            const uint32_t w = g * 32u + lane;
+            const unsigned c = __reduce_add_sync(0xffffffffu, (unsigned)(w < nw ? __popc(bm[w]) : 0));
+            if (lane == 0) gpre[g] = c;
+        }
+        __syncthreads();
+        if (warp == 0) {  // exclusive scan of the group sums: every lane a contiguous slice, then a warp scan of the slices
+            const uint32_t per = (ng + 31u) >> 5, b0 = lane * per, b1 = min(b0 + per, ng);
+            unsigned mine = 0;
+            for (uint32_t g = b0; g < b1; g++) mine += gpre[g];
+            unsigned incl = mine;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            unsigned run = incl - mine;
+            for (uint32_t g = b0; g < b1; g++) {
+                const unsigned c = gpre[g];
+                gpre[g] = run;
+                run += c;
+            }
+        }
+        __syncthreads();
+        for (uint64_t e = e0 + threadIdx.x; e < e1; e += RS_TPB) {
+            const uint32_t key = keys[e], col = key >> 6, w = col >> 5;
+            unsigned rank = gpre[w >> 5];
+            for (uint32_t k = w & ~31u; k < w; k++) rank += (unsigned)__popc(bm[k]);
+            rank += (unsigned)__popc(bm[w] & ((1u << (col & 31u)) - 1u));
+            out[e0 + rank] = key;
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void k_rebase(const uint64_t *in, int64_t n, uint64_t base, uint64_t *out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i] - base;
@@ -1299,13 +1355,22 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t sr
             tm.launches++;
             k_rebase<<<blocks_for(ns + 1, 256), 256, 0, st>>>(row_off.p + i, ns + 1, base, seg_off.p);
             tm.launches++;
-            size_t tb = 0;
-            cub::DeviceSegmentedSort::SortKeys(nullptr, tb, keys.p, gr->adj.p + base, (int)cnt_e, (int)ns, seg_off.p,
-                                               seg_off.p + 1, st);
-            if (tb + 16 > sort_tmp.n) VGA_TRY(sort_tmp.alloc(tb + 16));
-            VGA_CUDA(cub::DeviceSegmentedSort::SortKeys(sort_tmp.p, tb, keys.p, gr->adj.p + base, (int)cnt_e, (int)ns,
-                                                        seg_off.p, seg_off.p + 1, st));
-            tm.launches += 3;
+            const uint32_t total_v = (uint32_t)dg->cells;  // filled cells + ghosts
+            const size_t rs_bytes = sizeof(uint32_t) * ((size_t)((total_v + 31u) >> 5) + (size_t)((((total_v + 31u) >> 5) + 31u) >> 5) + 4);
+            if (ctx->opt.build_sort == 1 && rs_bytes <= ctx->smem_optin) {
+                VGA_CUDA(cudaFuncSetAttribute(k_rank_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_bytes));
+                const unsigned blocks = (unsigned)std::min<int64_t>(ns, (int64_t)ctx->sm_count * 16);
+                k_rank_sort<<<blocks, RS_TPB, rs_bytes, st>>>(keys.p, seg_off.p, ns, total_v, gr->adj.p + base);
+                tm.launches++;
+            } else {
+                size_t tb = 0;
+                cub::DeviceSegmentedSort::SortKeys(nullptr, tb, keys.p, gr->adj.p + base, (int)cnt_e, (int)ns, seg_off.p,
+                                                   seg_off.p + 1, st);
+                if (tb + 16 > sort_tmp.n) VGA_TRY(sort_tmp.alloc(tb + 16));
+                VGA_CUDA(cub::DeviceSegmentedSort::SortKeys(sort_tmp.p, tb, keys.p, gr->adj.p + base, (int)cnt_e, (int)ns,
+                                                            seg_off.p, seg_off.p + 1, st));
+                tm.launches += 3;
+            }
         }
         VGA_CUDA(cudaGetLastError());
         if (ctx->progress) ctx->progress(ctx->user, j, nsrc);

@@ -119,6 +119,8 @@ struct Options {
     int64_t sieve_big_gcap = 4096;
     int64_t sieve_big_bcap = 32768;
     int64_t build_chunk_entries = (int64_t)1 << 30;
+    int64_t build_sort = 0;      // rows sorted by 0: cub segmented radix sort; 1: bitmap rank in shared memory (k_rank_sort;
+                                 // EXPERIMENTAL, opt-in, validated under SIMT emulation)
     int64_t pull_alpha = 1;      // pull when frontier edges * alpha > candidate in-edges * beta (per batch)
     int64_t pull_beta = 1;
     int64_t bfs_order = 2;       // 0: x-major ordinals, 1: 8x8 tiles in Morton order, 2: + wall-respecting floods

@@ -97,8 +97,10 @@ def preprocess(src: str) -> str:
     return s
 
 
-def build(outdir=None, force=False):
-    outdir = outdir or os.path.join(HERE, "_build")
+def build(outdir=None, force=False, sanitize=False):
+    """sanitize=True: AddressSanitizer + UBSan build (device memory is the host heap, so out-of-bounds accesses of a kernel
+    are caught); uses the ucontext fiber switch, which ASan understands."""
+    outdir = outdir or os.path.join(HERE, "_build_asan" if sanitize else "_build")
     os.makedirs(outdir, exist_ok=True)
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HOST, f) for f in os.listdir(HOST)] + \
            [os.path.join(HERE, "include", "simt_emu.h"), os.path.abspath(__file__), os.path.join(ROOT, "include", "vga_b200.h")]
@@ -107,7 +109,8 @@ def build(outdir=None, force=False):
     newest = max(os.path.getmtime(p) for p in srcs)
     if not force and os.path.exists(so) and os.path.exists(hso) and min(os.path.getmtime(so), os.path.getmtime(hso)) > newest:
         return outdir
-    flags = ["-O1", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-w", "-I" + os.path.join(HERE, "include"), "-I" + CSRC]
+    san = ["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-DSIMT_USE_UCONTEXT"] if sanitize else []
+    flags = ["-O1", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-w", "-I" + os.path.join(HERE, "include"), "-I" + CSRC] + san
 
     def one(name):
         cpp = os.path.join(outdir, name + ".emu.cpp")
@@ -120,12 +123,13 @@ def build(outdir=None, force=False):
 
     with ThreadPoolExecutor(max_workers=5) as ex:
         objs = list(ex.map(one, CU))
-    subprocess.check_call(["g++", "-shared", "-o", so] + objs)
+    subprocess.check_call(["g++", "-shared", "-o", so] + san + objs)
     hsrc = [os.path.join(HOST, f) for f in ("pointmap.cpp", "graphio.cpp", "capi.cpp")]
-    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", hso] + hsrc +
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-o", hso] + san + hsrc +
                           ["-L" + outdir, "-lvga_b200", "-Wl,-rpath,$ORIGIN"])
     return outdir
 
 
 if __name__ == "__main__":
-    print(build(sys.argv[1] if len(sys.argv) > 1 else None, force=True))
+    args = [a for a in sys.argv[1:] if a != "--asan"]
+    print(build(args[0] if args else None, force=True, sanitize="--asan" in sys.argv))

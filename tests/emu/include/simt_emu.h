@@ -14,7 +14,9 @@
 // NOT detected; memory is the host heap ("device" pointers are host pointers).
 #pragma once
 
-#if !defined(__x86_64__)
+#if defined(SIMT_ASM_SWITCH) && !defined(SIMT_USE_UCONTEXT)
+#define SIMT_ASM_SWITCH 1
+#else
 #include <ucontext.h>
 #endif
 
@@ -150,7 +152,7 @@ enum Op { OP_NONE, OP_BALLOT, OP_ANY, OP_SHFL, OP_SHFL_DOWN, OP_SHFL_UP, OP_SHFL
 
 // Fiber switch.  x86-64: a hand-written switch of the callee-saved registers and the stack pointer (glibc's swapcontext
 // makes a signal-mask system call per switch, which dominated the run time); elsewhere: ucontext.
-#if defined(__x86_64__)
+#if defined(SIMT_ASM_SWITCH)
 typedef void *Context;  // saved stack pointer
 extern "C" void simt_switch(Context *save, Context load);
 asm(R"(
@@ -206,7 +208,7 @@ constexpr size_t STACK = 256 * 1024;
 inline void *dyn_smem() { return R.dyn.data(); }
 
 inline void to_scheduler(Lane *me) {
-#if defined(__x86_64__)
+#if defined(SIMT_ASM_SWITCH)
     simt_switch(&me->ctx, R.sched);
 #else
     swapcontext(&me->ctx, &R.sched);
@@ -214,7 +216,7 @@ inline void to_scheduler(Lane *me) {
 }
 inline void to_lane(Lane *l) {
     R.cur = l;
-#if defined(__x86_64__)
+#if defined(SIMT_ASM_SWITCH)
     simt_switch(&R.sched, l->ctx);
 #else
     swapcontext(&R.sched, &l->ctx);
@@ -225,14 +227,14 @@ inline void trampoline() {
     (*R.body)();
     R.cur->done = true;
     R.cur->waiting = false;
-#if defined(__x86_64__)
+#if defined(SIMT_ASM_SWITCH)
     to_scheduler(R.cur);  // a finished fiber is never resumed
     abort();
 #endif
 }
 
 inline void make_lane_context(Lane &l, char *stack, size_t size) {
-#if defined(__x86_64__)
+#if defined(SIMT_ASM_SWITCH)
     // initial frame: six callee-saved registers, the entry point for `ret`, and a null return address for the entry
     uintptr_t top = ((uintptr_t)stack + size) & ~(uintptr_t)15;
     void **sp = (void **)top;

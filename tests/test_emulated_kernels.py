@@ -113,8 +113,9 @@ def test_graphfile_pipelines_merges_and_cli_shim(emu_dir):
 
 
 def test_experimental_kernels(emu_dir):
-    """local_mode = 3 (bit-sliced counters), bfs_pull = 1 (pyramid pull), bfs_push_unroll = 4 on the small plans."""
-    run_gpu_tests_emulated(emu_dir, ["tests/test_zzzz_experimental_gpu.py", "-k", "oblique"])
+    """local_mode = 3 (bit-sliced counters), bfs_pull / bfs_push = 1 (pyramids), bfs_push_unroll = 4, build_sort = 1 (bitmap
+    rank sort) on the small plans."""
+    run_gpu_tests_emulated(emu_dir, ["tests/test_zzzz_experimental_gpu.py", "-k", "oblique or holes"])
 
 
 def test_real_cli_with_gpu_shims(emu_dir):
@@ -122,3 +123,26 @@ def test_real_cli_with_gpu_shims(emu_dir):
     if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "depthmapXcli_gpu")):
         pytest.skip("integration binaries not built")
     run_gpu_tests_emulated(emu_dir, ["tests/test_cli_dropin.py", "-k", "oblique:20"])
+
+
+@pytest.mark.skipif(not os.environ.get("VGA_EMU_ASAN"), reason="slow: set VGA_EMU_ASAN=1 (AddressSanitizer build of the emulation)")
+def test_kernels_under_address_sanitizer():
+    """Device memory is the host heap in the emulation, so an AddressSanitizer build catches out-of-bounds accesses and
+    reads of uninitialised-by-luck memory (ASan poisons fresh allocations) inside kernels.  Minutes, hence opt-in."""
+    sys.path.insert(0, EMU)
+    try:
+        import build_emu
+    finally:
+        sys.path.pop(0)
+    d = build_emu.build(sanitize=True)
+    libs = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip() + ":" + \
+        subprocess.run(["gcc", "-print-file-name=libubsan.so"], capture_output=True, text=True).stdout.strip()
+    env = dict(os.environ, VGA_EMU_LIBDIR=d, LD_LIBRARY_PATH=d, LD_PRELOAD=libs,
+               ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-m", "gpu", "--runxfail", "-x", "-q", "-p", "no:cacheprovider",
+                        "tests/test_zzzz_experimental_gpu.py", "tests/test_gpu_parity.py", "tests/test_stepdepth_gpu.py",
+                        "tests/test_zzz_graphfile_gpu.py", "-k",
+                        "(oblique and not overflow) or golden or ghost or empty or several or step_depth or visprep or loaded or merge"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=7200)
+    tail = "\n".join((r.stdout + r.stderr).splitlines()[-30:])
+    assert r.returncode == 0 and "AddressSanitizer" not in r.stdout + r.stderr.replace("ASan doesn't fully support", ""), tail

@@ -88,6 +88,35 @@ def test_pyramid_push_vs_oracle(name, radius, push, pull, mode, words):
     c.close()
 
 
+@pytest.mark.parametrize("name", ["oblique:30:30:7", "office:64:64:1", "urban:120:120:4", "room:24:24:1+holes"])
+def test_rank_sort_vs_oracle(name):
+    """build_sort = 1: rows ordered by bitmap rank in shared memory (k_rank_sort) instead of the segmented radix sort;
+    the sorted adjacency incl. bins, accepted flags and ghost columns must equal the oracle's."""
+    from oracle import pyoracle as po
+    flat = capi.prepare(plans.by_name(name.split("+")[0]))
+    if name.endswith("+holes"):  # unfilled cells inside diagonal runs -> ghost columns (numbered after the filled cells)
+        st = flat.state.copy()
+        for d in (3, 5):
+            st[(2 + d) * flat.rows + (2 + d)] &= ~np.uint16(2)
+        flat.state = st
+    og = po.OracleGraph(po.Grid(flat.cols, flat.rows, flat.spacing, flat.bl_x, flat.bl_y, flat.state, flat.line_off, flat.lines))
+    c = capi.Context(0)
+    c.set_option("build_sort", 1)
+    g = c.build(flat)
+    rp, col, b, acc = g.csr()
+    orp, oref, ob = og.iter_rows()
+    assert np.array_equal(rp, orp)
+    refs = g.cell_refs()
+    rowid = np.repeat(np.arange(len(orp) - 1), np.diff(orp).astype(np.int64))
+    order = np.lexsort((oref.astype(np.int64), rowid))
+    assert np.array_equal(refs[col], oref[order]) and np.array_equal(b, ob[order])
+    d = capi.Context(0)
+    rp2, col2, b2, acc2 = d.build(flat).csr()
+    assert np.array_equal(col, col2) and np.array_equal(b, b2) and np.array_equal(acc, acc2)
+    c.close()
+    d.close()
+
+
 def test_pyramid_paths_equal_default_on_c2():
     """Full-size C2: pyramid push + pull together must give exactly the integers of the default schedule."""
     flat = capi.prepare(plans.by_name("C2"))

@@ -9,6 +9,10 @@ mkdir -p gpurun_out
 python -m pytest tests -m gpu -q -rxX -p no:cacheprovider > gpurun_out/r2_pytest.log 2>&1
 tail -40 gpurun_out/r2_pytest.log
 {
+  echo "== C2 build default";  python tools/gpu_time.py C2 build
+  echo "== C2 build_sort=1";   python tools/gpu_time.py C2 build build_sort=1
+  echo "== C5 build default";  python tools/gpu_time.py C5 build
+  echo "== C5 build_sort=1";   python tools/gpu_time.py C5 build build_sort=1
   echo "== C2 default";        python tools/gpu_time.py C2 global
   echo "== C2 bfs_pull=1";     python tools/gpu_time.py C2 global bfs_pull=1
   echo "== C2 bfs_pull=1 pull_alpha=4"; python tools/gpu_time.py C2 global bfs_pull=1 pull_alpha=4
