@@ -82,7 +82,8 @@ struct BfsDev {
     int64_t pyr_off[PYR_LEVELS_DEV];
     int64_t pyr_cnt[PYR_LEVELS_DEV];
 };
-constexpr int NSTAT = 8;  // per-batch statistics: frontier edges, pull cost, new vertices, open vertices, frontier run cost
+constexpr int NSTAT = 8;  // per-batch statistics: frontier edges, pull cost, new vertices, open vertices, frontier run cost,
+                          // frontier run count
 
 template <int W> __device__ __forceinline__ void ldw(const u64 *p, u64 (&o)[W]) {
     if constexpr (W == 1) {
@@ -516,9 +517,9 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[bat
     const int b = blockIdx.y;
     if (!d.active[b]) return;
     __shared__ int s_cnt[W * 64];
-    __shared__ u64 s_stat[5];
+    __shared__ u64 s_stat[6];
     for (int i = threadIdx.x; i < W * 64; i += TPB) s_cnt[i] = 0;
-    if (threadIdx.x < 5) s_stat[threadIdx.x] = 0ULL;
+    if (threadIdx.x < 6) s_stat[threadIdx.x] = 0ULL;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     u64 *fr = d.frontier + (int64_t)b * d.n * W;
@@ -532,7 +533,7 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[bat
     int cnt[W][2];  // lane l counts source bits l and l+32 of each word
 #pragma unroll
     for (int j = 0; j < W; j++) cnt[j][0] = cnt[j][1] = 0;
-    u64 f_edges = 0, u_edges = 0, n_new = 0, n_open = 0, f_runs = 0;
+    u64 f_edges = 0, u_edges = 0, n_new = 0, n_open = 0, f_runs = 0, f_nrun = 0;
     for (int64_t base = (int64_t)blockIdx.x * TPB; base < d.n; base += (int64_t)gridDim.x * TPB) {
         int64_t v = base + threadIdx.x;
         u64 nw[W];
@@ -558,7 +559,10 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[bat
                 for (int j = 0; j < W; j++) zero[j] = 0ULL;
                 stw<W>(nx + v * W, zero);
                 f_edges += d.rowptr[v + 1] - d.rowptr[v];
-                if (d.f_costptr) f_runs += d.f_costptr[v + 1] - d.f_costptr[v];
+                if (d.f_costptr) {
+                    f_runs += d.f_costptr[v + 1] - d.f_costptr[v];
+                    f_nrun += d.f_runptr[v + 1] - d.f_runptr[v];
+                }
                 n_new += 1;
                 if (lout) {
                     // coarse pass (W == 1): bit j of coarse batch b is group b*64+j
@@ -629,6 +633,7 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[bat
         n_new += __shfl_down_sync(FULL, n_new, o);
         n_open += __shfl_down_sync(FULL, n_open, o);
         f_runs += __shfl_down_sync(FULL, f_runs, o);
+        f_nrun += __shfl_down_sync(FULL, f_nrun, o);
     }
     if (lane == 0) {
         if (f_edges) atomicAdd(&s_stat[0], f_edges);
@@ -636,12 +641,13 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[bat
         if (n_new) atomicAdd(&s_stat[2], n_new);
         if (n_open) atomicAdd(&s_stat[3], n_open);
         if (f_runs) atomicAdd(&s_stat[4], f_runs);
+        if (f_nrun) atomicAdd(&s_stat[5], f_nrun);
     }
     __syncthreads();
     if (counts)
         for (int i = threadIdx.x; i < W * 64; i += TPB)
             if (s_cnt[i]) atomicAdd(&counts[(int64_t)b * W * 64 + i], s_cnt[i]);
-    if (threadIdx.x < 5 && s_stat[threadIdx.x]) atomicAdd(&d.stats[b * NSTAT + threadIdx.x], s_stat[threadIdx.x]);
+    if (threadIdx.x < 6 && s_stat[threadIdx.x]) atomicAdd(&d.stats[b * NSTAT + threadIdx.x], s_stat[threadIdx.x]);
 }
 
 // per batch: retire empty batches, choose the next step's direction, reset statistics
@@ -650,8 +656,8 @@ __global__ void k_decide(BfsDev d, int nb, int bfs_mode, int64_t alpha, int64_t 
     if (b >= nb) return;
     if (!d.active[b]) return;
     u64 fe = d.stats[b * NSTAT + 0], ue = d.stats[b * NSTAT + 1], nn = d.stats[b * NSTAT + 2], open = d.stats[b * NSTAT + 3];
-    const u64 frc = d.stats[b * NSTAT + 4];
-    for (int i = 0; i < 5; i++) d.stats[b * NSTAT + i] = 0;
+    const u64 frc = d.stats[b * NSTAT + 4], fnr = d.stats[b * NSTAT + 5];
+    for (int i = 0; i < 6; i++) d.stats[b * NSTAT + i] = 0;
     // Retire the batch when nothing new was reached -- or when every vertex has been reached by every source of the
     // batch: expanding the last frontier could not find anything (on connected plans that last, useless expansion of
     // the largest frontier was 10-20 % of the top-down work).
@@ -677,6 +683,7 @@ __global__ void k_decide(BfsDev d, int nb, int bfs_mode, int64_t alpha, int64_t 
         atomicAdd(&work[0], fe);
         atomicAdd(&work[1], nn);
         if (m == 1) atomicAdd(&work[2], ue);
+        atomicAdd(&work[3], fnr);  // runs of the out-rows of the vertices that expand next (run-length model)
     }
 }
 
@@ -1208,6 +1215,16 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int6
         const double src_edges = (double)(rp[1] - rp[0]);
         const double vec = 8.0 * W;
         tm.algo_bytes = 4.0 * ((double)hw[0] + src_edges) + vec * ((double)hw[1] + (double)nsrc) + 2.0 * vec * (double)hw[1];
+        // the same model for the run-length rows of bfs_push = 1: 8 bytes per run (first ordinal, length) instead of 4 per
+        // entry; the sources' own rows counted from their run counts
+        tm.algo_bytes_runs = 0.0;
+        if (pyr_push) {
+            uint64_t fr[2] = {0, 0};
+            VGA_CUDA(cudaMemcpy(&fr[0], g->f_runptr.p + src_begin, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+            VGA_CUDA(cudaMemcpy(&fr[1], g->f_runptr.p + src_end, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+            tm.algo_bytes_runs = 8.0 * ((double)hw[3] + (double)(fr[1] - fr[0])) + vec * ((double)hw[1] + (double)nsrc) +
+                                 2.0 * vec * (double)hw[1];
+        }
     }
     if (dist && deepest > max_levels) {
         set_error("vga_global: level histogram needs " + std::to_string(deepest) + " columns");

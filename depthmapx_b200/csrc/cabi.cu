@@ -208,6 +208,7 @@ int vga_ctx_timing(const vga_ctx *ctx, vga_timing *out) {
     out->launches = ctx->timing.launches;
     out->main_launches = ctx->timing.main_launches;
     out->algo_bytes = ctx->timing.algo_bytes;
+    out->algo_bytes_runs = ctx->timing.algo_bytes_runs;
     return VGA_OK;
 }
 

@@ -102,7 +102,7 @@ struct Workspace {
 };
 
 struct Timing {
-    double h2d_ms = 0, kernel_ms = 0, d2h_ms = 0, main_kernel_ms = 0, algo_bytes = 0;
+    double h2d_ms = 0, kernel_ms = 0, d2h_ms = 0, main_kernel_ms = 0, algo_bytes = 0, algo_bytes_runs = 0;
     int64_t launches = 0, main_launches = 0;
 };
 

@@ -81,6 +81,7 @@ typedef struct {
     int64_t launches;  /* kernels launched by the call */
     int64_t main_launches;
     double algo_bytes; /* algorithmic bytes of the dominant kernel(s), DESIGN.md formula */
+    double algo_bytes_runs; /* vga_global with bfs_push = 1: the same model with run-length rows (8 bytes per run), else 0 */
 } vga_timing;
 
 const char *vga_last_error(void);
