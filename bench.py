@@ -360,6 +360,7 @@ def main():
     # dominant kernel group: BFS level kernels (CUDA events inside the library, on its stream)
     bfs_main_ms = reduce_max(float(np.mean([s["bfs_timing"]["main_kernel_ms"] for s in st_res])))
     bfs_algo = reduce_sum(float(np.mean([s["bfs_timing"]["algo_bytes"] for s in st_res])))
+    bfs_algo_runs = reduce_sum(float(np.mean([s["bfs_timing"].get("algo_bytes_runs", 0.0) for s in st_res])))
     sieve_main_ms = reduce_max(float(np.mean([s["build_timing"]["main_kernel_ms"] for s in st_res])))
     launches = reduce_sum(float(np.sum([s["build_timing"]["launches"] + s["bfs_timing"]["launches"] for s in st_res])))
     main_launches = float(np.mean([s["bfs_timing"]["main_launches"] for s in st_res]))
@@ -398,6 +399,8 @@ def main():
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "traffic": None,
                      "algorithmic_bytes_per_step": bfs_algo, "kernel_ms_per_step": bfs_main_ms,
+                     # with run-length rows (--opt bfs_push=1): the same model at 8 bytes per run instead of 4 per entry
+                     "algorithmic_bytes_per_step_run_length": bfs_algo_runs if bfs_algo_runs > 0 else None,
                      "launches_per_step": main_launches},
         "clocks": clocks,
         # size-independent result check: equal for every N on the same workload (sums over all sources of
