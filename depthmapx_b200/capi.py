@@ -35,7 +35,7 @@ ABI_SYMBOLS = [
     "vga_ctx_set_option", "vga_ctx_timing", "vga_ctx_sync", "vga_graph_build", "vga_grid_upload", "vga_dgrid_free",
     "vga_graph_build_resident", "vga_graph_from_csr", "vga_graph_free", "vga_graph_num_cells", "vga_graph_num_ghosts",
     "vga_graph_num_edges", "vga_graph_src_begin", "vga_graph_src_end", "vga_graph_csr", "vga_graph_cell_refs", "vga_graph_set_cell_refs",
-    "vga_graph_node_stats", "vga_global", "vga_global_attributes", "vga_local", "vga_local_attributes", "vga_step_depth",
+    "vga_graph_node_stats", "vga_graph_set_noexpand", "vga_global", "vga_global_attributes", "vga_local", "vga_local_attributes", "vga_step_depth",
     "vga_graph_device_rows", "vga_graph_from_device_rows",
 ]
 HOST_SYMBOLS = [
@@ -46,7 +46,7 @@ HOST_SYMBOLS = [
     "dmxh_map_encode_nodes", "dmxh_map_begin_graph", "dmxh_map_finish_graph", "dmxh_map_write_global", "dmxh_map_write_local",
     "dmxh_map_write_step_depth", "dmxh_graph_open", "dmxh_graph_close", "dmxh_graph_save", "dmxh_graph_num_maps",
     "dmxh_graph_displayed_map", "dmxh_graph_map", "dmxh_graph_walls", "dmxh_graph_new_map", "dmxh_graph_make_graph",
-    "dmxh_graph_made", "dmxh_map_merge", "dmxh_map_contracted_rows", "dmxh_map_radius_correction",
+    "dmxh_graph_made", "dmxh_map_fill_type", "dmxh_map_context_skip", "dmxh_map_merge", "dmxh_map_contracted_rows", "dmxh_map_radius_correction",
 ]
 
 LEVEL_PREPARE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32))
@@ -86,6 +86,7 @@ def abi():
         L.vga_graph_cell_refs.argtypes = [vp, vp]
         L.vga_graph_set_cell_refs.argtypes = [vp, vp, i64]
         L.vga_graph_node_stats.argtypes = [vp] * 7
+        L.vga_graph_set_noexpand.argtypes = [vp, vp]
         L.vga_global.argtypes = [vp, vp, C.c_int, i64, i64, vp, vp, vp, C.c_int32, C.POINTER(C.c_int32)]
         L.vga_global_attributes.argtypes = [i64, vp, vp, vp, C.c_int32] + [vp] * 7
         L.vga_local.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp]
@@ -150,6 +151,8 @@ def host():
         H.dmxh_graph_make_graph.argtypes = [vp, C.c_int, C.c_double]
         H.dmxh_graph_made.argtypes = [vp]
         H.dmxh_map_merge.argtypes = [vp] + [C.c_double] * 4
+        H.dmxh_map_fill_type.argtypes = [vp, C.c_double, C.c_double, C.c_int]
+        H.dmxh_map_context_skip.argtypes = [vp, vp]
         H.dmxh_map_contracted_rows.argtypes = [vp] * 6
         H.dmxh_map_radius_correction.argtypes = [vp, C.c_int, LEVEL_PREPARE_FN, LEVEL_RUN_FN, vp, vp, vp, vp, C.c_int32]
         _host = H
@@ -307,6 +310,15 @@ class Graph:
         r = np.ascontiguousarray(refs, np.int32)
         check(abi().vga_graph_set_cell_refs(self.h, _p(r), len(r)))
 
+    def set_noexpand(self, flags):
+        """uint8 [N]: cells that a radius-limited vga_global / vga_step_depth counts but does not expand; None clears."""
+        if flags is None or len(flags) == 0:
+            check(abi().vga_graph_set_noexpand(self.h, None))
+        else:
+            f = np.ascontiguousarray(flags, np.uint8)
+            assert len(f) == self.n
+            check(abi().vga_graph_set_noexpand(self.h, _p(f)))
+
     def node_stats(self):
         rows = self.src_end - self.src_begin
         out = dict(connectivity=np.zeros(rows, np.int32), sum_d=np.zeros(rows), sum_d2=np.zeros(rows),
@@ -410,8 +422,18 @@ class HostMap:
     def block_lines(self):
         return self._ret(host().dmxh_map_block_lines(self.h))
 
-    def fill(self, x, y):
+    def fill(self, x, y, fill_type=0):
+        """makePoints; fill_type 1 = semi-fill (context fill)."""
+        if fill_type:
+            return self._ret(host().dmxh_map_fill_type(self.h, x, y, fill_type))
         return self._ret(host().dmxh_map_fill(self.h, x, y))
+
+    def context_skip(self):
+        """uint8 [N] flags of the cells the analyses skip as sources (empty when there are none)."""
+        out = np.zeros(max(self.n, 1), np.uint8)
+        if not host().dmxh_map_context_skip(self.h, _p(out)):
+            return np.zeros(0, np.uint8)
+        return out[:self.n]
 
     @property
     def n(self):

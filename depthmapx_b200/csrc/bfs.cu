@@ -78,6 +78,8 @@ struct BfsDev {
     const uint2 *f_runs;
     const uint64_t *f_costptr;       // [n+1] prefix sums of the pyramid nodes an out-row touches
     int push_force;                  // bfs_push = 2: every top-down step after level 0 uses the pyramid (tests)
+    const uint8_t *noexpand;         // [n] or nullptr: vertices that are counted but never join the frontier (context-filled,
+                                     // not even cells under a radius limit)
     int pyr_levels;
     int64_t pyr_off[PYR_LEVELS_DEV];
     int64_t pyr_cnt[PYR_LEVELS_DEV];
@@ -586,7 +588,15 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[bat
                     stw<W>(nx + v * W, zero);
                 }
             }
-            stw<W>(fr + v * W, nw);
+            if (d.noexpand && d.noexpand[v]) {
+                // reached and counted, but not expanded (vgavisualglobal.cpp:108-110)
+                u64 zero[W];
+#pragma unroll
+                for (int j = 0; j < W; j++) zero[j] = 0ULL;
+                stw<W>(fr + v * W, zero);
+            } else {
+                stw<W>(fr + v * W, nw);
+            }
             if (anyneed != 0ULL) n_open += 1;  // still unreached by some source of the batch
             // in-edges (or, for the pyramid pull, pyramid loads) the next pull step would have to consider
             const uint64_t *cost = d.t_costptr ? d.t_costptr : d.t_rowptr;
@@ -1082,6 +1092,7 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int6
     d.t_runptr = pyr_pull ? g->t_runptr.p : nullptr;
     d.t_runs = pyr_pull ? g->t_runs.p : nullptr;
     d.t_costptr = pyr_pull ? g->t_costptr.p : nullptr;
+    d.noexpand = (radius != -1 && g->noexpand.p) ? g->noexpand.p : nullptr;
     d.npyr = npyr_p;
     d.push_force = ctx->opt.bfs_push == 2 ? 1 : 0;
     d.f_runptr = pyr_push ? g->f_runptr.p : nullptr;

@@ -255,10 +255,8 @@ int vga_grid_upload(vga_ctx *ctx, const vga_grid *grid, vga_dgrid **out) {
             int64_t c = x * grid->rows + y;
             uint16_t s = grid->state[c];
             bool filled = (s & 0x0002) != 0;
-            if (filled && (s & (0x0008 | 0x0040))) {
-                set_error("vga_grid: CONTEXTFILLED / MERGED cells are not supported by the GPU path");
-                return VGA_ERR_UNSUPPORTED;
-            }
+            // CONTEXTFILLED (0x0008) and MERGED (0x0040) do not matter to construction: sparkGraph2 looks at FILLED only;
+            // the analyses get them through vga_graph_set_noexpand / the contracted adjacency of the host layer
             uint8_t f = (filled ? 1 : 0) | ((grid->line_off[c + 1] > grid->line_off[c]) ? 2 : 0);
             cf[(size_t)c] = f;
             cft[(size_t)(y * grid->cols + x)] = f;
@@ -453,6 +451,21 @@ int vga_graph_set_cell_refs(vga_graph *g, const int32_t *ref, int64_t count) {
         return VGA_ERR_INVALID;
     }
     g->h_refs.assign(ref, ref + count);
+    return VGA_OK;
+}
+
+int vga_graph_set_noexpand(vga_graph *g, const uint8_t *flags) {
+    if (!g) return VGA_ERR_INVALID;
+    vga_ctx *ctx = g->ctx;
+    VGA_CUDA(cudaSetDevice(ctx->device));
+    g_alloc_stream = ctx->stream;
+    if (!flags || g->n == 0) {
+        g->noexpand.release();
+        return VGA_OK;
+    }
+    VGA_TRY(g->noexpand.alloc((size_t)g->n));
+    VGA_CUDA(cudaMemcpyAsync(g->noexpand.p, flags, (size_t)g->n, cudaMemcpyHostToDevice, ctx->stream));
+    VGA_CUDA(cudaStreamSynchronize(ctx->stream));
     return VGA_OK;
 }
 

@@ -23,12 +23,13 @@ __global__ void k_sd_seed(int32_t *depth, const int64_t *src, int64_t nsrc) {
 }
 
 __global__ void __launch_bounds__(STPB) k_sd_expand(int64_t n, const uint64_t *rowptr, const uint32_t *adj, int32_t *depth,
-                                                    int level, int *any) {
+                                                    int level, int *any, const uint8_t *noexpand) {
     const int lane = threadIdx.x & 31;
     bool wrote = false;
     for (int64_t base = (int64_t)blockIdx.x * STPB; base < n; base += (int64_t)gridDim.x * STPB) {
         int64_t u = base + threadIdx.x;
-        bool mine = (u < n) && depth[u] == level;
+        // context-filled cells that are not even are marked but not expanded beyond level 0 (vgavisualglobaldepth.cpp:53)
+        bool mine = (u < n) && depth[u] == level && !(level > 0 && noexpand && noexpand[u]);
         uint64_t my0 = 0, my1 = 0;
         if (mine) {
             my0 = rowptr[u];
@@ -83,7 +84,7 @@ int run_step_depth(vga_ctx *ctx, vga_graph *g, const int64_t *sources, int64_t n
         const unsigned blocks = (unsigned)std::min<int64_t>((n + STPB - 1) / STPB, 148 * 16);
         for (int level = 0;; level++) {
             VGA_CUDA(cudaMemsetAsync(any.p, 0, sizeof(int), st));
-            k_sd_expand<<<blocks, STPB, 0, st>>>(n, g->rowptr.p, g->adj.p, depth.p, level, any.p);
+            k_sd_expand<<<blocks, STPB, 0, st>>>(n, g->rowptr.p, g->adj.p, depth.p, level, any.p, g->noexpand.p);
             tm.launches++;
             tm.main_launches++;
             int h_any = 0;

@@ -185,6 +185,7 @@ struct vga_graph {
     vga::DevBuf<int32_t> bin_count; // [rows*32]
     vga::DevBuf<uint8_t> gridconn;
     std::vector<int32_t> h_refs;    // N + G packed PixelRefs (host)
+    vga::DevBuf<uint8_t> noexpand;  // [n] != 0: counted but not expanded (context-filled, not even); empty = none
     // derived analysis structures, built lazily
     vga::DevBuf<uint64_t> t_rowptr; // transpose (in-edges), [n+1]
     vga::DevBuf<uint32_t> t_col;    // [entries to filled targets]

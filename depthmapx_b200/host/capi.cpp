@@ -64,6 +64,16 @@ int dmxh_map_fill(void *map, double x, double y) {
     return guarded([&] { return static_cast<dmx::PointMap *>(map)->makePoints(dmx::Point2f(x, y), 0); });
 }
 
+int dmxh_map_fill_type(void *map, double x, double y, int fill_type) {
+    return guarded([&] { return static_cast<dmx::PointMap *>(map)->makePoints(dmx::Point2f(x, y), fill_type); });
+}
+
+int dmxh_map_context_skip(void *map, uint8_t *flags) {
+    const std::vector<uint8_t> f = static_cast<dmx::PointMap *>(map)->contextSkipFlags();
+    if (flags && !f.empty()) std::memcpy(flags, f.data(), f.size());
+    return f.empty() ? 0 : 1;
+}
+
 int dmxh_map_filled_count(void *map) { return static_cast<dmx::PointMap *>(map)->getFilledPointCount(); }
 
 void dmxh_map_flat(void *map, int64_t *cells, int64_t *nseg, uint16_t *state, uint32_t *line_off, double *lines) {
@@ -207,8 +217,10 @@ int dmxh_map_begin_graph(void *map, int boundarygraph) {
 int dmxh_map_write_global(void *map, double radius, int simple_version, const int32_t *total_nodes,
                           const int64_t *total_depth, const int32_t *dist, int32_t max_levels) {
     return guarded([&] {
-        dmx::VGAVisualGlobal::writeAttributes(*static_cast<dmx::PointMap *>(map), radius, simple_version != 0, total_nodes,
-                                              total_depth, dist, max_levels);
+        dmx::PointMap &m = *static_cast<dmx::PointMap *>(map);
+        const std::vector<uint8_t> skip = m.contextSkipFlags();
+        dmx::VGAVisualGlobal::writeAttributes(m, radius, simple_version != 0, total_nodes, total_depth, dist, max_levels,
+                                              skip.empty() ? nullptr : skip.data());
         return true;
     });
 }
@@ -216,7 +228,9 @@ int dmxh_map_write_global(void *map, double radius, int simple_version, const in
 int dmxh_map_write_local(void *map, int simple_version, const int64_t *cluster, const int32_t *k, const int32_t *total,
                          const float *control) {
     return guarded([&] {
-        dmx::VGAVisualLocal::writeAttributes(*static_cast<dmx::PointMap *>(map), simple_version != 0, cluster, k, total, control);
+        dmx::PointMap &m = *static_cast<dmx::PointMap *>(map);
+        const std::vector<uint8_t> skip = m.contextSkipFlags();
+        dmx::VGAVisualLocal::writeAttributes(m, simple_version != 0, cluster, k, total, control, skip.empty() ? nullptr : skip.data());
         return true;
     });
 }

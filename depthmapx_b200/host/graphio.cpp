@@ -478,9 +478,6 @@ void PointMap::ensureGraph() {
     std::vector<int32_t> ord;
     int64_t n, ghosts;
     ordinals(ord, n, ghosts);
-    for (size_t c = 0; c < cells; c++)
-        if (m_points[c].filled() && m_points[c].contextfilled())
-            throw RuntimeException("GPU path: context-filled cells are not supported");
     std::vector<int32_t> refs((size_t)(n + ghosts));
     for (size_t c = 0; c < cells; c++) refs[(size_t)ord[c]] = int(PixelRef((int)(c / m_rows), (int)(c % m_rows)));
     FlatRows rows;

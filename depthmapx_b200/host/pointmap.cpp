@@ -306,8 +306,9 @@ bool PointMap::makePoints(const Point2f &seed, int fill_type, Communicator *comm
         if (lines_cross_no_touch(w, Line(seed, depixelate(seedref)))) return false;
     if (!m_blockedlines) blockLines();
     m_undocounter++;
-    if (fill_type != 0) throw RuntimeException("makePoints: only FULLFILL (fill_type 0) is supported by the GPU path");
-    const int filltype = Point::FILLED;
+    if (fill_type != 0 && fill_type != 1)
+        throw RuntimeException("makePoints: fill types 0 (full) and 1 (semi / context fill) are supported");
+    const int filltype = fill_type == 0 ? Point::FILLED : (Point::FILLED | Point::CONTEXTFILLED);
     getPoint(seedref).set(filltype, m_undocounter);
     m_filled_point_count++;
     std::vector<PixelRef> a, b;
@@ -409,6 +410,21 @@ std::vector<int> PointMap::filledKeys() const {
         for (size_t j = 0; j < m_rows; j++)
             if (m_points[i * m_rows + j].filled()) keys.push_back(int(PixelRef((int)i, (int)j)));
     return keys;
+}
+
+std::vector<uint8_t> PointMap::contextSkipFlags() const {
+    std::vector<uint8_t> flags;
+    bool any = false;
+    for (size_t i = 0; i < m_cols; i++)
+        for (size_t j = 0; j < m_rows; j++) {
+            const Point &pt = m_points[i * m_rows + j];
+            if (!pt.filled()) continue;
+            const bool skip = pt.contextfilled() && !(i % 2 == 0 && j % 2 == 0);
+            flags.push_back(skip ? 1 : 0);
+            any = any || skip;
+        }
+    if (!any) flags.clear();
+    return flags;
 }
 
 // pointdata.cpp:1250-1264
@@ -535,7 +551,7 @@ static void check_supported(PointMap &map, const char *who) {
 
 // vgavisualglobal.cpp:33-63 (columns), 131-193 (formulas, which value is written when), 214 (display)
 void VGAVisualGlobal::writeAttributes(PointMap &map, double radius, bool simple_version, const int32_t *nodes,
-                                      const int64_t *depth, const int32_t *dist, int32_t maxl) {
+                                      const int64_t *depth, const int32_t *dist, int32_t maxl, const uint8_t *skip) {
     AttributeTable &attributes = map.getAttributeTable();
     const int64_t n = (int64_t)attributes.getNumRows();
     std::string radius_text;
@@ -562,6 +578,7 @@ void VGAVisualGlobal::writeAttributes(PointMap &map, double radius, bool simple_
     // come out identical
     for (int64_t v = 0; v < n; v++) {
         const size_t r = (size_t)v;
+        if (skip && skip[r]) continue;  // not a source in the reference: the row keeps its -1s
         if (!simple_version) attributes.setValue(r, count_col, nc[r]);
         if (nodes[r] > 1) {
             if (!simple_version) attributes.setValue(r, depth_col, md[r]);
@@ -616,6 +633,11 @@ bool VGAVisualGlobal::run(Communicator *comm, PointMap &map, bool simple_version
     }
     std::vector<int32_t> primary;
     vga_graph *graph = map.analysisGraph(&primary);
+    const std::vector<uint8_t> skip = map.contextSkipFlags();
+    if (!skip.empty() && !primary.empty())
+        throw RuntimeException("VGAVisualGlobal: context-filled cells together with merge links are not supported by the GPU path");
+    if (vga_graph_set_noexpand(graph, skip.empty() ? nullptr : skip.data()) != VGA_OK)
+        throw RuntimeException(std::string("VGAVisualGlobal: ") + vga_last_error());
     vga_ctx *ctx = map.context();
     CbState cb{comm, std::chrono::steady_clock::now(), false};
     vga_ctx_set_callbacks(ctx, progress_cb, cancel_cb, &cb);
@@ -645,13 +667,13 @@ bool VGAVisualGlobal::run(Communicator *comm, PointMap &map, bool simple_version
         copy_from_primary(primary, depth.data());
         copy_from_primary(primary, dist.data(), (size_t)maxl);
     }
-    writeAttributes(map, m_radius, simple_version, nodes.data(), depth.data(), dist.data(), maxl);
+    writeAttributes(map, m_radius, simple_version, nodes.data(), depth.data(), dist.data(), maxl, skip.empty() ? nullptr : skip.data());
     return true;
 }
 
 // vgavisuallocal.cpp:31-35, 84-96, 112
 void VGAVisualLocal::writeAttributes(PointMap &map, bool simple_version, const int64_t *cluster, const int32_t *k,
-                                     const int32_t *total, const float *control) {
+                                     const int32_t *total, const float *control, const uint8_t *skip) {
     if (simple_version) return;
     AttributeTable &attributes = map.getAttributeTable();
     const int64_t n = (int64_t)attributes.getNumRows();
@@ -665,6 +687,7 @@ void VGAVisualLocal::writeAttributes(PointMap &map, bool simple_version, const i
     std::vector<float> a((size_t)n), b((size_t)n), c((size_t)n);
     vga_local_attributes(n, cluster, k, total, control, a.data(), b.data(), c.data());
     for (int64_t v = 0; v < n; v++) {
+        if (skip && skip[(size_t)v]) continue;
         attributes.setValue((size_t)v, cluster_col, a[(size_t)v]);
         attributes.setValue((size_t)v, control_col, b[(size_t)v]);
         attributes.setValue((size_t)v, controllability_col, c[(size_t)v]);
@@ -688,7 +711,8 @@ bool VGAVisualLocal::run(Communicator *comm, PointMap &map, bool simple_version)
     int rc = vga_local(ctx, map.graph(), 0, n, cluster.data(), k.data(), total.data(), control.data());
     if (rc == VGA_ERR_CANCELLED) throw Communicator::CancelledException();
     if (rc != VGA_OK) throw RuntimeException(std::string("VGAVisualLocal: ") + vga_last_error());
-    writeAttributes(map, simple_version, cluster.data(), k.data(), total.data(), control.data());
+    const std::vector<uint8_t> skip = map.contextSkipFlags();
+    writeAttributes(map, simple_version, cluster.data(), k.data(), total.data(), control.data(), skip.empty() ? nullptr : skip.data());
     return true;
 }
 
@@ -719,6 +743,11 @@ bool VGAVisualGlobalDepth::run(Communicator *, PointMap &map, bool) {
         const int64_t v = (int64_t)(pos - keys.begin());
         sources.push_back(primary.empty() ? v : (int64_t)primary[(size_t)v]);
     }
+    const std::vector<uint8_t> skip = map.contextSkipFlags();
+    if (!skip.empty() && !primary.empty())
+        throw RuntimeException("VGAVisualGlobalDepth: context-filled cells together with merge links are not supported by the GPU path");
+    if (vga_graph_set_noexpand(graph, skip.empty() ? nullptr : skip.data()) != VGA_OK)
+        throw RuntimeException(std::string("VGAVisualGlobalDepth: ") + vga_last_error());
     std::vector<int32_t> depth((size_t)n, -1);
     int rc = vga_step_depth(map.context(), graph, sources.data(), (int64_t)sources.size(), depth.data());
     if (rc != VGA_OK) throw RuntimeException(std::string("VGAVisualGlobalDepth: ") + vga_last_error());

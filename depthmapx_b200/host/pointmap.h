@@ -251,6 +251,11 @@ class PointMap {
                           int32_t max_levels);
     // x-major packed PixelRefs of the filled cells (= attribute row keys once the graph is made)
     std::vector<int> filledKeys() const;
+    // per filled cell (x-major): 1 for context-filled cells (semi-fill, fill_type 1) that are not "even"
+    // (PixelRef::iseven, pixelref.h:68-69): the analyses skip them as sources and, under a radius limit, count but do not
+    // expand them (vgavisualglobal.cpp:75, 108-110; vgavisuallocal.cpp:43; vgavisualglobaldepth.cpp:53).  Empty when the
+    // map has no such cell.
+    std::vector<uint8_t> contextSkipFlags() const;
     // Second half of sparkGraph2 (pointdata.cpp:1268-1341 minus the per-source work): attribute rows, the three
     // columns, grid connections and flags from per-source results that libvga_b200 produced -- on this GPU
     // (sparkGraph2 calls it) or on other ranks of a multi-GPU build (gathered by the caller).
@@ -317,8 +322,10 @@ class VGAVisualGlobal : public IVGA {
     // column set-up + formula stage + row writes (vgavisualglobal.cpp:33-63, 131-193, 214) from the BFS integers
     // of all N cells in x-major order -- computed by vga_global on this GPU (run() calls it) or gathered from the
     // ranks of a multi-GPU run
+    // skip: optional per-row flags of the sources the reference does not analyse (PointMap::contextSkipFlags)
     static void writeAttributes(PointMap &map, double radius, bool simple_version, const int32_t *total_nodes,
-                                const int64_t *total_depth, const int32_t *dist, int32_t max_levels);
+                                const int64_t *total_depth, const int32_t *dist, int32_t max_levels,
+                                const uint8_t *skip = nullptr);
 };
 
 class VGAVisualLocal : public IVGA {
@@ -330,7 +337,7 @@ class VGAVisualLocal : public IVGA {
     explicit VGAVisualLocal(bool gates_only) : m_gates_only(gates_only) {}
     // vgavisuallocal.cpp:31-35, 84-96, 112 from the integers of vga_local
     static void writeAttributes(PointMap &map, bool simple_version, const int64_t *cluster, const int32_t *k,
-                                const int32_t *total, const float *control);
+                                const int32_t *total, const float *control, const uint8_t *skip = nullptr);
 };
 
 // Visual step depth from the map's selection (salalib/vgamodules/vgavisualglobaldepth.cpp:23-75)

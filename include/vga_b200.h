@@ -19,8 +19,8 @@
  * Conventions: every function returns 0 on success and a negative vga_status otherwise;
  * vga_last_error() gives the message of the last failure on the calling thread.  There is NO CPU
  * fallback: without a CUDA device every compute entry point fails with VGA_ERR_NO_DEVICE.
- * Unsupported inputs (merged pixels, CONTEXTFILLED cells, NaN blocks, grids of 2^26 cells or more)
- * are errors.
+ * Unsupported inputs (NaN blocks, grids of 2^26 cells or more) are errors.  Merge links and context-filled cells
+ * are handled above this ABI (contracted adjacency via vga_graph_from_csr, vga_graph_set_noexpand).
  * One process drives one GPU (vga_ctx_create(device)); multi-GPU runs shard sources across
  * processes (src_begin/src_end arguments) and exchange shards outside this library.
  *
@@ -136,6 +136,12 @@ int vga_graph_cell_refs(const vga_graph *g, int32_t *ref);
 /* Attach packed PixelRefs (N cells, then G ghosts) to an adopted graph so that the analyses can form
  * spatially coherent source batches.  Optional: results never depend on it, only speed does. */
 int vga_graph_set_cell_refs(vga_graph *g, const int32_t *ref, int64_t count);
+/* Context-filled cells (GUI semi-fill: FILLED | CONTEXTFILLED, salalib/pointdata.cpp:435-441) that are not "even"
+ * (PixelRef::iseven) are counted but NOT expanded by a radius-limited vga_global (vgavisualglobal.cpp:108-110) and by
+ * vga_step_depth beyond level 0 (vgavisualglobaldepth.cpp:53).  flags[v] != 0 marks such a cell (N bytes, x-major
+ * ordinals); NULL clears the marks.  vga_global with radius -1 ignores them, as the reference does.  Skipping those
+ * cells as SOURCES is the caller's business (the host layer and the shims do not write their rows). */
+int vga_graph_set_noexpand(vga_graph *g, const uint8_t *flags);
 /* Per source row: what sparkPixel2 stores besides the pixel lists.  connectivity = neighbourhood_size,
  * sum_d / sum_d2 = total_dist / total_dist_sqr (double running sums in reference order),
  * far_bin_dists [rows*32] floats, bin_count [rows*32] (accepted pixels per bin),

@@ -22,6 +22,10 @@ void dmxh_map_destroy(void *map);
 void dmxh_map_grid(void *map, int32_t *cols, int32_t *rows, double *spacing, double *bl_x, double *bl_y);
 int dmxh_map_block_lines(void *map);
 int dmxh_map_fill(void *map, double x, double y);
+/* fill_type 0 = full fill, 1 = semi-fill (FILLED | CONTEXTFILLED, the GUI's "context fill", pointdata.cpp:435-441) */
+int dmxh_map_fill_type(void *map, double x, double y, int fill_type);
+/* 1 if the map has context-filled cells that the analyses skip (flags: one byte per filled cell, may be NULL) */
+int dmxh_map_context_skip(void *map, uint8_t *flags);
 int dmxh_map_filled_count(void *map);
 /* flat hot-path inputs (vga_grid arrays); call with NULL arrays to get the sizes */
 void dmxh_map_flat(void *map, int64_t *cells, int64_t *nseg, uint16_t *state, uint32_t *line_off, double *lines);

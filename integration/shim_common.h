@@ -42,6 +42,7 @@ inline int cancel_cb(void *u) {
 struct Ordinals {
     std::vector<PixelRef> cells;   // filled, x-major
     std::vector<int32_t> ord;      // [cols*rows]
+    std::vector<uint8_t> skip;     // per filled cell: context-filled and not even (empty when there is none)
     int64_t n = 0, ghosts = 0;
 };
 inline Ordinals make_ordinals(PointMap &map) {
@@ -49,18 +50,24 @@ inline Ordinals make_ordinals(PointMap &map) {
     const size_t cols = map.getCols(), rows = map.getRows();
     o.ord.assign(cols * rows, -1);
     int64_t unfilled = 0;
+    bool any_skip = false;
     for (size_t i = 0; i < cols; i++)
         for (size_t j = 0; j < rows; j++) {
             PixelRef p((short)i, (short)j);
             if (map.getPoint(p).filled()) {
                 o.ord[i * rows + j] = (int32_t)o.cells.size();
                 o.cells.push_back(p);
+                // skipped as a source, counted but not expanded under a radius (vgavisualglobal.cpp:75, 108-110)
+                const bool skip = map.getPoint(p).contextfilled() && !p.iseven();
+                o.skip.push_back(skip ? 1 : 0);
+                any_skip = any_skip || skip;
             } else {
                 o.ord[i * rows + j] = -(int32_t)(1 + unfilled++);
             }
         }
     o.n = (int64_t)o.cells.size();
     o.ghosts = unfilled;
+    if (!any_skip) o.skip.clear();
     return o;
 }
 
@@ -82,7 +89,6 @@ inline void rows_from_nodes(PointMap &map, const Ordinals &o, std::vector<uint64
     const size_t rows = map.getRows();
     for (int64_t v = 0; v < o.n; v++) {
         Point &pt = map.getPoint(o.cells[(size_t)v]);
-        if (pt.contextfilled()) throw depthmapX::RuntimeException("GPU path: context-filled cells are not supported");
         if (pt.hasNode()) {
             Node &node = pt.getNode();
             node.first();
@@ -128,6 +134,11 @@ inline vga_graph *analysis_graph(PointMap &map, const Ordinals &o, dmx::Contract
     }
     if (rc != VGA_OK) throw depthmapX::RuntimeException(std::string("GPU path: ") + vga_last_error());
     set_refs(g, map, o);
+    if (!o.skip.empty()) {
+        if (any) throw depthmapX::RuntimeException("GPU path: context-filled cells together with merge links are not supported");
+        if (vga_graph_set_noexpand(g, o.skip.data()) != VGA_OK)
+            throw depthmapX::RuntimeException(std::string("GPU path: ") + vga_last_error());
+    }
     return g;
 }
 
@@ -157,7 +168,6 @@ inline vga_graph *graph_from_nodes(PointMap &map, const Ordinals &o) {
     const size_t rows = map.getRows();
     for (int64_t v = 0; v < o.n; v++) {
         Point &pt = map.getPoint(o.cells[(size_t)v]);
-        if (pt.contextfilled()) throw depthmapX::RuntimeException("GPU path: context-filled cells are not supported");
         if (pt.hasNode()) {
             Node &node = pt.getNode();
             node.first();

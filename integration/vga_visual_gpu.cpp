@@ -74,6 +74,7 @@ bool VGAVisualGlobal::run(Communicator *comm, PointMap &map, bool simple_version
                           tk.data(), en.data(), re.data());
     // same calls, same order per row as the reference's formula stage (which value is written when)
     for (int64_t v = 0; v < N; v++) {
+        if (!o.skip.empty() && o.skip[(size_t)v]) continue;  // not a source in the reference
         AttributeRow &row = attributes.getRow(AttributeKey(o.cells[(size_t)v]));
         const int tn = nodes[(size_t)v];
         if (!simple_version) row.setValue(count_col, nc[(size_t)v]);
@@ -124,6 +125,7 @@ bool VGAVisualLocal::run(Communicator *comm, PointMap &map, bool simple_version)
         std::vector<float> a((size_t)N), b((size_t)N), c((size_t)N);
         vga_local_attributes(N, cluster.data(), k.data(), total.data(), control.data(), a.data(), b.data(), c.data());
         for (int64_t v = 0; v < N; v++) {
+            if (!o.skip.empty() && o.skip[(size_t)v]) continue;  // vgavisuallocal.cpp:43
             AttributeRow &row = map.getAttributeTable().getRow(AttributeKey(o.cells[(size_t)v]));
             row.setValue(cluster_col, a[(size_t)v]);
             row.setValue(control_col, b[(size_t)v]);

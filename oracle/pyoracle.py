@@ -267,6 +267,7 @@ def rlib():
         L.dmxref_sample_global.restype = C.c_double
         L.dmxref_sample_global.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.dmxref_merge.argtypes = [C.c_void_p] + [C.c_double] * 4
+        L.dmxref_fill_type.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int]
         L.dmxref_graph_open.restype = C.c_void_p
         L.dmxref_graph_open.argtypes = [C.c_char_p]
         L.dmxref_graph_save.argtypes = [C.c_void_p, C.c_char_p]
@@ -302,7 +303,9 @@ class RefMap:
             rlib().dmxref_destroy(self.h)
             self.h = None
 
-    def fill(self, x, y):
+    def fill(self, x, y, fill_type=0):
+        if fill_type:
+            return bool(rlib().dmxref_fill_type(self.h, x, y, fill_type))
         return bool(rlib().dmxref_fill(self.h, x, y))
 
     def save(self, path):

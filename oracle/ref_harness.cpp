@@ -162,6 +162,12 @@ int dmxref_fill(void *h, double x, double y) {
     return m.makePoints(Point2f(x, y), 0) ? 1 : 0;
 }
 
+// makePoints with a fill type: 0 = full fill, 1 = semi-fill (FILLED | CONTEXTFILLED, the GUI's "context fill")
+int dmxref_fill_type(void *h, double x, double y, int fill_type) {
+    PointMap &m = *static_cast<Ref *>(h)->map;
+    return m.makePoints(Point2f(x, y), fill_type) ? 1 : 0;
+}
+
 int dmxref_block_lines(void *h) { return static_cast<Ref *>(h)->map->blockLines() ? 1 : 0; }
 
 int dmxref_filled_count(void *h) { return static_cast<Ref *>(h)->map->getFilledPointCount(); }

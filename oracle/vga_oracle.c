@@ -7,6 +7,7 @@
 #include <string.h>
 
 #define ST_FILLED 0x0002 /* salalib/point.h:32 */
+#define ST_CONTEXTFILLED 0x0008 /* semi-fill (GUI "context fill"): FILLED | CONTEXTFILLED, pointdata.cpp:435-441 */
 
 /* ---------------------------------------------------------------- geometry (genlib/p2dpoly) */
 
@@ -668,6 +669,13 @@ void vgao_node_attrs(const vgao_graph *gr, float *connectivity, float *first_mom
 
 static inline int64_t cell_of_ref(const vgao_graph *gr, int32_t r) { return (int64_t)ref_x(r) * gr->rows + ref_y(r); }
 
+/* a context-filled cell that is not "even" (PixelRef::iseven, pixelref.h:68-69) is skipped as a source and, when a
+ * radius is set, counted but not expanded (vgavisualglobal.cpp:75, 108-110; vgavisuallocal.cpp:43) */
+static inline int ctx_odd(const vgao_graph *gr, int32_t r) {
+    int64_t c = (int64_t)ref_x(r) * gr->rows + ref_y(r);
+    return (gr->state[c] & ST_CONTEXTFILLED) && !(ref_x(r) % 2 == 0 && ref_y(r) % 2 == 0);
+}
+
 int vgao_global(const vgao_graph *gr, int radius, int64_t src_begin, int64_t src_end, int32_t *total_nodes,
                 int64_t *total_depth, int32_t *dist, int32_t maxl, int32_t *nlevels) {
     int64_t cells = (int64_t)gr->cols * gr->rows;
@@ -683,6 +691,13 @@ int vgao_global(const vgao_graph *gr, int radius, int64_t src_begin, int64_t src
         int32_t stamp = (int32_t)(sidx - src_begin);
         int64_t out = sidx - src_begin;
         int64_t ncur = 0, nnxt = 0;
+        if (ctx_odd(gr, gr->cellref[sidx])) { /* skipped source: the reference writes nothing, total_nodes -1 marks it */
+            total_nodes[out] = -1;
+            total_depth[out] = 0;
+            if (dist) memset(dist + out * maxl, 0, sizeof(int32_t) * maxl);
+            if (nlevels) nlevels[out] = 0;
+            continue;
+        }
         cur[ncur++] = gr->cellref[sidx];
         /* the source is pushed without being marked (misc==0) and finalised when popped; it can
          * never be re-pushed because its misc is ~0 before any other node is expanded */
@@ -701,7 +716,7 @@ int vgao_global(const vgao_graph *gr, int radius, int64_t src_begin, int64_t src
                 td += level;
                 tn += 1;
                 cnt += 1;
-                if (radius == -1 || level < radius) {
+                if (radius == -1 || (level < radius && !ctx_odd(gr, cur[i]))) {
                     int64_t u = gr->ord[c];
                     for (uint64_t e = gr->it_ptr[u]; e < gr->it_ptr[u + 1]; e++) {
                         int64_t wc = cell_of_ref(gr, gr->it.ref[e]);
@@ -802,6 +817,13 @@ int vgao_local(const vgao_graph *gr, int64_t src_begin, int64_t src_end, int64_t
     int64_t hcap = 0;
     for (int64_t v = src_begin; v < src_end; v++) {
         int64_t out = v - src_begin;
+        if (ctx_odd(gr, gr->cellref[v])) { /* skipped cell (vgavisuallocal.cpp:43): k = -1 marks it */
+            cluster[out] = 0;
+            k[out] = -1;
+            total[out] = 0;
+            control[out] = 0.0f;
+            continue;
+        }
         /* contents(): iterated pixels, de-duplicated */
         int64_t nh = 0;
         for (uint64_t e = gr->it_ptr[v]; e < gr->it_ptr[v + 1]; e++) {
@@ -884,6 +906,7 @@ int vgao_step_depth(const vgao_graph *gr, const int32_t *src, int64_t nsrc, int3
             if (depth[u] != -1) continue; /* m_misc == ~0: already finalised */
             depth[u] = level;
             seen[c] = 1;
+            if (level > 0 && ctx_odd(gr, cur[i])) continue; /* marked, not expanded (vgavisualglobaldepth.cpp:53) */
             for (uint64_t e = gr->it_ptr[u]; e < gr->it_ptr[u + 1]; e++) {
                 int64_t wc = cell_of_ref(gr, gr->it.ref[e]);
                 if (!seen[wc]) {

@@ -51,3 +51,36 @@ def test_random_plan_bit_equal_to_reference(seed):
         rm.vga_local()
         for k, v in po.local_formulas(*og.local_ints()).items():
             assert np.array_equal(rm.attr(k), v), k
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("name", ["oblique:20:20:11", "office:24:24:2"])
+def test_context_filled_semantics_oracle_vs_reference(name):
+    """Semi-fill (fill_type 1: FILLED | CONTEXTFILLED): cells that are not "even" are skipped as sources by global and
+    local, counted but not expanded under a radius, and not expanded beyond level 0 by step depth -- the oracle's
+    restatement against the reference's VGAVisualGlobal / VGAVisualLocal / VGAVisualGlobalDepth on the same map."""
+    if not po.have_ref():
+        pytest.skip("compiled reference not present")
+    from depthmapx_b200 import plans
+    plan = plans.by_name(name)
+    r = po.RefMap(plan.walls, plan.spacing)
+    for s in plan.seeds:
+        assert r.fill(*s, fill_type=1)
+    grid = r.grid()
+    assert ((grid.state & 8) != 0).sum() == r.n
+    og = po.OracleGraph(grid)
+    r.makegraph()
+    r.vga_local()
+    r.vga_global(-1.0)
+    r.vga_global(3.0)
+    for radius, suffix in ((-1, ""), (3, " R3")):
+        tn, td, dist, nl = og.global_ints(radius)
+        skipped = tn == -1
+        assert 0 < skipped.sum() < len(tn)
+        for k, v in po.global_formulas(tn, td, dist, nl).items():
+            assert np.array_equal(np.where(skipped, -1.0, v).astype(np.float32), r.attr(k + suffix)), k + suffix
+    cl, k, tot, ctl = og.local_ints()
+    for n_, v in po.local_formulas(cl, np.where(k < 0, 0, k), tot, ctl).items():
+        assert np.array_equal(np.where(k < 0, -1.0, v).astype(np.float32), r.attr(n_)), n_
+    for src in ([5, 40], [0], [17, 18, 19]):
+        assert np.array_equal(og.step_depth(src).astype(np.float32), r.step_depth(src))

@@ -152,3 +152,53 @@ def test_cli_shims_on_linked_graph(files, tmp_path, case):
         r = subprocess.run([gpu_cli, "-f", src, "-o", out] + extra, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout + r.stderr
         assert data(out) == data(os.path.join(d, f"{case}__{want}.graph")), want
+
+
+@pytest.mark.parametrize("case", ["oblique12", "office16"])
+def test_context_filled_map_host_layer_and_cli(files, tmp_path, case):
+    """Semi-filled (FILLED | CONTEXTFILLED) maps: cells that are not "even" are skipped as sources and, under a radius,
+    counted but not expanded (vgavisualglobal.cpp:75, 108-110; vgavisuallocal.cpp:43; vgavisualglobaldepth.cpp:53).  The CLI
+    cannot semi-fill (GUI only), so the filled map is written by the host layer and then taken through makegraph, VGA
+    (radius n and 3, local) and step depth by the unmodified reference CLI, by the CLI with the GPU shims and by the host
+    layer: all three must write the same bytes."""
+    import subprocess
+    from conftest import ROOT
+    ref_cli = os.path.join(ROOT, "oracle", "_ref", "depthmapXcli_ref")
+    gpu_cli = os.path.join(ROOT, "oracle", "_ref", "depthmapXcli_gpu")
+    if not (os.path.exists(ref_cli) and os.path.exists(gpu_cli)):
+        pytest.skip("integration binaries not built (make -C integration)")
+    d, args = files
+    _spec, grid, seed, sdp = args[case][:4]
+    t = str(tmp_path)
+
+    def run(binary, a):
+        r = subprocess.run([binary] + a, cwd=t, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, " ".join(a) + "\n" + r.stdout + r.stderr
+
+    g = capi.GraphFile(os.path.join(d, f"{case}__plan.graph"))
+    m = g.new_map(float(grid))
+    assert m.fill(*[float(x) for x in seed.split(",")], fill_type=1)
+    assert m.context_skip().sum() > 0
+    g.save(os.path.join(t, "ctxfill.graph"))
+    for tag, binary in (("ref", ref_cli), ("gpu", gpu_cli)):
+        run(binary, ["-m", "VISPREP", "-f", "ctxfill.graph", "-o", f"prep_{tag}.graph", "-pm"])
+        run(binary, ["-m", "VGA", "-f", f"prep_{tag}.graph", "-o", f"vga_{tag}.graph", "-vm", "visibility", "-vg", "-vl", "-vr", "n"])
+        run(binary, ["-m", "VGA", "-f", f"vga_{tag}.graph", "-o", f"vga3_{tag}.graph", "-vm", "visibility", "-vg", "-vr", "3"])
+        run(binary, ["-m", "STEPDEPTH", "-f", f"prep_{tag}.graph", "-o", f"sd_{tag}.graph", "-sdp", sdp, "-sdt", "visual"])
+    for name in ("prep", "vga", "vga3", "sd"):
+        assert data(os.path.join(t, f"{name}_ref.graph")) == data(os.path.join(t, f"{name}_gpu.graph")), f"CLI shim: {name}"
+    # host layer
+    g.make_graph()
+    g.save(os.path.join(t, "prep_host.graph"))
+    assert data(os.path.join(t, "prep_host.graph")) == data(os.path.join(t, "prep_ref.graph"))
+    assert m.vga_local() and m.vga_global(-1.0)
+    g.save(os.path.join(t, "vga_host.graph"))
+    assert data(os.path.join(t, "vga_host.graph")) == data(os.path.join(t, "vga_ref.graph"))
+    g3 = capi.GraphFile(os.path.join(t, "vga_ref.graph"))
+    assert g3.map().vga_global(3.0)
+    g3.save(os.path.join(t, "vga3_host.graph"))
+    assert data(os.path.join(t, "vga3_host.graph")) == data(os.path.join(t, "vga3_ref.graph"))
+    g4 = capi.GraphFile(os.path.join(t, "prep_ref.graph"))
+    assert g4.map().step_depth([[float(x) for x in sdp.split(",")]])
+    g4.save(os.path.join(t, "sd_host.graph"))
+    assert data(os.path.join(t, "sd_host.graph")) == data(os.path.join(t, "sd_ref.graph"))
