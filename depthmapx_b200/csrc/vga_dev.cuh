@@ -12,7 +12,11 @@
 
 // Work counters of the CPU emulation used by the tests (tests/emu/): nothing in the CUDA build.
 #ifdef VGA_SIMT_EMULATION
-#define VGA_COUNT(name, n) (simt::counters()[#name] += (long long)(n))
+#define VGA_COUNT(name, n)                                      \
+    do {                                                        \
+        static long long &vga_count_slot__ = simt::counters()[#name]; \
+        vga_count_slot__ += (long long)(n);                     \
+    } while (0)
 #else
 #define VGA_COUNT(name, n) ((void)0)
 #endif

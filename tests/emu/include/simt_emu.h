@@ -14,7 +14,7 @@
 // NOT detected; memory is the host heap ("device" pointers are host pointers).
 #pragma once
 
-#if defined(SIMT_ASM_SWITCH) && !defined(SIMT_USE_UCONTEXT)
+#if defined(__x86_64__) && !defined(SIMT_USE_UCONTEXT)
 #define SIMT_ASM_SWITCH 1
 #else
 #include <ucontext.h>
@@ -401,7 +401,8 @@ extern "C" __attribute__((used, weak)) const char *simt_counters_dump(int reset)
     out = "{";
     for (auto &kv : simt::counters()) out += (out.size() > 1 ? ", \"" : "\"") + kv.first + "\": " + std::to_string(kv.second);
     out += "}";
-    if (reset) simt::counters().clear();
+    if (reset)
+        for (auto &kv : simt::counters()) kv.second = 0;  // slots stay: call sites hold references to them
     return out.c_str();
 }
 
