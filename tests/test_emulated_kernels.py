@@ -118,6 +118,15 @@ def test_experimental_kernels(emu_dir):
     run_gpu_tests_emulated(emu_dir, ["tests/test_zzzz_experimental_gpu.py", "-k", "oblique or holes"])
 
 
+def test_pyramid_schedules_on_a_plan_with_rooms(emu_dir):
+    """office:64 (4,096 cells, deeper level structure, 64 batches): both pyramids with automatic word width, the pyramid
+    pull alone in the hybrid schedule, and the forced pyramid push under a radius."""
+    f = "tests/test_zzzz_experimental_gpu.py::"
+    run_gpu_tests_emulated(emu_dir, [f + "test_pyramid_push_vs_oracle[1-1-2-0--1-office:64:64:1]",
+                                     f + "test_pyramid_pull_vs_oracle[2-1-1--1-office:64:64:1]",
+                                     f + "test_pyramid_push_vs_oracle[2-0-0-1-2-office:64:64:1]"])
+
+
 def test_real_cli_with_gpu_shims(emu_dir):
     """The real depthmapXcli with the shims of integration/ (one plan; the B200 run covers all three)."""
     if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "depthmapXcli_gpu")):
