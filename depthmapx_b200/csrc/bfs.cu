@@ -77,7 +77,7 @@ struct BfsDev {
     const uint64_t *f_runptr;        // [n+1] runs of the (sorted) out-rows, ghost columns excluded
     const uint2 *f_runs;
     const uint64_t *f_costptr;       // [n+1] prefix sums of the pyramid nodes an out-row touches
-    int push_force;                  // bfs_push = 2: every top-down step after level 0 uses the pyramid (tests)
+    int push_force;                  // bfs_push = 2: every top-down step uses the pyramid (tests)
     const uint8_t *noexpand;         // [n] or nullptr: vertices that are counted but never join the frontier (context-filled,
                                      // not even cells under a radius limit)
     int pyr_levels;
@@ -143,6 +143,27 @@ template <int W> __global__ void k_init(BfsDev d, const int32_t *src, int64_t ns
     u64 w = 1ULL << (i & 63);
     d.visited[(b * d.n + v) * W + j] = w;  // a vertex is a source in exactly one word: one writer
     d.frontier[(b * d.n + v) * W + j] = w;
+}
+
+// With the pyramid push available, the step from level 0 (the sources' own rows) also goes through the pyramid when that
+// is cheaper for the batch: one warp per batch sums the row lengths and the run costs of its sources.
+template <int W>
+__global__ void k_init_mode(BfsDev d, const int32_t *src, int64_t nsrc, int nbatch) {
+    const int b = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= nbatch) return;
+    const int64_t s0 = (int64_t)b * 64 * W, s1 = s0 + 64 * W < nsrc ? s0 + 64 * W : nsrc;
+    unsigned long long fe = 0, frc = 0;
+    for (int64_t i = s0 + lane; i < s1; i += 32) {
+        const int64_t v = src[i];
+        fe += d.rowptr[v + 1] - d.rowptr[v];
+        frc += d.f_costptr[v + 1] - d.f_costptr[v];
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        fe += __shfl_down_sync(FULL, fe, o);
+        frc += __shfl_down_sync(FULL, frc, o);
+    }
+    if (lane == 0 && (d.push_force || frc + 2 * (u64)d.n < fe)) d.mode[b] = 2;
 }
 
 // coarse pass (W = 1): the sources of group j (`per_group` consecutive sources) all carry bit j%64 of
@@ -835,7 +856,7 @@ int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, De
             k_push<W, 1><<<grid, TPB, 0, st>>>(d);
         tm.launches++;
         tm.main_launches++;
-        if (d.npyr && level > 0) {
+        if (d.npyr) {
             k_push_pyr<W><<<grid, TPB, 0, st>>>(d);
             tm.launches++;
             tm.main_launches++;
@@ -1176,6 +1197,10 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int6
         VGA_CUDA(cudaStreamSynchronize(st));
         k_init<W><<<blocks_for(cs, 256), 256, 0, st>>>(d, d_order.p + first, cs);
         tm.launches++;
+        if (d.npyr) {
+            k_init_mode<W><<<blocks_for(cb * 32, 256), 256, 0, st>>>(d, d_order.p + first, cs, (int)cb);
+            tm.launches++;
+        }
         mt.start();
         int nlev = 1;
         VGA_TRY(run_levels<W>(ctx, d, cb, radius, bfs_mode, &counts, &lcap, cstride, work.p, mt, &nlev));
