@@ -46,7 +46,7 @@ HOST_SYMBOLS = [
     "dmxh_map_encode_nodes", "dmxh_map_begin_graph", "dmxh_map_finish_graph", "dmxh_map_write_global", "dmxh_map_write_local",
     "dmxh_map_write_step_depth", "dmxh_graph_open", "dmxh_graph_close", "dmxh_graph_save", "dmxh_graph_num_maps",
     "dmxh_graph_displayed_map", "dmxh_graph_map", "dmxh_graph_walls", "dmxh_graph_new_map", "dmxh_graph_make_graph",
-    "dmxh_graph_made", "dmxh_map_fill_type", "dmxh_map_context_skip", "dmxh_map_merge", "dmxh_map_contracted_rows", "dmxh_map_radius_correction",
+    "dmxh_graph_made", "dmxh_map_num_rows", "dmxh_map_fill_type", "dmxh_map_context_skip", "dmxh_map_merge", "dmxh_map_contracted_rows", "dmxh_map_radius_correction",
 ]
 
 LEVEL_PREPARE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32))
@@ -152,6 +152,8 @@ def host():
         H.dmxh_graph_made.argtypes = [vp]
         H.dmxh_map_merge.argtypes = [vp] + [C.c_double] * 4
         H.dmxh_map_fill_type.argtypes = [vp, C.c_double, C.c_double, C.c_int]
+        H.dmxh_map_num_rows.restype = i64
+        H.dmxh_map_num_rows.argtypes = [vp]
         H.dmxh_map_context_skip.argtypes = [vp, vp]
         H.dmxh_map_contracted_rows.argtypes = [vp] * 6
         H.dmxh_map_radius_correction.argtypes = [vp, C.c_int, LEVEL_PREPARE_FN, LEVEL_RUN_FN, vp, vp, vp, vp, C.c_int32]
@@ -460,10 +462,11 @@ class HostMap:
     def columns(self):
         buf = C.create_string_buffer(8192)
         host().dmxh_map_columns(self.h, buf, 8192)
-        return [s for s in buf.value.decode().split("\n") if s]
+        return [s for s in buf.value.decode(errors="replace").split("\n") if s]
 
     def attr(self, name):
-        out = np.zeros(self.n, np.float32)
+        rows = int(host().dmxh_map_num_rows(self.h))  # cells that had a Node made (= filled cells of a made graph)
+        out = np.zeros(max(rows, 1), np.float32)[:rows]
         if not host().dmxh_map_attr(self.h, name.encode(), _p(out)):
             raise KeyError(name)
         return out

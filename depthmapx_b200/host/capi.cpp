@@ -112,11 +112,13 @@ int dmxh_map_columns(void *map, char *buf, int buflen) {
     return (int)t.getNumColumns();
 }
 
+int64_t dmxh_map_num_rows(void *map) { return (int64_t)static_cast<dmx::PointMap *>(map)->getAttributeTable().getNumRows(); }
+
 int dmxh_map_attr(void *map, const char *name, float *out) {
     const dmx::AttributeTable &t = static_cast<dmx::PointMap *>(map)->getAttributeTable();
     int c = t.getColumnIndex(name);
     if (c < 0) return 0;
-    std::memcpy(out, t.column(c).data(), t.getNumRows() * sizeof(float));
+    std::memcpy(out, t.column(c).data(), t.getNumRows() * sizeof(float));  // dmxh_map_num_rows floats
     return 1;
 }
 

@@ -56,6 +56,10 @@ void ByteReader::skip(size_t n) {
     m_pos += n;
 }
 
+void ByteReader::expect(uint64_t count, uint64_t min_bytes_each) const {
+    if (min_bytes_each && count > (m_size - m_pos) / min_bytes_each) throw RuntimeException("graph file: a count exceeds the data that is left");
+}
+
 std::string ByteReader::str() {  // dXstring::readString, genlib/stringutils.cpp:40-50
     const uint32_t len = get<uint32_t>();
     if (len > m_size - m_pos) throw RuntimeException("graph file: string runs past the end of data");
@@ -92,6 +96,8 @@ bool AttributeTable::read(ByteReader &in) {
     clear();
     m_layers = read_layers(in);
     const int32_t colcount = in.get<int32_t>();
+    if (colcount < 0) throw RuntimeException("graph file: negative column count");
+    in.expect((uint64_t)colcount, 4 + 4 + 4 + 8 + 4 + 1 + 1 + sizeof(DisplayParams) + 4);
     std::map<size_t, Column> tmp;
     for (int j = 0; j < colcount; j++) {
         Column c;
@@ -109,6 +115,8 @@ bool AttributeTable::read(ByteReader &in) {
     for (auto &kv : tmp) m_columns.push_back(kv.second);
     m_cols.assign(m_columns.size(), std::vector<float>());
     const int32_t rowcount = in.get<int32_t>();
+    if (rowcount < 0) throw RuntimeException("graph file: negative row count");
+    in.expect((uint64_t)rowcount, 4 + 8 + 4 + 4 * m_columns.size());
     m_keys.resize((size_t)rowcount);
     m_layer_keys.resize((size_t)rowcount);
     for (auto &c : m_cols) c.resize((size_t)rowcount);
@@ -218,6 +226,7 @@ static void read_node(ByteReader &in, NodeStore &ns) {
     }
     for (int i = 0; i < 32; i++) {
         const uint32_t n = in.get<uint32_t>();
+        in.expect(n, sizeof(PixelRef));
         ns.occl_off.push_back((uint32_t)ns.occl.size());
         for (uint32_t k = 0; k < n; k++) ns.occl.push_back(in.get<PixelRef>());
     }
@@ -275,6 +284,7 @@ bool PointMap::read(ByteReader &in) {
     m_spacing = in.get<double>();
     const int32_t rows = in.get<int32_t>(), cols = in.get<int32_t>();
     if (rows < 0 || cols < 0 || rows > 32767 || cols > 32767) throw RuntimeException("graph file: bad grid size");
+    in.expect((uint64_t)rows * (uint64_t)cols, 34);  // a Point record without a Node is 34 bytes
     m_rows = (size_t)rows;
     m_cols = (size_t)cols;
     m_filled_point_count = in.get<int32_t>();
@@ -305,6 +315,16 @@ bool PointMap::read(ByteReader &in) {
     }
     m_nodes.occl_off.push_back((uint32_t)m_nodes.occl.size());
     m_nodes_valid = true;
+    {
+        int filled = 0;
+        for (const Point &pt : m_points) filled += pt.filled() ? 1 : 0;
+        if (filled != m_filled_point_count) throw RuntimeException("graph file: the stored filled-point count does not match the cell states");
+        // attribute rows belong to filled cells that have a Node, in key order
+        for (int key : m_attributes.keys()) {
+            const PixelRef p(key);
+            if (!includes(p) || !getPoint(p).filled()) throw RuntimeException("graph file: attribute row of a cell that is not filled");
+        }
+    }
     m_selection_set.clear();
     m_has_selection = false;
     m_initialised = true;
@@ -362,7 +382,10 @@ void PointMap::flattenNodes(FlatRows &out) {
                 for (uint32_t k = 0; k < b.nruns; k++) {
                     const NodeStore::Run &r = ns.runs[b.first_run + k];
                     if (b.dir == NODIR) continue;
-                    for (PixelRef p = r.start; run_col(p, b.dir) <= run_col(r.end, b.dir); run_move(p, b.dir)) {
+                    // start .. end along the run's axis; counted in int so that a run ending at 32767 terminates
+                    const int cells_in_run = (int)run_col(r.end, b.dir) - (int)run_col(r.start, b.dir) + 1;
+                    PixelRef p = r.start;
+                    for (int k2 = 0; k2 < cells_in_run; k2++, run_move(p, b.dir)) {
                         out.ref.push_back(int(p));
                         out.bin.push_back((uint8_t)i);
                     }
@@ -624,6 +647,8 @@ void read_drawing_layer(ByteReader &in, std::vector<Line> &walls) {
     in.skip(1);                               // editable
     in.skip(32 + 4 + 4 + 4 + 4);              // region, rows, cols, next object ref, deprecated int
     const int32_t nshapes = in.get<int32_t>();
+    if (nshapes < 0) throw RuntimeException("graph file: negative shape count");
+    in.expect((uint64_t)nshapes, 4 + 1 + 40 + 32 + 4);
     std::vector<Line> lines;
     for (int32_t j = 0; j < nshapes; j++) {
         in.skip(4);  // key (std::map order = file order)
@@ -637,6 +662,7 @@ void read_drawing_layer(ByteReader &in, std::vector<Line> &walls) {
         in.raw(&region, 40);
         in.skip(16 + 8 + 8);  // centroid, area, perimeter
         const uint32_t npts = in.get<uint32_t>();
+        in.expect(npts, sizeof(Point2f));
         std::vector<Point2f> pts(npts);
         if (npts) in.raw(pts.data(), npts * sizeof(Point2f));
         const bool closed = (type & 0x40) != 0, poly = (type & 0x04) != 0;
@@ -762,6 +788,8 @@ int GraphFile::readFromBuffer(const char *data, size_t size) {
         if (have_type && type == 'p') {
             m_displayed_pointmap = in.get<int32_t>();
             const int32_t count = in.get<int32_t>();
+            if (count < 0 || m_displayed_pointmap < -1 || m_displayed_pointmap >= std::max(count, 1))
+                throw RuntimeException("graph file: bad point map count / displayed map");
             for (int32_t i = 0; i < count; i++) {
                 m_point_maps.emplace_back(new PointMap(m_region, m_walls));
                 m_point_maps.back()->read(in);

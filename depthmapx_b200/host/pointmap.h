@@ -48,7 +48,8 @@ struct PixelRef {
     PixelRef() = default;
     PixelRef(int ax, int ay) : x((short)ax), y((short)ay) {}
     explicit PixelRef(int packed) : x((short)(packed >> 16)), y((short)(packed & 0xffff)) {}
-    operator int() const { return (int(x) << 16) + (int(y) & 0xffff); }
+    // (int(x) << 16) + (int(y) & 0xffff) of the reference (pixelref.h:81-82), written without shifting a negative value
+    operator int() const { return (int)(((unsigned)(unsigned short)x << 16) | (unsigned)(unsigned short)y); }
 };
 
 struct Point {
@@ -136,6 +137,8 @@ class ByteReader {
         return v;
     }
     std::string str();  // dXstring::readString: u32 length + bytes
+    // a count read from the file must be coverable by the bytes that are left (guards allocations against damaged files)
+    void expect(uint64_t count, uint64_t min_bytes_each) const;
 
   private:
     const char *m_data;

@@ -33,7 +33,8 @@ int dmxh_map_make_graph(void *map, int boundarygraph, double maxdist);
 int dmxh_map_vga_global(void *map, double radius, int simple_version);
 int dmxh_map_vga_local(void *map, int simple_version);
 int dmxh_map_columns(void *map, char *buf, int buflen); /* '\n' separated, returns the count */
-int dmxh_map_attr(void *map, const char *name, float *out /* one per filled cell, x-major */);
+int64_t dmxh_map_num_rows(void *map); /* attribute rows = cells that had a Node made */
+int dmxh_map_attr(void *map, const char *name, float *out /* dmxh_map_num_rows values, x-major */);
 int dmxh_map_grid_connections(void *map, uint8_t *out /* one per filled cell */);
 void *dmxh_map_graph(void *map); /* vga_graph* of include/vga_b200.h, owned by the map */
 int dmxh_map_state(void *map, uint16_t *state /* cols*rows, x-major */);

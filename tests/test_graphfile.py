@@ -385,3 +385,50 @@ def test_loaded_map_equals_the_references_view(files, case, kind):
     st = np.zeros(m.cols * m.rows, np.uint16)
     po.rlib().dmxref_state(r.h, st.ctypes.data)
     assert np.array_equal(m.state(), st)
+
+
+def test_damaged_files_are_rejected_not_crashed(tmp_path):
+    """Random corruption (byte flips, overwritten counts, truncation) of a reference-written file: the reader either
+    loads it or reports it, in a subprocess so that a crash or a runaway allocation would show as a failure."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    fx = golden("graphfiles")
+    src = tmp_path / "good.graph"
+    src.write_bytes(fx["oblique12__vga_l"].tobytes())
+    script = f"""
+import sys, resource
+sys.path.insert(0, {ROOT!r})
+resource.setrlimit(resource.RLIMIT_AS, (4 << 30, 4 << 30))
+import numpy as np
+from depthmapx_b200 import capi
+good = open({str(src)!r}, 'rb').read()
+rng = np.random.default_rng(7)
+loaded = rejected = 0
+for trial in range(300):
+    b = bytearray(good)
+    kind = trial % 3
+    if kind == 0:
+        for _ in range(int(rng.integers(1, 6))):
+            b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+    elif kind == 1:
+        p = int(rng.integers(0, len(b) - 4))
+        b[p:p + 4] = int(rng.integers(0, 2 ** 32)).to_bytes(4, 'little')
+    else:
+        b = b[:int(rng.integers(8, len(b)))]
+    open({str(tmp_path / 'bad.graph')!r}, 'wb').write(bytes(b))
+    try:
+        g = capi.GraphFile({str(tmp_path / 'bad.graph')!r})
+        if g.num_maps:
+            m = g.map(0)
+            m.flat_rows(); m.bins(); m.columns()
+            g.save({str(tmp_path / 'out.graph')!r})
+        loaded += 1
+    except (RuntimeError, MemoryError):
+        rejected += 1
+print('OK', loaded, rejected)
+"""
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout[-500:] + r.stderr[-2000:]
+    loaded, rejected = [int(x) for x in r.stdout.split()[1:3]]
+    assert loaded > 0 and rejected > 0
