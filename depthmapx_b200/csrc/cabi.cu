@@ -334,6 +334,15 @@ int vga_graph_from_csr(vga_ctx *ctx, int64_t n_cells, int64_t n_ghosts, const ui
     cudaStream_t st = ctx->stream;
     const int64_t entries = (int64_t)rowptr[n_cells];
     if (entries > 0 && !col) return VGA_ERR_INVALID;
+    if (rowptr[0] != 0) {
+        set_error("vga_graph_from_csr: rowptr must start at 0");
+        return VGA_ERR_INVALID;
+    }
+    for (int64_t v = 0; v < n_cells; v++)
+        if (rowptr[v] > rowptr[v + 1]) {
+            set_error("vga_graph_from_csr: rowptr is not non-decreasing");
+            return VGA_ERR_INVALID;
+        }
     for (int64_t e = 0; e < entries; e++)
         if ((int64_t)col[e] >= n_cells + n_ghosts) {
             set_error("vga_graph_from_csr: column index out of range");
