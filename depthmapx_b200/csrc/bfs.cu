@@ -35,6 +35,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <numeric>
 
 #include "pyramid.cuh"
@@ -77,6 +78,8 @@ struct BfsDev {
     const uint64_t *f_runptr;        // [n+1] runs of the (sorted) out-rows, ghost columns excluded
     const uint2 *f_runs;
     const uint64_t *f_costptr;       // [n+1] prefix sums of the pyramid nodes an out-row touches
+    const uint32_t *f_nodes;         // bfs_pyr_nodes = 1: per row the ids of the pyramid nodes tiling its runs (id < n: leaf =
+    const uint32_t *t_nodes;         // the vertex itself, id >= n: inner node id - n); row offsets = f_costptr / t_costptr
     int push_force;                  // bfs_push = 2: every top-down step uses the pyramid (tests)
     const uint8_t *noexpand;         // [n] or nullptr: vertices that are counted but never join the frontier (context-filled,
                                      // not even cells under a radius limit)
@@ -418,6 +421,161 @@ template <int W> __global__ void __launch_bounds__(TPB) k_pyr_down(BfsDev d, int
     for (int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x; t < groups; t += (int64_t)gridDim.x * TPB) {
         VGA_COUNT(pyr_down_groups, 1);
         pyr_down_group<W>(dst, c0, s1, c1, s2, c2, s3, c3, t);
+    }
+}
+
+// ---- node-id lists (bfs_pyr_nodes = 1): the pyramid steps with the inner loops of the entry kernels ------------------
+// A row's runs are replaced by the ids of the pyramid nodes that tile them, so the top-down and bottom-up steps need no
+// per-run decomposition: they are k_push / k_pull over id lists, where an id < n addresses the vertex's own word and an
+// id >= n the inner node id - n of the batch's pyramid.
+
+// ids of the nodes of every run, written at the run's offset (exclusive scan of the per-run node counts)
+__global__ void k_emit_nodes(const uint2 *runs, int64_t nruns, const u64 *node_off, uint32_t n, BfsDev d, uint32_t *out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nruns) return;
+    const uint2 run = runs[r];
+    uint64_t o = node_off[r];
+    pyr_decompose(run.x, run.y, [&](int k, uint32_t i) { out[o++] = k == 0 ? i : n + (uint32_t)d.pyr_off[k] + i; });
+}
+__global__ void k_run_costs(const uint2 *runs, int64_t nruns, u64 *cost) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < nruns) cost[r] = (u64)pyr_cost(runs[r].x, runs[r].y);
+}
+
+// top-down step over node-id lists: k_push with the target word itself as the read-before-atomic filter (k_update drops
+// words that only repeat reached sources, as for k_push_pyr)
+template <int W> __global__ void __launch_bounds__(TPB) k_push_nodes(BfsDev d) {
+    const int b = blockIdx.y;
+    if (!d.active[b] || d.mode[b] != 2) return;
+    const int lane = threadIdx.x & 31;
+    const u64 *fr = d.frontier + (int64_t)b * d.n * W;
+    u64 *nx = d.next + (int64_t)b * d.n * W;
+    u64 *np = d.npyr + (int64_t)b * d.pyr_total * W;
+    const uint32_t n = (uint32_t)d.n;
+    for (int64_t base = (int64_t)blockIdx.x * TPB; base < d.n; base += (int64_t)gridDim.x * TPB) {
+        int64_t u = base + threadIdx.x;
+        u64 f[W];
+#pragma unroll
+        for (int j = 0; j < W; j++) f[j] = 0ULL;
+        if (u < d.n) ldw<W>(fr + u * W, f);
+        u64 anyf = 0ULL;
+#pragma unroll
+        for (int j = 0; j < W; j++) anyf |= f[j];
+        uint64_t my0 = 0, my1 = 0;
+        if (anyf != 0ULL) {
+            my0 = d.f_costptr[u];
+            my1 = d.f_costptr[u + 1];
+        }
+        unsigned m = __ballot_sync(FULL, anyf != 0ULL);
+        while (m) {
+            int src_lane = __ffs(m) - 1;
+            m &= m - 1;
+            u64 fw[W];
+#pragma unroll
+            for (int j = 0; j < W; j++) fw[j] = __shfl_sync(FULL, f[j], src_lane);
+            uint64_t e0 = __shfl_sync(FULL, my0, src_lane), e1 = __shfl_sync(FULL, my1, src_lane);
+            for (uint64_t e = e0 + lane; e < e1; e += 32) {
+                const uint32_t c = d.f_nodes[e];
+                VGA_COUNT(npush_nodes, 1);
+                u64 *p = c < n ? nx + (int64_t)c * W : np + (int64_t)(c - n) * W;
+                u64 cur[W];
+                ldw<W>(p, cur);
+#pragma unroll
+                for (int j = 0; j < W; j++) {
+                    u64 add = fw[j] & ~cur[j];
+                    if (add) {
+                        atomicOr(&p[j], add);
+                        VGA_COUNT(npush_atomics, 1);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// bottom-up step over node-id lists: k_pull with the frontier words of leaves and the frontier pyramid's inner nodes
+template <int W> __global__ void __launch_bounds__(TPB) k_pull_nodes(BfsDev d, int level) {
+    const int b = blockIdx.y;
+    if (!d.active[b] || d.mode[b] != 1) return;
+    const int lane = threadIdx.x & 31;
+    const u64 *fr = d.frontier + (int64_t)b * d.n * W;
+    const u64 *vis = d.visited + (int64_t)b * d.n * W;
+    const u64 *pyr = d.pyr + (int64_t)b * d.pyr_total * W;
+    u64 *nx = d.next + (int64_t)b * d.n * W;
+    const uint8_t *lvl = d.lvl_in ? d.lvl_in + (int64_t)(b / d.group) * d.n : nullptr;
+    const uint32_t n = (uint32_t)d.n;
+    u64 valid[W];
+#pragma unroll
+    for (int j = 0; j < W; j++) valid[j] = d.valid[(int64_t)b * W + j];
+    for (int64_t base = (int64_t)blockIdx.x * TPB; base < d.n; base += (int64_t)gridDim.x * TPB) {
+        int64_t w = base + threadIdx.x;
+        u64 need[W];
+#pragma unroll
+        for (int j = 0; j < W; j++) need[j] = 0ULL;
+        u64 anyneed = 0ULL;
+        if (w < d.n && !(lvl && (int)lvl[w] > level + 1)) {
+            u64 vv[W];
+            ldw<W>(vis + w * W, vv);
+#pragma unroll
+            for (int j = 0; j < W; j++) {
+                need[j] = valid[j] & ~vv[j];
+                anyneed |= need[j];
+            }
+        }
+        uint64_t my0 = 0, my1 = 0;
+        if (anyneed != 0ULL) {
+            my0 = d.t_costptr[w];
+            my1 = d.t_costptr[w + 1];
+        }
+        const unsigned m = __ballot_sync(FULL, anyneed != 0ULL);
+        const int ncand = __popc(m);
+        const int grp = lane >> 3, gl = lane & 7;
+        const unsigned gmask = 0xffu << (grp * 8);
+        for (int r = 0; r * 4 < ncand; r++) {
+            const int k = r * 4 + grp;
+            const bool has = k < ncand;
+            const int src_lane = has ? (int)__fns(m, 0, k + 1) : 0;
+            u64 nd[W];
+#pragma unroll
+            for (int j = 0; j < W; j++) nd[j] = __shfl_sync(FULL, need[j], src_lane);
+            const uint64_t e0 = __shfl_sync(FULL, my0, src_lane), e1 = __shfl_sync(FULL, my1, src_lane);
+            if (has) {
+                u64 acc[W];
+#pragma unroll
+                for (int j = 0; j < W; j++) acc[j] = 0ULL;
+                for (uint64_t e = e0; e < e1; e += 16) {
+                    const uint64_t ea = e + gl, eb = e + 8 + gl;
+                    u64 g0[W], g1[W];
+#pragma unroll
+                    for (int j = 0; j < W; j++) g0[j] = g1[j] = 0ULL;
+                    uint32_t ca = 0, cb = 0;
+                    if (ea < e1) ca = d.t_nodes[ea];
+                    if (eb < e1) cb = d.t_nodes[eb];
+                    VGA_COUNT(npull_nodes, (ea < e1) + (eb < e1));
+                    if (ea < e1) ldw<W>(ca < n ? fr + (int64_t)ca * W : pyr + (int64_t)(ca - n) * W, g0);
+                    if (eb < e1) ldw<W>(cb < n ? fr + (int64_t)cb * W : pyr + (int64_t)(cb - n) * W, g1);
+                    bool done = true;
+#pragma unroll
+                    for (int j = 0; j < W; j++) {
+                        u64 gj = g0[j] | g1[j];
+                        unsigned lo = __reduce_or_sync(gmask, (unsigned)gj);
+                        unsigned hi = __reduce_or_sync(gmask, (unsigned)(gj >> 32));
+                        acc[j] |= ((u64)hi << 32) | lo;
+                        done = done && ((acc[j] & nd[j]) == nd[j]);
+                    }
+                    if (done) break;
+                }
+                if (gl == 0) {
+                    const int64_t ww = (base + (threadIdx.x & ~31)) + src_lane;
+#pragma unroll
+                    for (int j = 0; j < W; j++) {
+                        u64 nw = acc[j] & nd[j];
+                        if (nw) nx[ww * W + j] = nw;
+                    }
+                }
+            }
+            __syncwarp();
+        }
     }
 }
 
@@ -857,7 +1015,10 @@ int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, De
         tm.launches++;
         tm.main_launches++;
         if (d.npyr) {
-            k_push_pyr<W><<<grid, TPB, 0, st>>>(d);
+            if (d.f_nodes)
+                k_push_nodes<W><<<grid, TPB, 0, st>>>(d);
+            else
+                k_push_pyr<W><<<grid, TPB, 0, st>>>(d);
             tm.launches++;
             tm.main_launches++;
             int kmax = 0;
@@ -879,7 +1040,10 @@ int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, De
                     tm.launches++;
                     tm.main_launches++;
                 }
-                k_pull_pyr<W><<<grid, TPB, 0, st>>>(d, level);
+                if (d.t_nodes)
+                    k_pull_nodes<W><<<grid, TPB, 0, st>>>(d, level);
+                else
+                    k_pull_pyr<W><<<grid, TPB, 0, st>>>(d, level);
             } else {
                 k_pull<W><<<grid, TPB, 0, st>>>(d, level);
             }
@@ -1026,6 +1190,8 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int6
     if (pyr_pull) VGA_TRY(ensure_runs(ctx, g));
     const bool pyr_push = ctx->opt.bfs_push >= 1 && pl.levels <= PYR_LEVELS_DEV && n > 1;
     if (pyr_push) VGA_TRY(ensure_fwd_runs(ctx, g));
+    const bool node_lists = ctx->opt.bfs_pyr_nodes == 1 && (pyr_push || pyr_pull);
+    if (node_lists) VGA_TRY(ensure_node_lists(ctx, g, pyr_push, pyr_pull));
     kt.stop();
     const double w1 = wall();
 
@@ -1116,6 +1282,8 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int6
     d.noexpand = (radius != -1 && g->noexpand.p) ? g->noexpand.p : nullptr;
     d.npyr = npyr_p;
     d.push_force = ctx->opt.bfs_push == 2 ? 1 : 0;
+    d.f_nodes = (node_lists && pyr_push) ? g->f_nodes.p : nullptr;
+    d.t_nodes = (node_lists && pyr_pull) ? g->t_nodes.p : nullptr;
     d.f_runptr = pyr_push ? g->f_runptr.p : nullptr;
     d.f_runs = pyr_push ? g->f_runs.p : nullptr;
     d.f_costptr = pyr_push ? g->f_costptr.p : nullptr;
@@ -1159,6 +1327,8 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int6
             c.t_costptr = nullptr;
             c.npyr = nullptr;
             c.f_costptr = nullptr;
+            c.f_nodes = nullptr;
+            c.t_nodes = nullptr;
             h_valid.assign((size_t)ng, ~0ULL);
             if (ngroups & 63) h_valid[(size_t)ng - 1] = (1ULL << (ngroups & 63)) - 1ULL;
             ones.assign((size_t)ng, 1);
@@ -1367,6 +1537,56 @@ int ensure_fwd_runs(vga_ctx *ctx, vga_graph *g) {
     if (g->has_fwd_runs) return VGA_OK;
     VGA_TRY(build_runs(ctx, g->n, g->rowptr.p, g->adj.p, 6, g->f_runptr, g->f_runs, g->f_costptr, &g->f_nruns));
     g->has_fwd_runs = true;
+    return VGA_OK;
+}
+
+// node-id lists from runs: per-run node counts -> exclusive scan -> ids written at the run's offset
+static int build_nodes(vga_ctx *ctx, int64_t n, const DevBuf<uint2> &runs, int64_t nruns, DevBuf<uint32_t> &nodes) {
+    cudaStream_t st = ctx->stream;
+    const PyrLayout pl = pyr_layout(n);
+    BfsDev d0;
+    memset(&d0, 0, sizeof(d0));
+    d0.pyr_levels = pl.levels;
+    for (int k = 0; k < PYR_LEVELS_DEV; k++) {
+        d0.pyr_off[k] = pl.off[k];
+        d0.pyr_cnt[k] = pl.cnt[k];
+    }
+    DevBuf<u64> cost, off;
+    DevBuf<unsigned char> tmp;
+    VGA_TRY(cost.alloc_zero((size_t)nruns + 1, st));
+    VGA_TRY(off.alloc((size_t)nruns + 1));
+    if (nruns > 0) {
+        k_run_costs<<<blocks_for(nruns, 256), 256, 0, st>>>(runs.p, nruns, cost.p);
+        ctx->timing.launches++;
+    }
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, cost.p, off.p, (int)(nruns + 1), st);
+    VGA_TRY(tmp.alloc(tb + 16));
+    VGA_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, cost.p, off.p, (int)(nruns + 1), st));
+    uint64_t total = 0;
+    VGA_CUDA(cudaMemcpyAsync(&total, off.p + nruns, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    VGA_CUDA(cudaStreamSynchronize(st));
+    VGA_TRY(nodes.alloc((size_t)total + 1));
+    if (nruns > 0) {
+        k_emit_nodes<<<blocks_for(nruns, 256), 256, 0, st>>>(runs.p, nruns, off.p, (uint32_t)n, d0, nodes.p);
+        ctx->timing.launches += 2;
+    }
+    VGA_CUDA(cudaStreamSynchronize(st));
+    VGA_CUDA(cudaGetLastError());
+    return VGA_OK;
+}
+
+int ensure_node_lists(vga_ctx *ctx, vga_graph *g, bool fwd, bool transposed) {
+    if (fwd && !g->has_f_nodes) {
+        VGA_TRY(ensure_fwd_runs(ctx, g));
+        VGA_TRY(build_nodes(ctx, g->n, g->f_runs, g->f_nruns, g->f_nodes));
+        g->has_f_nodes = true;
+    }
+    if (transposed && !g->has_t_nodes) {
+        VGA_TRY(ensure_runs(ctx, g));
+        VGA_TRY(build_nodes(ctx, g->n, g->t_runs, g->t_nruns, g->t_nodes));
+        g->has_t_nodes = true;
+    }
     return VGA_OK;
 }
 

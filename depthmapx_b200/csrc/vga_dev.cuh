@@ -135,6 +135,8 @@ struct Options {
     int64_t bfs_push = 0;        // top-down step: 0 = adjacency entries (k_push); 1 = additionally range-OR updates over the
                                  // runs of the out-rows through a pyramid of `next` (k_push_pyr + k_pyr_down) whenever the
                                  // per-batch cost model prefers them (EXPERIMENTAL, opt-in; validated under SIMT emulation)
+    int64_t bfs_pyr_nodes = 0;   // with bfs_push / bfs_pull = 1: rows as lists of pyramid NODE ids instead of runs, walked by
+                                 // copies of the entry kernels' inner loops (k_push_nodes / k_pull_nodes; EXPERIMENTAL, opt-in)
     int64_t bfs_pull = 0;        // bottom-up step: 0 scans in-row entries (k_pull); 1 = range-OR queries over an
                                  // OR-pyramid of the frontier with run-length in-rows (k_pull_pyr; EXPERIMENTAL, opt-in,
                                  // index logic unit-tested on CPU, kernels not yet run on a GPU)
@@ -209,6 +211,9 @@ struct vga_graph {
     vga::DevBuf<uint64_t> f_costptr;
     bool has_fwd_runs = false;
     int64_t f_nruns = 0;
+    // node-id lists (bfs_pyr_nodes = 1): the pyramid nodes tiling each row's runs; row offsets = f_costptr / t_costptr
+    vga::DevBuf<uint32_t> f_nodes, t_nodes;
+    bool has_f_nodes = false, has_t_nodes = false;
 };
 
 namespace vga {
@@ -218,6 +223,7 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *g, int64_t src_begin, int64_t src
 int ensure_transpose(vga_ctx *ctx, vga_graph *g);
 int ensure_runs(vga_ctx *ctx, vga_graph *g);
 int ensure_fwd_runs(vga_ctx *ctx, vga_graph *g);
+int ensure_node_lists(vga_ctx *ctx, vga_graph *g, bool fwd, bool transposed);
 // cabi.cu: per-segment ascending sort of 32-bit keys (cub::DeviceSegmentedSort in slices of < 2^31 entries)
 int sort_segments_u32(vga_ctx *ctx, uint32_t *keys_in, uint32_t *keys_out, int64_t entries, int64_t rows, const uint64_t *rowptr);
 // spatially coherent order of the sources [src_begin, src_end) for 64-source batches

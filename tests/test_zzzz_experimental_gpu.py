@@ -125,6 +125,28 @@ def test_rank_sort_vs_oracle(name):
     d.close()
 
 
+@pytest.mark.parametrize("name", ["oblique:30:30:7", "office:64:64:1", "urban:120:120:4"])
+@pytest.mark.parametrize("radius", [-1, 2])
+@pytest.mark.parametrize("push,pull,mode,words,coarse", [(1, 1, 2, 0, 0), (2, 0, 0, 1, 1), (0, 1, 1, 2, 1), (2, 1, 2, 4, 0)])
+def test_pyramid_node_lists_vs_oracle(name, radius, push, pull, mode, words, coarse):
+    """bfs_pyr_nodes = 1: rows as lists of pyramid node ids, walked by k_push_nodes / k_pull_nodes (the inner loops of the
+    entry kernels) instead of per-run decompositions."""
+    flat, og = oracle_for(name)
+    c = capi.Context(0)
+    for k, v in (("bfs_pyr_nodes", 1), ("bfs_push", push), ("bfs_pull", pull), ("bfs_mode", mode), ("bfs_words", words),
+                 ("bfs_coarse", coarse)):
+        c.set_option(k, v)
+    g = c.build(flat)
+    tn, td, dist, used = g.global_ints(radius)
+    rng = np.random.RandomState(9)
+    for s in rng.choice(g.n, min(g.n, 96), replace=False):
+        otn, otd, odist, onl = og.global_ints(radius, (int(s), int(s) + 1), maxl=64)
+        L = dist.shape[1]
+        assert otn[0] == tn[s] and otd[0] == td[s]
+        assert np.array_equal(odist[0, :L], dist[s]) and not odist[0, L:].any()
+    c.close()
+
+
 def test_pyramid_paths_equal_default_on_c2():
     """Full-size C2: pyramid push + pull together must give exactly the integers of the default schedule."""
     flat = capi.prepare(plans.by_name("C2"))
@@ -136,6 +158,14 @@ def test_pyramid_paths_equal_default_on_c2():
     b.set_option("bfs_push", 1)
     got = b.build(flat).global_ints(-1)
     b.close()
+    assert ref[3] == got[3]
+    for x, y in zip(ref[:3], got[:3]):
+        assert np.array_equal(x, y)
+    c = capi.Context(0)
+    for k, v in (("bfs_pull", 1), ("bfs_push", 1), ("bfs_coarse", 0), ("bfs_pyr_nodes", 1)):
+        c.set_option(k, v)
+    got = c.build(flat).global_ints(-1)
+    c.close()
     assert ref[3] == got[3]
     for x, y in zip(ref[:3], got[:3]):
         assert np.array_equal(x, y)

@@ -23,6 +23,8 @@ tail -40 gpurun_out/r2_pytest.log
   echo "== C2 bfs_push=1 bfs_pull=1 bfs_words=2"; python tools/gpu_time.py C2 global bfs_push=1 bfs_pull=1 bfs_words=2
   echo "== C2 pyramids, no coarse pass"; python tools/gpu_time.py C2 global bfs_push=1 bfs_pull=1 bfs_coarse=0
   echo "== C2 pyramids, no coarse pass, words=2"; python tools/gpu_time.py C2 global bfs_push=1 bfs_pull=1 bfs_coarse=0 bfs_words=2
+  echo "== C2 pyramids as node lists, no coarse"; python tools/gpu_time.py C2 global bfs_push=1 bfs_pull=1 bfs_coarse=0 bfs_pyr_nodes=1
+  echo "== C2 pyramids as node lists, no coarse, words=2"; python tools/gpu_time.py C2 global bfs_push=1 bfs_pull=1 bfs_coarse=0 bfs_pyr_nodes=1 bfs_words=2
   echo "== C2 bfs_push_unroll=4"; python tools/gpu_time.py C2 global bfs_push_unroll=4
   echo "== C2 bfs_push_unroll=4 bfs_pull=1"; python tools/gpu_time.py C2 global bfs_push_unroll=4 bfs_pull=1
   echo "== C4 slice default";  VGA_TIME_SRC=16384 python tools/gpu_time.py C4 global
@@ -33,6 +35,8 @@ tail -40 gpurun_out/r2_pytest.log
   echo "== C5 slice bfs_push=1 bfs_pull=1 words=4"; VGA_TIME_SRC=32768 python tools/gpu_time.py C5 global bfs_push=1 bfs_pull=1 bfs_words=4
   echo "== C5 slice pyramids, no coarse pass"; VGA_TIME_SRC=32768 python tools/gpu_time.py C5 global bfs_push=1 bfs_pull=1 bfs_coarse=0
   echo "== C5 slice pyramids, no coarse pass, words=4"; VGA_TIME_SRC=32768 python tools/gpu_time.py C5 global bfs_push=1 bfs_pull=1 bfs_coarse=0 bfs_words=4
+  echo "== C5 slice node lists, no coarse"; VGA_TIME_SRC=32768 python tools/gpu_time.py C5 global bfs_push=1 bfs_pull=1 bfs_coarse=0 bfs_pyr_nodes=1
+  echo "== C4 slice node lists, no coarse"; VGA_TIME_SRC=16384 python tools/gpu_time.py C4 global bfs_push=1 bfs_pull=1 bfs_coarse=0 bfs_pyr_nodes=1
   echo "== C4 slice pyramids, no coarse pass"; VGA_TIME_SRC=16384 python tools/gpu_time.py C4 global bfs_push=1 bfs_pull=1 bfs_coarse=0
   echo "== C4 slice bfs_push=1 bfs_pull=1"; VGA_TIME_SRC=16384 python tools/gpu_time.py C4 global bfs_push=1 bfs_pull=1
   echo "== C5 slice bfs_push_unroll=4"; VGA_TIME_SRC=32768 python tools/gpu_time.py C5 global bfs_push_unroll=4
