@@ -49,7 +49,7 @@ def test_pyramid_pull_vs_oracle(name, radius, mode, words, coarse):
     g = c.build(flat)
     tn, td, dist, used = g.global_ints(radius)
     rng = np.random.RandomState(3)
-    for s in rng.choice(g.n, min(g.n, 96), replace=False):
+    for s in rng.choice(g.n, min(g.n, 40), replace=False):
         otn, otd, odist, onl = og.global_ints(radius, (int(s), int(s) + 1), maxl=64)
         L = dist.shape[1]
         assert otn[0] == tn[s] and otd[0] == td[s]
@@ -85,7 +85,7 @@ def test_pyramid_push_vs_oracle(name, radius, push, pull, mode, words):
     g = c.build(flat)
     tn, td, dist, used = g.global_ints(radius)
     rng = np.random.RandomState(5)
-    for s in rng.choice(g.n, min(g.n, 96), replace=False):
+    for s in rng.choice(g.n, min(g.n, 40), replace=False):
         otn, otd, odist, onl = og.global_ints(radius, (int(s), int(s) + 1), maxl=64)
         L = dist.shape[1]
         assert otn[0] == tn[s] and otd[0] == td[s]
@@ -139,7 +139,7 @@ def test_pyramid_node_lists_vs_oracle(name, radius, push, pull, mode, words, coa
     g = c.build(flat)
     tn, td, dist, used = g.global_ints(radius)
     rng = np.random.RandomState(9)
-    for s in rng.choice(g.n, min(g.n, 96), replace=False):
+    for s in rng.choice(g.n, min(g.n, 40), replace=False):
         otn, otd, odist, onl = og.global_ints(radius, (int(s), int(s) + 1), maxl=64)
         L = dist.shape[1]
         assert otn[0] == tn[s] and otd[0] == td[s]
