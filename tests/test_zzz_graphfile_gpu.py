@@ -15,7 +15,8 @@ import pytest
 from conftest import golden
 from depthmapx_b200 import capi
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="passes under SIMT emulation on CPU; first B200 run pending")]
+# a kernel that never returns would hang the GPU box: give up on the whole run instead (these modules run last)
+pytestmark = [pytest.mark.timeout(900, method="thread"), pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="passes under SIMT emulation on CPU; first B200 run pending")]
 
 CASES = ["oblique12", "oblique10s07", "office16"]
 

@@ -20,7 +20,8 @@ def oracle_for(name):
     return _CACHE[name]
 
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="experimental opt-in path: passes under SIMT emulation on CPU, first B200 run pending")]
+# a kernel that never returns would hang the GPU box: give up on the whole run instead (these modules run last)
+pytestmark = [pytest.mark.timeout(900, method="thread"), pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="experimental opt-in path: passes under SIMT emulation on CPU, first B200 run pending")]
 
 
 @pytest.mark.parametrize("name", ["oblique:30:30:7", "office:64:64:1", "room:40:40:5"])
