@@ -21,6 +21,13 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "ref: needs oracle/_ref/libdmxref.so (the compiled reference)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """Every GPU test gets a hard time limit: a kernel that never returns must end the run, not hang the GPU box."""
+    for item in items:
+        if item.get_closest_marker("gpu") and not item.get_closest_marker("timeout"):
+            item.add_marker(pytest.mark.timeout(1800, method="thread"))
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _built():
     """Make sure the product libraries and the oracle exist (prebuilt files travel to the GPU box)."""
