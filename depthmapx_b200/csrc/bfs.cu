@@ -81,6 +81,7 @@ struct BfsDev {
     const uint32_t *f_nodes;         // bfs_pyr_nodes = 1: per row the ids of the pyramid nodes tiling its runs (id < n: leaf =
     const uint32_t *t_nodes;         // the vertex itself, id >= n: inner node id - n); row offsets = f_costptr / t_costptr
     int push_force;                  // bfs_push = 2: every top-down step uses the pyramid (tests)
+    int pyr_weight;                  // percent: cost of one pyramid-push node relative to one adjacency entry (bfs_pyr_cost)
     const uint8_t *noexpand;         // [n] or nullptr: vertices that are counted but never join the frontier (context-filled,
                                      // not even cells under a radius limit)
     int pyr_levels;
@@ -166,7 +167,7 @@ __global__ void k_init_mode(BfsDev d, const int32_t *src, int64_t nsrc, int nbat
         fe += __shfl_down_sync(FULL, fe, o);
         frc += __shfl_down_sync(FULL, frc, o);
     }
-    if (lane == 0 && (d.push_force || frc + 2 * (u64)d.n < fe)) d.mode[b] = 2;
+    if (lane == 0 && (d.push_force || (frc + 2 * (u64)d.n) * (u64)d.pyr_weight < fe * 100ULL)) d.mode[b] = 2;
 }
 
 // coarse pass (W = 1): the sources of group j (`per_group` consecutive sources) all carry bit j%64 of
@@ -863,8 +864,9 @@ __global__ void k_decide(BfsDev d, int nb, int bfs_mode, int64_t alpha, int64_t 
         m = 1;
     else if (bfs_mode == 2)
         m = (fe * (u64)alpha > ue * (u64)beta) ? 1 : 0;
-    if (m == 0 && d.npyr && (d.push_force || frc + 2 * (u64)d.n < fe)) m = 2;
-    if (m == 1 && d.npyr && bfs_mode == 2 && (frc + 2 * (u64)d.n) * (u64)alpha < ue * (u64)beta) m = 2;
+    const u64 pyr_cost_w = (frc + 2 * (u64)d.n) * (u64)d.pyr_weight;  // in hundredths of an adjacency entry
+    if (m == 0 && d.npyr && (d.push_force || pyr_cost_w < fe * 100ULL)) m = 2;
+    if (m == 1 && d.npyr && bfs_mode == 2 && pyr_cost_w * (u64)alpha < ue * (u64)beta * 100ULL) m = 2;
     d.mode[b] = m;
     if (work) {
         // work[0]: adjacency entries of the vertices that expand next (sum of deg over U_l),
@@ -1282,6 +1284,7 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int6
     d.noexpand = (radius != -1 && g->noexpand.p) ? g->noexpand.p : nullptr;
     d.npyr = npyr_p;
     d.push_force = ctx->opt.bfs_push == 2 ? 1 : 0;
+    d.pyr_weight = (int)std::max<int64_t>(1, ctx->opt.bfs_pyr_cost);
     d.f_nodes = (node_lists && pyr_push) ? g->f_nodes.p : nullptr;
     d.t_nodes = (node_lists && pyr_pull) ? g->t_nodes.p : nullptr;
     d.f_runptr = pyr_push ? g->f_runptr.p : nullptr;

@@ -44,6 +44,7 @@ static int set_option(Options &o, const std::string &key, int64_t value) {
     else if (key == "bfs_pull") o.bfs_pull = value;
     else if (key == "bfs_push") o.bfs_push = value;
     else if (key == "bfs_pyr_nodes") o.bfs_pyr_nodes = value;
+    else if (key == "bfs_pyr_cost") o.bfs_pyr_cost = value;
     else if (key == "bfs_push_unroll") o.bfs_push_unroll = value;
     else return VGA_ERR_INVALID;
     return VGA_OK;

@@ -135,6 +135,8 @@ struct Options {
     int64_t bfs_push = 0;        // top-down step: 0 = adjacency entries (k_push); 1 = additionally range-OR updates over the
                                  // runs of the out-rows through a pyramid of `next` (k_push_pyr + k_pyr_down) whenever the
                                  // per-batch cost model prefers them (EXPERIMENTAL, opt-in; validated under SIMT emulation)
+    int64_t bfs_pyr_cost = 100;  // percent: cost of one pyramid-push node relative to one adjacency entry in the per-batch choice
+                                 // between entry push, pyramid push and pull (to be tuned on the B200)
     int64_t bfs_pyr_nodes = 0;   // with bfs_push / bfs_pull = 1: rows as lists of pyramid NODE ids instead of runs, walked by
                                  // copies of the entry kernels' inner loops (k_push_nodes / k_pull_nodes; EXPERIMENTAL, opt-in)
     int64_t bfs_pull = 0;        // bottom-up step: 0 scans in-row entries (k_pull); 1 = range-OR queries over an

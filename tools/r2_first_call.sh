@@ -25,6 +25,8 @@ tail -40 gpurun_out/r2_pytest.log
   echo "== C2 pyramids, no coarse pass, words=2"; python tools/gpu_time.py C2 global bfs_push=1 bfs_pull=1 bfs_coarse=0 bfs_words=2
   echo "== C2 pyramids as node lists, no coarse"; python tools/gpu_time.py C2 global bfs_push=1 bfs_pull=1 bfs_coarse=0 bfs_pyr_nodes=1
   echo "== C2 pyramids as node lists, no coarse, words=2"; python tools/gpu_time.py C2 global bfs_push=1 bfs_pull=1 bfs_coarse=0 bfs_pyr_nodes=1 bfs_words=2
+  echo "== C2 node lists, pyramid node cost 200 %"; python tools/gpu_time.py C2 global bfs_push=1 bfs_pull=1 bfs_coarse=0 bfs_pyr_nodes=1 bfs_pyr_cost=200
+  echo "== C2 node lists, pyramid node cost 50 %"; python tools/gpu_time.py C2 global bfs_push=1 bfs_pull=1 bfs_coarse=0 bfs_pyr_nodes=1 bfs_pyr_cost=50
   echo "== C2 bfs_push_unroll=4"; python tools/gpu_time.py C2 global bfs_push_unroll=4
   echo "== C2 bfs_push_unroll=4 bfs_pull=1"; python tools/gpu_time.py C2 global bfs_push_unroll=4 bfs_pull=1
   echo "== C4 slice default";  VGA_TIME_SRC=16384 python tools/gpu_time.py C4 global
