@@ -1259,7 +1259,7 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int6
         VGA_TRY(lvl.alloc((size_t)max_cbatch * 64 * n));
     }
 
-    BfsDev d;
+    BfsDev d = {};  // every pointer of an unused option must be null
     d.n = n;
     d.rowptr = g->rowptr.p;
     d.adj = g->adj.p;
