@@ -117,24 +117,6 @@ template <int W> __device__ __forceinline__ void stw(u64 *p, const u64 (&o)[W]) 
     }
 }
 
-// 32 x 32 bit-matrix transpose across a warp: lane l passes row l and receives column l (bit i = bit l of lane i's
-// row), five butterfly stages of one shuffle each.  popc of the result = how many lanes had bit l set.
-__device__ __forceinline__ unsigned warp_transpose32(unsigned x, int lane) {
-    const unsigned masks[5] = {0x0000ffffu, 0x00ff00ffu, 0x0f0f0f0fu, 0x33333333u, 0x55555555u};
-#pragma unroll
-    for (int s = 0; s < 5; s++) {
-        const int j = 16 >> s;
-        const unsigned m = masks[s];
-        const unsigned y = __shfl_xor_sync(FULL, x, j);
-        if (lane & j) {
-            x ^= ((y >> j) ^ x) & m;
-        } else {
-            x ^= (((x >> j) ^ y) & m) << j;
-        }
-    }
-    return x;
-}
-constexpr int DENSE_COLUMNS = 8;  // from this many non-empty bit columns on, transpose + popc beats one ballot per column
 
 // source i of the ordered list -> bit (i & 63) of word (i >> 6); word wi lives in batch wi / W, slot wi % W
 template <int W> __global__ void k_init(BfsDev d, const int32_t *src, int64_t nsrc) {

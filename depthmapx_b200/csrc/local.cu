@@ -172,19 +172,30 @@ __global__ void __launch_bounds__(LTPB) k_lb_expand(LocalBatchDev d) {
                     u64 add = fw & ~r2[c];
                     if (add) atomicOr(&r2[c], add);
                 }
-                unsigned lo_any = __reduce_or_sync(FULL, (unsigned)x);
-                unsigned hi_any = __reduce_or_sync(FULL, (unsigned)(x >> 32));
-                while (lo_any) {
-                    int bit = __ffs(lo_any) - 1;
-                    lo_any &= lo_any - 1;
-                    int c = __popc(__ballot_sync(FULL, (x >> bit) & 1ULL));
-                    if (lane == bit) c0 += c;
+                // per-source counts = column sums of the warp's 32 x 64 bit matrix: one ballot per non-empty column, or,
+                // from DENSE_COLUMNS columns on, a 32 x 32 transpose (five shuffles) and one popc per half
+                const unsigned lo = (unsigned)x, hi = (unsigned)(x >> 32);
+                unsigned lo_any = __reduce_or_sync(FULL, lo);
+                unsigned hi_any = __reduce_or_sync(FULL, hi);
+                if (__popc(lo_any) >= DENSE_COLUMNS) {
+                    c0 += (u64)__popc(warp_transpose32(lo, lane));
+                } else {
+                    while (lo_any) {
+                        int bit = __ffs(lo_any) - 1;
+                        lo_any &= lo_any - 1;
+                        int c = __popc(__ballot_sync(FULL, (lo >> bit) & 1u));
+                        if (lane == bit) c0 += c;
+                    }
                 }
-                while (hi_any) {
-                    int bit = __ffs(hi_any) - 1;
-                    hi_any &= hi_any - 1;
-                    int c = __popc(__ballot_sync(FULL, (x >> (bit + 32)) & 1ULL));
-                    if (lane == bit) c1 += c;
+                if (__popc(hi_any) >= DENSE_COLUMNS) {
+                    c1 += (u64)__popc(warp_transpose32(hi, lane));
+                } else {
+                    while (hi_any) {
+                        int bit = __ffs(hi_any) - 1;
+                        hi_any &= hi_any - 1;
+                        int c = __popc(__ballot_sync(FULL, (hi >> bit) & 1u));
+                        if (lane == bit) c1 += c;
+                    }
                 }
             }
         }

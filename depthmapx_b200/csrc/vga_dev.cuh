@@ -238,6 +238,25 @@ int run_step_depth(vga_ctx *ctx, vga_graph *g, const int64_t *sources, int64_t n
 int run_local(vga_ctx *ctx, vga_graph *g, int64_t src_begin, int64_t src_end, int64_t *cluster, int32_t *k,
               int32_t *total, float *control);
 
+// 32 x 32 bit-matrix transpose across a warp: lane l passes row l and receives column l (bit i = bit l of lane i's
+// row), five butterfly stages of one shuffle each.  popc of the result = how many lanes had bit l set.
+__device__ __forceinline__ unsigned warp_transpose32(unsigned x, int lane) {
+    const unsigned masks[5] = {0x0000ffffu, 0x00ff00ffu, 0x0f0f0f0fu, 0x33333333u, 0x55555555u};
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        const int j = 16 >> s;
+        const unsigned m = masks[s];
+        const unsigned y = __shfl_xor_sync(0xffffffffu, x, j);
+        if (lane & j) {
+            x ^= ((y >> j) ^ x) & m;
+        } else {
+            x ^= (((x >> j) ^ y) & m) << j;
+        }
+    }
+    return x;
+}
+constexpr int DENSE_COLUMNS = 8;  // from this many non-empty bit columns on, transpose + popc beats one ballot per column
+
 // helpers for timing: record an event pair around a region on ctx->stream
 struct StageTimer {
     vga_ctx *ctx;

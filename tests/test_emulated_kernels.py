@@ -99,7 +99,8 @@ def test_default_paths_small_plans(emu_dir):
     """Validated defaults re-checked under emulation (guards against emulator drift): goldens of the reference, shards,
     ghost cells, empty inputs, host layer."""
     run_gpu_tests_emulated(emu_dir, ["tests/test_gpu_parity.py", "-k",
-                                     "golden or ghost or empty or single or shard or host_layer or boundary or maxdist or several_chunks"])
+                                     "golden or ghost or empty or single or shard or host_layer or boundary or maxdist or several_chunks "
+                                     "or (local_vs_oracle and oblique)"])
 
 
 def test_step_depth_kernel(emu_dir):
