@@ -299,19 +299,28 @@ __global__ void __launch_bounds__(LTPB) k_lb_total(LocalBatchDev d) {
     for (int64_t base = (int64_t)blockIdx.x * LTPB; base < d.universe; base += (int64_t)gridDim.x * LTPB) {
         int64_t v = base + threadIdx.x;
         u64 x = (v < d.universe) ? r2[v] : 0ULL;
-        unsigned lo_any = __reduce_or_sync(FULL, (unsigned)x);
-        unsigned hi_any = __reduce_or_sync(FULL, (unsigned)(x >> 32));
-        while (lo_any) {
-            int bit = __ffs(lo_any) - 1;
-            lo_any &= lo_any - 1;
-            int c = __popc(__ballot_sync(FULL, (x >> bit) & 1ULL));
-            if (lane == bit) c0 += c;
+        const unsigned lo = (unsigned)x, hi = (unsigned)(x >> 32);
+        unsigned lo_any = __reduce_or_sync(FULL, lo);
+        unsigned hi_any = __reduce_or_sync(FULL, hi);
+        if (__popc(lo_any) >= DENSE_COLUMNS) {  // column sums by transposition, as in k_lb_expand
+            c0 += __popc(warp_transpose32(lo, lane));
+        } else {
+            while (lo_any) {
+                int bit = __ffs(lo_any) - 1;
+                lo_any &= lo_any - 1;
+                int c = __popc(__ballot_sync(FULL, (lo >> bit) & 1u));
+                if (lane == bit) c0 += c;
+            }
         }
-        while (hi_any) {
-            int bit = __ffs(hi_any) - 1;
-            hi_any &= hi_any - 1;
-            int c = __popc(__ballot_sync(FULL, (x >> (bit + 32)) & 1ULL));
-            if (lane == bit) c1 += c;
+        if (__popc(hi_any) >= DENSE_COLUMNS) {
+            c1 += __popc(warp_transpose32(hi, lane));
+        } else {
+            while (hi_any) {
+                int bit = __ffs(hi_any) - 1;
+                hi_any &= hi_any - 1;
+                int c = __popc(__ballot_sync(FULL, (hi >> bit) & 1u));
+                if (lane == bit) c1 += c;
+            }
         }
     }
     if (c0) atomicAdd(&s_cnt[lane], c0);
