@@ -27,7 +27,8 @@ def _newer(target, deps):
 
 def build(force: bool = False, verbose: bool = False) -> None:
     os.makedirs(LIB, exist_ok=True)
-    hdrs = [os.path.join(CSRC, "vga_dev.cuh"), os.path.join(HERE, "..", "include", "vga_b200.h")]
+    hdrs = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    hdrs.append(os.path.join(HERE, "..", "include", "vga_b200.h"))
 
     def compile_one(name):
         src = os.path.join(CSRC, name + ".cu")

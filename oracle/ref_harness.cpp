@@ -353,7 +353,9 @@ double dmxref_sample_makegraph(void *h, const int32_t *src, int k, double maxdis
     for (int i = 0; i < k; i++) {
         PixelRef curs = ord[src[i]];
         m.getPoint(curs).m_node = std::unique_ptr<Node>(new Node());
-        m.m_attributes->addRow(AttributeKey(curs));
+        // a source sampled again (bench.py draws a fresh sample every step) keeps its row: the reference's addRow
+        // throws on a duplicate key (attributetable.cpp:278); sparkGraph2 itself adds each row once
+        if (!m.m_attributes->getRowPtr(AttributeKey(curs))) m.m_attributes->addRow(AttributeKey(curs));
         m.getPoint(curs).m_processflag = 0x00FF;
         m.sparkPixel2(curs, 1, maxdist);
     }

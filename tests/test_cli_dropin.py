@@ -54,3 +54,47 @@ def test_cli_outputs_byte_identical(tmp_path, name, grid, seed):
             run(binary, ["-m", "VISPREP", "-f", "plan.graph", "-o", f"prep_{tag2}_{tag}.graph", "-pg", grid, "-pp", seed,
                          "-pm"] + extra, d)
         assert same(os.path.join(d, f"prep_{tag2}_ref.graph"), os.path.join(d, f"prep_{tag2}_gpu.graph")), tag2
+
+
+# ---- the reference's own regression cases for this path (RegressionTest/regressionconfig.json) ---------------------
+# Inputs: tests/golden/regression/ (copied from the reference's testdata by tests/golden/make_regression_fixtures.py).
+# Expected output = what the unmodified reference CLI writes in the same run (byte-diff, same day: the file holds a date).
+
+REGRESSION = os.path.join(ROOT, "tests", "golden", "regression")
+REGRESSION_CASES = {
+    "pointmap_create_fill_make_one_operation": ("gallery_empty.graph", ["-m", "VISPREP", "-pg", "0.04", "-pp", "1.32,7.24",
+                                                                        "-pp", "4.88,5.24", "-pm"]),
+    "dense_pointmap_create_fill_make": ("rect1x1.graph", ["-m", "VISPREP", "-pg", "0.02", "-pp", "0.5,0.5"]),
+    "dense_pointmap_create_fill_make_graph": ("rect1x1.graph", ["-m", "VISPREP", "-pg", "0.02", "-pp", "0.5,0.5", "-pm"]),
+    "visibility_global_n": ("gallery_connected.graph", ["-m", "VGA", "-vm", "visibility", "-vg", "-vr", "n"]),
+    "visibility_global_3": ("gallery_connected.graph", ["-m", "VGA", "-vm", "visibility", "-vg", "-vr", "3"]),
+    "visibility_local": ("gallery_connected.graph", ["-m", "VGA", "-vm", "visibility", "-vl"]),
+    "visibility_global_local_simple": ("gallery_connected.graph", ["-m", "VGA", "-vm", "visibility", "-vg", "-vl", "-vr", "n", "-s"]),
+    "vga_visual_step_depth": ("gallery_connected.graph", ["-m", "STEPDEPTH", "-sdp", "3,5", "-sdt", "visual"]),
+}
+
+
+def regression_input(name, d):
+    import gzip
+    import shutil
+    dst = os.path.join(d, name)
+    if os.path.exists(os.path.join(REGRESSION, name)):
+        shutil.copyfile(os.path.join(REGRESSION, name), dst)
+    else:
+        with gzip.open(os.path.join(REGRESSION, name + ".gz"), "rb") as f, open(dst, "wb") as o:
+            shutil.copyfileobj(f, o)
+    return dst
+
+
+@pytest.mark.parametrize("case", sorted(REGRESSION_CASES))
+def test_reference_regression_case(tmp_path, case):
+    if not (os.path.exists(REF) and os.path.exists(GPU)):
+        pytest.skip("integration binaries not built (make -C integration)")
+    if capi.device_count() < 1:
+        pytest.fail("needs a CUDA device")
+    infile, args = REGRESSION_CASES[case]
+    d = str(tmp_path)
+    regression_input(infile, d)
+    for tag, binary in (("ref", REF), ("gpu", GPU)):
+        run(binary, args + ["-f", infile, "-o", f"out_{tag}.graph"], d)
+    assert same(os.path.join(d, "out_ref.graph"), os.path.join(d, "out_gpu.graph")), f"{case}: .graph differs"
