@@ -27,7 +27,7 @@ class VgaGrid(C.Structure):
 class VgaTiming(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("main_kernel_ms", C.c_double), ("launches", C.c_int64), ("main_launches", C.c_int64),
-                ("algo_bytes", C.c_double), ("algo_bytes_runs", C.c_double)]
+                ("algo_bytes", C.c_double), ("algo_bytes_csr", C.c_double), ("prep_ms", C.c_double)]
 
 
 ABI_SYMBOLS = [
@@ -36,7 +36,9 @@ ABI_SYMBOLS = [
     "vga_graph_build_resident", "vga_graph_from_csr", "vga_graph_free", "vga_graph_num_cells", "vga_graph_num_ghosts",
     "vga_graph_num_edges", "vga_graph_src_begin", "vga_graph_src_end", "vga_graph_csr", "vga_graph_cell_refs", "vga_graph_set_cell_refs",
     "vga_graph_node_stats", "vga_graph_set_noexpand", "vga_global", "vga_global_attributes", "vga_local", "vga_local_attributes", "vga_step_depth",
-    "vga_graph_device_rows", "vga_graph_from_device_rows",
+    "vga_graph_device_rows", "vga_graph_from_device_rows", "vga_global_sources", "vga_graph_batch_order",
+    "vga_graph_device_runs", "vga_graph_from_device_runs", "vga_graph_runs_alloc", "vga_graph_runs_commit",
+    "vga_graph_device_degrees",
 ]
 HOST_SYMBOLS = [
     "dmxh_last_error", "dmxh_map_create", "dmxh_map_destroy", "dmxh_map_grid", "dmxh_map_block_lines", "dmxh_map_fill",
@@ -94,6 +96,13 @@ def abi():
         L.vga_local_attributes.argtypes = [i64] + [vp] * 7
         L.vga_graph_device_rows.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
         L.vga_graph_from_device_rows.argtypes = [vp, i64, i64, vp, vp, i64, C.POINTER(vp)]
+        L.vga_global_sources.argtypes = [vp, vp, C.c_int, vp, i64, vp, vp, vp, C.c_int32, C.POINTER(C.c_int32)]
+        L.vga_graph_batch_order.argtypes = [vp, vp, vp]
+        L.vga_graph_device_runs.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
+        L.vga_graph_from_device_runs.argtypes = [vp, i64, i64, vp, vp, i64, vp, C.POINTER(vp)]
+        L.vga_graph_runs_alloc.argtypes = [vp, i64, i64, i64, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+        L.vga_graph_runs_commit.argtypes = [vp]
+        L.vga_graph_device_degrees.argtypes = [vp, vp, C.POINTER(vp)]
         _abi = L
     return _abi
 
@@ -246,6 +255,19 @@ class Context:
         check(abi().vga_graph_from_csr(self.h, n_cells, n_ghosts, _p(rowptr), _p(col), _p(b), C.byref(g)))
         return Graph(self, g)
 
+    def graph_from_device_runs(self, n_cells, n_ghosts, d_runptr: int, d_runs: int, n_runs: int, d_degree: int = 0) -> "Graph":
+        """Adopt device-resident run-length rows of all cells (BFS-only graph); pointers are CUDA device addresses."""
+        g = vp()
+        check(abi().vga_graph_from_device_runs(self.h, n_cells, n_ghosts, d_runptr, d_runs, n_runs, d_degree or None, C.byref(g)))
+        return Graph(self, g)
+
+    def graph_runs_alloc(self, n_cells, n_ghosts, n_runs):
+        """A BFS-only graph whose run-length rows the caller fills on the device: returns (graph, runptr address,
+        runs address, degree address); call graph.runs_commit() when the buffers are complete."""
+        g, rp, runs, deg = vp(), vp(), vp(), vp()
+        check(abi().vga_graph_runs_alloc(self.h, n_cells, n_ghosts, n_runs, C.byref(g), C.byref(rp), C.byref(runs), C.byref(deg)))
+        return Graph(self, g), rp.value, runs.value, deg.value
+
     def graph_from_device_rows(self, n_cells, n_ghosts, d_rowptr: int, d_adj: int, n_entries: int) -> "Graph":
         g = vp()
         check(abi().vga_graph_from_device_rows(self.h, n_cells, n_ghosts, d_rowptr, d_adj, n_entries, C.byref(g)))
@@ -294,13 +316,16 @@ class Graph:
         except Exception:
             pass
 
-    def csr(self):
+    def csr(self, bins=True):
+        """(rowptr, col, bin, accepted); bins=False skips the two byte arrays (full-size graphs)."""
         rows = self.src_end - self.src_begin
         rowptr = np.zeros(rows + 1, np.uint64)
-        col = np.zeros(max(self.entries, 1), np.uint32)
-        b = np.zeros(max(self.entries, 1), np.uint8)
-        acc = np.zeros(max(self.entries, 1), np.uint8)
+        col = np.empty(max(self.entries, 1), np.uint32)
+        b = np.empty(max(self.entries, 1), np.uint8) if bins else None
+        acc = np.empty(max(self.entries, 1), np.uint8) if bins else None
         check(abi().vga_graph_csr(self.h, _p(rowptr), _p(col), _p(b), _p(acc)))
+        if not bins:
+            return rowptr, col[:self.entries], None, None
         return rowptr, col[:self.entries], b[:self.entries], acc[:self.entries]
 
     def cell_refs(self):
@@ -335,15 +360,44 @@ class Graph:
         check(abi().vga_graph_device_rows(self.h, C.byref(rp), C.byref(adj), C.byref(ne)))
         return rp.value, adj.value, ne.value
 
-    def global_ints(self, radius=-1, src=None, maxl=32):
-        b, e = (0, self.n) if src is None else src
+    def device_runs(self):
+        """(device address of runptr, of the (first, length) run pairs, number of runs) of the rows this graph holds."""
+        rp, runs, nr = vp(), vp(), i64()
+        check(abi().vga_graph_device_runs(self.ctx.h, self.h, C.byref(rp), C.byref(runs), C.byref(nr)))
+        return rp.value, runs.value, nr.value
+
+    def runs_commit(self):
+        check(abi().vga_graph_runs_commit(self.h))
+
+    def device_degrees(self):
+        d = vp()
+        check(abi().vga_graph_device_degrees(self.ctx.h, self.h, C.byref(d)))
+        return d.value
+
+    def batch_order(self):
+        """Ordinals of all N sources in the order vga_global batches them (spatially compact groups)."""
+        o = np.zeros(self.n, np.int32)
+        check(abi().vga_graph_batch_order(self.ctx.h, self.h, _p(o)))
+        return o
+
+    def global_ints(self, radius=-1, src=None, maxl=32, sources=None):
+        """src = (begin, end) range of ordinals, or sources = explicit list of ordinals (outputs in list order)."""
+        lst = None
+        if sources is not None:
+            lst = np.ascontiguousarray(sources, np.int64)
+            b, e = 0, len(lst)
+        else:
+            b, e = (0, self.n) if src is None else src
         k = e - b
         while True:
             tn = np.zeros(k, np.int32)
             td = np.zeros(k, np.int64)
             dist = np.zeros((k, maxl), np.int32)
             used = C.c_int32(0)
-            rc = abi().vga_global(self.ctx.h, self.h, radius, b, e, _p(tn), _p(td), _p(dist), maxl, C.byref(used))
+            if lst is not None:
+                rc = abi().vga_global_sources(self.ctx.h, self.h, radius, _p(lst), k, _p(tn), _p(td), _p(dist), maxl, C.byref(used))
+            else:
+                rc = abi().vga_global(self.ctx.h, self.h, radius, b, e, _p(tn), _p(td), _p(dist), maxl, C.byref(used))
             if rc == -5 and used.value > maxl:
                 maxl = used.value
                 continue

@@ -28,6 +28,7 @@ static int set_option(Options &o, const std::string &key, int64_t value) {
     if (key == "bfs_mode") o.bfs_mode = value;
     else if (key == "bfs_chunk") o.bfs_chunk = value;
     else if (key == "bfs_words") o.bfs_words = value;
+    else if (key == "bfs_l2_words") o.bfs_l2_words = value;
     else if (key == "local_mode") o.local_mode = value;
     else if (key == "sieve_mode") o.sieve_mode = value;
     else if (key == "sieve_gcap") o.sieve_gcap = value;
@@ -39,13 +40,6 @@ static int set_option(Options &o, const std::string &key, int64_t value) {
     else if (key == "pull_alpha") o.pull_alpha = value;
     else if (key == "pull_beta") o.pull_beta = value;
     else if (key == "bfs_order") o.bfs_order = value;
-    else if (key == "bfs_group") o.bfs_group = value;
-    else if (key == "bfs_coarse") o.bfs_coarse = value;
-    else if (key == "bfs_pull") o.bfs_pull = value;
-    else if (key == "bfs_push") o.bfs_push = value;
-    else if (key == "bfs_pyr_nodes") o.bfs_pyr_nodes = value;
-    else if (key == "bfs_pyr_cost") o.bfs_pyr_cost = value;
-    else if (key == "bfs_push_unroll") o.bfs_push_unroll = value;
     else return VGA_ERR_INVALID;
     return VGA_OK;
 }
@@ -162,8 +156,7 @@ int vga_ctx_create(int device, vga_ctx **out) {
     o.sieve_gcap = env_i64("VGA_SIEVE_GCAP", o.sieve_gcap);
     o.sieve_bcap = env_i64("VGA_SIEVE_BCAP", o.sieve_bcap);
     o.pull_alpha = env_i64("VGA_PULL_ALPHA", o.pull_alpha);
-    o.bfs_pull = env_i64("VGA_BFS_PULL", o.bfs_pull);
-    o.bfs_push = env_i64("VGA_BFS_PUSH", o.bfs_push);
+    o.bfs_words = env_i64("VGA_BFS_WORDS", o.bfs_words);
     *out = c.release();
     return VGA_OK;
 }
@@ -210,7 +203,8 @@ int vga_ctx_timing(const vga_ctx *ctx, vga_timing *out) {
     out->launches = ctx->timing.launches;
     out->main_launches = ctx->timing.main_launches;
     out->algo_bytes = ctx->timing.algo_bytes;
-    out->algo_bytes_runs = ctx->timing.algo_bytes_runs;
+    out->algo_bytes_csr = ctx->timing.algo_bytes_csr;
+    out->prep_ms = ctx->timing.prep_ms;
     return VGA_OK;
 }
 
@@ -388,8 +382,12 @@ int vga_graph_from_csr(vga_ctx *ctx, int64_t n_cells, int64_t n_ghosts, const ui
 
 int vga_graph_from_device_rows(vga_ctx *ctx, int64_t n_cells, int64_t n_ghosts, const uint64_t *d_rowptr,
                                const uint32_t *d_adj, int64_t n_entries, vga_graph **out) {
-    if (!ctx || !out || !d_rowptr || n_cells < 0 || n_entries < 0) return VGA_ERR_INVALID;
+    if (!ctx || !out || !d_rowptr || n_cells < 0 || n_ghosts < 0 || n_entries < 0 || (n_entries > 0 && !d_adj)) return VGA_ERR_INVALID;
     *out = nullptr;
+    if (n_cells + n_ghosts >= ((int64_t)1 << 26)) {
+        set_error("more than 2^26 vertices is not supported");
+        return VGA_ERR_UNSUPPORTED;
+    }
     VGA_CUDA(cudaSetDevice(ctx->device));
     g_alloc_stream = ctx->stream;
     ctx->timing = Timing();
@@ -434,13 +432,18 @@ int vga_graph_csr(const vga_graph *g, uint64_t *rowptr, uint32_t *col, uint8_t *
     const int64_t rows = g->src_end - g->src_begin;
     if (rowptr) VGA_CUDA(cudaMemcpy(rowptr, g->rowptr.p, sizeof(uint64_t) * (rows + 1), cudaMemcpyDeviceToHost));
     if ((col || bin || accepted) && g->entries > 0) {
-        std::vector<uint32_t> h((size_t)g->entries);
-        VGA_CUDA(cudaMemcpy(h.data(), g->adj.p, sizeof(uint32_t) * g->entries, cudaMemcpyDeviceToHost));
-        for (int64_t e = 0; e < g->entries; e++) {
-            uint32_t v = h[(size_t)e];
-            if (col) col[e] = v >> 6;
-            if (bin) bin[e] = (uint8_t)(v & 31);
-            if (accepted) accepted[e] = (uint8_t)((v >> 5) & 1);
+        // unpacked in slices through a bounded staging buffer (a C5 graph has 5.5e9 entries = 22 GB)
+        const int64_t slice = (int64_t)1 << 26;
+        std::vector<uint32_t> h((size_t)std::min<int64_t>(slice, g->entries));
+        for (int64_t e0 = 0; e0 < g->entries; e0 += slice) {
+            const int64_t cnt = std::min<int64_t>(slice, g->entries - e0);
+            VGA_CUDA(cudaMemcpy(h.data(), g->adj.p + e0, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost));
+            for (int64_t i = 0; i < cnt; i++) {
+                const uint32_t v = h[(size_t)i];
+                if (col) col[e0 + i] = v >> 6;
+                if (bin) bin[e0 + i] = (uint8_t)(v & 31);
+                if (accepted) accepted[e0 + i] = (uint8_t)((v >> 5) & 1);
+            }
         }
     }
     return VGA_OK;
@@ -520,8 +523,125 @@ int vga_global(vga_ctx *ctx, const vga_graph *g, int radius, int64_t src_begin, 
     VGA_CUDA(cudaSetDevice(ctx->device));
     g_alloc_stream = ctx->stream;
     ctx->timing = Timing();
-    return run_global(ctx, const_cast<vga_graph *>(g), radius, src_begin, src_end, total_nodes, total_depth, dist, max_levels,
+    return run_global(ctx, const_cast<vga_graph *>(g), radius, nullptr, src_begin, src_end, total_nodes, total_depth, dist,
+                      max_levels, levels_used);
+}
+
+int vga_global_sources(vga_ctx *ctx, const vga_graph *g, int radius, const int64_t *sources, int64_t n_sources,
+                       int32_t *total_nodes, int64_t *total_depth, int32_t *dist, int32_t max_levels, int32_t *levels_used) {
+    if (!ctx || !g || n_sources < 0 || (n_sources > 0 && !sources)) return VGA_ERR_INVALID;
+    if (radius < -1) {
+        set_error("vga_global_sources: radius must be -1 (n) or >= 0");
+        return VGA_ERR_INVALID;
+    }
+    VGA_CUDA(cudaSetDevice(ctx->device));
+    g_alloc_stream = ctx->stream;
+    ctx->timing = Timing();
+    if (levels_used) *levels_used = 0;
+    if (n_sources == 0) return VGA_OK;
+    return run_global(ctx, const_cast<vga_graph *>(g), radius, sources, 0, n_sources, total_nodes, total_depth, dist, max_levels,
                       levels_used);
+}
+
+int vga_graph_batch_order(vga_ctx *ctx, const vga_graph *g, int32_t *order) {
+    if (!ctx || !g || !order) return VGA_ERR_INVALID;
+    VGA_CUDA(cudaSetDevice(ctx->device));
+    g_alloc_stream = ctx->stream;
+    std::vector<int32_t> o;
+    VGA_TRY(batch_source_order(ctx, const_cast<vga_graph *>(g), 0, g->n, o));
+    std::memcpy(order, o.data(), sizeof(int32_t) * o.size());
+    return VGA_OK;
+}
+
+int vga_graph_device_runs(vga_ctx *ctx, const vga_graph *g, const uint64_t **d_runptr, const void **d_runs, int64_t *n_runs) {
+    if (!ctx || !g) return VGA_ERR_INVALID;
+    VGA_CUDA(cudaSetDevice(ctx->device));
+    g_alloc_stream = ctx->stream;
+    vga_graph *gg = const_cast<vga_graph *>(g);
+    VGA_TRY(shard_runs(ctx, gg));  // a shard holds the rows [src_begin, src_end): runs of those rows only
+    if (d_runptr) *d_runptr = gg->f_runptr.p;
+    if (d_runs) *d_runs = gg->f_runs.p;
+    if (n_runs) *n_runs = gg->f_nruns;
+    return VGA_OK;
+}
+
+int vga_graph_runs_alloc(vga_ctx *ctx, int64_t n_cells, int64_t n_ghosts, int64_t n_runs, vga_graph **out, uint64_t **d_runptr,
+                         void **d_runs, uint32_t **d_degree) {
+    if (!ctx || !out || n_cells < 0 || n_ghosts < 0 || n_runs < 0) return VGA_ERR_INVALID;
+    *out = nullptr;
+    if (n_cells + n_ghosts >= ((int64_t)1 << 26)) {
+        set_error("more than 2^26 vertices is not supported");
+        return VGA_ERR_UNSUPPORTED;
+    }
+    VGA_CUDA(cudaSetDevice(ctx->device));
+    g_alloc_stream = ctx->stream;
+    std::unique_ptr<vga_graph> g(new vga_graph());
+    g->ctx = ctx;
+    g->n = n_cells;
+    g->ghosts = n_ghosts;
+    g->src_begin = 0;
+    g->src_end = n_cells;
+    g->entries = 0;
+    VGA_TRY(g->f_runptr.alloc((size_t)n_cells + 1));
+    VGA_TRY(g->f_runs.alloc((size_t)n_runs + 1));
+    VGA_TRY(g->deg.alloc((size_t)n_cells + 1));
+    VGA_CUDA(cudaMemsetAsync(g->deg.p, 0, sizeof(uint32_t) * ((size_t)n_cells + 1), ctx->stream));
+    VGA_CUDA(cudaStreamSynchronize(ctx->stream));  // the caller fills the buffers from other streams
+    g->f_nruns = n_runs;
+    if (d_runptr) *d_runptr = g->f_runptr.p;
+    if (d_runs) *d_runs = g->f_runs.p;
+    if (d_degree) *d_degree = g->deg.p;
+    *out = g.release();
+    return VGA_OK;
+}
+
+int vga_graph_runs_commit(vga_graph *g) {
+    if (!g || g->entries != 0 || !g->f_runptr.p) return VGA_ERR_INVALID;
+    g->has_fwd_runs = true;
+    return VGA_OK;
+}
+
+int vga_graph_device_degrees(vga_ctx *ctx, const vga_graph *g, const uint32_t **d_degree) {
+    if (!ctx || !g || !d_degree) return VGA_ERR_INVALID;
+    VGA_CUDA(cudaSetDevice(ctx->device));
+    g_alloc_stream = ctx->stream;
+    VGA_TRY(row_degrees(ctx, const_cast<vga_graph *>(g)));
+    *d_degree = g->deg.p;
+    return VGA_OK;
+}
+
+int vga_graph_from_device_runs(vga_ctx *ctx, int64_t n_cells, int64_t n_ghosts, const uint64_t *d_runptr, const void *d_runs,
+                               int64_t n_runs, const uint32_t *d_degree, vga_graph **out) {
+    if (!ctx || !out || !d_runptr || n_cells < 0 || n_ghosts < 0 || n_runs < 0 || (n_runs > 0 && !d_runs)) return VGA_ERR_INVALID;
+    *out = nullptr;
+    if (n_cells + n_ghosts >= ((int64_t)1 << 26)) {
+        set_error("more than 2^26 vertices is not supported");
+        return VGA_ERR_UNSUPPORTED;
+    }
+    VGA_CUDA(cudaSetDevice(ctx->device));
+    g_alloc_stream = ctx->stream;
+    ctx->timing = Timing();
+    cudaStream_t st = ctx->stream;
+    std::unique_ptr<vga_graph> g(new vga_graph());
+    g->ctx = ctx;
+    g->n = n_cells;
+    g->ghosts = n_ghosts;
+    g->src_begin = 0;
+    g->src_end = n_cells;
+    g->entries = 0;  // no entry rows: this graph serves vga_global / vga_global_sources only
+    VGA_TRY(g->f_runptr.alloc((size_t)n_cells + 1));
+    VGA_TRY(g->f_runs.alloc((size_t)n_runs + 1));
+    VGA_CUDA(cudaMemcpyAsync(g->f_runptr.p, d_runptr, sizeof(uint64_t) * (n_cells + 1), cudaMemcpyDeviceToDevice, st));
+    if (n_runs > 0) VGA_CUDA(cudaMemcpyAsync(g->f_runs.p, d_runs, sizeof(uint2) * n_runs, cudaMemcpyDeviceToDevice, st));
+    if (d_degree && n_cells > 0) {
+        VGA_TRY(g->deg.alloc((size_t)n_cells));
+        VGA_CUDA(cudaMemcpyAsync(g->deg.p, d_degree, sizeof(uint32_t) * n_cells, cudaMemcpyDeviceToDevice, st));
+    }
+    VGA_CUDA(cudaStreamSynchronize(st));
+    g->f_nruns = n_runs;
+    g->has_fwd_runs = true;
+    *out = g.release();
+    return VGA_OK;
 }
 
 int vga_global_attributes(int64_t n, const int32_t *total_nodes, const int64_t *total_depth, const int32_t *dist,

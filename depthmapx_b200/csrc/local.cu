@@ -206,88 +206,6 @@ __global__ void __launch_bounds__(LTPB) k_lb_expand(LocalBatchDev d) {
     if (threadIdx.x < 64 && s_cl[threadIdx.x]) atomicAdd(&d.cluster[(int64_t)b * 64 + threadIdx.x], s_cl[threadIdx.x]);
 }
 
-// EXPERIMENTAL (opt-in: local_mode = 3; prepared for round 2): same as k_lb_expand but
-// the per-source-bit counting uses bit-sliced (vertical) counters.  Every lane adds the 64-bit word
-// x = F1[u] & F1[w] of its edge into six bit planes with a ripple-carry (18 logic ops), and only every
-// 63 additions the planes are flushed with ballot+popc (6 x 64 ballots per 63 x 32 edges instead of
-// 64 ballots per 32 edges).
-__global__ void __launch_bounds__(LTPB) k_lb_expand_sliced(LocalBatchDev d) {
-    const int b = blockIdx.y;
-    const int lane = threadIdx.x & 31;
-    const u64 *f1 = d.f1 + (int64_t)b * d.universe;
-    u64 *r2 = d.r2 + (int64_t)b * d.universe;
-    __shared__ u64 s_cl[64];
-    if (threadIdx.x < 64) s_cl[threadIdx.x] = 0ULL;
-    __syncthreads();
-    constexpr int K = 6;
-    u64 plane[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) plane[k] = 0ULL;
-    int nadds = 0;
-    u64 c0 = 0, c1 = 0;  // lane l counts source bits l and l+32
-    auto flush = [&]() {
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-            const u64 pk = plane[k];
-            plane[k] = 0ULL;
-            unsigned lo_any = __reduce_or_sync(FULL, (unsigned)pk);
-            unsigned hi_any = __reduce_or_sync(FULL, (unsigned)(pk >> 32));
-            while (lo_any) {
-                int bit = __ffs(lo_any) - 1;
-                lo_any &= lo_any - 1;
-                u64 c = (u64)__popc(__ballot_sync(FULL, (pk >> bit) & 1ULL));
-                if (lane == bit) c0 += c << k;
-            }
-            while (hi_any) {
-                int bit = __ffs(hi_any) - 1;
-                hi_any &= hi_any - 1;
-                u64 c = (u64)__popc(__ballot_sync(FULL, (pk >> (bit + 32)) & 1ULL));
-                if (lane == bit) c1 += c << k;
-            }
-        }
-        nadds = 0;
-    };
-    for (int64_t base = (int64_t)blockIdx.x * LTPB; base < d.n; base += (int64_t)gridDim.x * LTPB) {
-        int64_t u = base + threadIdx.x;
-        u64 f = (u < d.n) ? f1[u] : 0ULL;
-        uint64_t my0 = 0, my1 = 0;
-        if (f != 0ULL) {
-            my0 = d.rowptr[u];
-            my1 = d.rowptr[u + 1];
-        }
-        unsigned m = __ballot_sync(FULL, f != 0ULL);
-        while (m) {
-            int src_lane = __ffs(m) - 1;
-            m &= m - 1;
-            u64 fw = __shfl_sync(FULL, f, src_lane);
-            uint64_t e0 = __shfl_sync(FULL, my0, src_lane), e1 = __shfl_sync(FULL, my1, src_lane);
-            for (uint64_t e = e0; e < e1; e += 32) {  // uniform trip count: every lane adds once per trip
-                uint64_t ee = e + lane;
-                u64 x = 0ULL;
-                if (ee < e1) {
-                    uint32_t c = d.adj[ee] >> 6;
-                    x = fw & f1[c];
-                    u64 add = fw & ~r2[c];
-                    if (add) atomicOr(&r2[c], add);
-                }
-                u64 carry = x;
-#pragma unroll
-                for (int k = 0; k < K; k++) {
-                    u64 t = plane[k] & carry;
-                    plane[k] ^= carry;
-                    carry = t;
-                }
-                if (++nadds == (1 << K) - 1) flush();
-            }
-        }
-    }
-    flush();
-    if (c0) atomicAdd(&s_cl[lane], c0);
-    if (c1) atomicAdd(&s_cl[lane + 32], c1);
-    __syncthreads();
-    if (threadIdx.x < 64 && s_cl[threadIdx.x]) atomicAdd(&d.cluster[(int64_t)b * 64 + threadIdx.x], s_cl[threadIdx.x]);
-}
-
 __global__ void __launch_bounds__(LTPB) k_lb_total(LocalBatchDev d) {
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31;
@@ -386,9 +304,6 @@ int run_local_batched(vga_ctx *ctx, vga_graph *g, int64_t src_begin, int64_t src
         VGA_CUDA(cudaMemsetAsync(d_cl.p, 0, sizeof(u64) * (size_t)cb * 64, st));
         VGA_CUDA(cudaMemsetAsync(d_tot.p, 0, sizeof(int32_t) * (size_t)cb * 64, st));
         k_lb_seed<<<(unsigned)((cs * 32 + 255) / 256), 256, 0, st>>>(d, d_order.p + first, cs);
-        if (ctx->opt.local_mode == 3)
-            k_lb_expand_sliced<<<dim3(xb_n, (unsigned)cb), LTPB, 0, st>>>(d);
-        else
             k_lb_expand<<<dim3(xb_n, (unsigned)cb), LTPB, 0, st>>>(d);
         k_lb_total<<<dim3(xb_u, (unsigned)cb), LTPB, 0, st>>>(d);
         tm.launches += 3;
@@ -442,7 +357,7 @@ int run_local(vga_ctx *ctx, vga_graph *g, int64_t src_begin, int64_t src_end, in
         // bit-parallel batches win from about a thousand neighbours per cell (C1: 1.6x, C4: 5.7x)
         int64_t lm = ctx->opt.local_mode;
         if (lm == 2) lm = ((double)g->entries >= 1024.0 * (double)n) ? 1 : 0;
-        if (lm == 1 || lm == 3) return run_local_batched(ctx, g, src_begin, src_end, cluster, k, total, control);
+        if (lm == 1) return run_local_batched(ctx, g, src_begin, src_end, cluster, k, total, control);
     }
     Timing &tm = ctx->timing;
     StageTimer kt(ctx, 0, &tm.kernel_ms);

@@ -1020,7 +1020,8 @@ __global__ void k_make_keys(GridDev g, const uint32_t *e_ref, const uint8_t *e_b
     keys[e] = (col << 6) | ((b & 0x80) ? 0u : 32u) | (uint32_t)(b & 31);
 }
 
-// Opt-in replacement of the segmented radix sort (build_sort = 1): a row is a SET of vertex numbers below `total`, so
+// Row ordering (default; build_sort = 0 selects the CUB segmented radix sort, which also serves grids whose bitmap exceeds
+// shared memory): a row is a SET of vertex numbers below `total`, so
 // its sorted order follows from a bitmap of the row -- rank(col) = number of set bits below col.  One CTA per row: set
 // the bits in shared memory, popc-sum groups of 32 words, scan the group sums, then every entry looks its rank up
 // (group prefix + at most 31 word popcs + one masked popc) and is written to its final place.  O(total/32 + deg) per
@@ -1137,12 +1138,13 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t sr
     StageTimer mt(ctx, 2, &tm.main_kernel_ms);
 
     const int64_t ntasks = nsrc * 8;
-    DevBuf<uint32_t> cnt, fillcnt;
-    DevBuf<uint8_t> ghostflag, bigflag;
-    DevBuf<int64_t> overflow_list;
-    DevBuf<unsigned long long> n_overflow;
-    DevBuf<int> error_flag;
-    DevBuf<uint64_t> row_tot, row_off;
+    // temporaries live in the context's grow-only workspace (no allocation after the first call of a given size)
+    WsBuf<uint32_t> cnt(ctx->ws, "mk_cnt"), fillcnt(ctx->ws, "mk_fillcnt");
+    WsBuf<uint8_t> ghostflag(ctx->ws, "mk_ghostflag"), bigflag(ctx->ws, "mk_bigflag");
+    WsBuf<int64_t> overflow_list(ctx->ws, "mk_overflow");
+    WsBuf<unsigned long long> n_overflow(ctx->ws, "mk_noverflow");
+    WsBuf<int> error_flag(ctx->ws, "mk_error");
+    WsBuf<uint64_t> row_tot(ctx->ws, "mk_rowtot"), row_off(ctx->ws, "mk_rowoff");
     VGA_TRY(cnt.alloc_zero((size_t)nsrc * 8 + 8, st));
     VGA_TRY(fillcnt.alloc_zero((size_t)nsrc * 4 + 4, st));
     VGA_TRY(ghostflag.alloc_zero(4, st));
@@ -1194,7 +1196,7 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t sr
     a.e_bin = nullptr;
 
     // big-capacity scratch (allocated on demand)
-    DevBuf<unsigned char> big_scratch;
+    WsBuf<unsigned char> big_scratch(ctx->ws, "mk_bigscratch");
     const int big_warps = ctx->sm_count * WARPS_PER_BLOCK;
     unsigned long long h_over = 0;
     int h_err = 0;
@@ -1251,7 +1253,7 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t sr
     {
         size_t tb = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, tb, row_tot.p, row_off.p, (int)(nsrc + 1), st);
-        DevBuf<unsigned char> tmp;
+        WsBuf<unsigned char> tmp(ctx->ws, "mk_scantmp");
         VGA_TRY(tmp.alloc(tb + 16));
         cub::DeviceScan::ExclusiveSum(tmp.p, tb, row_tot.p, row_off.p, (int)(nsrc + 1), st);
         tm.launches++;
@@ -1280,10 +1282,10 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t sr
         set_error("vga_graph_build: a single row chunk exceeds 2^31 entries");
         return VGA_ERR_CAPACITY;
     }
-    DevBuf<uint32_t> e_ref, keys;
-    DevBuf<uint8_t> e_bin;
-    DevBuf<uint64_t> seg_off;
-    DevBuf<unsigned char> sort_tmp;
+    WsBuf<uint32_t> e_ref(ctx->ws, "mk_eref"), keys(ctx->ws, "mk_keys");
+    WsBuf<uint8_t> e_bin(ctx->ws, "mk_ebin");
+    WsBuf<uint64_t> seg_off(ctx->ws, "mk_segoff");
+    WsBuf<unsigned char> sort_tmp(ctx->ws, "mk_sorttmp");
     VGA_TRY(e_ref.alloc((size_t)max_chunk + 1));
     VGA_TRY(e_bin.alloc((size_t)max_chunk + 1));
     VGA_TRY(keys.alloc((size_t)max_chunk + 1));
@@ -1357,7 +1359,7 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t sr
             tm.launches++;
             const uint32_t total_v = (uint32_t)dg->cells;  // filled cells + ghosts
             const size_t rs_bytes = sizeof(uint32_t) * ((size_t)((total_v + 31u) >> 5) + (size_t)((((total_v + 31u) >> 5) + 31u) >> 5) + 4);
-            if (ctx->opt.build_sort == 1 && rs_bytes <= ctx->smem_optin) {
+            if (ctx->opt.build_sort != 0 && rs_bytes <= ctx->smem_optin) {
                 VGA_CUDA(cudaFuncSetAttribute(k_rank_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_bytes));
                 const unsigned blocks = (unsigned)std::min<int64_t>(ns, (int64_t)ctx->sm_count * 16);
                 k_rank_sort<<<blocks, RS_TPB, rs_bytes, st>>>(keys.p, seg_off.p, ns, total_v, gr->adj.p + base);
@@ -1366,7 +1368,7 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t sr
                 size_t tb = 0;
                 cub::DeviceSegmentedSort::SortKeys(nullptr, tb, keys.p, gr->adj.p + base, (int)cnt_e, (int)ns, seg_off.p,
                                                    seg_off.p + 1, st);
-                if (tb + 16 > sort_tmp.n) VGA_TRY(sort_tmp.alloc(tb + 16));
+                VGA_TRY(sort_tmp.alloc(tb + 16));
                 VGA_CUDA(cub::DeviceSegmentedSort::SortKeys(sort_tmp.p, tb, keys.p, gr->adj.p + base, (int)cnt_e, (int)ns,
                                                             seg_off.p, seg_off.p + 1, st));
                 tm.launches += 3;

@@ -105,17 +105,38 @@ struct Workspace {
     void clear() { bufs.clear(); }
 };
 
+// Typed view of a named workspace buffer: same alloc / alloc_zero interface as DevBuf, but the memory stays with the
+// context between calls (the ~25 temporaries of one vga_graph_build were a source of millisecond-scale jitter).
+template <typename T> struct WsBuf {
+    Workspace *ws;
+    const char *name;
+    T *p = nullptr;
+    size_t n = 0;
+    WsBuf(Workspace &w, const char *nm) : ws(&w), name(nm) {}
+    int alloc(size_t count) {
+        void *q = nullptr;
+        VGA_TRY(ws->get(name, (count ? count : 1) * sizeof(T), &q));
+        p = (T *)q;
+        n = count;
+        return VGA_OK;
+    }
+    int alloc_zero(size_t count, cudaStream_t s) {
+        VGA_TRY(alloc(count));
+        if (count) VGA_CUDA(cudaMemsetAsync(p, 0, count * sizeof(T), s));
+        return VGA_OK;
+    }
+};
+
 struct Timing {
-    double h2d_ms = 0, kernel_ms = 0, d2h_ms = 0, main_kernel_ms = 0, algo_bytes = 0, algo_bytes_runs = 0;
+    double h2d_ms = 0, kernel_ms = 0, d2h_ms = 0, main_kernel_ms = 0, algo_bytes = 0, algo_bytes_csr = 0, prep_ms = 0;
     int64_t launches = 0, main_launches = 0;
 };
 
 // Tunables (vga_ctx_set_option / environment)
 struct Options {
-    int64_t bfs_mode = 2;        // 0 push only, 1 pull only, 2 direction-optimising hybrid
-    int64_t bfs_words = 0;       // 64-bit words per vertex and batch (a batch = 64*words sources): 1, 2, 4; 0 = auto
-    int64_t local_mode = 2;      // 0: one CTA per cell with bitmaps, 1: bit-parallel batches of 64 cells, 2: auto,
-                                 // 3: batches with bit-sliced counters (EXPERIMENTAL, opt-in, not yet run on a GPU)
+    int64_t bfs_mode = 2;        // 0 top-down (push) only, 1 bottom-up (pull) only, 2 direction-optimising hybrid
+    int64_t bfs_words = 0;       // 64-bit words per vertex and batch (a batch = 64*words sources): 1, 2, 4, 8; 0 = auto
+    int64_t local_mode = 2;      // 0: one CTA per cell with bitmaps, 1: bit-parallel batches of 64 cells, 2: auto
     int64_t bfs_chunk = 0;       // 64-source words in flight; 0 = auto from free memory
     int64_t sieve_mode = 1;      // 1: thread-per-(source,octant) kernel + warp kernel for overflow, 0: warp kernel
     int64_t sieve_gcap = 48;     // shared-memory gap capacity per warp
@@ -123,25 +144,13 @@ struct Options {
     int64_t sieve_big_gcap = 4096;
     int64_t sieve_big_bcap = 32768;
     int64_t build_chunk_entries = (int64_t)1 << 30;
-    int64_t build_sort = 0;      // rows sorted by 0: cub segmented radix sort; 1: bitmap rank in shared memory (k_rank_sort;
-                                 // EXPERIMENTAL, opt-in, validated under SIMT emulation)
-    int64_t pull_alpha = 1;      // pull when frontier edges * alpha > candidate in-edges * beta (per batch)
+    int64_t build_sort = 1;      // rows ordered by 1: bitmap rank in shared memory (k_rank_sort, own kernel; measured 1.13x-1.4x
+                                 // faster builds); 0: cub segmented radix sort (also the fallback for grids of > 1.8M cells)
+    int64_t pull_alpha = 1;      // bottom-up step when (frontier out-nodes + 2n) * alpha > (open vertices' in-nodes + n) * beta
     int64_t pull_beta = 1;
     int64_t bfs_order = 2;       // 0: x-major ordinals, 1: 8x8 tiles in Morton order, 2: + wall-respecting floods
-    int64_t bfs_group = 16;      // batches per coarse lower-bound group
-    int64_t bfs_coarse = 1;      // 1: coarse pass (64 group lower bounds per bit-parallel batch) prunes the pull step
-    int64_t bfs_push_unroll = 1; // adjacency entries per lane and round in the top-down step: 1 (default) or 4 (EXPERIMENTAL,
-                                 // opt-in, not yet run on a GPU: more loads in flight per lane)
-    int64_t bfs_push = 0;        // top-down step: 0 = adjacency entries (k_push); 1 = additionally range-OR updates over the
-                                 // runs of the out-rows through a pyramid of `next` (k_push_pyr + k_pyr_down) whenever the
-                                 // per-batch cost model prefers them (EXPERIMENTAL, opt-in; validated under SIMT emulation)
-    int64_t bfs_pyr_cost = 100;  // percent: cost of one pyramid-push node relative to one adjacency entry in the per-batch choice
-                                 // between entry push, pyramid push and pull (to be tuned on the B200)
-    int64_t bfs_pyr_nodes = 0;   // with bfs_push / bfs_pull = 1: rows as lists of pyramid NODE ids instead of runs, walked by
-                                 // copies of the entry kernels' inner loops (k_push_nodes / k_pull_nodes; EXPERIMENTAL, opt-in)
-    int64_t bfs_pull = 0;        // bottom-up step: 0 scans in-row entries (k_pull); 1 = range-OR queries over an
-                                 // OR-pyramid of the frontier with run-length in-rows (k_pull_pyr; EXPERIMENTAL, opt-in,
-                                 // index logic unit-tested on CPU, kernels not yet run on a GPU)
+    int64_t bfs_l2_words = 0;    // auto word width: largest W whose randomly accessed state (2 pyramids of n*W words) fits
+                                 // this many MB of L2; 0 = 96
 };
 
 }  // namespace vga
@@ -194,44 +203,41 @@ struct vga_graph {
     vga::DevBuf<uint8_t> gridconn;
     std::vector<int32_t> h_refs;    // N + G packed PixelRefs (host)
     vga::DevBuf<uint8_t> noexpand;  // [n] != 0: counted but not expanded (context-filled, not even); empty = none
-    // derived analysis structures, built lazily
-    vga::DevBuf<uint64_t> t_rowptr; // transpose (in-edges), [n+1]
-    vga::DevBuf<uint32_t> t_col;    // [entries to filled targets]
-    bool has_transpose = false;
-    int64_t t_entries = 0;
-    // run-length in-rows for the pyramid pull (bfs_pull = 1), built lazily: the sorted in-row of v is the union of
-    // the runs t_runs[t_runptr[v] .. t_runptr[v+1]) = (first ordinal, length); t_costptr = prefix sums of the
-    // pyramid loads a full scan of each in-row costs
-    vga::DevBuf<uint64_t> t_runptr;  // [n+1]
-    vga::DevBuf<uint2> t_runs;
-    vga::DevBuf<uint64_t> t_costptr; // [n+1]
-    bool has_runs = false;
-    int64_t t_nruns = 0;
-    // run-length out-rows for the pyramid push (bfs_push = 1), ghost columns excluded
-    vga::DevBuf<uint64_t> f_runptr;
-    vga::DevBuf<uint2> f_runs;
-    vga::DevBuf<uint64_t> f_costptr;
-    bool has_fwd_runs = false;
-    int64_t f_nruns = 0;
-    // node-id lists (bfs_pyr_nodes = 1): the pyramid nodes tiling each row's runs; row offsets = f_costptr / t_costptr
+    // ---- BFS structures, built lazily from the sorted rows (bfs.cu) or adopted (vga_graph_from_device_runs) ----------
+    // Rows of a grid visibility graph are unions of a few runs of consecutive ordinals.  f_runs: the out-row of u is the
+    // union of f_runs[f_runptr[u] .. f_runptr[u+1]) = (first ordinal, length), ghost columns excluded; t_runs: the same
+    // for the in-rows (transposed by bfs.cu in O(runs), no entry-sized transpose exists).  f_nodes / t_nodes: per row the
+    // ids of the OR-pyramid nodes that tile its runs (id < n: the vertex's own word, id >= n: inner node id - n), row
+    // offsets f_nodeptr / t_nodeptr.  The BFS reads only the node lists.
+    vga::DevBuf<uint64_t> f_runptr, t_runptr;    // [n+1]
+    vga::DevBuf<uint2> f_runs, t_runs;
+    int64_t f_nruns = 0, t_nruns = 0;
+    bool has_fwd_runs = false, has_runs = false;
+    bool has_shard_runs = false;                 // f_runs hold the rows [src_begin, src_end) of a shard only
+    vga::DevBuf<uint64_t> f_nodeptr, t_nodeptr;  // [n+1]
     vga::DevBuf<uint32_t> f_nodes, t_nodes;
     bool has_f_nodes = false, has_t_nodes = false;
+    vga::DevBuf<uint32_t> deg;                   // [n] entries per row when the graph holds runs only (statistics), else empty
+    // spatially coherent order of all n sources (cached: the host-side clustering costs milliseconds per call)
+    std::vector<int32_t> h_order;
 };
 
 namespace vga {
 // makegraph.cu
 int build_graph(vga_ctx *ctx, const vga_dgrid *g, int64_t src_begin, int64_t src_end, vga_graph **out);
 // bfs.cu
-int ensure_transpose(vga_ctx *ctx, vga_graph *g);
-int ensure_runs(vga_ctx *ctx, vga_graph *g);
-int ensure_fwd_runs(vga_ctx *ctx, vga_graph *g);
-int ensure_node_lists(vga_ctx *ctx, vga_graph *g, bool fwd, bool transposed);
+int ensure_fwd_runs(vga_ctx *ctx, vga_graph *g);  // run-length out-rows from the sorted entries
+int shard_runs(vga_ctx *ctx, vga_graph *g);       // the same for the rows a shard holds
+int row_degrees(vga_ctx *ctx, vga_graph *g);      // entries per held row (g->deg)
+int ensure_bfs_lists(vga_ctx *ctx, vga_graph *g, bool transposed);  // node lists (+ transposed runs / node lists)
 // cabi.cu: per-segment ascending sort of 32-bit keys (cub::DeviceSegmentedSort in slices of < 2^31 entries)
 int sort_segments_u32(vga_ctx *ctx, uint32_t *keys_in, uint32_t *keys_out, int64_t entries, int64_t rows, const uint64_t *rowptr);
 // spatially coherent order of the sources [src_begin, src_end) for 64-source batches
 int batch_source_order(vga_ctx *ctx, vga_graph *g, int64_t src_begin, int64_t src_end, std::vector<int32_t> &order);
-int run_global(vga_ctx *ctx, vga_graph *g, int radius, int64_t src_begin, int64_t src_end, int32_t *total_nodes,
-               int64_t *total_depth, int32_t *dist, int32_t max_levels, int32_t *levels_used);
+int batch_source_order_list(vga_ctx *ctx, vga_graph *g, const int64_t *sources, int64_t nsrc, std::vector<int32_t> &order);
+// sources: explicit list of ordinals (nullptr = the range [src_begin, src_end)); outputs in list order
+int run_global(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources, int64_t src_begin, int64_t src_end,
+               int32_t *total_nodes, int64_t *total_depth, int32_t *dist, int32_t max_levels, int32_t *levels_used);
 // stepdepth.cu
 int run_step_depth(vga_ctx *ctx, vga_graph *g, const int64_t *sources, int64_t nsrc, int32_t *depth_out);
 // local.cu

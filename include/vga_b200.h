@@ -80,8 +80,10 @@ typedef struct {
     double main_kernel_ms;   /* the dominant kernel(s) only: BFS level kernels / sieve passes / local */
     int64_t launches;  /* kernels launched by the call */
     int64_t main_launches;
-    double algo_bytes; /* algorithmic bytes of the dominant kernel(s), DESIGN.md formula */
-    double algo_bytes_runs; /* vga_global with bfs_push = 1: the same model with run-length rows (8 bytes per run), else 0 */
+    double algo_bytes; /* algorithmic bytes of the dominant kernel(s), DESIGN.md formula, rows in the format the
+                          kernels read (vga_global: 4 bytes per pyramid-node id of a run-length row) */
+    double algo_bytes_csr; /* vga_global: the same model with 4-byte CSR entries (SURVEY.md 8d as written), else 0 */
+    double prep_ms;    /* vga_global: one-time derivation of the BFS row lists of the graph (first call only) */
 } vga_timing;
 
 const char *vga_last_error(void);
@@ -160,6 +162,15 @@ int vga_global(vga_ctx *ctx, const vga_graph *g, int radius, int64_t src_begin, 
                int32_t *total_nodes, int64_t *total_depth, int32_t *dist, int32_t max_levels,
                int32_t *levels_used);
 
+/* The same for an explicit list of source ordinals (any order; the library forms spatially coherent batches itself).
+ * Outputs are in list order. */
+int vga_global_sources(vga_ctx *ctx, const vga_graph *g, int radius, const int64_t *sources, int64_t n_sources,
+                       int32_t *total_nodes, int64_t *total_depth, int32_t *dist, int32_t max_levels,
+                       int32_t *levels_used);
+/* The order in which vga_global batches all N sources (order[i] = ordinal of the i-th source; consecutive groups of
+ * 64*W entries are the spatially compact batches).  Lets a caller pick representative subsets of whole batches. */
+int vga_graph_batch_order(vga_ctx *ctx, const vga_graph *g, int32_t *order);
+
 /* Formula stage (host, FP64 -> float exactly as AttributeRow::setValue stores them); -1 sentinels
  * as in the reference.  Any output may be NULL. */
 int vga_global_attributes(int64_t n, const int32_t *total_nodes, const int64_t *total_depth, const int32_t *dist,
@@ -182,11 +193,30 @@ int vga_step_depth(vga_ctx *ctx, const vga_graph *g, const int64_t *sources, int
 /* ---- device-resident access for multi-GPU plumbing (pointers are CUDA device pointers) ------ */
 
 /* Device pointers of the sorted shard rows (valid until vga_graph_free): rowptr (u64, local,
- * rows+1), packed adjacency entries (u32: col<<5 | bin), number of entries. */
+ * rows+1), packed adjacency entries (u32: col<<6 | accepted<<5 | bin), number of entries. */
 int vga_graph_device_rows(const vga_graph *g, const uint64_t **d_rowptr, const uint32_t **d_adj, int64_t *n_entries);
 /* Adopt device-resident packed rows for all N cells (e.g. after an NCCL all-gather of shards). */
 int vga_graph_from_device_rows(vga_ctx *ctx, int64_t n_cells, int64_t n_ghosts, const uint64_t *d_rowptr,
                                const uint32_t *d_adj, int64_t n_entries, vga_graph **out);
+
+/* Run-length form of the shard's rows: what the BFS reads and what a multi-GPU run exchanges (8 bytes per run instead of
+ * 4 bytes per entry: 1.3 GB instead of 22 GB at 10^6 cells).  runptr (u64, local, rows+1), runs = pairs of u32 (first
+ * column ordinal, length) sorted by first ordinal, ghost columns excluded.  Valid until vga_graph_free. */
+int vga_graph_device_runs(vga_ctx *ctx, const vga_graph *g, const uint64_t **d_runptr, const void **d_runs, int64_t *n_runs);
+/* Adopt device-resident run-length rows of all N cells (e.g. the all-gathered shards).  The graph serves vga_global /
+ * vga_global_sources only (no entries, bins or statistics).  d_degree (u32 [N], entries per row, may be NULL) only
+ * feeds the CSR byte model of vga_timing. */
+int vga_graph_from_device_runs(vga_ctx *ctx, int64_t n_cells, int64_t n_ghosts, const uint64_t *d_runptr, const void *d_runs,
+                               int64_t n_runs, const uint32_t *d_degree, vga_graph **out);
+
+/* The same without the staging copy: the library allocates the run-length rows of a BFS-only graph and hands out
+ * WRITABLE device pointers (runptr u64 [N+1], runs 2 x u32 [n_runs], degree u32 [N], zeroed); the caller fills them
+ * (e.g. NCCL broadcasts of every rank's shard straight into their final place) and then calls vga_graph_runs_commit. */
+int vga_graph_runs_alloc(vga_ctx *ctx, int64_t n_cells, int64_t n_ghosts, int64_t n_runs, vga_graph **out,
+                         uint64_t **d_runptr, void **d_runs, uint32_t **d_degree);
+int vga_graph_runs_commit(vga_graph *g);
+/* entries per row (u32) of the rows this graph holds, device-resident (valid until vga_graph_free) */
+int vga_graph_device_degrees(vga_ctx *ctx, const vga_graph *g, const uint32_t **d_degree);
 
 #ifdef __cplusplus
 }

@@ -108,6 +108,12 @@ def olib():
         L.vgao_local_formulas.argtypes = [C.c_int64] + [C.c_void_p] * 7
         L.vgao_step_depth.restype = C.c_int
         L.vgao_step_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.vgao_global_csr.restype = C.c_int
+        L.vgao_global_csr.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_int32]
+        L.vgao_local_csr.restype = C.c_int
+        L.vgao_local_csr.argtypes = [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.vgao_sieve_kat.restype = C.c_int
         L.vgao_sieve_kat.argtypes = [C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         _olib = L
@@ -200,6 +206,60 @@ class OracleGraph:
         ctl = np.zeros(k, np.float32)
         olib().vgao_local(self.h, b, e, _p(cl), _p(kk), _p(tot), _p(ctl))
         return cl, kk, tot, ctl
+
+
+def _threads():
+    return max(1, min(32, os.cpu_count() or 1))
+
+
+def global_csr(n, rowptr, col, sources, radius=-1, maxl=64, shift=0):
+    """vgao_global over an ordinal CSR (rowptr uint64 [n+1], col uint32 [E], entry = col >> shift) for the listed
+    sources; the sources are split over host threads (the C call releases the GIL).  No copy of col is made."""
+    from concurrent.futures import ThreadPoolExecutor
+    rowptr = np.ascontiguousarray(rowptr, np.uint64)
+    assert col.dtype == np.uint32 and col.flags.c_contiguous
+    src = np.ascontiguousarray(sources, np.int64)
+    k = len(src)
+    tn = np.zeros(k, np.int32)
+    td = np.zeros(k, np.int64)
+    dist = np.zeros((k, maxl), np.int32)
+    L = olib()
+
+    def part(lo, hi):
+        return L.vgao_global_csr(n, _p(rowptr), _p(col), shift, radius, src[lo:hi].ctypes.data, hi - lo,
+                                 tn[lo:hi].ctypes.data, td[lo:hi].ctypes.data, dist[lo:hi].ctypes.data, maxl)
+    nt = min(_threads(), k) or 1
+    cuts = [k * i // nt for i in range(nt + 1)]
+    with ThreadPoolExecutor(nt) as ex:
+        rcs = list(ex.map(lambda ab: part(*ab), zip(cuts[:-1], cuts[1:])))
+    if any(rcs):
+        raise RuntimeError("oracle BFS: maxl too small")
+    return tn, td, dist
+
+
+def local_csr(n, nv, rowptr, col, refs, cells, shift=0):
+    """vgao_local over an ordinal CSR for the listed cells (rows sorted or not); refs = packed PixelRef of all nv
+    vertices (cells then ghosts).  Split over host threads."""
+    from concurrent.futures import ThreadPoolExecutor
+    rowptr = np.ascontiguousarray(rowptr, np.uint64)
+    assert col.dtype == np.uint32 and col.flags.c_contiguous
+    refs = np.ascontiguousarray(refs, np.int32)
+    cs = np.ascontiguousarray(cells, np.int64)
+    k = len(cs)
+    cl = np.zeros(k, np.int64)
+    kk = np.zeros(k, np.int32)
+    tot = np.zeros(k, np.int32)
+    ctl = np.zeros(k, np.float32)
+    L = olib()
+
+    def part(lo, hi):
+        return L.vgao_local_csr(n, nv, _p(rowptr), _p(col), shift, _p(refs), cs[lo:hi].ctypes.data, hi - lo,
+                                cl[lo:hi].ctypes.data, kk[lo:hi].ctypes.data, tot[lo:hi].ctypes.data, ctl[lo:hi].ctypes.data)
+    nt = min(_threads(), k) or 1
+    cuts = [k * i // nt for i in range(nt + 1)]
+    with ThreadPoolExecutor(nt) as ex:
+        list(ex.map(lambda ab: part(*ab), zip(cuts[:-1], cuts[1:])))
+    return cl, kk, tot, ctl
 
 
 def global_formulas(tn, td, dist, nl):

@@ -366,6 +366,83 @@ double dmxref_sample_makegraph(void *h, const int32_t *src, int k, double maxdis
     return t1 - t0;
 }
 
+// ---- the graph of a large plan built by several processes (bench.py --impl reference on the 10^6-cell workload) -----
+// The reference is single-threaded and non-reentrant (function-local statics in sparkPixel2), but independent PROCESSES
+// can each make the Nodes of a share of the sources (the body of sparkGraph2's source loop, as in
+// dmxref_sample_makegraph) and hand them over through the reference's own Node serialisation (Node::write / Node::read,
+// salalib/ngraph.cpp:195-220 -- what a .graph file holds).  File: int32 count, then per source int32 ordinal + Node.
+
+static std::vector<PixelRef> filled_order(PointMap &m) {
+    size_t rows = m.getRows(), cols = m.getCols();
+    std::vector<PixelRef> ord;
+    for (size_t x = 0; x < cols; x++)
+        for (size_t y = 0; y < rows; y++)
+            if (m.getPoint(PixelRef((short)x, (short)y)).filled()) ord.push_back(PixelRef((short)x, (short)y));
+    return ord;
+}
+
+// Makes the Nodes of the listed sources and writes them to `path`; the Nodes are dropped again afterwards (the caller
+// loads all parts with dmxref_load_nodes).  Returns seconds spent in the construction, negative on failure.
+double dmxref_build_nodes_to_file(void *h, const int32_t *src, int k, double maxdist, const char *path) {
+    PointMap &m = *static_cast<Ref *>(h)->map;
+    if (!m.m_blockedlines) m.blockLines();
+    std::vector<PixelRef> ord = filled_order(m);
+    m.m_attributes->insertOrResetLockedColumn("Connectivity");
+    m.m_attributes->insertOrResetColumn("Point First Moment");
+    m.m_attributes->insertOrResetColumn("Point Second Moment");
+    m.tagState(true);
+    std::ofstream out(path, std::ios::binary);
+    if (!out) return -1.0;
+    int32_t count = k;
+    out.write((const char *)&count, sizeof(count));
+    double spent = 0.0;
+    for (int i = 0; i < k; i++) {
+        PixelRef curs = ord[src[i]];
+        double t0 = now_s();
+        m.getPoint(curs).m_node = std::unique_ptr<Node>(new Node());
+        if (!m.m_attributes->getRowPtr(AttributeKey(curs))) m.m_attributes->addRow(AttributeKey(curs));
+        m.getPoint(curs).m_processflag = 0x00FF;
+        m.sparkPixel2(curs, 1, maxdist);
+        spent += now_s() - t0;
+        int32_t o = src[i];
+        out.write((const char *)&o, sizeof(o));
+        m.getPoint(curs).getNode().write(out);
+        m.getPoint(curs).m_node.reset();
+    }
+    m.tagState(false);
+    out.close();
+    return out ? spent : -1.0;
+}
+
+// Reads a file written by dmxref_build_nodes_to_file into the map's Points.  Returns the number of Nodes read, -1 on failure.
+int64_t dmxref_load_nodes(void *h, const char *path) {
+    PointMap &m = *static_cast<Ref *>(h)->map;
+    std::vector<PixelRef> ord = filled_order(m);
+    std::ifstream in(path, std::ios::binary);
+    if (!in) return -1;
+    int32_t count = 0;
+    in.read((char *)&count, sizeof(count));
+    for (int32_t i = 0; i < count; i++) {
+        int32_t o = -1;
+        in.read((char *)&o, sizeof(o));
+        if (!in || o < 0 || (size_t)o >= ord.size()) return -1;
+        Point &p = m.getPoint(ord[o]);
+        p.m_node = std::unique_ptr<Node>(new Node());
+        p.m_node->read(in);
+        if (!in) return -1;
+    }
+    return count;
+}
+
+// number of filled cells that hold a Node
+int64_t dmxref_node_count(void *h) {
+    PointMap &m = *static_cast<Ref *>(h)->map;
+    int64_t c = 0;
+    for (const PixelRef &p : filled_order(m))
+        if (m.getPoint(p).m_node) c++;
+    return c;
+}
+
 // Global BFS for K sampled sources on a made graph: the per-source body of
 // VGAVisualGlobal::run (vgavisualglobal.cpp:80-130, no merges) re-stated around the
 // reference's own public VGAVisualGlobal::extractUnseen.  Outputs integers per source.

@@ -885,6 +885,127 @@ void vgao_local_formulas(int64_t n, const int64_t *cluster, const int32_t *k, co
     }
 }
 
+/* ---------------------------------------------------------------- full-size checks over an ordinal CSR
+ * The same level BFS (vgao_global) and local counts (vgao_local) over an adjacency handed over as CSR of vertex
+ * ORDINALS (x-major index of the filled cell; ordinals >= n are unfilled "ghost" cells inside diagonal runs: never
+ * counted or expanded, p.filled() test vgavisualglobal.cpp:104; members of neighbourhoods in vgavisuallocal.cpp:50-57
+ * but without a node of their own).  No copy of the adjacency is made, so the full-size configurations (5.5e9 entries)
+ * can be checked for sampled sources / cells.  Entries are `col[e] >> shift` (shift 6 = the library's packed form).
+ * Single-threaded per call; the Python binding splits the independent sources / cells over threads. */
+int vgao_global_csr(int64_t n, const uint64_t *rowptr, const uint32_t *col, int shift, int radius, const int64_t *src,
+                    int64_t nsrc, int32_t *total_nodes, int64_t *total_depth, int32_t *dist, int32_t maxl) {
+    int rc = 0;
+    {
+        uint8_t *seen = (uint8_t *)malloc((size_t)n);
+        uint32_t *cur = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)n);
+        uint32_t *nxt = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)n);
+        for (int64_t s = 0; s < nsrc; s++) {
+            memset(seen, 0, (size_t)n);
+            int64_t ncur = 0, nnxt = 0;
+            cur[ncur++] = (uint32_t)src[s];
+            seen[src[s]] = 1;
+            int32_t tn = 0;
+            int64_t td = 0;
+            int level = 0;
+            if (dist) memset(dist + s * maxl, 0, sizeof(int32_t) * maxl);
+            while (ncur > 0) {
+                nnxt = 0;
+                for (int64_t i = 0; i < ncur; i++) {
+                    const uint32_t u = cur[i];
+                    td += level;
+                    tn += 1;
+                    if (radius == -1 || level < radius) {
+                        for (uint64_t e = rowptr[u]; e < rowptr[u + 1]; e++) {
+                            const uint32_t w = col[e] >> shift;
+                            if (w < (uint32_t)n && !seen[w]) {
+                                seen[w] = 1;
+                                nxt[nnxt++] = w;
+                            }
+                        }
+                    }
+                }
+                if (level < maxl) {
+                    if (dist) dist[s * maxl + level] = (int32_t)ncur;
+                } else {
+                    rc = -1;
+                }
+                uint32_t *t = cur;
+                cur = nxt;
+                nxt = t;
+                ncur = nnxt;
+                level++;
+            }
+            total_nodes[s] = tn;
+            total_depth[s] = td;
+        }
+        free(seen);
+        free(cur);
+        free(nxt);
+    }
+    return rc;
+}
+
+/* rows must be sorted by ordinal (PixelRef order with ghosts last is NOT PixelRef order: `ref` gives the packed
+ * PixelRef of every vertex, n cells then the ghosts, so that the float32 control sum runs in the reference's
+ * sorted-PixelRef order, vgavisuallocal.cpp:50-52) */
+static int cmp_refpair(const void *pa, const void *pb) {
+    const int64_t a = *(const int64_t *)pa, b = *(const int64_t *)pb; /* (unsigned ref << 32) | ordinal: x then y */
+    return (a > b) - (a < b);
+}
+int vgao_local_csr(int64_t n, int64_t nv, const uint64_t *rowptr, const uint32_t *col, int shift, const int32_t *ref,
+                   const int64_t *cells, int64_t ncells, int64_t *cluster, int32_t *k, int32_t *total, float *control) {
+    {
+        int64_t *in_hood = (int64_t *)malloc(sizeof(int64_t) * (size_t)nv);
+        int64_t *in_total = (int64_t *)malloc(sizeof(int64_t) * (size_t)nv);
+        for (int64_t i = 0; i < nv; i++) in_hood[i] = in_total[i] = -1;
+        int64_t *hood = NULL;
+        int64_t hcap = 0;
+        for (int64_t s = 0; s < ncells; s++) {
+            const int64_t v = cells[s];
+            int64_t nh = 0;
+            for (uint64_t e = rowptr[v]; e < rowptr[v + 1]; e++) {
+                const uint32_t w = col[e] >> shift;
+                if (in_hood[w] != s) {
+                    in_hood[w] = s;
+                    if (nh == hcap) {
+                        hcap = hcap ? hcap * 2 : 1024;
+                        hood = (int64_t *)realloc(hood, sizeof(int64_t) * (size_t)hcap);
+                    }
+                    /* PixelRef operator< compares x then y as shorts; coordinates are non-negative here */
+                    hood[nh++] = ((int64_t)(uint32_t)ref[w] << 32) | (int64_t)w;
+                }
+            }
+            qsort(hood, (size_t)nh, sizeof(int64_t), cmp_refpair);
+            int64_t cl = 0, ntotal = 0;
+            float ctl = 0.0f;
+            for (int64_t i = 0; i < nh; i++) {
+                const uint32_t u = (uint32_t)(hood[i] & 0xffffffff);
+                if (u >= (uint32_t)n) continue; /* not filled: no node */
+                int64_t isz = 0, rsz = 0;
+                for (uint64_t e = rowptr[u]; e < rowptr[u + 1]; e++) {
+                    const uint32_t w = col[e] >> shift;
+                    rsz++;
+                    if (in_hood[w] == s) isz++;
+                    if (in_total[w] != s) {
+                        in_total[w] = s;
+                        ntotal++;
+                    }
+                }
+                ctl += 1.0f / (float)rsz;
+                cl += isz;
+            }
+            cluster[s] = cl;
+            k[s] = (int32_t)nh;
+            total[s] = (int32_t)ntotal;
+            control[s] = ctl;
+        }
+        free(in_hood);
+        free(in_total);
+        free(hood);
+    }
+    return 0;
+}
+
 /* ---------------------------------------------------------------- step depth (vgavisualglobaldepth.cpp:23-75)
  * BFS from a set of cells; depth[v] = level at which the filled cell v is first popped, -1 if never
  * (the column is reset to -1 by insertOrResetColumn).  No merges / context fill. */

@@ -72,6 +72,14 @@ int vgao_local(const vgao_graph *gr, int64_t src_begin, int64_t src_end, int64_t
 void vgao_local_formulas(int64_t n, const int64_t *cluster, const int32_t *k, const int32_t *total,
                          const float *control, float *clustering, float *control_out, float *controllability);
 
+/* vgao_global / vgao_local over an adjacency given as CSR of vertex ordinals (entry = col[e] >> shift; ordinals >= n are
+ * ghost cells), for sampled sources / cells of the full-size configurations; no copy of the adjacency; callers may
+ * split the samples over threads.  ref = packed PixelRef of every vertex (n cells, then ghosts). */
+int vgao_global_csr(int64_t n, const uint64_t *rowptr, const uint32_t *col, int shift, int radius, const int64_t *src,
+                    int64_t nsrc, int32_t *total_nodes, int64_t *total_depth, int32_t *dist, int32_t maxl);
+int vgao_local_csr(int64_t n, int64_t nv, const uint64_t *rowptr, const uint32_t *col, int shift, const int32_t *ref,
+                   const int64_t *cells, int64_t ncells, int64_t *cluster, int32_t *k, int32_t *total, float *control);
+
 /* visual step depth from a set of source cells (x-major ordinals): depth[N], -1 = not reached
  * (salalib/vgamodules/vgavisualglobaldepth.cpp:23-75) */
 int vgao_step_depth(const vgao_graph *gr, const int32_t *src, int64_t nsrc, int32_t *depth);

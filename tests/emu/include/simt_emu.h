@@ -463,6 +463,10 @@ inline float __fadd_rn(float a, float b) { return a + b; }
 inline double __longlong_as_double(long long v) { return simt::from_bits<double>((uint64_t)v); }
 inline long long __double_as_longlong(double v) { return (long long)simt::to_bits(v); }
 
+// cache-hinted loads / stores: plain accesses on the CPU
+template <typename T> inline T __ldcs(const T *p) { return *p; }
+template <typename T> inline T __ldcg(const T *p) { return *p; }
+template <typename T> inline void __stcs(T *p, T v) { *p = v; }
 template <typename T, typename V> inline T atomicAdd(T *p, V v) {
     T o = *p;
     *p = (T)(o + (T)v);

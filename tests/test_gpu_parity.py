@@ -174,13 +174,11 @@ def cached_oracle(name):
 
 @pytest.mark.parametrize("name", ["oblique:30:30:7", "office:64:64:1"])
 @pytest.mark.parametrize("radius", [-1, 2])
-@pytest.mark.parametrize("mode,words,coarse,order", [(0, 1, 0, 0), (1, 1, 1, 1), (2, 1, 1, 2), (0, 4, 0, 2), (1, 2, 1, 2),
-                                                     (2, 4, 1, 2), (2, 0, 1, 2)])
-def test_global_vs_oracle_all_modes(name, radius, mode, words, coarse, order):
+@pytest.mark.parametrize("mode,words,order", [(0, 1, 0), (1, 1, 1), (2, 1, 2), (0, 4, 2), (1, 2, 2), (2, 4, 2), (2, 0, 2)])
+def test_global_vs_oracle_all_modes(name, radius, mode, words, order):
     c = capi.Context(0)
     c.set_option("bfs_mode", mode)
     c.set_option("bfs_words", words)
-    c.set_option("bfs_coarse", coarse)
     c.set_option("bfs_order", order)
     flat, og = cached_oracle(name)
     g = c.build(flat)
@@ -379,8 +377,8 @@ def test_properties_c1_full_size(ctx):
 
 def test_properties_c2_full_size(ctx):
     """BASELINE config 2 (the bench workload) at full size: histogram identities, full reachability, and
-    equality of two entirely different BFS schedules (default: coherent clusters + coarse-pruned hybrid
-    vs. plain x-major push-only single-word batches).  Both local kernels must agree on a slice (config 3)."""
+    equality of two entirely different BFS schedules (default: coherent clusters + direction-optimising hybrid
+    vs. plain x-major top-down-only single-word batches).  Both local kernels must agree on a slice (config 3)."""
     flat = capi.prepare(plans.by_name("C2"))
     g = ctx.build(flat)
     tn, td, dist, used = g.global_ints(-1)
@@ -388,7 +386,7 @@ def test_properties_c2_full_size(ctx):
     assert ((dist * np.arange(dist.shape[1])).sum(axis=1) == td).all()
     assert (tn == g.n).all()
     c2 = capi.Context(0)
-    for k, v in (("bfs_mode", 0), ("bfs_words", 1), ("bfs_order", 0), ("bfs_coarse", 0), ("local_mode", 1)):
+    for k, v in (("bfs_mode", 0), ("bfs_words", 1), ("bfs_order", 0), ("local_mode", 1)):
         c2.set_option(k, v)
     g2 = c2.build(flat)
     tn2, td2, dist2, used2 = g2.global_ints(-1)

@@ -125,3 +125,48 @@ def test_step_depth_matches_reference():
             cache[name] = po.OracleGraph(grid_of(golden(name)))
         d = cache[name].step_depth(sd[k])
         assert np.array_equal(d.astype(np.float32), sd[f"{name}__{i}__depth"]), k
+
+
+# ---- the CSR form of the oracle used by the full-size GPU parity tests -------------------------------------------
+
+def ordinal_csr(flat, og):
+    """The oracle's iterated adjacency as CSR of vertex ordinals: N cells in x-major order, then all unfilled cells
+    in x-major order (the library's numbering, include/vga_b200.h)."""
+    rp, ref, _ = og.iter_rows()
+    st = flat.state.reshape(flat.cols, flat.rows)
+    gx, gy = np.nonzero((st & 2) == 0)
+    allrefs = np.concatenate([og.cell_refs(), ((gx.astype(np.int64) << 16) + gy).astype(np.int32)])
+    key = allrefs.astype(np.uint32).astype(np.int64)
+    order = np.argsort(key, kind="stable")
+    col = order[np.searchsorted(key[order], ref.astype(np.uint32).astype(np.int64))].astype(np.uint32)
+    return rp, col, allrefs
+
+
+@pytest.mark.parametrize("name", ["oblique:30:30:7", "office:48:48:2", "room:24:24:1+holes"])
+def test_csr_oracle_equals_graph_oracle(name):
+    from depthmapx_b200 import capi, plans
+    flat = capi.prepare(plans.by_name(name.split("+")[0]))
+    if name.endswith("+holes"):  # unfilled cells inside diagonal runs -> ghost vertices
+        st = flat.state.copy()
+        for d in (3, 5):
+            st[(2 + d) * flat.rows + (2 + d)] &= ~np.uint16(2)
+        flat.state = st
+    og = po.OracleGraph(po.Grid(flat.cols, flat.rows, flat.spacing, flat.bl_x, flat.bl_y, flat.state, flat.line_off, flat.lines))
+    n = og.n
+    rp, col, allrefs = ordinal_csr(flat, og)
+    if name.endswith("+holes"):
+        assert (col >= n).any()
+    src = np.random.RandomState(1).choice(n, min(n, 40), replace=False)
+    for radius in (-1, 2):
+        tn, td, dist = po.global_csr(n, rp, col, src, radius)
+        for i, s in enumerate(src):
+            otn, otd, odist, _ = og.global_ints(radius, (int(s), int(s) + 1), maxl=64)
+            assert otn[0] == tn[i] and otd[0] == td[i] and np.array_equal(odist[0], dist[i])
+    # packed form (col << 6 | flags), as the library stores it
+    tn2, td2, dist2 = po.global_csr(n, rp, (col << 6) | np.uint32(37), src, -1, shift=6)
+    tn1, td1, dist1 = po.global_csr(n, rp, col, src, -1)
+    assert np.array_equal(tn1, tn2) and np.array_equal(td1, td2) and np.array_equal(dist1, dist2)
+    cl, kk, tot, ctl = po.local_csr(n, len(allrefs), rp, col, allrefs, src)
+    for i, s in enumerate(src):
+        o = og.local_ints((int(s), int(s) + 1))
+        assert o[0][0] == cl[i] and o[1][0] == kk[i] and o[2][0] == tot[i] and o[3][0] == ctl[i]

@@ -4,9 +4,8 @@ that must be byte-identical to what the unmodified reference CLI wrote (tests/go
 
 The codec and the attribute stages are pinned on CPU (tests/test_graphfile.py); what is new on the GPU side is
 PointMap::nodes() (Node encoding from the device rows), PointMap::ensureGraph() (upload of a loaded adjacency with bins)
-and the host-level VGAVisualGlobalDepth.  These have not run on a B200 yet (round 1 ran out of GPU minutes); they do pass
-against the SIMT emulation of the CUDA sources on CPU (tests/test_emulated_kernels.py runs this module with --runxfail).
-Until the first B200 run the module is xfail(strict=False) and sorted last: it cannot mask or break the parity suite."""
+and the host-level VGAVisualGlobalDepth.  Green on a B200 since round 2 (all cases; the first-run xfail guard of round 1
+is gone); the CPU suite runs the same module against the SIMT emulation (tests/test_emulated_kernels.py)."""
 import os
 
 import numpy as np
@@ -16,7 +15,7 @@ from conftest import golden
 from depthmapx_b200 import capi
 
 # a kernel that never returns would hang the GPU box: give up on the whole run instead (these modules run last)
-pytestmark = [pytest.mark.timeout(900, method="thread"), pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="passes under SIMT emulation on CPU; first B200 run pending")]
+pytestmark = [pytest.mark.timeout(900, method="thread"), pytest.mark.gpu]
 
 CASES = ["oblique12", "oblique10s07", "office16"]
 
