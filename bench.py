@@ -1,24 +1,32 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the visibility-graph hot path (makegraph + VGA visibility global).
 
-One "step" = one full pass of the hot path over the workload's floor plan:
-    sparkGraph2 (all N cells)  ->  all-sources BFS (N sources, radius n)  -> per-source integers on the host.
-metric = cells/s through makegraph + VGA global (BASELINE.json), with the two stages also reported
-separately (makegraph cells/s, global source-BFS cells/s).
+Workload (default): BASELINE.json configs[4], the configuration the metric is quoted on -- the 1024x1024 synthetic urban
+grid, 1,048,576 open cells, 5.48e9 adjacency entries (C5).  Other configs: --workload C1|C2|C4|kind:W:H:seed.
 
+One "step" = one pass of the hot path over the plan:
+    sparkGraph2 for ALL N cells (every rank its share of the source rows)
+    -> [N > 1: one exchange of the run-length rows over NCCL: every rank then holds the whole graph]
+    -> all-sources BFS (VGAVisualGlobal) from a fixed, evenly spread subset of S sources made of whole spatial batches
+       (every `stride`-th group of 512 sources of the library's batch order; S = N / stride; stride 1 = every source)
+    -> per-source integers on the host of rank 0.
+A full C5 pass (S = N) takes ~10 s on one GPU, the driver times 2 x 25 steps, hence the subset; the BFS cost per source
+does not depend on which sources are chosen (every BFS covers the whole graph), and the subset keeps the library's
+spatially compact batches intact.  It is identical for every N (strong scaling).
+
+  metric       cells/s through makegraph + global BFS = 1 / (t_graph / N + t_bfs / S), t_graph = construction + exchange +
+               derivation of the BFS row lists (once per graph), t_bfs = the BFS over the S sources; medians over the timed
+               steps.  With S = N this is N / step time.  `full_job_ms_extrapolated` = t_graph + t_bfs * N / S.
+  ms_per_step  median measured step (device time between CUDA events with the device idle at both ends, max over ranks)
   value        inputs (flat grid) already resident in HBM when the timed region starts
-  e2e          the same step through the C ABI with HOST buffers: H2D of the grid and D2H of the
-               results inside the timed region
-  roofline     dominant kernel group = the BFS level kernels (push / pull / update), CUDA-event timed
-               inside the library on the stream they are launched on; algorithmic bytes per DESIGN.md
-  cpu_baseline the reference's own CPU implementation (oracle/_ref/libdmxref.so = unmodified reference
-               sources) on a bounded sample, 1 core (the reference is single-threaded)
+  e2e          the same step through the C ABI with HOST buffers (pinned): H2D of the grid and D2H of the results inside
+  roofline     dominant kernel group = the BFS level kernels, CUDA-event timed inside the library on the stream they are
+               launched on; algorithmic bytes per DESIGN.md with rows in the format the kernels read (pyramid node lists);
+               the CSR-entry model of SURVEY.md 8d is reported beside it
+  cpu_baseline the reference's own CPU implementation (oracle/_ref/libdmxref.so = unmodified reference sources) on a
+               bounded sample, on all host cores (one process per core: the reference is single-threaded)
 
-N > 1 (torchrun): makegraph rows are sharded by source range, the shards are all-gathered once over
-NCCL, BFS sources are partitioned over the replicated adjacency, results are gathered to rank 0.
-Strong scaling: the workload is fixed.
-
---impl reference times the reference CPU implementation on the same workload/metric (bounded sample).
+--impl reference times the reference CPU implementation on the same workload / metric (bounded sample per step).
 """
 from __future__ import annotations
 
@@ -38,6 +46,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "VGA makegraph + global source-BFS cells/sec"
 UNIT = "cells/s"
+GROUP = 512  # sources per subset granule = the largest batch (8 words) of the library
 
 
 def load_peaks():
@@ -93,45 +102,86 @@ class ClockSampler(threading.Thread):
                         reasons.add(nme)
             except Exception:
                 continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+        # median under load: samples of an idle GPU (set-up phases) would pull it down
+        busy = [x for x in sm if x >= 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx or None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def sample_sources(n, k, seed=1):
-    return sorted(random.Random(seed).sample(range(n), min(k, n)))
+def stats(xs):
+    xs = [float(x) for x in xs]
+    return {"min": min(xs), "median": float(np.median(xs)), "max": max(xs)}
 
 
-def reference_sample(plan, k_mk, k_bfs, radius, full_makegraph):
-    """Time the reference CPU implementation.  Returns dict with per-cell seconds of both stages."""
+def default_stride(workload):
+    return 4 if workload == "C5" else 1
+
+
+def workload_config(args, plan):
+    return {"workload": f"{args.workload}: {plan.name} synthetic plan, spacing {plan.spacing}, makegraph over all cells + "
+                        f"VGA visibility global radius {'n' if args.radius == -1 else args.radius}",
+            "walls": len(plan.walls)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm (CPU)
+
+def reference_arm(args, plan):
     from oracle import pyoracle as po
+    from oracle import refpool
+    if not po.have_ref():
+        po.build(ref=True)
+    procs = os.cpu_count() or 1
+    pool = refpool.RefPool(plan, procs, log=lambda *a: print("[reference]", *a, file=sys.stderr, flush=True))
+    n = pool.n
+    k = procs  # one source per process and step: the smallest sample that uses every core
+    times, mk, bfs = [], [], []
+    for it in range(args.warmup + args.steps):
+        src = sorted(random.Random(100 + it).sample(range(n), min(k, n)))
+        wall, mk_sum, bfs_sum, mk_max, bfs_max = pool.step(src, args.radius)
+        if it >= args.warmup:
+            times.append(wall)
+            mk.append(mk_sum / len(src))
+            bfs.append(bfs_sum / len(src))
+    pool.close()
+    ms = 1e3 * float(np.median(times))
+    val = k / (ms / 1e3)
+    sample = (f"each step = {k} sampled sources of the same plan, one per process on {procs} processes: the reference's "
+              f"sparkPixel2(make=1) and the per-source body of VGAVisualGlobal::run (extractUnseen) on the complete graph "
+              f"(made beforehand by the same processes, untimed: {pool.build_s:.0f} s, or loaded from the scratch cache); N={n}")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64 (sieve) + int (BFS)", "data": "synthetic",
+            "config": dict(workload_config(args, plan), cells=n),
+            "step_ms": stats([t * 1e3 for t in times]),
+            "per_source_s": {"makegraph": float(np.median(mk)), "global_bfs": float(np.median(bfs))},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": procs, "kind": "reference", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def cpu_baseline_sample(args, plan, log):
+    """One bounded sample of the reference on all host cores (rank 0, N = 1)."""
+    from oracle import pyoracle as po
+    from oracle import refpool
     if not po.have_ref():
         return None
-    a = po.RefMap(plan.walls, plan.spacing)
-    for s in plan.seeds:
-        a.fill(*s)
-    n = a.n
-    out = {"n": n, "kind": "reference"}
-    if full_makegraph:
-        t = a.makegraph()
-        out["mk_s_per_cell"] = t / n
-        out["mk_sample"] = f"full sparkGraph2 over all {n} cells ({t:.2f} s)"
-        b = a
-    else:
-        src = sample_sources(n, k_mk, 2)
-        t, edges = a.sample_makegraph(src)
-        out["mk_s_per_cell"] = t / len(src)
-        out["mk_sample"] = f"{len(src)} sampled sources through sparkPixel2(make=1) ({t:.2f} s)"
-        b = po.RefMap(plan.walls, plan.spacing)
-        for s in plan.seeds:
-            b.fill(*s)
-        b.makegraph()
-    src = sample_sources(n, k_bfs, 1)
-    t, tn, td = b.sample_global(src, radius)
-    out["bfs_s_per_cell"] = t / len(src)
-    out["bfs_sample"] = f"{len(src)} sampled sources, per-source body of VGAVisualGlobal::run around the reference's extractUnseen ({t:.2f} s)"
-    out["map"] = b
-    return out
+    procs = os.cpu_count() or 1
+    pool = refpool.RefPool(plan, procs, log=log)
+    n = pool.n
+    src = sorted(random.Random(1).sample(range(n), min(procs * args.cpu_sources_per_core, n)))
+    wall, mk_sum, bfs_sum, mk_max, bfs_max = pool.step(src, args.radius)
+    pool.close()
+    return {"value": len(src) / wall, "unit": UNIT, "cores": procs, "kind": "reference",
+            "sample": f"{len(src)} sampled sources on {procs} processes ({wall:.1f} s wall): sparkPixel2(make=1) "
+                      f"({mk_sum / len(src) * 1e3:.2f} ms per source) + per-source body of VGAVisualGlobal::run around the "
+                      f"reference's extractUnseen ({bfs_sum / len(src):.3f} s per source) on the complete reference graph",
+            "makegraph_cells_per_s_per_core": len(src) / mk_sum if mk_sum > 0 else None,
+            "global_bfs_cells_per_s_per_core": len(src) / bfs_sum if bfs_sum > 0 else None,
+            "host_cores_available": os.cpu_count()}
 
+
+# ------------------------------------------------------------------------------------------------ our arm (GPU)
 
 def main():
     ap = argparse.ArgumentParser()
@@ -139,14 +189,17 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", help="C1..C5 or kind:W:H:seed (default C2, BASELINE.json configs[1])")
+    ap.add_argument("--workload", default="C5", help="C1..C5 or kind:W:H:seed (default C5, BASELINE.json configs[4])")
     ap.add_argument("--radius", type=int, default=-1)
-    ap.add_argument("--vga-local", dest="local", action="store_true", help="also run VGA local in the step (not part of the headline metric)")
+    ap.add_argument("--bfs-stride", type=int, default=0,
+                    help="BFS sources = every stride-th group of 512 sources of the batch order (0 = 4 for C5, 1 otherwise)")
+    ap.add_argument("--local-cells", type=int, default=4096,
+                    help="VGA local on this many cells per step, reported separately (0 = off; 1 GPU only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (big workloads run by hand)")
-    ap.add_argument("--cpu-bfs-sources", type=int, default=48)
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm")
+    ap.add_argument("--cpu-sources-per-core", type=int, default=1)
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
-                    help="vga_ctx_set_option for our arm (e.g. --opt bfs_pull=1): A/B runs of opt-in kernels; recorded in config")
+                    help="vga_ctx_set_option for our arm (e.g. --opt bfs_words=4): A/B runs; recorded in config")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -155,55 +208,20 @@ def main():
 
     from depthmapx_b200 import plans
     plan = plans.by_name(args.workload)
-    workload_desc = {"workload": f"{args.workload}: {plan.name} synthetic plan, spacing {plan.spacing}, "
-                                 f"makegraph + VGA visibility global radius {'n' if args.radius == -1 else args.radius}",
-                     "walls": len(plan.walls)}
 
-    # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return 0
-        from oracle import pyoracle as po
-        if not po.have_ref():
-            po.build(ref=True)
-        k = 24
-        a = po.RefMap(plan.walls, plan.spacing)
-        for s in plan.seeds:
-            a.fill(*s)
-        n = a.n
-        b = po.RefMap(plan.walls, plan.spacing)
-        for s in plan.seeds:
-            b.fill(*s)
-        b.makegraph()  # untimed set-up: the BFS sample needs every Node
-        times = []
-        for it in range(args.warmup + args.steps):
-            src = sample_sources(n, k, 100 + it)
-            t1, _ = a.sample_makegraph(src)
-            t2, _, _ = b.sample_global(src, args.radius)
-            if it >= args.warmup:
-                times.append(t1 + t2)
-        ms = 1e3 * sum(times) / len(times)
-        val = k / (ms / 1e3)
-        sample = (f"each step = {k} sampled sources of the same plan through the reference's sparkPixel2(make=1) "
-                  f"and the per-source body of VGAVisualGlobal::run (extractUnseen); N={n}")
-        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f64+u64", "data": "synthetic",
-                "config": dict(workload_desc, cells=n),
-                "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample},
-                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
-        return 0
+        return reference_arm(args, plan)
 
-    # ------------------------------------------------------------------ our arm (GPU)
     import torch
     from depthmapx_b200 import capi, multi
     if capi.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device -- libvga_b200 has no CPU path")
     dist = None
+    saved_stdout = None
     if world > 1:
-        # NCCL prints a version banner on stdout: point fd 1 at stderr while the job runs and give it back
-        # for the one JSON line
+        # NCCL prints a version banner on stdout: point fd 1 at stderr while the job runs and give it back for the one JSON line
         sys.stdout.flush()
         saved_stdout = os.dup(1)
         os.dup2(2, 1)
@@ -213,100 +231,139 @@ def main():
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
 
+    def log(*a):
+        if rank == 0:
+            print("[bench]", *a, file=sys.stderr, flush=True)
+
+    t_setup = time.time()
     flat = capi.prepare(plan)  # host pre-steps (setGrid, blockLines, fill): not part of the hot path
     ctx = capi.Context(local_rank)
     for kv in args.opt:
         key, value = kv.split("=")
         ctx.set_option(key, int(value))
-    if args.opt:
-        workload_desc["options"] = dict(kv.split("=") for kv in args.opt)
     dgrid = ctx.upload(flat)
     n = flat.n_filled
-    lo, hi = multi.partition(n, world)[rank]
+    # makegraph shards: contiguous source ranges balanced by estimated work (open area), SURVEY.md 8e
+    if world > 1:
+        parts = multi.partition_by_work(multi.estimate_source_work(flat.state, flat.cols, flat.rows), world)
+    else:
+        parts = [(0, n)]
+    lo, hi = parts[rank]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > L2 (126 MB)
+    log(f"{args.workload}: N={n}, host pre-steps {time.time() - t_setup:.1f} s")
 
     def barrier():
         if dist is not None:
             dist.barrier()
-        torch.cuda.synchronize(dev)
         ctx.sync()
+        torch.cuda.synchronize(dev)
 
-    def step(grid_obj, stats):
+    def replicate(g, st):
+        """N > 1: the run-length rows of every rank's shard, broadcast straight into the library's final allocation."""
+        rp_ptr, runs_ptr, nr = g.device_runs()
+        deg_ptr = g.device_degrees()
+        rows = hi - lo
+        sizes = multi.exchange_sizes(rows, nr, dist, world, dev)
+        total_runs = sum(s[1] for s in sizes)
+        full, f_rp, f_runs, f_deg = ctx.graph_runs_alloc(n, g.ghosts, total_runs)
+        out = (multi.wrap(f_rp, (n + 1) * 8, torch.int64, dev), multi.wrap(f_runs, max(total_runs, 1) * 8, torch.int64, dev),
+               multi.wrap(f_deg, max(n, 1) * 4, torch.int32, dev))
+        multi.allgather_runs(multi.wrap(rp_ptr, (rows + 1) * 8, torch.int64, dev),
+                             multi.wrap(runs_ptr, max(nr, 1) * 8, torch.int64, dev),
+                             multi.wrap(deg_ptr, max(rows, 1) * 4, torch.int32, dev), sizes, dist, rank, world, out=out)
+        torch.cuda.synchronize(dev)
+        full.runs_commit()
+        full.set_cell_refs(g.cell_refs())  # coordinates -> spatially coherent BFS batches
+        st["exchange_bytes"] = int(total_runs) * 8 + (n + 1) * 8 + n * 4
+        return full
+
+    # ---- the fixed BFS source subset (set-up, untimed): whole groups of the library's batch order, evenly spread
+    stride = args.bfs_stride if args.bfs_stride > 0 else default_stride(args.workload)
+    g0 = ctx.build(dgrid, (lo, hi))
+    full0 = replicate(g0, {}) if world > 1 else g0
+    order = full0.batch_order()
+    edges_total = g0.entries
+    if world > 1:
+        full0.free()
+    g0.free()
+    ngroups = (n + GROUP - 1) // GROUP
+    picked = [gi for gi in range(ngroups) if gi % stride == 0]
+    my_groups = picked[(len(picked) * rank) // world:(len(picked) * (rank + 1)) // world]
+    my_sources = np.concatenate([order[gi * GROUP:(gi + 1) * GROUP] for gi in my_groups]).astype(np.int64) if my_groups \
+        else np.zeros(0, np.int64)
+    counts = []
+    for r in range(world):
+        gs = picked[(len(picked) * r) // world:(len(picked) * (r + 1)) // world]
+        counts.append(int(sum(min(GROUP, n - gi * GROUP) for gi in gs)))
+    S = int(sum(counts))
+    local_cells = args.local_cells if world == 1 else 0
+    local_range = (max(0, n // 2 - local_cells // 2), min(n, max(0, n // 2 - local_cells // 2) + local_cells))
+    log(f"BFS subset: {S} of {n} sources ({len(picked)} groups of {GROUP}, stride {stride}); set-up {time.time() - t_setup:.1f} s")
+
+    def step(grid_obj, st):
         """one pass of the hot path; grid_obj is a DeviceGrid (resident) or a FlatGrid (host buffers)"""
         t0 = time.perf_counter()
         g = ctx.build(grid_obj, (lo, hi))
         tb = ctx.timing()
         t1 = time.perf_counter()
-        full = g
-        if world > 1:
-            rp_ptr, adj_ptr, ne = g.device_rows()
-            rows = hi - lo
-            rp_local = multi.wrap(rp_ptr, (rows + 1) * 8, torch.int64, dev)
-            adj_local = multi.wrap(adj_ptr, ne * 4, torch.int32, dev)[:ne]
-            rp_full, adj_full, base = multi.allgather_rows(rp_local, adj_local, dist, world)
-            torch.cuda.synchronize(dev)
-            full = ctx.graph_from_device_rows(n, g.ghosts, rp_full.data_ptr(), adj_full.data_ptr(), base)
-            full.set_cell_refs(g.cell_refs())  # coordinates -> spatially coherent BFS batches
-            del rp_full, adj_full, rp_local, adj_local
-            if base * 4 > (4 << 30):
-                torch.cuda.empty_cache()  # the library holds its own copy now; give multi-GB staging buffers back
-            stats["gather_bytes"] = int(base) * 4
+        full = replicate(g, st) if world > 1 else g
         t2 = time.perf_counter()
-        tn, td, hist, used = full.global_ints(args.radius, (lo, hi))
+        tn, td, hist, used = full.global_ints(args.radius, sources=my_sources)
         tg = ctx.timing()
         t3 = time.perf_counter()
-        local_ms = 0.0
-        if args.local:
-            tl0 = time.perf_counter()
-            full.local_ints((lo, hi))
-            local_ms = (time.perf_counter() - tl0) * 1e3
+        tl = None
+        if local_cells > 0:
+            full.local_ints(local_range)
+            tl = ctx.timing()
+        t4 = time.perf_counter()
         if world > 1:
-            # result gather to rank 0: tn, td, level histogram (padded to 64 levels)
-            L = 64
-            pack = np.zeros((hi - lo, L + 2), np.int64)
-            pack[:, 0] = tn
-            pack[:, 1] = td
-            pack[:, 2:2 + min(L, hist.shape[1])] = hist[:, :L]
-            mine = torch.from_numpy(pack).to(dev)
-            cnts = [e - s for s, e in multi.partition(n, world)]
-            res = multi.gather_results(mine, cnts, dist, rank, world)
+            # result gather to rank 0: source ordinal, tn, td, level histogram (padded to 62 levels)
+            L = 62
+            pack = np.zeros((len(my_sources), L + 3), np.int64)
+            pack[:, 0] = my_sources
+            pack[:, 1] = tn
+            pack[:, 2] = td
+            pack[:, 3:3 + min(L, hist.shape[1])] = hist[:, :L]
+            res = multi.gather_results(torch.from_numpy(pack).to(dev), counts, dist, rank, world)
             torch.cuda.synchronize(dev)
             if rank == 0:
-                stats["_gathered"] = res  # checksum is computed outside the timed region
+                st["_res"] = res  # the checksum is computed outside the timed region
             full.free()
         else:
-            stats["_local"] = (tn, td, hist)
+            st["_local"] = (tn, td, hist)
+        edges = g.entries
         g.free()
-        t4 = time.perf_counter()
-        stats.update(build_ms=(t1 - t0) * 1e3, gather_ms=(t2 - t1) * 1e3, bfs_ms=(t3 - t2) * 1e3, total_ms=(t4 - t0) * 1e3,
-                     build_timing=tb, bfs_timing=tg, edges=g.entries, levels=used, local_ms=local_ms,
-                     d2h_bytes=tn.nbytes + td.nbytes + hist.nbytes)
-        return tn, td, hist
+        t5 = time.perf_counter()
+        st.update(build_ms=(t1 - t0) * 1e3, exchange_ms=(t2 - t1) * 1e3, bfs_ms=(t3 - t2) * 1e3, local_ms=(t4 - t3) * 1e3,
+                  tail_ms=(t5 - t4) * 1e3, build_timing=tb, bfs_timing=tg, local_timing=tl, edges=edges, levels=used,
+                  d2h_bytes=tn.nbytes + td.nbytes + hist.nbytes)
 
-    def timed(grid_obj, steps, warmup):
+    def timed(grid_obj, steps, warmup, tag):
         per, acc = [], []
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
         for it in range(warmup + steps):
             flush.fill_(it & 0xff)  # evict L2 between iterations
             barrier()
             st = {}
-            t0 = time.perf_counter()
+            ev0.record()
             step(grid_obj, st)
             barrier()
-            dt = (time.perf_counter() - t0) * 1e3
-            if os.environ.get("VGA_BENCH_DEBUG"):
-                print(f"[rank {rank}] it={it} total={dt:.1f} build={st['build_ms']:.1f} gather={st['gather_ms']:.1f} "
-                      f"bfs={st['bfs_ms']:.1f} (kernels {st['bfs_timing']['kernel_ms']:.1f}, level kernels "
-                      f"{st['bfs_timing']['main_kernel_ms']:.1f}) tail={st['total_ms'] - st['build_ms'] - st['gather_ms'] - st['bfs_ms']:.1f}",
-                      file=sys.stderr, flush=True)
-            # result checksum of this iteration (untimed); only scalars are kept
-            if "_gathered" in st:
-                r = st.pop("_gathered").cpu().numpy()
-                st["checksum"] = {"sum_nodes": int(r[:, 0].sum()), "sum_depth": int(r[:, 1].sum()),
-                                  "sum_hist_weighted": int((r[:, 2:] * (np.arange(r.shape[1] - 2) + 1)[None, :]).sum())}
+            ev1.record()
+            ev1.synchronize()
+            dt = ev0.elapsed_time(ev1)  # device idle at both marks: the span of the step on the device's clock
+            if "_res" in st:
+                r = st.pop("_res").cpu().numpy()
+                st["checksum"] = {"sources": int(r.shape[0]), "sum_nodes": int(r[:, 1].sum()), "sum_depth": int(r[:, 2].sum()),
+                                  "sum_hist_weighted": int((r[:, 3:] * (np.arange(r.shape[1] - 3) + 1)[None, :]).sum())}
             elif "_local" in st:
                 tn_, td_, h_ = st.pop("_local")
-                st["checksum"] = {"sum_nodes": int(tn_.astype(np.int64).sum()), "sum_depth": int(td_.sum()),
+                st["checksum"] = {"sources": int(len(tn_)), "sum_nodes": int(tn_.astype(np.int64).sum()), "sum_depth": int(td_.sum()),
                                   "sum_hist_weighted": int((h_.astype(np.int64) * (np.arange(h_.shape[1]) + 1)[None, :]).sum())}
+            if os.environ.get("VGA_BENCH_DEBUG"):
+                print(f"[rank {rank}] {tag} it={it} step={dt:.1f} build={st['build_ms']:.1f} exchange={st['exchange_ms']:.1f} "
+                      f"bfs={st['bfs_ms']:.1f} (prep {st['bfs_timing']['prep_ms']:.1f}, level kernels "
+                      f"{st['bfs_timing']['main_kernel_ms']:.1f}) local={st['local_ms']:.1f}", file=sys.stderr, flush=True)
             if it >= warmup:
                 per.append(dt)
                 acc.append(st)
@@ -315,10 +372,8 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    # the contract's >= 3 warm-ups hold for the default workload; the minutes-long big workloads (C4/C5,
-    # run by hand with --workload) may use fewer and can skip the host-buffer arm
-    warm = max(args.warmup, 3) if args.workload == "C2" else args.warmup
-    per_res, st_res = timed(dgrid, args.steps, warm)
+    warm = max(args.warmup, 3)  # the contract's minimum
+    per_res, st_res = timed(dgrid, args.steps, warm, "resident")
     pinned_inputs = False
     if args.no_e2e:
         per_e2e, st_e2e = per_res, st_res
@@ -335,91 +390,132 @@ def main():
             pinned_inputs = all(t.is_pinned() for t in keep)
         except Exception:
             flat_e2e = flat
-        per_e2e, st_e2e = timed(flat_e2e, max(2, min(args.steps, 3)) if args.workload == "C2" else 1, 1 if args.workload == "C2" else 0)
+        per_e2e, st_e2e = timed(flat_e2e, args.steps, warm, "host-buffers")
     clocks = sampler.finish() if sampler else None
 
-    def reduce_max(x):
+    def reduce(x, op):
         if dist is None:
-            return x
+            return float(x)
         t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def reduce_sum(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    def rmax(x):
+        return reduce(x, dist.ReduceOp.MAX if dist else None)
 
-    ms_res = reduce_max(sum(per_res) / len(per_res))
-    ms_e2e = reduce_max(sum(per_e2e) / len(per_e2e))
-    build_ms = reduce_max(float(np.mean([s["build_ms"] for s in st_res])))
-    bfs_ms = reduce_max(float(np.mean([s["bfs_ms"] for s in st_res])))
-    gather_ms = reduce_max(float(np.mean([s["gather_ms"] for s in st_res])))
-    # dominant kernel group: BFS level kernels (CUDA events inside the library, on its stream)
-    bfs_main_ms = reduce_max(float(np.mean([s["bfs_timing"]["main_kernel_ms"] for s in st_res])))
-    bfs_algo = reduce_sum(float(np.mean([s["bfs_timing"]["algo_bytes"] for s in st_res])))
-    bfs_algo_runs = reduce_sum(float(np.mean([s["bfs_timing"].get("algo_bytes_runs", 0.0) for s in st_res])))
-    sieve_main_ms = reduce_max(float(np.mean([s["build_timing"]["main_kernel_ms"] for s in st_res])))
-    launches = reduce_sum(float(np.sum([s["build_timing"]["launches"] + s["bfs_timing"]["launches"] for s in st_res])))
-    main_launches = float(np.mean([s["bfs_timing"]["main_launches"] for s in st_res]))
-    edges = reduce_sum(float(st_res[0]["edges"]))
-    # every collective must happen BEFORE the non-zero ranks leave (a lone all_reduce on rank 0 would
-    # block until the NCCL watchdog aborts the process)
-    local_ms = reduce_max(float(np.mean([s["local_ms"] for s in st_res]))) if args.local else None
+    def rsum(x):
+        return reduce(x, dist.ReduceOp.SUM if dist else None)
+
+    def med(sts, f):
+        return float(np.median([f(s) for s in sts]))
+
+    def summarize(per, sts):
+        """medians over the timed steps, max over ranks (every collective happens on every rank)"""
+        o = {}
+        o["step_ms"] = rmax(float(np.median(per)))
+        o["step_min"] = rmax(min(per))
+        o["step_max"] = rmax(max(per))
+        o["build_ms"] = rmax(med(sts, lambda s: s["build_ms"]))
+        o["exchange_ms"] = rmax(med(sts, lambda s: s["exchange_ms"]))
+        o["bfs_ms"] = rmax(med(sts, lambda s: s["bfs_ms"]))
+        o["prep_ms"] = rmax(med(sts, lambda s: s["bfs_timing"]["prep_ms"]))
+        o["local_ms"] = rmax(med(sts, lambda s: s["local_ms"]))
+        o["bfs_main_ms"] = rmax(med(sts, lambda s: s["bfs_timing"]["main_kernel_ms"]))
+        o["sieve_main_ms"] = rmax(med(sts, lambda s: s["build_timing"]["main_kernel_ms"]))
+        o["build_kernel_ms"] = rmax(med(sts, lambda s: s["build_timing"]["kernel_ms"]))
+        o["h2d_ms"] = rmax(med(sts, lambda s: s["build_timing"]["h2d_ms"]))
+        o["d2h_ms"] = rmax(med(sts, lambda s: s["bfs_timing"]["d2h_ms"]))
+        o["algo"] = rsum(med(sts, lambda s: s["bfs_timing"]["algo_bytes"]))
+        o["algo_csr"] = rsum(med(sts, lambda s: s["bfs_timing"]["algo_bytes_csr"]))
+        o["launches"] = rsum(float(np.sum([s["build_timing"]["launches"] + s["bfs_timing"]["launches"] +
+                                           (s["local_timing"]["launches"] if s["local_timing"] else 0) for s in sts])))
+        o["main_launches"] = med(sts, lambda s: s["bfs_timing"]["main_launches"])
+        o["edges"] = rsum(float(sts[0]["edges"]))
+        o["d2h_bytes"] = rsum(float(sts[0]["d2h_bytes"]))
+        o["stage_ranges"] = {k: stats([s[k] for s in sts]) for k in ("build_ms", "exchange_ms", "bfs_ms", "local_ms")}
+        o["stage_ranges"]["step_ms"] = stats(per)
+        return o
+
+    R = summarize(per_res, st_res)
+    E = R if args.no_e2e else summarize(per_e2e, st_e2e)
     peak, peak_src = load_peaks()
-    achieved = bfs_algo / (bfs_main_ms * 1e-3) / 1e9 / world  # per GPU
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return 0
 
+    def cells_per_s(o):
+        t_graph = o["build_ms"] + o["exchange_ms"] + o["prep_ms"]
+        t_bfs = max(o["bfs_ms"] - o["prep_ms"], 1e-9)
+        per_cell_ms = t_graph / n + t_bfs / max(S, 1)
+        return 1e3 / per_cell_ms, t_graph + t_bfs * n / max(S, 1)
+
+    val, full_ms = cells_per_s(R)
+    val_e2e, full_ms_e2e = cells_per_s(E)
+    achieved = R["algo"] / (R["bfs_main_ms"] * 1e-3) / 1e9 / world  # per GPU
+    achieved_csr = R["algo_csr"] / (R["bfs_main_ms"] * 1e-3) / 1e9 / world
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r2_bfs_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            rec = tj.get(args.workload)
+            if rec and world == 1:
+                # measured dram bytes per source of the level kernels (ncu --set full capture) x the sources of one step
+                traffic = float(rec["dram_bytes_per_source"]) * S
+        except Exception:
+            traffic = None
+    cfg = dict(workload_config(args, plan), cells=n, edges=int(edges_total) if world == 1 else int(R["edges"]),
+               bfs_sources=S, bfs_source_stride=stride,
+               bfs_subset=f"every {stride}th group of {GROUP} sources of the library's spatial batch order (fixed, same for every N)",
+               value_definition="1 / (t_graph/N + t_bfs/S): t_graph = makegraph + exchange + BFS row lists, t_bfs = BFS over the S sources; medians",
+               levels=int(st_res[0]["levels"]), l2="flushed between iterations (256 MB write)",
+               parallelism=f"makegraph rows and BFS sources sharded x{world}; graph replicated as run-length rows")
+    if args.opt:
+        cfg["options"] = dict(kv.split("=") for kv in args.opt)
     line = {
-        "metric": METRIC, "value": n / (ms_res * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": warm, "ms_per_step": ms_res, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64 (sieve) + u64 bit-masks (BFS)", "data": "synthetic",
-        "config": dict(workload_desc, cells=n, edges=int(edges), levels=int(st_res[0]["levels"]),
-                       l2="flushed between iterations (256 MB write)", parallelism=f"source-sharded x{world}"),
-        "stages": {"makegraph_ms": build_ms, "makegraph_cells_per_s": n / (build_ms * 1e-3),
-                   "makegraph_edges_per_s": edges / (build_ms * 1e-3), "global_bfs_ms": bfs_ms,
-                   "global_bfs_cells_per_s": n / (bfs_ms * 1e-3), "allgather_ms": gather_ms,
-                   "sieve_kernels_ms": sieve_main_ms, "bfs_level_kernels_ms": bfs_main_ms,
-                   "local_ms": local_ms},
-        "e2e": {"value": n / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(flat.input_bytes()), "d2h_bytes_per_step": int(st_e2e[0]["d2h_bytes"]),
-                "makegraph_ms": float(np.mean([s["build_ms"] for s in st_e2e])),
-                "global_bfs_ms": float(np.mean([s["bfs_ms"] for s in st_e2e])),
-                "h2d_ms": float(np.mean([s["build_timing"]["h2d_ms"] for s in st_e2e])),
-                "d2h_ms": float(np.mean([s["bfs_timing"]["d2h_ms"] for s in st_e2e])),
-                "note": "vga_graph_build(host vga_grid) + vga_global(host outputs); inputs in "
+        "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": R["step_ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64 (sieve) + u64 bit-masks (BFS)", "data": "synthetic", "config": cfg,
+        "full_job_ms_extrapolated": full_ms,
+        "stages": {"makegraph_ms": R["build_ms"], "makegraph_cells_per_s": n / (R["build_ms"] * 1e-3),
+                   "makegraph_edges_per_s": (edges_total if world == 1 else R["edges"]) / (R["build_ms"] * 1e-3),
+                   "exchange_ms": R["exchange_ms"], "bfs_row_lists_ms": R["prep_ms"],
+                   "global_bfs_ms": R["bfs_ms"], "global_bfs_cells_per_s": S / (max(R["bfs_ms"] - R["prep_ms"], 1e-9) * 1e-3),
+                   "sieve_kernels_ms": R["sieve_main_ms"], "makegraph_kernels_ms": R["build_kernel_ms"],
+                   "bfs_level_kernels_ms": R["bfs_main_ms"],
+                   "local_ms": R["local_ms"] if local_cells > 0 else None,
+                   "local_cells": (local_range[1] - local_range[0]) if local_cells > 0 else 0,
+                   "local_cells_per_s": ((local_range[1] - local_range[0]) / (R["local_ms"] * 1e-3)) if local_cells > 0 and R["local_ms"] > 0 else None,
+                   "ranges": R["stage_ranges"]},
+        "e2e": {"value": val_e2e, "unit": UNIT, "ms_per_step": E["step_ms"], "full_job_ms_extrapolated": full_ms_e2e,
+                "h2d_bytes_per_step": int(flat.input_bytes()), "d2h_bytes_per_step": int(E["d2h_bytes"]),
+                "makegraph_ms": E["build_ms"], "exchange_ms": E["exchange_ms"], "global_bfs_ms": E["bfs_ms"],
+                "h2d_ms": E["h2d_ms"], "d2h_ms": E["d2h_ms"], "ranges": E["stage_ranges"],
+                "note": "vga_graph_build(host vga_grid) + vga_global_sources(host outputs); inputs in "
                         + ("pinned" if pinned_inputs else "pageable") + " host memory"},
-        "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "BFS level kernels k_push/k_pull/k_update/k_decide",
+        "gpu_launches": int(R["launches"]),
+        "roofline": {"bound": "hbm", "kernel": "BFS level kernels k_push_nodes/k_pyr_down/k_pyr_build/k_pull_nodes/k_update/k_decide",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "peak_source": peak_src, "traffic": None,
-                     "algorithmic_bytes_per_step": bfs_algo, "kernel_ms_per_step": bfs_main_ms,
-                     # with run-length rows (--opt bfs_push=1): the same model at 8 bytes per run instead of 4 per entry
-                     "algorithmic_bytes_per_step_run_length": bfs_algo_runs if bfs_algo_runs > 0 else None,
-                     "launches_per_step": main_launches},
+                     "peak_source": peak_src, "traffic": traffic,
+                     "byte_model": "rows as pyramid node lists (4 B per node id of the expanding vertices) + frontier / visited / next vectors",
+                     "algorithmic_bytes_per_step": R["algo"], "kernel_ms_per_step": R["bfs_main_ms"],
+                     "csr_model": {"algorithmic_bytes_per_step": R["algo_csr"], "achieved": achieved_csr, "frac": achieved_csr / peak,
+                                   "note": "SURVEY.md 8d as written (4-byte CSR entries): what round 1's kernels streamed; kept for comparison"},
+                     "launches_per_step": R["main_launches"]},
         "clocks": clocks,
-        # size-independent result check: equal for every N on the same workload (sums over all sources of
+        # size-independent result check: equal for every N on the same workload (sums over the subset's sources of
         # Node Count, total depth and the level histogram weighted by level+1)
         "result_checksum": st_res[-1].get("checksum"),
     }
     if world == 1 and not args.no_cpu_baseline:
         try:
-            ref = reference_sample(plan, 256, args.cpu_bfs_sources, args.radius, full_makegraph=(edges < 1.5e8))
+            ref = cpu_baseline_sample(args, plan, log)
         except Exception as e:  # the checker library is optional on the GPU box
             ref = None
-            line["cpu_baseline_error"] = str(e)
+            line["cpu_baseline_error"] = repr(e)
         if ref:
-            per_cell = ref["mk_s_per_cell"] + ref["bfs_s_per_cell"]
-            line["cpu_baseline"] = {"value": 1.0 / per_cell, "unit": UNIT, "cores": 1, "kind": "reference",
-                                    "sample": f"makegraph: {ref['mk_sample']}; global: {ref['bfs_sample']}",
-                                    "makegraph_cells_per_s": 1.0 / ref["mk_s_per_cell"],
-                                    "global_bfs_cells_per_s": 1.0 / ref["bfs_s_per_cell"],
-                                    "host_cores_available": os.cpu_count()}
+            line["cpu_baseline"] = ref
     if dist is not None:
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)

@@ -491,52 +491,47 @@ __global__ void k_neighbour_bits(int64_t n, const uint64_t *runptr, const uint2 
 }
 
 // ---- run-length rows from SORTED entry rows: one warp per vertex ----------------------------------------------------
-// entry e of row v holds ordinal arr[e] >> shift; ordinals >= limit (ghost columns, which sort last) are not part of
-// any run.  A run starts at a valid entry that is the first of the row or does not continue the previous ordinal.
-__global__ void k_count_runs(const uint64_t *rowptr, const uint32_t *arr, int shift, uint32_t limit, int64_t n, u64 *count,
-                             uint32_t *nvalid) {
+// entry e of row v holds ordinal arr[e] >> shift.  A run starts at an entry that is the first of the row, does not
+// continue the previous ordinal, or is the first ghost column (ordinal == brk = number of filled cells): runs never
+// straddle the filled / ghost boundary, and the ghost runs (first >= brk) are the tail of every row.  The BFS skips
+// them (ghosts are never counted or expanded), the local measures need them.
+__global__ void k_count_runs(const uint64_t *rowptr, const uint32_t *arr, int shift, uint32_t brk, int64_t n, u64 *count) {
     const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (v >= n) return;
     const uint64_t e0 = rowptr[v], e1 = rowptr[v + 1];
-    unsigned c = 0, nv = 0;
+    unsigned c = 0;
     for (uint64_t e = e0 + lane; e < e1; e += 32) {
         const uint32_t x = arr[e] >> shift;
-        if (x >= limit) continue;
-        nv++;
-        c += (e == e0 || x != (arr[e - 1] >> shift) + 1u) ? 1u : 0u;
+        c += (e == e0 || x != (arr[e - 1] >> shift) + 1u || x == brk) ? 1u : 0u;
     }
     c = __reduce_add_sync(FULL, c);
-    nv = __reduce_add_sync(FULL, nv);
-    if (lane == 0) {
-        count[v] = c;
-        nvalid[v] = nv;
-    }
+    if (lane == 0) count[v] = c;
 }
 // first_off[r] = offset (within its row) of the entry that starts run r
-__global__ void k_mark_runs(const uint64_t *rowptr, const uint32_t *arr, int shift, const uint32_t *nvalid, int64_t n,
+__global__ void k_mark_runs(const uint64_t *rowptr, const uint32_t *arr, int shift, uint32_t brk, int64_t n,
                             const uint64_t *runptr, uint32_t *first_off) {
     const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (v >= n) return;
-    const uint64_t e0 = rowptr[v], e1 = e0 + nvalid[v];
+    const uint64_t e0 = rowptr[v], e1 = rowptr[v + 1];
     uint64_t out = runptr[v];
     for (uint64_t eb = e0; eb < e1; eb += 32) {
         const uint64_t e = eb + lane;
-        const bool start = e < e1 && (e == e0 || (arr[e] >> shift) != (arr[e - 1] >> shift) + 1u);
+        const bool start = e < e1 && (e == e0 || (arr[e] >> shift) != (arr[e - 1] >> shift) + 1u || (arr[e] >> shift) == brk);
         const unsigned mask = __ballot_sync(FULL, start);
         if (start) first_off[out + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)(e - e0);
         out += __popc(mask);
     }
 }
 // runs[r] = (first ordinal, length)
-__global__ void k_emit_runs(const uint64_t *rowptr, const uint32_t *arr, int shift, const uint32_t *nvalid, int64_t n,
+__global__ void k_emit_runs(const uint64_t *rowptr, const uint32_t *arr, int shift, int64_t n,
                             const uint64_t *runptr, const uint32_t *first_off, uint2 *runs) {
     const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (v >= n) return;
     const uint64_t e0 = rowptr[v];
-    const uint32_t nv = nvalid[v];
+    const uint32_t nv = (uint32_t)(rowptr[v + 1] - e0);
     const uint64_t r0 = runptr[v], r1 = runptr[v + 1];
     for (uint64_t r = r0 + lane; r < r1; r += 32) {
         const uint32_t off = first_off[r];
@@ -582,6 +577,7 @@ __global__ void k_trans_events(int64_t n, const uint64_t *runptr, const uint2 *r
     const uint64_t q0 = r1, q1 = u + 1 < n ? runptr[u + 2] : r1;      // row u+1 (empty for the last row)
     for (uint64_t r = r0 + lane; r < r1; r += 32) {
         const uint2 run = runs[r];
+        if (run.x >= (uint32_t)n) continue;  // ghost columns have no in-row
         if (MODE == 0) {
             uncovered_columns(runs, p0, p1, run.x, run.x + run.y, [&](uint32_t v) { atomicAdd(&count[v], 1ULL); });
         } else {
@@ -611,15 +607,16 @@ __global__ void k_trans_pair(int64_t n, const uint64_t *t_runptr, const uint32_t
 }
 
 // ---- node-id lists from runs -------------------------------------------------------------------------------------------
-__global__ void k_run_costs(const uint2 *runs, int64_t nruns, u64 *cost) {
+__global__ void k_run_costs(const uint2 *runs, int64_t nruns, uint32_t n, u64 *cost) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < nruns) cost[r] = (u64)pyr_cost(runs[r].x, runs[r].y);
+    if (r < nruns) cost[r] = runs[r].x < n ? (u64)pyr_cost(runs[r].x, runs[r].y) : 0ULL;  // ghost runs: no nodes
 }
 // ids of the nodes of every run, written at the run's offset (exclusive scan of the per-run node counts)
 __global__ void k_emit_nodes(const uint2 *runs, int64_t nruns, const u64 *node_off, uint32_t n, BfsDev d, uint32_t *out) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nruns) return;
     const uint2 run = runs[r];
+    if (run.x >= n) return;
     uint64_t o = node_off[r];
     pyr_decompose(run.x, run.y, [&](int k, uint32_t i) { out[o++] = k == 0 ? i : n + (uint32_t)d.pyr_off[k] + i; });
 }
@@ -1038,17 +1035,16 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources,
     return VGA_OK;
 }
 
-// Run-length form of sorted rows: one run per maximal stretch of consecutive ordinals (ghost columns excluded).
-int build_runs(vga_ctx *ctx, int64_t n /*rows*/, uint32_t limit /*columns*/, const uint64_t *rowptr, const uint32_t *arr, int shift,
+// Run-length form of sorted rows: one run per maximal stretch of consecutive ordinals (broken at the first ghost column).
+int build_runs(vga_ctx *ctx, int64_t n /*rows*/, uint32_t brk /*filled cells*/, const uint64_t *rowptr, const uint32_t *arr, int shift,
                DevBuf<uint64_t> &runptr, DevBuf<uint2> &runs, int64_t *nruns) {
     cudaStream_t st = ctx->stream;
     DevBuf<u64> count;
-    DevBuf<uint32_t> nvalid, first_off;
+    DevBuf<uint32_t> first_off;
     VGA_TRY(count.alloc_zero((size_t)n + 1, st));
-    VGA_TRY(nvalid.alloc_zero((size_t)n + 1, st));
     VGA_TRY(runptr.alloc((size_t)n + 1));
     if (n > 0) {
-        k_count_runs<<<blocks_for(n * 32, 256), 256, 0, st>>>(rowptr, arr, shift, limit, n, count.p, nvalid.p);
+        k_count_runs<<<blocks_for(n * 32, 256), 256, 0, st>>>(rowptr, arr, shift, brk, n, count.p);
         ctx->timing.launches++;
     }
     VGA_TRY(exclusive_sum_u64(ctx, count.p, (u64 *)runptr.p, n + 1));
@@ -1059,8 +1055,8 @@ int build_runs(vga_ctx *ctx, int64_t n /*rows*/, uint32_t limit /*columns*/, con
     VGA_TRY(first_off.alloc((size_t)total + 1));
     VGA_TRY(runs.alloc((size_t)total + 1));
     if (n > 0) {
-        k_mark_runs<<<blocks_for(n * 32, 256), 256, 0, st>>>(rowptr, arr, shift, nvalid.p, n, runptr.p, first_off.p);
-        k_emit_runs<<<blocks_for(n * 32, 256), 256, 0, st>>>(rowptr, arr, shift, nvalid.p, n, runptr.p, first_off.p, runs.p);
+        k_mark_runs<<<blocks_for(n * 32, 256), 256, 0, st>>>(rowptr, arr, shift, brk, n, runptr.p, first_off.p);
+        k_emit_runs<<<blocks_for(n * 32, 256), 256, 0, st>>>(rowptr, arr, shift, n, runptr.p, first_off.p, runs.p);
         ctx->timing.launches += 2;
     }
     VGA_CUDA(cudaStreamSynchronize(st));
@@ -1120,7 +1116,7 @@ int build_nodes(vga_ctx *ctx, int64_t n, const DevBuf<uint64_t> &runptr, const D
     VGA_TRY(off.alloc((size_t)nruns + 1));
     VGA_TRY(nodeptr.alloc((size_t)n + 1));
     if (nruns > 0) {
-        k_run_costs<<<blocks_for(nruns, 256), 256, 0, st>>>(runs.p, nruns, cost.p);
+        k_run_costs<<<blocks_for(nruns, 256), 256, 0, st>>>(runs.p, nruns, (uint32_t)n, cost.p);
         ctx->timing.launches++;
     }
     VGA_TRY(exclusive_sum_u64(ctx, cost.p, off.p, nruns + 1));

@@ -110,6 +110,139 @@ __global__ void k_control(int64_t n, const uint64_t *rowptr, const uint32_t *adj
     control[v - src_begin] = c;
 }
 
+// ---- run-length variant (default) ---------------------------------------------------------------------------------
+// The same per-cell bitmaps, fed by RUNS instead of entries: a neighbour row u is a short list of (first ordinal, length)
+// pairs (vga_graph::f_runs, ~35 cells per run on urban plans), |iter(N(u)) n N(v)| is a handful of masked popcounts on the
+// bitmap of N(v) and the union a handful of word ORs -- 10-100x fewer operations than one bit test per entry, and the
+// only form a rank of a multi-GPU run holds (vga_graph_from_device_runs).  The vertex universe is covered in `passes`
+// column ranges of `span` bits when two bitmaps of the whole universe exceed shared memory (two passes at 10^6 cells).
+struct LocalRunsDev {
+    int64_t n, universe;
+    const uint64_t *runptr;
+    const uint2 *runs;
+    int64_t src_begin, src_end;
+    u64 *work;  // [1] next cell
+    int passes;
+    uint32_t span;  // bits per pass (multiple of 32)
+    long long *cluster;
+    int32_t *k, *total;
+};
+
+// bits [a, b) of word w of a bitmap whose bit 0 is ordinal c0 (a, b already relative to c0)
+__device__ __forceinline__ uint32_t word_mask(uint32_t w, uint32_t a, uint32_t b) {
+    const uint32_t lo = w << 5, hi = lo + 32u;
+    uint32_t m = 0xffffffffu;
+    if (a > lo) m &= 0xffffffffu << (a - lo);
+    if (b < hi) m &= 0xffffffffu >> (hi - b);
+    return m;
+}
+
+__global__ void k_local_runs(LocalRunsDev d) {
+    extern __shared__ __align__(16) uint32_t sm[];
+    __shared__ long long s_v;
+    __shared__ unsigned long long s_cluster;
+    __shared__ int s_total, s_k;
+    const uint32_t words = d.span >> 5;
+    uint32_t *bmN = sm, *bmT = sm + words;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    while (true) {
+        if (threadIdx.x == 0) {
+            s_v = (long long)atomicAdd(d.work, 1ULL) + d.src_begin;
+            s_cluster = 0;
+            s_total = 0;
+            s_k = 0;
+        }
+        __syncthreads();
+        const int64_t v = s_v;
+        if (v >= d.src_end) break;
+        const uint64_t r0 = d.runptr[v], r1 = d.runptr[v + 1];
+        for (int pass = 0; pass < d.passes; pass++) {
+            const uint32_t c0 = (uint32_t)pass * d.span;
+            const uint32_t c1 = (uint32_t)min((int64_t)c0 + d.span, d.universe);
+            for (uint32_t i = threadIdx.x; i < 2 * words; i += blockDim.x) sm[i] = 0u;
+            __syncthreads();
+            // membership bitmap of N(v) for this column range; k = |N(v)| on the first pass
+            int myk = 0;
+            for (uint64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+                const uint2 run = d.runs[r];
+                if (pass == 0) myk += (int)run.y;
+                const uint32_t a = max(run.x, c0), b = min(run.x + run.y, c1);
+                if (a < b)
+                    for (uint32_t w = (a - c0) >> 5; w <= (b - 1 - c0) >> 5; w++) atomicOr(&bmN[w], word_mask(w, a - c0, b - c0));
+            }
+            if (pass == 0) {
+                myk = __reduce_add_sync(FULL, myk);
+                if (lane == 0 && myk) atomicAdd(&s_k, myk);
+            }
+            __syncthreads();
+            // every filled member u of N(v): one warp per member (member index m strided over the warps; the warp walks v's
+            // runs once to turn m into an ordinal), one lane per run of u
+            unsigned long long wcl = 0;
+            {
+                uint64_t r = r0;
+                uint32_t before = 0;  // members in the runs before r
+                uint2 vr = r < r1 ? d.runs[r] : make_uint2(0xffffffffu, 0u);
+                for (uint32_t m = warp;; m += nwarps) {
+                    while (r < r1 && m >= before + vr.y) {
+                        before += vr.y;
+                        r++;
+                        vr = r < r1 ? d.runs[r] : make_uint2(0xffffffffu, 0u);
+                    }
+                    if (r >= r1 || vr.x >= (uint32_t)d.n) break;  // past the last member / ghost members: not filled, no row
+                    const uint32_t u = vr.x + (m - before);
+                    const uint64_t q0 = d.runptr[u], q1 = d.runptr[u + 1];
+                    int cnt = 0;
+                    for (uint64_t q = q0 + lane; q < q1; q += 32) {
+                        const uint2 run = d.runs[q];
+                        const uint32_t a = max(run.x, c0), b = min(run.x + run.y, c1);
+                        if (a < b)
+                            for (uint32_t w = (a - c0) >> 5; w <= (b - 1 - c0) >> 5; w++) {
+                                const uint32_t mk = word_mask(w, a - c0, b - c0);
+                                cnt += __popc(bmN[w] & mk);
+                                if ((bmT[w] & mk) != mk) atomicOr(&bmT[w], mk);
+                            }
+                    }
+                    cnt = __reduce_add_sync(FULL, cnt);
+                    wcl += (unsigned long long)cnt;
+                }
+            }
+            if (lane == 0 && wcl) atomicAdd(&s_cluster, wcl);
+            __syncthreads();
+            int pc = 0;
+            for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) pc += __popc(bmT[i]);
+            pc = __reduce_add_sync(FULL, pc);
+            if (lane == 0 && pc) atomicAdd(&s_total, pc);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            const int64_t o = v - d.src_begin;
+            d.cluster[o] = (long long)s_cluster;
+            d.k[o] = s_k;
+            d.total[o] = s_total;
+        }
+        __syncthreads();
+    }
+}
+
+// control over runs: entries per row from the CSR offsets or, for a graph that holds runs only, from deg
+__global__ void k_control_runs(int64_t n, const uint64_t *runptr, const uint2 *runs, const uint64_t *rowptr, const uint32_t *deg,
+                               int64_t src_begin, int64_t src_end, float *control) {
+    int64_t v = src_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= src_end) return;
+    float c = 0.0f;
+    for (uint64_t r = runptr[v]; r < runptr[v + 1]; r++) {
+        const uint2 run = runs[r];
+        if (run.x >= (uint32_t)n) break;
+        for (uint32_t u = run.x; u < run.x + run.y; u++) {
+            const int retro = rowptr ? (int)(rowptr[u + 1] - rowptr[u]) : (int)deg[u];
+            c = __fadd_rn(c, __fdiv_rn(1.0f, (float)retro));
+        }
+    }
+    control[v - src_begin] = c;
+}
+
 // ---- bit-parallel batched variant --------------------------------------------------------------
 // 64 spatially coherent cells form a batch (same clusters as the BFS).  With F1[w] = mask of the
 // batch's cells s that have w in their row (w ranges over the whole universe, ghosts included):
@@ -304,7 +437,7 @@ int run_local_batched(vga_ctx *ctx, vga_graph *g, int64_t src_begin, int64_t src
         VGA_CUDA(cudaMemsetAsync(d_cl.p, 0, sizeof(u64) * (size_t)cb * 64, st));
         VGA_CUDA(cudaMemsetAsync(d_tot.p, 0, sizeof(int32_t) * (size_t)cb * 64, st));
         k_lb_seed<<<(unsigned)((cs * 32 + 255) / 256), 256, 0, st>>>(d, d_order.p + first, cs);
-            k_lb_expand<<<dim3(xb_n, (unsigned)cb), LTPB, 0, st>>>(d);
+        k_lb_expand<<<dim3(xb_n, (unsigned)cb), LTPB, 0, st>>>(d);
         k_lb_total<<<dim3(xb_u, (unsigned)cb), LTPB, 0, st>>>(d);
         tm.launches += 3;
         tm.main_launches += 3;
@@ -338,6 +471,78 @@ int run_local_batched(vga_ctx *ctx, vga_graph *g, int64_t src_begin, int64_t src
     return VGA_OK;
 }
 
+int run_local_runs(vga_ctx *ctx, vga_graph *g, int64_t src_begin, int64_t src_end, int64_t *cluster, int32_t *k, int32_t *total,
+                   float *control) {
+    cudaStream_t st = ctx->stream;
+    const int64_t n = g->n, ns = src_end - src_begin;
+    Timing &tm = ctx->timing;
+    StageTimer kt(ctx, 0, &tm.kernel_ms);
+    StageTimer mt(ctx, 2, &tm.main_kernel_ms);
+    StageTimer dt(ctx, 4, &tm.d2h_ms);
+    StageTimer pt(ctx, 6, &tm.prep_ms);
+    pt.start();
+    VGA_TRY(ensure_fwd_runs(ctx, g));
+    if (g->entries == 0 && !g->deg.p) {
+        set_error("vga_local: a graph adopted from runs needs the per-row entry counts (d_degree)");
+        return VGA_ERR_INVALID;
+    }
+    pt.stop();
+    DevBuf<long long> d_cluster;
+    DevBuf<int32_t> d_k, d_total;
+    DevBuf<float> d_control;
+    DevBuf<u64> work;
+    VGA_TRY(d_cluster.alloc((size_t)ns));
+    VGA_TRY(d_k.alloc((size_t)ns));
+    VGA_TRY(d_total.alloc((size_t)ns));
+    VGA_TRY(d_control.alloc((size_t)ns));
+    VGA_TRY(work.alloc_zero(1, st));
+    LocalRunsDev d;
+    d.n = n;
+    d.universe = n + g->ghosts;
+    d.runptr = g->f_runptr.p;
+    d.runs = g->f_runs.p;
+    d.src_begin = src_begin;
+    d.src_end = src_end;
+    d.work = work.p;
+    d.cluster = d_cluster.p;
+    d.k = d_k.p;
+    d.total = d_total.p;
+    // two bitmaps of `span` bits per CTA within ~200 KB of shared memory
+    const size_t smem_cap = std::min<size_t>(ctx->smem_optin, (size_t)200 << 10);
+    int64_t max_span = (int64_t)(smem_cap / 8) * 32;  // bits: 2 bitmaps * span / 8 bytes
+    if (ctx->opt.local_span > 0) max_span = std::min<int64_t>(max_span, std::max<int64_t>(32, ctx->opt.local_span / 32 * 32));
+    d.passes = (int)std::max<int64_t>(1, (d.universe + max_span - 1) / max_span);
+    d.span = (uint32_t)(((d.universe + d.passes - 1) / d.passes + 31) / 32 * 32);
+    const size_t smem = (size_t)(d.span / 32) * 2 * sizeof(uint32_t);
+    // small universes: many CTAs of 256 threads per SM; large ones: one CTA of 1024 threads per SM
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, smem_cap / std::max<size_t>(smem, 1)));
+    const int threads = per_sm >= 4 ? 256 : (per_sm >= 2 ? 512 : 1024);
+    int blocks = (int)std::min<int64_t>((int64_t)ctx->sm_count * per_sm, ns);
+    VGA_CUDA(cudaFuncSetAttribute(k_local_runs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kt.start();
+    mt.start();
+    k_local_runs<<<blocks, threads, smem, st>>>(d);
+    tm.launches++;
+    tm.main_launches++;
+    VGA_CUDA(cudaGetLastError());
+    mt.stop();
+    k_control_runs<<<(unsigned)((ns + 127) / 128), 128, 0, st>>>(n, g->f_runptr.p, g->f_runs.p, g->entries > 0 ? g->rowptr.p : nullptr,
+                                                               g->entries > 0 ? nullptr : g->deg.p, src_begin, src_end, d_control.p);
+    tm.launches++;
+    VGA_CUDA(cudaGetLastError());
+    kt.stop();
+    dt.start();
+    if (cluster) VGA_CUDA(cudaMemcpyAsync(cluster, d_cluster.p, sizeof(int64_t) * ns, cudaMemcpyDeviceToHost, st));
+    if (k) VGA_CUDA(cudaMemcpyAsync(k, d_k.p, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, st));
+    if (total) VGA_CUDA(cudaMemcpyAsync(total, d_total.p, sizeof(int32_t) * ns, cudaMemcpyDeviceToHost, st));
+    if (control) VGA_CUDA(cudaMemcpyAsync(control, d_control.p, sizeof(float) * ns, cudaMemcpyDeviceToHost, st));
+    dt.stop();
+    VGA_CUDA(cudaStreamSynchronize(st));
+    // algorithmic bytes (local: rowbytes(v) + sum of rowbytes(u) over N(v), no-reuse model) are not
+    // accumulated here: bench.py reports cells/s for this stage
+    return VGA_OK;
+}
+
 }  // namespace
 
 int run_local(vga_ctx *ctx, vga_graph *g, int64_t src_begin, int64_t src_end, int64_t *cluster, int32_t *k,
@@ -353,10 +558,9 @@ int run_local(vga_ctx *ctx, vga_graph *g, int64_t src_begin, int64_t src_end, in
     const int64_t ns = std::max<int64_t>(0, src_end - src_begin);
     if (ns == 0) return VGA_OK;
     {
-        // auto (measured, profiles/): per-cell bitmaps win while rows are short (C2: deg 431), the
-        // bit-parallel batches win from about a thousand neighbours per cell (C1: 1.6x, C4: 5.7x)
+        // auto: the run-length kernel (also the only one for a graph that holds runs only); 0 / 1 select the entry kernels
         int64_t lm = ctx->opt.local_mode;
-        if (lm == 2) lm = ((double)g->entries >= 1024.0 * (double)n) ? 1 : 0;
+        if (lm == 2 || lm == 3 || g->entries == 0) return run_local_runs(ctx, g, src_begin, src_end, cluster, k, total, control);
         if (lm == 1) return run_local_batched(ctx, g, src_begin, src_end, cluster, k, total, control);
     }
     Timing &tm = ctx->timing;

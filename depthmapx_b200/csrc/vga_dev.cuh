@@ -136,7 +136,10 @@ struct Timing {
 struct Options {
     int64_t bfs_mode = 2;        // 0 top-down (push) only, 1 bottom-up (pull) only, 2 direction-optimising hybrid
     int64_t bfs_words = 0;       // 64-bit words per vertex and batch (a batch = 64*words sources): 1, 2, 4, 8; 0 = auto
-    int64_t local_mode = 2;      // 0: one CTA per cell with bitmaps, 1: bit-parallel batches of 64 cells, 2: auto
+    int64_t local_mode = 2;      // 2 / 3: one CTA per cell, bitmaps fed by run-length rows (default); 0: the same fed by entries;
+                                 // 1: bit-parallel batches of 64 cells over entries
+    int64_t local_span = 0;      // run-length local kernel: bits of the vertex universe per pass (0 = what fits shared memory);
+                                 // tests force several passes on small plans with it
     int64_t bfs_chunk = 0;       // 64-source words in flight; 0 = auto from free memory
     int64_t sieve_mode = 1;      // 1: thread-per-(source,octant) kernel + warp kernel for overflow, 0: warp kernel
     int64_t sieve_gcap = 48;     // shared-memory gap capacity per warp
@@ -205,7 +208,7 @@ struct vga_graph {
     vga::DevBuf<uint8_t> noexpand;  // [n] != 0: counted but not expanded (context-filled, not even); empty = none
     // ---- BFS structures, built lazily from the sorted rows (bfs.cu) or adopted (vga_graph_from_device_runs) ----------
     // Rows of a grid visibility graph are unions of a few runs of consecutive ordinals.  f_runs: the out-row of u is the
-    // union of f_runs[f_runptr[u] .. f_runptr[u+1]) = (first ordinal, length), ghost columns excluded; t_runs: the same
+    // union of f_runs[f_runptr[u] .. f_runptr[u+1]) = (first ordinal, length), ghost runs (first >= n) last; t_runs: the same
     // for the in-rows (transposed by bfs.cu in O(runs), no entry-sized transpose exists).  f_nodes / t_nodes: per row the
     // ids of the OR-pyramid nodes that tile its runs (id < n: the vertex's own word, id >= n: inner node id - n), row
     // offsets f_nodeptr / t_nodeptr.  The BFS reads only the node lists.

@@ -201,7 +201,8 @@ int vga_graph_from_device_rows(vga_ctx *ctx, int64_t n_cells, int64_t n_ghosts, 
 
 /* Run-length form of the shard's rows: what the BFS reads and what a multi-GPU run exchanges (8 bytes per run instead of
  * 4 bytes per entry: 1.3 GB instead of 22 GB at 10^6 cells).  runptr (u64, local, rows+1), runs = pairs of u32 (first
- * column ordinal, length) sorted by first ordinal, ghost columns excluded.  Valid until vga_graph_free. */
+ * column ordinal, length) sorted by first ordinal; no run straddles N, the ghost columns (>= N) are the last runs of a
+ * row.  Valid until vga_graph_free. */
 int vga_graph_device_runs(vga_ctx *ctx, const vga_graph *g, const uint64_t **d_runptr, const void **d_runs, int64_t *n_runs);
 /* Adopt device-resident run-length rows of all N cells (e.g. the all-gathered shards).  The graph serves vga_global /
  * vga_global_sources only (no entries, bins or statistics).  d_degree (u32 [N], entries per row, may be NULL) only

@@ -7,7 +7,8 @@ re-entrant, so parallelism comes from PROCESSES:
   1. the graph the BFS sample needs (every Node of the plan -- minutes of sparkPixel2 for the 10^6-cell workload) is
      made once by P forked builders, each running the body of sparkGraph2's source loop for an interleaved share of the
      sources and handing its Nodes over through the reference's own Node::write / Node::read; the parts are cached in
-     a scratch directory (repo-local .refcache/, ignored by git and gpurun), so later invocations on the same box load them;
+     a scratch directory ($VGA_REFCACHE or <tmp>/vga_refcache, 1.7 GB for the 10^6-cell plan), so later invocations on the same
+     box load them;
   2. the parent loads all parts and forks P workers that share the graph copy-on-write;
   3. a timed step hands every worker a share of the step's sampled sources: sparkPixel2(make = 1) for each (the
      construction half of the metric) and the per-source body of VGAVisualGlobal::run around the reference's
@@ -18,6 +19,7 @@ from __future__ import annotations
 import hashlib
 import multiprocessing as mp
 import os
+import tempfile
 import time
 
 import numpy as np
@@ -31,7 +33,7 @@ def _cache_dir(plan, spacing):
     h = hashlib.sha1()
     h.update(np.ascontiguousarray(plan.walls, np.float64).tobytes())
     h.update(repr((spacing, plan.seeds)).encode())
-    base = os.environ.get("VGA_REFCACHE", os.path.join(ROOT, ".refcache"))
+    base = os.environ.get("VGA_REFCACHE", os.path.join(tempfile.gettempdir(), "vga_refcache"))
     return os.path.join(base, h.hexdigest()[:16])
 
 

@@ -19,6 +19,7 @@ if os.environ.get("VGA_EMU_LIBDIR"):
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "ref: needs oracle/_ref/libdmxref.so (the compiled reference)")
+    config.addinivalue_line("markers", "slow: minutes on the GPU box (the 10^6-cell configuration)")
 
 
 def pytest_collection_modifyitems(config, items):

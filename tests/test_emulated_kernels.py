@@ -1,13 +1,10 @@
 """CPU: the CUDA translation units of libvga_b200 executed by a SIMT emulator (tests/emu/: kernel launches become
 fiber-per-thread block executions with real warp collectives; see tests/emu/include/simt_emu.h), so that kernel logic and
-the host-side launch sequences are exercised without a GPU.  This is how the code paths written after round 1's GPU
-budget was spent (host-layer .graph pipelines, merge links, the step-depth CLI shim, bit-sliced local counters, the
-pyramid pull, the unrolled push) were validated before their first B200 run, and it keeps every kernel under test in the
-GPU-less container from now on.
+the host-side launch sequences are exercised without a GPU.  It keeps every kernel under test in the GPU-less container (round 2's BFS rewrite around pyramid node
+lists and the O(runs) transposition were developed against it before their first B200 run).
 
 GPU test modules are re-run unchanged in a subprocess whose ctypes loader points at the emulation build
-(VGA_EMU_LIBDIR, tests/conftest.py); `--runxfail` turns the guards of the pending-first-GPU-run modules off, so a wrong
-result fails here.  The emulator is single-threaded: it checks logic (indices, masks, collectives, launch order), not
+(VGA_EMU_LIBDIR, tests/conftest.py).  The emulator is single-threaded: it checks logic (indices, masks, collectives, launch order), not
 races or performance.  Nothing in the product can load it."""
 import os
 import subprocess
@@ -113,19 +110,17 @@ def test_graphfile_pipelines_merges_and_cli_shim(emu_dir):
     run_gpu_tests_emulated(emu_dir, ["tests/test_zzz_graphfile_gpu.py"])
 
 
-def test_experimental_kernels(emu_dir):
-    """local_mode = 3 (bit-sliced counters), bfs_pull / bfs_push = 1 (pyramids), bfs_push_unroll = 4, build_sort = 1 (bitmap
-    rank sort) on the small plans."""
-    run_gpu_tests_emulated(emu_dir, ["tests/test_zzzz_experimental_gpu.py", "-k", "oblique or holes"])
+def test_bfs_schedules_and_row_ordering(emu_dir):
+    """tests/test_gpu_bfs_schedules.py on the small plans: the three directions, every word width, explicit source lists,
+    the O(runs) transposition (pinned by the bottom-up-only schedule), both row-ordering kernels, the run-length round trip."""
+    run_gpu_tests_emulated(emu_dir, ["tests/test_gpu_bfs_schedules.py", "-k", "oblique or holes or round_trip"])
 
 
-def test_pyramid_schedules_on_a_plan_with_rooms(emu_dir):
-    """office:64 (4,096 cells, deeper level structure, 64 batches): both pyramids with automatic word width, the pyramid
-    pull alone in the hybrid schedule, and the forced pyramid push under a radius."""
-    f = "tests/test_zzzz_experimental_gpu.py::"
-    run_gpu_tests_emulated(emu_dir, [f + "test_pyramid_push_vs_oracle[1-1-2-0--1-office:64:64:1]",
-                                     f + "test_pyramid_pull_vs_oracle[2-1-1--1-office:64:64:1]",
-                                     f + "test_pyramid_push_vs_oracle[2-0-0-1-2-office:64:64:1]"])
+def test_bfs_schedules_on_a_plan_with_rooms(emu_dir):
+    """office:64 (4,096 cells, deeper level structure, several batches): hybrid with automatic word width, bottom-up only
+    with two words, top-down only with four."""
+    f = "tests/test_gpu_bfs_schedules.py::test_schedules_vs_oracle"
+    run_gpu_tests_emulated(emu_dir, [f + "[2-0-2--1-office:64:64:1]", f + "[1-2-2--1-office:64:64:1]", f + "[0-4-2-2-office:64:64:1]"])
 
 
 def test_real_cli_with_gpu_shims(emu_dir):
@@ -150,7 +145,7 @@ def test_kernels_under_address_sanitizer():
     env = dict(os.environ, VGA_EMU_LIBDIR=d, LD_LIBRARY_PATH=d, LD_PRELOAD=libs,
                ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
     r = subprocess.run([sys.executable, "-m", "pytest", "-m", "gpu", "--runxfail", "-x", "-q", "-p", "no:cacheprovider",
-                        "tests/test_zzzz_experimental_gpu.py", "tests/test_gpu_parity.py", "tests/test_stepdepth_gpu.py",
+                        "tests/test_gpu_bfs_schedules.py", "tests/test_gpu_parity.py", "tests/test_stepdepth_gpu.py",
                         "tests/test_zzz_graphfile_gpu.py", "-k",
                         "(oblique and not overflow) or golden or ghost or empty or several or step_depth or visprep or loaded or merge"],
                        cwd=ROOT, env=env, capture_output=True, text=True, timeout=7200)

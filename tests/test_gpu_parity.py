@@ -193,9 +193,10 @@ def test_global_vs_oracle_all_modes(name, radius, mode, words, order):
 
 
 @pytest.mark.parametrize("name", ["oblique:30:30:7", "office:64:64:1", "urban:120:120:4"])
-@pytest.mark.parametrize("local_mode", [0, 1])
+@pytest.mark.parametrize("local_mode", [0, 1, 2])
 def test_local_vs_oracle(name, local_mode):
-    """Both local kernels (bit-parallel batched = default, CTA-per-cell bitmaps) against the oracle."""
+    """The local kernels (2 = default: per-cell bitmaps fed by run-length rows; 0: fed by entries; 1: bit-parallel
+    batches) against the oracle."""
     flat, og = cached_oracle(name)
     c = capi.Context(0)
     c.set_option("local_mode", local_mode)
@@ -209,6 +210,20 @@ def test_local_vs_oracle(name, local_mode):
     if g.n <= 5000:  # whole map through the batched path (several batches, partial last batch)
         for x, y in zip(g.local_ints(), og.local_ints()):
             assert np.array_equal(x, y)
+    c.close()
+
+
+@pytest.mark.parametrize("name", ["oblique:30:30:7", "office:64:64:1"])
+def test_local_runs_in_several_passes(name):
+    """The run-length local kernel covering the vertex universe in several column ranges (as at 10^6 cells, where two
+    bitmaps of the whole universe exceed shared memory): runs clipped at the range borders, counts summed over the passes."""
+    flat, og = cached_oracle(name)
+    c = capi.Context(0)
+    c.set_option("local_span", 320)
+    g = c.build(flat)
+    hi = min(g.n, 400)
+    for x, y in zip(g.local_ints((0, hi)), og.local_ints((0, hi))):
+        assert np.array_equal(x, y)
     c.close()
 
 
