@@ -311,6 +311,140 @@ template <int W> __global__ void __launch_bounds__(TPB) k_pull_nodes(BfsDev d) {
     }
 }
 
+// ---- lane-cooperative variants (bfs_coop = 1, W >= 4) ---------------------------------------------------------------
+// ncu on the heavy top-down launch of a 10^6-cell plan (profiles/r2_prof_k_push_nodes_C5slice_summary.txt): bound by L1
+// data-pipe wavefronts (87 %) -- a warp-wide gather of 32 scattered 16-byte vectors costs one wavefront per vector, and a
+// lane that owns a whole W-word vector issues W/2 such gathers, so wider batches bought nothing (266 / 301 / 437 ms for
+// W = 2 / 4 / 8).  Here G = W/2 consecutive lanes share one node: each loads / updates its own 16-byte slice, so a node's
+// vector arrives in ONE wavefront whatever W is, and the visits per source drop by G.
+template <int W, int G> __global__ void __launch_bounds__(TPB) k_push_nodes_coop(BfsDev d) {
+    static_assert(W == 2 * G, "two words per lane");
+    const int b = blockIdx.y;
+    if (!d.active[b] || d.mode[b] != 0) return;
+    const int lane = threadIdx.x & 31;
+    const int g = lane % G, sub = lane / G;
+    constexpr int NPI = 32 / G;  // nodes per warp iteration
+    const u64 *fr = d.frontier + (int64_t)b * d.n * W;
+    u64 *nx = d.next + (int64_t)b * d.n * W;
+    u64 *np = d.npyr + (int64_t)b * d.pyr_total * W;
+    const uint32_t n = (uint32_t)d.n;
+    for (int64_t base = (int64_t)blockIdx.x * TPB; base < d.n; base += (int64_t)gridDim.x * TPB) {
+        const int64_t wbase = base + (threadIdx.x & ~31);
+        int64_t u = base + threadIdx.x;
+        u64 anyf = 0ULL;
+        if (u < d.n) {
+            u64 f[W];
+            ldw_stream<W>(fr + u * W, f);
+#pragma unroll
+            for (int j = 0; j < W; j++) anyf |= f[j];
+        }
+        uint64_t my0 = 0, my1 = 0;
+        if (anyf != 0ULL) {
+            my0 = d.f_ptr[u];
+            my1 = d.f_ptr[u + 1];
+        }
+        unsigned m = __ballot_sync(FULL, anyf != 0ULL);
+        while (m) {
+            int src_lane = __ffs(m) - 1;
+            m &= m - 1;
+            const uint64_t e0 = __shfl_sync(FULL, my0, src_lane), e1 = __shfl_sync(FULL, my1, src_lane);
+            // this lane's slice of the vertex's frontier vector (just read by the warp: an L1 / L2 hit)
+            const ulonglong2 myf = *reinterpret_cast<const ulonglong2 *>(fr + (wbase + src_lane) * W + 2 * g);
+            if ((myf.x | myf.y) == 0ULL) continue;
+            for (uint64_t e = e0 + sub; e < e1; e += NPI) {
+                const uint32_t c = __ldcs(d.f_nodes + e);
+                VGA_COUNT(npush_nodes, 1);
+                u64 *p = (c < n ? nx + (int64_t)c * W : np + (int64_t)(c - n) * W) + 2 * g;
+                const ulonglong2 cur = *reinterpret_cast<const ulonglong2 *>(p);
+                const u64 a0 = myf.x & ~cur.x, a1 = myf.y & ~cur.y;
+                if (a0) atomicOr(&p[0], a0);
+                if (a1) atomicOr(&p[1], a1);
+            }
+        }
+    }
+}
+
+template <int W, int G> __global__ void __launch_bounds__(TPB) k_pull_nodes_coop(BfsDev d) {
+    static_assert(W == 2 * G && G <= 8, "two words per lane, a node within an 8-lane group");
+    const int b = blockIdx.y;
+    if (!d.active[b] || d.mode[b] != 1) return;
+    const int lane = threadIdx.x & 31;
+    const u64 *fr = d.frontier + (int64_t)b * d.n * W;
+    const u64 *vis = d.visited + (int64_t)b * d.n * W;
+    const u64 *pyr = d.pyr + (int64_t)b * d.pyr_total * W;
+    u64 *nx = d.next + (int64_t)b * d.n * W;
+    const uint32_t n = (uint32_t)d.n;
+    const int grp = lane >> 3, gl = lane & 7;
+    const int g = gl % G, sub = gl / G;
+    constexpr int NPG = 8 / G;  // nodes per 8-lane group and load
+    const unsigned gmask = 0xffu << (grp * 8);
+    const ulonglong2 valid = *reinterpret_cast<const ulonglong2 *>(d.valid + (int64_t)b * W + 2 * g);
+    for (int64_t base = (int64_t)blockIdx.x * TPB; base < d.n; base += (int64_t)gridDim.x * TPB) {
+        const int64_t wbase = base + (threadIdx.x & ~31);
+        int64_t w = base + threadIdx.x;
+        u64 anyneed = 0ULL;
+        if (w < d.n) {
+            u64 vv[W];
+            ldw_stream<W>(vis + w * W, vv);
+#pragma unroll
+            for (int j = 0; j < W; j++) anyneed |= d.valid[(int64_t)b * W + j] & ~vv[j];
+        }
+        uint64_t my0 = 0, my1 = 0;
+        if (anyneed != 0ULL) {
+            my0 = d.t_ptr[w];
+            my1 = d.t_ptr[w + 1];
+        }
+        const unsigned m = __ballot_sync(FULL, anyneed != 0ULL);
+        const int ncand = __popc(m);
+        for (int r = 0; r * 4 < ncand; r++) {
+            const int k = r * 4 + grp;
+            const bool has = k < ncand;
+            const int src_lane = has ? (int)__fns(m, 0, k + 1) : 0;
+            const uint64_t e0 = __shfl_sync(FULL, my0, src_lane), e1 = __shfl_sync(FULL, my1, src_lane);
+            if (has) {
+                const int64_t ww = wbase + src_lane;
+                const ulonglong2 vv = *reinterpret_cast<const ulonglong2 *>(vis + ww * W + 2 * g);
+                const u64 nd0 = valid.x & ~vv.x, nd1 = valid.y & ~vv.y;
+                u64 acc0 = 0ULL, acc1 = 0ULL;
+                for (uint64_t e = e0; e < e1; e += 2 * NPG) {
+                    const uint64_t ea = e + sub, eb = e + NPG + sub;
+                    u64 x0 = 0ULL, x1 = 0ULL;
+                    uint32_t ca = 0, cb = 0;
+                    if (ea < e1) ca = __ldcs(d.t_nodes + ea);
+                    if (eb < e1) cb = __ldcs(d.t_nodes + eb);
+                    VGA_COUNT(npull_nodes, (g == 0) * ((ea < e1) + (eb < e1)));
+                    if (ea < e1) {
+                        const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>((ca < n ? fr + (int64_t)ca * W : pyr + (int64_t)(ca - n) * W) + 2 * g);
+                        x0 |= t.x;
+                        x1 |= t.y;
+                    }
+                    if (eb < e1) {
+                        const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>((cb < n ? fr + (int64_t)cb * W : pyr + (int64_t)(cb - n) * W) + 2 * g);
+                        x0 |= t.x;
+                        x1 |= t.y;
+                    }
+                    // OR over the lanes of the group that hold the same slice
+#pragma unroll
+                    for (int o = G; o < 8; o <<= 1) {
+                        x0 |= __shfl_xor_sync(gmask, x0, o);
+                        x1 |= __shfl_xor_sync(gmask, x1, o);
+                    }
+                    acc0 |= x0;
+                    acc1 |= x1;
+                    const bool mine_done = ((acc0 & nd0) == nd0) && ((acc1 & nd1) == nd1);
+                    if (__ballot_sync(gmask, !mine_done) == 0u) break;
+                }
+                if (sub == 0) {
+                    const u64 n0 = acc0 & nd0, n1 = acc1 & nd1;
+                    if (n0) nx[ww * W + 2 * g] = n0;
+                    if (n1) nx[ww * W + 2 * g + 1] = n1;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // fold next into visited/frontier, count new vertices per source, gather direction statistics;
 // `level_next` = level of the vertices being added
 template <int W>
@@ -667,7 +801,14 @@ int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, De
     while (radius == -1 || level < radius) {
         dim3 grid(xblocks, (unsigned)nb);
         if (bfs_mode != 1 || level == 0) {
-            k_push_nodes<W><<<grid, TPB, 0, st>>>(d);
+            if constexpr (W >= 4 && W <= 16) {
+                if (ctx->opt.bfs_coop)
+                    k_push_nodes_coop<W, W / 2><<<grid, TPB, 0, st>>>(d);
+                else
+                    k_push_nodes<W><<<grid, TPB, 0, st>>>(d);
+            } else {
+                k_push_nodes<W><<<grid, TPB, 0, st>>>(d);
+            }
             tm.launches++;
             tm.main_launches++;
             for (int k = kmax; k >= 0; k -= 3) {
@@ -686,7 +827,14 @@ int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, De
                 tm.launches++;
                 tm.main_launches++;
             }
-            k_pull_nodes<W><<<grid, TPB, 0, st>>>(d);
+            if constexpr (W >= 4 && W <= 16) {
+                if (ctx->opt.bfs_coop)
+                    k_pull_nodes_coop<W, W / 2><<<grid, TPB, 0, st>>>(d);
+                else
+                    k_pull_nodes<W><<<grid, TPB, 0, st>>>(d);
+            } else {
+                k_pull_nodes<W><<<grid, TPB, 0, st>>>(d);
+            }
             tm.launches++;
             tm.main_launches++;
         }
@@ -1101,7 +1249,7 @@ int transpose_runs(vga_ctx *ctx, vga_graph *g) {
 
 // node-id lists from runs: per-run node counts -> exclusive scan -> ids written at the run's offset
 int build_nodes(vga_ctx *ctx, int64_t n, const DevBuf<uint64_t> &runptr, const DevBuf<uint2> &runs, int64_t nruns,
-                DevBuf<uint64_t> &nodeptr, DevBuf<uint32_t> &nodes) {
+                DevBuf<uint64_t> &nodeptr, DevBuf<uint32_t> &nodes, int64_t *nnodes) {
     cudaStream_t st = ctx->stream;
     const PyrLayout pl = pyr_layout(n);
     BfsDev d0;
@@ -1123,6 +1271,7 @@ int build_nodes(vga_ctx *ctx, int64_t n, const DevBuf<uint64_t> &runptr, const D
     uint64_t total = 0;
     VGA_CUDA(cudaMemcpyAsync(&total, off.p + nruns, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     VGA_CUDA(cudaStreamSynchronize(st));
+    *nnodes = (int64_t)total;
     VGA_TRY(nodes.alloc((size_t)total + 1));
     if (nruns > 0) {
         k_emit_nodes<<<blocks_for(nruns, 256), 256, 0, st>>>(runs.p, nruns, off.p, (uint32_t)n, d0, nodes.p);
@@ -1190,12 +1339,12 @@ int ensure_bfs_lists(vga_ctx *ctx, vga_graph *g, bool transposed) {
     }
     VGA_TRY(ensure_fwd_runs(ctx, g));
     if (!g->has_f_nodes) {
-        VGA_TRY(build_nodes(ctx, g->n, g->f_runptr, g->f_runs, g->f_nruns, g->f_nodeptr, g->f_nodes));
+        VGA_TRY(build_nodes(ctx, g->n, g->f_runptr, g->f_runs, g->f_nruns, g->f_nodeptr, g->f_nodes, &g->f_nnodes));
         g->has_f_nodes = true;
     }
     if (transposed && !g->has_t_nodes) {
         if (!g->has_runs) VGA_TRY(transpose_runs(ctx, g));
-        VGA_TRY(build_nodes(ctx, g->n, g->t_runptr, g->t_runs, g->t_nruns, g->t_nodeptr, g->t_nodes));
+        VGA_TRY(build_nodes(ctx, g->n, g->t_runptr, g->t_runs, g->t_nruns, g->t_nodeptr, g->t_nodes, &g->t_nnodes));
         g->has_t_nodes = true;
     }
     return VGA_OK;
@@ -1226,13 +1375,16 @@ int run_global(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources, i
     if (nsrc <= 0) return VGA_OK;
     int words = (int)ctx->opt.bfs_words;
     if (words <= 0) {
-        // auto (measured on B200, profiles/): node visits are L2 gathers of W*8 bytes, so a wider batch serves more sources
-        // per 32-byte sector -- as long as the randomly accessed state of one batch (two pyramids of ~2n words each
-        // direction) stays L2 resident (126 MB)
-        const int64_t l2_mb = ctx->opt.bfs_l2_words > 0 ? ctx->opt.bfs_l2_words : 96;
-        words = 8;
-        while (words > 1 && 2.0 * (double)n * 8.0 * words > (double)l2_mb * 1e6) words >>= 1;
-        if (words > 4) words = 4;
+        // auto (measured on B200, profiles/README.md): two words (128 sources) per batch; four when the out-rows are long
+        // (from ~384 pyramid nodes per row, e.g. the halls of the gallery plan: 46 vs 52 ms on a C4 slice).  Wider batches
+        // lose more to the lower coherence of their sources than they gain (C5: 266 / 301 / 437 ms for 2 / 4 / 8 words).
+        {
+            StageTimer pt(ctx, 6, &ctx->timing.prep_ms);
+            pt.start();
+            VGA_TRY(ensure_bfs_lists(ctx, g, ctx->opt.bfs_mode != 0));
+            pt.stop();
+        }
+        words = (n > 0 && g->f_nnodes >= ctx->opt.bfs_wide_nodes * n) ? 4 : 2;
     }
     while (words > 1 && nsrc <= 64 * (words / 2)) words >>= 1;
     switch (words) {

@@ -28,10 +28,12 @@ static int set_option(Options &o, const std::string &key, int64_t value) {
     if (key == "bfs_mode") o.bfs_mode = value;
     else if (key == "bfs_chunk") o.bfs_chunk = value;
     else if (key == "bfs_words") o.bfs_words = value;
-    else if (key == "bfs_l2_words") o.bfs_l2_words = value;
+    else if (key == "bfs_wide_nodes") o.bfs_wide_nodes = value;
+    else if (key == "bfs_coop") o.bfs_coop = value;
     else if (key == "local_mode") o.local_mode = value;
     else if (key == "local_span") o.local_span = value;
     else if (key == "sieve_mode") o.sieve_mode = value;
+    else if (key == "sieve_thread_cap") o.sieve_thread_cap = value;
     else if (key == "sieve_gcap") o.sieve_gcap = value;
     else if (key == "sieve_bcap") o.sieve_bcap = value;
     else if (key == "sieve_big_gcap") o.sieve_big_gcap = value;
@@ -140,6 +142,7 @@ int vga_ctx_create(int device, vga_ctx **out) {
     c->device = device;
     VGA_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto &e : c->ev) VGA_CUDA(cudaEventCreate(&e));
+    register_cache(c->stream);
     cudaDeviceProp p;
     VGA_CUDA(cudaGetDeviceProperties(&p, device));
     c->sm_count = p.multiProcessorCount;
@@ -168,6 +171,7 @@ void vga_ctx_destroy(vga_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     g_alloc_stream = ctx->stream;
     ctx->ws.clear();
+    unregister_cache(ctx->stream);  // parked blocks go back to the pool; buffers still alive free themselves directly
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     {
         cudaMemPool_t pool;

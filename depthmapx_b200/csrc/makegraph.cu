@@ -25,6 +25,9 @@
 //   make_keys + cub segmented sort -- rows sorted by x-major ordinal, packed col<<6|accepted<<5|bin.
 #include <cub/cub.cuh>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include <algorithm>
 #include <memory>
 
@@ -693,10 +696,10 @@ template <bool EMIT> __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_s
 // shared memory (TG entries per thread, interleaved), the row's blocks in local memory.  Tasks that
 // exceed TG gaps / TB blocks are flagged and re-run by the warp kernel with global scratch.
 constexpr int TT = 128;  // threads per CTA
-constexpr int TG = 8;    // gaps per thread (shared memory)
-constexpr int TB = 24;   // blocks per row per thread (local memory)
+// TG = gaps per thread (shared memory), TB = blocks per row per thread (local memory): (8, 24) by default, (16, 48) with
+// sieve_thread_cap = 1 (fewer tasks fall back to the warp kernel, at twice the shared memory per CTA)
 
-template <bool EMIT> __global__ void __launch_bounds__(TT) k_sieve_thread(SieveArgs a, int64_t nsrc) {
+template <bool EMIT, int TG, int TB> __global__ void __launch_bounds__(TT) k_sieve_thread(SieveArgs a, int64_t nsrc) {
     __shared__ Zone s_gaps[TG * TT];
     const int tid = threadIdx.x;
     const int64_t t = (int64_t)blockIdx.x * TT + tid;
@@ -1205,8 +1208,10 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t sr
     mt.start();
     // ---- pass 1: count
     if (ntasks > 0) {
-        if (ctx->opt.sieve_mode == 1)
-            k_sieve_thread<false><<<blocks_for(ntasks, TT), TT, 0, st>>>(a, nsrc);
+        if (ctx->opt.sieve_mode == 1 && ctx->opt.sieve_thread_cap == 1)
+            k_sieve_thread<false, 16, 48><<<blocks_for(ntasks, TT), TT, 0, st>>>(a, nsrc);
+        else if (ctx->opt.sieve_mode == 1)
+            k_sieve_thread<false, 8, 24><<<blocks_for(ntasks, TT), TT, 0, st>>>(a, nsrc);
         else
             k_sieve<false><<<blocks_for(ntasks, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, smem_bytes, st>>>(a);
         tm.launches++;
@@ -1215,6 +1220,9 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t sr
     }
     VGA_CUDA(cudaMemcpyAsync(&h_over, n_overflow.p, sizeof(h_over), cudaMemcpyDeviceToHost, st));
     VGA_CUDA(cudaStreamSynchronize(st));
+    if (std::getenv("VGA_DEBUG_TIMING"))
+        fprintf(stderr, "[vga_graph_build] %lld of %lld (source, octant) tasks exceed the thread kernel's capacity\n", (long long)h_over,
+                (long long)ntasks);
     if (h_over > 0) {
         VGA_TRY(big_scratch.alloc(per_warp_bytes(big_gcap, big_bcap) * (size_t)big_warps));
         SieveArgs b = a;
@@ -1313,8 +1321,10 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t sr
         e.e_ref = e_ref.p;
         e.e_bin = e_bin.p;
         mt.start();
-        if (ctx->opt.sieve_mode == 1)
-            k_sieve_thread<true><<<blocks_for(ns * 8, TT), TT, 0, st>>>(e, ns);
+        if (ctx->opt.sieve_mode == 1 && ctx->opt.sieve_thread_cap == 1)
+            k_sieve_thread<true, 16, 48><<<blocks_for(ns * 8, TT), TT, 0, st>>>(e, ns);
+        else if (ctx->opt.sieve_mode == 1)
+            k_sieve_thread<true, 8, 24><<<blocks_for(ns * 8, TT), TT, 0, st>>>(e, ns);
         else
             k_sieve<true><<<blocks_for(ns * 8, WARPS_PER_BLOCK), WARPS_PER_BLOCK * 32, smem_bytes, st>>>(e);
         tm.launches++;

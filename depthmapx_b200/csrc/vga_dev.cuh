@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -47,34 +49,134 @@ void set_error(const std::string &msg);
 // being mapped and unmapped every time (cudaMalloc/cudaFree of GBs costs 100s of ms).
 extern thread_local cudaStream_t g_alloc_stream;
 
-// RAII device buffer (cudaMallocAsync / cudaFreeAsync); zero-size allocations are nullptr.
+// Cache of large device blocks, one per context (keyed by the context's stream).  A step of the hot path allocates and
+// frees the same multi-GB buffers over and over (22 GB of entries, GBs of run / node lists at 10^6 cells); CUDA's
+// stream-ordered pool re-maps physical memory whenever its free blocks were split by smaller requests in between, which
+// showed up as seconds of jitter per call (bench: 1.3 s -> 4.5 s for the same build).  Blocks of BIG_BLOCK bytes or
+// more are therefore parked here on release and handed out again (smallest block that fits and is not more than twice
+// the request); all use is ordered on the context's single stream.
+struct BlockCache {
+    std::mutex m;
+    std::vector<std::pair<void *, size_t>> blocks;
+    cudaStream_t stream = nullptr;
+    bool closed = false;
+    static constexpr size_t BIG_BLOCK = (size_t)16 << 20;
+    void *take(size_t bytes, size_t *got) {
+        std::lock_guard<std::mutex> lock(m);
+        int best = -1;
+        for (int i = 0; i < (int)blocks.size(); i++)
+            if (blocks[i].second >= bytes && blocks[i].second <= 2 * bytes && (best < 0 || blocks[i].second < blocks[best].second)) best = i;
+        if (best < 0) return nullptr;
+        void *p = blocks[best].first;
+        *got = blocks[best].second;
+        blocks.erase(blocks.begin() + best);
+        return p;
+    }
+    bool give(void *p, size_t bytes) {
+        std::lock_guard<std::mutex> lock(m);
+        if (closed) return false;
+        blocks.emplace_back(p, bytes);
+        // bounded: the oldest parked blocks go back to the pool beyond 48 blocks / 96 GB
+        size_t held = 0;
+        for (auto &b : blocks) held += b.second;
+        while (!blocks.empty() && (blocks.size() > 48 || held > ((size_t)96 << 30))) {
+            held -= blocks.front().second;
+            cudaFreeAsync(blocks.front().first, stream);
+            blocks.erase(blocks.begin());
+        }
+        return true;
+    }
+    void drain() {
+        std::lock_guard<std::mutex> lock(m);
+        for (auto &b : blocks) cudaFreeAsync(b.first, stream);
+        blocks.clear();
+        closed = true;
+    }
+};
+inline std::mutex g_cache_registry_mutex;
+inline std::vector<std::shared_ptr<BlockCache>> g_cache_registry;
+inline std::shared_ptr<BlockCache> cache_of_stream(cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(g_cache_registry_mutex);
+    for (auto &c : g_cache_registry)
+        if (c->stream == s) return c;
+    return nullptr;
+}
+inline void register_cache(cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(g_cache_registry_mutex);
+    auto c = std::make_shared<BlockCache>();
+    c->stream = s;
+    g_cache_registry.push_back(c);
+}
+inline void unregister_cache(cudaStream_t s) {
+    std::shared_ptr<BlockCache> c;
+    {
+        std::lock_guard<std::mutex> lock(g_cache_registry_mutex);
+        for (size_t i = 0; i < g_cache_registry.size(); i++)
+            if (g_cache_registry[i]->stream == s) {
+                c = g_cache_registry[i];
+                g_cache_registry.erase(g_cache_registry.begin() + i);
+                break;
+            }
+    }
+    if (c) c->drain();
+}
+
+// RAII device buffer (cudaMallocAsync / cudaFreeAsync, large blocks through the context's BlockCache); zero-size
+// allocations are nullptr.
 template <typename T> struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
+    size_t block_bytes = 0;             // size of the underlying block when it came from / goes to the cache
+    std::shared_ptr<BlockCache> cache;  // where a large block returns to
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), block_bytes(o.block_bytes), cache(std::move(o.cache)) {
+        o.p = nullptr;
+        o.n = 0;
+        o.block_bytes = 0;
+    }
     DevBuf &operator=(DevBuf &&o) noexcept {
         if (this != &o) {
             release();
             p = o.p;
             n = o.n;
+            block_bytes = o.block_bytes;
+            cache = std::move(o.cache);
             o.p = nullptr;
             o.n = 0;
+            o.block_bytes = 0;
         }
         return *this;
     }
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFreeAsync(p, g_alloc_stream);
+        if (p) {
+            if (!(cache && block_bytes && cache->give(p, block_bytes))) cudaFreeAsync(p, g_alloc_stream);
+        }
         p = nullptr;
         n = 0;
+        block_bytes = 0;
+        cache.reset();
     }
     int alloc(size_t count) {
         release();
         if (count == 0) return VGA_OK;
-        VGA_CUDA(cudaMallocAsync((void **)&p, count * sizeof(T), g_alloc_stream));
+        const size_t bytes = count * sizeof(T);
+        if (bytes >= BlockCache::BIG_BLOCK) {
+            cache = cache_of_stream(g_alloc_stream);
+            if (cache) {
+                size_t got = 0;
+                if (void *q = cache->take(bytes, &got)) {
+                    p = (T *)q;
+                    n = count;
+                    block_bytes = got;
+                    return VGA_OK;
+                }
+                block_bytes = bytes;
+            }
+        }
+        VGA_CUDA(cudaMallocAsync((void **)&p, bytes, g_alloc_stream));
         n = count;
         return VGA_OK;
     }
@@ -142,6 +244,7 @@ struct Options {
                                  // tests force several passes on small plans with it
     int64_t bfs_chunk = 0;       // 64-source words in flight; 0 = auto from free memory
     int64_t sieve_mode = 1;      // 1: thread-per-(source,octant) kernel + warp kernel for overflow, 0: warp kernel
+    int64_t sieve_thread_cap = 0; // thread kernel capacity: 0 = 8 gaps / 24 blocks per task, 1 = 16 / 48
     int64_t sieve_gcap = 48;     // shared-memory gap capacity per warp
     int64_t sieve_bcap = 192;    // shared-memory block capacity per warp
     int64_t sieve_big_gcap = 4096;
@@ -152,8 +255,8 @@ struct Options {
     int64_t pull_alpha = 1;      // bottom-up step when (frontier out-nodes + 2n) * alpha > (open vertices' in-nodes + n) * beta
     int64_t pull_beta = 1;
     int64_t bfs_order = 2;       // 0: x-major ordinals, 1: 8x8 tiles in Morton order, 2: + wall-respecting floods
-    int64_t bfs_l2_words = 0;    // auto word width: largest W whose randomly accessed state (2 pyramids of n*W words) fits
-                                 // this many MB of L2; 0 = 96
+    int64_t bfs_coop = 0;        // W >= 4: W/2 lanes share a node, 16 bytes each (k_push_nodes_coop / k_pull_nodes_coop)
+    int64_t bfs_wide_nodes = 384; // auto word width: 4 words from this many pyramid nodes per out-row on average, else 2
 };
 
 }  // namespace vga
@@ -214,7 +317,7 @@ struct vga_graph {
     // offsets f_nodeptr / t_nodeptr.  The BFS reads only the node lists.
     vga::DevBuf<uint64_t> f_runptr, t_runptr;    // [n+1]
     vga::DevBuf<uint2> f_runs, t_runs;
-    int64_t f_nruns = 0, t_nruns = 0;
+    int64_t f_nruns = 0, t_nruns = 0, f_nnodes = 0, t_nnodes = 0;
     bool has_fwd_runs = false, has_runs = false;
     bool has_shard_runs = false;                 // f_runs hold the rows [src_begin, src_end) of a shard only
     vga::DevBuf<uint64_t> f_nodeptr, t_nodeptr;  // [n+1]

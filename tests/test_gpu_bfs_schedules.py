@@ -49,6 +49,24 @@ def test_schedules_vs_oracle(name, radius, mode, words, order):
     c.close()
 
 
+@pytest.mark.parametrize("name", ["oblique:30:30:7", "office:64:64:1", "room:24:24:1+holes"])
+@pytest.mark.parametrize("radius", [-1, 2])
+@pytest.mark.parametrize("mode,words", [(0, 4), (1, 4), (2, 4), (0, 8), (1, 8), (2, 8)])
+def test_lane_cooperative_kernels_vs_oracle(name, radius, mode, words):
+    """bfs_coop = 1: W/2 lanes share a pyramid node, 16 bytes each (k_push_nodes_coop / k_pull_nodes_coop)."""
+    flat, og = oracle_for(name)
+    c = capi.Context(0)
+    for k, v in (("bfs_coop", 1), ("bfs_mode", mode), ("bfs_words", words)):
+        c.set_option(k, v)
+    g = c.build(flat)
+    tn, td, dist, used = g.global_ints(radius)
+    otn, otd, odist, onl = og.global_ints(radius, maxl=max(dist.shape[1], 8))
+    L = dist.shape[1]
+    assert np.array_equal(tn, otn) and np.array_equal(td, otd)
+    assert np.array_equal(dist, odist[:, :L]) and not odist[:, L:].any()
+    c.close()
+
+
 @pytest.mark.parametrize("name", ["oblique:30:30:7", "office:64:64:1"])
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_whole_map_every_source(name, mode):
