@@ -194,7 +194,7 @@ def main():
     ap.add_argument("--bfs-stride", type=int, default=0,
                     help="BFS sources = every stride-th group of 512 sources of the batch order (0 = 4 for C5, 1 otherwise)")
     ap.add_argument("--local-cells", type=int, default=4096,
-                    help="VGA local on this many cells per step, reported separately (0 = off; 1 GPU only)")
+                    help="VGA local on this many cells per step (split over the ranks), reported separately (0 = off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm")
     ap.add_argument("--cpu-sources-per-core", type=int, default=1)
@@ -260,22 +260,7 @@ def main():
 
     def replicate(g, st):
         """N > 1: the run-length rows of every rank's shard, broadcast straight into the library's final allocation."""
-        rp_ptr, runs_ptr, nr = g.device_runs()
-        deg_ptr = g.device_degrees()
-        rows = hi - lo
-        sizes = multi.exchange_sizes(rows, nr, dist, world, dev)
-        total_runs = sum(s[1] for s in sizes)
-        full, f_rp, f_runs, f_deg = ctx.graph_runs_alloc(n, g.ghosts, total_runs)
-        out = (multi.wrap(f_rp, (n + 1) * 8, torch.int64, dev), multi.wrap(f_runs, max(total_runs, 1) * 8, torch.int64, dev),
-               multi.wrap(f_deg, max(n, 1) * 4, torch.int32, dev))
-        multi.allgather_runs(multi.wrap(rp_ptr, (rows + 1) * 8, torch.int64, dev),
-                             multi.wrap(runs_ptr, max(nr, 1) * 8, torch.int64, dev),
-                             multi.wrap(deg_ptr, max(rows, 1) * 4, torch.int32, dev), sizes, dist, rank, world, out=out)
-        torch.cuda.synchronize(dev)
-        full.runs_commit()
-        full.set_cell_refs(g.cell_refs())  # coordinates -> spatially coherent BFS batches
-        st["exchange_bytes"] = int(total_runs) * 8 + (n + 1) * 8 + n * 4
-        return full
+        return multi.replicate_graph(ctx, g, n, hi - lo, dist, rank, world, dev, st)
 
     # ---- the fixed BFS source subset (set-up, untimed): whole groups of the library's batch order, evenly spread
     stride = args.bfs_stride if args.bfs_stride > 0 else default_stride(args.workload)
@@ -296,8 +281,11 @@ def main():
         gs = picked[(len(picked) * r) // world:(len(picked) * (r + 1)) // world]
         counts.append(int(sum(min(GROUP, n - gi * GROUP) for gi in gs)))
     S = int(sum(counts))
-    local_cells = args.local_cells if world == 1 else 0
-    local_range = (max(0, n // 2 - local_cells // 2), min(n, max(0, n // 2 - local_cells // 2) + local_cells))
+    local_cells = args.local_cells
+    l0 = max(0, n // 2 - local_cells // 2)
+    l1 = min(n, l0 + local_cells)
+    # every rank its share of the local-measure cells (the replicated run-length graph serves vga_local too)
+    local_range = (l0 + ((l1 - l0) * rank) // world, l0 + ((l1 - l0) * (rank + 1)) // world)
     log(f"BFS subset: {S} of {n} sources ({len(picked)} groups of {GROUP}, stride {stride}); set-up {time.time() - t_setup:.1f} s")
 
     def step(grid_obj, st):
@@ -312,7 +300,7 @@ def main():
         tg = ctx.timing()
         t3 = time.perf_counter()
         tl = None
-        if local_cells > 0:
+        if local_cells > 0 and local_range[1] > local_range[0]:
             full.local_ints(local_range)
             tl = ctx.timing()
         t4 = time.perf_counter()
@@ -469,7 +457,7 @@ def main():
                bfs_sources=S, bfs_source_stride=stride,
                bfs_subset=f"every {stride}th group of {GROUP} sources of the library's spatial batch order (fixed, same for every N)",
                value_definition="1 / (t_graph/N + t_bfs/S): t_graph = makegraph + exchange + BFS row lists, t_bfs = BFS over the S sources; medians",
-               levels=int(st_res[0]["levels"]), l2="flushed between iterations (256 MB write)",
+               levels=int(st_res[0]["levels"]), bfs_batch_sources=64 * int(st_res[0]["bfs_timing"].get("batch_words", 0)), l2="flushed between iterations (256 MB write)",
                parallelism=f"makegraph rows and BFS sources sharded x{world}; graph replicated as run-length rows")
     if args.opt:
         cfg["options"] = dict(kv.split("=") for kv in args.opt)
@@ -485,8 +473,8 @@ def main():
                    "sieve_kernels_ms": R["sieve_main_ms"], "makegraph_kernels_ms": R["build_kernel_ms"],
                    "bfs_level_kernels_ms": R["bfs_main_ms"],
                    "local_ms": R["local_ms"] if local_cells > 0 else None,
-                   "local_cells": (local_range[1] - local_range[0]) if local_cells > 0 else 0,
-                   "local_cells_per_s": ((local_range[1] - local_range[0]) / (R["local_ms"] * 1e-3)) if local_cells > 0 and R["local_ms"] > 0 else None,
+                   "local_cells": (l1 - l0) if local_cells > 0 else 0,
+                   "local_cells_per_s": ((l1 - l0) / (R["local_ms"] * 1e-3)) if local_cells > 0 and R["local_ms"] > 0 else None,
                    "ranges": R["stage_ranges"]},
         "e2e": {"value": val_e2e, "unit": UNIT, "ms_per_step": E["step_ms"], "full_job_ms_extrapolated": full_ms_e2e,
                 "h2d_bytes_per_step": int(flat.input_bytes()), "d2h_bytes_per_step": int(E["d2h_bytes"]),

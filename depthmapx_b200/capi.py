@@ -27,7 +27,8 @@ class VgaGrid(C.Structure):
 class VgaTiming(C.Structure):
     _fields_ = [("h2d_ms", C.c_double), ("kernel_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("main_kernel_ms", C.c_double), ("launches", C.c_int64), ("main_launches", C.c_int64),
-                ("algo_bytes", C.c_double), ("algo_bytes_csr", C.c_double), ("prep_ms", C.c_double)]
+                ("algo_bytes", C.c_double), ("algo_bytes_csr", C.c_double), ("prep_ms", C.c_double),
+                ("batch_words", C.c_int64)]
 
 
 ABI_SYMBOLS = [

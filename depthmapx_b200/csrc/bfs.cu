@@ -997,6 +997,7 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources,
     const int64_t n = g->n;
     Timing &tm = ctx->timing;
     const int bfs_mode = (int)ctx->opt.bfs_mode;
+    tm.batch_words = W;
     StageTimer kt(ctx, 0, &tm.kernel_ms);
     StageTimer mt(ctx, 2, &tm.main_kernel_ms);
     StageTimer dt(ctx, 4, &tm.d2h_ms);

@@ -210,6 +210,7 @@ int vga_ctx_timing(const vga_ctx *ctx, vga_timing *out) {
     out->algo_bytes = ctx->timing.algo_bytes;
     out->algo_bytes_csr = ctx->timing.algo_bytes_csr;
     out->prep_ms = ctx->timing.prep_ms;
+    out->batch_words = ctx->timing.batch_words;
     return VGA_OK;
 }
 

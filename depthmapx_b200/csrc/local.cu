@@ -110,7 +110,7 @@ __global__ void k_control(int64_t n, const uint64_t *rowptr, const uint32_t *adj
     control[v - src_begin] = c;
 }
 
-// ---- run-length variant (default) ---------------------------------------------------------------------------------
+// ---- run-length variant (local_mode = 3; the kernel for graphs that hold runs only) ---------------------------------------------------------------------------------
 // The same per-cell bitmaps, fed by RUNS instead of entries: a neighbour row u is a short list of (first ordinal, length)
 // pairs (vga_graph::f_runs, ~35 cells per run on urban plans), |iter(N(u)) n N(v)| is a handful of masked popcounts on the
 // bitmap of N(v) and the union a handful of word ORs -- 10-100x fewer operations than one bit test per entry, and the
@@ -558,10 +558,12 @@ int run_local(vga_ctx *ctx, vga_graph *g, int64_t src_begin, int64_t src_end, in
     const int64_t ns = std::max<int64_t>(0, src_end - src_begin);
     if (ns == 0) return VGA_OK;
     {
-        // auto: the run-length kernel (also the only one for a graph that holds runs only); 0 / 1 select the entry kernels
+        // auto (measured on B200, profiles/README.md): the bit-parallel batches over entries while the graph holds entries
+        // (C1 11 / 58 / 120 ms, C5 slice 39 / 54 ms for batches / run-length / entry bitmaps); a graph that holds runs only
+        // (the replicated graph of a multi-GPU run) is served by the run-length kernel
         int64_t lm = ctx->opt.local_mode;
-        if (lm == 2 || lm == 3 || g->entries == 0) return run_local_runs(ctx, g, src_begin, src_end, cluster, k, total, control);
-        if (lm == 1) return run_local_batched(ctx, g, src_begin, src_end, cluster, k, total, control);
+        if (lm == 3 || g->entries == 0) return run_local_runs(ctx, g, src_begin, src_end, cluster, k, total, control);
+        if (lm == 1 || lm == 2) return run_local_batched(ctx, g, src_begin, src_end, cluster, k, total, control);
     }
     Timing &tm = ctx->timing;
     StageTimer kt(ctx, 0, &tm.kernel_ms);

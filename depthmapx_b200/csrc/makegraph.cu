@@ -1204,11 +1204,12 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t sr
     unsigned long long h_over = 0;
     int h_err = 0;
 
+    const int64_t thread_cap = ctx->opt.sieve_thread_cap >= 0 ? ctx->opt.sieve_thread_cap : (N >= 200000 ? 1 : 0);
     kt.start();
     mt.start();
     // ---- pass 1: count
     if (ntasks > 0) {
-        if (ctx->opt.sieve_mode == 1 && ctx->opt.sieve_thread_cap == 1)
+        if (ctx->opt.sieve_mode == 1 && thread_cap == 1)
             k_sieve_thread<false, 16, 48><<<blocks_for(ntasks, TT), TT, 0, st>>>(a, nsrc);
         else if (ctx->opt.sieve_mode == 1)
             k_sieve_thread<false, 8, 24><<<blocks_for(ntasks, TT), TT, 0, st>>>(a, nsrc);
@@ -1321,7 +1322,7 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t sr
         e.e_ref = e_ref.p;
         e.e_bin = e_bin.p;
         mt.start();
-        if (ctx->opt.sieve_mode == 1 && ctx->opt.sieve_thread_cap == 1)
+        if (ctx->opt.sieve_mode == 1 && thread_cap == 1)
             k_sieve_thread<true, 16, 48><<<blocks_for(ns * 8, TT), TT, 0, st>>>(e, ns);
         else if (ctx->opt.sieve_mode == 1)
             k_sieve_thread<true, 8, 24><<<blocks_for(ns * 8, TT), TT, 0, st>>>(e, ns);

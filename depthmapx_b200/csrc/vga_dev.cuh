@@ -231,6 +231,7 @@ template <typename T> struct WsBuf {
 
 struct Timing {
     double h2d_ms = 0, kernel_ms = 0, d2h_ms = 0, main_kernel_ms = 0, algo_bytes = 0, algo_bytes_csr = 0, prep_ms = 0;
+    int64_t batch_words = 0;
     int64_t launches = 0, main_launches = 0;
 };
 
@@ -238,13 +239,16 @@ struct Timing {
 struct Options {
     int64_t bfs_mode = 2;        // 0 top-down (push) only, 1 bottom-up (pull) only, 2 direction-optimising hybrid
     int64_t bfs_words = 0;       // 64-bit words per vertex and batch (a batch = 64*words sources): 1, 2, 4, 8; 0 = auto
-    int64_t local_mode = 2;      // 2 / 3: one CTA per cell, bitmaps fed by run-length rows (default); 0: the same fed by entries;
-                                 // 1: bit-parallel batches of 64 cells over entries
+    int64_t local_mode = 2;      // 2: auto (1 while the graph holds entries, 3 for a runs-only graph); 1: bit-parallel batches of
+                                 // 64 cells over entries; 3: one CTA per cell, bitmaps fed by run-length rows; 0: the same fed
+                                 // by entries
     int64_t local_span = 0;      // run-length local kernel: bits of the vertex universe per pass (0 = what fits shared memory);
                                  // tests force several passes on small plans with it
     int64_t bfs_chunk = 0;       // 64-source words in flight; 0 = auto from free memory
     int64_t sieve_mode = 1;      // 1: thread-per-(source,octant) kernel + warp kernel for overflow, 0: warp kernel
-    int64_t sieve_thread_cap = 0; // thread kernel capacity: 0 = 8 gaps / 24 blocks per task, 1 = 16 / 48
+    int64_t sieve_thread_cap = -1; // thread kernel capacity: 0 = 8 gaps / 24 blocks per task, 1 = 16 / 48, -1 = auto (1 from
+                                 // 200,000 cells: on the 10^6-cell plan 30 % of the tasks exceed 8 / 24 and fall back to the
+                                 // warp kernel, 4.8 % exceed 16 / 48: 1342 -> 1123 ms; small plans lose occupancy: 10.9 -> 13.4 ms)
     int64_t sieve_gcap = 48;     // shared-memory gap capacity per warp
     int64_t sieve_bcap = 192;    // shared-memory block capacity per warp
     int64_t sieve_big_gcap = 4096;

@@ -106,6 +106,28 @@ def allgather_runs(runptr_local: torch.Tensor, runs_local: torch.Tensor, deg_loc
     return rp_full, runs_full, deg_full, total
 
 
+def replicate_graph(ctx, g, n: int, rows: int, dist, rank: int, world: int, device, stats=None):
+    """The run-length rows of every rank's shard `g` (rows [lo, lo + rows) of the n cells), broadcast straight into a
+    BFS / local graph allocated by the library (vga_graph_runs_alloc): one pass, no padding, no staging copy.  Returns the
+    replicated capi.Graph (no entries: it serves vga_global, vga_global_sources and vga_local)."""
+    rp_ptr, runs_ptr, nr = g.device_runs()
+    deg_ptr = g.device_degrees()
+    sizes = exchange_sizes(rows, nr, dist, world, device)
+    total_runs = sum(s[1] for s in sizes)
+    full, f_rp, f_runs, f_deg = ctx.graph_runs_alloc(n, g.ghosts, total_runs)
+    out = (wrap(f_rp, (n + 1) * 8, torch.int64, device), wrap(f_runs, max(total_runs, 1) * 8, torch.int64, device),
+           wrap(f_deg, max(n, 1) * 4, torch.int32, device))
+    allgather_runs(wrap(rp_ptr, (rows + 1) * 8, torch.int64, device), wrap(runs_ptr, max(nr, 1) * 8, torch.int64, device),
+                   wrap(deg_ptr, max(rows, 1) * 4, torch.int32, device), sizes, dist, rank, world, out=out)
+    if device.type == "cuda":
+        torch.cuda.synchronize(device)
+    full.runs_commit()
+    full.set_cell_refs(g.cell_refs())  # coordinates -> spatially coherent BFS batches
+    if stats is not None:
+        stats["exchange_bytes"] = int(total_runs) * 8 + (n + 1) * 8 + n * 4
+    return full
+
+
 def gather_results(mine: torch.Tensor, counts, dist, rank: int, world: int, dst: int = 0):
     """mine: int64 [rows_r, width] per-source integers of this rank; returns [sum(counts), width] on dst (else None)."""
     mx = max(counts)

@@ -84,6 +84,7 @@ typedef struct {
                           kernels read (vga_global: 4 bytes per pyramid-node id of a run-length row) */
     double algo_bytes_csr; /* vga_global: the same model with 4-byte CSR entries (SURVEY.md 8d as written), else 0 */
     double prep_ms;    /* vga_global: one-time derivation of the BFS row lists of the graph (first call only) */
+    int64_t batch_words; /* vga_global: 64-bit words per vertex and batch used (a batch = 64 * words sources) */
 } vga_timing;
 
 const char *vga_last_error(void);

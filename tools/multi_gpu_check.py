@@ -1,6 +1,6 @@
-"""Multi-GPU parity check (run under torchrun on N GPUs): sharded makegraph + all-gather + partitioned
-BFS must equal the single-GPU result bit for bit."""
-import os, sys, time
+"""Multi-GPU parity check (run under torchrun on N GPUs): sharded makegraph (work-balanced source ranges) + exchange of
+the run-length rows + partitioned BFS / local must equal the single-GPU result bit for bit."""
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
@@ -15,36 +15,41 @@ name = sys.argv[1] if len(sys.argv) > 1 else "office:128:128:5"
 flat = capi.prepare(plans.by_name(name))
 ctx = capi.Context(lr)
 n = flat.n_filled
-lo, hi = multi.partition(n, world)[rank]
+parts = multi.partition_by_work(multi.estimate_source_work(flat.state, flat.cols, flat.rows), world)
+lo, hi = parts[rank]
 g = ctx.build(flat, (lo, hi))
-rp_ptr, adj_ptr, ne = g.device_rows()
-rp_local = multi.wrap(rp_ptr, (hi - lo + 1) * 8, torch.int64, dev)
-adj_local = multi.wrap(adj_ptr, ne * 4, torch.int32, dev)[:ne]
-rp_full, adj_full, total = multi.allgather_rows(rp_local, adj_local, dist, world)
-torch.cuda.synchronize(dev)
-full = ctx.graph_from_device_rows(n, g.ghosts, rp_full.data_ptr(), adj_full.data_ptr(), total)
-full.set_cell_refs(g.cell_refs())
-tn, td, hist, used = full.global_ints(-1, (lo, hi))
+full = multi.replicate_graph(ctx, g, n, hi - lo, dist, rank, world, dev)
+order = full.batch_order()
+a, b = multi.partition(n, world)[rank]
+mine = order[a:b].astype(np.int64)
+tn, td, hist, used = full.global_ints(-1, sources=mine)
 L = 32
-pack = np.zeros((hi - lo, L + 2), np.int64)
-pack[:, 0] = tn; pack[:, 1] = td; pack[:, 2:2 + min(L, hist.shape[1])] = hist[:, :L]
+pack = np.zeros((len(mine), L + 3), np.int64)
+pack[:, 0] = mine; pack[:, 1] = tn; pack[:, 2] = td; pack[:, 3:3 + min(L, hist.shape[1])] = hist[:, :L]
 counts = [e - s for s, e in multi.partition(n, world)]
 res = multi.gather_results(torch.from_numpy(pack).to(dev), counts, dist, rank, world)
-cl, kk, tot, ctl = full.local_ints((lo, min(hi, lo + 64)))
+cells = (lo, min(hi, lo + 64))
+cl, kk, tot, ctl = full.local_ints(cells)
 ok = True
+single = ctx.build(flat)
+scl, skk, stot, sctl = single.local_ints(cells)
+ok &= bool(np.array_equal(cl, scl) and np.array_equal(kk, skk) and np.array_equal(tot, stot) and np.array_equal(ctl, sctl))
+srp, scol, sb, sacc = single.csr()
+mrp, mcol, mb, macc = g.csr()
+ok &= bool(np.array_equal(mrp + srp[lo], srp[lo:hi + 1]) and np.array_equal(mcol, scol[int(srp[lo]):int(srp[hi])])
+           and np.array_equal(mb, sb[int(srp[lo]):int(srp[hi])]))
 if rank == 0:
     res = res.cpu().numpy()
-    single = ctx.build(flat)
     stn, std_, shist, sused = single.global_ints(-1)
-    ok &= bool(np.array_equal(res[:, 0], stn) and np.array_equal(res[:, 1], std_))
+    o = np.argsort(res[:, 0])
+    ok &= bool(np.array_equal(res[o, 0], np.arange(n)) and np.array_equal(res[o, 1], stn) and np.array_equal(res[o, 2], std_))
     Lc = min(L, shist.shape[1])
-    ok &= bool(np.array_equal(res[:, 2:2 + Lc], shist[:, :Lc]))
-    srp, scol, sb, sacc = single.csr()
-    frp, fcol, fb, facc = full.csr()
-    ok &= bool(np.array_equal(srp, frp) and np.array_equal(scol, fcol) and np.array_equal(sb, fb) and np.array_equal(sacc, facc))
-    scl, skk, stot, sctl = single.local_ints((lo, min(hi, lo + 64)))
-    ok &= bool(np.array_equal(cl, scl) and np.array_equal(kk, skk) and np.array_equal(tot, stot) and np.array_equal(ctl, sctl))
-    print(f"multi-gpu check world={world} plan={name} N={n} E={total}: {'OK' if ok else 'MISMATCH'}", flush=True)
+    ok &= bool(np.array_equal(res[o, 3:3 + Lc], shist[:, :Lc]))
+flag = torch.tensor([1 if ok else 0], device=dev)
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+ok = bool(flag.item())
+if rank == 0:
+    print(f"multi-gpu check world={world} plan={name} N={n} parts={parts}: {'OK' if ok else 'MISMATCH'}", flush=True)
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
