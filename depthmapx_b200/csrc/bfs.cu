@@ -1003,14 +1003,19 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources,
     StageTimer dt(ctx, 4, &tm.d2h_ms);
     StageTimer pt(ctx, 6, &tm.prep_ms);
 
+    const bool dbg = std::getenv("VGA_DEBUG_TIMING") != nullptr;
+    auto wall = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double w0 = wall();
     pt.start();
     VGA_TRY(ensure_bfs_lists(ctx, g, bfs_mode != 0));
     pt.stop();
     const PyrLayout pl = pyr_layout(n);
+    const double w1 = wall();
 
     std::vector<int32_t> order;
     std::vector<int64_t> position;
     VGA_TRY(source_order(ctx, g, sources, src_begin, nsrc, order, position));
+    const double w2 = wall();
     DevBuf<int32_t> d_order;
     VGA_TRY(d_order.alloc((size_t)nsrc));
     VGA_CUDA(cudaMemcpyAsync(d_order.p, order.data(), sizeof(int32_t) * nsrc, cudaMemcpyHostToDevice, st));
@@ -1054,8 +1059,8 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources,
     d.f_nodes = g->f_nodes.p;
     d.t_ptr = bfs_mode != 0 ? g->t_nodeptr.p : nullptr;
     d.t_nodes = bfs_mode != 0 ? g->t_nodes.p : nullptr;
-    d.rowptr = g->entries > 0 ? g->rowptr.p : nullptr;
-    d.deg = g->entries > 0 ? nullptr : g->deg.p;
+    d.rowptr = !g->runs_only ? g->rowptr.p : nullptr;
+    d.deg = g->runs_only ? g->deg.p : nullptr;
     d.visited = visited;
     d.frontier = frontier;
     d.next = next;
@@ -1079,6 +1084,8 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources,
     std::vector<u64> h_valid;
     std::vector<int> ones;
     const int64_t cstride = chunk * W * 64;  // counts per level
+    const double w3 = wall();
+    double w_unpack = 0.0;
 
     for (int64_t b0 = 0; b0 < nbatch; b0 += chunk) {
         const int64_t cb = std::min<int64_t>(chunk, nbatch - b0);
@@ -1120,6 +1127,7 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources,
         h_counts.resize((size_t)nlev * cstride);
         VGA_CUDA(cudaMemcpyAsync(h_counts.data(), counts.p, sizeof(int32_t) * (size_t)nlev * cstride, cudaMemcpyDeviceToHost, st));
         dt.stop();
+        const double wu0 = wall();
         for (int64_t i = 0; i < cs; i++) {
             const int64_t o = position[(size_t)(first + i)];
             const int64_t wi = i >> 6;  // word index within the chunk = b*W + j
@@ -1138,9 +1146,14 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources,
             if (total_nodes) total_nodes[o] = (int32_t)tn;
             if (total_depth) total_depth[o] = td;
         }
+        w_unpack += wall() - wu0;
         if (ctx->progress) ctx->progress(ctx->user, std::min<int64_t>(nsrc, (b0 + cb) * W * 64), nsrc);
     }
     if (levels_used) *levels_used = deepest;
+    if (dbg)
+        fprintf(stderr, "[vga_global] W=%d chunk=%lld: row lists %.2f ms, source order %.2f ms, state set-up %.2f ms, chunks %.2f ms "
+                "(level kernels %.2f, result unpack on the host %.2f)\n", W, (long long)chunk, w1 - w0, w2 - w1, w3 - w2, wall() - w3,
+                tm.main_kernel_ms, w_unpack);
     {
         u64 hw[4] = {0, 0, 0, 0};
         VGA_CUDA(cudaMemcpy(hw, work.p, sizeof(hw), cudaMemcpyDeviceToHost));
@@ -1153,7 +1166,7 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources,
                 VGA_CUDA(cudaMemcpy(&a[0], g->f_nodeptr.p + src_begin, sizeof(uint64_t), cudaMemcpyDeviceToHost));
                 VGA_CUDA(cudaMemcpy(&a[1], g->f_nodeptr.p + src_begin + nsrc, sizeof(uint64_t), cudaMemcpyDeviceToHost));
                 src_nodes = (double)(a[1] - a[0]);
-                if (g->entries > 0) {
+                if (!g->runs_only) {
                     VGA_CUDA(cudaMemcpy(&b[0], g->rowptr.p + src_begin, sizeof(uint64_t), cudaMemcpyDeviceToHost));
                     VGA_CUDA(cudaMemcpy(&b[1], g->rowptr.p + src_begin + nsrc, sizeof(uint64_t), cudaMemcpyDeviceToHost));
                     src_edges = (double)(b[1] - b[0]);
@@ -1162,7 +1175,7 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources,
                 fp.resize((size_t)n + 1);
                 VGA_CUDA(cudaMemcpy(fp.data(), g->f_nodeptr.p, sizeof(uint64_t) * (n + 1), cudaMemcpyDeviceToHost));
                 for (int64_t i = 0; i < nsrc; i++) src_nodes += (double)(fp[(size_t)sources[i] + 1] - fp[(size_t)sources[i]]);
-                if (g->entries > 0) {
+                if (!g->runs_only) {
                     VGA_CUDA(cudaMemcpy(fp.data(), g->rowptr.p, sizeof(uint64_t) * (n + 1), cudaMemcpyDeviceToHost));
                     for (int64_t i = 0; i < nsrc; i++) src_edges += (double)(fp[(size_t)sources[i] + 1] - fp[(size_t)sources[i]]);
                 }
@@ -1376,16 +1389,17 @@ int run_global(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources, i
     if (nsrc <= 0) return VGA_OK;
     int words = (int)ctx->opt.bfs_words;
     if (words <= 0) {
-        // auto (measured on B200, profiles/README.md): two words (128 sources) per batch; four when the out-rows are long
-        // (from ~384 pyramid nodes per row, e.g. the halls of the gallery plan: 46 vs 52 ms on a C4 slice).  Wider batches
-        // lose more to the lower coherence of their sources than they gain (C5: 266 / 301 / 437 ms for 2 / 4 / 8 words).
+        // auto (measured on B200, profiles/README.md): four words (256 sources) per batch with the lane-cooperative kernels
+        // (10^6-cell bench subset: level kernels 1792 / 1508 / 1687 ms for 2 / 4 / 8 words); eight when the out-rows are long
+        // (from ~384 pyramid nodes per row, the halls of the gallery plan).  Without the cooperative kernels two / four.
         {
             StageTimer pt(ctx, 6, &ctx->timing.prep_ms);
             pt.start();
             VGA_TRY(ensure_bfs_lists(ctx, g, ctx->opt.bfs_mode != 0));
             pt.stop();
         }
-        words = (n > 0 && g->f_nnodes >= ctx->opt.bfs_wide_nodes * n) ? 4 : 2;
+        const bool wide = n > 0 && g->f_nnodes >= ctx->opt.bfs_wide_nodes * n;
+        words = ctx->opt.bfs_coop ? (wide ? 8 : 4) : (wide ? 4 : 2);
     }
     while (words > 1 && nsrc <= 64 * (words / 2)) words >>= 1;
     switch (words) {

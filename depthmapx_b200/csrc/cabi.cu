@@ -588,6 +588,7 @@ int vga_graph_runs_alloc(vga_ctx *ctx, int64_t n_cells, int64_t n_ghosts, int64_
     g->src_begin = 0;
     g->src_end = n_cells;
     g->entries = 0;
+    g->runs_only = true;
     VGA_TRY(g->f_runptr.alloc((size_t)n_cells + 1));
     VGA_TRY(g->f_runs.alloc((size_t)n_runs + 1));
     VGA_TRY(g->deg.alloc((size_t)n_cells + 1));
@@ -602,7 +603,7 @@ int vga_graph_runs_alloc(vga_ctx *ctx, int64_t n_cells, int64_t n_ghosts, int64_
 }
 
 int vga_graph_runs_commit(vga_graph *g) {
-    if (!g || g->entries != 0 || !g->f_runptr.p) return VGA_ERR_INVALID;
+    if (!g || !g->runs_only || !g->f_runptr.p) return VGA_ERR_INVALID;
     g->has_fwd_runs = true;
     return VGA_OK;
 }
@@ -634,7 +635,8 @@ int vga_graph_from_device_runs(vga_ctx *ctx, int64_t n_cells, int64_t n_ghosts, 
     g->ghosts = n_ghosts;
     g->src_begin = 0;
     g->src_end = n_cells;
-    g->entries = 0;  // no entry rows: this graph serves vga_global / vga_global_sources only
+    g->entries = 0;  // no entry rows: this graph serves vga_global / vga_global_sources / vga_local only
+    g->runs_only = true;
     VGA_TRY(g->f_runptr.alloc((size_t)n_cells + 1));
     VGA_TRY(g->f_runs.alloc((size_t)n_runs + 1));
     VGA_CUDA(cudaMemcpyAsync(g->f_runptr.p, d_runptr, sizeof(uint64_t) * (n_cells + 1), cudaMemcpyDeviceToDevice, st));

@@ -482,7 +482,7 @@ int run_local_runs(vga_ctx *ctx, vga_graph *g, int64_t src_begin, int64_t src_en
     StageTimer pt(ctx, 6, &tm.prep_ms);
     pt.start();
     VGA_TRY(ensure_fwd_runs(ctx, g));
-    if (g->entries == 0 && !g->deg.p) {
+    if (g->runs_only && !g->deg.p) {
         set_error("vga_local: a graph adopted from runs needs the per-row entry counts (d_degree)");
         return VGA_ERR_INVALID;
     }
@@ -526,8 +526,8 @@ int run_local_runs(vga_ctx *ctx, vga_graph *g, int64_t src_begin, int64_t src_en
     tm.main_launches++;
     VGA_CUDA(cudaGetLastError());
     mt.stop();
-    k_control_runs<<<(unsigned)((ns + 127) / 128), 128, 0, st>>>(n, g->f_runptr.p, g->f_runs.p, g->entries > 0 ? g->rowptr.p : nullptr,
-                                                               g->entries > 0 ? nullptr : g->deg.p, src_begin, src_end, d_control.p);
+    k_control_runs<<<(unsigned)((ns + 127) / 128), 128, 0, st>>>(n, g->f_runptr.p, g->f_runs.p, !g->runs_only ? g->rowptr.p : nullptr,
+                                                               !g->runs_only ? nullptr : g->deg.p, src_begin, src_end, d_control.p);
     tm.launches++;
     VGA_CUDA(cudaGetLastError());
     kt.stop();
@@ -562,7 +562,7 @@ int run_local(vga_ctx *ctx, vga_graph *g, int64_t src_begin, int64_t src_end, in
         // (C1 11 / 58 / 120 ms, C5 slice 39 / 54 ms for batches / run-length / entry bitmaps); a graph that holds runs only
         // (the replicated graph of a multi-GPU run) is served by the run-length kernel
         int64_t lm = ctx->opt.local_mode;
-        if (lm == 3 || g->entries == 0) return run_local_runs(ctx, g, src_begin, src_end, cluster, k, total, control);
+        if (lm == 3 || g->runs_only) return run_local_runs(ctx, g, src_begin, src_end, cluster, k, total, control);
         if (lm == 1 || lm == 2) return run_local_batched(ctx, g, src_begin, src_end, cluster, k, total, control);
     }
     Timing &tm = ctx->timing;

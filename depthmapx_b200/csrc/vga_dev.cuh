@@ -259,8 +259,10 @@ struct Options {
     int64_t pull_alpha = 1;      // bottom-up step when (frontier out-nodes + 2n) * alpha > (open vertices' in-nodes + n) * beta
     int64_t pull_beta = 1;
     int64_t bfs_order = 2;       // 0: x-major ordinals, 1: 8x8 tiles in Morton order, 2: + wall-respecting floods
-    int64_t bfs_coop = 0;        // W >= 4: W/2 lanes share a node, 16 bytes each (k_push_nodes_coop / k_pull_nodes_coop)
-    int64_t bfs_wide_nodes = 384; // auto word width: 4 words from this many pyramid nodes per out-row on average, else 2
+    int64_t bfs_coop = 1;        // W >= 4: W/2 lanes share a node, 16 bytes each (k_push_nodes_coop / k_pull_nodes_coop; measured
+                                 // on the 10^6-cell bench subset: level kernels 1792 ms at W = 2 -> 1508 ms at W = 4); 0 = one
+                                 // lane per node for every W
+    int64_t bfs_wide_nodes = 384; // auto word width: 8 words from this many pyramid nodes per out-row on average, else 4
 };
 
 }  // namespace vga
@@ -323,6 +325,7 @@ struct vga_graph {
     vga::DevBuf<uint2> f_runs, t_runs;
     int64_t f_nruns = 0, t_nruns = 0, f_nnodes = 0, t_nnodes = 0;
     bool has_fwd_runs = false, has_runs = false;
+    bool runs_only = false;                      // adopted from run-length rows: no entry rows, bins or statistics
     bool has_shard_runs = false;                 // f_runs hold the rows [src_begin, src_end) of a shard only
     vga::DevBuf<uint64_t> f_nodeptr, t_nodeptr;  // [n+1]
     vga::DevBuf<uint32_t> f_nodes, t_nodes;
