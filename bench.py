@@ -267,6 +267,7 @@ def main():
     g0 = ctx.build(dgrid, (lo, hi))
     full0 = replicate(g0, {}) if world > 1 else g0
     order = full0.batch_order()
+    list_sizes = full0.list_sizes()
     edges_total = g0.entries
     if world > 1:
         full0.free()
@@ -457,7 +458,7 @@ def main():
                bfs_sources=S, bfs_source_stride=stride,
                bfs_subset=f"every {stride}th group of {GROUP} sources of the library's spatial batch order (fixed, same for every N)",
                value_definition="1 / (t_graph/N + t_bfs/S): t_graph = makegraph + exchange + BFS row lists, t_bfs = BFS over the S sources; medians",
-               levels=int(st_res[0]["levels"]), bfs_batch_sources=64 * int(st_res[0]["bfs_timing"].get("batch_words", 0)), l2="flushed between iterations (256 MB write)",
+               row_lists=list_sizes, levels=int(st_res[0]["levels"]), bfs_batch_sources=64 * int(st_res[0]["bfs_timing"].get("batch_words", 0)), l2="flushed between iterations (256 MB write)",
                parallelism=f"makegraph rows and BFS sources sharded x{world}; graph replicated as run-length rows")
     if args.opt:
         cfg["options"] = dict(kv.split("=") for kv in args.opt)

@@ -39,7 +39,7 @@ ABI_SYMBOLS = [
     "vga_graph_node_stats", "vga_graph_set_noexpand", "vga_global", "vga_global_attributes", "vga_local", "vga_local_attributes", "vga_step_depth",
     "vga_graph_device_rows", "vga_graph_from_device_rows", "vga_global_sources", "vga_graph_batch_order",
     "vga_graph_device_runs", "vga_graph_from_device_runs", "vga_graph_runs_alloc", "vga_graph_runs_commit",
-    "vga_graph_device_degrees",
+    "vga_graph_device_degrees", "vga_graph_list_sizes",
 ]
 HOST_SYMBOLS = [
     "dmxh_last_error", "dmxh_map_create", "dmxh_map_destroy", "dmxh_map_grid", "dmxh_map_block_lines", "dmxh_map_fill",
@@ -104,6 +104,7 @@ def abi():
         L.vga_graph_runs_alloc.argtypes = [vp, i64, i64, i64, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
         L.vga_graph_runs_commit.argtypes = [vp]
         L.vga_graph_device_degrees.argtypes = [vp, vp, C.POINTER(vp)]
+        L.vga_graph_list_sizes.argtypes = [vp, vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
         _abi = L
     return _abi
 
@@ -374,6 +375,12 @@ class Graph:
         d = vp()
         check(abi().vga_graph_device_degrees(self.ctx.h, self.h, C.byref(d)))
         return d.value
+
+    def list_sizes(self):
+        """dict(out_runs, out_nodes, in_runs, in_nodes): sizes of the row lists the BFS reads."""
+        a, b, c, d = i64(), i64(), i64(), i64()
+        check(abi().vga_graph_list_sizes(self.ctx.h, self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return {"out_runs": a.value, "out_nodes": b.value, "in_runs": c.value, "in_nodes": d.value}
 
     def batch_order(self):
         """Ordinals of all N sources in the order vga_global batches them (spatially compact groups)."""

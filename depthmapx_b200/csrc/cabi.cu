@@ -549,6 +549,18 @@ int vga_global_sources(vga_ctx *ctx, const vga_graph *g, int radius, const int64
                       levels_used);
 }
 
+int vga_graph_list_sizes(vga_ctx *ctx, const vga_graph *g, int64_t *out_runs, int64_t *out_nodes, int64_t *in_runs, int64_t *in_nodes) {
+    if (!ctx || !g) return VGA_ERR_INVALID;
+    VGA_CUDA(cudaSetDevice(ctx->device));
+    g_alloc_stream = ctx->stream;
+    VGA_TRY(ensure_bfs_lists(ctx, const_cast<vga_graph *>(g), true));
+    if (out_runs) *out_runs = g->f_nruns;
+    if (out_nodes) *out_nodes = g->f_nnodes;
+    if (in_runs) *in_runs = g->t_nruns;
+    if (in_nodes) *in_nodes = g->t_nnodes;
+    return VGA_OK;
+}
+
 int vga_graph_batch_order(vga_ctx *ctx, const vga_graph *g, int32_t *order) {
     if (!ctx || !g || !order) return VGA_ERR_INVALID;
     VGA_CUDA(cudaSetDevice(ctx->device));

@@ -172,6 +172,10 @@ int vga_global_sources(vga_ctx *ctx, const vga_graph *g, int radius, const int64
  * 64*W entries are the spatially compact batches).  Lets a caller pick representative subsets of whole batches. */
 int vga_graph_batch_order(vga_ctx *ctx, const vga_graph *g, int32_t *order);
 
+/* Sizes of the row lists the BFS reads (derived on first use): runs and pyramid-node ids of the out-rows and in-rows. */
+int vga_graph_list_sizes(vga_ctx *ctx, const vga_graph *g, int64_t *out_runs, int64_t *out_nodes, int64_t *in_runs,
+                         int64_t *in_nodes);
+
 /* Formula stage (host, FP64 -> float exactly as AttributeRow::setValue stores them); -1 sentinels
  * as in the reference.  Any output may be NULL. */
 int vga_global_attributes(int64_t n, const int32_t *total_nodes, const int64_t *total_depth, const int32_t *dist,
