@@ -364,7 +364,10 @@ template <int W, int G> __global__ void __launch_bounds__(TPB) k_push_nodes_coop
     }
 }
 
-template <int W, int G> __global__ void __launch_bounds__(TPB) k_pull_nodes_coop(BfsDev d) {
+// U = node loads per lane between two early-exit checks (2 or 4): a vertex whose missing bits arrive at a later level scans
+// its whole in-row, and the group-wide OR + ballot per check is then pure overhead.  A lane whose own 16-byte slice is
+// complete skips its loads (with W >= 4 the slices are 64-source clusters of their own, often complete at different levels).
+template <int W, int G, int U> __global__ void __launch_bounds__(TPB) k_pull_nodes_coop(BfsDev d) {
     static_assert(W == 2 * G && G <= 8, "two words per lane, a node within an 8-lane group");
     const int b = blockIdx.y;
     if (!d.active[b] || d.mode[b] != 1) return;
@@ -406,22 +409,26 @@ template <int W, int G> __global__ void __launch_bounds__(TPB) k_pull_nodes_coop
                 const ulonglong2 vv = *reinterpret_cast<const ulonglong2 *>(vis + ww * W + 2 * g);
                 const u64 nd0 = valid.x & ~vv.x, nd1 = valid.y & ~vv.y;
                 u64 acc0 = 0ULL, acc1 = 0ULL;
-                for (uint64_t e = e0; e < e1; e += 2 * NPG) {
-                    const uint64_t ea = e + sub, eb = e + NPG + sub;
+                bool mine_done = (nd0 | nd1) == 0ULL;
+                for (uint64_t e = e0; e < e1; e += U * NPG) {
                     u64 x0 = 0ULL, x1 = 0ULL;
-                    uint32_t ca = 0, cb = 0;
-                    if (ea < e1) ca = __ldcs(d.t_nodes + ea);
-                    if (eb < e1) cb = __ldcs(d.t_nodes + eb);
-                    VGA_COUNT(npull_nodes, (g == 0) * ((ea < e1) + (eb < e1)));
-                    if (ea < e1) {
-                        const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>((ca < n ? fr + (int64_t)ca * W : pyr + (int64_t)(ca - n) * W) + 2 * g);
-                        x0 |= t.x;
-                        x1 |= t.y;
-                    }
-                    if (eb < e1) {
-                        const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>((cb < n ? fr + (int64_t)cb * W : pyr + (int64_t)(cb - n) * W) + 2 * g);
-                        x0 |= t.x;
-                        x1 |= t.y;
+                    if (!mine_done) {
+                        uint32_t c[U];
+#pragma unroll
+                        for (int i = 0; i < U; i++) {
+                            const uint64_t ei = e + (uint64_t)(i * NPG + sub);
+                            c[i] = ei < e1 ? __ldcs(d.t_nodes + ei) : 0xffffffffu;
+                        }
+#pragma unroll
+                        for (int i = 0; i < U; i++) {
+                            if (c[i] != 0xffffffffu) {
+                                VGA_COUNT(npull_nodes, g == 0);
+                                const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(
+                                    (c[i] < n ? fr + (int64_t)c[i] * W : pyr + (int64_t)(c[i] - n) * W) + 2 * g);
+                                x0 |= t.x;
+                                x1 |= t.y;
+                            }
+                        }
                     }
                     // OR over the lanes of the group that hold the same slice
 #pragma unroll
@@ -431,7 +438,7 @@ template <int W, int G> __global__ void __launch_bounds__(TPB) k_pull_nodes_coop
                     }
                     acc0 |= x0;
                     acc1 |= x1;
-                    const bool mine_done = ((acc0 & nd0) == nd0) && ((acc1 & nd1) == nd1);
+                    mine_done = ((acc0 & nd0) == nd0) && ((acc1 & nd1) == nd1);
                     if (__ballot_sync(gmask, !mine_done) == 0u) break;
                 }
                 if (sub == 0) {
@@ -828,8 +835,10 @@ int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, De
                 tm.main_launches++;
             }
             if constexpr (W >= 4 && W <= 16) {
-                if (ctx->opt.bfs_coop)
-                    k_pull_nodes_coop<W, W / 2><<<grid, TPB, 0, st>>>(d);
+                if (ctx->opt.bfs_coop && ctx->opt.bfs_pull_unroll == 4)
+                    k_pull_nodes_coop<W, W / 2, 4><<<grid, TPB, 0, st>>>(d);
+                else if (ctx->opt.bfs_coop)
+                    k_pull_nodes_coop<W, W / 2, 2><<<grid, TPB, 0, st>>>(d);
                 else
                     k_pull_nodes<W><<<grid, TPB, 0, st>>>(d);
             } else {
@@ -1390,8 +1399,8 @@ int run_global(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources, i
     int words = (int)ctx->opt.bfs_words;
     if (words <= 0) {
         // auto (measured on B200, profiles/README.md): four words (256 sources) per batch with the lane-cooperative kernels
-        // (10^6-cell bench subset: level kernels 1792 / 1508 / 1687 ms for 2 / 4 / 8 words); eight when the out-rows are long
-        // (from ~384 pyramid nodes per row, the halls of the gallery plan).  Without the cooperative kernels two / four.
+        // (10^6-cell bench subset: level kernels 1792 / 1508 / 1687 ms for 2 / 4 / 8 words; C4 slice 40.7 / 46.3 ms for 4 / 8).
+        // One lane per node (bfs_coop = 0): two words, four when the out-rows are long (from ~384 pyramid nodes per row).
         {
             StageTimer pt(ctx, 6, &ctx->timing.prep_ms);
             pt.start();
@@ -1399,7 +1408,7 @@ int run_global(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources, i
             pt.stop();
         }
         const bool wide = n > 0 && g->f_nnodes >= ctx->opt.bfs_wide_nodes * n;
-        words = ctx->opt.bfs_coop ? (wide ? 8 : 4) : (wide ? 4 : 2);
+        words = ctx->opt.bfs_coop ? 4 : (wide ? 4 : 2);
     }
     while (words > 1 && nsrc <= 64 * (words / 2)) words >>= 1;
     switch (words) {

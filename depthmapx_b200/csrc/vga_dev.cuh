@@ -262,7 +262,8 @@ struct Options {
     int64_t bfs_coop = 1;        // W >= 4: W/2 lanes share a node, 16 bytes each (k_push_nodes_coop / k_pull_nodes_coop; measured
                                  // on the 10^6-cell bench subset: level kernels 1792 ms at W = 2 -> 1508 ms at W = 4); 0 = one
                                  // lane per node for every W
-    int64_t bfs_wide_nodes = 384; // auto word width: 8 words from this many pyramid nodes per out-row on average, else 4
+    int64_t bfs_pull_unroll = 2; // node loads per lane between two early-exit checks of the bottom-up step: 2 or 4
+    int64_t bfs_wide_nodes = 384; // auto word width with bfs_coop = 0: 4 words from this many pyramid nodes per out-row, else 2
 };
 
 }  // namespace vga

@@ -34,9 +34,10 @@ def oracle_for(name):
 @pytest.mark.parametrize("mode,words,order", [(0, 1, 0), (1, 1, 1), (2, 1, 2), (0, 4, 2), (1, 2, 2), (2, 4, 2), (2, 8, 2),
                                               (1, 8, 0), (2, 0, 2)])
 def test_schedules_vs_oracle(name, radius, mode, words, order):
+    """One lane per node (bfs_coop = 0) for every width; words = 0 = the automatic choice with the default kernels."""
     flat, og = oracle_for(name)
     c = capi.Context(0)
-    for k, v in (("bfs_mode", mode), ("bfs_words", words), ("bfs_order", order)):
+    for k, v in (("bfs_mode", mode), ("bfs_words", words), ("bfs_order", order), ("bfs_coop", 1 if words == 0 else 0)):
         c.set_option(k, v)
     g = c.build(flat)
     tn, td, dist, used = g.global_ints(radius)
@@ -51,12 +52,13 @@ def test_schedules_vs_oracle(name, radius, mode, words, order):
 
 @pytest.mark.parametrize("name", ["oblique:30:30:7", "office:64:64:1", "room:24:24:1+holes"])
 @pytest.mark.parametrize("radius", [-1, 2])
-@pytest.mark.parametrize("mode,words", [(0, 4), (1, 4), (2, 4), (0, 8), (1, 8), (2, 8)])
-def test_lane_cooperative_kernels_vs_oracle(name, radius, mode, words):
-    """bfs_coop = 1: W/2 lanes share a pyramid node, 16 bytes each (k_push_nodes_coop / k_pull_nodes_coop)."""
+@pytest.mark.parametrize("mode,words,unroll", [(0, 4, 2), (1, 4, 2), (2, 4, 2), (0, 8, 2), (1, 8, 4), (2, 8, 2), (1, 4, 4), (2, 4, 4)])
+def test_lane_cooperative_kernels_vs_oracle(name, radius, mode, words, unroll):
+    """bfs_coop = 1 (default): W/2 lanes share a pyramid node, 16 bytes each (k_push_nodes_coop / k_pull_nodes_coop with 2 or
+    4 node loads per lane between early-exit checks)."""
     flat, og = oracle_for(name)
     c = capi.Context(0)
-    for k, v in (("bfs_coop", 1), ("bfs_mode", mode), ("bfs_words", words)):
+    for k, v in (("bfs_coop", 1), ("bfs_mode", mode), ("bfs_words", words), ("bfs_pull_unroll", unroll)):
         c.set_option(k, v)
     g = c.build(flat)
     tn, td, dist, used = g.global_ints(radius)
