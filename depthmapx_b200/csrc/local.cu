@@ -562,6 +562,23 @@ int run_local(vga_ctx *ctx, vga_graph *g, int64_t src_begin, int64_t src_end, in
         // (C1 11 / 58 / 120 ms, C5 slice 39 / 54 ms for batches / run-length / entry bitmaps); a graph that holds runs only
         // (the replicated graph of a multi-GPU run) is served by the run-length kernel
         int64_t lm = ctx->opt.local_mode;
+        if (lm == 4 || (lm == 2 && local_tc_applicable(g))) {
+            // dense graph: cluster / total as a masked int8 product on the tensor cores (C1: 16x faster than the batches
+            // with the library GEMM, profiles/r2_tc_probe_C1.json); control in sorted-row order as everywhere
+            if (g->runs_only) {
+                set_error("vga_local: the tensor-core kernel needs a graph with entry rows");
+                return VGA_ERR_INVALID;
+            }
+            VGA_TRY(run_local_tc(ctx, g, src_begin, src_end, cluster, k, total));
+            DevBuf<float> d_control;
+            VGA_TRY(d_control.alloc((size_t)ns));
+            k_control<<<(unsigned)((ns + 127) / 128), 128, 0, st>>>(n, g->rowptr.p, g->adj.p, src_begin, src_end, d_control.p);
+            ctx->timing.launches++;
+            VGA_CUDA(cudaGetLastError());
+            if (control) VGA_CUDA(cudaMemcpyAsync(control, d_control.p, sizeof(float) * ns, cudaMemcpyDeviceToHost, st));
+            VGA_CUDA(cudaStreamSynchronize(st));
+            return VGA_OK;
+        }
         if (lm == 3 || g->runs_only) return run_local_runs(ctx, g, src_begin, src_end, cluster, k, total, control);
         if (lm == 1 || lm == 2) return run_local_batched(ctx, g, src_begin, src_end, cluster, k, total, control);
     }

@@ -239,7 +239,8 @@ struct Timing {
 struct Options {
     int64_t bfs_mode = 2;        // 0 top-down (push) only, 1 bottom-up (pull) only, 2 direction-optimising hybrid
     int64_t bfs_words = 0;       // 64-bit words per vertex and batch (a batch = 64*words sources): 1, 2, 4, 8; 0 = auto
-    int64_t local_mode = 2;      // 2: auto (1 while the graph holds entries, 3 for a runs-only graph); 1: bit-parallel batches of
+    int64_t local_mode = 2;      // 2: auto (4 for dense graphs that fit, 1 while the graph holds entries, 3 for a runs-only graph);
+                                 // 4: tensor cores (tcgen05 int8 masked product, local_tc.cu); 1: bit-parallel batches of
                                  // 64 cells over entries; 3: one CTA per cell, bitmaps fed by run-length rows; 0: the same fed
                                  // by entries
     int64_t local_span = 0;      // run-length local kernel: bits of the vertex universe per pass (0 = what fits shared memory);
@@ -262,7 +263,8 @@ struct Options {
     int64_t bfs_coop = 1;        // W >= 4: W/2 lanes share a node, 16 bytes each (k_push_nodes_coop / k_pull_nodes_coop; measured
                                  // on the 10^6-cell bench subset: level kernels 1792 ms at W = 2 -> 1508 ms at W = 4); 0 = one
                                  // lane per node for every W
-    int64_t bfs_pull_unroll = 2; // node loads per lane between two early-exit checks of the bottom-up step: 2 or 4
+    int64_t bfs_pull_unroll = 4; // node loads per lane between two early-exit checks of the bottom-up step: 4 (measured on the
+                                 // C5 bench subset: level kernels 1483 -> 1439 ms) or 2
     int64_t bfs_wide_nodes = 384; // auto word width with bfs_coop = 0: 4 words from this many pyramid nodes per out-row, else 2
 };
 
@@ -332,6 +334,8 @@ struct vga_graph {
     vga::DevBuf<uint32_t> f_nodes, t_nodes;
     bool has_f_nodes = false, has_t_nodes = false;
     vga::DevBuf<uint32_t> deg;                   // [n] entries per row when the graph holds runs only (statistics), else empty
+    // bit matrices of the tensor-core local kernel (local_tc.cu), built on first use: A[v][w] and its transpose A^T[w][u]
+    vga::DevBuf<uint32_t> tc_bits_a, tc_bits_t;
     // spatially coherent order of all n sources (cached: the host-side clustering costs milliseconds per call)
     std::vector<int32_t> h_order;
 };
@@ -354,6 +358,9 @@ int run_global(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources, i
                int32_t *total_nodes, int64_t *total_depth, int32_t *dist, int32_t max_levels, int32_t *levels_used);
 // stepdepth.cu
 int run_step_depth(vga_ctx *ctx, vga_graph *g, const int64_t *sources, int64_t nsrc, int32_t *depth_out);
+// local_tc.cu: tcgen05 kernel for dense graphs (cluster, k, total; control comes from local.cu)
+bool local_tc_applicable(const vga_graph *g);
+int run_local_tc(vga_ctx *ctx, vga_graph *g, int64_t src_begin, int64_t src_end, int64_t *cluster, int32_t *k, int32_t *total);
 // local.cu
 int run_local(vga_ctx *ctx, vga_graph *g, int64_t src_begin, int64_t src_end, int64_t *cluster, int32_t *k,
               int32_t *total, float *control);

@@ -213,6 +213,46 @@ def test_local_vs_oracle(name, local_mode):
     c.close()
 
 
+@pytest.mark.skipif(bool(__import__("os").environ.get("VGA_EMU_LIBDIR")), reason="the SIMT emulation has no tensor cores")
+@pytest.mark.parametrize("name", ["room:40:40:5", "oblique:30:30:7", "room:100:100:0", "office:64:64:1"])
+def test_local_tensor_core_kernel_vs_oracle(name):
+    """local_mode = 4: cluster / total as a masked int8 product on the tensor cores (tcgen05.mma kind::i8, local_tc.cu),
+    operands expanded from bit matrices into shared memory, empty K chunks skipped; every cell of the map (several row
+    and column tiles, partial last tiles) and a slice against the oracle.  room:100 = BASELINE config 1 (auto mode picks
+    this kernel there: deg/N = 0.32)."""
+    flat, og = cached_oracle(name)
+    c = capi.Context(0)
+    c.set_option("local_mode", 4)
+    g = c.build(flat)
+    whole = g.n <= 5000
+    rng = (0, g.n) if whole else (g.n // 2 - 300, g.n // 2 + 300)
+    for x, y in zip(g.local_ints(rng), og.local_ints(rng)):
+        assert np.array_equal(x, y)
+    for x, y in zip(g.local_ints((7, 8)), og.local_ints((7, 8))):  # a single cell
+        assert np.array_equal(x, y)
+    c.close()
+
+
+def test_local_tensor_core_kernel_with_ghost_columns():
+    """Unfilled cells inside diagonal runs are columns of the product (they count in k / total) but never middle vertices."""
+    if __import__("os").environ.get("VGA_EMU_LIBDIR"):
+        pytest.skip("the SIMT emulation has no tensor cores")
+    from oracle import pyoracle as po
+    flat = capi.prepare(plans.by_name("room:24:24:1"))
+    st = flat.state.copy()
+    for d in (3, 5):
+        st[(2 + d) * flat.rows + (2 + d)] &= ~np.uint16(2)
+    flat.state = st
+    og = oracle_graph(flat)
+    c = capi.Context(0)
+    c.set_option("local_mode", 4)
+    g = c.build(flat)
+    assert g.ghosts > 0
+    for x, y in zip(g.local_ints(), og.local_ints()):
+        assert np.array_equal(x, y)
+    c.close()
+
+
 @pytest.mark.parametrize("name", ["oblique:30:30:7", "office:64:64:1"])
 def test_local_runs_in_several_passes(name):
     """The run-length local kernel covering the vertex universe in several column ranges (as at 10^6 cells, where two
