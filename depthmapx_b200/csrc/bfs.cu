@@ -753,13 +753,16 @@ __global__ void k_run_costs(const uint2 *runs, int64_t nruns, uint32_t n, u64 *c
     if (r < nruns) cost[r] = runs[r].x < n ? (u64)pyr_cost(runs[r].x, runs[r].y) : 0ULL;  // ghost runs: no nodes
 }
 // ids of the nodes of every run, written at the run's offset (exclusive scan of the per-run node counts)
-__global__ void k_emit_nodes(const uint2 *runs, int64_t nruns, const u64 *node_off, uint32_t n, BfsDev d, uint32_t *out) {
+// `leaf` (y-major lists): a level-0 node i is written as the vertex leaf[i] (its x-major ordinal) -- leaves are always the
+// vertices' own words, only the inner nodes belong to the list's own pyramid
+__global__ void k_emit_nodes(const uint2 *runs, int64_t nruns, const u64 *node_off, uint32_t n, BfsDev d, const uint32_t *leaf,
+                             uint32_t *out) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nruns) return;
     const uint2 run = runs[r];
     if (run.x >= n) return;
     uint64_t o = node_off[r];
-    pyr_decompose(run.x, run.y, [&](int k, uint32_t i) { out[o++] = k == 0 ? i : n + (uint32_t)d.pyr_off[k] + i; });
+    pyr_decompose(run.x, run.y, [&](int k, uint32_t i) { out[o++] = k == 0 ? (leaf ? leaf[i] : i) : n + (uint32_t)d.pyr_off[k] + i; });
 }
 // nodeptr[v] = node offset of the first run of row v (node_off has nruns + 1 entries)
 __global__ void k_row_node_offsets(int64_t n, const uint64_t *runptr, const u64 *node_off, uint64_t *nodeptr) {
@@ -769,6 +772,152 @@ __global__ void k_row_node_offsets(int64_t n, const uint64_t *runptr, const u64 
 __global__ void k_row_lengths(int64_t n, const uint64_t *rowptr, uint32_t *deg) {
     const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v < n) deg[v] = (uint32_t)(rowptr[v + 1] - rowptr[v]);
+}
+
+// ---- y-major alternative rows ---------------------------------------------------------------------------------------
+// Ordinals number the cells x-major, so a row is a list of VERTICAL spans: a cell of a corridor or street that runs along x
+// sees a thousand columns and needs a thousand runs, while in y-major numbering the same set is a handful of horizontal
+// spans (measured on sampled rows of the 10^6-cell plan: 276 pyramid nodes per row x-major, 307 y-major, 166 with the
+// smaller of the two per row; 89 / 57 / 42 on the office plan).  Every row therefore also gets its y-major run list and
+// the BFS walks whichever is shorter: inner nodes of a y-major list live in a second pyramid built over the y-major
+// order of the vertices, leaves stay the vertices' own words (ids are translated to x-major ordinals when the list is
+// written), and the level-0 passes of that pyramid go through the permutation (pyramid.cuh `leaf`).
+
+// y-major rank of every filled cell: flag[y * cols + x] = 1, exclusive scan, gather
+__global__ void k_mark_cells_ymajor(int64_t n, const int32_t *refs, int cols, u64 *flag) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const uint32_t r = (uint32_t)refs[v];
+    flag[(int64_t)(r & 0xffff) * cols + (r >> 16)] = 1ULL;
+}
+__global__ void k_perm_from_scan(int64_t n, const int32_t *refs, int cols, const u64 *scan, uint32_t *perm_y, uint32_t *perm_x) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const uint32_t r = (uint32_t)refs[v];
+    const uint32_t y = (uint32_t)scan[(int64_t)(r & 0xffff) * cols + (r >> 16)];
+    perm_y[v] = y;
+    perm_x[y] = (uint32_t)v;
+}
+
+// One CTA per row u: the row's members (x-major runs, ghost runs skipped) are set as bits perm_y[w] of a bitmap of the n
+// vertices in shared memory; the bitmap's runs are the row's y-major runs.  MODE 0 counts them, MODE 1 writes them
+// (first y-major ordinal, length) in ascending order at out_ptr[u].
+template <int MODE>
+__global__ void k_yruns(int64_t n, const uint64_t *runptr, const uint2 *runs, const uint32_t *perm_y, u64 *count,
+                        const uint64_t *out_ptr, uint2 *out) {
+    extern __shared__ __align__(16) uint32_t ysm[];
+    const uint32_t words = (uint32_t)((n + 31) >> 5);
+    uint32_t *bm = ysm;                 // [words + 1] (one zero word behind the end)
+    uint32_t *part = ysm + words + 1;   // [blockDim.x + 1] per-thread counts of starts / ends
+    const uint32_t per = (words + blockDim.x - 1) / blockDim.x;
+    for (int64_t u = blockIdx.x; u < n; u += gridDim.x) {
+        for (uint32_t i = threadIdx.x; i <= words; i += blockDim.x) bm[i] = 0u;
+        __syncthreads();
+        for (uint64_t r = runptr[u] + threadIdx.x; r < runptr[u + 1]; r += blockDim.x) {
+            const uint2 run = runs[r];
+            if (run.x >= (uint32_t)n) continue;  // ghost columns are not part of the BFS
+            for (uint32_t w = run.x; w < run.x + run.y; w++) {
+                const uint32_t y = perm_y[w];
+                atomicOr(&bm[y >> 5], 1u << (y & 31));
+            }
+        }
+        __syncthreads();
+        // this thread's slice of words: starts = bits whose predecessor is clear, ends = bits whose successor is clear
+        const uint32_t w0 = min(threadIdx.x * per, words), w1 = min(w0 + per, words);
+        uint32_t ns = 0;
+        for (uint32_t i = w0; i < w1; i++) {
+            const uint32_t x = bm[i], prev = i ? bm[i - 1] >> 31 : 0u;
+            ns += __popc(x & ~((x << 1) | prev));
+        }
+        if (MODE == 0) {
+            part[threadIdx.x] = ns;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                u64 tot = 0;
+                for (uint32_t i = 0; i < blockDim.x; i++) tot += part[i];
+                count[u] = tot;
+            }
+            __syncthreads();
+        } else {
+            uint32_t ne = 0;
+            for (uint32_t i = w0; i < w1; i++) {
+                const uint32_t x = bm[i], next = bm[i + 1] & 1u;
+                ne += __popc(x & ~((x >> 1) | (next << 31)));
+            }
+            // exclusive offsets of this thread's starts and ends (two serial scans by two threads: the counts are tiny next
+            // to the bitmap work)
+            uint32_t *part_e = part + blockDim.x + 1;
+            part[threadIdx.x] = ns;
+            part_e[threadIdx.x] = ne;
+            __syncthreads();
+            if (threadIdx.x < 2) {
+                uint32_t *p = threadIdx.x == 0 ? part : part_e;
+                uint32_t run_total = 0;
+                for (uint32_t i = 0; i < blockDim.x; i++) {
+                    const uint32_t c = p[i];
+                    p[i] = run_total;
+                    run_total += c;
+                }
+            }
+            __syncthreads();
+            uint2 *o = out + out_ptr[u];
+            uint32_t ks = part[threadIdx.x], ke = part_e[threadIdx.x];
+            for (uint32_t i = w0; i < w1; i++) {
+                const uint32_t x = bm[i], prev = i ? bm[i - 1] >> 31 : 0u, next = bm[i + 1] & 1u;
+                uint32_t st = x & ~((x << 1) | prev);
+                while (st) {
+                    const int b = __ffs(st) - 1;
+                    st &= st - 1;
+                    o[ks++].x = (i << 5) + (uint32_t)b;
+                }
+                uint32_t en = x & ~((x >> 1) | (next << 31));
+                while (en) {
+                    const int b = __ffs(en) - 1;
+                    en &= en - 1;
+                    o[ke++].y = (i << 5) + (uint32_t)b;  // position of the last bit, turned into a length below
+                }
+            }
+            __syncthreads();
+            const uint64_t total = out_ptr[u + 1] - out_ptr[u];
+            for (uint64_t k = threadIdx.x; k < total; k += blockDim.x) o[k].y = o[k].y - o[k].x + 1u;
+            __syncthreads();
+        }
+    }
+}
+
+// rows handed over in x-major row order -> the same lists in y-major row order (row perm_y[u] = list of u): sizes, then copy
+__global__ void k_row_sizes_permuted(int64_t n, const uint64_t *ptr, const uint32_t *perm_y, u64 *size_y) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < n) size_y[perm_y[u]] = ptr[u + 1] - ptr[u];
+}
+__global__ void k_rows_copy_permuted(int64_t n, const uint64_t *ptr, const uint2 *runs, const uint32_t *perm_y, const uint64_t *ptr_y,
+                                     uint2 *runs_y) {
+    const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (u >= n) return;
+    const uint64_t s = ptr[u], e = ptr[u + 1], d = ptr_y[perm_y[u]];
+    for (uint64_t i = s + lane; i < e; i += 32) runs_y[d + (i - s)] = runs[i];
+}
+
+// per row the shorter of its x-major node list (list index = row) and its y-major one (list index = ymap ? ymap[row] : row)
+__global__ void k_choose_lists(int64_t n, const uint64_t *xptr, const uint64_t *yptr, const uint32_t *ymap, u64 *size, uint8_t *isy) {
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const int64_t yv = ymap ? (int64_t)ymap[v] : v;
+    const u64 cx = xptr[v + 1] - xptr[v], cy = yptr[yv + 1] - yptr[yv];
+    const bool y = cy * 10 < cx * 9;  // the y-major pyramid has to pay for its own build / down pass: take it for >= 10 %
+    isy[v] = y ? 1 : 0;
+    size[v] = y ? cy : cx;
+}
+__global__ void k_copy_chosen(int64_t n, const uint64_t *xptr, const uint32_t *xnodes, const uint64_t *yptr, const uint32_t *ynodes,
+                              const uint32_t *ymap, const uint8_t *isy, const uint64_t *optr, uint32_t *onodes) {
+    const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (v >= n) return;
+    const int64_t yv = ymap ? (int64_t)ymap[v] : v;
+    const uint32_t *src = isy[v] ? ynodes + yptr[yv] : xnodes + xptr[v];
+    const uint64_t cnt = optr[v + 1] - optr[v], d = optr[v];
+    for (uint64_t i = lane; i < cnt; i += 32) onodes[d + i] = src[i];
 }
 
 inline unsigned blocks_for(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }

@@ -81,15 +81,19 @@ template <typename Visit> VGA_HD int pyr_decompose(uint32_t a, uint32_t len, Vis
 // Builds three pyramid levels at once: work item t ORs the aligned group of 8 nodes [8t, 8t+8) of level k (src, cnt0
 // nodes of W words each) into 4 nodes of level k+1, 2 of level k+2 and 1 of level k+3 (d1/d2/d3 with cnt1/cnt2/cnt3
 // nodes; a count of 0 = that level does not exist).  Work items: ceil(cnt0 / 8).
+// `leaf` (optional, level 0 only): the words of level-0 node idx live at src[leaf[idx]] -- a pyramid over a PERMUTED
+// order of the vertices (the y-major pyramid of bfs.cu) reads / writes the shared x-major state through it.
 template <int W>
 VGA_HD void pyr_build_group(const unsigned long long *src, int64_t cnt0, unsigned long long *d1, int64_t cnt1,
-                            unsigned long long *d2, int64_t cnt2, unsigned long long *d3, int64_t cnt3, int64_t t) {
+                            unsigned long long *d2, int64_t cnt2, unsigned long long *d3, int64_t cnt3, int64_t t,
+                            const uint32_t *leaf = nullptr) {
     unsigned long long a[8][W];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const int64_t idx = 8 * t + i;
+        const int64_t at = (leaf && idx < cnt0) ? (int64_t)leaf[idx] : idx;
 #pragma unroll
-        for (int j = 0; j < W; j++) a[i][j] = idx < cnt0 ? src[idx * W + j] : 0ULL;
+        for (int j = 0; j < W; j++) a[i][j] = idx < cnt0 ? src[at * W + j] : 0ULL;
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -122,7 +126,7 @@ VGA_HD void pyr_build_group(const unsigned long long *src, int64_t cnt0, unsigne
 // round.  Same grouping as pyr_build_group; a count of 0 = that level does not exist.
 template <int W>
 VGA_HD void pyr_down_group(unsigned long long *dst, int64_t cnt0, unsigned long long *s1, int64_t cnt1, unsigned long long *s2,
-                           int64_t cnt2, unsigned long long *s3, int64_t cnt3, int64_t t) {
+                           int64_t cnt2, unsigned long long *s3, int64_t cnt3, int64_t t, const uint32_t *leaf = nullptr) {
     unsigned long long a3[W], a2[2][W], a1[4][W];
 #pragma unroll
     for (int j = 0; j < W; j++) {
@@ -158,9 +162,10 @@ VGA_HD void pyr_down_group(unsigned long long *dst, int64_t cnt0, unsigned long 
     for (int i = 0; i < 8; i++) {
         const int64_t idx = 8 * t + i;
         if (idx < cnt0) {
+            const int64_t at = leaf ? (int64_t)leaf[idx] : idx;
 #pragma unroll
             for (int j = 0; j < W; j++)
-                if (a1[i >> 1][j]) dst[idx * W + j] |= a1[i >> 1][j];
+                if (a1[i >> 1][j]) dst[at * W + j] |= a1[i >> 1][j];
         }
     }
 }
