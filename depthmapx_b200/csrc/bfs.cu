@@ -67,6 +67,11 @@ struct BfsDev {
     u64 *visited, *frontier, *next;  // [batches][n][W]
     u64 *pyr;                        // [batches][pyr_total][W]: OR-pyramid levels >= 1 of the frontier (pull)
     u64 *npyr;                       // [batches][pyr_total][W]: inner nodes of `next` (push); all zero between levels
+    // y-major alternative lists (nullptr when the graph has none): the same two pyramids over the y-major order of the
+    // vertices; their level 0 is the shared x-major state, reached through perm_x (y-major rank -> ordinal)
+    u64 *pyr_y, *npyr_y;
+    const uint32_t *perm_x;
+    const uint8_t *f_isy, *t_isy;    // [n] 1 = the row's list is the y-major one
     int64_t pyr_total;               // inner nodes per batch
     const u64 *valid;                // [batches*W] valid source bits of each word
     int *active;                     // [batches] 1 while the batch goes on
@@ -169,10 +174,12 @@ template <int W> __global__ void __launch_bounds__(TPB) k_push_nodes(BfsDev d) {
 #pragma unroll
             for (int j = 0; j < W; j++) fw[j] = __shfl_sync(FULL, f[j], src_lane);
             uint64_t e0 = __shfl_sync(FULL, my0, src_lane), e1 = __shfl_sync(FULL, my1, src_lane);
+            // inner nodes of a y-major list live in the y-major pyramid
+            u64 *npu = (d.f_isy && d.f_isy[base + (threadIdx.x & ~31) + src_lane]) ? d.npyr_y + (int64_t)b * d.pyr_total * W : np;
             for (uint64_t e = e0 + lane; e < e1; e += 32) {
                 const uint32_t c = __ldcs(d.f_nodes + e);
                 VGA_COUNT(npush_nodes, 1);
-                u64 *p = c < n ? nx + (int64_t)c * W : np + (int64_t)(c - n) * W;
+                u64 *p = c < n ? nx + (int64_t)c * W : npu + (int64_t)(c - n) * W;
                 u64 cur[W];
                 ldw<W>(p, cur);
 #pragma unroll
@@ -189,10 +196,11 @@ template <int W> __global__ void __launch_bounds__(TPB) k_push_nodes(BfsDev d) {
 }
 
 // down pass of the push, three levels per launch, top chunk first: level k+3 .. k+1 -> level k (`next` for k = 0)
-template <int W> __global__ void __launch_bounds__(TPB) k_pyr_down(BfsDev d, int k) {
+template <int W> __global__ void __launch_bounds__(TPB) k_pyr_down(BfsDev d, int k, int ymaj) {
     const int b = blockIdx.y;
     if (!d.active[b] || d.mode[b] != 0) return;
-    u64 *np = d.npyr + (int64_t)b * d.pyr_total * W;
+    u64 *np = (ymaj ? d.npyr_y : d.npyr) + (int64_t)b * d.pyr_total * W;
+    const uint32_t *leaf = (ymaj && k == 0) ? d.perm_x : nullptr;
     u64 *dst = k == 0 ? d.next + (int64_t)b * d.n * W : np + d.pyr_off[k] * W;
     u64 *s1 = k + 1 < d.pyr_levels ? np + d.pyr_off[k + 1] * W : nullptr;
     u64 *s2 = k + 2 < d.pyr_levels ? np + d.pyr_off[k + 2] * W : nullptr;
@@ -202,16 +210,17 @@ template <int W> __global__ void __launch_bounds__(TPB) k_pyr_down(BfsDev d, int
     const int64_t groups = (c0 + 7) / 8;
     for (int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x; t < groups; t += (int64_t)gridDim.x * TPB) {
         VGA_COUNT(pyr_down_groups, 1);
-        pyr_down_group<W>(dst, c0, s1, c1, s2, c2, s3, c3, t);
+        pyr_down_group<W>(dst, c0, s1, c1, s2, c2, s3, c3, t, leaf);
     }
 }
 
 // Three pyramid levels per launch for every batch whose next step is a pull: level k (the frontier for k = 0) ->
 // levels k+1 .. k+3.  One work item per aligned group of 8 level-k nodes.
-template <int W> __global__ void __launch_bounds__(TPB) k_pyr_build(BfsDev d, int k) {
+template <int W> __global__ void __launch_bounds__(TPB) k_pyr_build(BfsDev d, int k, int ymaj) {
     const int b = blockIdx.y;
     if (!d.active[b] || d.mode[b] != 1) return;
-    u64 *pyr = d.pyr + (int64_t)b * d.pyr_total * W;
+    u64 *pyr = (ymaj ? d.pyr_y : d.pyr) + (int64_t)b * d.pyr_total * W;
+    const uint32_t *leaf = (ymaj && k == 0) ? d.perm_x : nullptr;
     const u64 *src = k == 0 ? d.frontier + (int64_t)b * d.n * W : pyr + d.pyr_off[k] * W;
     u64 *d1 = k + 1 < d.pyr_levels ? pyr + d.pyr_off[k + 1] * W : nullptr;
     u64 *d2 = k + 2 < d.pyr_levels ? pyr + d.pyr_off[k + 2] * W : nullptr;
@@ -221,7 +230,7 @@ template <int W> __global__ void __launch_bounds__(TPB) k_pyr_build(BfsDev d, in
     const int64_t groups = (c0 + 7) / 8;
     for (int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x; t < groups; t += (int64_t)gridDim.x * TPB) {
         VGA_COUNT(pyr_build_groups, 1);
-        pyr_build_group<W>(src, c0, d1, c1, d2, c2, d3, c3, t);
+        pyr_build_group<W>(src, c0, d1, c1, d2, c2, d3, c3, t, leaf);
     }
 }
 
@@ -275,6 +284,7 @@ template <int W> __global__ void __launch_bounds__(TPB) k_pull_nodes(BfsDev d) {
                 u64 acc[W];
 #pragma unroll
                 for (int j = 0; j < W; j++) acc[j] = 0ULL;
+                const u64 *pyu = (d.t_isy && d.t_isy[(base + (threadIdx.x & ~31)) + src_lane]) ? d.pyr_y + (int64_t)b * d.pyr_total * W : pyr;
                 for (uint64_t e = e0; e < e1; e += 16) {
                     const uint64_t ea = e + gl, eb = e + 8 + gl;
                     u64 g0[W], g1[W];
@@ -284,8 +294,8 @@ template <int W> __global__ void __launch_bounds__(TPB) k_pull_nodes(BfsDev d) {
                     if (ea < e1) ca = __ldcs(d.t_nodes + ea);
                     if (eb < e1) cb = __ldcs(d.t_nodes + eb);
                     VGA_COUNT(npull_nodes, (ea < e1) + (eb < e1));
-                    if (ea < e1) ldw<W>(ca < n ? fr + (int64_t)ca * W : pyr + (int64_t)(ca - n) * W, g0);
-                    if (eb < e1) ldw<W>(cb < n ? fr + (int64_t)cb * W : pyr + (int64_t)(cb - n) * W, g1);
+                    if (ea < e1) ldw<W>(ca < n ? fr + (int64_t)ca * W : pyu + (int64_t)(ca - n) * W, g0);
+                    if (eb < e1) ldw<W>(cb < n ? fr + (int64_t)cb * W : pyu + (int64_t)(cb - n) * W, g1);
                     bool done = true;
 #pragma unroll
                     for (int j = 0; j < W; j++) {
@@ -351,10 +361,11 @@ template <int W, int G> __global__ void __launch_bounds__(TPB) k_push_nodes_coop
             // this lane's slice of the vertex's frontier vector (just read by the warp: an L1 / L2 hit)
             const ulonglong2 myf = *reinterpret_cast<const ulonglong2 *>(fr + (wbase + src_lane) * W + 2 * g);
             if ((myf.x | myf.y) == 0ULL) continue;
+            u64 *npu = (d.f_isy && d.f_isy[wbase + src_lane]) ? d.npyr_y + (int64_t)b * d.pyr_total * W : np;
             for (uint64_t e = e0 + sub; e < e1; e += NPI) {
                 const uint32_t c = __ldcs(d.f_nodes + e);
                 VGA_COUNT(npush_nodes, 1);
-                u64 *p = (c < n ? nx + (int64_t)c * W : np + (int64_t)(c - n) * W) + 2 * g;
+                u64 *p = (c < n ? nx + (int64_t)c * W : npu + (int64_t)(c - n) * W) + 2 * g;
                 const ulonglong2 cur = *reinterpret_cast<const ulonglong2 *>(p);
                 const u64 a0 = myf.x & ~cur.x, a1 = myf.y & ~cur.y;
                 if (a0) atomicOr(&p[0], a0);
@@ -410,6 +421,7 @@ template <int W, int G, int U> __global__ void __launch_bounds__(TPB) k_pull_nod
                 const u64 nd0 = valid.x & ~vv.x, nd1 = valid.y & ~vv.y;
                 u64 acc0 = 0ULL, acc1 = 0ULL;
                 bool mine_done = (nd0 | nd1) == 0ULL;
+                const u64 *pyu = (d.t_isy && d.t_isy[ww]) ? d.pyr_y + (int64_t)b * d.pyr_total * W : pyr;
                 for (uint64_t e = e0; e < e1; e += U * NPG) {
                     u64 x0 = 0ULL, x1 = 0ULL;
                     if (!mine_done) {
@@ -424,7 +436,7 @@ template <int W, int G, int U> __global__ void __launch_bounds__(TPB) k_pull_nod
                             if (c[i] != 0xffffffffu) {
                                 VGA_COUNT(npull_nodes, g == 0);
                                 const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(
-                                    (c[i] < n ? fr + (int64_t)c[i] * W : pyr + (int64_t)(c[i] - n) * W) + 2 * g);
+                                    (c[i] < n ? fr + (int64_t)c[i] * W : pyu + (int64_t)(c[i] - n) * W) + 2 * g);
                                 x0 |= t.x;
                                 x1 |= t.y;
                             }
@@ -801,67 +813,92 @@ __global__ void k_perm_from_scan(int64_t n, const int32_t *refs, int cols, const
 
 // One CTA per row u: the row's members (x-major runs, ghost runs skipped) are set as bits perm_y[w] of a bitmap of the n
 // vertices in shared memory; the bitmap's runs are the row's y-major runs.  MODE 0 counts them, MODE 1 writes them
-// (first y-major ordinal, length) in ascending order at out_ptr[u].
+// (first y-major ordinal, length) in ascending order at out_ptr[u].  Only the word range [lo, hi] the row touches is
+// cleared and scanned (perm_y grows along an x-major run, so its ends bound it); one warp per run sets the bits; the
+// per-thread start / end counts are combined by shuffle scans.
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *warp_tot /*[33]*/, uint32_t *total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = lane < nw ? warp_tot[lane] : 0u, winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, winc, o);
+            if (lane >= o) winc += t;
+        }
+        warp_tot[lane] = winc - w;
+        if (lane == 31) warp_tot[32] = winc;
+    }
+    __syncthreads();
+    const uint32_t r = warp_tot[wid] + inc - v;
+    *total = warp_tot[32];
+    __syncthreads();  // warp_tot may be reused
+    return r;
+}
+
 template <int MODE>
 __global__ void k_yruns(int64_t n, const uint64_t *runptr, const uint2 *runs, const uint32_t *perm_y, u64 *count,
                         const uint64_t *out_ptr, uint2 *out) {
     extern __shared__ __align__(16) uint32_t ysm[];
     const uint32_t words = (uint32_t)((n + 31) >> 5);
     uint32_t *bm = ysm;                 // [words + 1] (one zero word behind the end)
-    uint32_t *part = ysm + words + 1;   // [blockDim.x + 1] per-thread counts of starts / ends
-    const uint32_t per = (words + blockDim.x - 1) / blockDim.x;
+    uint32_t *wt = ysm + words + 1;     // [33] scan scratch, then [2] range
+    uint32_t *range = wt + 33;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    // the whole bitmap is zero between rows: every row clears the range it used
+    for (uint32_t i = threadIdx.x; i <= words; i += blockDim.x) bm[i] = 0u;
+    if (threadIdx.x == 0) {
+        range[0] = 0xffffffffu;
+        range[1] = 0u;
+    }
+    __syncthreads();
     for (int64_t u = blockIdx.x; u < n; u += gridDim.x) {
-        for (uint32_t i = threadIdx.x; i <= words; i += blockDim.x) bm[i] = 0u;
-        __syncthreads();
-        for (uint64_t r = runptr[u] + threadIdx.x; r < runptr[u + 1]; r += blockDim.x) {
+        const uint64_t r0 = runptr[u], r1 = runptr[u + 1];
+        uint32_t lo = 0xffffffffu, hi = 0u;
+        for (uint64_t r = r0 + wid; r < r1; r += nw) {
             const uint2 run = runs[r];
             if (run.x >= (uint32_t)n) continue;  // ghost columns are not part of the BFS
-            for (uint32_t w = run.x; w < run.x + run.y; w++) {
+            for (uint32_t w = run.x + lane; w < run.x + run.y; w += 32) {
                 const uint32_t y = perm_y[w];
                 atomicOr(&bm[y >> 5], 1u << (y & 31));
+                lo = min(lo, y >> 5);
+                hi = max(hi, y >> 5);
             }
+        }
+        lo = __reduce_min_sync(FULL, lo);
+        hi = __reduce_max_sync(FULL, hi);
+        if (lane == 0 && lo <= hi) {
+            atomicMin(&range[0], lo);
+            atomicMax(&range[1], hi);
         }
         __syncthreads();
+        const uint32_t wlo = range[0], whi = range[1];
+        const bool any = wlo <= whi;
+        const uint32_t span = any ? whi - wlo + 1 : 0u;
+        const uint32_t per = (span + blockDim.x - 1) / blockDim.x;
         // this thread's slice of words: starts = bits whose predecessor is clear, ends = bits whose successor is clear
-        const uint32_t w0 = min(threadIdx.x * per, words), w1 = min(w0 + per, words);
-        uint32_t ns = 0;
+        const uint32_t w0 = wlo + min(threadIdx.x * per, span), w1 = wlo + min((threadIdx.x + 1) * per, span);
+        uint32_t ns = 0, ne = 0;
         for (uint32_t i = w0; i < w1; i++) {
-            const uint32_t x = bm[i], prev = i ? bm[i - 1] >> 31 : 0u;
+            const uint32_t x = bm[i], prev = i ? bm[i - 1] >> 31 : 0u, next = bm[i + 1] & 1u;
             ns += __popc(x & ~((x << 1) | prev));
+            if (MODE == 1) ne += __popc(x & ~((x >> 1) | (next << 31)));
         }
+        uint32_t total = 0;
+        uint32_t ks = block_excl_scan(ns, wt, &total);  // ends with a barrier: range[] and bm[] reads above are complete
         if (MODE == 0) {
-            part[threadIdx.x] = ns;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                u64 tot = 0;
-                for (uint32_t i = 0; i < blockDim.x; i++) tot += part[i];
-                count[u] = tot;
-            }
-            __syncthreads();
+            if (threadIdx.x == 0) count[u] = total;
         } else {
-            uint32_t ne = 0;
-            for (uint32_t i = w0; i < w1; i++) {
-                const uint32_t x = bm[i], next = bm[i + 1] & 1u;
-                ne += __popc(x & ~((x >> 1) | (next << 31)));
-            }
-            // exclusive offsets of this thread's starts and ends (two serial scans by two threads: the counts are tiny next
-            // to the bitmap work)
-            uint32_t *part_e = part + blockDim.x + 1;
-            part[threadIdx.x] = ns;
-            part_e[threadIdx.x] = ne;
-            __syncthreads();
-            if (threadIdx.x < 2) {
-                uint32_t *p = threadIdx.x == 0 ? part : part_e;
-                uint32_t run_total = 0;
-                for (uint32_t i = 0; i < blockDim.x; i++) {
-                    const uint32_t c = p[i];
-                    p[i] = run_total;
-                    run_total += c;
-                }
-            }
-            __syncthreads();
+            uint32_t tot_e = 0;
+            uint32_t ke = block_excl_scan(ne, wt, &tot_e);
             uint2 *o = out + out_ptr[u];
-            uint32_t ks = part[threadIdx.x], ke = part_e[threadIdx.x];
             for (uint32_t i = w0; i < w1; i++) {
                 const uint32_t x = bm[i], prev = i ? bm[i - 1] >> 31 : 0u, next = bm[i + 1] & 1u;
                 uint32_t st = x & ~((x << 1) | prev);
@@ -878,10 +915,16 @@ __global__ void k_yruns(int64_t n, const uint64_t *runptr, const uint2 *runs, co
                 }
             }
             __syncthreads();
-            const uint64_t total = out_ptr[u + 1] - out_ptr[u];
-            for (uint64_t k = threadIdx.x; k < total; k += blockDim.x) o[k].y = o[k].y - o[k].x + 1u;
-            __syncthreads();
+            for (uint32_t k = threadIdx.x; k < total; k += blockDim.x) o[k].y = o[k].y - o[k].x + 1u;
         }
+        __syncthreads();
+        // leave the bitmap zero for the next row
+        for (uint32_t i = wlo + threadIdx.x; any && i <= whi; i += blockDim.x) bm[i] = 0u;
+        if (threadIdx.x == 0) {
+            range[0] = 0xffffffffu;
+            range[1] = 0u;
+        }
+        __syncthreads();
     }
 }
 
@@ -967,22 +1010,24 @@ int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, De
             }
             tm.launches++;
             tm.main_launches++;
-            for (int k = kmax; k >= 0; k -= 3) {
-                const int64_t groups = (d.pyr_cnt[k] + 7) / 8;
-                dim3 pgrid((unsigned)std::min<int64_t>((groups + TPB - 1) / TPB, 4096), (unsigned)nb);
-                k_pyr_down<W><<<pgrid, TPB, 0, st>>>(d, k);
-                tm.launches++;
-                tm.main_launches++;
-            }
+            for (int ymaj = 0; ymaj < (d.npyr_y ? 2 : 1); ymaj++)
+                for (int k = kmax; k >= 0; k -= 3) {
+                    const int64_t groups = (d.pyr_cnt[k] + 7) / 8;
+                    dim3 pgrid((unsigned)std::min<int64_t>((groups + TPB - 1) / TPB, 4096), (unsigned)nb);
+                    k_pyr_down<W><<<pgrid, TPB, 0, st>>>(d, k, ymaj);
+                    tm.launches++;
+                    tm.main_launches++;
+                }
         }
         if (bfs_mode != 0 && level > 0) {
-            for (int k = 0; k + 1 < d.pyr_levels; k += 3) {
-                const int64_t groups = (d.pyr_cnt[k] + 7) / 8;
-                dim3 pgrid((unsigned)std::min<int64_t>((groups + TPB - 1) / TPB, 4096), (unsigned)nb);
-                k_pyr_build<W><<<pgrid, TPB, 0, st>>>(d, k);
-                tm.launches++;
-                tm.main_launches++;
-            }
+            for (int ymaj = 0; ymaj < (d.pyr_y ? 2 : 1); ymaj++)
+                for (int k = 0; k + 1 < d.pyr_levels; k += 3) {
+                    const int64_t groups = (d.pyr_cnt[k] + 7) / 8;
+                    dim3 pgrid((unsigned)std::min<int64_t>((groups + TPB - 1) / TPB, 4096), (unsigned)nb);
+                    k_pyr_build<W><<<pgrid, TPB, 0, st>>>(d, k, ymaj);
+                    tm.launches++;
+                    tm.main_launches++;
+                }
             if constexpr (W >= 4 && W <= 16) {
                 if (ctx->opt.bfs_coop && ctx->opt.bfs_pull_unroll == 4)
                     k_pull_nodes_coop<W, W / 2, 4><<<grid, TPB, 0, st>>>(d);
@@ -1186,7 +1231,7 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources,
     VGA_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const int64_t budget = (int64_t)std::min<size_t>((size_t)(free_b * 0.4), (size_t)48 << 30);
     int64_t chunk = ctx->opt.bfs_chunk > 0 ? std::max<int64_t>(1, ctx->opt.bfs_chunk / W)
-                                           : std::max<int64_t>(1, budget / (44 * W * std::max<int64_t>(n, 1)));
+                                           : std::max<int64_t>(1, budget / ((g->has_y ? 60 : 44) * W * std::max<int64_t>(n, 1)));
     chunk = std::min<int64_t>(chunk, nbatch);
     chunk = std::min<int64_t>(chunk, 65535);
 
@@ -1203,6 +1248,12 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources,
     VGA_TRY(ctx->ws.get("bfs_npyr", sizeof(u64) * (size_t)chunk * (size_t)std::max<int64_t>(pl.total, 1) * W, (void **)&npyr_p));
     // all zero between levels: the down pass clears what the push wrote
     VGA_CUDA(cudaMemsetAsync(npyr_p, 0, sizeof(u64) * (size_t)chunk * (size_t)std::max<int64_t>(pl.total, 1) * W, st));
+    u64 *pyr_y = nullptr, *npyr_y = nullptr;
+    if (g->has_y) {
+        if (bfs_mode != 0) VGA_TRY(ctx->ws.get("bfs_pyr_y", sizeof(u64) * (size_t)chunk * (size_t)std::max<int64_t>(pl.total, 1) * W, (void **)&pyr_y));
+        VGA_TRY(ctx->ws.get("bfs_npyr_y", sizeof(u64) * (size_t)chunk * (size_t)std::max<int64_t>(pl.total, 1) * W, (void **)&npyr_y));
+        VGA_CUDA(cudaMemsetAsync(npyr_y, 0, sizeof(u64) * (size_t)chunk * (size_t)std::max<int64_t>(pl.total, 1) * W, st));
+    }
     VGA_TRY(valid.alloc((size_t)chunk * W));
     VGA_TRY(stats.alloc((size_t)chunk * NSTAT));
     VGA_TRY(work.alloc_zero(4, st));
@@ -1224,6 +1275,11 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources,
     d.next = next;
     d.pyr = pyr_p;
     d.npyr = npyr_p;
+    d.pyr_y = pyr_y;
+    d.npyr_y = npyr_y;
+    d.perm_x = g->has_y ? g->perm_x.p : nullptr;
+    d.f_isy = g->has_y ? g->f_isy.p : nullptr;
+    d.t_isy = (g->has_y && bfs_mode != 0) ? g->t_isy.p : nullptr;
     d.pyr_total = pl.total;
     d.valid = valid.p;
     d.active = active.p;
@@ -1384,44 +1440,42 @@ int build_runs(vga_ctx *ctx, int64_t n /*rows*/, uint32_t brk /*filled cells*/, 
     return VGA_OK;
 }
 
-// in-rows as runs from the out-rows' runs (see k_trans_events)
-int transpose_runs(vga_ctx *ctx, vga_graph *g) {
+// in-rows as runs from the out-rows' runs (see k_trans_events); rows and columns share one numbering of the n vertices
+int transpose_runs(vga_ctx *ctx, int64_t n, const DevBuf<uint64_t> &runptr, const DevBuf<uint2> &runs, DevBuf<uint64_t> &t_runptr,
+                   DevBuf<uint2> &t_runs, int64_t *t_nruns) {
     cudaStream_t st = ctx->stream;
-    const int64_t n = g->n;
     DevBuf<u64> count;
     DevBuf<uint32_t> cur_s, cur_e, t_start, t_end;
     VGA_TRY(count.alloc_zero((size_t)n + 1, st));
-    VGA_TRY(g->t_runptr.alloc((size_t)n + 1));
+    VGA_TRY(t_runptr.alloc((size_t)n + 1));
     if (n > 0) {
-        k_trans_events<0><<<blocks_for(n * 32, 256), 256, 0, st>>>(n, g->f_runptr.p, g->f_runs.p, count.p, nullptr, nullptr, nullptr,
-                                                                  nullptr, nullptr);
+        k_trans_events<0><<<blocks_for(n * 32, 256), 256, 0, st>>>(n, runptr.p, runs.p, count.p, nullptr, nullptr, nullptr, nullptr, nullptr);
         ctx->timing.launches++;
     }
-    VGA_TRY(exclusive_sum_u64(ctx, count.p, (u64 *)g->t_runptr.p, n + 1));
+    VGA_TRY(exclusive_sum_u64(ctx, count.p, (u64 *)t_runptr.p, n + 1));
     uint64_t total = 0;
-    VGA_CUDA(cudaMemcpyAsync(&total, g->t_runptr.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    VGA_CUDA(cudaMemcpyAsync(&total, t_runptr.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
     VGA_CUDA(cudaStreamSynchronize(st));
-    g->t_nruns = (int64_t)total;
+    *t_nruns = (int64_t)total;
     VGA_TRY(cur_s.alloc_zero((size_t)n + 1, st));
     VGA_TRY(cur_e.alloc_zero((size_t)n + 1, st));
     VGA_TRY(t_start.alloc((size_t)total + 1));
     VGA_TRY(t_end.alloc((size_t)total + 1));
-    VGA_TRY(g->t_runs.alloc((size_t)total + 1));
+    VGA_TRY(t_runs.alloc((size_t)total + 1));
     if (n > 0) {
-        k_trans_events<1><<<blocks_for(n * 32, 256), 256, 0, st>>>(n, g->f_runptr.p, g->f_runs.p, nullptr, g->t_runptr.p, cur_s.p,
-                                                                  cur_e.p, t_start.p, t_end.p);
-        k_trans_pair<<<blocks_for(n * 32, 256), 256, 0, st>>>(n, g->t_runptr.p, t_start.p, t_end.p, g->t_runs.p);
+        k_trans_events<1><<<blocks_for(n * 32, 256), 256, 0, st>>>(n, runptr.p, runs.p, nullptr, t_runptr.p, cur_s.p, cur_e.p, t_start.p,
+                                                                  t_end.p);
+        k_trans_pair<<<blocks_for(n * 32, 256), 256, 0, st>>>(n, t_runptr.p, t_start.p, t_end.p, t_runs.p);
         ctx->timing.launches += 2;
     }
     VGA_CUDA(cudaStreamSynchronize(st));
     VGA_CUDA(cudaGetLastError());
-    g->has_runs = true;
     return VGA_OK;
 }
 
 // node-id lists from runs: per-run node counts -> exclusive scan -> ids written at the run's offset
 int build_nodes(vga_ctx *ctx, int64_t n, const DevBuf<uint64_t> &runptr, const DevBuf<uint2> &runs, int64_t nruns,
-                DevBuf<uint64_t> &nodeptr, DevBuf<uint32_t> &nodes, int64_t *nnodes) {
+                DevBuf<uint64_t> &nodeptr, DevBuf<uint32_t> &nodes, int64_t *nnodes, const uint32_t *leaf = nullptr) {
     cudaStream_t st = ctx->stream;
     const PyrLayout pl = pyr_layout(n);
     BfsDev d0;
@@ -1446,10 +1500,97 @@ int build_nodes(vga_ctx *ctx, int64_t n, const DevBuf<uint64_t> &runptr, const D
     *nnodes = (int64_t)total;
     VGA_TRY(nodes.alloc((size_t)total + 1));
     if (nruns > 0) {
-        k_emit_nodes<<<blocks_for(nruns, 256), 256, 0, st>>>(runs.p, nruns, off.p, (uint32_t)n, d0, nodes.p);
+        k_emit_nodes<<<blocks_for(nruns, 256), 256, 0, st>>>(runs.p, nruns, off.p, (uint32_t)n, d0, leaf, nodes.p);
         ctx->timing.launches++;
     }
     k_row_node_offsets<<<blocks_for(n + 1, 256), 256, 0, st>>>(n, runptr.p, off.p, nodeptr.p);
+    ctx->timing.launches++;
+    VGA_CUDA(cudaStreamSynchronize(st));
+    VGA_CUDA(cudaGetLastError());
+    return VGA_OK;
+}
+
+// y-major rank of every vertex (perm_y) and its inverse (perm_x); needs the cells' coordinates
+int ensure_perm(vga_ctx *ctx, vga_graph *g) {
+    if (g->perm_y.p) return VGA_OK;
+    cudaStream_t st = ctx->stream;
+    const int64_t n = g->n;
+    int maxx = 0, maxy = 0;
+    for (int64_t v = 0; v < n; v++) {
+        const uint32_t r = (uint32_t)g->h_refs[(size_t)v];
+        maxx = std::max(maxx, (int)(r >> 16));
+        maxy = std::max(maxy, (int)(r & 0xffff));
+    }
+    const int64_t cols = maxx + 1, rows = maxy + 1;
+    DevBuf<int32_t> d_refs;
+    DevBuf<u64> flag, scan;
+    VGA_TRY(d_refs.alloc((size_t)n));
+    VGA_TRY(flag.alloc_zero((size_t)(cols * rows) + 1, st));
+    VGA_TRY(scan.alloc((size_t)(cols * rows) + 1));
+    VGA_TRY(g->perm_y.alloc((size_t)n));
+    VGA_TRY(g->perm_x.alloc((size_t)n));
+    VGA_CUDA(cudaMemcpyAsync(d_refs.p, g->h_refs.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    k_mark_cells_ymajor<<<blocks_for(n, 256), 256, 0, st>>>(n, d_refs.p, (int)cols, flag.p);
+    VGA_TRY(exclusive_sum_u64(ctx, flag.p, scan.p, cols * rows + 1));
+    k_perm_from_scan<<<blocks_for(n, 256), 256, 0, st>>>(n, d_refs.p, (int)cols, scan.p, g->perm_y.p, g->perm_x.p);
+    ctx->timing.launches += 2;
+    VGA_CUDA(cudaStreamSynchronize(st));
+    VGA_CUDA(cudaGetLastError());
+    return VGA_OK;
+}
+
+// the y-major run lists of the out-rows, in x-major row order (k_yruns)
+int build_yruns(vga_ctx *ctx, vga_graph *g, DevBuf<uint64_t> &yptr, DevBuf<uint2> &yruns, int64_t *nruns) {
+    cudaStream_t st = ctx->stream;
+    const int64_t n = g->n;
+    DevBuf<u64> count;
+    VGA_TRY(count.alloc_zero((size_t)n + 1, st));
+    VGA_TRY(yptr.alloc((size_t)n + 1));
+    const size_t words = (size_t)((n + 31) >> 5);
+    const int threads = words >= 8192 ? 1024 : 256;
+    const size_t smem = sizeof(uint32_t) * (words + 1 + 33 + 2);
+    if (smem > ctx->smem_optin) {
+        set_error("y-major rows: the vertex bitmap exceeds shared memory");
+        return VGA_ERR_UNSUPPORTED;
+    }
+    VGA_CUDA(cudaFuncSetAttribute(k_yruns<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VGA_CUDA(cudaFuncSetAttribute(k_yruns<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per_sm = (int)std::max<size_t>(1, std::min<size_t>((size_t)(2048 / threads), (ctx->smem_optin - 1024) / std::max<size_t>(smem, 1)));
+    const unsigned blocks = (unsigned)std::min<int64_t>(std::max<int64_t>(n, 1), (int64_t)ctx->sm_count * per_sm);
+    k_yruns<0><<<blocks, threads, smem, st>>>(n, g->f_runptr.p, g->f_runs.p, g->perm_y.p, count.p, nullptr, nullptr);
+    ctx->timing.launches++;
+    VGA_TRY(exclusive_sum_u64(ctx, count.p, (u64 *)yptr.p, n + 1));
+    uint64_t total = 0;
+    VGA_CUDA(cudaMemcpyAsync(&total, yptr.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    VGA_CUDA(cudaStreamSynchronize(st));
+    *nruns = (int64_t)total;
+    VGA_TRY(yruns.alloc((size_t)total + 1));
+    k_yruns<1><<<blocks, threads, smem, st>>>(n, g->f_runptr.p, g->f_runs.p, g->perm_y.p, nullptr, yptr.p, yruns.p);
+    ctx->timing.launches++;
+    VGA_CUDA(cudaStreamSynchronize(st));
+    VGA_CUDA(cudaGetLastError());
+    return VGA_OK;
+}
+
+// final lists of one direction: per row the shorter of the x-major list (index = row) and the y-major one (index =
+// ymap ? ymap[row] : row)
+int choose_lists(vga_ctx *ctx, int64_t n, const DevBuf<uint64_t> &xptr, const DevBuf<uint32_t> &xnodes, const DevBuf<uint64_t> &yptr,
+                 const DevBuf<uint32_t> &ynodes, const uint32_t *ymap, DevBuf<uint64_t> &optr, DevBuf<uint32_t> &onodes,
+                 DevBuf<uint8_t> &isy, int64_t *nnodes) {
+    cudaStream_t st = ctx->stream;
+    DevBuf<u64> size;
+    VGA_TRY(size.alloc_zero((size_t)n + 1, st));
+    VGA_TRY(isy.alloc((size_t)n + 1));
+    VGA_TRY(optr.alloc((size_t)n + 1));
+    k_choose_lists<<<blocks_for(n, 256), 256, 0, st>>>(n, xptr.p, yptr.p, ymap, size.p, isy.p);
+    ctx->timing.launches++;
+    VGA_TRY(exclusive_sum_u64(ctx, size.p, (u64 *)optr.p, n + 1));
+    uint64_t total = 0;
+    VGA_CUDA(cudaMemcpyAsync(&total, optr.p + n, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    VGA_CUDA(cudaStreamSynchronize(st));
+    *nnodes = (int64_t)total;
+    VGA_TRY(onodes.alloc((size_t)total + 1));
+    k_copy_chosen<<<blocks_for(n * 32, 256), 256, 0, st>>>(n, xptr.p, xnodes.p, yptr.p, ynodes.p, ymap, isy.p, optr.p, onodes.p);
     ctx->timing.launches++;
     VGA_CUDA(cudaStreamSynchronize(st));
     VGA_CUDA(cudaGetLastError());
@@ -1505,18 +1646,61 @@ int row_degrees(vga_ctx *ctx, vga_graph *g) {
 }
 
 int ensure_bfs_lists(vga_ctx *ctx, vga_graph *g, bool transposed) {
-    if (g->n + 2 * (int64_t)pyr_layout(g->n).total >= ((int64_t)1 << 32) || pyr_layout(g->n).levels > PYR_LEVELS_DEV) {
+    const int64_t n = g->n;
+    if (n + 2 * (int64_t)pyr_layout(n).total >= ((int64_t)1 << 32) || pyr_layout(n).levels > PYR_LEVELS_DEV) {
         set_error("too many vertices for 32-bit pyramid node ids");
         return VGA_ERR_UNSUPPORTED;
     }
     VGA_TRY(ensure_fwd_runs(ctx, g));
+    // y-major alternative lists need the cells' coordinates and a vertex bitmap that fits shared memory
+    const bool hybrid = ctx->opt.bfs_hybrid != 0 && n > 1 && (int64_t)g->h_refs.size() >= n &&
+                        sizeof(uint32_t) * ((size_t)((n + 31) >> 5) + 1 + 35) <= ctx->smem_optin;
     if (!g->has_f_nodes) {
-        VGA_TRY(build_nodes(ctx, g->n, g->f_runptr, g->f_runs, g->f_nruns, g->f_nodeptr, g->f_nodes, &g->f_nnodes));
+        if (!hybrid) {
+            VGA_TRY(build_nodes(ctx, n, g->f_runptr, g->f_runs, g->f_nruns, g->f_nodeptr, g->f_nodes, &g->f_nnodes));
+        } else {
+            DevBuf<uint64_t> xptr, yptr;
+            DevBuf<uint32_t> xnodes, ynodes;
+            int64_t nx = 0, ny = 0;
+            VGA_TRY(build_nodes(ctx, n, g->f_runptr, g->f_runs, g->f_nruns, xptr, xnodes, &nx));
+            VGA_TRY(ensure_perm(ctx, g));
+            VGA_TRY(build_yruns(ctx, g, g->fy_runptr, g->fy_runs, &g->fy_nruns));
+            VGA_TRY(build_nodes(ctx, n, g->fy_runptr, g->fy_runs, g->fy_nruns, yptr, ynodes, &ny, g->perm_x.p));
+            VGA_TRY(choose_lists(ctx, n, xptr, xnodes, yptr, ynodes, nullptr, g->f_nodeptr, g->f_nodes, g->f_isy, &g->f_nnodes));
+            g->has_y = true;
+        }
         g->has_f_nodes = true;
     }
     if (transposed && !g->has_t_nodes) {
-        if (!g->has_runs) VGA_TRY(transpose_runs(ctx, g));
-        VGA_TRY(build_nodes(ctx, g->n, g->t_runptr, g->t_runs, g->t_nruns, g->t_nodeptr, g->t_nodes, &g->t_nnodes));
+        if (!g->has_runs) {
+            VGA_TRY(transpose_runs(ctx, n, g->f_runptr, g->f_runs, g->t_runptr, g->t_runs, &g->t_nruns));
+            g->has_runs = true;
+        }
+        if (!g->has_y) {
+            VGA_TRY(build_nodes(ctx, n, g->t_runptr, g->t_runs, g->t_nruns, g->t_nodeptr, g->t_nodes, &g->t_nnodes));
+        } else {
+            cudaStream_t st = ctx->stream;
+            DevBuf<uint64_t> xptr, yptr, yy_ptr, ty_ptr;
+            DevBuf<uint32_t> xnodes, ynodes;
+            DevBuf<uint2> yy_runs, ty_runs;
+            DevBuf<u64> size_y;
+            int64_t nx = 0, ny = 0, ty_nruns = 0;
+            VGA_TRY(build_nodes(ctx, n, g->t_runptr, g->t_runs, g->t_nruns, xptr, xnodes, &nx));
+            // the y-major out-rows in y-major ROW order, transposed in that numbering: in-rows of the y-major world
+            VGA_TRY(size_y.alloc_zero((size_t)n + 1, st));
+            VGA_TRY(yy_ptr.alloc((size_t)n + 1));
+            VGA_TRY(yy_runs.alloc((size_t)g->fy_nruns + 1));
+            k_row_sizes_permuted<<<blocks_for(n, 256), 256, 0, st>>>(n, g->fy_runptr.p, g->perm_y.p, size_y.p);
+            VGA_TRY(exclusive_sum_u64(ctx, size_y.p, (u64 *)yy_ptr.p, n + 1));
+            k_rows_copy_permuted<<<blocks_for(n * 32, 256), 256, 0, st>>>(n, g->fy_runptr.p, g->fy_runs.p, g->perm_y.p, yy_ptr.p, yy_runs.p);
+            ctx->timing.launches += 2;
+            VGA_TRY(transpose_runs(ctx, n, yy_ptr, yy_runs, ty_ptr, ty_runs, &ty_nruns));
+            VGA_TRY(build_nodes(ctx, n, ty_ptr, ty_runs, ty_nruns, yptr, ynodes, &ny, g->perm_x.p));
+            // the in-row of vertex v in the y-major world is row perm_y[v]
+            VGA_TRY(choose_lists(ctx, n, xptr, xnodes, yptr, ynodes, g->perm_y.p, g->t_nodeptr, g->t_nodes, g->t_isy, &g->t_nnodes));
+            g->fy_runs.release();  // only needed for this derivation
+            g->fy_runptr.release();
+        }
         g->has_t_nodes = true;
     }
     return VGA_OK;

@@ -31,6 +31,7 @@ static int set_option(Options &o, const std::string &key, int64_t value) {
     else if (key == "bfs_wide_nodes") o.bfs_wide_nodes = value;
     else if (key == "bfs_coop") o.bfs_coop = value;
     else if (key == "bfs_pull_unroll") o.bfs_pull_unroll = value;
+    else if (key == "bfs_hybrid") o.bfs_hybrid = value;
     else if (key == "local_mode") o.local_mode = value;
     else if (key == "local_span") o.local_span = value;
     else if (key == "sieve_mode") o.sieve_mode = value;

@@ -263,6 +263,7 @@ struct Options {
     int64_t bfs_coop = 1;        // W >= 4: W/2 lanes share a node, 16 bytes each (k_push_nodes_coop / k_pull_nodes_coop; measured
                                  // on the 10^6-cell bench subset: level kernels 1792 ms at W = 2 -> 1508 ms at W = 4); 0 = one
                                  // lane per node for every W
+    int64_t bfs_hybrid = 1;      // every row is walked as the shorter of its x-major and y-major pyramid-node lists (0 = x-major only)
     int64_t bfs_pull_unroll = 4; // node loads per lane between two early-exit checks of the bottom-up step: 4 (measured on the
                                  // C5 bench subset: level kernels 1483 -> 1439 ms) or 2
     int64_t bfs_wide_nodes = 384; // auto word width with bfs_coop = 0: 4 words from this many pyramid nodes per out-row, else 2
@@ -333,6 +334,16 @@ struct vga_graph {
     vga::DevBuf<uint64_t> f_nodeptr, t_nodeptr;  // [n+1]
     vga::DevBuf<uint32_t> f_nodes, t_nodes;
     bool has_f_nodes = false, has_t_nodes = false;
+    // y-major alternative (bfs.cu): perm_y[v] = rank of cell v in y-major order, perm_x = its inverse; f_isy / t_isy[v] = 1
+    // when the list of row v is the y-major one (inner node ids then refer to the pyramid over the y-major order; leaf ids
+    // are x-major ordinals in both kinds of list); fy_runs = y-major out-rows in x-major row order (kept until the in-rows
+    // are derived)
+    vga::DevBuf<uint32_t> perm_y, perm_x;
+    vga::DevBuf<uint8_t> f_isy, t_isy;
+    vga::DevBuf<uint64_t> fy_runptr;
+    vga::DevBuf<uint2> fy_runs;
+    int64_t fy_nruns = 0;
+    bool has_y = false;
     vga::DevBuf<uint32_t> deg;                   // [n] entries per row when the graph holds runs only (statistics), else empty
     // bit matrices of the tensor-core local kernel (local_tc.cu), built on first use: A[v][w] and its transpose A^T[w][u]
     vga::DevBuf<uint32_t> tc_bits_a, tc_bits_t;

@@ -148,7 +148,7 @@ template <typename F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribu
 // ---------------------------------------------------------------------------------------------- SIMT core
 namespace simt {
 
-enum Op { OP_NONE, OP_BALLOT, OP_ANY, OP_SHFL, OP_SHFL_DOWN, OP_SHFL_UP, OP_SHFL_XOR, OP_RED_OR, OP_RED_ADD, OP_SYNCWARP, OP_SYNCTHREADS };
+enum Op { OP_NONE, OP_BALLOT, OP_ANY, OP_SHFL, OP_SHFL_DOWN, OP_SHFL_UP, OP_SHFL_XOR, OP_RED_OR, OP_RED_ADD, OP_RED_MIN, OP_RED_MAX, OP_SYNCWARP, OP_SYNCTHREADS };
 
 // Fiber switch.  x86-64: a hand-written switch of the callee-saved registers and the stack pointer (glibc's swapcontext
 // makes a signal-mask system call per switch, which dominated the run time); elsewhere: ucontext.
@@ -268,9 +268,11 @@ inline void resolve_warp(Lane *w, int count, bool &progress) {
         }
         if (!ready) continue;
         auto in = [&](int l) { return l >= 0 && l < count && ((a.mask >> l) & 1u) && !w[l].done; };
-        uint64_t red = 0;
+        uint64_t red = a.op == OP_RED_MIN ? ~0ull : 0;
         for (int l = 0; l < 32; l++)
             if (in(l)) {
+                if (a.op == OP_RED_MIN && w[l].val < red) red = w[l].val;
+                if (a.op == OP_RED_MAX && w[l].val > red) red = w[l].val;
                 if (a.op == OP_BALLOT || a.op == OP_ANY) red |= (w[l].val ? 1ull : 0ull) << l;
                 if (a.op == OP_RED_OR) red |= w[l].val;
                 if (a.op == OP_RED_ADD) red += w[l].val;
@@ -281,7 +283,7 @@ inline void resolve_warp(Lane *w, int count, bool &progress) {
             switch (a.op) {
             case OP_BALLOT: res[l] = red; break;
             case OP_ANY: res[l] = red != 0; break;
-            case OP_RED_OR: case OP_RED_ADD: res[l] = red; break;
+            case OP_RED_OR: case OP_RED_ADD: case OP_RED_MIN: case OP_RED_MAX: res[l] = red; break;
             case OP_SHFL: { int s = w[l].arg & 31; res[l] = in(s) ? w[s].val : w[l].val; break; }
             case OP_SHFL_DOWN: { int s = l + w[l].arg; res[l] = (s < 32 && in(s)) ? w[s].val : w[l].val; break; }
             case OP_SHFL_UP: { int s = l - w[l].arg; res[l] = (s >= 0 && in(s)) ? w[s].val : w[l].val; break; }
@@ -429,6 +431,8 @@ template <typename T> inline T __shfl_xor_sync(unsigned mask, T v, int lanemask,
 }
 inline unsigned __reduce_or_sync(unsigned mask, unsigned v) { return (unsigned)simt::collective(simt::OP_RED_OR, mask, v, 0); }
 inline unsigned __reduce_add_sync(unsigned mask, unsigned v) { return (unsigned)simt::collective(simt::OP_RED_ADD, mask, v, 0); }
+inline unsigned __reduce_min_sync(unsigned mask, unsigned v) { return (unsigned)simt::collective(simt::OP_RED_MIN, mask, v, 0); }
+inline unsigned __reduce_max_sync(unsigned mask, unsigned v) { return (unsigned)simt::collective(simt::OP_RED_MAX, mask, v, 0); }
 inline int __reduce_add_sync(unsigned mask, int v) { return (int)(unsigned)simt::collective(simt::OP_RED_ADD, mask, (unsigned)v, 0); }
 
 // position of the offset-th set bit of mask counting from bit `base` upwards (offset > 0), 0xffffffff if there is none

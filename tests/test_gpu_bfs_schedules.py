@@ -109,6 +109,37 @@ def test_explicit_source_lists(name):
 
 
 @pytest.mark.parametrize("name", ["oblique:30:30:7", "office:64:64:1", "urban:120:120:4", "room:24:24:1+holes"])
+@pytest.mark.parametrize("mode,words", [(0, 4), (1, 4), (2, 0), (1, 1)])
+def test_hybrid_x_or_y_major_lists_vs_oracle(name, mode, words):
+    """bfs_hybrid = 1 (default): every row is walked as the shorter of its x-major and y-major pyramid-node lists (second
+    pyramid over the y-major vertex order).  Never longer than x-major only, and the same integers as the oracle in every
+    direction (top-down only pins the y-major out-lists, bottom-up only the y-major in-lists)."""
+    flat, og = oracle_for(name)
+    sizes = {}
+    res = {}
+    for hyb in (0, 1):
+        c = capi.Context(0)
+        for k, v in (("bfs_hybrid", hyb), ("bfs_mode", mode), ("bfs_words", words)):
+            c.set_option(k, v)
+        g = c.build(flat)
+        res[hyb] = g.global_ints(-1)
+        sizes[hyb] = g.list_sizes()
+        c.close()
+    assert sizes[1]["out_nodes"] <= sizes[0]["out_nodes"] and sizes[1]["out_runs"] == sizes[0]["out_runs"]
+    if mode != 0:
+        assert sizes[1]["in_nodes"] <= sizes[0]["in_nodes"]
+    for a, b in zip(res[0][:3], res[1][:3]):
+        assert np.array_equal(a, b)
+    tn, td, dist, _ = res[1]
+    rng = np.random.RandomState(11)
+    for s in rng.choice(len(tn), min(len(tn), 32), replace=False):
+        otn, otd, odist, onl = og.global_ints(-1, (int(s), int(s) + 1), maxl=64)
+        L = dist.shape[1]
+        assert otn[0] == tn[s] and otd[0] == td[s]
+        assert np.array_equal(odist[0, :L], dist[s]) and not odist[0, L:].any()
+
+
+@pytest.mark.parametrize("name", ["oblique:30:30:7", "office:64:64:1", "urban:120:120:4", "room:24:24:1+holes"])
 def test_row_ordering_kernels_vs_oracle(name):
     """build_sort = 1 (default): rows ordered by bitmap rank in shared memory (k_rank_sort); build_sort = 0: CUB segmented
     radix sort.  The sorted adjacency incl. bins, accepted flags and ghost columns must equal the oracle's and each other."""
