@@ -851,6 +851,7 @@ __global__ void k_yruns(int64_t n, const uint64_t *runptr, const uint2 *runs, co
     uint32_t *bm = ysm;                 // [words + 1] (one zero word behind the end)
     uint32_t *wt = ysm + words + 1;     // [33] scan scratch, then [2] range
     uint32_t *range = wt + 33;
+    uint32_t *run_first = range + 2, *run_off = run_first + blockDim.x;  // [blockDim.x] each: the chunk of runs in flight
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     // the whole bitmap is zero between rows: every row clears the range it used
     for (uint32_t i = threadIdx.x; i <= words; i += blockDim.x) bm[i] = 0u;
@@ -862,15 +863,31 @@ __global__ void k_yruns(int64_t n, const uint64_t *runptr, const uint2 *runs, co
     for (int64_t u = blockIdx.x; u < n; u += gridDim.x) {
         const uint64_t r0 = runptr[u], r1 = runptr[u + 1];
         uint32_t lo = 0xffffffffu, hi = 0u;
-        for (uint64_t r = r0 + wid; r < r1; r += nw) {
-            const uint2 run = runs[r];
-            if (run.x >= (uint32_t)n) continue;  // ghost columns are not part of the BFS
-            for (uint32_t w = run.x + lane; w < run.x + run.y; w += 32) {
-                const uint32_t y = perm_y[w];
+        // blockDim.x runs at a time: their lengths are scanned and the CELLS are dealt out to the threads (binary search of
+        // the cell index in the scanned offsets), so the two dependent loads (run, perm_y) are paid once per chunk
+        for (uint64_t rb = r0; rb < r1; rb += blockDim.x) {
+            const uint64_t r = rb + threadIdx.x;
+            uint2 run = make_uint2(0u, 0u);
+            if (r < r1) run = runs[r];
+            if (run.x >= (uint32_t)n) run.y = 0u;  // ghost columns are not part of the BFS
+            uint32_t cells = 0;
+            const uint32_t off = block_excl_scan(run.y, wt, &cells);
+            run_first[threadIdx.x] = run.x;
+            run_off[threadIdx.x] = off;
+            __syncthreads();
+            const uint32_t nr = (uint32_t)min((uint64_t)blockDim.x, r1 - rb);
+            for (uint32_t c = threadIdx.x; c < cells; c += blockDim.x) {
+                uint32_t a = 0, b = nr;  // last run whose offset is <= c
+                while (b - a > 1) {
+                    const uint32_t m = (a + b) >> 1;
+                    if (run_off[m] <= c) a = m; else b = m;
+                }
+                const uint32_t y = perm_y[run_first[a] + (c - run_off[a])];
                 atomicOr(&bm[y >> 5], 1u << (y & 31));
                 lo = min(lo, y >> 5);
                 hi = max(hi, y >> 5);
             }
+            __syncthreads();
         }
         lo = __reduce_min_sync(FULL, lo);
         hi = __reduce_max_sync(FULL, hi);
@@ -1548,7 +1565,7 @@ int build_yruns(vga_ctx *ctx, vga_graph *g, DevBuf<uint64_t> &yptr, DevBuf<uint2
     VGA_TRY(yptr.alloc((size_t)n + 1));
     const size_t words = (size_t)((n + 31) >> 5);
     const int threads = words >= 8192 ? 1024 : 256;
-    const size_t smem = sizeof(uint32_t) * (words + 1 + 33 + 2);
+    const size_t smem = sizeof(uint32_t) * (words + 1 + 33 + 2 + 2 * (size_t)threads);
     if (smem > ctx->smem_optin) {
         set_error("y-major rows: the vertex bitmap exceeds shared memory");
         return VGA_ERR_UNSUPPORTED;
@@ -1653,8 +1670,10 @@ int ensure_bfs_lists(vga_ctx *ctx, vga_graph *g, bool transposed) {
     }
     VGA_TRY(ensure_fwd_runs(ctx, g));
     // y-major alternative lists need the cells' coordinates and a vertex bitmap that fits shared memory
-    const bool hybrid = ctx->opt.bfs_hybrid != 0 && n > 1 && (int64_t)g->h_refs.size() >= n &&
-                        sizeof(uint32_t) * ((size_t)((n + 31) >> 5) + 1 + 35) <= ctx->smem_optin;
+    const bool want_y = ctx->opt.bfs_hybrid >= 2 ||
+                        (ctx->opt.bfs_hybrid == 1 && (ctx->bfs_sources_hint < 0 || ctx->bfs_sources_hint * 4 >= n));
+    const bool hybrid = want_y && n > 1 && (int64_t)g->h_refs.size() >= n &&
+                        sizeof(uint32_t) * ((size_t)((n + 31) >> 5) + 1 + 35 + 2048) <= ctx->smem_optin;
     if (!g->has_f_nodes) {
         if (!hybrid) {
             VGA_TRY(build_nodes(ctx, n, g->f_runptr, g->f_runs, g->f_nruns, g->f_nodeptr, g->f_nodes, &g->f_nnodes));
@@ -1729,6 +1748,11 @@ int run_global(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources, i
     }
     if (levels_used) *levels_used = 0;
     if (nsrc <= 0) return VGA_OK;
+    ctx->bfs_sources_hint = nsrc;
+    struct HintReset {
+        vga_ctx *c;
+        ~HintReset() { c->bfs_sources_hint = -1; }
+    } hint_reset{ctx};
     int words = (int)ctx->opt.bfs_words;
     if (words <= 0) {
         // auto (measured on B200, profiles/README.md): four words (256 sources) per batch with the lane-cooperative kernels

@@ -263,7 +263,10 @@ struct Options {
     int64_t bfs_coop = 1;        // W >= 4: W/2 lanes share a node, 16 bytes each (k_push_nodes_coop / k_pull_nodes_coop; measured
                                  // on the 10^6-cell bench subset: level kernels 1792 ms at W = 2 -> 1508 ms at W = 4); 0 = one
                                  // lane per node for every W
-    int64_t bfs_hybrid = 1;      // every row is walked as the shorter of its x-major and y-major pyramid-node lists (0 = x-major only)
+    int64_t bfs_hybrid = 1;      // every row is walked as the shorter of its x-major and y-major pyramid-node lists: 2 = always,
+                                 // 0 = x-major only, 1 = when the call that derives the lists has at least n / 4 sources
+                                 // (measured on the 10^6-cell plan: the second set of lists costs ~0.2 us per row once per
+                                 // graph and saves ~1 us per source; a rank of an 8-GPU run has n / 8 sources)
     int64_t bfs_pull_unroll = 4; // node loads per lane between two early-exit checks of the bottom-up step: 4 (measured on the
                                  // C5 bench subset: level kernels 1483 -> 1439 ms) or 2
     int64_t bfs_wide_nodes = 384; // auto word width with bfs_coop = 0: 4 words from this many pyramid nodes per out-row, else 2
@@ -283,6 +286,7 @@ struct vga_ctx {
     vga_progress_fn progress = nullptr;
     vga_cancel_fn cancel = nullptr;
     void *user = nullptr;
+    int64_t bfs_sources_hint = -1;  // sources of the vga_global call in progress (-1 = unknown): decides whether y-major lists pay
 };
 
 struct vga_dgrid {

@@ -119,7 +119,7 @@ def test_hybrid_x_or_y_major_lists_vs_oracle(name, mode, words):
     res = {}
     for hyb in (0, 1):
         c = capi.Context(0)
-        for k, v in (("bfs_hybrid", hyb), ("bfs_mode", mode), ("bfs_words", words)):
+        for k, v in (("bfs_hybrid", 2 * hyb), ("bfs_mode", mode), ("bfs_words", words)):
             c.set_option(k, v)
         g = c.build(flat)
         res[hyb] = g.global_ints(-1)

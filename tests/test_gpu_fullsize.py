@@ -86,6 +86,7 @@ def test_c2_complete_adjacency_statistics_and_sampled_analyses():
     from oracle import pyoracle as po
     flat = capi.prepare(plans.by_name("C2"))
     c = capi.Context(0)
+    c.set_option("bfs_hybrid", 2)  # x-major / y-major lists whatever the number of sources of the first call
     g = c.build(flat)
     og = po.OracleGraph(oracle_grid(flat))
     rp, col, b, acc = g.csr()
@@ -128,6 +129,7 @@ def test_c5_sampled_rows_sources_and_cells():
     several BFS chunks, adjacency slices beyond 2^31 entries and 64-bit row offsets, pinned against the oracle."""
     flat = capi.prepare(plans.by_name("C5"))
     c = capi.Context(0)
+    c.set_option("bfs_hybrid", 2)  # the y-major lists at full size (C4 above runs x-major only: few sources per call)
     g = c.build(flat)
     assert g.entries > 2 ** 32
     check_rows_vs_oracle(g, flat, sample_blocks(g.n, 4, 32, 7) + [(g.n - 16, g.n)])
