@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 HOST = os.path.join(HERE, "host")
 LIB = os.path.join(HERE, "lib")
-CU = ["makegraph", "bfs", "local", "local_tc", "stepdepth", "cabi"]
+CU = ["makegraph", "bfs", "local", "local_tc", "stepdepth", "metric", "cabi"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

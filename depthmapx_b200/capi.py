@@ -39,7 +39,7 @@ ABI_SYMBOLS = [
     "vga_graph_node_stats", "vga_graph_set_noexpand", "vga_global", "vga_global_attributes", "vga_local", "vga_local_attributes", "vga_step_depth",
     "vga_graph_device_rows", "vga_graph_from_device_rows", "vga_global_sources", "vga_graph_batch_order",
     "vga_graph_device_runs", "vga_graph_from_device_runs", "vga_graph_runs_alloc", "vga_graph_runs_commit",
-    "vga_graph_device_degrees", "vga_graph_list_sizes",
+    "vga_graph_device_degrees", "vga_graph_list_sizes", "vga_metric", "vga_angular",
 ]
 HOST_SYMBOLS = [
     "dmxh_last_error", "dmxh_map_create", "dmxh_map_destroy", "dmxh_map_grid", "dmxh_map_block_lines", "dmxh_map_fill",
@@ -94,6 +94,8 @@ def abi():
         L.vga_global_attributes.argtypes = [i64, vp, vp, vp, C.c_int32] + [vp] * 7
         L.vga_local.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp]
         L.vga_step_depth.argtypes = [vp, vp, vp, i64, vp]
+        L.vga_metric.argtypes = [vp, vp, vp, C.c_double, C.c_double, vp, i64, vp, vp, vp, vp, C.POINTER(i64)]
+        L.vga_angular.argtypes = [vp, vp, vp, C.c_double, vp, i64, vp, vp, vp, C.POINTER(i64)]
         L.vga_local_attributes.argtypes = [i64] + [vp] * 7
         L.vga_graph_device_rows.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
         L.vga_graph_from_device_rows.argtypes = [vp, i64, i64, vp, vp, i64, C.POINTER(vp)]
@@ -419,6 +421,30 @@ class Graph:
         check(abi().vga_step_depth(self.ctx.h, self.h, _p(src), len(src), _p(d)))
         return d
 
+    def metric(self, blocked_adjacent, spacing, radius=-1.0, sources=None):
+        """VGAMetric::run for the listed source ordinals (None = all): float32 columns (Metric Mean Shortest-Path Angle,
+        Metric Mean Shortest-Path Distance, Metric Mean Straight-Line Distance, Metric Node Count) + the number of
+        turn-angle evaluations whose float rounding is not guaranteed (see include/vga_b200.h)."""
+        ba = np.ascontiguousarray(blocked_adjacent, np.uint8)
+        src = None if sources is None else np.ascontiguousarray(sources, np.int64)
+        k = self.n if src is None else len(src)
+        out = [np.zeros(k, np.float32) for _ in range(4)]
+        unsafe = i64()
+        check(abi().vga_metric(self.ctx.h, self.h, _p(ba), float(spacing), float(radius), None if src is None else _p(src), k,
+                               *[_p(a) for a in out], C.byref(unsafe)))
+        return tuple(out) + (unsafe.value,)
+
+    def angular(self, blocked_adjacent, radius=-1.0, sources=None):
+        """VGAAngular::run: (Angular Mean Depth, Angular Total Depth, Angular Node Count, unsafe angle evaluations)."""
+        ba = np.ascontiguousarray(blocked_adjacent, np.uint8)
+        src = None if sources is None else np.ascontiguousarray(sources, np.int64)
+        k = self.n if src is None else len(src)
+        out = [np.zeros(k, np.float32) for _ in range(3)]
+        unsafe = i64()
+        check(abi().vga_angular(self.ctx.h, self.h, _p(ba), float(radius), None if src is None else _p(src), k,
+                                *[_p(a) for a in out], C.byref(unsafe)))
+        return tuple(out) + (unsafe.value,)
+
     def local_ints(self, src=None):
         b, e = (0, self.n) if src is None else src
         k = e - b
@@ -697,6 +723,20 @@ class GraphFile:
     def save(self, path):
         if host().dmxh_graph_save(self.h, os.fsencode(path)) < 0:
             raise RuntimeError(host().dmxh_last_error().decode())
+
+
+def blocked_adjacent(flat) -> np.ndarray:
+    """uint8 [N] per filled cell (x-major): the cell is BLOCKED (Point::m_state & 0x0004) or one of its eight neighbours
+    inside the grid is (Point::blocked || PointMap::blockedAdjacent, salalib/pointdata.cpp:1016-1066) -- the cells
+    VGAMetric / VGAAngular expand (salalib/ngraph.cpp:71, 82)."""
+    st = np.asarray(flat.state).reshape(flat.cols, flat.rows)
+    pad = np.zeros((flat.cols + 2, flat.rows + 2), bool)
+    pad[1:-1, 1:-1] = (st & 0x0004) != 0
+    near = np.zeros((flat.cols, flat.rows), bool)
+    for dx in (0, 1, 2):
+        for dy in (0, 1, 2):
+            near |= pad[dx:dx + flat.cols, dy:dy + flat.rows]
+    return near.reshape(-1)[((st & 0x0002) != 0).reshape(-1)].astype(np.uint8)
 
 
 def prepare(plan, maxdist=-1.0) -> FlatGrid:

@@ -267,6 +267,7 @@ struct Options {
                                  // 0 = x-major only, 1 = when the call that derives the lists has at least n / 4 sources
                                  // (measured on the 10^6-cell plan: the second set of lists costs ~0.2 us per row once per
                                  // graph and saves ~1 us per source; a rank of an 8-GPU run has n / 8 sources)
+    int64_t metric_slots = 0;    // metric / angular VGA: sources (warps) in flight, 0 = resident warps bounded by memory
     int64_t bfs_pull_unroll = 4; // node loads per lane between two early-exit checks of the bottom-up step: 4 (measured on the
                                  // C5 bench subset: level kernels 1483 -> 1439 ms) or 2
     int64_t bfs_wide_nodes = 384; // auto word width with bfs_coop = 0: 4 words from this many pyramid nodes per out-row, else 2
@@ -371,6 +372,9 @@ int batch_source_order_list(vga_ctx *ctx, vga_graph *g, const int64_t *sources, 
 // sources: explicit list of ordinals (nullptr = the range [src_begin, src_end)); outputs in list order
 int run_global(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources, int64_t src_begin, int64_t src_end,
                int32_t *total_nodes, int64_t *total_depth, int32_t *dist, int32_t max_levels, int32_t *levels_used);
+// metric.cu: metric (angular = 0: 4 output columns) / angular (3 columns) VGA for an explicit list of sources
+int run_metric_angular(vga_ctx *ctx, vga_graph *g, int angular, const uint8_t *expand, double spacing, double radius,
+                       const int64_t *sources, int64_t nsrc, float *const *out, int nout, int64_t *angle_unsafe);
 // stepdepth.cu
 int run_step_depth(vga_ctx *ctx, vga_graph *g, const int64_t *sources, int64_t nsrc, int32_t *depth_out);
 // local_tc.cu: tcgen05 kernel for dense graphs (cluster, k, total; control comes from local.cu)

@@ -15,6 +15,8 @@
  *   vga_global_attributes the formula stage of VGAVisualGlobal::run :131-193 (host, glibc libm)
  *   vga_local             VGAVisualLocal::run salalib/vgamodules/vgavisuallocal.cpp:41-81
  *   vga_local_attributes  the formula stage :84-96
+ *   vga_metric/vga_angular VGAMetric::run / VGAAngular::run salalib/vgamodules/vgametric.cpp:25-136,
+ *                         vgaangular.cpp:22-133 (row f4)
  *
  * Conventions: every function returns 0 on success and a negative vga_status otherwise;
  * vga_last_error() gives the message of the last failure on the calling thread.  There is NO CPU
@@ -194,6 +196,26 @@ int vga_local_attributes(int64_t n, const int64_t *cluster, const int32_t *k, co
  * ordinals, the map's selection); depth[v] for all N cells = level at which v is first reached, -1 if
  * never.  No merge links / context fill. */
 int vga_step_depth(vga_ctx *ctx, const vga_graph *g, const int64_t *sources, int64_t n_sources, int32_t *depth);
+
+/* Metric / angular VGA (VGAMetric::run salalib/vgamodules/vgametric.cpp:25-136, VGAAngular::run
+ * salalib/vgamodules/vgaangular.cpp:22-133, extractMetric / extractAngular salalib/ngraph.cpp:67-87, 329-365): per
+ * source a shortest-path search over the iterated adjacency with float32 keys (path length in cells / cumulated turn in
+ * units of 90 degrees), pops in the order of the reference's std::set<(key, pixel)>, float32 sums in pop order.
+ * blocked_adjacent[v] != 0 (N bytes, x-major ordinals) for cells that are BLOCKED or have a BLOCKED cell among their
+ * eight neighbours (Point::blocked / PointMap::blockedAdjacent, salalib/pointdata.cpp:1016-1066): only those and the
+ * source are expanded.  The graph needs cell coordinates (vga_graph_build gives them, else vga_graph_set_cell_refs).
+ * sources = ordinals (NULL = all N cells, n_sources ignored); outputs in list order, exactly the values
+ * AttributeRow::setValue receives: vga_metric -> "Metric Mean Shortest-Path Angle", "Metric Mean Shortest-Path
+ * Distance", "Metric Mean Straight-Line Distance", "Metric Node Count"; vga_angular -> "Angular Mean Depth", "Angular
+ * Total Depth", "Angular Node Count".  radius -1.0 = n (metric: in map units, compared with key * spacing; angular: in
+ * units of 90 degrees).  Any output may be NULL.  *angle_unsafe = number of turn-angle evaluations whose float32
+ * rounding could depend on the last bits of acos (0 = the angle sums are guaranteed bit-equal to a glibc host; distances
+ * and node counts of vga_metric never depend on it).  No merge links. */
+int vga_metric(vga_ctx *ctx, const vga_graph *g, const uint8_t *blocked_adjacent, double spacing, double radius,
+               const int64_t *sources, int64_t n_sources, float *mean_angle, float *mean_path_dist, float *mean_line_dist,
+               float *node_count, int64_t *angle_unsafe);
+int vga_angular(vga_ctx *ctx, const vga_graph *g, const uint8_t *blocked_adjacent, double radius, const int64_t *sources,
+                int64_t n_sources, float *mean_depth, float *total_depth, float *node_count, int64_t *angle_unsafe);
 
 /* ---- device-resident access for multi-GPU plumbing (pointers are CUDA device pointers) ------ */
 

@@ -108,6 +108,10 @@ def olib():
         L.vgao_local_formulas.argtypes = [C.c_int64] + [C.c_void_p] * 7
         L.vgao_step_depth.restype = C.c_int
         L.vgao_step_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.vgao_metric.restype = C.c_int
+        L.vgao_metric.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int64, C.c_int64] + [C.c_void_p] * 4
+        L.vgao_angular.restype = C.c_int
+        L.vgao_angular.argtypes = [C.c_void_p, C.c_double, C.c_int64, C.c_int64] + [C.c_void_p] * 3
         L.vgao_global_csr.restype = C.c_int
         L.vgao_global_csr.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_int32]
@@ -196,6 +200,21 @@ class OracleGraph:
         d = np.zeros(self.n, np.int32)
         olib().vgao_step_depth(self.h, _p(src), len(src), _p(d))
         return d
+
+    def metric(self, spacing, radius=-1.0, src=None):
+        """(Metric Mean Shortest-Path Angle, Metric Mean Shortest-Path Distance, Metric Mean Straight-Line Distance,
+        Metric Node Count) as float32 columns of the sources src = (begin, end)."""
+        b, e = (0, self.n) if src is None else src
+        out = [np.zeros(e - b, np.float32) for _ in range(4)]
+        olib().vgao_metric(self.h, float(spacing), float(radius), b, e, *[_p(a) for a in out])
+        return tuple(out)
+
+    def angular(self, radius=-1.0, src=None):
+        """(Angular Mean Depth, Angular Total Depth, Angular Node Count) as float32 columns."""
+        b, e = (0, self.n) if src is None else src
+        out = [np.zeros(e - b, np.float32) for _ in range(3)]
+        olib().vgao_angular(self.h, float(radius), b, e, *[_p(a) for a in out])
+        return tuple(out)
 
     def local_ints(self, src=None):
         b, e = (0, self.n) if src is None else src
@@ -320,6 +339,10 @@ def rlib():
         L.dmxref_vga_global.argtypes = [C.c_void_p, C.c_double, C.c_int]
         L.dmxref_vga_local.restype = C.c_double
         L.dmxref_vga_local.argtypes = [C.c_void_p, C.c_int]
+        L.dmxref_vga_metric.restype = C.c_double
+        L.dmxref_vga_metric.argtypes = [C.c_void_p, C.c_double]
+        L.dmxref_vga_angular.restype = C.c_double
+        L.dmxref_vga_angular.argtypes = [C.c_void_p, C.c_double]
         L.dmxref_step_depth.restype = C.c_double
         L.dmxref_step_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.dmxref_sample_makegraph.restype = C.c_double
@@ -431,6 +454,12 @@ class RefMap:
 
     def vga_local(self, simple=False):
         return rlib().dmxref_vga_local(self.h, int(simple))
+
+    def vga_metric(self, radius=-1.0):
+        return rlib().dmxref_vga_metric(self.h, radius)
+
+    def vga_angular(self, radius=-1.0):
+        return rlib().dmxref_vga_angular(self.h, radius)
 
     def step_depth(self, sources):
         src = np.ascontiguousarray(sources, np.int32)

@@ -61,6 +61,8 @@
 #include "salalib/vgamodules/vgavisualglobal.h"
 #include "salalib/vgamodules/vgavisuallocal.h"
 #include "salalib/vgamodules/vgavisualglobaldepth.h"
+#include "salalib/vgamodules/vgametric.h"
+#include "salalib/vgamodules/vgaangular.h"
 #undef protected
 #undef private
 
@@ -306,6 +308,24 @@ double dmxref_vga_local(void *h, int simple) {
     PointMap &m = *static_cast<Ref *>(h)->map;
     double t0 = now_s();
     bool ok = VGAVisualLocal(false).run(nullptr, m, simple != 0);
+    double t1 = now_s();
+    return ok ? (t1 - t0) : -1.0;
+}
+
+// Metric / angular VGA: the reference's VGAMetric::run / VGAAngular::run (salalib/vgamodules/vgametric.cpp,
+// vgaangular.cpp) unmodified; results are the "Metric ..." / "Angular ..." columns via dmxref_attr.
+double dmxref_vga_metric(void *h, double radius) {
+    PointMap &m = *static_cast<Ref *>(h)->map;
+    double t0 = now_s();
+    bool ok = VGAMetric(radius, false).run(nullptr, m, false);
+    double t1 = now_s();
+    return ok ? (t1 - t0) : -1.0;
+}
+
+double dmxref_vga_angular(void *h, double radius) {
+    PointMap &m = *static_cast<Ref *>(h)->map;
+    double t0 = now_s();
+    bool ok = VGAAngular(radius, false).run(nullptr, m, false);
     double t1 = now_s();
     return ok ? (t1 - t0) : -1.0;
 }

@@ -1047,3 +1047,193 @@ int vgao_step_depth(const vgao_graph *gr, const int32_t *src, int64_t nsrc, int3
     free(nxt);
     return 0;
 }
+
+/* ---------------------------------------------------------------- metric / angular VGA
+ * VGAMetric::run salalib/vgamodules/vgametric.cpp:25-136, VGAAngular::run vgaangular.cpp:22-133,
+ * Node/Bin::extractMetric / extractAngular salalib/ngraph.cpp:67-87, 329-365, MetricTriple / AngularTriple ordering
+ * salalib/pointdata.h:377-419, dist / angle salalib/pixelref.h:116-131, blockedAdjacent pointdata.cpp:1016-1066.
+ *
+ * A Dijkstra-like search per source over the ITERATED adjacency with a std::set<(key, pixel, lastpixel)> ordered by
+ * (key, pixel) -- here a binary heap ordered by (key, pixel, insertion number): the set refuses a second element
+ * with an equal (key, pixel), which then pops where the first one did; the heap pops the later duplicate right after
+ * the first, when the pixel is already finalised (or is not a filled cell), so it is ignored either way.
+ * Per-cell state of the reference (Point::m_misc / m_dist / m_cumangle) is kept for ALL cells, filled or not, because
+ * the gaps of diagonal bins are relaxed and queued like any other pixel (they are never expanded).
+ * No merge links (the oracle has none).  radius < 0 (-1.0) = unlimited. */
+#define ST_BLOCKED 0x0004 /* salalib/point.h:33 */
+typedef struct { float key; int32_t ref, last; uint64_t seq; } HeapE;
+static inline int heap_less(const HeapE *a, const HeapE *b) {
+    if (a->key != b->key) return a->key < b->key;
+    int ax = ref_x(a->ref), bx = ref_x(b->ref);
+    if (ax != bx) return ax < bx; /* PixelRef operator<, pixelref.h:95-98 */
+    int ay = ref_y(a->ref), by = ref_y(b->ref);
+    if (ay != by) return ay < by;
+    return a->seq < b->seq;
+}
+typedef struct { HeapE *e; int64_t n, cap; uint64_t seq; } Heap;
+static void heap_push(Heap *h, float key, int32_t ref, int32_t last) {
+    if (h->n == h->cap) {
+        h->cap = h->cap ? 2 * h->cap : 1024;
+        h->e = (HeapE *)realloc(h->e, sizeof(HeapE) * h->cap);
+    }
+    HeapE x = {key, ref, last, h->seq++};
+    int64_t i = h->n++;
+    while (i > 0) {
+        int64_t p = (i - 1) / 2;
+        if (!heap_less(&x, &h->e[p])) break;
+        h->e[i] = h->e[p];
+        i = p;
+    }
+    h->e[i] = x;
+}
+static HeapE heap_pop(Heap *h) {
+    HeapE top = h->e[0], x = h->e[--h->n];
+    int64_t i = 0;
+    for (;;) {
+        int64_t c = 2 * i + 1;
+        if (c >= h->n) break;
+        if (c + 1 < h->n && heap_less(&h->e[c + 1], &h->e[c])) c++;
+        if (!heap_less(&h->e[c], &x)) break;
+        h->e[i] = h->e[c];
+        i = c;
+    }
+    if (h->n > 0) h->e[i] = x;
+    return top;
+}
+static inline int cell_blocked(const vgao_graph *gr, int x, int y) {
+    return x >= 0 && x < gr->cols && y >= 0 && y < gr->rows && (gr->state[(int64_t)x * gr->rows + y] & ST_BLOCKED) != 0;
+}
+/* Node::extractMetric / extractAngular expand a popped pixel only if its key is 0 or it is blocked or has a blocked cell
+ * among its 8 neighbours (ngraph.cpp:71, 82) */
+static int expands(const vgao_graph *gr, int32_t r) {
+    int x = ref_x(r), y = ref_y(r);
+    for (int dx = -1; dx <= 1; dx++)
+        for (int dy = -1; dy <= 1; dy++)
+            if (cell_blocked(gr, x + dx, y + dy)) return 1;
+    return 0;
+}
+static inline double ref_dist(int32_t a, int32_t b) { /* pixelref.h:116-119: sqr() of ints is an int */
+    int dx = ref_x(a) - ref_x(b), dy = ref_y(a) - ref_y(b);
+    return sqrt((double)(dx * dx + dy * dy));
+}
+#ifndef M_PI
+#define M_PI 3.14159265358979323846 /* glibc math.h value, the one the reference compiles against */
+#endif
+static const int32_t NO_PIXEL = -1; /* PixelRef(-1,-1) packs to -1 */
+static inline double ref_angle(int32_t a, int32_t b, int32_t c) { /* pixelref.h:121-131 */
+    if (c == NO_PIXEL) return 0.0;
+    int abx = ref_x(a) - ref_x(b), aby = ref_y(a) - ref_y(b), bcx = ref_x(b) - ref_x(c), bcy = ref_y(b) - ref_y(c);
+    return acos((double)(abx * bcx + aby * bcy) /
+                (sqrt((double)(abx * abx + aby * aby)) * sqrt((double)(bcx * bcx + bcy * bcy)) + 1e-12));
+}
+
+int vgao_metric(const vgao_graph *gr, double spacing, double radius, int64_t src_begin, int64_t src_end, float *mspa,
+                float *mspl, float *msld, float *count) {
+    int64_t cells = (int64_t)gr->cols * gr->rows;
+    uint8_t *misc = (uint8_t *)malloc(cells);
+    float *mdist = (float *)malloc(sizeof(float) * cells), *cum = (float *)malloc(sizeof(float) * cells);
+    Heap h = {0, 0, 0, 0};
+    if (src_end > gr->n) src_end = gr->n;
+    for (int64_t s = src_begin; s < src_end; s++) {
+        int32_t curs = gr->cellref[s];
+        for (int64_t i = 0; i < cells; i++) {
+            misc[i] = 0;
+            mdist[i] = -1.0f;
+            cum[i] = 0.0f;
+        }
+        float euclid_depth = 0.0f, total_depth = 0.0f, total_angle = 0.0f;
+        int total_nodes = 0;
+        h.n = 0;
+        h.seq = 0;
+        heap_push(&h, 0.0f, curs, NO_PIXEL);
+        while (h.n > 0) {
+            HeapE here = heap_pop(&h);
+            if (radius != -1.0 && (here.key * spacing) > radius) break;
+            int64_t c = cell_of_ref(gr, here.ref);
+            if ((gr->state[c] & ST_FILLED) && !misc[c]) {
+                if (here.key == 0.0f || expands(gr, here.ref)) {
+                    int64_t u = gr->ord[c];
+                    for (uint64_t e = gr->it_ptr[u]; e < gr->it_ptr[u + 1]; e++) {
+                        int32_t pix = gr->it.ref[e];
+                        int64_t pc = cell_of_ref(gr, pix);
+                        if (!misc[pc] && (mdist[pc] == -1.0 || (here.key + ref_dist(pix, here.ref) < mdist[pc]))) {
+                            mdist[pc] = here.key + (float)ref_dist(pix, here.ref);
+                            cum[pc] = cum[c] + (here.last == NO_PIXEL ? 0.0f : (float)(ref_angle(pix, here.ref, here.last) / (M_PI * 0.5)));
+                            heap_push(&h, mdist[pc], pix, here.ref);
+                        }
+                    }
+                }
+                misc[c] = 1;
+                total_depth += (float)(here.key * spacing);
+                total_angle += cum[c];
+                euclid_depth += (float)(spacing * ref_dist(here.ref, curs));
+                total_nodes += 1;
+            }
+        }
+        int64_t o = s - src_begin;
+        mspa[o] = (float)((double)total_angle / (double)total_nodes);
+        mspl[o] = (float)((double)total_depth / (double)total_nodes);
+        msld[o] = (float)((double)euclid_depth / (double)total_nodes);
+        count[o] = (float)total_nodes;
+    }
+    free(h.e);
+    free(misc);
+    free(mdist);
+    free(cum);
+    return 0;
+}
+
+/* mean_depth is only written when total_nodes > 0 (always true: the source counts itself) */
+int vgao_angular(const vgao_graph *gr, double radius, int64_t src_begin, int64_t src_end, float *mean_depth,
+                 float *total_depth, float *count) {
+    int64_t cells = (int64_t)gr->cols * gr->rows;
+    uint8_t *misc = (uint8_t *)malloc(cells);
+    float *cum = (float *)malloc(sizeof(float) * cells);
+    Heap h = {0, 0, 0, 0};
+    if (src_end > gr->n) src_end = gr->n;
+    for (int64_t s = src_begin; s < src_end; s++) {
+        int32_t curs = gr->cellref[s];
+        for (int64_t i = 0; i < cells; i++) {
+            misc[i] = 0;
+            cum[i] = -1.0f;
+        }
+        float total_angle = 0.0f;
+        int total_nodes = 0;
+        h.n = 0;
+        h.seq = 0;
+        heap_push(&h, 0.0f, curs, NO_PIXEL);
+        cum[cell_of_ref(gr, curs)] = 0.0f;
+        while (h.n > 0) {
+            HeapE here = heap_pop(&h);
+            if (radius != -1.0 && here.key > radius) break;
+            int64_t c = cell_of_ref(gr, here.ref);
+            if ((gr->state[c] & ST_FILLED) && !misc[c]) {
+                if (here.key == 0.0f || expands(gr, here.ref)) {
+                    int64_t u = gr->ord[c];
+                    for (uint64_t e = gr->it_ptr[u]; e < gr->it_ptr[u + 1]; e++) {
+                        int32_t pix = gr->it.ref[e];
+                        int64_t pc = cell_of_ref(gr, pix);
+                        if (!misc[pc]) {
+                            float ang = (here.last == NO_PIXEL) ? 0.0f : (float)(ref_angle(pix, here.ref, here.last) / (M_PI * 0.5));
+                            if (cum[pc] == -1.0 || here.key + ang < cum[pc]) {
+                                cum[pc] = cum[c] + ang;
+                                heap_push(&h, cum[pc], pix, here.ref);
+                            }
+                        }
+                    }
+                }
+                misc[c] = 1;
+                total_angle += cum[c];
+                total_nodes += 1;
+            }
+        }
+        int64_t o = s - src_begin;
+        mean_depth[o] = total_nodes > 0 ? (float)((double)total_angle / (double)total_nodes) : -1.0f;
+        total_depth[o] = total_angle;
+        count[o] = (float)total_nodes;
+    }
+    free(h.e);
+    free(misc);
+    free(cum);
+    return 0;
+}

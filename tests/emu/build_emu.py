@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "depthmapx_b200", "csrc")
 HOST = os.path.join(ROOT, "depthmapx_b200", "host")
-CU = ["makegraph", "bfs", "local", "local_tc", "stepdepth", "cabi"]
+CU = ["makegraph", "bfs", "local", "local_tc", "stepdepth", "metric", "cabi"]
 
 
 def _match_back_angle(s, i):

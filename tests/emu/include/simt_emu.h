@@ -52,6 +52,10 @@ struct uint2 {
     unsigned x, y;
 };
 inline uint2 make_uint2(unsigned a, unsigned b) { return uint2{a, b}; }
+struct alignas(16) uint4 {
+    unsigned x, y, z, w;
+};
+inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return uint4{a, b, c, d}; }
 struct alignas(16) ulonglong2 {
     unsigned long long x, y;
 };
@@ -464,6 +468,11 @@ inline double __ddiv_rn(double a, double b) { return a / b; }
 inline double __dsqrt_rn(double a) { return std::sqrt(a); }
 inline float __fdiv_rn(float a, float b) { return a / b; }
 inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __double2float_rn(double a) { return (float)a; }
+inline unsigned __float_as_uint(float v) { unsigned u; std::memcpy(&u, &v, 4); return u; }
+inline float __uint_as_float(unsigned u) { float v; std::memcpy(&v, &u, 4); return v; }
+inline int __float_as_int(float v) { int u; std::memcpy(&u, &v, 4); return u; }
+inline float __int_as_float(int u) { float v; std::memcpy(&v, &u, 4); return v; }
 inline double __longlong_as_double(long long v) { return simt::from_bits<double>((uint64_t)v); }
 inline long long __double_as_longlong(double v) { return (long long)simt::to_bits(v); }
 

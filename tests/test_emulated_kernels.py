@@ -104,6 +104,12 @@ def test_step_depth_kernel(emu_dir):
     run_gpu_tests_emulated(emu_dir, ["tests/test_stepdepth_gpu.py"])
 
 
+def test_metric_angular_kernel(emu_dir):
+    """tests/test_gpu_metric.py on the smallest plan: the warp-per-source search with the 32-ary indexed heap (metric and
+    angular, whole map, permuted source lists, one CTA of slots vs many, error paths) against the oracle."""
+    run_gpu_tests_emulated(emu_dir, ["tests/test_gpu_metric.py", "-k", "whole_map or errors"])
+
+
 def test_graphfile_pipelines_merges_and_cli_shim(emu_dir):
     """tests/test_zzz_graphfile_gpu.py: VISPREP / VGA / STEPDEPTH / LINK pipelines file to file and the real depthmapXcli
     with the step-depth shim, byte-compared with the reference CLI's files."""

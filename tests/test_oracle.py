@@ -170,3 +170,28 @@ def test_csr_oracle_equals_graph_oracle(name):
     for i, s in enumerate(src):
         o = og.local_ints((int(s), int(s) + 1))
         assert o[0][0] == cl[i] and o[1][0] == kk[i] and o[2][0] == tot[i] and o[3][0] == ctl[i]
+
+
+# ---- metric / angular VGA: the oracle's vgao_metric / vgao_angular against the reference's own columns
+# (tests/golden/metric_angular.npz, written from libdmxref.so by tests/golden/make_golden_metric.py)
+
+@pytest.mark.parametrize("name", ["oblique:30:30:7", "office:40:40:1", "oblique:24:24:5:0.7", "urban:60:60:4"])
+def test_metric_angular_oracle_matches_reference_columns(name):
+    import os
+    from conftest import ROOT
+    from depthmapx_b200 import capi, plans
+    z = np.load(os.path.join(ROOT, "tests", "golden", "metric_angular.npz"), allow_pickle=False)
+    flat = capi.prepare(plans.by_name(name))
+    og = po.OracleGraph(po.Grid(flat.cols, flat.rows, flat.spacing, flat.bl_x, flat.bl_y, flat.state, flat.line_off, flat.lines))
+    # all sources of the small plans, three slices of the larger ones (one C call per slice)
+    slices = [(0, og.n)] if og.n <= 1200 else [(0, 60), (og.n // 2, og.n // 2 + 60), (og.n - 60, og.n)]
+    for tag, radius in (("n", -1.0), ("r", float(z[name + "/metric_radius"]))):
+        for lo, hi in slices:
+            got = og.metric(flat.spacing, radius, (lo, hi))
+            for col, a in zip(("angle", "path", "line", "count"), got):
+                assert np.array_equal(z[f"{name}/metric_{tag}/{col}"][lo:hi].view(np.int32), a.view(np.int32)), (tag, col, lo)
+    for tag, radius in (("n", -1.0), ("r", float(z[name + "/angular_radius"]))):
+        for lo, hi in slices:
+            got = og.angular(radius, (lo, hi))
+            for col, a in zip(("mean", "total", "count"), got):
+                assert np.array_equal(z[f"{name}/angular_{tag}/{col}"][lo:hi].view(np.int32), a.view(np.int32)), (tag, col, lo)

@@ -51,6 +51,19 @@ def test_random_plan_bit_equal_to_reference(seed):
         rm.vga_local()
         for k, v in po.local_formulas(*og.local_ints()).items():
             assert np.array_equal(rm.attr(k), v), k
+    # oracle metric / angular == reference VGAMetric / VGAAngular (row f4), radius n and a finite radius, float32 bit-equal
+    for mr in (-1.0, rng.choice([3.0, 5.5, 8.0]) * sp):
+        assert rm.vga_metric(mr) >= 0
+        sfx = "" if mr == -1.0 else " R%.2f" % mr
+        names = ["Metric Mean Shortest-Path Angle", "Metric Mean Shortest-Path Distance", "Metric Mean Straight-Line Distance",
+                 "Metric Node Count"]
+        for k, v in zip(names, og.metric(p.spacing, mr)):
+            assert np.array_equal(rm.attr(k + sfx).view(np.int32), v.view(np.int32)), (k, mr)
+    for ar in (-1.0, rng.choice([0.5, 1.0, 2.0])):
+        assert rm.vga_angular(ar) >= 0
+        sfx = "" if ar == -1.0 else " R%.2f" % ar
+        for k, v in zip(["Angular Mean Depth", "Angular Total Depth", "Angular Node Count"], og.angular(ar)):
+            assert np.array_equal(rm.attr(k + sfx).view(np.int32), v.view(np.int32)), (k, ar)
 
 
 @pytest.mark.ref
