@@ -94,8 +94,8 @@ def abi():
         L.vga_global_attributes.argtypes = [i64, vp, vp, vp, C.c_int32] + [vp] * 7
         L.vga_local.argtypes = [vp, vp, i64, i64, vp, vp, vp, vp]
         L.vga_step_depth.argtypes = [vp, vp, vp, i64, vp]
-        L.vga_metric.argtypes = [vp, vp, vp, C.c_double, C.c_double, vp, i64, vp, vp, vp, vp, C.POINTER(i64)]
-        L.vga_angular.argtypes = [vp, vp, vp, C.c_double, vp, i64, vp, vp, vp, C.POINTER(i64)]
+        L.vga_metric.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, vp, i64, vp, vp, vp, vp, C.POINTER(i64)]
+        L.vga_angular.argtypes = [vp, vp, vp, vp, C.c_double, vp, i64, vp, vp, vp, C.POINTER(i64)]
         L.vga_local_attributes.argtypes = [i64] + [vp] * 7
         L.vga_graph_device_rows.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
         L.vga_graph_from_device_rows.argtypes = [vp, i64, i64, vp, vp, i64, C.POINTER(vp)]
@@ -421,7 +421,7 @@ class Graph:
         check(abi().vga_step_depth(self.ctx.h, self.h, _p(src), len(src), _p(d)))
         return d
 
-    def metric(self, blocked_adjacent, spacing, radius=-1.0, sources=None):
+    def metric(self, blocked_adjacent, spacing, radius=-1.0, sources=None, partner=None):
         """VGAMetric::run for the listed source ordinals (None = all): float32 columns (Metric Mean Shortest-Path Angle,
         Metric Mean Shortest-Path Distance, Metric Mean Straight-Line Distance, Metric Node Count) + the number of
         turn-angle evaluations whose float rounding is not guaranteed (see include/vga_b200.h)."""
@@ -430,18 +430,20 @@ class Graph:
         k = self.n if src is None else len(src)
         out = [np.zeros(k, np.float32) for _ in range(4)]
         unsafe = i64()
-        check(abi().vga_metric(self.ctx.h, self.h, _p(ba), float(spacing), float(radius), None if src is None else _p(src), k,
+        mp = None if partner is None else np.ascontiguousarray(partner, np.int32)
+        check(abi().vga_metric(self.ctx.h, self.h, _p(ba), _p(mp), float(spacing), float(radius), None if src is None else _p(src), k,
                                *[_p(a) for a in out], C.byref(unsafe)))
         return tuple(out) + (unsafe.value,)
 
-    def angular(self, blocked_adjacent, radius=-1.0, sources=None):
+    def angular(self, blocked_adjacent, radius=-1.0, sources=None, partner=None):
         """VGAAngular::run: (Angular Mean Depth, Angular Total Depth, Angular Node Count, unsafe angle evaluations)."""
         ba = np.ascontiguousarray(blocked_adjacent, np.uint8)
         src = None if sources is None else np.ascontiguousarray(sources, np.int64)
         k = self.n if src is None else len(src)
         out = [np.zeros(k, np.float32) for _ in range(3)]
         unsafe = i64()
-        check(abi().vga_angular(self.ctx.h, self.h, _p(ba), float(radius), None if src is None else _p(src), k,
+        mp = None if partner is None else np.ascontiguousarray(partner, np.int32)
+        check(abi().vga_angular(self.ctx.h, self.h, _p(ba), _p(mp), float(radius), None if src is None else _p(src), k,
                                 *[_p(a) for a in out], C.byref(unsafe)))
         return tuple(out) + (unsafe.value,)
 

@@ -726,7 +726,8 @@ int vga_step_depth(vga_ctx *ctx, const vga_graph *g, const int64_t *sources, int
     return run_step_depth(ctx, const_cast<vga_graph *>(g), sources, n_sources, depth);
 }
 
-static int metric_angular_entry(vga_ctx *ctx, const vga_graph *g, int angular, const uint8_t *blocked_adjacent, double spacing,
+static int metric_angular_entry(vga_ctx *ctx, const vga_graph *g, int angular, const uint8_t *blocked_adjacent,
+                                const int32_t *merge_partner, double spacing,
                                 double radius, const int64_t *sources, int64_t n_sources, float *const *out, int nout,
                                 int64_t *angle_unsafe) {
     if (!ctx || !g || n_sources < 0) return VGA_ERR_INVALID;
@@ -740,21 +741,21 @@ static int metric_angular_entry(vga_ctx *ctx, const vga_graph *g, int angular, c
         for (int64_t i = 0; i < g->n; i++) all[(size_t)i] = i;
         sources = all.data();
     }
-    return run_metric_angular(ctx, const_cast<vga_graph *>(g), angular, blocked_adjacent, spacing, radius, sources, n_sources, out,
+    return run_metric_angular(ctx, const_cast<vga_graph *>(g), angular, blocked_adjacent, merge_partner, spacing, radius, sources, n_sources, out,
                               nout, angle_unsafe);
 }
 
-int vga_metric(vga_ctx *ctx, const vga_graph *g, const uint8_t *blocked_adjacent, double spacing, double radius,
+int vga_metric(vga_ctx *ctx, const vga_graph *g, const uint8_t *blocked_adjacent, const int32_t *merge_partner, double spacing, double radius,
                const int64_t *sources, int64_t n_sources, float *mean_angle, float *mean_path_dist, float *mean_line_dist,
                float *node_count, int64_t *angle_unsafe) {
     float *out[4] = {mean_angle, mean_path_dist, mean_line_dist, node_count};
-    return metric_angular_entry(ctx, g, 0, blocked_adjacent, spacing, radius, sources, n_sources, out, 4, angle_unsafe);
+    return metric_angular_entry(ctx, g, 0, blocked_adjacent, merge_partner, spacing, radius, sources, n_sources, out, 4, angle_unsafe);
 }
 
-int vga_angular(vga_ctx *ctx, const vga_graph *g, const uint8_t *blocked_adjacent, double radius, const int64_t *sources,
+int vga_angular(vga_ctx *ctx, const vga_graph *g, const uint8_t *blocked_adjacent, const int32_t *merge_partner, double radius, const int64_t *sources,
                 int64_t n_sources, float *mean_depth, float *total_depth, float *node_count, int64_t *angle_unsafe) {
     float *out[3] = {mean_depth, total_depth, node_count};
-    return metric_angular_entry(ctx, g, 1, blocked_adjacent, 1.0, radius, sources, n_sources, out, 3, angle_unsafe);
+    return metric_angular_entry(ctx, g, 1, blocked_adjacent, merge_partner, 1.0, radius, sources, n_sources, out, 3, angle_unsafe);
 }
 
 int vga_local_attributes(int64_t n, const int64_t *cluster, const int32_t *k, const int32_t *total, const float *control,

@@ -25,7 +25,8 @@
 // differ in the last bits, which changes the float32 turn only when the double lies within a few ulps of a float rounding
 // boundary (probability ~1e-8 per evaluation); such evaluations are COUNTED and returned (`angle_unsafe`), so a caller knows
 // when bit-equality with the reference is guaranteed (0) -- distances and node counts never depend on it in the metric
-// analysis.  Merge links are not supported here (error above this layer).
+// analysis.  Merge links (Point::m_merge) are followed as the reference does: the partner of a popped cell is expanded from
+// the same key and finalised without being counted.
 // Parity: tests/test_gpu_metric.py (oracle = oracle/vga_oracle.c vgao_metric / vgao_angular, pinned against the reference).
 #include <algorithm>
 
@@ -48,6 +49,7 @@ struct MaArgs {
     const uint2 *runs;
     const int32_t *refs;     // packed PixelRef per ordinal
     const uint8_t *expand;   // [n] blocked or blocked-adjacent
+    const int32_t *partner;  // [n] merge partner (Point::m_merge), -1 = none; nullptr = no merge links
     const int64_t *sources;  // [nsrc] ordinals
     int64_t nsrc;
     double spacing, radius;
@@ -136,6 +138,109 @@ __device__ __forceinline__ u64 heap_pop(u64 *heap, uint32_t *pos, uint32_t &size
     return top;
 }
 
+// Node::extractMetric / extractAngular of the pixel uu popped with key k: every cell of its row that is not finalised is
+// relaxed (Bin::extractMetric / extractAngular, ngraph.cpp:329-365); cum_u = m_cumangle of uu, pred = the last pixel of the
+// popped element (NONE = NoPixel: no turn).
+__device__ __forceinline__ void expand_row(const MaArgs &a, uint4 *state, uint32_t *pos, u64 *heap, uint32_t &size, int lane,
+                                           bool angular, uint32_t uu, float k, float cum_u, uint32_t pred) {
+    const int64_t n = a.n;
+    const int32_t ru = a.refs[uu];
+    const int ux = ref_x(ru), uy = ref_y(ru);
+    int bcx = 0, bcy = 0;
+    double nbc = 0.0;
+    if (pred != NONE) {
+        const int32_t rp = a.refs[pred];
+        bcx = ux - ref_x(rp);
+        bcy = uy - ref_y(rp);
+        nbc = cell_dist(bcx, bcy);
+    }
+    const uint64_t r0 = a.runptr[uu], r1 = a.runptr[uu + 1];
+    for (uint64_t rb = r0; rb < r1; rb += 32) {
+        // 32 runs, their cells dealt to the lanes
+        uint2 run = make_uint2(0u, 0u);
+        if (rb + lane < r1) run = a.runs[rb + lane];
+        if (run.x >= (uint32_t)n) run.y = 0u;  // ghost columns: queued by the reference, never expanded or counted
+        uint32_t incl = run.y;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const uint32_t excl = incl - run.y;
+        const uint32_t cells = __shfl_sync(FULL, incl, 31);
+        for (uint32_t cb = 0; cb < cells; cb += 32) {
+            const uint32_t c = cb + lane;
+            int lo = 0, hi = 32;  // last lane whose first cell index is <= c
+#pragma unroll
+            for (int it = 0; it < 5; it++) {
+                const int mid = (lo + hi) >> 1;
+                const uint32_t ev = __shfl_sync(FULL, excl, mid);
+                if (ev <= c) lo = mid; else hi = mid;
+            }
+            const uint32_t first = __shfl_sync(FULL, run.x, lo);
+            const uint32_t eoff = __shfl_sync(FULL, excl, lo);
+            const bool act = c < cells;
+            const uint32_t v = first + (c - eoff);
+            bool queue = false;
+            uint32_t newkey = 0, oldkey = 0;
+            if (act) {
+                uint4 sv = state[v];
+                if (sv.z != KEY_POPPED) {
+                    const int32_t rv = a.refs[v];
+                    const int abx = ref_x(rv) - ux, aby = ref_y(rv) - uy;
+                    bool relax;
+                    float nk = 0.0f, ncum = 0.0f;
+                    if (!angular) {
+                        const double w = cell_dist(abx, aby);
+                        const float m = __uint_as_float(sv.x);
+                        // pt.m_dist == -1.0 || curs.dist + dist(pix, curs.pixel) < pt.m_dist   (float + double)
+                        relax = m == -1.0f || __dadd_rn((double)k, w) < (double)m;
+                        if (relax) {
+                            nk = __fadd_rn(k, __double2float_rn(w));
+                            const float ang = pred == NONE ? 0.0f : turn_angle(abx, aby, bcx, bcy, nbc, a.unsafe);
+                            ncum = __fadd_rn(cum_u, ang);
+                            sv.x = __float_as_uint(nk);
+                        }
+                    } else {
+                        const float ang = pred == NONE ? 0.0f : turn_angle(abx, aby, bcx, bcy, nbc, a.unsafe);
+                        const float m = __uint_as_float(sv.y);
+                        // pt.m_cumangle == -1.0 || curs.angle + ang < pt.m_cumangle   (float + float)
+                        relax = m == -1.0f || __fadd_rn(k, ang) < m;
+                        if (relax) {
+                            ncum = __fadd_rn(cum_u, ang);
+                            nk = ncum;
+                        }
+                    }
+                    if (relax) {
+                        sv.y = __float_as_uint(ncum);
+                        oldkey = sv.z;
+                        newkey = __float_as_uint(nk);
+                        // the set keeps the first of two equal (key, pixel) elements and pops the smallest first
+                        if (oldkey == KEY_INF || nk < __uint_as_float(oldkey)) {
+                            sv.z = newkey;
+                            sv.w = uu;
+                            queue = true;
+                        }
+                        state[v] = sv;
+                    }
+                }
+            }
+            unsigned qm = __ballot_sync(FULL, queue);
+            while (qm) {
+                const int l = __ffs(qm) - 1;
+                qm &= qm - 1;
+                const uint32_t qv = __shfl_sync(FULL, v, l);
+                const uint32_t qk = __shfl_sync(FULL, newkey, l);
+                const uint32_t qo = __shfl_sync(FULL, oldkey, l);
+                const uint32_t fresh_at = size;
+                if (qo == KEY_INF) size++;
+                if (lane == 0) heap_up(heap, pos, qo == KEY_INF ? fresh_at : pos[qv], ((u64)qk << 32) | qv);
+            }
+        }
+    }
+    __syncwarp();  // state and heap writes of this row before anything reads them
+}
+
 __global__ void __launch_bounds__(MWARPS * 32) k_metric_angular(MaArgs a) {
     const int lane = threadIdx.x & 31;
     const int64_t slot = (int64_t)blockIdx.x * MWARPS + (threadIdx.x >> 5);
@@ -173,109 +278,28 @@ __global__ void __launch_bounds__(MWARPS * 32) k_metric_angular(MaArgs a) {
             const float k = __uint_as_float((uint32_t)(top >> 32));
             if (a.radius != -1.0 && (angular ? (double)k : __dmul_rn((double)k, a.spacing)) > a.radius) break;
             const uint4 su = state[u];
+            if (su.z == KEY_POPPED) continue;  // finalised as the merge partner of an earlier pop (m_misc == ~0)
             const float cum_u = __uint_as_float(su.y);
-            const uint32_t pred = su.w;
-            const int32_t ru = a.refs[u];
-            const int ux = ref_x(ru), uy = ref_y(ru);
-            if (k == 0.0f || a.expand[u]) {
-                int bcx = 0, bcy = 0;
-                double nbc = 0.0;
-                if (pred != NONE) {
-                    const int32_t rp = a.refs[pred];
-                    bcx = ux - ref_x(rp);
-                    bcy = uy - ref_y(rp);
-                    nbc = cell_dist(bcx, bcy);
-                }
-                const uint64_t r0 = a.runptr[u], r1 = a.runptr[u + 1];
-                for (uint64_t rb = r0; rb < r1; rb += 32) {
-                    // 32 runs, their cells dealt to the lanes
-                    uint2 run = make_uint2(0u, 0u);
-                    if (rb + lane < r1) run = a.runs[rb + lane];
-                    if (run.x >= (uint32_t)n) run.y = 0u;  // ghost columns: queued by the reference, never expanded or counted
-                    uint32_t incl = run.y;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t t = __shfl_up_sync(FULL, incl, o);
-                        if (lane >= o) incl += t;
-                    }
-                    const uint32_t excl = incl - run.y;
-                    const uint32_t cells = __shfl_sync(FULL, incl, 31);
-                    for (uint32_t cb = 0; cb < cells; cb += 32) {
-                        const uint32_t c = cb + lane;
-                        int lo = 0, hi = 32;  // last lane whose first cell index is <= c
-#pragma unroll
-                        for (int it = 0; it < 5; it++) {
-                            const int mid = (lo + hi) >> 1;
-                            const uint32_t ev = __shfl_sync(FULL, excl, mid);
-                            if (ev <= c) lo = mid; else hi = mid;
-                        }
-                        const uint32_t first = __shfl_sync(FULL, run.x, lo);
-                        const uint32_t eoff = __shfl_sync(FULL, excl, lo);
-                        const bool act = c < cells;
-                        const uint32_t v = first + (c - eoff);
-                        bool queue = false;
-                        uint32_t newkey = 0, oldkey = 0;
-                        if (act) {
-                            uint4 sv = state[v];
-                            if (sv.z != KEY_POPPED) {
-                                const int32_t rv = a.refs[v];
-                                const int abx = ref_x(rv) - ux, aby = ref_y(rv) - uy;
-                                bool relax;
-                                float nk, ncum;
-                                if (!angular) {
-                                    const double w = cell_dist(abx, aby);
-                                    const float m = __uint_as_float(sv.x);
-                                    // pt.m_dist == -1.0 || curs.dist + dist(pix, curs.pixel) < pt.m_dist   (float + double)
-                                    relax = m == -1.0f || __dadd_rn((double)k, w) < (double)m;
-                                    if (relax) {
-                                        nk = __fadd_rn(k, __double2float_rn(w));
-                                        const float ang = pred == NONE ? 0.0f : turn_angle(abx, aby, bcx, bcy, nbc, a.unsafe);
-                                        ncum = __fadd_rn(cum_u, ang);
-                                        sv.x = __float_as_uint(nk);
-                                    }
-                                } else {
-                                    const float ang = pred == NONE ? 0.0f : turn_angle(abx, aby, bcx, bcy, nbc, a.unsafe);
-                                    const float m = __uint_as_float(sv.y);
-                                    // pt.m_cumangle == -1.0 || curs.angle + ang < pt.m_cumangle   (float + float)
-                                    relax = m == -1.0f || __fadd_rn(k, ang) < m;
-                                    if (relax) {
-                                        ncum = __fadd_rn(cum_u, ang);
-                                        nk = ncum;
-                                    }
-                                }
-                                if (relax) {
-                                    sv.y = __float_as_uint(ncum);
-                                    oldkey = sv.z;
-                                    newkey = __float_as_uint(nk);
-                                    // the set keeps the first of two equal (key, pixel) elements and pops the smallest first
-                                    if (oldkey == KEY_INF || nk < __uint_as_float(oldkey)) {
-                                        sv.z = newkey;
-                                        sv.w = u;
-                                        queue = true;
-                                    }
-                                    state[v] = sv;
-                                }
-                            }
-                        }
-                        unsigned qm = __ballot_sync(FULL, queue);
-                        while (qm) {
-                            const int l = __ffs(qm) - 1;
-                            qm &= qm - 1;
-                            const uint32_t qv = __shfl_sync(FULL, v, l);
-                            const uint32_t qk = __shfl_sync(FULL, newkey, l);
-                            const uint32_t qo = __shfl_sync(FULL, oldkey, l);
-                            const uint32_t fresh_at = size;
-                            if (qo == KEY_INF) size++;
-                            if (lane == 0) heap_up(heap, pos, qo == KEY_INF ? fresh_at : pos[qv], ((u64)qk << 32) | qv);
-                        }
-                    }
-                }
-            }
+            if (k == 0.0f || a.expand[u]) expand_row(a, state, pos, heap, size, lane, angular, u, k, cum_u, su.w);
+            __syncwarp();  // every lane has read state[u]
             if (lane == 0) state[u].z = KEY_POPPED;
             __syncwarp();
+            // merge link (vgametric.cpp:96-104, vgaangular.cpp:91-99): the partner takes over the cumulated angle and is
+            // expanded from the same key with no last pixel, then finalised without being counted
+            const int32_t u2 = a.partner ? a.partner[u] : -1;
+            if (u2 >= 0 && state[u2].z != KEY_POPPED) {
+                __syncwarp();  // every lane has read the partner's state
+                if (k == 0.0f || a.expand[u2]) expand_row(a, state, pos, heap, size, lane, angular, (uint32_t)u2, k, cum_u, NONE);
+                if (lane == 0) {
+                    state[u2].y = __float_as_uint(cum_u);
+                    state[u2].z = KEY_POPPED;
+                }
+                __syncwarp();
+            }
+            const int32_t ru = a.refs[u];
             if (!angular) {
                 total_depth = __fadd_rn(total_depth, __double2float_rn(__dmul_rn((double)k, a.spacing)));
-                euclid_depth = __fadd_rn(euclid_depth, __double2float_rn(__dmul_rn(a.spacing, cell_dist(ux - ref_x(rsrc), uy - ref_y(rsrc)))));
+                euclid_depth = __fadd_rn(euclid_depth, __double2float_rn(__dmul_rn(a.spacing, cell_dist(ref_x(ru) - ref_x(rsrc), ref_y(ru) - ref_y(rsrc)))));
             }
             total_angle = __fadd_rn(total_angle, cum_u);
             total_nodes += 1;
@@ -298,7 +322,7 @@ __global__ void __launch_bounds__(MWARPS * 32) k_metric_angular(MaArgs a) {
 
 }  // namespace
 
-int run_metric_angular(vga_ctx *ctx, vga_graph *g, int angular, const uint8_t *expand, double spacing, double radius,
+int run_metric_angular(vga_ctx *ctx, vga_graph *g, int angular, const uint8_t *expand, const int32_t *partner, double spacing, double radius,
                        const int64_t *sources, int64_t nsrc, float *const *out, int nout, int64_t *angle_unsafe) {
     cudaStream_t st = ctx->stream;
     const int64_t n = g->n;
@@ -342,6 +366,7 @@ int run_metric_angular(vga_ctx *ctx, vga_graph *g, int angular, const uint8_t *e
     VGA_TRY(ctx->ws.get("ma_heap", sizeof(u64) * (size_t)slots * (size_t)n, (void **)&heap));
     DevBuf<int32_t> d_refs;
     DevBuf<uint8_t> d_expand;
+    DevBuf<int32_t> d_partner;
     DevBuf<int64_t> d_src;
     DevBuf<float> d_out;
     DevBuf<unsigned long long> d_ctr;  // [0] next source, [1] unsafe angle evaluations
@@ -352,12 +377,22 @@ int run_metric_angular(vga_ctx *ctx, vga_graph *g, int angular, const uint8_t *e
     VGA_TRY(d_ctr.alloc_zero(2, st));
     VGA_CUDA(cudaMemcpyAsync(d_refs.p, g->h_refs.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
     VGA_CUDA(cudaMemcpyAsync(d_expand.p, expand, (size_t)n, cudaMemcpyHostToDevice, st));
+    if (partner) {
+        for (int64_t v = 0; v < n; v++)
+            if (partner[v] >= n || (partner[v] >= 0 && (partner[v] == v || partner[partner[v]] != v))) {
+                set_error(std::string(who) + ": merge links must pair distinct cells symmetrically");
+                return VGA_ERR_INVALID;
+            }
+        VGA_TRY(d_partner.alloc((size_t)n));
+        VGA_CUDA(cudaMemcpyAsync(d_partner.p, partner, sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+    }
     MaArgs a{};
     a.n = n;
     a.runptr = g->f_runptr.p;
     a.runs = g->f_runs.p;
     a.refs = d_refs.p;
     a.expand = d_expand.p;
+    a.partner = partner ? d_partner.p : nullptr;
     a.spacing = spacing;
     a.radius = radius;
     a.angular = angular;

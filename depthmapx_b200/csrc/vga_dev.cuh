@@ -373,7 +373,7 @@ int batch_source_order_list(vga_ctx *ctx, vga_graph *g, const int64_t *sources, 
 int run_global(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources, int64_t src_begin, int64_t src_end,
                int32_t *total_nodes, int64_t *total_depth, int32_t *dist, int32_t max_levels, int32_t *levels_used);
 // metric.cu: metric (angular = 0: 4 output columns) / angular (3 columns) VGA for an explicit list of sources
-int run_metric_angular(vga_ctx *ctx, vga_graph *g, int angular, const uint8_t *expand, double spacing, double radius,
+int run_metric_angular(vga_ctx *ctx, vga_graph *g, int angular, const uint8_t *expand, const int32_t *partner, double spacing, double radius,
                        const int64_t *sources, int64_t nsrc, float *const *out, int nout, int64_t *angle_unsafe);
 // stepdepth.cu
 int run_step_depth(vga_ctx *ctx, vga_graph *g, const int64_t *sources, int64_t nsrc, int32_t *depth_out);

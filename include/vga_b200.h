@@ -210,11 +210,16 @@ int vga_step_depth(vga_ctx *ctx, const vga_graph *g, const int64_t *sources, int
  * Total Depth", "Angular Node Count".  radius -1.0 = n (metric: in map units, compared with key * spacing; angular: in
  * units of 90 degrees).  Any output may be NULL.  *angle_unsafe = number of turn-angle evaluations whose float32
  * rounding could depend on the last bits of acos (0 = the angle sums are guaranteed bit-equal to a glibc host; distances
- * and node counts of vga_metric never depend on it).  No merge links. */
-int vga_metric(vga_ctx *ctx, const vga_graph *g, const uint8_t *blocked_adjacent, double spacing, double radius,
+ * and node counts of vga_metric never depend on it).  merge_partner[v] (N ints, NULL = no merge links) = ordinal of the
+ * cell v is merged with (Point::m_merge), -1 = none, symmetric: when v is finalised its partner is expanded from the same
+ * key and finalised without being counted (vgametric.cpp:96-104, vgaangular.cpp:91-99); g is the PLAIN adjacency, not the
+ * contracted one of vga_global. */
+int vga_metric(vga_ctx *ctx, const vga_graph *g, const uint8_t *blocked_adjacent, const int32_t *merge_partner, double spacing,
+               double radius,
                const int64_t *sources, int64_t n_sources, float *mean_angle, float *mean_path_dist, float *mean_line_dist,
                float *node_count, int64_t *angle_unsafe);
-int vga_angular(vga_ctx *ctx, const vga_graph *g, const uint8_t *blocked_adjacent, double radius, const int64_t *sources,
+int vga_angular(vga_ctx *ctx, const vga_graph *g, const uint8_t *blocked_adjacent, const int32_t *merge_partner, double radius,
+                const int64_t *sources,
                 int64_t n_sources, float *mean_depth, float *total_depth, float *node_count, int64_t *angle_unsafe);
 
 /* ---- device-resident access for multi-GPU plumbing (pointers are CUDA device pointers) ------ */

@@ -109,9 +109,9 @@ def olib():
         L.vgao_step_depth.restype = C.c_int
         L.vgao_step_depth.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.vgao_metric.restype = C.c_int
-        L.vgao_metric.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int64, C.c_int64] + [C.c_void_p] * 4
+        L.vgao_metric.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int64, C.c_int64] + [C.c_void_p] * 4
         L.vgao_angular.restype = C.c_int
-        L.vgao_angular.argtypes = [C.c_void_p, C.c_double, C.c_int64, C.c_int64] + [C.c_void_p] * 3
+        L.vgao_angular.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int64, C.c_int64] + [C.c_void_p] * 3
         L.vgao_global_csr.restype = C.c_int
         L.vgao_global_csr.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_int32]
@@ -201,19 +201,21 @@ class OracleGraph:
         olib().vgao_step_depth(self.h, _p(src), len(src), _p(d))
         return d
 
-    def metric(self, spacing, radius=-1.0, src=None):
+    def metric(self, spacing, radius=-1.0, src=None, partner=None):
         """(Metric Mean Shortest-Path Angle, Metric Mean Shortest-Path Distance, Metric Mean Straight-Line Distance,
         Metric Node Count) as float32 columns of the sources src = (begin, end)."""
         b, e = (0, self.n) if src is None else src
         out = [np.zeros(e - b, np.float32) for _ in range(4)]
-        olib().vgao_metric(self.h, float(spacing), float(radius), b, e, *[_p(a) for a in out])
+        mp = None if partner is None else np.ascontiguousarray(partner, np.int32)
+        olib().vgao_metric(self.h, None if mp is None else _p(mp), float(spacing), float(radius), b, e, *[_p(a) for a in out])
         return tuple(out)
 
-    def angular(self, radius=-1.0, src=None):
+    def angular(self, radius=-1.0, src=None, partner=None):
         """(Angular Mean Depth, Angular Total Depth, Angular Node Count) as float32 columns."""
         b, e = (0, self.n) if src is None else src
         out = [np.zeros(e - b, np.float32) for _ in range(3)]
-        olib().vgao_angular(self.h, float(radius), b, e, *[_p(a) for a in out])
+        mp = None if partner is None else np.ascontiguousarray(partner, np.int32)
+        olib().vgao_angular(self.h, None if mp is None else _p(mp), float(radius), b, e, *[_p(a) for a in out])
         return tuple(out)
 
     def local_ints(self, src=None):

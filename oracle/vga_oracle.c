@@ -1059,7 +1059,8 @@ int vgao_step_depth(const vgao_graph *gr, const int32_t *src, int64_t nsrc, int3
  * the first, when the pixel is already finalised (or is not a filled cell), so it is ignored either way.
  * Per-cell state of the reference (Point::m_misc / m_dist / m_cumangle) is kept for ALL cells, filled or not, because
  * the gaps of diagonal bins are relaxed and queued like any other pixel (they are never expanded).
- * No merge links (the oracle has none).  radius < 0 (-1.0) = unlimited. */
+ * Merge links: partner[v] = ordinal of the cell v is merged with (-1 none; NULL = no links): the partner of a finalised
+ * cell is expanded from the same key with no last pixel and finalised without being counted.  radius -1.0 = unlimited. */
 #define ST_BLOCKED 0x0004 /* salalib/point.h:33 */
 typedef struct { float key; int32_t ref, last; uint64_t seq; } HeapE;
 static inline int heap_less(const HeapE *a, const HeapE *b) {
@@ -1127,8 +1128,8 @@ static inline double ref_angle(int32_t a, int32_t b, int32_t c) { /* pixelref.h:
                 (sqrt((double)(abx * abx + aby * aby)) * sqrt((double)(bcx * bcx + bcy * bcy)) + 1e-12));
 }
 
-int vgao_metric(const vgao_graph *gr, double spacing, double radius, int64_t src_begin, int64_t src_end, float *mspa,
-                float *mspl, float *msld, float *count) {
+int vgao_metric(const vgao_graph *gr, const int32_t *partner, double spacing, double radius, int64_t src_begin, int64_t src_end,
+                float *mspa, float *mspl, float *msld, float *count) {
     int64_t cells = (int64_t)gr->cols * gr->rows;
     uint8_t *misc = (uint8_t *)malloc(cells);
     float *mdist = (float *)malloc(sizeof(float) * cells), *cum = (float *)malloc(sizeof(float) * cells);
@@ -1164,6 +1165,26 @@ int vgao_metric(const vgao_graph *gr, double spacing, double radius, int64_t src
                     }
                 }
                 misc[c] = 1;
+                if (partner && partner[gr->ord[c]] >= 0) { /* vgametric.cpp:96-104 */
+                    int64_t u2 = partner[gr->ord[c]];
+                    int32_t r2 = gr->cellref[u2];
+                    int64_t c2 = cell_of_ref(gr, r2);
+                    if (!misc[c2]) {
+                        cum[c2] = cum[c];
+                        if (here.key == 0.0f || expands(gr, r2)) {
+                            for (uint64_t e = gr->it_ptr[u2]; e < gr->it_ptr[u2 + 1]; e++) {
+                                int32_t pix = gr->it.ref[e];
+                                int64_t pc = cell_of_ref(gr, pix);
+                                if (!misc[pc] && (mdist[pc] == -1.0 || (here.key + ref_dist(pix, r2) < mdist[pc]))) {
+                                    mdist[pc] = here.key + (float)ref_dist(pix, r2);
+                                    cum[pc] = cum[c2] + 0.0f; /* lastpixel == NoPixel */
+                                    heap_push(&h, mdist[pc], pix, r2);
+                                }
+                            }
+                        }
+                        misc[c2] = 1;
+                    }
+                }
                 total_depth += (float)(here.key * spacing);
                 total_angle += cum[c];
                 euclid_depth += (float)(spacing * ref_dist(here.ref, curs));
@@ -1184,8 +1205,8 @@ int vgao_metric(const vgao_graph *gr, double spacing, double radius, int64_t src
 }
 
 /* mean_depth is only written when total_nodes > 0 (always true: the source counts itself) */
-int vgao_angular(const vgao_graph *gr, double radius, int64_t src_begin, int64_t src_end, float *mean_depth,
-                 float *total_depth, float *count) {
+int vgao_angular(const vgao_graph *gr, const int32_t *partner, double radius, int64_t src_begin, int64_t src_end,
+                 float *mean_depth, float *total_depth, float *count) {
     int64_t cells = (int64_t)gr->cols * gr->rows;
     uint8_t *misc = (uint8_t *)malloc(cells);
     float *cum = (float *)malloc(sizeof(float) * cells);
@@ -1223,6 +1244,28 @@ int vgao_angular(const vgao_graph *gr, double radius, int64_t src_begin, int64_t
                     }
                 }
                 misc[c] = 1;
+                if (partner && partner[gr->ord[c]] >= 0) { /* vgaangular.cpp:91-99 */
+                    int64_t u2 = partner[gr->ord[c]];
+                    int32_t r2 = gr->cellref[u2];
+                    int64_t c2 = cell_of_ref(gr, r2);
+                    if (!misc[c2]) {
+                        cum[c2] = cum[c];
+                        if (here.key == 0.0f || expands(gr, r2)) {
+                            for (uint64_t e = gr->it_ptr[u2]; e < gr->it_ptr[u2 + 1]; e++) {
+                                int32_t pix = gr->it.ref[e];
+                                int64_t pc = cell_of_ref(gr, pix);
+                                if (!misc[pc]) {
+                                    float ang = 0.0f; /* lastpixel == NoPixel */
+                                    if (cum[pc] == -1.0 || here.key + ang < cum[pc]) {
+                                        cum[pc] = cum[c2] + ang;
+                                        heap_push(&h, cum[pc], pix, r2);
+                                    }
+                                }
+                            }
+                        }
+                        misc[c2] = 1;
+                    }
+                }
                 total_angle += cum[c];
                 total_nodes += 1;
             }

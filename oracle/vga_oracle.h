@@ -91,11 +91,12 @@ int vgao_sieve_kat(double cx, double cy, int q, const double *segs, int nsegs, d
 
 /* metric / angular VGA (row f4): the four "Metric ..." columns (Mean Shortest-Path Angle, Mean Shortest-Path Distance,
  * Mean Straight-Line Distance, Node Count) and the three "Angular ..." columns (Mean Depth, Total Depth, Node Count)
- * as row.setValue stores them; radius -1.0 = n; spacing = PointMap::m_spacing. */
-int vgao_metric(const vgao_graph *gr, double spacing, double radius, int64_t src_begin, int64_t src_end, float *mspa,
-                float *mspl, float *msld, float *count);
-int vgao_angular(const vgao_graph *gr, double radius, int64_t src_begin, int64_t src_end, float *mean_depth,
-                 float *total_depth, float *count);
+ * as row.setValue stores them; radius -1.0 = n; spacing = PointMap::m_spacing; partner = merge links as ordinals
+ * ([N], -1 = none) or NULL. */
+int vgao_metric(const vgao_graph *gr, const int32_t *partner, double spacing, double radius, int64_t src_begin, int64_t src_end,
+                float *mspa, float *mspl, float *msld, float *count);
+int vgao_angular(const vgao_graph *gr, const int32_t *partner, double radius, int64_t src_begin, int64_t src_end,
+                 float *mean_depth, float *total_depth, float *count);
 
 #ifdef __cplusplus
 }

@@ -20,10 +20,12 @@ if __name__ == "__main__":
     os.makedirs(DST, exist_ok=True)
     for name in ("gallery_empty.graph", "rect1x1.graph"):
         shutil.copyfile(os.path.join(SRC, name), os.path.join(DST, name))
-    # 3.7 MB -> stored gzip-compressed with a fixed mtime so the file is reproducible
-    with open(os.path.join(SRC, "gallery_connected.graph"), "rb") as f, \
-            open(os.path.join(DST, "gallery_connected.graph.gz"), "wb") as raw, \
-            gzip.GzipFile(filename="", mode="wb", fileobj=raw, mtime=0) as g:
-        g.write(f.read())
+    # 3.7 MB / 0.6 MB -> stored gzip-compressed with a fixed mtime so the files are reproducible
+    # (turns_connected.graph: input of the vga_metric / vga_angular regression cases)
+    for name in ("gallery_connected.graph", "turns_connected.graph"):
+        with open(os.path.join(SRC, name), "rb") as f, \
+                open(os.path.join(DST, name + ".gz"), "wb") as raw, \
+                gzip.GzipFile(filename="", mode="wb", fileobj=raw, mtime=0) as g:
+            g.write(f.read())
     for f in sorted(os.listdir(DST)):
         print(f, os.path.getsize(os.path.join(DST, f)))

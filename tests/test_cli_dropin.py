@@ -48,6 +48,12 @@ def test_cli_outputs_byte_identical(tmp_path, name, grid, seed):
                          "-vg", "-vl", "-vr", radius], d)
         assert same(os.path.join(d, f"vga_{radius}_ref.graph"), os.path.join(d, f"vga_{radius}_gpu.graph")), \
             f"VGA -vr {radius} .graph differs"
+    # row f4: metric (radius n and 6 cells) and angular VGA
+    for tag2, args in (("metric_n", ["-vm", "metric", "-vr", "n"]), ("metric_r", ["-vm", "metric", "-vr", str(6 * float(grid))]),
+                       ("angular", ["-vm", "angular"])):
+        for tag, binary in (("ref", REF), ("gpu", GPU)):
+            run(binary, ["-m", "VGA", "-f", "prep_ref.graph", "-o", f"{tag2}_{tag}.graph"] + args, d)
+        assert same(os.path.join(d, f"{tag2}_ref.graph"), os.path.join(d, f"{tag2}_gpu.graph")), f"VGA {tag2} .graph differs"
     # boundary graph (-pb) and restricted visibility (-pr) variants of VISPREP
     for extra, tag2 in ((["-pb"], "pb"), (["-pr", "7.5"], "pr")):
         for tag, binary in (("ref", REF), ("gpu", GPU)):
@@ -71,6 +77,12 @@ REGRESSION_CASES = {
     "visibility_local": ("gallery_connected.graph", ["-m", "VGA", "-vm", "visibility", "-vl"]),
     "visibility_global_local_simple": ("gallery_connected.graph", ["-m", "VGA", "-vm", "visibility", "-vg", "-vl", "-vr", "n", "-s"]),
     "vga_visual_step_depth": ("gallery_connected.graph", ["-m", "STEPDEPTH", "-sdp", "3,5", "-sdt", "visual"]),
+    # row f4: metric / angular VGA (both inputs carry merge links)
+    "vga_metric": ("turns_connected.graph", ["-m", "VGA", "-vm", "metric", "-vr", "n"]),
+    "vga_angular": ("turns_connected.graph", ["-m", "VGA", "-vm", "angular"]),
+    "vga_metric_only_map": ("gallery_connected.graph", ["-m", "VGA", "-vm", "metric", "-vr", "n"]),
+    "vga_angular_only_map": ("gallery_connected.graph", ["-m", "VGA", "-vm", "angular"]),
+    "vga_metric_radius": ("turns_connected.graph", ["-m", "VGA", "-vm", "metric", "-vr", "0.6"]),
 }
 
 

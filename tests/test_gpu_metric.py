@@ -98,6 +98,40 @@ def test_whole_map_and_source_order():
     c.close()
 
 
+@pytest.mark.parametrize("name", ["oblique:20:20:3", "office:24:24:2"])
+def test_merge_links_vs_oracle(name):
+    """Merge links (Point::m_merge): the partner of a finalised cell is expanded from the same key and finalised without
+    being counted (vgametric.cpp:96-104, vgaangular.cpp:91-99); oracle pinned against the reference with merges by
+    tests/test_oracle_vs_reference.py::test_metric_angular_with_merge_links_against_the_reference."""
+    flat, og = oracle_for(name)
+    c = capi.Context(0)
+    g = c.build(flat)
+    ba = capi.blocked_adjacent(flat)
+    rng = np.random.RandomState(8)
+    cells = rng.choice(g.n, 8, replace=False)
+    partner = np.full(g.n, -1, np.int32)
+    for a, b in zip(cells[0::2], cells[1::2]):
+        partner[a], partner[b] = b, a
+    for radius in (-1.0, 5.0 * flat.spacing):
+        got = g.metric(ba, flat.spacing, radius, None, partner)
+        want = og.metric(flat.spacing, radius, partner=partner)
+        for i, (a, b) in enumerate(zip(want, got[:4])):
+            if i == 0 and got[4] != 0:
+                continue
+            assert np.array_equal(bits(a), bits(b)), (name, radius, i)
+    for radius in (-1.0, 1.0):
+        got = g.angular(ba, radius, None, partner)
+        want = og.angular(radius, partner=partner)
+        if got[3] == 0:
+            for i, (a, b) in enumerate(zip(want, got[:3])):
+                assert np.array_equal(bits(a), bits(b)), (name, radius, i)
+    bad = partner.copy()
+    bad[cells[0]] = cells[2]  # asymmetric
+    with pytest.raises(capi.VgaError):
+        g.metric(ba, flat.spacing, -1.0, None, bad)
+    c.close()
+
+
 def test_errors():
     flat, _ = oracle_for("oblique:20:20:3")
     c = capi.Context(0)

@@ -97,3 +97,40 @@ def test_context_filled_semantics_oracle_vs_reference(name):
         assert np.array_equal(np.where(k < 0, -1.0, v).astype(np.float32), r.attr(n_)), n_
     for src in ([5, 40], [0], [17, 18, 19]):
         assert np.array_equal(og.step_depth(src).astype(np.float32), r.step_depth(src))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_metric_angular_with_merge_links_against_the_reference(seed):
+    """Row f4 with merge links (vgametric.cpp:96-104, vgaangular.cpp:91-99): three random pairs of merged cells, radius n
+    and a finite radius, every column float32 bit-equal to the reference's."""
+    rng = random.Random(3000 + seed)
+    w, h = rng.randrange(10, 24), rng.randrange(10, 24)
+    sp = rng.choice([1.0, 0.7, 1.3])
+    p = plans.oblique(w, h, seed, n_axis=rng.randrange(2, 8), n_oblique=rng.randrange(0, 5), spacing=sp)
+    rm = po.RefMap(p.walls, p.spacing)
+    if not rm.fill(*p.seeds[0]):
+        pytest.skip("seed cell not fillable in this plan")
+    g = rm.grid()
+    og = po.OracleGraph(g)
+    rm.makegraph()
+    refs = og.cell_refs()
+    if og.n < 10:
+        pytest.skip("too few cells")
+    partner = np.full(og.n, -1, np.int32)
+    cells = rng.sample(range(og.n), 6)
+    for a, b in zip(cells[0::2], cells[1::2]):
+        ra, rb = int(refs[a]), int(refs[b])
+        assert rm.merge(g.bl_x + (ra >> 16) * sp, g.bl_y + (ra & 0xffff) * sp, g.bl_x + (rb >> 16) * sp, g.bl_y + (rb & 0xffff) * sp)
+        partner[a], partner[b] = b, a
+    for mr in (-1.0, 6.0 * sp):
+        assert rm.vga_metric(mr) >= 0
+        sfx = "" if mr == -1.0 else " R%.2f" % mr
+        names = ["Metric Mean Shortest-Path Angle", "Metric Mean Shortest-Path Distance", "Metric Mean Straight-Line Distance",
+                 "Metric Node Count"]
+        for k, v in zip(names, og.metric(p.spacing, mr, partner=partner)):
+            assert np.array_equal(rm.attr(k + sfx).view(np.int32), v.view(np.int32)), (k, mr)
+    for ar in (-1.0, 1.0):
+        assert rm.vga_angular(ar) >= 0
+        sfx = "" if ar == -1.0 else " R%.2f" % ar
+        for k, v in zip(["Angular Mean Depth", "Angular Total Depth", "Angular Node Count"], og.angular(ar, partner=partner)):
+            assert np.array_equal(rm.attr(k + sfx).view(np.int32), v.view(np.int32)), (k, ar)
