@@ -43,7 +43,7 @@ ABI_SYMBOLS = [
 ]
 HOST_SYMBOLS = [
     "dmxh_last_error", "dmxh_map_create", "dmxh_map_destroy", "dmxh_map_grid", "dmxh_map_block_lines", "dmxh_map_fill",
-    "dmxh_map_filled_count", "dmxh_map_flat", "dmxh_map_make_graph", "dmxh_map_vga_global", "dmxh_map_vga_local",
+    "dmxh_map_filled_count", "dmxh_map_flat", "dmxh_map_make_graph", "dmxh_map_vga_global", "dmxh_map_vga_local", "dmxh_map_vga_metric", "dmxh_map_vga_angular",
     "dmxh_map_columns", "dmxh_map_attr", "dmxh_map_grid_connections", "dmxh_map_graph", "dmxh_release_context",
     "dmxh_map_state", "dmxh_map_step_depth", "dmxh_map_select", "dmxh_map_selection", "dmxh_map_flat_rows", "dmxh_map_bins",
     "dmxh_map_encode_nodes", "dmxh_map_begin_graph", "dmxh_map_finish_graph", "dmxh_map_write_global", "dmxh_map_write_local",
@@ -131,6 +131,8 @@ def host():
         H.dmxh_map_make_graph.argtypes = [vp, C.c_int, C.c_double]
         H.dmxh_map_vga_global.argtypes = [vp, C.c_double, C.c_int]
         H.dmxh_map_vga_local.argtypes = [vp, C.c_int]
+        H.dmxh_map_vga_metric.argtypes = [vp, C.c_double]
+        H.dmxh_map_vga_angular.argtypes = [vp, C.c_double]
         H.dmxh_map_columns.argtypes = [vp, C.c_char_p, C.c_int]
         H.dmxh_map_attr.argtypes = [vp, C.c_char_p, vp]
         H.dmxh_map_grid_connections.argtypes = [vp, vp]
@@ -548,6 +550,12 @@ class HostMap:
 
     def vga_local(self, simple=False):
         return self._ret(host().dmxh_map_vga_local(self.h, int(simple)))
+
+    def vga_metric(self, radius=-1.0):
+        return self._ret(host().dmxh_map_vga_metric(self.h, float(radius)))
+
+    def vga_angular(self, radius=-1.0):
+        return self._ret(host().dmxh_map_vga_angular(self.h, float(radius)))
 
     def columns(self):
         buf = C.create_string_buffer(8192)

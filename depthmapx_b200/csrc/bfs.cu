@@ -1071,7 +1071,11 @@ int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, De
         }
         VGA_CUDA(cudaMemsetAsync(d.any, 0, sizeof(int), st));
         k_update<W><<<grid, TPB, 0, st>>>(d, counts ? counts->p + (size_t)(level + 1) * counts_stride : nullptr);
-        k_decide<<<blocks_for(nb, 128), 128, 0, st>>>(d, (int)nb, bfs_mode, ctx->opt.pull_alpha, ctx->opt.pull_beta, work);
+        // measured on a C5 slice of 16,384 sources with both list kinds (profiles/r2_pull_alpha_hybrid.log): level kernels
+        // 75.9 / 69.1 / 70.0 / 82.6 ms for alpha 1 / 2 / 3 / 5 -- the in-lists shrink more than the out-lists and the down
+        // pass runs over two pyramids; x-major lists only: alpha 1 is best
+        k_decide<<<blocks_for(nb, 128), 128, 0, st>>>(d, (int)nb, bfs_mode, ctx->opt.pull_alpha > 0 ? ctx->opt.pull_alpha : (d.npyr_y ? 2 : 1),
+                                                       ctx->opt.pull_beta, work);
         tm.launches += 2;
         tm.main_launches += 2;
         int h_any = 0;

@@ -257,7 +257,8 @@ struct Options {
     int64_t build_chunk_entries = (int64_t)1 << 30;
     int64_t build_sort = 1;      // rows ordered by 1: bitmap rank in shared memory (k_rank_sort, own kernel; measured 1.13x-1.4x
                                  // faster builds); 0: cub segmented radix sort (also the fallback for grids of > 1.8M cells)
-    int64_t pull_alpha = 1;      // bottom-up step when (frontier out-nodes + 2n) * alpha > (open vertices' in-nodes + n) * beta
+    int64_t pull_alpha = 0;      // bottom-up step when (frontier out-nodes + 2n) * alpha > (open vertices' in-nodes + n) * beta;
+                                 // 0 = 2 when the graph has x- and y-major lists, else 1
     int64_t pull_beta = 1;
     int64_t bfs_order = 2;       // 0: x-major ordinals, 1: 8x8 tiles in Morton order, 2: + wall-respecting floods
     int64_t bfs_coop = 1;        // W >= 4: W/2 lanes share a node, 16 bytes each (k_push_nodes_coop / k_pull_nodes_coop; measured

@@ -103,6 +103,14 @@ int dmxh_map_vga_local(void *map, int simple_version) {
     });
 }
 
+int dmxh_map_vga_metric(void *map, double radius) {
+    return guarded([&] { return dmx::VGAMetric(radius, false).run(nullptr, *static_cast<dmx::PointMap *>(map), false); });
+}
+
+int dmxh_map_vga_angular(void *map, double radius) {
+    return guarded([&] { return dmx::VGAAngular(radius, false).run(nullptr, *static_cast<dmx::PointMap *>(map), false); });
+}
+
 int dmxh_map_columns(void *map, char *buf, int buflen) {
     const dmx::AttributeTable &t = static_cast<dmx::PointMap *>(map)->getAttributeTable();
     std::string s;

@@ -63,6 +63,11 @@ int AttributeTable::insertOrResetColumn(const std::string &name) {
     return idx;
 }
 
+int AttributeTable::getOrInsertColumn(const std::string &name) {
+    const int idx = getColumnIndex(name);
+    return idx >= 0 ? idx : insertOrResetColumn(name);
+}
+
 int AttributeTable::insertOrResetLockedColumn(const std::string &name) {
     int idx = insertOrResetColumn(name);
     m_columns[idx].locked = true;
@@ -427,6 +432,45 @@ std::vector<uint8_t> PointMap::contextSkipFlags() const {
     return flags;
 }
 
+std::vector<uint8_t> PointMap::blockedAdjacentFlags() const {
+    std::vector<uint8_t> flags;
+    for (size_t i = 0; i < m_cols; i++)
+        for (size_t j = 0; j < m_rows; j++) {
+            if (!m_points[i * m_rows + j].filled()) continue;
+            bool near = false;
+            for (int dx = -1; dx <= 1 && !near; dx++)
+                for (int dy = -1; dy <= 1 && !near; dy++) {
+                    const long x = (long)i + dx, y = (long)j + dy;
+                    near = x >= 0 && x < (long)m_cols && y >= 0 && y < (long)m_rows && m_points[(size_t)x * m_rows + (size_t)y].blocked();
+                }
+            flags.push_back(near ? 1 : 0);
+        }
+    return flags;
+}
+
+std::vector<int32_t> PointMap::mergePartners() const {
+    std::vector<int32_t> ord(m_cols * m_rows, -1), partner;
+    int32_t n = 0;
+    for (size_t c = 0; c < m_cols * m_rows; c++)
+        if (m_points[c].filled()) ord[c] = n++;
+    bool any = false;
+    for (size_t c = 0; c < m_cols * m_rows; c++) {
+        const Point &pt = m_points[c];
+        if (!pt.filled()) continue;
+        int32_t q = -1;
+        if (pt.merged()) {
+            const PixelRef m = pt.merge;
+            if (m.x < 0 || m.y < 0 || (size_t)m.x >= m_cols || (size_t)m.y >= m_rows || ord[(size_t)m.x * m_rows + (size_t)m.y] < 0)
+                throw RuntimeException("merge links must pair filled cells");
+            q = ord[(size_t)m.x * m_rows + (size_t)m.y];
+            any = true;
+        }
+        partner.push_back(q);
+    }
+    if (!any) partner.clear();
+    return partner;
+}
+
 // pointdata.cpp:1250-1264
 void PointMap::beginSparkGraph(bool boundarygraph) {
     if (!m_blockedlines) blockLines();
@@ -753,6 +797,102 @@ bool VGAVisualGlobalDepth::run(Communicator *, PointMap &map, bool) {
     if (rc != VGA_OK) throw RuntimeException(std::string("VGAVisualGlobalDepth: ") + vga_last_error());
     copy_from_primary(primary, depth.data());
     writeAttributes(map, depth.data());
+    return true;
+}
+
+static std::string radius_suffix(double radius, bool by_width, double width) {
+    // vgametric.cpp:33-41 (first test on the radius), vgaangular.cpp:30-38 (first test on the region's width)
+    if (radius == -1.0) return std::string();
+    char buf[64];
+    const char *fmt = (by_width ? width > 100.0 : radius > 100.0) ? "%.f" : (width < 1.0 ? "%.4f" : "%.2f");
+    std::snprintf(buf, sizeof buf, fmt, radius);
+    return std::string(" R") + buf;
+}
+
+void VGAMetric::writeAttributes(PointMap &map, double radius, const float *mean_angle, const float *mean_path_dist,
+                                const float *mean_line_dist, const float *node_count) {
+    AttributeTable &attributes = map.getAttributeTable();
+    const std::string rt = radius_suffix(radius, false, map.getRegion().width());
+    const int mspa_col = attributes.insertOrResetColumn("Metric Mean Shortest-Path Angle" + rt);
+    const int mspl_col = attributes.insertOrResetColumn("Metric Mean Shortest-Path Distance" + rt);
+    const int dist_col = attributes.insertOrResetColumn("Metric Mean Straight-Line Distance" + rt);
+    const int count_col = attributes.insertOrResetColumn("Metric Node Count" + rt);
+    if (node_count) {
+        const size_t n = attributes.getNumRows();
+        for (size_t v = 0; v < n; v++) {
+            attributes.setValue(v, mspa_col, mean_angle[v]);
+            attributes.setValue(v, mspl_col, mean_path_dist[v]);
+            attributes.setValue(v, dist_col, mean_line_dist[v]);
+            attributes.setValue(v, count_col, node_count[v]);
+        }
+    }
+    map.overrideDisplayedAttribute(-2);
+    map.setDisplayedAttribute(mspl_col);
+}
+
+bool VGAMetric::run(Communicator *comm, PointMap &map, bool) {
+    check_supported(map, "VGAMetric");
+    const int64_t n = (int64_t)map.getAttributeTable().getNumRows();
+    if (comm) comm->CommPostMessage(Communicator::NUM_RECORDS, map.getFilledPointCount());
+    if (m_gates_only) {  // the reference skips every cell (vgametric.cpp:65-68): columns only
+        writeAttributes(map, m_radius, nullptr, nullptr, nullptr, nullptr);
+        return true;
+    }
+    const std::vector<uint8_t> flags = map.blockedAdjacentFlags();
+    const std::vector<int32_t> partner = map.mergePartners();
+    vga_ctx *ctx = map.context();
+    CbState cb{comm, std::chrono::steady_clock::now(), false};
+    vga_ctx_set_callbacks(ctx, progress_cb, cancel_cb, &cb);
+    std::vector<float> angle((size_t)n), path((size_t)n), line((size_t)n), count((size_t)n);
+    const int rc = vga_metric(ctx, map.graph(), flags.data(), partner.empty() ? nullptr : partner.data(), map.getSpacing(), m_radius,
+                              nullptr, n, angle.data(), path.data(), line.data(), count.data(), nullptr);
+    vga_ctx_set_callbacks(ctx, nullptr, nullptr, nullptr);
+    if (rc == VGA_ERR_CANCELLED) throw Communicator::CancelledException();
+    if (rc != VGA_OK) throw RuntimeException(std::string("VGAMetric: ") + vga_last_error());
+    writeAttributes(map, m_radius, angle.data(), path.data(), line.data(), count.data());
+    return true;
+}
+
+void VGAAngular::writeAttributes(PointMap &map, double radius, const float *mean_depth, const float *total_depth,
+                                 const float *node_count) {
+    AttributeTable &attributes = map.getAttributeTable();
+    const std::string rt = radius_suffix(radius, true, map.getRegion().width());
+    // getOrInsertColumn: existing columns keep their values and statistics (vgaangular.cpp:44-52)
+    const int mean_depth_col = attributes.getOrInsertColumn("Angular Mean Depth" + rt);
+    const int total_depth_col = attributes.getOrInsertColumn("Angular Total Depth" + rt);
+    const int count_col = attributes.getOrInsertColumn("Angular Node Count" + rt);
+    if (node_count) {
+        const size_t n = attributes.getNumRows();
+        for (size_t v = 0; v < n; v++) {
+            if (node_count[v] > 0.0f) attributes.setValue(v, mean_depth_col, mean_depth[v]);
+            attributes.setValue(v, total_depth_col, total_depth[v]);
+            attributes.setValue(v, count_col, node_count[v]);
+        }
+    }
+    map.setDisplayedAttribute(-2);
+    map.setDisplayedAttribute(mean_depth_col);
+}
+
+bool VGAAngular::run(Communicator *comm, PointMap &map, bool) {
+    check_supported(map, "VGAAngular");
+    const int64_t n = (int64_t)map.getAttributeTable().getNumRows();
+    if (comm) comm->CommPostMessage(Communicator::NUM_RECORDS, map.getFilledPointCount());
+    if (m_gates_only) {
+        writeAttributes(map, m_radius, nullptr, nullptr, nullptr);
+        return true;
+    }
+    const std::vector<uint8_t> flags = map.blockedAdjacentFlags();
+    const std::vector<int32_t> partner = map.mergePartners();
+    vga_ctx *ctx = map.context();
+    CbState cb{comm, std::chrono::steady_clock::now(), false};
+    vga_ctx_set_callbacks(ctx, progress_cb, cancel_cb, &cb);
+    std::vector<float> mean((size_t)n), total((size_t)n), count((size_t)n);
+    const int rc = vga_angular(ctx, map.graph(), flags.data(), partner.empty() ? nullptr : partner.data(), m_radius, nullptr, n,
+                               mean.data(), total.data(), count.data(), nullptr);
+    vga_ctx_set_callbacks(ctx, nullptr, nullptr, nullptr);
+    if (rc == VGA_ERR_CANCELLED) throw Communicator::CancelledException();
+    if (rc != VGA_OK) throw RuntimeException(std::string("VGAAngular: ") + vga_last_error());
+    writeAttributes(map, m_radius, mean.data(), total.data(), count.data());
     return true;
 }
 

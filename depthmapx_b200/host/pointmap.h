@@ -94,6 +94,7 @@ class AttributeTable {
     AttributeTable();
     int insertOrResetColumn(const std::string &name);        // attributetable.cpp:303-319
     int insertOrResetLockedColumn(const std::string &name);  // :321-326
+    int getOrInsertColumn(const std::string &name);          // :290-301: an existing column keeps its values and statistics
     int getColumnIndex(const std::string &name) const;       // -1 if absent
     bool hasColumn(const std::string &name) const { return getColumnIndex(name) >= 0; }
     size_t getNumColumns() const { return m_columns.size(); }
@@ -202,6 +203,7 @@ class PointMap {
     const AttributeTable &getAttributeTable() const { return m_attributes; }
     int getDisplayedAttribute() const { return m_displayed_attribute; }
     void setDisplayedAttribute(int col) { m_displayed_attribute = col; }
+    void overrideDisplayedAttribute(int col) { m_displayed_attribute = col; }  // pointdata.h: sets the member, nothing else
     const std::string &getName() const { return m_name; }
 
     // flat image of the hot-path inputs (the vga_grid of the C ABI); arrays owned by the map
@@ -242,6 +244,10 @@ class PointMap {
     bool unmergePixel(PixelRef a);
     bool isPixelMerged(const PixelRef &a) const { return getPoint(a).merged(); }
     bool hasMerges() const;
+    // Point::blocked || PointMap::blockedAdjacent (pointdata.cpp:1016-1066) per attribute row: the cells VGAMetric /
+    // VGAAngular expand; Point::m_merge per row as row indices (-1 = not merged), empty when nothing is merged
+    std::vector<uint8_t> blockedAdjacentFlags() const;
+    std::vector<int32_t> mergePartners() const;
     // The adjacency the BFS analyses (global, step depth) run on when cells are merged: every merged pair contracted
     // into its smaller-ordinal cell, see merge_contract.h.
     typedef dmx::Contracted Contracted;
@@ -350,6 +356,34 @@ class VGAVisualGlobalDepth : public IVGA {
     bool run(Communicator *comm, PointMap &map, bool simple_version) override;
     // column "Visual Step Depth" from the per-cell depths of vga_step_depth (-1 = not reached: value stays -1)
     static void writeAttributes(PointMap &map, const int32_t *depth);
+};
+
+// Metric VGA (salalib/vgamodules/vgametric.cpp:25-136): per-source shortest metric paths; radius in map units
+class VGAMetric : public IVGA {
+    double m_radius;
+    bool m_gates_only;
+
+  public:
+    std::string getAnalysisName() const override { return "Metric Analysis"; }
+    bool run(Communicator *comm, PointMap &map, bool simple_version) override;
+    VGAMetric(double radius, bool gates_only) : m_radius(radius), m_gates_only(gates_only) {}
+    // columns (vgametric.cpp:32-56), row writes (:116-120) and display (:131-133) from the four columns of vga_metric; NULL
+    // arrays = columns only (gates_only)
+    static void writeAttributes(PointMap &map, double radius, const float *mean_angle, const float *mean_path_dist,
+                                const float *mean_line_dist, const float *node_count);
+};
+
+// Angular VGA (salalib/vgamodules/vgaangular.cpp:22-133): least-turn paths; radius in units of 90 degrees
+class VGAAngular : public IVGA {
+    double m_radius;
+    bool m_gates_only;
+
+  public:
+    std::string getAnalysisName() const override { return "Angular Analysis"; }
+    bool run(Communicator *comm, PointMap &map, bool simple_version) override;
+    VGAAngular(double radius, bool gates_only) : m_radius(radius), m_gates_only(gates_only) {}
+    static void writeAttributes(PointMap &map, double radius, const float *mean_depth, const float *total_depth,
+                                const float *node_count);
 };
 
 // process-wide GPU context (one process drives one GPU; device from VGA_DEVICE or LOCAL_RANK)

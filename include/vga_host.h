@@ -32,6 +32,9 @@ void dmxh_map_flat(void *map, int64_t *cells, int64_t *nseg, uint16_t *state, ui
 int dmxh_map_make_graph(void *map, int boundarygraph, double maxdist);
 int dmxh_map_vga_global(void *map, double radius, int simple_version);
 int dmxh_map_vga_local(void *map, int simple_version);
+/* dmx::VGAMetric(radius, false).run / dmx::VGAAngular(radius, false).run; radius -1.0 = n */
+int dmxh_map_vga_metric(void *map, double radius);
+int dmxh_map_vga_angular(void *map, double radius);
 int dmxh_map_columns(void *map, char *buf, int buflen); /* '\n' separated, returns the count */
 int64_t dmxh_map_num_rows(void *map); /* attribute rows = cells that had a Node made */
 int dmxh_map_attr(void *map, const char *name, float *out /* dmxh_map_num_rows values, x-major */);

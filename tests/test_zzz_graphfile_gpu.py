@@ -66,6 +66,33 @@ def test_vga_on_loaded_graph(files, tmp_path, case):
 
 
 @pytest.mark.parametrize("case", CASES)
+def test_metric_and_angular_on_loaded_graph(files, tmp_path, case):
+    """Row f4 through the host layer (dmx::VGAMetric / dmx::VGAAngular): -m VGA -vm metric -vr n | -vr <4 cells>, -vm angular
+    (and a second angular run on its own output: getOrInsertColumn keeps the columns), and both on the map with merge links --
+    files byte-identical to the unmodified reference CLI's (tests/golden/graphfiles_metric.npz)."""
+    d, _ = files
+    fx = golden("graphfiles_metric")
+    out = str(tmp_path / "o.graph")
+
+    def check(src, key, fn):
+        if isinstance(src, bytes):
+            open(str(tmp_path / "in.graph"), "wb").write(src)
+            src = str(tmp_path / "in.graph")
+        g = capi.GraphFile(src)
+        assert fn(g.map())
+        g.save(out)
+        assert data(out) == fx[f"{case}__{key}"].tobytes(), key
+
+    prep, prep_l = os.path.join(d, f"{case}__prep.graph"), os.path.join(d, f"{case}__prep_l.graph")
+    check(prep, "metric", lambda m: m.vga_metric(-1.0))
+    check(prep, "metric_r", lambda m: m.vga_metric(float(str(fx[f"{case}__radius"]))))
+    check(prep, "angular", lambda m: m.vga_angular(-1.0))
+    check(fx[f"{case}__angular"].tobytes(), "angular2", lambda m: m.vga_angular(-1.0))
+    check(prep_l, "metric_l", lambda m: m.vga_metric(-1.0))
+    check(prep_l, "angular_l", lambda m: m.vga_angular(-1.0))
+
+
+@pytest.mark.parametrize("case", CASES)
 def test_step_depth_on_loaded_graph(files, tmp_path, case):
     """-m STEPDEPTH -sdp x,y -sdt visual"""
     d, args = files

@@ -18,8 +18,8 @@ for rep in range(2):
     print(f"build rep{rep}: wall {dt*1e3:.1f} ms N={g.n} E={g.entries} {ctx.timing()}", flush=True)
     if rep == 0: g.free()
 if "global" in what:
-    for rad in (-1, 3):
-        for rep in range(2):
+    for rad in [int(x) for x in os.environ.get("VGA_TIME_RADII", "-1,3").split(",")]:
+        for rep in range(int(os.environ.get("VGA_TIME_REPS", "2"))):
             lim = int(os.environ.get("VGA_TIME_SRC", "0"))
             src = None if lim <= 0 else (g.n // 2 - lim // 2, g.n // 2 - lim // 2 + lim)
             t0 = time.time(); tn, td, dist, used = g.global_ints(rad, src); dt = time.time() - t0
