@@ -42,6 +42,7 @@ constexpr uint32_t NONE = 0xffffffffu;
 constexpr uint32_t KEY_INF = 0x7f800000u;     // never queued
 constexpr uint32_t KEY_POPPED = 0xffffffffu;  // finalised (Point::m_misc == ~0)
 constexpr int MWARPS = 4;                     // warps (= sources in flight) per CTA
+constexpr int MU = 4;                         // chunks of 32 row cells whose states are in flight together
 
 struct MaArgs {
     int64_t n;
@@ -168,25 +169,43 @@ __device__ __forceinline__ void expand_row(const MaArgs &a, uint4 *state, uint32
         }
         const uint32_t excl = incl - run.y;
         const uint32_t cells = __shfl_sync(FULL, incl, 31);
-        for (uint32_t cb = 0; cb < cells; cb += 32) {
-            const uint32_t c = cb + lane;
-            int lo = 0, hi = 32;  // last lane whose first cell index is <= c
+        // MU chunks of 32 cells per round: the vertex states and coordinates of all of them are requested before the first is
+        // used (the search is latency bound: one dependent pop -> row -> state chain per warp)
+        for (uint32_t cb = 0; cb < cells; cb += 32 * MU) {
+            uint32_t vv[MU];
+            uint4 svv[MU];
+            int32_t rvv[MU];
+            bool actv[MU];
 #pragma unroll
-            for (int it = 0; it < 5; it++) {
-                const int mid = (lo + hi) >> 1;
-                const uint32_t ev = __shfl_sync(FULL, excl, mid);
-                if (ev <= c) lo = mid; else hi = mid;
+            for (int j = 0; j < MU; j++) {
+                const uint32_t c = cb + 32 * j + lane;
+                int lo = 0, hi = 32;  // last lane whose first cell index is <= c
+#pragma unroll
+                for (int it = 0; it < 5; it++) {
+                    const int mid = (lo + hi) >> 1;
+                    const uint32_t ev = __shfl_sync(FULL, excl, mid);
+                    if (ev <= c) lo = mid; else hi = mid;
+                }
+                const uint32_t first = __shfl_sync(FULL, run.x, lo);
+                const uint32_t eoff = __shfl_sync(FULL, excl, lo);
+                actv[j] = c < cells;
+                vv[j] = first + (c - eoff);
+                svv[j] = make_uint4(0u, 0u, KEY_POPPED, 0u);
+                rvv[j] = 0;
+                if (actv[j]) {
+                    svv[j] = state[vv[j]];
+                    rvv[j] = a.refs[vv[j]];
+                }
             }
-            const uint32_t first = __shfl_sync(FULL, run.x, lo);
-            const uint32_t eoff = __shfl_sync(FULL, excl, lo);
-            const bool act = c < cells;
-            const uint32_t v = first + (c - eoff);
-            bool queue = false;
-            uint32_t newkey = 0, oldkey = 0;
-            if (act) {
-                uint4 sv = state[v];
-                if (sv.z != KEY_POPPED) {
-                    const int32_t rv = a.refs[v];
+#pragma unroll
+            for (int j = 0; j < MU; j++) {
+                if (cb + 32 * j >= cells) break;  // uniform
+                const uint32_t v = vv[j];
+                bool queue = false;
+                uint32_t newkey = 0, oldkey = 0;
+                uint4 sv = svv[j];
+                if (actv[j] && sv.z != KEY_POPPED) {
+                    const int32_t rv = rvv[j];
                     const int abx = ref_x(rv) - ux, aby = ref_y(rv) - uy;
                     bool relax;
                     float nk = 0.0f, ncum = 0.0f;
@@ -224,24 +243,24 @@ __device__ __forceinline__ void expand_row(const MaArgs &a, uint4 *state, uint32
                         state[v] = sv;
                     }
                 }
-            }
-            unsigned qm = __ballot_sync(FULL, queue);
-            while (qm) {
-                const int l = __ffs(qm) - 1;
-                qm &= qm - 1;
-                const uint32_t qv = __shfl_sync(FULL, v, l);
-                const uint32_t qk = __shfl_sync(FULL, newkey, l);
-                const uint32_t qo = __shfl_sync(FULL, oldkey, l);
-                const uint32_t fresh_at = size;
-                if (qo == KEY_INF) size++;
-                if (lane == 0) heap_up(heap, pos, qo == KEY_INF ? fresh_at : pos[qv], ((u64)qk << 32) | qv);
+                unsigned qm = __ballot_sync(FULL, queue);
+                while (qm) {
+                    const int l = __ffs(qm) - 1;
+                    qm &= qm - 1;
+                    const uint32_t qv = __shfl_sync(FULL, v, l);
+                    const uint32_t qk = __shfl_sync(FULL, newkey, l);
+                    const uint32_t qo = __shfl_sync(FULL, oldkey, l);
+                    const uint32_t fresh_at = size;
+                    if (qo == KEY_INF) size++;
+                    if (lane == 0) heap_up(heap, pos, qo == KEY_INF ? fresh_at : pos[qv], ((u64)qk << 32) | qv);
+                }
             }
         }
     }
     __syncwarp();  // state and heap writes of this row before anything reads them
 }
 
-__global__ void __launch_bounds__(MWARPS * 32) k_metric_angular(MaArgs a) {
+__global__ void __launch_bounds__(MWARPS * 32, 6) k_metric_angular(MaArgs a) {
     const int lane = threadIdx.x & 31;
     const int64_t slot = (int64_t)blockIdx.x * MWARPS + (threadIdx.x >> 5);
     const int64_t n = a.n;
@@ -350,11 +369,12 @@ int run_metric_angular(vga_ctx *ctx, vga_graph *g, int angular, const uint8_t *e
     Timing &tm = ctx->timing;
     StageTimer kt(ctx, 0, &tm.kernel_ms);
     StageTimer mt(ctx, 2, &tm.main_kernel_ms);
-    // sources in flight: 28 bytes per (slot, vertex); bounded by the resident warps and by 40 % of the free memory
+    // sources in flight: 28 bytes per (slot, vertex); bounded by the resident warps (6 CTAs of 4 warps per SM) and by 40 % of
+    // the free memory
     size_t free_b = 0, total_b = 0;
     VGA_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const int64_t per_slot = 28 * n;
-    int64_t slots = std::min<int64_t>((int64_t)ctx->sm_count * 32, (int64_t)((double)free_b * 0.4) / std::max<int64_t>(per_slot, 1));
+    int64_t slots = std::min<int64_t>((int64_t)ctx->sm_count * 6 * MWARPS, (int64_t)((double)free_b * 0.4) / std::max<int64_t>(per_slot, 1));
     if (ctx->opt.metric_slots > 0) slots = ctx->opt.metric_slots;
     slots = std::max<int64_t>(MWARPS, std::min<int64_t>(slots, (nsrc + MWARPS - 1) / MWARPS * MWARPS));
     slots = slots / MWARPS * MWARPS;

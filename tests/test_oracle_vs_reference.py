@@ -52,6 +52,8 @@ def test_random_plan_bit_equal_to_reference(seed):
         for k, v in po.local_formulas(*og.local_ints()).items():
             assert np.array_equal(rm.attr(k), v), k
     # oracle metric / angular == reference VGAMetric / VGAAngular (row f4), radius n and a finite radius, float32 bit-equal
+    if rm.n > 800:
+        return  # both searches are O(n^2 log n) per map; the larger plans are covered by tests/golden/metric_angular.npz
     for mr in (-1.0, rng.choice([3.0, 5.5, 8.0]) * sp):
         assert rm.vga_metric(mr) >= 0
         sfx = "" if mr == -1.0 else " R%.2f" % mr
