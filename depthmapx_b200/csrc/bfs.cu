@@ -327,7 +327,9 @@ template <int W> __global__ void __launch_bounds__(TPB) k_pull_nodes(BfsDev d) {
 // lane that owns a whole W-word vector issues W/2 such gathers, so wider batches bought nothing (266 / 301 / 437 ms for
 // W = 2 / 4 / 8).  Here G = W/2 consecutive lanes share one node: each loads / updates its own 16-byte slice, so a node's
 // vector arrives in ONE wavefront whatever W is, and the visits per source drop by G.
-template <int W, int G> __global__ void __launch_bounds__(TPB) k_push_nodes_coop(BfsDev d) {
+// PU = nodes per lane whose ids, then vectors, are requested before the first is used (the kernel stalls on the dependent
+// id -> vector chain: 80 % long-scoreboard samples with one node in flight, profiles/r2_prof_k_push_nodes_coop_summary.txt)
+template <int W, int G, int PU> __global__ void __launch_bounds__(TPB) k_push_nodes_coop(BfsDev d) {
     static_assert(W == 2 * G, "two words per lane");
     const int b = blockIdx.y;
     if (!d.active[b] || d.mode[b] != 0) return;
@@ -362,14 +364,27 @@ template <int W, int G> __global__ void __launch_bounds__(TPB) k_push_nodes_coop
             const ulonglong2 myf = *reinterpret_cast<const ulonglong2 *>(fr + (wbase + src_lane) * W + 2 * g);
             if ((myf.x | myf.y) == 0ULL) continue;
             u64 *npu = (d.f_isy && d.f_isy[wbase + src_lane]) ? d.npyr_y + (int64_t)b * d.pyr_total * W : np;
-            for (uint64_t e = e0 + sub; e < e1; e += NPI) {
-                const uint32_t c = __ldcs(d.f_nodes + e);
-                VGA_COUNT(npush_nodes, 1);
-                u64 *p = (c < n ? nx + (int64_t)c * W : npu + (int64_t)(c - n) * W) + 2 * g;
-                const ulonglong2 cur = *reinterpret_cast<const ulonglong2 *>(p);
-                const u64 a0 = myf.x & ~cur.x, a1 = myf.y & ~cur.y;
-                if (a0) atomicOr(&p[0], a0);
-                if (a1) atomicOr(&p[1], a1);
+            for (uint64_t e = e0 + sub; e < e1; e += NPI * PU) {
+                uint32_t c[PU];
+#pragma unroll
+                for (int i = 0; i < PU; i++) c[i] = e + (uint64_t)i * NPI < e1 ? __ldcs(d.f_nodes + e + (uint64_t)i * NPI) : 0xffffffffu;
+                u64 *p[PU];
+                ulonglong2 cur[PU];
+#pragma unroll
+                for (int i = 0; i < PU; i++) {
+                    p[i] = (c[i] < n ? nx + (int64_t)c[i] * W : npu + (int64_t)(c[i] - n) * W) + 2 * g;
+                    cur[i] = make_ulonglong2(~0ULL, ~0ULL);
+                    if (c[i] != 0xffffffffu) {
+                        VGA_COUNT(npush_nodes, 1);
+                        cur[i] = *reinterpret_cast<const ulonglong2 *>(p[i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < PU; i++) {
+                    const u64 a0 = myf.x & ~cur[i].x, a1 = myf.y & ~cur[i].y;
+                    if (a0) atomicOr(&p[i][0], a0);
+                    if (a1) atomicOr(&p[i][1], a1);
+                }
             }
         }
     }
@@ -1018,8 +1033,12 @@ int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, De
         dim3 grid(xblocks, (unsigned)nb);
         if (bfs_mode != 1 || level == 0) {
             if constexpr (W >= 4 && W <= 16) {
-                if (ctx->opt.bfs_coop)
-                    k_push_nodes_coop<W, W / 2><<<grid, TPB, 0, st>>>(d);
+                if (ctx->opt.bfs_coop && ctx->opt.bfs_push_unroll >= 4)
+                    k_push_nodes_coop<W, W / 2, 4><<<grid, TPB, 0, st>>>(d);
+                else if (ctx->opt.bfs_coop && ctx->opt.bfs_push_unroll >= 2)
+                    k_push_nodes_coop<W, W / 2, 2><<<grid, TPB, 0, st>>>(d);
+                else if (ctx->opt.bfs_coop)
+                    k_push_nodes_coop<W, W / 2, 1><<<grid, TPB, 0, st>>>(d);
                 else
                     k_push_nodes<W><<<grid, TPB, 0, st>>>(d);
             } else {

@@ -268,6 +268,7 @@ struct Options {
                                  // 0 = x-major only, 1 = when the call that derives the lists has at least n / 4 sources
                                  // (measured on the 10^6-cell plan: the second set of lists costs ~0.2 us per row once per
                                  // graph and saves ~1 us per source; a rank of an 8-GPU run has n / 8 sources)
+    int64_t bfs_push_unroll = 4; // nodes per lane in flight in the top-down step (1, 2 or 4)
     int64_t metric_slots = 0;    // metric / angular VGA: sources (warps) in flight, 0 = resident warps bounded by memory
     int64_t bfs_pull_unroll = 4; // node loads per lane between two early-exit checks of the bottom-up step: 4 (measured on the
                                  // C5 bench subset: level kernels 1483 -> 1439 ms) or 2

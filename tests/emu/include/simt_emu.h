@@ -59,6 +59,7 @@ inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { return
 struct alignas(16) ulonglong2 {
     unsigned long long x, y;
 };
+inline ulonglong2 make_ulonglong2(unsigned long long a, unsigned long long b) { return ulonglong2{a, b}; }
 
 // ---------------------------------------------------------------------------------------------- runtime API
 typedef int cudaError_t;
