@@ -60,6 +60,7 @@ struct BfsDev {
     int64_t n;                       // filled vertices
     const uint64_t *f_ptr;           // [n+1] out-rows: offsets into f_nodes
     const uint32_t *f_nodes;         // node ids: id < n = the vertex's own word, id >= n = inner pyramid node id - n
+    const uint32_t *f_split;         // [n] leading "new" nodes of every out-row (the others are covered by row u-1), or nullptr
     const uint64_t *t_ptr;           // [n+1] in-rows (nullptr in push-only runs)
     const uint32_t *t_nodes;
     const uint64_t *rowptr;          // [n+1] entry offsets of the CSR rows, or nullptr (statistics of the CSR byte model)
@@ -72,6 +73,11 @@ struct BfsDev {
     u64 *pyr_y, *npyr_y;
     const uint32_t *perm_x;
     const uint8_t *f_isy, *t_isy;    // [n] 1 = the row's list is the y-major one
+    // [batches][dirty_stride] one bit per group of 8 vertices (= per work item of the last down launch): some node of pyramid
+    // levels 1-3 above the group holds bits (set by k_push_delta and by the down launch that fills level 3, consumed and
+    // cleared by the last down launch, which skips the clear groups); nullptr = every group is visited
+    uint32_t *dirty, *dirty_y;
+    int64_t dirty_stride;
     int64_t pyr_total;               // inner nodes per batch
     const u64 *valid;                // [batches*W] valid source bits of each word
     int *active;                     // [batches] 1 while the batch goes on
@@ -84,8 +90,10 @@ struct BfsDev {
     int64_t pyr_cnt[PYR_LEVELS_DEV];
 };
 // per-batch statistics of a level: 0 CSR entries of the new frontier's rows, 1 in-row nodes of the open vertices,
-// 2 new vertices, 3 open vertices, 4 out-row nodes of the new frontier
+// 2 new vertices, 3 open vertices, 4 out-row nodes of the new frontier, 5 the out-row nodes the next top-down step will
+// visit (= 4 without f_split)
 constexpr int NSTAT = 8;
+constexpr int UPD_PLANES = 4, UPD_FLUSH = 15;  // k_update: bit-sliced counters hold 2^4 - 1 additions
 
 template <int W> __device__ __forceinline__ void ldw(const u64 *p, u64 (&o)[W]) {
     if constexpr (W == 1) {
@@ -127,6 +135,21 @@ template <int W> __device__ __forceinline__ void stw(u64 *p, const u64 (&o)[W]) 
     }
 }
 
+// LW consecutive words of a vector (what one lane of the lane-cooperative kernels owns): 16-byte accesses for LW = 2
+template <int LW> struct Slice {
+    u64 w[LW];
+};
+template <int LW> __device__ __forceinline__ Slice<LW> ld_slice(const u64 *p) {
+    Slice<LW> s;
+    if constexpr (LW == 2) {
+        const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(p);
+        s.w[0] = t.x;
+        s.w[1] = t.y;
+    } else {
+        s.w[0] = p[0];
+    }
+    return s;
+}
 // source i of the ordered list -> bit (i & 63) of word (i >> 6); word wi lives in batch wi / W, slot wi % W
 template <int W> __global__ void k_init(BfsDev d, const int32_t *src, int64_t nsrc) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -196,7 +219,7 @@ template <int W> __global__ void __launch_bounds__(TPB) k_push_nodes(BfsDev d) {
 }
 
 // down pass of the push, three levels per launch, top chunk first: level k+3 .. k+1 -> level k (`next` for k = 0)
-template <int W> __global__ void __launch_bounds__(TPB) k_pyr_down(BfsDev d, int k, int ymaj) {
+template <int W> __global__ void __launch_bounds__(TPB, W <= 4 ? 4 : 1) k_pyr_down(BfsDev d, int k, int ymaj) {
     const int b = blockIdx.y;
     if (!d.active[b] || d.mode[b] != 0) return;
     u64 *np = (ymaj ? d.npyr_y : d.npyr) + (int64_t)b * d.pyr_total * W;
@@ -208,9 +231,27 @@ template <int W> __global__ void __launch_bounds__(TPB) k_pyr_down(BfsDev d, int
     const int64_t c0 = d.pyr_cnt[k];
     const int64_t c1 = s1 ? d.pyr_cnt[k + 1] : 0, c2 = s2 ? d.pyr_cnt[k + 2] : 0, c3 = s3 ? d.pyr_cnt[k + 3] : 0;
     const int64_t groups = (c0 + 7) / 8;
-    for (int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x; t < groups; t += (int64_t)gridDim.x * TPB) {
-        VGA_COUNT(pyr_down_groups, 1);
-        pyr_down_group<W>(dst, c0, s1, c1, s2, c2, s3, c3, t, leaf);
+    uint32_t *dirty = (ymaj ? d.dirty_y : d.dirty);
+    if (dirty) dirty += (int64_t)b * d.dirty_stride;
+    const int lane = threadIdx.x & 31;
+    // warp-uniform loop: 32 consecutive groups per warp and round = one word of the dirty bitmap
+    for (int64_t tb = (int64_t)blockIdx.x * TPB + (threadIdx.x & ~31); tb < groups; tb += (int64_t)gridDim.x * TPB) {
+        const int64_t t = tb + lane;
+        if (k == 0 && dirty) {
+            const uint32_t word = dirty[tb >> 5];
+            if (word == 0u) continue;
+            if (t < groups && ((word >> lane) & 1u)) {
+                VGA_COUNT(pyr_down_groups, 1);
+                pyr_down_group<W>(dst, c0, s1, c1, s2, c2, s3, c3, t, leaf);
+            }
+            __syncwarp();
+            if (lane == 0) dirty[tb >> 5] = 0u;
+        } else if (t < groups) {
+            VGA_COUNT(pyr_down_groups, 1);
+            const unsigned written = pyr_down_group<W>(dst, c0, s1, c1, s2, c2, s3, c3, t, leaf);
+            // level-3 nodes 8t .. 8t+7 feed the work items 8t .. 8t+7 of the last launch: byte t of the bitmap, owned by this thread
+            if (k == 3 && dirty && written) reinterpret_cast<uint8_t *>(dirty)[t] |= (uint8_t)written;
+        }
     }
 }
 
@@ -375,7 +416,7 @@ template <int W, int G, int PU> __global__ void __launch_bounds__(TPB) k_push_no
                     p[i] = (c[i] < n ? nx + (int64_t)c[i] * W : npu + (int64_t)(c[i] - n) * W) + 2 * g;
                     cur[i] = make_ulonglong2(~0ULL, ~0ULL);
                     if (c[i] != 0xffffffffu) {
-                        VGA_COUNT(npush_nodes, 1);
+                        VGA_COUNT(npush_nodes, g == 0);
                         cur[i] = *reinterpret_cast<const ulonglong2 *>(p[i]);
                     }
                 }
@@ -384,6 +425,144 @@ template <int W, int G, int PU> __global__ void __launch_bounds__(TPB) k_push_no
                     const u64 a0 = myf.x & ~cur[i].x, a1 = myf.y & ~cur[i].y;
                     if (a0) atomicOr(&p[i][0], a0);
                     if (a1) atomicOr(&p[i][1], a1);
+                }
+            }
+        }
+    }
+}
+
+
+// ---- top-down step that leaves shared nodes to the previous vertex (bfs_delta = 1, default) -------------------------------
+// Rows of consecutive ordinals (vertically adjacent cells) are nearly the same set: 93 % of the pyramid nodes of an out-row
+// of an urban plan cover only cells that row u-1 holds as well, and with spatially coherent batches a vertex joins the
+// frontier with the same source bits as its neighbour at the same level -- so most of what k_push_nodes ORs into a node has
+// just been ORed there by the neighbour (ncu: 2 % of the visits add a bit).  Every out-row is stored as [new nodes |
+// covered nodes] (k_emit_nodes / k_copy_chosen, f_split).  A vertex u pushes its frontier vector F[u] to its new nodes and
+// only F[u] & ~F[u-1] to its covered nodes: every cell of a covered node is in row u-1, and vertex u-1 delivers F[u-1]
+// to all of its row in this same launch (by the same rule, recursively down to a vertex whose predecessor holds no bit).
+// A warp takes 32 consecutive vertices and walks the new nodes of all of them, plus the covered nodes of the few whose
+// vector is not a subset of the predecessor's, as ONE flat list (segment found by binary search in a shared-memory prefix of
+// the lengths), so short lists keep every lane busy.
+// LW words per lane (2, or 1 for W = 1), G = W / LW lanes share a node (see k_push_nodes_coop), PU nodes per lane in flight.
+template <int W, int PU> __global__ void __launch_bounds__(TPB) k_push_delta(BfsDev d) {
+    constexpr int LW = W >= 2 ? 2 : 1;
+    constexpr int G = W / LW;
+    constexpr int NPI = 32 / G;  // nodes per warp and load
+    const int b = blockIdx.y;
+    if (!d.active[b] || d.mode[b] != 0) return;
+    // per warp: 64 list segments (vertex l: segment 2l = its new nodes, 2l+1 = its covered nodes when it has bits of its own)
+    __shared__ uint32_t s_pre[TPB / 32][65];
+    __shared__ uint64_t s_ptr[TPB / 32][64];
+    __shared__ uint8_t s_isy[TPB / 32][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int g = lane % G, sub = lane / G;
+    const u64 *fr = d.frontier + (int64_t)b * d.n * W;
+    u64 *nx = d.next + (int64_t)b * d.n * W;
+    u64 *np = d.npyr + (int64_t)b * d.pyr_total * W;
+    u64 *npy = d.npyr_y ? d.npyr_y + (int64_t)b * d.pyr_total * W : np;
+    const uint32_t n = (uint32_t)d.n;
+    for (int64_t base = (int64_t)blockIdx.x * TPB; base < d.n; base += (int64_t)gridDim.x * TPB) {
+        const int64_t wbase = base + (threadIdx.x & ~31);
+        const int64_t u = base + threadIdx.x;
+        u64 f[W];
+#pragma unroll
+        for (int j = 0; j < W; j++) f[j] = 0ULL;
+        if (u < d.n) ldw_stream<W>(fr + u * W, f);
+        u64 anyf = 0ULL, anyeff = 0ULL;
+#pragma unroll
+        for (int j = 0; j < W; j++) {
+            // the predecessor's vector: the lane below, or (lane 0) the last vertex of the previous tile
+            u64 pf = __shfl_up_sync(FULL, f[j], 1);
+            if (lane == 0) pf = (u > 0 && u < d.n) ? fr[(u - 1) * W + j] : 0ULL;
+            anyf |= f[j];
+            anyeff |= f[j] & ~pf;
+        }
+        if (__ballot_sync(FULL, anyf != 0ULL) == 0u) continue;
+        uint64_t my0 = 0;
+        uint32_t cnt_new = 0, cnt_cov = 0;
+        if (anyf != 0ULL) {
+            my0 = d.f_ptr[u];
+            cnt_new = d.f_split[u];
+            if (anyeff != 0ULL) cnt_cov = (uint32_t)(d.f_ptr[u + 1] - my0) - cnt_new;
+        }
+        // exclusive prefix of the segment lengths of the tile
+        uint32_t inc = cnt_new + cnt_cov;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += t;
+        }
+        const uint32_t total = __shfl_sync(FULL, inc, 31);
+        __syncwarp();  // the previous tile's readers are done
+        s_pre[wid][2 * lane] = inc - cnt_new - cnt_cov;
+        s_pre[wid][2 * lane + 1] = inc - cnt_cov;
+        if (lane == 31) s_pre[wid][64] = total;
+        s_ptr[wid][2 * lane] = my0;
+        s_ptr[wid][2 * lane + 1] = my0 + cnt_new;
+        s_isy[wid][lane] = (d.f_isy && anyf != 0ULL) ? d.f_isy[u] : (uint8_t)0;
+        __syncwarp();
+        // all segments of the tile as one flat list: short lists keep every lane busy
+        for (uint32_t t0 = 0; t0 < total; t0 += NPI * PU) {
+            uint32_t c[PU];
+            int seg[PU];
+            u64 *p[PU];
+            Slice<LW> cur[PU];
+#pragma unroll
+            for (int i = 0; i < PU; i++) {
+                const uint32_t t = t0 + (uint32_t)(i * NPI + sub);
+                c[i] = 0xffffffffu;
+                seg[i] = 0;
+                p[i] = nullptr;
+                if (t < total) {
+                    int lo = 0, hi = 64;  // last segment with s_pre <= t (empty segments share their successor's prefix)
+                    while (hi - lo > 1) {
+                        const int m = (lo + hi) >> 1;
+                        if (s_pre[wid][m] <= t) lo = m; else hi = m;
+                    }
+                    seg[i] = lo;
+                    c[i] = __ldcs(d.f_nodes + s_ptr[wid][lo] + (t - s_pre[wid][lo]));
+                    p[i] = (c[i] < n ? nx + (int64_t)c[i] * W : (s_isy[wid][lo >> 1] ? npy : np) + (int64_t)(c[i] - n) * W) + LW * g;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < PU; i++) {
+                if (c[i] != 0xffffffffu) {
+                    VGA_COUNT(npush_nodes, g == 0);
+                    cur[i] = ld_slice<LW>(p[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < PU; i++) {
+                if (c[i] != 0xffffffffu) {
+                    // the owner's vector (and its predecessor's) were read by this warp a moment ago: L1 hits
+                    const int64_t v = wbase + (seg[i] >> 1);
+                    Slice<LW> fv = ld_slice<LW>(fr + v * W + LW * g);
+                    if ((seg[i] & 1) && v > 0) {
+                        const Slice<LW> pf = ld_slice<LW>(fr + (v - 1) * W + LW * g);
+#pragma unroll
+                        for (int j = 0; j < LW; j++) fv.w[j] &= ~pf.w[j];
+                    }
+                    bool added = false;
+#pragma unroll
+                    for (int j = 0; j < LW; j++) {
+                        const u64 a = fv.w[j] & ~cur[i].w[j];
+                        if (a) {
+                            atomicOr(&p[i][j], a);
+                            added = true;
+                            VGA_COUNT(npush_atomics, 1);
+                        }
+                    }
+                    // an inner node of levels 1-3 received bits: the last down launch must visit the 8 vertices below it
+                    if (added && c[i] >= n && d.dirty) {
+                        const int64_t x = (int64_t)(c[i] - n);
+                        if (x < d.pyr_off[4]) {
+                            const int L = x < d.pyr_off[2] ? 1 : (x < d.pyr_off[3] ? 2 : 3);
+                            const int64_t t = (x - d.pyr_off[L]) >> (3 - L);
+                            uint32_t *dw = (s_isy[wid][seg[i] >> 1] ? d.dirty_y : d.dirty) + (int64_t)b * d.dirty_stride + (t >> 5);
+                            const uint32_t bit = 1u << (t & 31);
+                            if (!(*dw & bit)) atomicOr(dw, bit);
+                        }
+                    }
                 }
             }
         }
@@ -482,13 +661,13 @@ template <int W, int G, int U> __global__ void __launch_bounds__(TPB) k_pull_nod
 // fold next into visited/frontier, count new vertices per source, gather direction statistics;
 // `level_next` = level of the vertices being added
 template <int W>
-__global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[batches*W][64] of level_next*/) {
+__global__ void __launch_bounds__(TPB, W <= 4 ? 3 : 1) k_update(BfsDev d, int32_t *counts /*[batches*W][64] of level_next*/) {
     const int b = blockIdx.y;
     if (!d.active[b]) return;
     __shared__ int s_cnt[W * 64];
-    __shared__ u64 s_stat[5];
+    __shared__ u64 s_stat[6];
     for (int i = threadIdx.x; i < W * 64; i += TPB) s_cnt[i] = 0;
-    if (threadIdx.x < 5) s_stat[threadIdx.x] = 0ULL;
+    if (threadIdx.x < 6) s_stat[threadIdx.x] = 0ULL;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     u64 *fr = d.frontier + (int64_t)b * d.n * W;
@@ -500,12 +679,36 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[bat
     int cnt[W][2];  // lane l counts source bits l and l+32 of each word
 #pragma unroll
     for (int j = 0; j < W; j++) cnt[j][0] = cnt[j][1] = 0;
-    u64 f_edges = 0, u_nodes = 0, n_new = 0, n_open = 0, f_nodes = 0;
+    // New vertices per source = column sums of the bit matrix (vertices x sources).  Every thread first adds the words of
+    // its own vertices into bit-sliced counters (plane k = bit k of 64 vertical counts, a ripple of half adders: ~2 AND/XOR
+    // pairs per word) and only every UPD_FLUSH iterations the warp turns the planes into per-source counts (32 x 32
+    // bit-matrix transposes + popc, planes that are zero across the warp skipped): one transpose per word and iteration
+    // before, 4 planes per 15 iterations now.
+    u64 plane[W][UPD_PLANES];
+#pragma unroll
+    for (int j = 0; j < W; j++)
+#pragma unroll
+        for (int k = 0; k < UPD_PLANES; k++) plane[j][k] = 0ULL;
+    int pending = 0;
+    auto flush = [&]() {
+#pragma unroll
+        for (int j = 0; j < W; j++)
+#pragma unroll
+            for (int k = 0; k < UPD_PLANES; k++) {
+                const unsigned lo = (unsigned)plane[j][k], hi = (unsigned)(plane[j][k] >> 32);
+                if (__any_sync(FULL, lo != 0u)) cnt[j][0] += __popc(warp_transpose32(lo, lane)) << k;
+                if (__any_sync(FULL, hi != 0u)) cnt[j][1] += __popc(warp_transpose32(hi, lane)) << k;
+                plane[j][k] = 0ULL;
+            }
+        pending = 0;
+    };
+    u64 f_edges = 0, u_nodes = 0, n_new = 0, n_open = 0, f_nodes = 0, f_visit = 0;
     for (int64_t base = (int64_t)blockIdx.x * TPB; base < d.n; base += (int64_t)gridDim.x * TPB) {
         int64_t v = base + threadIdx.x;
         u64 nw[W];
 #pragma unroll
         for (int j = 0; j < W; j++) nw[j] = 0ULL;
+        bool expands = false;
         if (v < d.n) {
             VGA_COUNT(update_words, 1);
             u64 vv[W], xx[W];
@@ -524,7 +727,6 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[bat
 #pragma unroll
             for (int j = 0; j < W; j++) zero[j] = 0ULL;
             if (anyx) stw<W>(nx + v * W, zero);
-            bool expands = false;
             if (anynew) {
                 stw<W>(vis + v * W, vv);
                 n_new += 1;
@@ -540,36 +742,31 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[bat
                 if (d.t_ptr) u_nodes += d.t_ptr[v + 1] - d.t_ptr[v];
             }
         }
+        if (d.f_split) {
+            // what k_push_delta will visit for v: its new nodes, and the covered ones only if it holds a source bit that the
+            // vertex below it does not push (the first vertex of a warp tile is charged in full: 1/32 of the estimate)
+            bool sub = lane != 0;
+#pragma unroll
+            for (int j = 0; j < W; j++) {
+                const u64 mine = expands ? nw[j] : 0ULL;
+                const u64 pf = __shfl_up_sync(FULL, mine, 1);
+                if (mine & ~pf) sub = false;
+            }
+            if (expands) f_visit += sub ? (u64)d.f_split[v] : d.f_ptr[v + 1] - d.f_ptr[v];
+        }
 #pragma unroll
         for (int j = 0; j < W; j++) {
-            // new vertices per source: column sums of the warp's 32 x 64 bit matrix.  Few non-empty columns (late
-            // levels): one ballot per column; many (a coherent batch reaching a vertex with most of its sources at
-            // once): transpose the two 32 x 32 halves and popc.
-            const unsigned lo = (unsigned)nw[j], hi = (unsigned)(nw[j] >> 32);
-            unsigned lo_any = __reduce_or_sync(FULL, lo);
-            unsigned hi_any = __reduce_or_sync(FULL, hi);
-            if (__popc(lo_any) >= DENSE_COLUMNS) {
-                cnt[j][0] += __popc(warp_transpose32(lo, lane));
-            } else {
-                while (lo_any) {
-                    int bit = __ffs(lo_any) - 1;
-                    lo_any &= lo_any - 1;
-                    int c = __popc(__ballot_sync(FULL, (lo >> bit) & 1u));
-                    if (lane == bit) cnt[j][0] += c;
-                }
-            }
-            if (__popc(hi_any) >= DENSE_COLUMNS) {
-                cnt[j][1] += __popc(warp_transpose32(hi, lane));
-            } else {
-                while (hi_any) {
-                    int bit = __ffs(hi_any) - 1;
-                    hi_any &= hi_any - 1;
-                    int c = __popc(__ballot_sync(FULL, (hi >> bit) & 1u));
-                    if (lane == bit) cnt[j][1] += c;
-                }
+            u64 carry = nw[j];
+#pragma unroll
+            for (int k = 0; k < UPD_PLANES; k++) {
+                const u64 t = plane[j][k] & carry;
+                plane[j][k] ^= carry;
+                carry = t;
             }
         }
+        if (++pending == UPD_FLUSH) flush();  // uniform: every thread of the block makes the same number of iterations
     }
+    if (pending) flush();
 #pragma unroll
     for (int j = 0; j < W; j++) {
         if (cnt[j][0]) atomicAdd(&s_cnt[j * 64 + lane], cnt[j][0]);
@@ -581,6 +778,7 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[bat
         n_new += __shfl_down_sync(FULL, n_new, o);
         n_open += __shfl_down_sync(FULL, n_open, o);
         f_nodes += __shfl_down_sync(FULL, f_nodes, o);
+        f_visit += __shfl_down_sync(FULL, f_visit, o);
     }
     if (lane == 0) {
         if (f_edges) atomicAdd(&s_stat[0], f_edges);
@@ -588,22 +786,26 @@ __global__ void __launch_bounds__(TPB) k_update(BfsDev d, int32_t *counts /*[bat
         if (n_new) atomicAdd(&s_stat[2], n_new);
         if (n_open) atomicAdd(&s_stat[3], n_open);
         if (f_nodes) atomicAdd(&s_stat[4], f_nodes);
+        if (f_visit) atomicAdd(&s_stat[5], f_visit);
     }
     __syncthreads();
     if (counts)
         for (int i = threadIdx.x; i < W * 64; i += TPB)
             if (s_cnt[i]) atomicAdd(&counts[(int64_t)b * W * 64 + i], s_cnt[i]);
-    if (threadIdx.x < 5 && s_stat[threadIdx.x]) atomicAdd(&d.stats[b * NSTAT + threadIdx.x], s_stat[threadIdx.x]);
+    if (threadIdx.x < 6 && s_stat[threadIdx.x]) atomicAdd(&d.stats[b * NSTAT + threadIdx.x], s_stat[threadIdx.x]);
 }
 
 // per batch: retire finished batches, choose the next step's direction, reset statistics
-__global__ void k_decide(BfsDev d, int nb, int bfs_mode, int64_t alpha, int64_t beta, u64 *work /*[4]*/) {
+__global__ void k_decide(BfsDev d, int nb, int bfs_mode, int64_t alpha, int64_t beta, int64_t wdelta, u64 *work /*[4]*/) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
     if (!d.active[b]) return;
     const u64 fe = d.stats[b * NSTAT + 0], un = d.stats[b * NSTAT + 1], nn = d.stats[b * NSTAT + 2], open = d.stats[b * NSTAT + 3];
     const u64 fn = d.stats[b * NSTAT + 4];
-    for (int i = 0; i < 5; i++) d.stats[b * NSTAT + i] = 0;
+    // nodes the next top-down step would visit; a visit of k_push_delta nearly always ends in an atomic and costs
+    // `wdelta` times a node offered to the bottom-up step (measured, profiles/r2_level_timing_C5slice.log)
+    const u64 fv = d.f_split ? d.stats[b * NSTAT + 5] * (u64)wdelta : fn;
+    for (int i = 0; i < 6; i++) d.stats[b * NSTAT + i] = 0;
     // Retire the batch when nothing new was reached -- or when every vertex has been reached by every source of the
     // batch: expanding the last (largest) frontier could not find anything.
     if (nn != 0) atomicOr(d.any, 2);  // bit 1: this level added vertices (the histogram has one more level)
@@ -618,7 +820,7 @@ __global__ void k_decide(BfsDev d, int nb, int bfs_mode, int64_t alpha, int64_t 
     if (bfs_mode == 1)
         m = 1;
     else if (bfs_mode == 2)
-        m = ((fn + 2 * (u64)d.n) * (u64)alpha > (un + (u64)d.n) * (u64)beta) ? 1 : 0;
+        m = ((fv + 2 * (u64)d.n) * (u64)alpha > (un + (u64)d.n) * (u64)beta) ? 1 : 0;
     d.mode[b] = m;
     if (work) {
         // work[0]: adjacency entries of the vertices that expand next (SURVEY.md §8d CSR model, sum of deg over U_l),
@@ -779,17 +981,48 @@ __global__ void k_run_costs(const uint2 *runs, int64_t nruns, uint32_t n, u64 *c
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r < nruns) cost[r] = runs[r].x < n ? (u64)pyr_cost(runs[r].x, runs[r].y) : 0ULL;  // ghost runs: no nodes
 }
-// ids of the nodes of every run, written at the run's offset (exclusive scan of the per-run node counts)
+// ids of the nodes of every run, written at the run's offset (exclusive scan of the per-run node counts); one warp per
+// row, one lane per run.
 // `leaf` (y-major lists): a level-0 node i is written as the vertex leaf[i] (its x-major ordinal) -- leaves are always the
-// vertices' own words, only the inner nodes belong to the list's own pyramid
-__global__ void k_emit_nodes(const uint2 *runs, int64_t nruns, const u64 *node_off, uint32_t n, BfsDev d, const uint32_t *leaf,
-                             uint32_t *out) {
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nruns) return;
-    const uint2 run = runs[r];
-    if (run.x >= n) return;
-    uint64_t o = node_off[r];
-    pyr_decompose(run.x, run.y, [&](int k, uint32_t i) { out[o++] = k == 0 ? (leaf ? leaf[i] : i) : n + (uint32_t)d.pyr_off[k] + i; });
+// vertices' own words, only the inner nodes belong to the list's own pyramid.
+// `cover` (out-rows): bit 31 of an id (NODE_COVERED) is set when every cell the node covers also belongs to the PREVIOUS
+// row (row u-1 of the same run arrays, whose runs end where this row's begin): the top-down step then leaves the node
+// to the previous vertex whenever that vertex pushes a superset of the source bits (k_push_delta).
+constexpr uint32_t NODE_COVERED = 0x80000000u;
+__global__ void k_emit_nodes(int64_t rows, const uint64_t *runptr, const uint2 *runs, const u64 *node_off, uint32_t n, BfsDev d,
+                             const uint32_t *leaf, int cover, uint32_t *out) {
+    const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (u >= rows) return;
+    const uint64_t r0 = runptr[u], r1 = runptr[u + 1];
+    const uint64_t p0 = (cover && u > 0) ? runptr[u - 1] : r0;
+    // end of the previous row's run that contains cell s (0 = none); ghost runs start at >= n and sort last
+    auto covering_end = [&](uint32_t s) -> uint32_t {
+        uint64_t a = p0, b = r0;  // first run of [p0, r0) that starts beyond s
+        while (a < b) {
+            const uint64_t m = (a + b) >> 1;
+            if (runs[m].x <= s) a = m + 1; else b = m;
+        }
+        if (a == p0) return 0u;
+        const uint2 pr = runs[a - 1];
+        return pr.x + pr.y;
+    };
+    for (uint64_t r = r0 + lane; r < r1; r += 32) {
+        const uint2 run = runs[r];
+        if (run.x >= n) continue;
+        uint64_t o = node_off[r];
+        const uint32_t cend = p0 < r0 ? covering_end(run.x) : 0u;
+        const bool whole = cend >= run.x + run.y;
+        pyr_decompose(run.x, run.y, [&](int k, uint32_t i) {
+            bool cov = whole;
+            if (!whole && p0 < r0) {
+                const uint32_t s = i << k, e = (i + 1u) << k;  // inside the run: no clipping at n
+                cov = (s == run.x ? cend : covering_end(s)) >= e;
+            }
+            const uint32_t id = k == 0 ? (leaf ? leaf[i] : i) : n + (uint32_t)d.pyr_off[k] + i;
+            out[o++] = cov ? (id | NODE_COVERED) : id;
+        });
+    }
 }
 // nodeptr[v] = node offset of the first run of row v (node_off has nruns + 1 entries)
 __global__ void k_row_node_offsets(int64_t n, const uint64_t *runptr, const u64 *node_off, uint64_t *nodeptr) {
@@ -984,15 +1217,29 @@ __global__ void k_choose_lists(int64_t n, const uint64_t *xptr, const uint64_t *
     isy[v] = y ? 1 : 0;
     size[v] = y ? cy : cx;
 }
+// copies the chosen list of every row; nodes flagged NODE_COVERED go behind the others (flag stripped) and split[v] = the
+// number of unflagged ("new") nodes at the front.  yptr == nullptr: every row takes its x list.
 __global__ void k_copy_chosen(int64_t n, const uint64_t *xptr, const uint32_t *xnodes, const uint64_t *yptr, const uint32_t *ynodes,
-                              const uint32_t *ymap, const uint8_t *isy, const uint64_t *optr, uint32_t *onodes) {
+                              const uint32_t *ymap, const uint8_t *isy, const uint64_t *optr, uint32_t *onodes, uint32_t *split) {
     const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (v >= n) return;
     const int64_t yv = ymap ? (int64_t)ymap[v] : v;
-    const uint32_t *src = isy[v] ? ynodes + yptr[yv] : xnodes + xptr[v];
+    const uint32_t *src = (yptr && isy[v]) ? ynodes + yptr[yv] : xnodes + xptr[v];
     const uint64_t cnt = optr[v + 1] - optr[v], d = optr[v];
-    for (uint64_t i = lane; i < cnt; i += 32) onodes[d + i] = src[i];
+    const unsigned below = (1u << lane) - 1u;
+    uint64_t at = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        for (uint64_t i0 = 0; i0 < cnt; i0 += 32) {
+            const uint64_t i = i0 + lane;
+            const uint32_t id = i < cnt ? src[i] : 0u;
+            const bool mine = i < cnt && ((id & NODE_COVERED) != 0u) == (pass == 1);
+            const unsigned m = __ballot_sync(FULL, mine);
+            if (mine) onodes[d + at + __popc(m & below)] = id & ~NODE_COVERED;
+            at += __popc(m);
+        }
+        if (pass == 0 && split && lane == 0) split[v] = (uint32_t)at;
+    }
 }
 
 inline unsigned blocks_for(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
@@ -1029,10 +1276,23 @@ int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, De
     int kmax = 0;
     while (kmax + 4 < d.pyr_levels) kmax += 3;
     int level = 0, nlev = 1;
+    // VGA_LEVEL_TIMING=1 (development aid): device time of every kernel group of every level on stderr
+    const bool lt = std::getenv("VGA_LEVEL_TIMING") != nullptr;
+    cudaEvent_t le[6] = {};
+    if (lt)
+        for (auto &e : le) cudaEventCreate(&e);
     while (radius == -1 || level < radius) {
         dim3 grid(xblocks, (unsigned)nb);
+        if (lt) cudaEventRecord(le[0], st);
         if (bfs_mode != 1 || level == 0) {
-            if constexpr (W >= 4 && W <= 16) {
+            if (d.f_split) {
+                if (ctx->opt.bfs_delta_unroll >= 4)
+                    k_push_delta<W, 4><<<grid, TPB, 0, st>>>(d);
+                else if (ctx->opt.bfs_delta_unroll >= 2)
+                    k_push_delta<W, 2><<<grid, TPB, 0, st>>>(d);
+                else
+                    k_push_delta<W, 1><<<grid, TPB, 0, st>>>(d);
+            } else if constexpr (W >= 4 && W <= 16) {
                 if (ctx->opt.bfs_coop && ctx->opt.bfs_push_unroll >= 4)
                     k_push_nodes_coop<W, W / 2, 4><<<grid, TPB, 0, st>>>(d);
                 else if (ctx->opt.bfs_coop && ctx->opt.bfs_push_unroll >= 2)
@@ -1046,6 +1306,7 @@ int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, De
             }
             tm.launches++;
             tm.main_launches++;
+            if (lt) cudaEventRecord(le[1], st);
             for (int ymaj = 0; ymaj < (d.npyr_y ? 2 : 1); ymaj++)
                 for (int k = kmax; k >= 0; k -= 3) {
                     const int64_t groups = (d.pyr_cnt[k] + 7) / 8;
@@ -1055,6 +1316,8 @@ int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, De
                     tm.main_launches++;
                 }
         }
+        if (lt && !(bfs_mode != 1 || level == 0)) cudaEventRecord(le[1], st);
+        if (lt) cudaEventRecord(le[2], st);
         if (bfs_mode != 0 && level > 0) {
             for (int ymaj = 0; ymaj < (d.pyr_y ? 2 : 1); ymaj++)
                 for (int k = 0; k + 1 < d.pyr_levels; k += 3) {
@@ -1064,6 +1327,7 @@ int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, De
                     tm.launches++;
                     tm.main_launches++;
                 }
+            if (lt) cudaEventRecord(le[3], st);
             if constexpr (W >= 4 && W <= 16) {
                 if (ctx->opt.bfs_coop && ctx->opt.bfs_pull_unroll == 4)
                     k_pull_nodes_coop<W, W / 2, 4><<<grid, TPB, 0, st>>>(d);
@@ -1077,6 +1341,8 @@ int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, De
             tm.launches++;
             tm.main_launches++;
         }
+        if (lt && !(bfs_mode != 0 && level > 0)) cudaEventRecord(le[3], st);
+        if (lt) cudaEventRecord(le[4], st);
         if (counts && level + 1 >= *lcap) {
             mt.stop();
             DevBuf<int32_t> bigger;
@@ -1089,21 +1355,50 @@ int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, De
             mt.start();
         }
         VGA_CUDA(cudaMemsetAsync(d.any, 0, sizeof(int), st));
-        k_update<W><<<grid, TPB, 0, st>>>(d, counts ? counts->p + (size_t)(level + 1) * counts_stride : nullptr);
+        // ~15 vertices per thread (one flush of the bit-sliced counters) as long as that leaves >= 16 CTAs per SM
+        const int64_t ublocks_all = (d.n + TPB - 1) / TPB;
+        const int64_t ublocks = std::min<int64_t>(ublocks_all, std::max<int64_t>((ublocks_all + UPD_FLUSH - 1) / UPD_FLUSH,
+                                                                                 ((int64_t)ctx->sm_count * 16 + nb - 1) / nb));
+        k_update<W><<<dim3((unsigned)ublocks, (unsigned)nb), TPB, 0, st>>>(d, counts ? counts->p + (size_t)(level + 1) * counts_stride : nullptr);
         // measured on a C5 slice of 16,384 sources with both list kinds (profiles/r2_pull_alpha_hybrid.log): level kernels
         // 75.9 / 69.1 / 70.0 / 82.6 ms for alpha 1 / 2 / 3 / 5 -- the in-lists shrink more than the out-lists and the down
         // pass runs over two pyramids; x-major lists only: alpha 1 is best
-        k_decide<<<blocks_for(nb, 128), 128, 0, st>>>(d, (int)nb, bfs_mode, ctx->opt.pull_alpha > 0 ? ctx->opt.pull_alpha : (d.npyr_y ? 2 : 1),
-                                                       ctx->opt.pull_beta, work);
+        double lsum[NSTAT] = {};
+        if (lt) {
+            std::vector<u64> hs((size_t)nb * NSTAT);
+            cudaMemcpyAsync(hs.data(), d.stats, sizeof(u64) * nb * NSTAT, cudaMemcpyDeviceToHost, st);
+            cudaStreamSynchronize(st);
+            for (int64_t i = 0; i < nb; i++)
+                for (int k = 0; k < NSTAT; k++) lsum[k] += (double)hs[(size_t)(i * NSTAT + k)];
+        }
+        k_decide<<<blocks_for(nb, 128), 128, 0, st>>>(d, (int)nb, bfs_mode,
+                                                       ctx->opt.pull_alpha > 0 ? ctx->opt.pull_alpha : ((d.npyr_y && !d.f_split) ? 2 : 1),
+                                                       ctx->opt.pull_beta, std::max<int64_t>(1, ctx->opt.bfs_delta_weight), work);
         tm.launches += 2;
         tm.main_launches += 2;
+        if (lt) cudaEventRecord(le[5], st);
         int h_any = 0;
         VGA_CUDA(cudaMemcpyAsync(&h_any, d.any, sizeof(int), cudaMemcpyDeviceToHost, st));
         VGA_CUDA(cudaStreamSynchronize(st));
+        if (lt) {
+            float ms[5];
+            for (int i = 0; i < 5; i++) cudaEventElapsedTime(&ms[i], le[i], le[i + 1]);
+            std::vector<int> hm((size_t)nb), ha((size_t)nb);
+            cudaMemcpy(hm.data(), d.mode, sizeof(int) * nb, cudaMemcpyDeviceToHost);
+            cudaMemcpy(ha.data(), d.active, sizeof(int) * nb, cudaMemcpyDeviceToHost);
+            int np = 0, nl = 0;
+            for (int64_t i = 0; i < nb; i++)
+                if (ha[(size_t)i]) (hm[(size_t)i] ? nl : np)++;
+            fprintf(stderr, "[level %d] push %.3f down %.3f build %.3f pull %.3f update %.3f ms; next step: %d batches push, %d pull; "
+                    "per batch: new vertices %.0f, open %.0f, out-row nodes %.0f (to visit %.0f), in-row nodes of open %.0f\n",
+                    level, ms[0], ms[1], ms[2], ms[3], ms[4], np, nl, lsum[2] / nb, lsum[3] / nb, lsum[4] / nb, lsum[5] / nb, lsum[1] / nb);
+        }
         if (h_any & 2) nlev = level + 2;
         if (!(h_any & 1)) break;
         level++;
     }
+    if (lt)
+        for (auto &e : le) cudaEventDestroy(e);
     *nlev_out = nlev;
     return VGA_OK;
 }
@@ -1294,6 +1589,18 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources,
         VGA_TRY(ctx->ws.get("bfs_npyr_y", sizeof(u64) * (size_t)chunk * (size_t)std::max<int64_t>(pl.total, 1) * W, (void **)&npyr_y));
         VGA_CUDA(cudaMemsetAsync(npyr_y, 0, sizeof(u64) * (size_t)chunk * (size_t)std::max<int64_t>(pl.total, 1) * W, st));
     }
+    // dirty-group bitmaps of the down pass (only k_push_delta maintains them)
+    const int64_t dirty_stride = (((n + 7) / 8 + 31) / 32 + 3) & ~(int64_t)3;
+    const bool use_dirty = ctx->opt.bfs_delta && g->f_split.p && ctx->opt.bfs_down_skip;
+    uint32_t *dirty_x = nullptr, *dirty_y = nullptr;
+    if (use_dirty) {
+        VGA_TRY(ctx->ws.get("bfs_dirty", sizeof(uint32_t) * (size_t)chunk * dirty_stride, (void **)&dirty_x));
+        VGA_CUDA(cudaMemsetAsync(dirty_x, 0, sizeof(uint32_t) * (size_t)chunk * dirty_stride, st));
+        if (g->has_y) {
+            VGA_TRY(ctx->ws.get("bfs_dirty_y", sizeof(uint32_t) * (size_t)chunk * dirty_stride, (void **)&dirty_y));
+            VGA_CUDA(cudaMemsetAsync(dirty_y, 0, sizeof(uint32_t) * (size_t)chunk * dirty_stride, st));
+        }
+    }
     VGA_TRY(valid.alloc((size_t)chunk * W));
     VGA_TRY(stats.alloc((size_t)chunk * NSTAT));
     VGA_TRY(work.alloc_zero(4, st));
@@ -1306,6 +1613,7 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources,
     d.n = n;
     d.f_ptr = g->f_nodeptr.p;
     d.f_nodes = g->f_nodes.p;
+    d.f_split = (ctx->opt.bfs_delta && g->f_split.p) ? g->f_split.p : nullptr;
     d.t_ptr = bfs_mode != 0 ? g->t_nodeptr.p : nullptr;
     d.t_nodes = bfs_mode != 0 ? g->t_nodes.p : nullptr;
     d.rowptr = !g->runs_only ? g->rowptr.p : nullptr;
@@ -1321,6 +1629,9 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources,
     d.f_isy = g->has_y ? g->f_isy.p : nullptr;
     d.t_isy = (g->has_y && bfs_mode != 0) ? g->t_isy.p : nullptr;
     d.pyr_total = pl.total;
+    d.dirty = dirty_x;
+    d.dirty_y = dirty_y;
+    d.dirty_stride = dirty_stride;
     d.valid = valid.p;
     d.active = active.p;
     d.mode = mode.p;
@@ -1514,8 +1825,9 @@ int transpose_runs(vga_ctx *ctx, int64_t n, const DevBuf<uint64_t> &runptr, cons
 }
 
 // node-id lists from runs: per-run node counts -> exclusive scan -> ids written at the run's offset
+// cover: flag the nodes whose cells the previous row holds as well (k_emit_nodes)
 int build_nodes(vga_ctx *ctx, int64_t n, const DevBuf<uint64_t> &runptr, const DevBuf<uint2> &runs, int64_t nruns,
-                DevBuf<uint64_t> &nodeptr, DevBuf<uint32_t> &nodes, int64_t *nnodes, const uint32_t *leaf = nullptr) {
+                DevBuf<uint64_t> &nodeptr, DevBuf<uint32_t> &nodes, int64_t *nnodes, const uint32_t *leaf = nullptr, bool cover = false) {
     cudaStream_t st = ctx->stream;
     const PyrLayout pl = pyr_layout(n);
     BfsDev d0;
@@ -1540,7 +1852,7 @@ int build_nodes(vga_ctx *ctx, int64_t n, const DevBuf<uint64_t> &runptr, const D
     *nnodes = (int64_t)total;
     VGA_TRY(nodes.alloc((size_t)total + 1));
     if (nruns > 0) {
-        k_emit_nodes<<<blocks_for(nruns, 256), 256, 0, st>>>(runs.p, nruns, off.p, (uint32_t)n, d0, leaf, nodes.p);
+        k_emit_nodes<<<blocks_for(n * 32, 256), 256, 0, st>>>(n, runptr.p, runs.p, off.p, (uint32_t)n, d0, leaf, cover ? 1 : 0, nodes.p);
         ctx->timing.launches++;
     }
     k_row_node_offsets<<<blocks_for(n + 1, 256), 256, 0, st>>>(n, runptr.p, off.p, nodeptr.p);
@@ -1616,7 +1928,7 @@ int build_yruns(vga_ctx *ctx, vga_graph *g, DevBuf<uint64_t> &yptr, DevBuf<uint2
 // ymap ? ymap[row] : row)
 int choose_lists(vga_ctx *ctx, int64_t n, const DevBuf<uint64_t> &xptr, const DevBuf<uint32_t> &xnodes, const DevBuf<uint64_t> &yptr,
                  const DevBuf<uint32_t> &ynodes, const uint32_t *ymap, DevBuf<uint64_t> &optr, DevBuf<uint32_t> &onodes,
-                 DevBuf<uint8_t> &isy, int64_t *nnodes) {
+                 DevBuf<uint8_t> &isy, int64_t *nnodes, uint32_t *split = nullptr) {
     cudaStream_t st = ctx->stream;
     DevBuf<u64> size;
     VGA_TRY(size.alloc_zero((size_t)n + 1, st));
@@ -1630,7 +1942,19 @@ int choose_lists(vga_ctx *ctx, int64_t n, const DevBuf<uint64_t> &xptr, const De
     VGA_CUDA(cudaStreamSynchronize(st));
     *nnodes = (int64_t)total;
     VGA_TRY(onodes.alloc((size_t)total + 1));
-    k_copy_chosen<<<blocks_for(n * 32, 256), 256, 0, st>>>(n, xptr.p, xnodes.p, yptr.p, ynodes.p, ymap, isy.p, optr.p, onodes.p);
+    k_copy_chosen<<<blocks_for(n * 32, 256), 256, 0, st>>>(n, xptr.p, xnodes.p, yptr.p, ynodes.p, ymap, isy.p, optr.p, onodes.p, split);
+    ctx->timing.launches++;
+    VGA_CUDA(cudaStreamSynchronize(st));
+    VGA_CUDA(cudaGetLastError());
+    return VGA_OK;
+}
+
+// one kind of list only: the flagged nodes of every row moved behind the others (k_copy_chosen), split[v] = new nodes
+int partition_lists(vga_ctx *ctx, int64_t n, const DevBuf<uint64_t> &ptr, const DevBuf<uint32_t> &nodes, int64_t nnodes,
+                    DevBuf<uint32_t> &onodes, uint32_t *split) {
+    cudaStream_t st = ctx->stream;
+    VGA_TRY(onodes.alloc((size_t)nnodes + 1));
+    k_copy_chosen<<<blocks_for(n * 32, 256), 256, 0, st>>>(n, ptr.p, nodes.p, nullptr, nullptr, nullptr, nullptr, ptr.p, onodes.p, split);
     ctx->timing.launches++;
     VGA_CUDA(cudaStreamSynchronize(st));
     VGA_CUDA(cudaGetLastError());
@@ -1698,17 +2022,22 @@ int ensure_bfs_lists(vga_ctx *ctx, vga_graph *g, bool transposed) {
     const bool hybrid = want_y && n > 1 && (int64_t)g->h_refs.size() >= n &&
                         sizeof(uint32_t) * ((size_t)((n + 31) >> 5) + 1 + 35 + 2048) <= ctx->smem_optin;
     if (!g->has_f_nodes) {
+        // out-rows: the nodes whose cells the previous row holds too go to the back of the list (f_split = the others)
+        VGA_TRY(g->f_split.alloc((size_t)n + 1));
         if (!hybrid) {
-            VGA_TRY(build_nodes(ctx, n, g->f_runptr, g->f_runs, g->f_nruns, g->f_nodeptr, g->f_nodes, &g->f_nnodes));
+            DevBuf<uint32_t> xnodes;
+            VGA_TRY(build_nodes(ctx, n, g->f_runptr, g->f_runs, g->f_nruns, g->f_nodeptr, xnodes, &g->f_nnodes, nullptr, true));
+            VGA_TRY(partition_lists(ctx, n, g->f_nodeptr, xnodes, g->f_nnodes, g->f_nodes, g->f_split.p));
         } else {
             DevBuf<uint64_t> xptr, yptr;
             DevBuf<uint32_t> xnodes, ynodes;
             int64_t nx = 0, ny = 0;
-            VGA_TRY(build_nodes(ctx, n, g->f_runptr, g->f_runs, g->f_nruns, xptr, xnodes, &nx));
+            VGA_TRY(build_nodes(ctx, n, g->f_runptr, g->f_runs, g->f_nruns, xptr, xnodes, &nx, nullptr, true));
             VGA_TRY(ensure_perm(ctx, g));
             VGA_TRY(build_yruns(ctx, g, g->fy_runptr, g->fy_runs, &g->fy_nruns));
-            VGA_TRY(build_nodes(ctx, n, g->fy_runptr, g->fy_runs, g->fy_nruns, yptr, ynodes, &ny, g->perm_x.p));
-            VGA_TRY(choose_lists(ctx, n, xptr, xnodes, yptr, ynodes, nullptr, g->f_nodeptr, g->f_nodes, g->f_isy, &g->f_nnodes));
+            VGA_TRY(build_nodes(ctx, n, g->fy_runptr, g->fy_runs, g->fy_nruns, yptr, ynodes, &ny, g->perm_x.p, true));
+            VGA_TRY(choose_lists(ctx, n, xptr, xnodes, yptr, ynodes, nullptr, g->f_nodeptr, g->f_nodes, g->f_isy, &g->f_nnodes,
+                                 g->f_split.p));
             g->has_y = true;
         }
         g->has_f_nodes = true;

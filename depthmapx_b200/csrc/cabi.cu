@@ -34,6 +34,10 @@ static int set_option(Options &o, const std::string &key, int64_t value) {
     else if (key == "bfs_hybrid") o.bfs_hybrid = value;
     else if (key == "metric_slots") o.metric_slots = value;
     else if (key == "bfs_push_unroll") o.bfs_push_unroll = value;
+    else if (key == "bfs_delta") o.bfs_delta = value;
+    else if (key == "bfs_down_skip") o.bfs_down_skip = value;
+    else if (key == "bfs_delta_unroll") o.bfs_delta_unroll = value;
+    else if (key == "bfs_delta_weight") o.bfs_delta_weight = value;
     else if (key == "local_mode") o.local_mode = value;
     else if (key == "local_span") o.local_span = value;
     else if (key == "sieve_mode") o.sieve_mode = value;

@@ -78,6 +78,46 @@ template <typename Visit> VGA_HD int pyr_decompose(uint32_t a, uint32_t len, Vis
     return nodes;
 }
 
+// W consecutive words of a node: 16-byte accesses in device code (nodes are 8 * W bytes apart and 16-byte aligned for W >= 2),
+// plain words on the host (unit tests, emulation)
+template <int W> VGA_HD void pyr_ld(const unsigned long long *p, unsigned long long (&o)[W]) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (W >= 2) {
+#pragma unroll
+        for (int j = 0; j < W; j += 2) {
+            const ulonglong2 t = *reinterpret_cast<const ulonglong2 *>(p + j);
+            o[j] = t.x;
+            o[j + 1] = t.y;
+        }
+        return;
+    }
+#endif
+#pragma unroll
+    for (int j = 0; j < W; j++) o[j] = p[j];
+}
+template <int W> VGA_HD void pyr_st(unsigned long long *p, const unsigned long long (&o)[W]) {
+#if defined(__CUDA_ARCH__)
+    if constexpr (W >= 2) {
+#pragma unroll
+        for (int j = 0; j < W; j += 2) {
+            ulonglong2 t;
+            t.x = o[j];
+            t.y = o[j + 1];
+            *reinterpret_cast<ulonglong2 *>(p + j) = t;
+        }
+        return;
+    }
+#endif
+#pragma unroll
+    for (int j = 0; j < W; j++) p[j] = o[j];
+}
+template <int W> VGA_HD bool pyr_any(const unsigned long long (&o)[W]) {
+    unsigned long long a = 0ULL;
+#pragma unroll
+    for (int j = 0; j < W; j++) a |= o[j];
+    return a != 0ULL;
+}
+
 // Builds three pyramid levels at once: work item t ORs the aligned group of 8 nodes [8t, 8t+8) of level k (src, cnt0
 // nodes of W words each) into 4 nodes of level k+1, 2 of level k+2 and 1 of level k+3 (d1/d2/d3 with cnt1/cnt2/cnt3
 // nodes; a count of 0 = that level does not exist).  Work items: ceil(cnt0 / 8).
@@ -92,30 +132,29 @@ VGA_HD void pyr_build_group(const unsigned long long *src, int64_t cnt0, unsigne
     for (int i = 0; i < 8; i++) {
         const int64_t idx = 8 * t + i;
         const int64_t at = (leaf && idx < cnt0) ? (int64_t)leaf[idx] : idx;
+        if (idx < cnt0) {
+            pyr_ld<W>(src + at * W, a[i]);
+        } else {
 #pragma unroll
-        for (int j = 0; j < W; j++) a[i][j] = idx < cnt0 ? src[at * W + j] : 0ULL;
+            for (int j = 0; j < W; j++) a[i][j] = 0ULL;
+        }
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
 #pragma unroll
         for (int j = 0; j < W; j++) a[i][j] = a[2 * i][j] | a[2 * i + 1][j];
-        if (4 * t + i < cnt1) {
-#pragma unroll
-            for (int j = 0; j < W; j++) d1[(4 * t + i) * W + j] = a[i][j];
-        }
+        if (4 * t + i < cnt1) pyr_st<W>(d1 + (4 * t + i) * W, a[i]);
     }
 #pragma unroll
     for (int i = 0; i < 2; i++) {
 #pragma unroll
         for (int j = 0; j < W; j++) a[i][j] = a[2 * i][j] | a[2 * i + 1][j];
-        if (2 * t + i < cnt2) {
-#pragma unroll
-            for (int j = 0; j < W; j++) d2[(2 * t + i) * W + j] = a[i][j];
-        }
+        if (2 * t + i < cnt2) pyr_st<W>(d2 + (2 * t + i) * W, a[i]);
     }
     if (t < cnt3) {
 #pragma unroll
-        for (int j = 0; j < W; j++) d3[t * W + j] = a[0][j] | a[1][j];
+        for (int j = 0; j < W; j++) a[0][j] |= a[1][j];
+        pyr_st<W>(d3 + t * W, a[0]);
     }
 }
 
@@ -123,51 +162,56 @@ VGA_HD void pyr_build_group(const unsigned long long *src, int64_t cnt0, unsigne
 // pyr_decompose(a, len), and a down pass then pushes every node's word to the leaves it covers.  Work item t takes the
 // word of node t of level k+3 (already complete: the pass runs from the top), ORs in the nodes of levels k+2 and k+1
 // below it and adds the result to the 8 nodes [8t, 8t+8) of level k (dst); the nodes it read are cleared for the next
-// round.  Same grouping as pyr_build_group; a count of 0 = that level does not exist.
+// round.  Same grouping as pyr_build_group; a count of 0 = that level does not exist.  Returns the mask of level-k nodes written.
 template <int W>
-VGA_HD void pyr_down_group(unsigned long long *dst, int64_t cnt0, unsigned long long *s1, int64_t cnt1, unsigned long long *s2,
-                           int64_t cnt2, unsigned long long *s3, int64_t cnt3, int64_t t, const uint32_t *leaf = nullptr) {
-    unsigned long long a3[W], a2[2][W], a1[4][W];
+VGA_HD unsigned pyr_down_group(unsigned long long *dst, int64_t cnt0, unsigned long long *s1, int64_t cnt1, unsigned long long *s2,
+                               int64_t cnt2, unsigned long long *s3, int64_t cnt3, int64_t t, const uint32_t *leaf = nullptr) {
+    unsigned long long a3[W], a2[2][W], a1[4][W], zero[W];
 #pragma unroll
-    for (int j = 0; j < W; j++) {
-        a3[j] = 0ULL;
-        if (t < cnt3) {
-            a3[j] = s3[t * W + j];
-            if (a3[j]) s3[t * W + j] = 0ULL;
+    for (int j = 0; j < W; j++) a3[j] = zero[j] = 0ULL;
+    if (t < cnt3) {
+        pyr_ld<W>(s3 + t * W, a3);
+        if (pyr_any<W>(a3)) pyr_st<W>(s3 + t * W, zero);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+#pragma unroll
+        for (int j = 0; j < W; j++) a2[i][j] = a3[j];
+        if (2 * t + i < cnt2) {
+            unsigned long long v[W];
+            pyr_ld<W>(s2 + (2 * t + i) * W, v);
+            if (pyr_any<W>(v)) pyr_st<W>(s2 + (2 * t + i) * W, zero);
+#pragma unroll
+            for (int j = 0; j < W; j++) a2[i][j] |= v[j];
         }
     }
 #pragma unroll
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < 4; i++) {
 #pragma unroll
-        for (int j = 0; j < W; j++) {
-            a2[i][j] = a3[j];
-            if (2 * t + i < cnt2) {
-                const unsigned long long v = s2[(2 * t + i) * W + j];
-                if (v) s2[(2 * t + i) * W + j] = 0ULL;
-                a2[i][j] |= v;
-            }
+        for (int j = 0; j < W; j++) a1[i][j] = a2[i >> 1][j];
+        if (4 * t + i < cnt1) {
+            unsigned long long v[W];
+            pyr_ld<W>(s1 + (4 * t + i) * W, v);
+            if (pyr_any<W>(v)) pyr_st<W>(s1 + (4 * t + i) * W, zero);
+#pragma unroll
+            for (int j = 0; j < W; j++) a1[i][j] |= v[j];
         }
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < W; j++) {
-            a1[i][j] = a2[i >> 1][j];
-            if (4 * t + i < cnt1) {
-                const unsigned long long v = s1[(4 * t + i) * W + j];
-                if (v) s1[(4 * t + i) * W + j] = 0ULL;
-                a1[i][j] |= v;
-            }
-        }
+    }
+    unsigned written = 0u;  // bit i: node 8t+i of level k received something
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const int64_t idx = 8 * t + i;
-        if (idx < cnt0) {
+        if (idx < cnt0 && pyr_any<W>(a1[i >> 1])) {
             const int64_t at = leaf ? (int64_t)leaf[idx] : idx;
+            unsigned long long cur[W];
+            pyr_ld<W>(dst + at * W, cur);
 #pragma unroll
-            for (int j = 0; j < W; j++)
-                if (a1[i >> 1][j]) dst[at * W + j] |= a1[i >> 1][j];
+            for (int j = 0; j < W; j++) cur[j] |= a1[i >> 1][j];
+            pyr_st<W>(dst + at * W, cur);
+            written |= 1u << i;
         }
     }
+    return written;
 }
 
 // number of pyramid loads a query of [a, a+len) costs (the pull step's work estimate)

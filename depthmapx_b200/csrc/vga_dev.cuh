@@ -272,6 +272,15 @@ struct Options {
     int64_t metric_slots = 0;    // metric / angular VGA: sources (warps) in flight, 0 = resident warps bounded by memory
     int64_t bfs_pull_unroll = 4; // node loads per lane between two early-exit checks of the bottom-up step: 4 (measured on the
                                  // C5 bench subset: level kernels 1483 -> 1439 ms) or 2
+    int64_t bfs_delta = 1;       // top-down step: a vertex leaves the nodes that row u-1 covers as well to vertex u-1 for the source
+                                 // bits both push (k_push_delta; 93 % of the out-row nodes of an urban plan); 0 = every vertex
+                                 // pushes its whole row (k_push_nodes[_coop])
+    int64_t bfs_delta_unroll = 1; // k_push_delta: nodes per lane in flight (1, 2 or 4; measured on the C5 bench subset: level kernels 859 / 897 / 932 ms)
+    int64_t bfs_delta_weight = 6; // direction rule with k_push_delta: one visited node counts as this many offered in-row nodes
+                                 // (measured per level on a C5 slice: ~20 ps per top-down visit, 1.6-5.7 ps per node offered to
+                                 // the bottom-up step; any weight from 4 to 12 picks the faster direction at every level there)
+    int64_t bfs_down_skip = 1;   // with k_push_delta: the last down launch visits only the groups of 8 vertices below a node of levels
+                                 // 1-3 that received bits (dirty bitmap); 0 = every group
     int64_t bfs_wide_nodes = 384; // auto word width with bfs_coop = 0: 4 words from this many pyramid nodes per out-row, else 2
 };
 
@@ -340,6 +349,9 @@ struct vga_graph {
     bool has_shard_runs = false;                 // f_runs hold the rows [src_begin, src_end) of a shard only
     vga::DevBuf<uint64_t> f_nodeptr, t_nodeptr;  // [n+1]
     vga::DevBuf<uint32_t> f_nodes, t_nodes;
+    // out-rows: the first f_split[u] nodes of row u are "new", the others cover only cells that row u-1 holds as well (the
+    // top-down step leaves those to vertex u-1 when it pushes a superset of u's source bits, bfs.cu k_push_delta)
+    vga::DevBuf<uint32_t> f_split;               // [n]
     bool has_f_nodes = false, has_t_nodes = false;
     // y-major alternative (bfs.cu): perm_y[v] = rank of cell v in y-major order, perm_x = its inverse; f_isy / t_isy[v] = 1
     // when the list of row v is the y-major one (inner node ids then refer to the pyramid over the y-major order; leaf ids

@@ -140,6 +140,35 @@ def test_hybrid_x_or_y_major_lists_vs_oracle(name, mode, words):
 
 
 @pytest.mark.parametrize("name", ["oblique:30:30:7", "office:64:64:1", "urban:120:120:4", "room:24:24:1+holes"])
+@pytest.mark.parametrize("mode,words,unroll,hyb", [(0, 1, 4, 0), (0, 2, 2, 2), (2, 4, 4, 2), (0, 4, 1, 2), (0, 8, 2, 0), (2, 0, 4, 1),
+                                                   (1, 4, 2, 2), (1, 1, 1, 0), (2, 8, 1, 2)])
+def test_delta_push_vs_full_push_and_oracle(name, mode, words, unroll, hyb):
+    """bfs_delta = 1 (default): out-rows stored as [new nodes | nodes whose cells row u-1 holds as well]; a vertex pushes
+    its whole vector only to the new nodes and F[u] & ~F[u-1] to the others (k_push_delta).  Same integers as every vertex
+    pushing its whole row (bfs_delta = 0, k_push_nodes[_coop]) and as the oracle; top-down only pins it at every level."""
+    flat, og = oracle_for(name)
+    for radius in (-1, 2):
+        res = {}
+        for delta in (0, 1):
+            c = capi.Context(0)
+            for k, v in (("bfs_delta", delta), ("bfs_mode", mode), ("bfs_words", words),
+                         ("bfs_push_unroll", unroll), ("bfs_delta_unroll", unroll), ("bfs_hybrid", hyb)):
+                c.set_option(k, v)
+            g = c.build(flat)
+            res[delta] = g.global_ints(radius)
+            c.close()
+        for a, b in zip(res[0][:3], res[1][:3]):
+            assert np.array_equal(a, b)
+        tn, td, dist, _ = res[1]
+        rng = np.random.RandomState(13)
+        for s in rng.choice(len(tn), min(len(tn), 24), replace=False):
+            otn, otd, odist, onl = og.global_ints(radius, (int(s), int(s) + 1), maxl=64)
+            L = dist.shape[1]
+            assert otn[0] == tn[s] and otd[0] == td[s]
+            assert np.array_equal(odist[0, :L], dist[s]) and not odist[0, L:].any()
+
+
+@pytest.mark.parametrize("name", ["oblique:30:30:7", "office:64:64:1", "urban:120:120:4", "room:24:24:1+holes"])
 def test_row_ordering_kernels_vs_oracle(name):
     """build_sort = 1 (default): rows ordered by bitmap rank in shared memory (k_rank_sort); build_sort = 0: CUB segmented
     radix sort.  The sorted adjacency incl. bins, accepted flags and ghost columns must equal the oracle's and each other."""

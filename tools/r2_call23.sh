@@ -1,0 +1,33 @@
+#!/bin/bash
+# GPU call 23 of round 2 (1 GPU): 16-byte accesses in the pyramid passes + dirty-group skipping in the last down launch:
+# parity on hardware, per-level times on the C5 slice (skipping on / off), C5 bench subset.
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_gpu_bfs_schedules.py -m gpu -x -q -p no:cacheprovider > gpurun_out/r2c23_pytest.log 2>&1
+echo "pytest rc=$?"; tail -3 gpurun_out/r2c23_pytest.log
+export VGA_TIME_SRC=16384 VGA_TIME_RADII=-1 VGA_TIME_REPS=1 VGA_LEVEL_TIMING=1
+run() {
+  T=$1; shift
+  timeout 300 python tools/gpu_time.py C5 global bfs_hybrid=2 "$@" > gpurun_out/r2c23_$T.log 2>&1
+  echo "== $T rc=$? $*"; grep -E "^\[level|^global" gpurun_out/r2c23_$T.log | cut -c1-150
+}
+run lt_hybrid
+run lt_hybrid_noskip bfs_down_skip=0
+unset VGA_TIME_SRC VGA_TIME_RADII VGA_TIME_REPS VGA_LEVEL_TIMING
+ab() {
+  T=$1; shift
+  timeout 400 python bench.py --no-e2e --no-cpu-baseline --steps 2 --warmup 3 "$@" > gpurun_out/r2c23_$T.json 2> gpurun_out/r2c23_$T.err
+  echo "== $T rc=$? $*"
+  python - <<PY
+import json
+try:
+    j = json.load(open("gpurun_out/r2c23_$T.json"))
+    s = j["stages"]
+    print("   value %.0f cells/s  build %.0f  lists %.0f  bfs %.0f  level kernels %.0f  local %.0f  checksum %s" % (
+        j["value"], s["makegraph_ms"], s["bfs_row_lists_ms"], s["global_bfs_ms"], s["bfs_level_kernels_ms"], s["local_ms"],
+        j["result_checksum"]["sum_depth"]))
+except Exception as e:
+    print("   no line:", e)
+PY
+}
+ab default
+ab C2 --workload C2
