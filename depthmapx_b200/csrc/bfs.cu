@@ -73,11 +73,6 @@ struct BfsDev {
     u64 *pyr_y, *npyr_y;
     const uint32_t *perm_x;
     const uint8_t *f_isy, *t_isy;    // [n] 1 = the row's list is the y-major one
-    // [batches][dirty_stride] one bit per group of 8 vertices (= per work item of the last down launch): some node of pyramid
-    // levels 1-3 above the group holds bits (set by k_push_delta and by the down launch that fills level 3, consumed and
-    // cleared by the last down launch, which skips the clear groups); nullptr = every group is visited
-    uint32_t *dirty, *dirty_y;
-    int64_t dirty_stride;
     int64_t pyr_total;               // inner nodes per batch
     const u64 *valid;                // [batches*W] valid source bits of each word
     int *active;                     // [batches] 1 while the batch goes on
@@ -231,27 +226,9 @@ template <int W> __global__ void __launch_bounds__(TPB, W <= 4 ? 4 : 1) k_pyr_do
     const int64_t c0 = d.pyr_cnt[k];
     const int64_t c1 = s1 ? d.pyr_cnt[k + 1] : 0, c2 = s2 ? d.pyr_cnt[k + 2] : 0, c3 = s3 ? d.pyr_cnt[k + 3] : 0;
     const int64_t groups = (c0 + 7) / 8;
-    uint32_t *dirty = (ymaj ? d.dirty_y : d.dirty);
-    if (dirty) dirty += (int64_t)b * d.dirty_stride;
-    const int lane = threadIdx.x & 31;
-    // warp-uniform loop: 32 consecutive groups per warp and round = one word of the dirty bitmap
-    for (int64_t tb = (int64_t)blockIdx.x * TPB + (threadIdx.x & ~31); tb < groups; tb += (int64_t)gridDim.x * TPB) {
-        const int64_t t = tb + lane;
-        if (k == 0 && dirty) {
-            const uint32_t word = dirty[tb >> 5];
-            if (word == 0u) continue;
-            if (t < groups && ((word >> lane) & 1u)) {
-                VGA_COUNT(pyr_down_groups, 1);
-                pyr_down_group<W>(dst, c0, s1, c1, s2, c2, s3, c3, t, leaf);
-            }
-            __syncwarp();
-            if (lane == 0) dirty[tb >> 5] = 0u;
-        } else if (t < groups) {
-            VGA_COUNT(pyr_down_groups, 1);
-            const unsigned written = pyr_down_group<W>(dst, c0, s1, c1, s2, c2, s3, c3, t, leaf);
-            // level-3 nodes 8t .. 8t+7 feed the work items 8t .. 8t+7 of the last launch: byte t of the bitmap, owned by this thread
-            if (k == 3 && dirty && written) reinterpret_cast<uint8_t *>(dirty)[t] |= (uint8_t)written;
-        }
+    for (int64_t t = (int64_t)blockIdx.x * TPB + threadIdx.x; t < groups; t += (int64_t)gridDim.x * TPB) {
+        VGA_COUNT(pyr_down_groups, 1);
+        pyr_down_group<W>(dst, c0, s1, c1, s2, c2, s3, c3, t, leaf);
     }
 }
 
@@ -542,25 +519,12 @@ template <int W, int PU> __global__ void __launch_bounds__(TPB) k_push_delta(Bfs
 #pragma unroll
                         for (int j = 0; j < LW; j++) fv.w[j] &= ~pf.w[j];
                     }
-                    bool added = false;
 #pragma unroll
                     for (int j = 0; j < LW; j++) {
                         const u64 a = fv.w[j] & ~cur[i].w[j];
                         if (a) {
                             atomicOr(&p[i][j], a);
-                            added = true;
                             VGA_COUNT(npush_atomics, 1);
-                        }
-                    }
-                    // an inner node of levels 1-3 received bits: the last down launch must visit the 8 vertices below it
-                    if (added && c[i] >= n && d.dirty) {
-                        const int64_t x = (int64_t)(c[i] - n);
-                        if (x < d.pyr_off[4]) {
-                            const int L = x < d.pyr_off[2] ? 1 : (x < d.pyr_off[3] ? 2 : 3);
-                            const int64_t t = (x - d.pyr_off[L]) >> (3 - L);
-                            uint32_t *dw = (s_isy[wid][seg[i] >> 1] ? d.dirty_y : d.dirty) + (int64_t)b * d.dirty_stride + (t >> 5);
-                            const uint32_t bit = 1u << (t & 31);
-                            if (!(*dw & bit)) atomicOr(dw, bit);
                         }
                     }
                 }
@@ -1589,18 +1553,6 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources,
         VGA_TRY(ctx->ws.get("bfs_npyr_y", sizeof(u64) * (size_t)chunk * (size_t)std::max<int64_t>(pl.total, 1) * W, (void **)&npyr_y));
         VGA_CUDA(cudaMemsetAsync(npyr_y, 0, sizeof(u64) * (size_t)chunk * (size_t)std::max<int64_t>(pl.total, 1) * W, st));
     }
-    // dirty-group bitmaps of the down pass (only k_push_delta maintains them)
-    const int64_t dirty_stride = (((n + 7) / 8 + 31) / 32 + 3) & ~(int64_t)3;
-    const bool use_dirty = ctx->opt.bfs_delta && g->f_split.p && ctx->opt.bfs_down_skip;
-    uint32_t *dirty_x = nullptr, *dirty_y = nullptr;
-    if (use_dirty) {
-        VGA_TRY(ctx->ws.get("bfs_dirty", sizeof(uint32_t) * (size_t)chunk * dirty_stride, (void **)&dirty_x));
-        VGA_CUDA(cudaMemsetAsync(dirty_x, 0, sizeof(uint32_t) * (size_t)chunk * dirty_stride, st));
-        if (g->has_y) {
-            VGA_TRY(ctx->ws.get("bfs_dirty_y", sizeof(uint32_t) * (size_t)chunk * dirty_stride, (void **)&dirty_y));
-            VGA_CUDA(cudaMemsetAsync(dirty_y, 0, sizeof(uint32_t) * (size_t)chunk * dirty_stride, st));
-        }
-    }
     VGA_TRY(valid.alloc((size_t)chunk * W));
     VGA_TRY(stats.alloc((size_t)chunk * NSTAT));
     VGA_TRY(work.alloc_zero(4, st));
@@ -1629,9 +1581,6 @@ int run_global_w(vga_ctx *ctx, vga_graph *g, int radius, const int64_t *sources,
     d.f_isy = g->has_y ? g->f_isy.p : nullptr;
     d.t_isy = (g->has_y && bfs_mode != 0) ? g->t_isy.p : nullptr;
     d.pyr_total = pl.total;
-    d.dirty = dirty_x;
-    d.dirty_y = dirty_y;
-    d.dirty_stride = dirty_stride;
     d.valid = valid.p;
     d.active = active.p;
     d.mode = mode.p;

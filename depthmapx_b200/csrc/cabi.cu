@@ -35,13 +35,13 @@ static int set_option(Options &o, const std::string &key, int64_t value) {
     else if (key == "metric_slots") o.metric_slots = value;
     else if (key == "bfs_push_unroll") o.bfs_push_unroll = value;
     else if (key == "bfs_delta") o.bfs_delta = value;
-    else if (key == "bfs_down_skip") o.bfs_down_skip = value;
     else if (key == "bfs_delta_unroll") o.bfs_delta_unroll = value;
     else if (key == "bfs_delta_weight") o.bfs_delta_weight = value;
     else if (key == "local_mode") o.local_mode = value;
     else if (key == "local_span") o.local_span = value;
     else if (key == "sieve_mode") o.sieve_mode = value;
     else if (key == "sieve_thread_cap") o.sieve_thread_cap = value;
+    else if (key == "sieve_sort_emit") o.sieve_sort_emit = value;
     else if (key == "sieve_gcap") o.sieve_gcap = value;
     else if (key == "sieve_bcap") o.sieve_bcap = value;
     else if (key == "sieve_big_gcap") o.sieve_big_gcap = value;

@@ -622,6 +622,7 @@ struct SieveArgs {
     uint64_t chunk_base;      // subtracted from row_off
     uint32_t *e_ref;
     uint8_t *e_bin;
+    const uint32_t *order;    // thread kernel, emit pass: thread t runs task slot order[t] (tasks sorted by size), or nullptr
 };
 
 template <bool EMIT> __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) k_sieve(SieveArgs a) {
@@ -702,8 +703,9 @@ constexpr int TT = 128;  // threads per CTA
 template <bool EMIT, int TG, int TB> __global__ void __launch_bounds__(TT) k_sieve_thread(SieveArgs a, int64_t nsrc) {
     __shared__ Zone s_gaps[TG * TT];
     const int tid = threadIdx.x;
-    const int64_t t = (int64_t)blockIdx.x * TT + tid;
+    int64_t t = (int64_t)blockIdx.x * TT + tid;
     if (t >= a.ntasks) return;
+    if (EMIT && a.order) t = a.order[t];
     const int q = (int)(t / nsrc);
     const int64_t src_local = t % nsrc;
     const int64_t task = src_local * 8 + q;
@@ -943,6 +945,19 @@ template <bool EMIT, int TG, int TB> __global__ void __launch_bounds__(TT) k_sie
         a.cnt[src_local * 8 + q] = nacc;
         if (q < 4) a.fillcnt[src_local * 4 + q] = nfill;
     }
+}
+
+// Emit pass of the thread kernel: the 32 tasks of a warp are 32 consecutive sources looking into the same octant, and their
+// sizes differ (a warp is as slow as its largest task: lane efficiency 0.56 by accepted cells on an urban plan, measured with
+// the oracle's rows).  The counts of pass 1 are known, so the emit pass runs the tasks in order of decreasing size: key =
+// complement of the accepted cells / 16 (ties keep their spatial order: the radix sort is stable), value = thread slot.
+__global__ void k_task_keys(const uint32_t *cnt, int64_t nsrc, uint32_t *key, uint32_t *val) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nsrc * 8) return;
+    const int q = (int)(t / nsrc);
+    const int64_t s = t % nsrc;
+    key[t] = 0x0fffffffu - min(cnt[s * 8 + q] >> 4, 0x0fffffffu);
+    val[t] = (uint32_t)t;
 }
 
 // per-source row sizes -> totals (accepted + fill-ins)
@@ -1197,6 +1212,7 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t sr
     a.chunk_base = 0;
     a.e_ref = nullptr;
     a.e_bin = nullptr;
+    a.order = nullptr;
 
     // big-capacity scratch (allocated on demand)
     WsBuf<unsigned char> big_scratch(ctx->ws, "mk_bigscratch");
@@ -1295,6 +1311,15 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t sr
     WsBuf<uint8_t> e_bin(ctx->ws, "mk_ebin");
     WsBuf<uint64_t> seg_off(ctx->ws, "mk_segoff");
     WsBuf<unsigned char> sort_tmp(ctx->ws, "mk_sorttmp");
+    WsBuf<uint32_t> tk_in(ctx->ws, "mk_tkin"), tk_out(ctx->ws, "mk_tkout"), tv_in(ctx->ws, "mk_tvin"), tv_out(ctx->ws, "mk_tvout");
+    WsBuf<unsigned char> tsort_tmp(ctx->ws, "mk_tsorttmp");
+    const bool sort_tasks = ctx->opt.sieve_mode == 1 && ctx->opt.sieve_sort_emit != 0 && nsrc * 8 < ((int64_t)1 << 31);
+    if (sort_tasks) {
+        VGA_TRY(tk_in.alloc((size_t)nsrc * 8 + 8));
+        VGA_TRY(tk_out.alloc((size_t)nsrc * 8 + 8));
+        VGA_TRY(tv_in.alloc((size_t)nsrc * 8 + 8));
+        VGA_TRY(tv_out.alloc((size_t)nsrc * 8 + 8));
+    }
     VGA_TRY(e_ref.alloc((size_t)max_chunk + 1));
     VGA_TRY(e_bin.alloc((size_t)max_chunk + 1));
     VGA_TRY(keys.alloc((size_t)max_chunk + 1));
@@ -1322,6 +1347,15 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t sr
         e.e_ref = e_ref.p;
         e.e_bin = e_bin.p;
         mt.start();
+        if (sort_tasks && ns * 8 > 32) {
+            k_task_keys<<<blocks_for(ns * 8, 256), 256, 0, st>>>(e.cnt, ns, tk_in.p, tv_in.p);
+            size_t tb = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tb, tk_in.p, tk_out.p, tv_in.p, tv_out.p, (int)(ns * 8), 0, 28, st);
+            VGA_TRY(tsort_tmp.alloc(tb + 16));
+            VGA_CUDA(cub::DeviceRadixSort::SortPairs(tsort_tmp.p, tb, tk_in.p, tk_out.p, tv_in.p, tv_out.p, (int)(ns * 8), 0, 28, st));
+            tm.launches += 3;
+            e.order = tv_out.p;
+        }
         if (ctx->opt.sieve_mode == 1 && thread_cap == 1)
             k_sieve_thread<true, 16, 48><<<blocks_for(ns * 8, TT), TT, 0, st>>>(e, ns);
         else if (ctx->opt.sieve_mode == 1)

@@ -250,6 +250,8 @@ struct Options {
     int64_t sieve_thread_cap = -1; // thread kernel capacity: 0 = 8 gaps / 24 blocks per task, 1 = 16 / 48, -1 = auto (1 from
                                  // 200,000 cells: on the 10^6-cell plan 30 % of the tasks exceed 8 / 24 and fall back to the
                                  // warp kernel, 4.8 % exceed 16 / 48: 1342 -> 1123 ms; small plans lose occupancy: 10.9 -> 13.4 ms)
+    int64_t sieve_sort_emit = 1; // thread kernel, emit pass: tasks in order of decreasing size (counts of pass 1), so that the 32 tasks
+                                 // of a warp are alike; 0 = 32 consecutive sources per warp as in the count pass
     int64_t sieve_gcap = 48;     // shared-memory gap capacity per warp
     int64_t sieve_bcap = 192;    // shared-memory block capacity per warp
     int64_t sieve_big_gcap = 4096;
@@ -279,8 +281,6 @@ struct Options {
     int64_t bfs_delta_weight = 6; // direction rule with k_push_delta: one visited node counts as this many offered in-row nodes
                                  // (measured per level on a C5 slice: ~20 ps per top-down visit, 1.6-5.7 ps per node offered to
                                  // the bottom-up step; any weight from 4 to 12 picks the faster direction at every level there)
-    int64_t bfs_down_skip = 1;   // with k_push_delta: the last down launch visits only the groups of 8 vertices below a node of levels
-                                 // 1-3 that received bits (dirty bitmap); 0 = every group
     int64_t bfs_wide_nodes = 384; // auto word width with bfs_coop = 0: 4 words from this many pyramid nodes per out-row, else 2
 };
 

@@ -554,4 +554,24 @@ struct DeviceSegmentedSort {
         return cudaSuccess;
     }
 };
+struct DeviceRadixSort {
+    // stable ascending sort of (key, value) pairs on the key bits [begin_bit, end_bit)
+    template <typename K, typename V>
+    static cudaError_t SortPairs(void *tmp, size_t &bytes, const K *kin, K *kout, const V *vin, V *vout, int n, int begin_bit = 0,
+                                 int end_bit = (int)sizeof(K) * 8, cudaStream_t = nullptr) {
+        if (!tmp) {
+            bytes = 16;
+            return cudaSuccess;
+        }
+        std::vector<int> idx((size_t)n);
+        for (int i = 0; i < n; i++) idx[(size_t)i] = i;
+        const K mask = end_bit - begin_bit >= (int)sizeof(K) * 8 ? ~K(0) : (K)(((K(1) << (end_bit - begin_bit)) - 1));
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return ((kin[a] >> begin_bit) & mask) < ((kin[b] >> begin_bit) & mask); });
+        for (int i = 0; i < n; i++) {
+            kout[i] = kin[idx[(size_t)i]];
+            vout[i] = vin[idx[(size_t)i]];
+        }
+        return cudaSuccess;
+    }
+};
 }  // namespace cub
