@@ -484,7 +484,7 @@ def main():
                 "note": "vga_graph_build(host vga_grid) + vga_global_sources(host outputs); inputs in "
                         + ("pinned" if pinned_inputs else "pageable") + " host memory"},
         "gpu_launches": int(R["launches"]),
-        "roofline": {"bound": "hbm", "kernel": "BFS level kernels k_push_nodes/k_pyr_down/k_pyr_build/k_pull_nodes/k_update/k_decide",
+        "roofline": {"bound": "hbm", "kernel": "BFS level kernels k_push_delta/k_pyr_down/k_pyr_build/k_pull_nodes_coop/k_update/k_decide",
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "peak_source": peak_src, "traffic": traffic,
                      "byte_model": "rows as pyramid node lists (4 B per node id of the expanding vertices) + frontier / visited / next vectors",

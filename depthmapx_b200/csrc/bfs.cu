@@ -479,6 +479,7 @@ template <int W, int PU> __global__ void __launch_bounds__(TPB) k_push_delta(Bfs
         s_isy[wid][lane] = (d.f_isy && anyf != 0ULL) ? d.f_isy[u] : (uint8_t)0;
         __syncwarp();
         // all segments of the tile as one flat list: short lists keep every lane busy
+        int at = -1;  // segment of this lane's previous element: its elements come in ascending order
         for (uint32_t t0 = 0; t0 < total; t0 += NPI * PU) {
             uint32_t c[PU];
             int seg[PU];
@@ -491,11 +492,21 @@ template <int W, int PU> __global__ void __launch_bounds__(TPB) k_push_delta(Bfs
                 seg[i] = 0;
                 p[i] = nullptr;
                 if (t < total) {
-                    int lo = 0, hi = 64;  // last segment with s_pre <= t (empty segments share their successor's prefix)
-                    while (hi - lo > 1) {
-                        const int m = (lo + hi) >> 1;
-                        if (s_pre[wid][m] <= t) lo = m; else hi = m;
+                    // last segment with s_pre <= t (empty segments share their successor's prefix): binary search for the
+                    // lane's first element, then a walk forward (segments are about as long as the lane's stride)
+                    int lo;
+                    if (at < 0) {
+                        lo = 0;
+                        int hi = 64;
+                        while (hi - lo > 1) {
+                            const int m = (lo + hi) >> 1;
+                            if (s_pre[wid][m] <= t) lo = m; else hi = m;
+                        }
+                    } else {
+                        lo = at;
+                        while (s_pre[wid][lo + 1] <= t) lo++;  // s_pre[64] = total > t
                     }
+                    at = lo;
                     seg[i] = lo;
                     c[i] = __ldcs(d.f_nodes + s_ptr[wid][lo] + (t - s_pre[wid][lo]));
                     p[i] = (c[i] < n ? nx + (int64_t)c[i] * W : (s_isy[wid][lo >> 1] ? npy : np) + (int64_t)(c[i] - n) * W) + LW * g;
