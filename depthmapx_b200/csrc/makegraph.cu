@@ -1046,50 +1046,88 @@ __global__ void k_make_keys(GridDev g, const uint32_t *e_ref, const uint8_t *e_b
 // row instead of four radix passes over small segments.  Needs unique columns per row (the sieve's de-duplication rule
 // guarantees it).  Shared memory: total/32 words + total/1024 group prefixes.
 constexpr int RS_TPB = 256;
+// shared memory of k_rank_sort for a universe of `total` vertices: bitmap words, group prefixes, per-word prefixes (u16), range
+inline size_t rank_sort_smem(uint32_t total) {
+    const size_t nw = ((size_t)total + 31u) >> 5, ng = (nw + 31u) >> 5;
+    return sizeof(uint32_t) * (nw + ng + 4) + sizeof(uint16_t) * ((nw + 1) & ~(size_t)1);
+}
+// One CTA per row: the row's columns set as bits of a bitmap of the whole vertex universe in shared memory; rank(col) = set
+// bits below col = prefix of its group of 32 words + prefix of its word inside the group (u16) + masked popc of the word.
+// The bitmap is zero between rows and only the word range a row touches is counted, scanned and cleared again: a room cell
+// sees a few columns of the plan, i.e. a narrow range of ordinals.
 __global__ void __launch_bounds__(RS_TPB) k_rank_sort(const uint32_t *keys, const uint64_t *seg_off, int64_t nrows, uint32_t total,
                                                       uint32_t *out) {
     extern __shared__ __align__(16) uint32_t rs_smem[];
     const uint32_t nw = (total + 31u) >> 5, ng = (nw + 31u) >> 5;
-    uint32_t *bm = rs_smem, *gpre = rs_smem + nw;
+    uint32_t *bm = rs_smem, *gpre = rs_smem + nw, *range = gpre + ng;
+    uint16_t *wpre = reinterpret_cast<uint16_t *>(range + 4);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = RS_TPB / 32;
+    for (uint32_t w = threadIdx.x; w < nw; w += RS_TPB) bm[w] = 0u;
+    if (threadIdx.x == 0) {
+        range[0] = 0xffffffffu;
+        range[1] = 0u;
+    }
+    __syncthreads();
     for (int64_t row = blockIdx.x; row < nrows; row += gridDim.x) {
         const uint64_t e0 = seg_off[row], e1 = seg_off[row + 1];
-        for (uint32_t w = threadIdx.x; w < nw; w += RS_TPB) bm[w] = 0u;
-        __syncthreads();
+        uint32_t lo = 0xffffffffu, hi = 0u;
         for (uint64_t e = e0 + threadIdx.x; e < e1; e += RS_TPB) {
             const uint32_t col = keys[e] >> 6;
             atomicOr(&bm[col >> 5], 1u << (col & 31u));
+            lo = min(lo, col >> 5);
+            hi = max(hi, col >> 5);
+        }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        if (lane == 0 && lo <= hi) {
+            atomicMin(&range[0], lo);
+            atomicMax(&range[1], hi);
         }
         __syncthreads();
-        for (uint32_t g = warp; g < ng; g += nwarps) {  // popcount of every group of 32 words
-            const uint32_t w = g * 32u + lane;
-            const unsigned c = __reduce_add_sync(0xffffffffu, (unsigned)(w < nw ? __popc(bm[w]) : 0));
-            if (lane == 0) gpre[g] = c;
-        }
-        __syncthreads();
-        if (warp == 0) {  // exclusive scan of the group sums: every lane a contiguous slice, then a warp scan of the slices
-            const uint32_t per = (ng + 31u) >> 5, b0 = lane * per, b1 = min(b0 + per, ng);
-            unsigned mine = 0;
-            for (uint32_t g = b0; g < b1; g++) mine += gpre[g];
-            unsigned incl = mine;
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += up;
+        const uint32_t wlo = range[0], whi = range[1];
+        if (wlo <= whi) {  // block-uniform
+            const uint32_t glo = wlo >> 5, ghi = whi >> 5;
+            for (uint32_t g = glo + warp; g <= ghi; g += nwarps) {  // per word: prefix inside its group; per group: its sum
+                const uint32_t w = g * 32u + lane;
+                const unsigned c = (unsigned)(w < nw ? __popc(bm[w]) : 0);
+                unsigned incl = c;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                if (w < nw) wpre[w] = (uint16_t)(incl - c);
+                if (lane == 31) gpre[g] = incl;
             }
-            unsigned run = incl - mine;
-            for (uint32_t g = b0; g < b1; g++) {
-                const unsigned c = gpre[g];
-                gpre[g] = run;
-                run += c;
+            __syncthreads();
+            if (warp == 0) {  // exclusive scan of the group sums: every lane a contiguous slice, then a warp scan of the slices
+                const uint32_t cnt = ghi - glo + 1u, per = (cnt + 31u) >> 5, b0 = glo + min(lane * per, cnt), b1 = glo + min((lane + 1u) * per, cnt);
+                unsigned mine = 0;
+                for (uint32_t g = b0; g < b1; g++) mine += gpre[g];
+                unsigned incl = mine;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                unsigned run = incl - mine;
+                for (uint32_t g = b0; g < b1; g++) {
+                    const unsigned c = gpre[g];
+                    gpre[g] = run;
+                    run += c;
+                }
             }
-        }
-        __syncthreads();
-        for (uint64_t e = e0 + threadIdx.x; e < e1; e += RS_TPB) {
-            const uint32_t key = keys[e], col = key >> 6, w = col >> 5;
-            unsigned rank = gpre[w >> 5];
-            for (uint32_t k = w & ~31u; k < w; k++) rank += (unsigned)__popc(bm[k]);
-            rank += (unsigned)__popc(bm[w] & ((1u << (col & 31u)) - 1u));
-            out[e0 + rank] = key;
+            __syncthreads();
+            for (uint64_t e = e0 + threadIdx.x; e < e1; e += RS_TPB) {
+                const uint32_t key = keys[e], col = key >> 6, w = col >> 5;
+                const unsigned rank = gpre[w >> 5] + (unsigned)wpre[w] + (unsigned)__popc(bm[w] & ((1u << (col & 31u)) - 1u));
+                out[e0 + rank] = key;
+            }
+            __syncthreads();
+            // leave the bitmap zero for the next row
+            for (uint32_t w = wlo + threadIdx.x; w <= whi; w += RS_TPB) bm[w] = 0u;
+            if (threadIdx.x == 0) {
+                range[0] = 0xffffffffu;
+                range[1] = 0u;
+            }
         }
         __syncthreads();
     }
@@ -1403,10 +1441,10 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t sr
             k_rebase<<<blocks_for(ns + 1, 256), 256, 0, st>>>(row_off.p + i, ns + 1, base, seg_off.p);
             tm.launches++;
             const uint32_t total_v = (uint32_t)dg->cells;  // filled cells + ghosts
-            const size_t rs_bytes = sizeof(uint32_t) * ((size_t)((total_v + 31u) >> 5) + (size_t)((((total_v + 31u) >> 5) + 31u) >> 5) + 4);
+            const size_t rs_bytes = rank_sort_smem(total_v);
             if (ctx->opt.build_sort != 0 && rs_bytes <= ctx->smem_optin) {
                 VGA_CUDA(cudaFuncSetAttribute(k_rank_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_bytes));
-                const unsigned blocks = (unsigned)std::min<int64_t>(ns, (int64_t)ctx->sm_count * 16);
+                const unsigned blocks = (unsigned)std::min<int64_t>(ns, (int64_t)ctx->sm_count * 4);  // one CTA per SM fits; each clears its bitmap once
                 k_rank_sort<<<blocks, RS_TPB, rs_bytes, st>>>(keys.p, seg_off.p, ns, total_v, gr->adj.p + base);
                 tm.launches++;
             } else {

@@ -258,7 +258,7 @@ struct Options {
     int64_t sieve_big_bcap = 32768;
     int64_t build_chunk_entries = (int64_t)1 << 30;
     int64_t build_sort = 1;      // rows ordered by 1: bitmap rank in shared memory (k_rank_sort, own kernel; measured 1.13x-1.4x
-                                 // faster builds); 0: cub segmented radix sort (also the fallback for grids of > 1.8M cells)
+                                 // faster builds); 0: cub segmented radix sort (also the fallback for grids of > 1.2M cells)
     int64_t pull_alpha = 0;      // bottom-up step when (frontier out-nodes + 2n) * alpha > (open vertices' in-nodes + n) * beta;
                                  // 0 = 2 when the graph has x- and y-major lists, else 1
     int64_t pull_beta = 1;
