@@ -970,57 +970,76 @@ __global__ void k_row_totals(const uint32_t *cnt, const uint32_t *fillcnt, int64
     tot[i] = t;
 }
 
-// Connectivity, moments (double running sums in reference order), far distances, bin counts,
-// grid connections: one thread per source walking its unsorted row (pointdata.cpp:1463-1497,
-// 1735-1768).
-__global__ void k_node_stats(GridDev g, int64_t src_begin, int64_t chunk_first, int64_t nsrc_chunk,
-                             const uint64_t *row_off, uint64_t chunk_base, const uint32_t *cnt,
-                             const uint32_t *e_ref, const uint8_t *e_bin, int32_t *connectivity, double *sum_d,
-                             double *sum_d2, float *far_dist, int32_t *bin_count, uint8_t *gridconn) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nsrc_chunk) return;
-    int64_t sl = chunk_first + i;  // source index relative to src_begin
-    int32_t ref = g.cellref[src_begin + sl];
-    int cx = ref >> 16, cy = ref & 0xffff;
-    float far[32];
-    int32_t bc[32];
-#pragma unroll
-    for (int b = 0; b < 32; b++) {
-        far[b] = 0.0f;
-        bc[b] = 0;
-    }
-    uint64_t beg = row_off[sl] - chunk_base, end = row_off[sl + 1] - chunk_base;
+// Connectivity, moments, far distances, bin counts, grid connections of a source from its unsorted row (pointdata.cpp:
+// 1463-1497, 1735-1768).  One WARP per source: 32 entries are loaded at a time (coalesced) and their distances computed in
+// parallel; the per-bin maxima and counts and the grid-connection bits do not depend on the order (the float maximum of
+// the reference's running comparison equals the maximum of the rounded values: rounding is monotone), but the two moments
+// are double running sums whose rounding depends on the order of the additions, so lane 0 / lane 1 add the 32 distances /
+// squares of a round one after the other, in row order, exactly like the reference's loop.
+constexpr int NS_TPB = 256;
+__global__ void __launch_bounds__(NS_TPB) k_node_stats(GridDev g, int64_t src_begin, int64_t chunk_first, int64_t nsrc_chunk,
+                                                       const uint64_t *row_off, uint64_t chunk_base, const uint32_t *cnt,
+                                                       const uint32_t *e_ref, const uint8_t *e_bin, int32_t *connectivity,
+                                                       double *sum_d, double *sum_d2, float *far_dist, int32_t *bin_count,
+                                                       uint8_t *gridconn) {
+    __shared__ unsigned s_far[NS_TPB / 32][32];
+    __shared__ int s_bc[NS_TPB / 32][32];
+    __shared__ double s_d[NS_TPB / 32][32], s_d2[NS_TPB / 32][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int64_t i = ((int64_t)blockIdx.x * NS_TPB + threadIdx.x) >> 5;
+    if (i >= nsrc_chunk) return;  // whole warps leave
+    const int64_t sl = chunk_first + i;  // source index relative to src_begin
+    const int32_t ref = g.cellref[src_begin + sl];
+    const int cx = ref >> 16, cy = ref & 0xffff;
+    s_far[wid][lane] = 0u;  // bits of 0.0f
+    s_bc[wid][lane] = 0;
+    const uint64_t beg = row_off[sl] - chunk_base, end = row_off[sl + 1] - chunk_base;
     uint32_t nacc = 0;
     for (int k = 0; k < 8; k++) nacc += cnt[sl * 8 + k];
-    double td = 0.0, td2 = 0.0;
-    uint8_t gc = 0;
-    for (uint64_t e = beg; e < end; e++) {
-        uint32_t r = e_ref[e];
-        int b = e_bin[e] & 31;
-        int dx = (int)(r >> 16) - cx, dy = (int)(r & 0xffff) - cy;
-        if (e - beg < nacc) {
-            double fx = (double)dx, fy = (double)dy;
-            double d = mul(__dsqrt_rn(add(mul(fx, fx), mul(fy, fy))), g.spacing);
-            if (d > (double)far[b]) far[b] = (float)d;
-            td = add(td, d);
-            td2 = add(td2, mul(d, d));
-            bc[b]++;
+    double acc = 0.0;  // lane 0: sum of distances, lane 1: sum of squares
+    unsigned gc = 0u;
+    __syncwarp();
+    for (uint64_t e0 = beg; e0 < end; e0 += 32) {
+        const uint64_t e = e0 + lane;
+        double d = 0.0;
+        if (e < end) {
+            const uint32_t r = e_ref[e];
+            const int b = e_bin[e] & 31;
+            const int dx = (int)(r >> 16) - cx, dy = (int)(r & 0xffff) - cy;
+            if (e - beg < nacc) {  // accepted cells come first, the fill-ins of diagonal bins after them
+                const double fx = (double)dx, fy = (double)dy;
+                d = mul(__dsqrt_rn(add(mul(fx, fx), mul(fy, fy))), g.spacing);
+                atomicMax(&s_far[wid][b], __float_as_uint((float)d));  // non-negative floats order like their bits
+                atomicAdd(&s_bc[wid][b], 1);
+            }
+            if (dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1) {
+                // neighbour i of the 8-neighbourhood (E, NE, N, NW, W, SW, S, SE) is looked up in bin 4i
+                const int idx_of[9] = {5, 6, 7, 4, -1, 0, 3, 2, 1};  // [(dy+1)*3 + (dx+1)]
+                const int idx = idx_of[(dy + 1) * 3 + (dx + 1)];
+                if (idx >= 0 && b == idx * 4) gc |= 1u << idx;
+            }
         }
-        if (dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1) {
-            // neighbour i of the 8-neighbourhood (E, NE, N, NW, W, SW, S, SE) is looked up in bin 4i
-            const int idx_of[9] = {5, 6, 7, 4, -1, 0, 3, 2, 1};  // [(dy+1)*3 + (dx+1)]
-            int idx = idx_of[(dy + 1) * 3 + (dx + 1)];
-            if (idx >= 0 && b == idx * 4) gc |= (uint8_t)(1 << idx);
-        }
+        s_d[wid][lane] = d;
+        s_d2[wid][lane] = mul(d, d);
+        __syncwarp();
+        const uint64_t done = e0 - beg;
+        const int m = done >= nacc ? 0 : (int)min((uint64_t)32, (uint64_t)nacc - done);  // accepted entries of this round
+        if (lane == 0)
+            for (int l = 0; l < m; l++) acc = add(acc, s_d[wid][l]);
+        else if (lane == 1)
+            for (int l = 0; l < m; l++) acc = add(acc, s_d2[wid][l]);
+        __syncwarp();
     }
-    connectivity[sl] = (int32_t)nacc;
-    sum_d[sl] = td;
-    sum_d2[sl] = td2;
-    for (int b = 0; b < 32; b++) {
-        far_dist[sl * 32 + b] = far[b];
-        bin_count[sl * 32 + b] = bc[b];
+    gc = __reduce_or_sync(0xffffffffu, gc);
+    if (lane == 0) {
+        connectivity[sl] = (int32_t)nacc;
+        sum_d[sl] = acc;
+        gridconn[sl] = (uint8_t)gc;
+    } else if (lane == 1) {
+        sum_d2[sl] = acc;
     }
-    gridconn[sl] = gc;
+    far_dist[sl * 32 + lane] = __uint_as_float(s_far[wid][lane]);
+    bin_count[sl * 32 + lane] = s_bc[wid][lane];
 }
 
 // sort keys: col<<6 | accepted<<5 | bin.  col = ordinal of a filled cell; an unfilled cell c (ghost)
@@ -1430,7 +1449,7 @@ int build_graph(vga_ctx *ctx, const vga_dgrid *dg, int64_t src_begin, int64_t sr
             }
         }
         mt.stop();
-        k_node_stats<<<blocks_for(ns, 128), 128, 0, st>>>(g, src_begin, i, ns, row_off.p, base, cnt.p, e_ref.p, e_bin.p,
+        k_node_stats<<<blocks_for(ns * 32, NS_TPB), NS_TPB, 0, st>>>(g, src_begin, i, ns, row_off.p, base, cnt.p, e_ref.p, e_bin.p,
                                                          gr->connectivity.p, gr->sum_d.p, gr->sum_d2.p,
                                                          gr->far_dist.p, gr->bin_count.p, gr->gridconn.p);
         tm.launches++;
