@@ -1337,7 +1337,8 @@ int run_levels(vga_ctx *ctx, BfsDev &d, int64_t nb, int radius, int bfs_mode, De
         k_update<W><<<dim3((unsigned)ublocks, (unsigned)nb), TPB, 0, st>>>(d, counts ? counts->p + (size_t)(level + 1) * counts_stride : nullptr);
         // measured on a C5 slice of 16,384 sources with both list kinds (profiles/r2_pull_alpha_hybrid.log): level kernels
         // 75.9 / 69.1 / 70.0 / 82.6 ms for alpha 1 / 2 / 3 / 5 -- the in-lists shrink more than the out-lists and the down
-        // pass runs over two pyramids; x-major lists only: alpha 1 is best
+        // pass runs over two pyramids; x-major lists only: alpha 1 is best.  With k_push_delta: alpha 1 and the visits weighted
+        // (bfs_delta_weight, see k_decide)
         double lsum[NSTAT] = {};
         if (lt) {
             std::vector<u64> hs((size_t)nb * NSTAT);
